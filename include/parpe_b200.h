@@ -1,0 +1,256 @@
+/*
+ * parpe_b200.h -- C ABI of the B200-native objective/gradient hot path of parPE.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types,
+ * no exceptions, caller-allocated outputs.  The reference has no C plugin ABI for
+ * this path -- it sits behind the C++ classes parpe::SummedGradientFunction<int> /
+ * parpe::GradientFunction (include/parpecommon/functions.h:26-118) implemented by
+ * parpe::AmiciSummedGradientFunction (include/parpeamici/multiConditionProblem.h:
+ * 95-237).  Each entry point below names the reference interface it replaces;
+ * the header-only C++ adapter that forwards to these functions with the
+ * reference's own signatures is parpe_b200/include/parpe_b200/
+ * b200SummedGradientFunction.h, and INTEGRATION.md shows the binding a parPE
+ * maintainer would add.
+ *
+ * All floating point is IEEE double, all indices 32-bit int (as in the reference)
+ * except byte/element offsets, which are int64.
+ *
+ * Thread-compatibility: one handle must not be evaluated from two threads at
+ * once (same contract as the reference, whose evaluate() mutates the solver
+ * through const: src/parpeamici/multiConditionProblem.cpp:826-835).  Different
+ * handles may be used concurrently.
+ */
+#ifndef PARPE_B200_H
+#define PARPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_ABI_VERSION 1
+
+/* parpe::FunctionEvaluationStatus (include/parpecommon/functions.h:16-20) */
+#define PB200_EVAL_SUCCESS 0
+#define PB200_EVAL_FAILURE 1
+
+/* library-level error codes (negative; never returned by evaluate for a
+ * simulation failure -- those are reported the reference's way: fval=+inf and
+ * PB200_EVAL_FAILURE, src/parpeamici/multiConditionProblem.cpp:669-672) */
+#define PB200_ERR_ARG (-1)
+#define PB200_ERR_MODEL (-2)
+#define PB200_ERR_CUDA (-3)
+#define PB200_ERR_NO_DEVICE (-4)
+
+/* amici::ParameterScaling (deps/AMICI/include/amici/defines.h:118-122) */
+#define PB200_SCALE_NONE 0
+#define PB200_SCALE_LN 1
+#define PB200_SCALE_LOG10 2
+
+/* per-condition simulation status: amici return codes
+ * (deps/AMICI/include/amici/defines.h:60-91); 0 = AMICI_SUCCESS */
+#define PB200_SIM_SUCCESS 0
+#define PB200_SIM_TOO_MUCH_WORK (-1)
+#define PB200_SIM_TOO_MUCH_ACC (-2)
+#define PB200_SIM_ERR_FAILURE (-3)
+#define PB200_SIM_CONV_FAILURE (-4)
+#define PB200_SIM_LSETUP_FAIL (-6)
+#define PB200_SIM_RHSFUNC_FAIL (-8)
+#define PB200_SIM_FIRST_RHSFUNC_ERR (-9)
+#define PB200_SIM_REPTD_RHSFUNC_ERR (-10)
+#define PB200_SIM_UNREC_RHSFUNC_ERR (-11)
+#define PB200_SIM_ILL_INPUT (-22)
+#define PB200_SIM_TOO_CLOSE (-27)
+#define PB200_SIM_SRHSFUNC_FAIL (-41)
+#define PB200_SIM_REPTD_SRHSFUNC_ERR (-43)
+#define PB200_SIM_UNREC_SRHSFUNC_ERR (-44)
+#define PB200_SIM_ERROR (-99)      /* AMICI_ERROR: e.g. sigma <= 0 or non-finite */
+
+/* per-condition integrator counters returned by pb200_get_condition_results
+ * (same counters CVODES exposes; deps/AMICI/src/solver.cpp:342-368) */
+enum {
+    PB200_STAT_NST = 0,   /* accepted steps                     */
+    PB200_STAT_NFE,       /* RHS evaluations                    */
+    PB200_STAT_NSETUPS,   /* LU factorisations                  */
+    PB200_STAT_NJE,       /* Jacobian evaluations               */
+    PB200_STAT_NNI,       /* state Newton iterations            */
+    PB200_STAT_NNIS,      /* sensitivity Newton iterations      */
+    PB200_STAT_NFSE,      /* sensitivity RHS evaluations        */
+    PB200_STAT_NETF,      /* state error-test failures          */
+    PB200_STAT_NETFS,     /* sensitivity error-test failures    */
+    PB200_STAT_NCFN,      /* state corrector failures           */
+    PB200_STAT_NCFNS,     /* sensitivity corrector failures     */
+    PB200_STAT_NOR,       /* order reductions by STALD          */
+    PB200_STAT_TRIALS,    /* tolerance-relaxation trials used   */
+    PB200_STAT_QSUM,      /* sum over accepted steps of order q */
+    PB200_NSTATS = 16
+};
+
+/*
+ * Everything evaluate() needs that the reference reads from its data provider
+ * (parpe::MultiConditionDataProvider, include/parpeamici/
+ * multiConditionDataProvider.h:22-111; HDF5 layout doc/hdf5.md:1-172).  All
+ * tables are copied to the device at pb200_create; the caller may free them
+ * afterwards.
+ */
+typedef struct pb200_problem_desc {
+    int32_t abi_version;       /* PB200_ABI_VERSION */
+    const char* model_name;    /* generated model, see pb200_model_info */
+    int32_t n_conditions;      /* C: number of simulation conditions */
+    int32_t n_opt;             /* number of optimisation parameters */
+    int32_t np, nk, ny;        /* must equal the model's dimensions (checked) */
+    /* measurements, /measurements/{t,y,ysigma}/<c> of doc/hdf5.md:60-83 */
+    const int64_t* t_offsets;  /* [C+1] first output time of condition c in t[] */
+    const double* t;           /* [t_offsets[C]] output times (may repeat) */
+    const double* y;           /* [t_offsets[C]*ny] row-major obs + it*ny; NaN = no measurement */
+    const double* sigma;       /* same layout; NaN = use the model's sigma */
+    /* /fixedParameters/k column of the simulation condition, doc/hdf5.md:36-58 */
+    const double* k;           /* [C*nk] row-major per condition */
+    /* /parameters/optimizationSimulationMapping (transposed: per condition
+     * contiguous), -1 = not mapped (multiConditionDataProvider.cpp:84-102) */
+    const int32_t* mapping;    /* [C*np] */
+    const int32_t* pscale_sim; /* [C*np]  /parameters/pscaleSimulation */
+    const int32_t* pscale_opt; /* [n_opt] /parameters/pscaleOptimization */
+    const double* overrides;   /* [C*np] /parameters/parameterOverrides, or NULL */
+    /* /amiciOptions attributes (deps/AMICI/src/hdf5.cpp) */
+    double t0;
+    double atol, rtol;         /* also used for sensitivities (rtol_fsa/atol_fsa unset) */
+    int32_t maxsteps;          /* total internal steps per simulation (AMICI default 10000) */
+    int32_t stldet;            /* BDF stability-limit detection, AMICI default 1 */
+    int32_t sensi_errcon;      /* sensitivities in the error test; AMICI forces 1 (solver.cpp:646) */
+    /* runAndLogSimulation retry policy (multiConditionProblem.cpp:352-365) */
+    int32_t num_trials;        /* PARPE_NUM_SIMULATION_TRIALS, default 6 */
+    double relaxation_factor;  /* PARPE_INTEGRATION_TOLERANCE_RELAXATION_FACTOR, default 100 */
+    /* kernel mapping hint: lanes cooperating on one condition (0 = automatic) */
+    int32_t lanes_per_condition;
+    int32_t reserved[7];
+} pb200_problem_desc;
+
+typedef struct pb200_handle pb200_handle;
+
+/* library / model registry ------------------------------------------------ */
+int pb200_abi_version(void);
+/* number of CUDA devices visible; <= 0 if none (no CPU fallback exists) */
+int pb200_device_count(void);
+int pb200_model_count(void);
+/* name of model i, or NULL */
+const char* pb200_model_name(int i);
+/* dimensions of a generated model; returns 0 or PB200_ERR_MODEL */
+int pb200_model_info(const char* model_name, int* nx, int* np, int* nk, int* ny);
+/* last error message of the calling thread ("" if none) */
+const char* pb200_last_error(void);
+
+/* lifetime ---------------------------------------------------------------- */
+/*
+ * Replaces: construction of MultiConditionDataProviderHDF5 +
+ * AmiciSummedGradientFunction (multiConditionProblem.cpp:612-635).
+ * device: CUDA ordinal.  Returns 0 and *out, or a negative PB200_ERR_*.
+ */
+int pb200_create(const pb200_problem_desc* desc, int device, pb200_handle** out);
+void pb200_destroy(pb200_handle* h);
+
+/*
+ * Shard the data indices of every evaluation over `world` processes: this handle
+ * then simulates positions [floor(rank*n/world), floor((rank+1)*n/world)) of the
+ * index list only and returns PARTIAL sums (the caller all-reduces them).
+ * Replaces: LoadBalancerMaster's dynamic assignment of packages to MPI workers
+ * (src/parpeloadbalancer/loadBalancerMaster.cpp:104-134) by a static contiguous
+ * partition in index order (amiciSimulationRunner.cpp:49-80 chunk order).
+ */
+int pb200_set_partition(pb200_handle* h, int rank, int world);
+/* [lo,hi) of an n-long index list owned by (rank, world): the assignment rule */
+void pb200_partition_bounds(int n, int rank, int world, int* lo, int* hi);
+
+/* the hot path ------------------------------------------------------------ */
+/*
+ * Replaces: AmiciSummedGradientFunction::evaluate(parameters, datasets, fval,
+ * gradient, logger, cpuTime)  (multiConditionProblem.cpp:647-675).
+ *   theta[n_opt]   optimisation parameters (optimiser scale), host memory
+ *   idx[n_idx]     data (condition) indices, host memory; duplicates allowed
+ *   grad           NULL => cost only (reference: gradient.empty())
+ *   fval, grad     fully overwritten; grad has n_opt entries
+ *   seconds        nullable; device time of the evaluation
+ * Returns PB200_EVAL_SUCCESS / PB200_EVAL_FAILURE (then *fval = +inf), or a
+ * negative PB200_ERR_* for API misuse / CUDA errors.
+ */
+int pb200_evaluate(pb200_handle* h, const double* theta, int n_opt, const int* idx,
+                   int n_idx, double* fval, double* grad, double* seconds);
+
+/*
+ * Same computation with device-resident inputs and outputs, enqueued on
+ * `stream` (a cudaStream_t; NULL = default stream) without host
+ * synchronisation: d_out[0] = partial nllh, d_out[1] = number of failed
+ * conditions, d_out[2..2+n_opt) = partial gradient (zeros if !want_grad).
+ * Used for the multi-GPU path (NCCL all-reduce on d_out) and for
+ * device-timed throughput.  +inf / failure mapping is the caller's job.
+ */
+int pb200_evaluate_device(pb200_handle* h, const double* d_theta, const int* d_idx,
+                          int n_idx, int want_grad, double* d_out, void* stream);
+
+/*
+ * Per-condition results of the most recent evaluation on this handle, in
+ * index-list order restricted to this handle's partition (what the reference
+ * ships back per condition as AmiciResultPackageSimple,
+ * include/parpeamici/amiciSimulationRunner.h:157-182).  Any pointer may be NULL.
+ *   llh[n]  sllh[n*np] (plist-compacted, simulation scale)  status[n]
+ *   stats[n*PB200_NSTATS]
+ * Returns the number of conditions n, or negative on error.
+ */
+int pb200_get_condition_results(pb200_handle* h, double* llh, double* sllh,
+                                int* status, int64_t* stats);
+
+/*
+ * Replaces: AmiciSummedGradientFunction::getModelOutputsAndSigmas
+ * (multiConditionProblem.cpp:506-563): simulate ALL conditions without
+ * sensitivities; y_out / sigmay_out use the layout of desc->y.
+ * Returns PB200_EVAL_SUCCESS / PB200_EVAL_FAILURE.
+ */
+int pb200_get_model_outputs(pb200_handle* h, const double* theta, int n_opt,
+                            double* y_out, double* sigmay_out);
+
+/* hierarchical optimisation -------------------------------------------- */
+/*
+ * Analytic inner problem of parpe::HierarchicalOptimizationWrapper
+ * (src/parpeamici/hierarchicalOptimization.cpp:142-238,702-930,989-1134).
+ * The inner parameters are identified by their optimisation-parameter index;
+ * each comes with (condition, observable) pairs it applies to
+ * (AnalyticalParameterProvider, hierarchicalOptimizationAnalyticalParameterProvider.h).
+ */
+typedef struct pb200_hier_desc {
+    /* /scalingParameterIndices, /offsetParameterIndices, /sigmaParameterIndices
+     * (doc/hdf5.md:118-172): optimisation-parameter indices, ascending */
+    int32_t n_scaling, n_offset, n_sigma;
+    const int32_t* scaling_idx;     /* [n_scaling] */
+    const int32_t* offset_idx;      /* [n_offset] */
+    const int32_t* sigma_idx;       /* [n_sigma] */
+    /* /{scaling,offset,sigma}ParametersMapToObservables: rows of
+     * (inner parameter number, condition index, observable index), row-major
+     * int[n_rows*3], as read by AnalyticalParameterHdf5Reader::
+     * readParameterConditionObservableMappingFromFile
+     * (hierarchicalOptimizationAnalyticalParameterProvider.cpp) */
+    int32_t n_scaling_rows, n_offset_rows, n_sigma_rows;
+    const int32_t* scaling_map;
+    const int32_t* offset_map;
+    const int32_t* sigma_map;
+    int32_t reserved[8];
+} pb200_hier_desc;
+
+int pb200_hier_attach(pb200_handle* h, const pb200_hier_desc* hd);
+/* number of outer (numerically optimised) parameters = n_opt - n_inner */
+int pb200_hier_num_outer(pb200_handle* h);
+/*
+ * Replaces: HierarchicalOptimizationWrapper::evaluate (hierarchicalOptimization.cpp:
+ * 142-238).  theta_outer[n_outer] -> fval, grad_outer[n_outer] (NULL => cost only);
+ * full_parameters[n_opt] (nullable) receives the spliced vector incl. the optimal
+ * inner parameters.
+ */
+int pb200_hier_evaluate(pb200_handle* h, const double* theta_outer, int n_outer,
+                        double* fval, double* grad_outer, double* full_parameters,
+                        double* seconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARPE_B200_H */

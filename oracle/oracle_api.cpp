@@ -1,0 +1,194 @@
+// TEST INFRASTRUCTURE (oracle) -- not part of the product path.
+//
+// C API over the oracle (reference AMICI/CVODES + restated parPE glue) so that
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg can drive it
+// through ctypes with the same tables they hand to the CUDA library.
+#include <cstring>
+#include <map>
+#include <string>
+
+#include "../include/parpe_b200.h"
+#include "hierarchical.hpp"
+#include "parpe_glue.hpp"
+
+#include "models/model_boehm.h"
+#include "models/model_fujita.h"
+#include "models/model_steadystate.h"
+#include "models/model_steadystate_scaled.h"
+
+#ifdef PB200_ORACLE_WITH_VENDORED
+// the reference's own pre-generated model (deps/AMICI/models/model_steadystate),
+// compiled in place by the Makefile: cross-checks our generator
+#include "model_steadystate.h"
+#endif
+
+using namespace pb200_oracle;
+
+namespace {
+std::unique_ptr<amici::Model> makeModel(const std::string& name) {
+    using namespace pb200_oracle_models;
+    if (name == "steadystate") return create_steadystate();
+    if (name == "steadystate_scaled") return create_steadystate_scaled();
+    if (name == "boehm") return create_boehm();
+    if (name == "fujita") return create_fujita();
+#ifdef PB200_ORACLE_WITH_VENDORED
+    if (name == "steadystate_vendored")
+        return std::make_unique<amici::model_model_steadystate::Model_model_steadystate>();
+#endif
+    return nullptr;
+}
+thread_local std::string g_err;
+}  // namespace
+
+struct ora_problem {
+    std::unique_ptr<Problem> p;
+    std::unique_ptr<HierarchicalSpec> hier;
+};
+
+extern "C" {
+
+const char* ora_last_error() { return g_err.c_str(); }
+
+int ora_has_model(const char* name) { return makeModel(name) ? 1 : 0; }
+
+// ism: 1 simultaneous / 2 staggered; linsol: 1 dense / 9 KLU
+ora_problem* ora_create(const pb200_problem_desc* d, int ism, int linsol) {
+    try {
+        auto model = makeModel(d->model_name);
+        if (!model) {
+            g_err = std::string("unknown model ") + d->model_name;
+            return nullptr;
+        }
+        Tables t;
+        t.n_conditions = d->n_conditions;
+        t.n_opt = d->n_opt;
+        t.np = d->np;
+        t.nk = d->nk;
+        t.ny = d->ny;
+        const int C = d->n_conditions;
+        t.t_offsets.assign(d->t_offsets, d->t_offsets + C + 1);
+        int64_t nt_total = t.t_offsets[C];
+        t.t.assign(d->t, d->t + nt_total);
+        t.y.assign(d->y, d->y + nt_total * d->ny);
+        t.sigma.assign(d->sigma, d->sigma + nt_total * d->ny);
+        t.k.assign(d->k, d->k + (size_t)C * d->nk);
+        t.mapping.assign(d->mapping, d->mapping + (size_t)C * d->np);
+        t.pscale_sim.assign(d->pscale_sim, d->pscale_sim + (size_t)C * d->np);
+        t.pscale_opt.assign(d->pscale_opt, d->pscale_opt + d->n_opt);
+        if (d->overrides)
+            t.overrides.assign(d->overrides, d->overrides + (size_t)C * d->np);
+        t.t0 = d->t0;
+        t.atol = d->atol;
+        t.rtol = d->rtol;
+        t.maxsteps = d->maxsteps;
+        t.stldet = d->stldet;
+        t.num_trials = d->num_trials;
+        t.relaxation_factor = d->relaxation_factor;
+        t.ism = ism;
+        t.linsol = linsol;
+        model->setT0(d->t0);
+        auto* h = new ora_problem;
+        h->p = std::make_unique<Problem>(std::move(model), std::move(t));
+        return h;
+    } catch (std::exception const& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+void ora_destroy(ora_problem* h) { delete h; }
+
+// returns 0/1 (FunctionEvaluationStatus) or -1 on exception
+int ora_evaluate(ora_problem* h, const double* theta, const int* idx, int n_idx, double* fval,
+                 double* grad, int nthreads, int collect_stats, double* llh_c, double* sllh_c,
+                 int* status_c, int64_t* stats_c, double* seconds_c) {
+    try {
+        std::vector<int> vidx(idx, idx + n_idx);
+        std::vector<ConditionResult> res;
+        int rc = h->p->evaluate(theta, vidx, *fval, grad, nthreads, &res, collect_stats != 0);
+        const int np = h->p->tables().np;
+        for (int r = 0; r < n_idx; ++r) {
+            if (llh_c) llh_c[r] = res[r].llh;
+            if (status_c) status_c[r] = res[r].status;
+            if (seconds_c) seconds_c[r] = res[r].seconds;
+            if (sllh_c) {
+                for (int j = 0; j < np; ++j)
+                    sllh_c[(size_t)r * np + j] = j < (int)res[r].gradient.size() ? res[r].gradient[j] : 0.0;
+            }
+            if (stats_c) {
+                int64_t* s = stats_c + (size_t)r * PB200_NSTATS;
+                for (int j = 0; j < PB200_NSTATS; ++j) s[j] = -1;
+                s[PB200_STAT_NST] = res[r].nst;
+                s[PB200_STAT_NFE] = res[r].nfe;
+                s[PB200_STAT_NETF] = res[r].netf;
+                s[PB200_STAT_NCFN] = res[r].ncfn;
+                s[PB200_STAT_TRIALS] = res[r].trials;
+            }
+        }
+        return rc;
+    } catch (std::exception const& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// y_out / sigmay_out in the layout of desc->y
+int ora_get_model_outputs(ora_problem* h, const double* theta, double* y_out, double* sigmay_out,
+                          int nthreads) {
+    try {
+        std::vector<std::vector<double>> y, s;
+        int rc = h->p->getModelOutputsAndSigmas(theta, y, s, nthreads);
+        auto const& tab = h->p->tables();
+        for (int c = 0; c < tab.n_conditions; ++c) {
+            size_t off = (size_t)tab.t_offsets[c] * tab.ny;
+            size_t n = (size_t)(tab.t_offsets[c + 1] - tab.t_offsets[c]) * tab.ny;
+            for (size_t i = 0; i < n; ++i) {
+                y_out[off + i] = i < y[c].size() ? y[c][i] : NAN;
+                sigmay_out[off + i] = i < s[c].size() ? s[c][i] : NAN;
+            }
+        }
+        return rc;
+    } catch (std::exception const& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// A5 helpers exposed for the bit-exact indexing tests
+void ora_map_parameters(ora_problem* h, int c, const double* theta, double* p_sim) {
+    std::vector<double> p;
+    h->p->mapAndSetOptimizationToSimulationVariables(c, theta, p);
+    std::memcpy(p_sim, p.data(), p.size() * sizeof(double));
+}
+int ora_plist(ora_problem* h, int c, int* plist) {
+    auto pl = h->p->plistFor(h->p->mappingFor(c));
+    std::memcpy(plist, pl.data(), pl.size() * sizeof(int));
+    return (int)pl.size();
+}
+double ora_get_unscaled(double v, int scale) { return getUnscaledParameter(v, scale); }
+double ora_get_scaled(double v, int scale) { return getScaledParameter(v, scale); }
+double ora_apply_chain_rule(double g, double p, int oldScale, int newScale) {
+    return applyChainRule(g, p, oldScale, newScale);
+}
+
+// ---- hierarchical (A15) --------------------------------------------------
+int ora_hier_attach(ora_problem* h, const pb200_hier_desc* hd) {
+    try {
+        h->hier = std::make_unique<HierarchicalSpec>(HierarchicalSpec::fromDesc(*hd, h->p->tables()));
+        return 0;
+    } catch (std::exception const& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+int ora_hier_num_outer(ora_problem* h) { return h->hier ? h->hier->numOuter() : -1; }
+int ora_hier_evaluate(ora_problem* h, const double* theta_outer, double* fval, double* grad_outer,
+                      double* full_parameters, int nthreads) {
+    try {
+        return hierarchicalEvaluate(*h->p, *h->hier, theta_outer, *fval, grad_outer, full_parameters, nthreads);
+    } catch (std::exception const& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+}  // extern "C"
