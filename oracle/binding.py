@@ -40,6 +40,7 @@ def lib():
         L.ora_evaluate.argtypes = [C.c_void_p, dp, ip, C.c_int, dp, dp, C.c_int, C.c_int, dp, dp, ip,
                                    C.POINTER(C.c_int64), dp]
         L.ora_get_model_outputs.argtypes = [C.c_void_p, dp, dp, dp, C.c_int]
+        L.ora_debug_numsteps.argtypes = [C.c_void_p, dp, C.c_int, C.c_int, ip, ip]
         L.ora_map_parameters.argtypes = [C.c_void_p, C.c_int, dp, dp]
         L.ora_plist.argtypes = [C.c_void_p, C.c_int, ip]
         for f in (L.ora_get_unscaled, L.ora_get_scaled):
@@ -110,6 +111,14 @@ class OracleProblem:
         if rc < 0:
             raise RuntimeError(lib().ora_last_error().decode())
         return rc, y, s
+
+    def debug_numsteps(self, theta, c=0, want_grad=True):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        n = self.tables.nt(c)
+        ns, od = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        r = lib().ora_debug_numsteps(self._h, _dp(theta), c, int(want_grad), ns.ctypes.data_as(C.POINTER(C.c_int)),
+                                     od.ctypes.data_as(C.POINTER(C.c_int)))
+        return ns[:max(r, 0)], od[:max(r, 0)]
 
     def map_parameters(self, c, theta):
         theta = np.ascontiguousarray(theta, dtype=np.float64)

@@ -154,6 +154,25 @@ int ora_get_model_outputs(ora_problem* h, const double* theta, double* y_out, do
     }
 }
 
+// debugging aid: cumulative step count and order at every output time of condition c
+int ora_debug_numsteps(ora_problem* h, const double* theta, int c, int want_grad, int* numsteps, int* order) {
+    try {
+        std::vector<int> vidx{c};
+        std::vector<ConditionResult> res;
+        double fval;
+        std::vector<double> grad(h->p->tables().n_opt);
+        h->p->evaluate(theta, vidx, fval, want_grad ? grad.data() : nullptr, 1, &res, true);
+        for (size_t i = 0; i < res[0].numsteps.size(); ++i) {
+            numsteps[i] = res[0].numsteps[i];
+            order[i] = res[0].order[i];
+        }
+        return (int)res[0].numsteps.size();
+    } catch (std::exception const& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
 // A5 helpers exposed for the bit-exact indexing tests
 void ora_map_parameters(ora_problem* h, int c, const double* theta, double* p_sim) {
     std::vector<double> p;

@@ -171,6 +171,8 @@ ConditionResult Problem::runAndLogSimulation(amici::Model& model, int c, bool se
             r.nfe = rdata->numrhsevals.back();
             r.netf = rdata->numerrtestfails.back();
             r.ncfn = rdata->numnonlinsolvconvfails.back();
+            r.numsteps = rdata->numsteps;
+            r.order = rdata->order;
         }
         return r;
     }

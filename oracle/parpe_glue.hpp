@@ -54,6 +54,7 @@ struct ConditionResult {  // AmiciResultPackageSimple, amiciSimulationRunner.h:1
     int status = 0;
     int trials = 0;
     long nst = -1, nfe = -1, nsetups = -1, nni = -1, netf = -1, ncfn = -1;
+    std::vector<int> numsteps, order;  // per output time (full reporting only)
 };
 
 class Problem {

@@ -228,47 +228,47 @@ def emit_device_header(d: Derived, path: str) -> None:
       (fl["xdot"], fl["J"], fl["dxdotdp"], fl["nnz_dxdotdp"]))
     sig = "const double t, const double* __restrict__ x, const double* __restrict__ p, const double* __restrict__ k"
 
-    A("    PB_HD static inline void x0(double* __restrict__ x0, const double t, const double* __restrict__ p, const double* __restrict__ k) {")
+    A("    PB_HD static void x0(double* __restrict__ x0, const double t, const double* __restrict__ p, const double* __restrict__ k) {")
     A("        (void)t; (void)p; (void)k;")
     L.extend(_cse_block(pr, ["x0[%d]" % i for i in range(s.nx)], list(s.x0), "        "))
     A("    }")
     A("    // d x0 / d p[ip]; caller zero-fills sx0")
-    A("    PB_HD static inline void sx0(double* __restrict__ sx0, const double t, const double* __restrict__ p, const double* __restrict__ k, const int ip) {")
+    A("    PB_HD static void sx0(double* __restrict__ sx0, const double t, const double* __restrict__ p, const double* __restrict__ k, const int ip) {")
     A("        (void)t; (void)p; (void)k; (void)sx0;")
     L.extend(_switch_ip(pr, s.nx, d.sx0, "sx0", "        "))
     A("    }")
-    A("    PB_HD static inline void xdot(double* __restrict__ xdot, %s) {" % sig)
+    A("    PB_HD static void xdot(double* __restrict__ xdot, %s) {" % sig)
     A("        (void)t; (void)p; (void)k;")
     L.extend(_cse_block(pr, ["xdot[%d]" % i for i in range(s.nx)], list(s.xdot), "        "))
     A("    }")
     A("    // dense column-major Jacobian J[r + c*NX]; caller zero-fills J")
-    A("    PB_HD static inline void jac(double* __restrict__ J, %s) {" % sig)
+    A("    PB_HD static void jac(double* __restrict__ J, %s) {" % sig)
     A("        (void)t; (void)p; (void)k;")
     L.extend(_nonzero_assign(pr, "J[%d]", [(r + c * s.nx, d.J[r, c]) for c in range(s.nx) for r in range(s.nx)], "        "))
     A("    }")
     A("    // column ip of d xdot / d p; caller zero-fills out")
-    A("    PB_HD static inline void dxdotdp(double* __restrict__ out, %s, const int ip) {" % sig)
+    A("    PB_HD static void dxdotdp(double* __restrict__ out, %s, const int ip) {" % sig)
     A("        (void)t; (void)p; (void)k; (void)x; (void)out;")
     L.extend(_switch_ip(pr, s.nx, d.dxdotdp, "out", "        "))
     A("    }")
-    A("    PB_HD static inline void y(double* __restrict__ y, %s) {" % sig)
+    A("    PB_HD static void y(double* __restrict__ y, %s) {" % sig)
     A("        (void)t; (void)p; (void)k; (void)x;")
     L.extend(_cse_block(pr, ["y[%d]" % i for i in range(s.ny)], list(s.observables), "        "))
     A("    }")
     A("    // dydx[iy + ix*NY] column-major; caller zero-fills")
-    A("    PB_HD static inline void dydx(double* __restrict__ dydx, %s) {" % sig)
+    A("    PB_HD static void dydx(double* __restrict__ dydx, %s) {" % sig)
     A("        (void)t; (void)p; (void)k; (void)x;")
     L.extend(_nonzero_assign(pr, "dydx[%d]", [(r + c * s.ny, d.dydx[r, c]) for c in range(s.nx) for r in range(s.ny)], "        "))
     A("    }")
-    A("    PB_HD static inline void dydp(double* __restrict__ out, %s, const int ip) {" % sig)
+    A("    PB_HD static void dydp(double* __restrict__ out, %s, const int ip) {" % sig)
     A("        (void)t; (void)p; (void)k; (void)x; (void)out;")
     L.extend(_switch_ip(pr, s.ny, d.dydp, "out", "        "))
     A("    }")
-    A("    PB_HD static inline void sigmay(double* __restrict__ sigmay, const double t, const double* __restrict__ p, const double* __restrict__ k) {")
+    A("    PB_HD static void sigmay(double* __restrict__ sigmay, const double t, const double* __restrict__ p, const double* __restrict__ k) {")
     A("        (void)t; (void)p; (void)k;")
     L.extend(_cse_block(pr, ["sigmay[%d]" % i for i in range(s.ny)], list(s.sigmay), "        "))
     A("    }")
-    A("    PB_HD static inline void dsigmaydp(double* __restrict__ out, const double t, const double* __restrict__ p, const double* __restrict__ k, const int ip) {")
+    A("    PB_HD static void dsigmaydp(double* __restrict__ out, const double t, const double* __restrict__ p, const double* __restrict__ k, const int ip) {")
     A("        (void)t; (void)p; (void)k; (void)out;")
     L.extend(_switch_ip(pr, s.ny, d.dsigmaydp, "out", "        "))
     A("    }")

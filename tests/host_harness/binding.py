@@ -1,0 +1,50 @@
+"""TEST INFRASTRUCTURE -- ctypes binding of the host build of the integrator core."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "libhost_sim.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "host_sim.cpp")
+    deps = [src, os.path.join(_HERE, "..", "..", "parpe_b200", "csrc", "bdf_core.cuh")]
+    mdir = os.path.join(_HERE, "..", "..", "parpe_b200", "csrc", "models")
+    deps += [os.path.join(mdir, f) for f in os.listdir(mdir)]
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", LIB, src])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        L.hs_simulate.argtypes = [C.c_char_p, dp, dp, ip, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double,
+                                  C.c_double, C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int64), dp, dp, ip]
+        _lib = L
+    return _lib
+
+
+def simulate(model, p_unscaled, k, plist, t, my, sd, t0=0.0, rtol=1e-8, atol=1e-12, maxsteps=10000, stldet=1,
+             errconS=1, want_outputs=False):
+    d = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    p_unscaled, k, t, my, sd = d(p_unscaled), d(k), d(t), d(my).reshape(-1), d(sd).reshape(-1)
+    plist = np.ascontiguousarray(plist, dtype=np.int32)
+    ns = len(plist)
+    llh = C.c_double()
+    sllh = np.zeros(max(ns, 1))
+    stats = np.zeros(16, dtype=np.int64)
+    y = np.zeros(my.size) if want_outputs else None
+    s = np.zeros(my.size) if want_outputs else None
+    trace = np.zeros(2 * len(t), dtype=np.int32)
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+    st = lib().hs_simulate(model.encode(), P(p_unscaled), P(k), plist.ctypes.data_as(C.POINTER(C.c_int)), ns, len(t),
+                           P(t), P(my), P(sd), t0, rtol, atol, maxsteps, stldet, errconS, C.byref(llh), P(sllh),
+                           stats.ctypes.data_as(C.POINTER(C.c_int64)), P(y), P(s), trace.ctypes.data_as(C.POINTER(C.c_int)))
+    return dict(numsteps=trace[0::2], order=trace[1::2], status=st, llh=llh.value, sllh=sllh[:ns], stats=stats, y=y, sigmay=s)

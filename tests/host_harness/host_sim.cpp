@@ -1,0 +1,56 @@
+// TEST INFRASTRUCTURE -- host instantiation of the device integrator core.
+//
+// Compiles parpe_b200/csrc/bdf_core.cuh and the generated model functions as plain
+// C++ with the SingleLane group, so the algorithm that runs on the GPU can be
+// stepped on the CPU and diffed against the CVODES oracle (tests/test_host_core.py).
+// It is never linked into, or called by, the product library (libparpe_b200.so).
+#define PB200_HOST_TRACE 1
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#include "../../parpe_b200/csrc/bdf_core.cuh"
+#include "../../parpe_b200/csrc/models/boehm.cuh"
+#include "../../parpe_b200/csrc/models/fujita.cuh"
+#include "../../parpe_b200/csrc/models/steadystate.cuh"
+#include "../../parpe_b200/csrc/models/steadystate_scaled.cuh"
+
+using namespace pb200;
+
+template <class M>
+static int run(const double* p_unscaled, const double* k, const int* plist, int ns, int nt, const double* t,
+               const double* my, const double* sd, double t0, double rtol, double atol, int maxsteps, int stldet,
+               int errconS, double* llh, double* sllh, int64_t* stats, double* y_out, double* sigmay_out, int* trace) {
+    constexpr int CPL = M::NP + 1;
+    static thread_local GroupShared<M> sh;
+    static thread_local Bdf<M, SingleLane, CPL> bdf;
+    bdf.sh = &sh;
+    for (int i = 0; i < M::NP; ++i) sh.p[i] = p_unscaled[i];
+    for (int i = 0; i < M::NK; ++i) sh.k[i] = k[i];
+    for (int i = 0; i < ns; ++i) sh.plist[i] = plist[i];
+    bdf.opt.t0 = t0;
+    bdf.opt.maxsteps = maxsteps;
+    bdf.opt.stldet = stldet;
+    bdf.opt.errconS = errconS;
+    ConditionIO io{nt, t, my, sd, ns, y_out, sigmay_out, trace};
+    double s[CPL];
+    int status = bdf.simulate(io, rtol, atol, *llh, s);
+    for (int j = 0; j < ns; ++j) sllh[j] = s[j + 1];
+    bdf.export_stats(stats, 1);
+    return status;
+}
+
+extern "C" int hs_simulate(const char* model, const double* p_unscaled, const double* k, const int* plist, int ns,
+                           int nt, const double* t, const double* my, const double* sd, double t0, double rtol,
+                           double atol, int maxsteps, int stldet, int errconS, double* llh, double* sllh,
+                           int64_t* stats, double* y_out, double* sigmay_out, int* trace) {
+#define DISPATCH(NAME)                                                                                      \
+    if (!std::strcmp(model, #NAME))                                                                         \
+        return run<models::Model_##NAME>(p_unscaled, k, plist, ns, nt, t, my, sd, t0, rtol, atol, maxsteps, \
+                                         stldet, errconS, llh, sllh, stats, y_out, sigmay_out, trace);
+    DISPATCH(steadystate)
+    DISPATCH(steadystate_scaled)
+    DISPATCH(boehm)
+    DISPATCH(fujita)
+    return -12345;
+}
