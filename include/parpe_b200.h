@@ -179,15 +179,20 @@ int pb200_evaluate(pb200_handle* h, const double* theta, int n_opt, const int* i
                    int n_idx, double* fval, double* grad, double* seconds);
 
 /*
- * Same computation with device-resident inputs and outputs, enqueued on
- * `stream` (a cudaStream_t; NULL = default stream) without host
- * synchronisation: d_out[0] = partial nllh, d_out[1] = number of failed
- * conditions, d_out[2..2+n_opt) = partial gradient (zeros if !want_grad).
- * Used for the multi-GPU path (NCCL all-reduce on d_out) and for
- * device-timed throughput.  +inf / failure mapping is the caller's job.
+ * Same computation, enqueued on `stream` (a cudaStream_t; NULL = default stream)
+ * without host synchronisation, results left on the device:
+ * d_out[0] = partial nllh, d_out[1] = number of failed conditions,
+ * d_out[2..2+n_opt) = partial gradient (zeros if !want_grad).  theta and idx are
+ * host pointers (the optimiser lives on the host; they are staged through pinned
+ * memory).  Used for the multi-GPU path (NCCL all-reduce on d_out) and for
+ * device-timed throughput.  The +inf / failure mapping is the caller's job.
  */
-int pb200_evaluate_device(pb200_handle* h, const double* d_theta, const int* d_idx,
+int pb200_evaluate_device(pb200_handle* h, const double* theta, int n_opt, const int* idx,
                           int n_idx, int want_grad, double* d_out, void* stream);
+
+/* launch geometry and device time of the most recent simulate+reduce launch pair */
+int pb200_last_launch(pb200_handle* h, int* lanes_per_condition, int* grid, int* block,
+                      double* seconds);
 
 /*
  * Per-condition results of the most recent evaluation on this handle, in

@@ -1,0 +1,69 @@
+"""Build the CUDA library in-tree: ``parpe_b200/csrc/libparpe_b200.so`` for sm_100a.
+
+``nvcc`` cross-compiles here without a GPU; the built ``.so`` is git-ignored but travels
+to the GPU box with the repository snapshot.
+"""
+from __future__ import annotations
+
+import concurrent.futures
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "build")
+LIB = os.path.join(CSRC, "libparpe_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
+         "-ccbin", "/usr/bin/g++"]
+
+
+def _sources():
+    return [os.path.join(CSRC, "parpe_b200.cu")] + sorted(glob.glob(os.path.join(CSRC, "models", "inst_*.cu")))
+
+
+def _deps():
+    return (glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) +
+            glob.glob(os.path.join(CSRC, "models", "*.cuh")) +
+            [os.path.join(HERE, "..", "include", "parpe_b200.h")])
+
+
+def _compile(src, obj, log):
+    cmd = [NVCC] + ARCH + FLAGS + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(log, "w") as fh:
+        fh.write(" ".join(cmd) + "\n" + r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stdout[-4000:]))
+    return obj
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = _sources()
+    newest_dep = max(os.path.getmtime(p) for p in _deps())
+    jobs = []
+    for s in srcs:
+        o = os.path.join(OBJ, os.path.basename(s)[:-3] + ".o")
+        stale = force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), newest_dep)
+        jobs.append((s, o, stale))
+    todo = [(s, o) for s, o, st in jobs if st]
+    if todo:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(todo))) as ex:
+            futs = [ex.submit(_compile, s, o, o[:-2] + ".log") for s, o in todo]
+            for f in futs:
+                f.result()
+                if verbose:
+                    print("compiled", f.result())
+    objs = [o for _, o, _ in jobs]
+    if todo or not os.path.exists(LIB):
+        cmd = [NVCC] + ARCH + ["-shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,102 @@
+"""ctypes binding of the C ABI (``include/parpe_b200.h``) -- the library is
+``parpe_b200/csrc/libparpe_b200.so`` (CUDA, sm_100a).  There is no CPU fallback: if the
+library or a CUDA device is missing, the compute entry points raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .tables import PB200_NSTATS, HierDesc, ProblemDesc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libparpe_b200.so")
+
+EXPORTED_SYMBOLS = [
+    "pb200_abi_version", "pb200_device_count", "pb200_model_count", "pb200_model_name", "pb200_model_info",
+    "pb200_last_error", "pb200_create", "pb200_destroy", "pb200_set_partition", "pb200_partition_bounds",
+    "pb200_evaluate", "pb200_evaluate_device", "pb200_last_launch", "pb200_get_condition_results",
+    "pb200_get_model_outputs", "pb200_hier_attach", "pb200_hier_num_outer", "pb200_hier_evaluate",
+]
+
+_lib = None
+
+
+class B200LibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library (fails loudly if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200LibraryError(
+            "CUDA extension missing: %s (run `python -m parpe_b200.build`); there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.pb200_abi_version.restype = C.c_int
+    L.pb200_device_count.restype = C.c_int
+    L.pb200_model_count.restype = C.c_int
+    L.pb200_model_name.restype = C.c_char_p
+    L.pb200_model_name.argtypes = [C.c_int]
+    L.pb200_model_info.argtypes = [C.c_char_p, ip, ip, ip, ip]
+    L.pb200_last_error.restype = C.c_char_p
+    L.pb200_create.argtypes = [C.POINTER(ProblemDesc), C.c_int, C.POINTER(C.c_void_p)]
+    L.pb200_destroy.argtypes = [C.c_void_p]
+    L.pb200_destroy.restype = None
+    L.pb200_set_partition.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.pb200_partition_bounds.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip]
+    L.pb200_partition_bounds.restype = None
+    L.pb200_evaluate.argtypes = [C.c_void_p, dp, C.c_int, ip, C.c_int, dp, dp, dp]
+    L.pb200_evaluate_device.argtypes = [C.c_void_p, dp, C.c_int, ip, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.pb200_last_launch.argtypes = [C.c_void_p, ip, ip, ip, dp]
+    L.pb200_get_condition_results.argtypes = [C.c_void_p, dp, dp, ip, C.POINTER(C.c_int64)]
+    L.pb200_get_model_outputs.argtypes = [C.c_void_p, dp, C.c_int, dp, dp]
+    L.pb200_hier_attach.argtypes = [C.c_void_p, C.POINTER(HierDesc)]
+    L.pb200_hier_num_outer.argtypes = [C.c_void_p]
+    L.pb200_hier_evaluate.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp, dp]
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return lib().pb200_last_error().decode()
+
+
+def check(rc: int, what: str) -> int:
+    if rc < 0:
+        raise B200LibraryError("%s failed (%d): %s" % (what, rc, last_error()))
+    return rc
+
+
+def device_count() -> int:
+    return lib().pb200_device_count()
+
+
+def models():
+    L = lib()
+    out = {}
+    for i in range(L.pb200_model_count()):
+        name = L.pb200_model_name(i)
+        nx, np_, nk, ny = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        L.pb200_model_info(name, C.byref(nx), C.byref(np_), C.byref(nk), C.byref(ny))
+        out[name.decode()] = dict(nx=nx.value, np=np_.value, nk=nk.value, ny=ny.value)
+    return out
+
+
+def partition_bounds(n: int, rank: int, world: int):
+    lo, hi = C.c_int(), C.c_int()
+    lib().pb200_partition_bounds(n, rank, world, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None

@@ -378,4 +378,9 @@ def generate(spec: ModelSpec, repo_root: str) -> Derived:
     d = derive(spec)
     emit_device_header(d, os.path.join(repo_root, "parpe_b200", "csrc", "models", spec.name + ".cuh"))
     emit_amici_model(d, os.path.join(repo_root, "oracle", "models"))
+    inst = os.path.join(repo_root, "parpe_b200", "csrc", "models", "inst_%s.cu" % spec.name)
+    with open(inst, "w") as fh:
+        fh.write("// GENERATED by parpe_b200/codegen/modelgen.py -- kernel instantiations for model %s.\n"
+                 "#include \"../kernels.cuh\"\n#include \"%s.cuh\"\nPB200_REGISTER_MODEL(Model_%s)\n"
+                 % (spec.name, spec.name, spec.name))
     return d

@@ -1,0 +1,297 @@
+// kernels.cuh -- the CUDA kernels of the hot path and the per-model launch table.
+//
+//   simulate_kernel<M,G,CPL>  persistent, one lane group per condition, dynamic
+//                             work queue (replaces AmiciSimulationRunner +
+//                             LoadBalancerMaster/Worker + messageHandler +
+//                             runAndLogSimulation for one GPU: SURVEY.md rows
+//                             A2-A4, A8-A14)
+//   reduce_kernel             fixed-order reduction of the per-condition results
+//                             into (nllh, #errors, gradient) -- aggregateLikelihood
+//                             (row A6)
+#ifndef PB200_KERNELS_CUH
+#define PB200_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "bdf_core.cuh"
+
+namespace pb200 {
+
+/// Device-resident problem tables + per-evaluation buffers handed to the kernels.
+struct KernelArgs {
+    // --- resident tables (uploaded once at pb200_create) ---
+    int n_conditions, n_opt, np, nk, ny;
+    const int64_t* t_offsets;      // [C+1]
+    const double* t;               // [sum nt]
+    const double* my;              // [sum nt * ny]
+    const double* sd;              // [sum nt * ny]
+    const double* k;               // [C*nk]
+    const int* mapping;            // [C*np]
+    const int* pscale_sim;         // [C*np]
+    const int* pscale_opt;         // [n_opt]
+    const double* ov_scaled;       // [C*np] parameter overrides (simulation scale) or null
+    const double* ov_unscaled;     // [C*np] same, unscaled on the host at create time
+    const int* plist;              // [C*np] sensitivity parameter list per condition
+    const int* nplist;             // [C]
+    // --- per evaluation ---
+    const double* theta_tab;       // [n_opt*3*2]: for optimisation parameter j and simulation
+                                   // scale s: (value in simulation scale, unscaled value)
+    const int* idx;                // [n] condition index of every position of this partition
+    const int* order;              // [n] processing order of positions (cost-descending) or null
+    int n;                         // positions in this partition
+    int want_grad;
+    int* counter;                  // work-queue head
+    // --- per-position outputs ---
+    double* llh;                   // [n]
+    double* sllh;                  // [n*np] plist-compacted, simulation scale (A7 result package)
+    double* gcontrib;              // [n*np] -chain-ruled gradient contribution per model parameter
+    int* status;                   // [n]
+    int64_t* stats;                // [n*NSTATS]
+    double* y_out;                 // layout of my[] (by condition) or null
+    double* sigmay_out;
+    // --- options ---
+    SolverOptions opt;
+    int num_trials;
+    double relaxation_factor;
+};
+
+constexpr double PB_LN10 = 2.302585092994046;
+
+/// Where a group's uniform state lives: shared memory for multi-lane groups; for a
+/// one-lane group it is private to the thread (a __shared__ array of THREADS copies would
+/// exceed the static shared-memory limit).
+template <class M, int G, int THREADS>
+__device__ __forceinline__ GroupShared<M>* group_storage_shared() {
+    __shared__ GroupShared<M> shm[THREADS / G];
+    return &shm[threadIdx.x / G];
+}
+
+template <class M, int G, int CPL, int THREADS>
+__global__ void __launch_bounds__(THREADS) simulate_kernel(const KernelArgs a) {
+    LaneGroup<G> grp;
+    typename std::conditional<G == 1, GroupShared<M>, char>::type priv_storage_;
+    GroupShared<M>* sh;
+    if constexpr (G == 1) sh = &priv_storage_;
+    else sh = group_storage_shared<M, G, THREADS>();
+    Bdf<M, LaneGroup<G>, CPL> bdf;
+    bdf.sh = sh;
+    bdf.opt = a.opt;
+    const int lane = grp.lane();
+
+    for (;;) {
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(a.counter, 1);
+        pos = grp.bcast0(pos);
+        if (pos >= a.n) break;
+        const int r = a.order ? a.order[pos] : pos;
+        const int c = a.idx[r];
+        const size_t cp = (size_t)c * M::NP;
+
+        // ---- A5: optimisation -> simulation parameters (integer gather; the values come
+        //      from the host-computed table so they are bit-identical to the reference's
+        //      getScaledParameter(getUnscaledParameter(.)) chain) ----
+        grp.sync();
+        for (int i = lane; i < M::NP; i += G) {
+            const int j = a.mapping[cp + i];
+            double pu;
+            if (j >= 0) pu = a.theta_tab[((size_t)j * 3 + a.pscale_sim[cp + i]) * 2 + 1];
+            else if (a.ov_unscaled) pu = a.ov_unscaled[cp + i];
+            else pu = NAN;
+            sh->p[i] = pu;
+            sh->plist[i] = a.plist[cp + i];
+        }
+        for (int i = lane; i < M::NK; i += G) sh->k[i] = a.k[(size_t)c * M::NK + i];
+        grp.sync();
+
+        ConditionIO io;
+        const int64_t t0off = a.t_offsets[c];
+        io.nt = (int)(a.t_offsets[c + 1] - t0off);
+        io.t = a.t + t0off;
+        io.my = a.my + t0off * M::NY;
+        io.sd = a.sd + t0off * M::NY;
+        io.ns = a.want_grad ? a.nplist[c] : 0;
+        io.y_out = a.y_out ? a.y_out + t0off * M::NY : nullptr;
+        io.sigmay_out = a.sigmay_out ? a.sigmay_out + t0off * M::NY : nullptr;
+
+        // ---- A8: runAndLogSimulation retry loop (multiConditionProblem.cpp:369-465) ----
+        double llh = NAN;
+        double sllh[CPL];
+        int status = SIM_ERROR;
+        int trial = 1;
+        double relax = 1.0;
+        for (; trial <= a.num_trials; ++trial) {
+            status = bdf.simulate(io, a.opt.rtol * relax, a.opt.atol * relax, llh, sllh);
+            if (status == SIM_SUCCESS) break;
+            // next trial: tolerances * relaxation^(trial) relative to the template
+            relax = 1.0;
+            for (int e = 0; e < trial; ++e) relax *= a.relaxation_factor;
+        }
+        if (trial > a.num_trials) trial = a.num_trials;
+
+        // ---- outputs: A7 result package + A6 chain rule to the optimiser scale ----
+        if (lane == 0) {
+            a.llh[r] = llh;
+            a.status[r] = status;
+            bdf.export_stats(a.stats + (size_t)r * NSTATS, trial);
+        }
+        if (a.want_grad) {
+            for (int i = lane; i < M::NP; i += G) {
+                a.gcontrib[(size_t)r * M::NP + i] = 0.0;
+                a.sllh[(size_t)r * M::NP + i] = 0.0;
+            }
+            grp.sync();
+#pragma unroll
+            for (int m = 0; m < CPL; ++m) {
+                const int col = lane + m * G;
+                if (col < 1 || col > io.ns) continue;
+                const int ip = sh->plist[col - 1];
+                const int ssim = a.pscale_sim[cp + ip];
+                const int jopt = a.mapping[cp + ip];
+                const double pu = sh->p[ip];
+                // ReturnData::applyChainRuleFactorToSimulationResults (rdata.cpp:672-686, 706-708)
+                double s = sllh[m];
+                if (ssim == 2) s *= pu * PB_LN10;
+                else if (ssim == 1) s *= pu;
+                a.sllh[(size_t)r * M::NP + (col - 1)] = s;
+                // applyChainRule (multiConditionDataProvider.cpp:762-796), coefficient -1
+                const int sopt = a.pscale_opt[jopt];
+                double gr = s;
+                if (ssim != sopt) {
+                    if (ssim == 2) gr /= pu * PB_LN10;
+                    else if (ssim == 1) gr /= pu;
+                    if (sopt == 2) gr *= pu * PB_LN10;
+                    else if (sopt == 1) gr *= pu;
+                }
+                a.gcontrib[(size_t)r * M::NP + ip] = -1.0 * gr;
+            }
+        }
+        grp.sync();
+    }
+}
+
+/// Deterministic reduction: block 0 -> nllh and error count; block 1+j -> gradient entry j.
+/// out[0] = sum_r -llh[r]; out[1] = #conditions with status != 0; out[2+j] = gradient.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) reduce_kernel(const KernelArgs a, double* __restrict__ out) {
+    __shared__ double red[THREADS];
+    __shared__ double red2[THREADS];
+    const int tid = threadIdx.x;
+    double acc = 0.0, acc2 = 0.0;
+    if (blockIdx.x == 0) {
+        for (int r = tid; r < a.n; r += THREADS) {
+            acc -= a.llh[r];
+            acc2 += (a.status[r] != 0) ? 1.0 : 0.0;
+        }
+    } else {
+        const int j = blockIdx.x - 1;
+        if (a.want_grad) {
+            for (int r = tid; r < a.n; r += THREADS) {
+                const size_t cp = (size_t)a.idx[r] * a.np;
+                const size_t rp = (size_t)r * a.np;
+                for (int i = 0; i < a.np; ++i)
+                    if (a.mapping[cp + i] == j) acc += a.gcontrib[rp + i];
+            }
+        }
+    }
+    red[tid] = acc;
+    red2[tid] = acc2;
+    __syncthreads();
+    for (int s = THREADS / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            red[tid] += red[tid + s];
+            red2[tid] += red2[tid + s];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (blockIdx.x == 0) {
+            out[0] = red[0];
+            out[1] = red2[0];
+        } else {
+            out[1 + blockIdx.x] = red[0];
+        }
+    }
+}
+
+// ---- per-model launch table ------------------------------------------------------
+struct ModelOps {
+    const char* name;
+    int nx, np, nk, ny;
+    int default_lanes;  // G used for gradient evaluations unless overridden
+    int flops_xdot, flops_J, flops_dxdotdp, nnzJ;
+    // launches simulate_kernel; lanes: requested G (0 = default); returns cudaError_t as int
+    int (*launch)(const KernelArgs& a, int lanes, int sm_count, cudaStream_t stream, int* lanes_used, int* grid_used,
+                  int* block_used);
+};
+
+void register_model(const ModelOps& ops);
+const ModelOps* find_model(const char* name);
+int model_count();
+const ModelOps* model_at(int i);
+
+constexpr int PB_THREADS = 128;
+
+template <class M, int G, int CPL>
+int launch_one(const KernelArgs& a, int sm_count, cudaStream_t stream, int* grid_used, int* block_used) {
+    auto kern = simulate_kernel<M, G, CPL, PB_THREADS>;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PB_THREADS, 0);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    const int groups_per_block = PB_THREADS / G;
+    int grid = sm_count * per_sm;  // persistent: one resident wave, work queue inside
+    const int needed = (a.n + groups_per_block - 1) / groups_per_block;
+    if (grid > needed) grid = needed;
+    if (grid < 1) grid = 1;
+    kern<<<grid, PB_THREADS, 0, stream>>>(a);
+    if (grid_used) *grid_used = grid;
+    if (block_used) *block_used = PB_THREADS;
+    return (int)cudaGetLastError();
+}
+
+constexpr int pb_pow2_at_least(int n) { return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32; }
+constexpr int pb_cpl(int ncol, int g) { return (ncol + g - 1) / g; }
+
+/// Instantiations offered per model: cost-only (G=1, one column), and for gradients the
+/// default group size G0 = pow2 >= NP+1 (capped at 32, one column per lane when it fits)
+/// plus a full-warp variant (G=32).
+template <class M>
+int launch_model(const KernelArgs& a, int lanes, int sm_count, cudaStream_t stream, int* lanes_used, int* grid_used,
+                 int* block_used) {
+    constexpr int NCOL = M::NP + 1;
+    constexpr int G0 = pb_pow2_at_least(NCOL);
+    if (!a.want_grad) {
+        if (lanes_used) *lanes_used = 1;
+        return launch_one<M, 1, 1>(a, sm_count, stream, grid_used, block_used);
+    }
+    if (lanes == 32 && G0 != 32) {
+        if (lanes_used) *lanes_used = 32;
+        return launch_one<M, 32, pb_cpl(NCOL, 32)>(a, sm_count, stream, grid_used, block_used);
+    }
+    if (lanes_used) *lanes_used = G0;
+    return launch_one<M, G0, pb_cpl(NCOL, G0)>(a, sm_count, stream, grid_used, block_used);
+}
+
+template <class M>
+ModelOps make_ops() {
+    ModelOps o;
+    o.name = M::NAME;
+    o.nx = M::NX; o.np = M::NP; o.nk = M::NK; o.ny = M::NY;
+    o.default_lanes = pb_pow2_at_least(M::NP + 1);
+    o.flops_xdot = M::FLOPS_XDOT; o.flops_J = M::FLOPS_J; o.flops_dxdotdp = M::FLOPS_DXDOTDP; o.nnzJ = M::NNZ;
+    o.launch = &launch_model<M>;
+    return o;
+}
+
+#define PB200_REGISTER_MODEL(MODEL)                                  \
+    namespace {                                                      \
+    struct Reg_##MODEL {                                             \
+        Reg_##MODEL() { pb200::register_model(pb200::make_ops<pb200::models::MODEL>()); } \
+    } reg_instance_##MODEL;                                          \
+    }
+
+}  // namespace pb200
+#endif

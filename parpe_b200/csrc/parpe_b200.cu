@@ -1,0 +1,543 @@
+// parpe_b200.cu -- C ABI (include/parpe_b200.h) over the CUDA kernels.
+//
+// Host side of the per-GPU condition-batch scheduler that replaces
+// AmiciSimulationRunner + LoadBalancerMaster/Worker:
+// tables are resident in HBM, one evaluation = upload of the parameter table
+// (48*n_opt bytes) and, if it changed, the index list; one persistent kernel with an
+// in-kernel work queue; one reduction kernel; download of 2+n_opt doubles.
+// There is no CPU fallback: without a CUDA device every compute entry point fails.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/parpe_b200.h"
+#include "hier_kernels.cuh"
+#include "kernels.cuh"
+
+namespace pb200 {
+
+static std::vector<ModelOps>& registry() {
+    static std::vector<ModelOps> r;
+    return r;
+}
+void register_model(const ModelOps& ops) { registry().push_back(ops); }
+const ModelOps* find_model(const char* name) {
+    for (auto& m : registry())
+        if (!std::strcmp(m.name, name)) return &m;
+    return nullptr;
+}
+int model_count() { return (int)registry().size(); }
+const ModelOps* model_at(int i) { return (i >= 0 && i < model_count()) ? &registry()[i] : nullptr; }
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define PB_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(PB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+
+// amici::getUnscaledParameter / getScaledParameter (deps/AMICI/src/misc.cpp:26-63), evaluated
+// on the host with the same libm calls as the reference so the values are bit-identical
+static double unscale(double v, int s) {
+    switch (s) {
+    case PB200_SCALE_LOG10: return std::pow(10, v);
+    case PB200_SCALE_LN: return std::exp(v);
+    default: return v;
+    }
+}
+static double scale(double v, int s) {
+    switch (s) {
+    case PB200_SCALE_LOG10: return std::log10(v);
+    case PB200_SCALE_LN: return std::log(v);
+    default: return v;
+    }
+}
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const T* src, size_t count) {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+template <class T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMallocHost((void**)&p, count * sizeof(T));
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~PinnedBuf() { release(); }
+};
+
+}  // namespace pb200
+
+using namespace pb200;
+
+struct pb200_handle {
+    const ModelOps* ops = nullptr;
+    int device = 0, sm_count = 0;
+    int C = 0, n_opt = 0, np = 0, nk = 0, ny = 0;
+    int64_t nt_total = 0;
+    int lanes = 0;
+    int rank = 0, world = 1;
+    std::vector<int> pscale_opt;
+    std::vector<int64_t> t_offsets;
+    // resident tables
+    DevBuf<int64_t> d_t_offsets;
+    DevBuf<double> d_t, d_my, d_sd, d_k, d_ov_scaled, d_ov_unscaled;
+    DevBuf<int> d_mapping, d_pscale_sim, d_pscale_opt, d_plist, d_nplist;
+    // per-evaluation buffers
+    int cap = 0;
+    DevBuf<double> d_llh, d_sllh, d_gcontrib, d_theta_tab, d_out, d_yout, d_sout;
+    DevBuf<int> d_status, d_idx, d_counter;
+    DevBuf<int64_t> d_stats;
+    PinnedBuf<double> h_theta_tab, h_out;
+    PinnedBuf<int> h_idx;
+    std::vector<int> idx_cache;  // index list currently resident in d_idx
+    int last_n = 0;
+    int last_want_grad = 0;
+    int last_lanes = 0, last_grid = 0, last_block = 0;
+    KernelArgs args{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_staged = nullptr;
+    bool staged_pending = false;
+    // hierarchical
+    HierDevice* hier = nullptr;
+};
+
+static int ensure_capacity(pb200_handle* h, int n) {
+    if (n <= h->cap) return 0;
+    int cap = n;
+    PB_CUDA(h->d_llh.alloc(cap));
+    PB_CUDA(h->d_sllh.alloc((size_t)cap * h->np));
+    PB_CUDA(h->d_gcontrib.alloc((size_t)cap * h->np));
+    PB_CUDA(h->d_status.alloc(cap));
+    PB_CUDA(h->d_stats.alloc((size_t)cap * NSTATS));
+    PB_CUDA(h->d_idx.alloc(cap));
+    PB_CUDA(h->h_idx.alloc(cap));
+    h->idx_cache.clear();
+    h->cap = cap;
+    return 0;
+}
+
+// stage theta table + index list and enqueue simulate + reduce on `stream`
+static int enqueue_evaluation(pb200_handle* h, const double* theta, const int* idx, int n_idx, int want_grad,
+                              double* d_out, double* d_yout, double* d_sout, cudaStream_t stream) {
+    PB_CUDA(cudaSetDevice(h->device));
+    int lo, hi;
+    pb200_partition_bounds(n_idx, h->rank, h->world, &lo, &hi);
+    const int n = hi - lo;
+    for (int r = lo; r < hi; ++r)
+        if (idx[r] < 0 || idx[r] >= h->C) return fail(PB200_ERR_ARG, "data index out of range");
+    if (int rc = ensure_capacity(h, n > 0 ? n : 1)) return rc;
+    if (h->staged_pending) {  // pinned staging buffers may still be in flight
+        PB_CUDA(cudaEventSynchronize(h->ev_staged));
+        h->staged_pending = false;
+    }
+    // A5: per optimisation parameter and simulation scale: value in simulation scale and its
+    // unscaled value, exactly as mapAndSetOptimizationToSimulationVariables + AMICI compute them
+    for (int j = 0; j < h->n_opt; ++j) {
+        const double lin = unscale(theta[j], h->pscale_opt[j]);
+        for (int s = 0; s < 3; ++s) {
+            const double sc = scale(lin, s);
+            h->h_theta_tab.p[((size_t)j * 3 + s) * 2 + 0] = sc;
+            h->h_theta_tab.p[((size_t)j * 3 + s) * 2 + 1] = unscale(sc, s);
+        }
+    }
+    PB_CUDA(cudaMemcpyAsync(h->d_theta_tab.p, h->h_theta_tab.p, sizeof(double) * 6 * h->n_opt,
+                            cudaMemcpyHostToDevice, stream));
+    const bool same_idx = (int)h->idx_cache.size() == n && (n == 0 || !std::memcmp(h->idx_cache.data(), idx + lo, sizeof(int) * n));
+    if (!same_idx) {
+        std::memcpy(h->h_idx.p, idx + lo, sizeof(int) * n);
+        PB_CUDA(cudaMemcpyAsync(h->d_idx.p, h->h_idx.p, sizeof(int) * n, cudaMemcpyHostToDevice, stream));
+        h->idx_cache.assign(idx + lo, idx + hi);
+    }
+    PB_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), stream));
+    PB_CUDA(cudaEventRecord(h->ev_staged, stream));
+    h->staged_pending = true;
+
+    KernelArgs a = h->args;
+    a.theta_tab = h->d_theta_tab.p;
+    a.idx = h->d_idx.p;
+    a.order = nullptr;
+    a.n = n;
+    a.want_grad = want_grad;
+    a.counter = h->d_counter.p;
+    a.llh = h->d_llh.p;
+    a.sllh = h->d_sllh.p;
+    a.gcontrib = h->d_gcontrib.p;
+    a.status = h->d_status.p;
+    a.stats = h->d_stats.p;
+    a.y_out = d_yout;
+    a.sigmay_out = d_sout;
+    PB_CUDA(cudaEventRecord(h->ev_start, stream));
+    if (n > 0) {
+        int e = h->ops->launch(a, h->lanes, h->sm_count, stream, &h->last_lanes, &h->last_grid, &h->last_block);
+        if (e != 0) return fail(PB200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)e));
+    }
+    reduce_kernel<256><<<1 + h->n_opt, 256, 0, stream>>>(a, d_out);
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaEventRecord(h->ev_stop, stream));
+    h->last_n = n;
+    h->last_want_grad = want_grad;
+    return 0;
+}
+
+extern "C" {
+
+int pb200_abi_version(void) { return PB200_ABI_VERSION; }
+
+int pb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int pb200_model_count(void) { return model_count(); }
+const char* pb200_model_name(int i) {
+    const ModelOps* m = model_at(i);
+    return m ? m->name : nullptr;
+}
+int pb200_model_info(const char* model_name, int* nx, int* np, int* nk, int* ny) {
+    const ModelOps* m = model_name ? find_model(model_name) : nullptr;
+    if (!m) return fail(PB200_ERR_MODEL, "unknown model");
+    if (nx) *nx = m->nx;
+    if (np) *np = m->np;
+    if (nk) *nk = m->nk;
+    if (ny) *ny = m->ny;
+    return 0;
+}
+const char* pb200_last_error(void) { return g_err.c_str(); }
+
+void pb200_partition_bounds(int n, int rank, int world, int* lo, int* hi) {
+    if (world < 1) world = 1;
+    *lo = (int)(((int64_t)rank * n) / world);
+    *hi = (int)(((int64_t)(rank + 1) * n) / world);
+}
+
+int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
+    if (!d || !out) return fail(PB200_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (d->abi_version != PB200_ABI_VERSION) return fail(PB200_ERR_ARG, "ABI version mismatch");
+    const ModelOps* ops = d->model_name ? find_model(d->model_name) : nullptr;
+    if (!ops) return fail(PB200_ERR_MODEL, std::string("unknown model ") + (d->model_name ? d->model_name : "(null)"));
+    if (ops->np != d->np || ops->nk != d->nk || ops->ny != d->ny)
+        return fail(PB200_ERR_MODEL, "np/nk/ny do not match the model");
+    if (d->n_conditions < 0 || d->n_opt < 0 || !d->t_offsets) return fail(PB200_ERR_ARG, "bad dimensions");
+    if (pb200_device_count() <= 0) return fail(PB200_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    PB_CUDA(cudaSetDevice(device));
+    const int C = d->n_conditions;
+    for (int c = 0; c < C; ++c) {
+        if (d->t_offsets[c + 1] < d->t_offsets[c]) return fail(PB200_ERR_ARG, "t_offsets not monotone");
+        for (int i = 0; i < d->np; ++i) {
+            const int j = d->mapping[(size_t)c * d->np + i];
+            if (j >= d->n_opt) return fail(PB200_ERR_ARG, "mapping entry out of range");
+            const int s = d->pscale_sim[(size_t)c * d->np + i];
+            if (s < 0 || s > 2) return fail(PB200_ERR_ARG, "invalid simulation parameter scale");
+        }
+    }
+    for (int j = 0; j < d->n_opt; ++j)
+        if (d->pscale_opt[j] < 0 || d->pscale_opt[j] > 2) return fail(PB200_ERR_ARG, "invalid optimisation parameter scale");
+
+    auto* h = new pb200_handle;
+    std::unique_ptr<pb200_handle, void (*)(pb200_handle*)> guard(h, pb200_destroy);
+    h->ops = ops;
+    h->device = device;
+    cudaDeviceProp prop;
+    PB_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    h->C = C;
+    h->n_opt = d->n_opt;
+    h->np = d->np;
+    h->nk = d->nk;
+    h->ny = d->ny;
+    h->lanes = d->lanes_per_condition;
+    h->pscale_opt.assign(d->pscale_opt, d->pscale_opt + d->n_opt);
+    h->t_offsets.assign(d->t_offsets, d->t_offsets + C + 1);
+    h->nt_total = C > 0 ? d->t_offsets[C] : 0;
+
+    // A5 getSensitivityParameterList (multiConditionDataProvider.cpp:323-339), once per condition
+    std::vector<int> plist((size_t)C * d->np, 0), nplist(C, 0);
+    for (int c = 0; c < C; ++c) {
+        int k = 0;
+        for (int i = 0; i < d->np; ++i)
+            if (d->mapping[(size_t)c * d->np + i] >= 0) plist[(size_t)c * d->np + k++] = i;
+        nplist[c] = k;
+    }
+    PB_CUDA(h->d_t_offsets.upload(d->t_offsets, C + 1));
+    PB_CUDA(h->d_t.upload(d->t, h->nt_total));
+    PB_CUDA(h->d_my.upload(d->y, h->nt_total * d->ny));
+    PB_CUDA(h->d_sd.upload(d->sigma, h->nt_total * d->ny));
+    PB_CUDA(h->d_k.upload(d->k, (size_t)C * d->nk));
+    PB_CUDA(h->d_mapping.upload(d->mapping, (size_t)C * d->np));
+    PB_CUDA(h->d_pscale_sim.upload(d->pscale_sim, (size_t)C * d->np));
+    PB_CUDA(h->d_pscale_opt.upload(d->pscale_opt, d->n_opt));
+    PB_CUDA(h->d_plist.upload(plist.data(), plist.size()));
+    PB_CUDA(h->d_nplist.upload(nplist.data(), nplist.size()));
+    if (d->overrides) {
+        std::vector<double> ovu((size_t)C * d->np);
+        for (size_t i = 0; i < ovu.size(); ++i) ovu[i] = unscale(d->overrides[i], d->pscale_sim[i]);
+        PB_CUDA(h->d_ov_scaled.upload(d->overrides, ovu.size()));
+        PB_CUDA(h->d_ov_unscaled.upload(ovu.data(), ovu.size()));
+    }
+    PB_CUDA(h->d_theta_tab.alloc((size_t)6 * (d->n_opt > 0 ? d->n_opt : 1)));
+    PB_CUDA(h->h_theta_tab.alloc((size_t)6 * (d->n_opt > 0 ? d->n_opt : 1)));
+    PB_CUDA(h->d_out.alloc(2 + d->n_opt));
+    PB_CUDA(h->h_out.alloc(2 + d->n_opt));
+    PB_CUDA(h->d_counter.alloc(1));
+    PB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    PB_CUDA(cudaEventCreate(&h->ev_start));
+    PB_CUDA(cudaEventCreate(&h->ev_stop));
+    PB_CUDA(cudaEventCreateWithFlags(&h->ev_staged, cudaEventDisableTiming));
+
+    KernelArgs& a = h->args;
+    a.n_conditions = C;
+    a.n_opt = d->n_opt;
+    a.np = d->np;
+    a.nk = d->nk;
+    a.ny = d->ny;
+    a.t_offsets = h->d_t_offsets.p;
+    a.t = h->d_t.p;
+    a.my = h->d_my.p;
+    a.sd = h->d_sd.p;
+    a.k = h->d_k.p;
+    a.mapping = h->d_mapping.p;
+    a.pscale_sim = h->d_pscale_sim.p;
+    a.pscale_opt = h->d_pscale_opt.p;
+    a.ov_scaled = h->d_ov_scaled.p;
+    a.ov_unscaled = h->d_ov_unscaled.p;
+    a.plist = h->d_plist.p;
+    a.nplist = h->d_nplist.p;
+    a.opt.t0 = d->t0;
+    a.opt.rtol = d->rtol;
+    a.opt.atol = d->atol;
+    a.opt.maxsteps = d->maxsteps;
+    a.opt.stldet = d->stldet;
+    a.opt.errconS = d->sensi_errcon;
+    a.num_trials = d->num_trials > 0 ? d->num_trials : 1;
+    a.relaxation_factor = d->relaxation_factor;
+    if (int rc = ensure_capacity(h, C > 0 ? C : 1)) return rc;
+    guard.release();
+    *out = h;
+    return 0;
+}
+
+void pb200_destroy(pb200_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    hier_destroy(h->hier);
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+    if (h->ev_staged) cudaEventDestroy(h->ev_staged);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int pb200_set_partition(pb200_handle* h, int rank, int world) {
+    if (!h || world < 1 || rank < 0 || rank >= world) return fail(PB200_ERR_ARG, "bad partition");
+    h->rank = rank;
+    h->world = world;
+    h->idx_cache.clear();
+    return 0;
+}
+
+int pb200_evaluate(pb200_handle* h, const double* theta, int n_opt, const int* idx, int n_idx, double* fval,
+                   double* grad, double* seconds) {
+    if (!h || !theta || !fval || (n_idx > 0 && !idx)) return fail(PB200_ERR_ARG, "null argument");
+    if (n_opt != h->n_opt) return fail(PB200_ERR_ARG, "parameter vector size does not match numParameters");
+    const int want_grad = grad != nullptr;
+    if (int rc = enqueue_evaluation(h, theta, idx, n_idx, want_grad, h->d_out.p, nullptr, nullptr, h->stream)) return rc;
+    PB_CUDA(cudaMemcpyAsync(h->h_out.p, h->d_out.p, sizeof(double) * (2 + h->n_opt), cudaMemcpyDeviceToHost, h->stream));
+    PB_CUDA(cudaStreamSynchronize(h->stream));
+    if (seconds) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop);
+        *seconds = ms * 1e-3;
+    }
+    // A1: zero-filled outputs, then sums; any error or non-finite -> +inf, failure
+    *fval = h->h_out.p[0];
+    if (grad)
+        for (int j = 0; j < h->n_opt; ++j) grad[j] = h->h_out.p[2 + j];
+    const double errors = h->h_out.p[1];
+    if (errors != 0.0 || !std::isfinite(*fval)) {
+        *fval = std::numeric_limits<double>::infinity();
+        return PB200_EVAL_FAILURE;
+    }
+    return PB200_EVAL_SUCCESS;
+}
+
+int pb200_evaluate_device(pb200_handle* h, const double* theta, int n_opt, const int* idx, int n_idx, int want_grad,
+                          double* d_out, void* stream) {
+    if (!h || !theta || !d_out || (n_idx > 0 && !idx)) return fail(PB200_ERR_ARG, "null argument");
+    if (n_opt != h->n_opt) return fail(PB200_ERR_ARG, "parameter vector size does not match numParameters");
+    return enqueue_evaluation(h, theta, idx, n_idx, want_grad, d_out, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int pb200_last_launch(pb200_handle* h, int* lanes, int* grid, int* block, double* seconds) {
+    if (!h) return fail(PB200_ERR_ARG, "null handle");
+    if (lanes) *lanes = h->last_lanes;
+    if (grid) *grid = h->last_grid;
+    if (block) *block = h->last_block;
+    if (seconds) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop) != cudaSuccess) {
+            cudaGetLastError();
+            ms = -1e3f;
+        }
+        *seconds = ms * 1e-3;
+    }
+    return 0;
+}
+
+int pb200_get_condition_results(pb200_handle* h, double* llh, double* sllh, int* status, int64_t* stats) {
+    if (!h) return fail(PB200_ERR_ARG, "null handle");
+    PB_CUDA(cudaSetDevice(h->device));
+    PB_CUDA(cudaDeviceSynchronize());
+    const int n = h->last_n;
+    if (llh) PB_CUDA(cudaMemcpy(llh, h->d_llh.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (sllh) {
+        if (h->last_want_grad) PB_CUDA(cudaMemcpy(sllh, h->d_sllh.p, sizeof(double) * (size_t)n * h->np, cudaMemcpyDeviceToHost));
+        else std::memset(sllh, 0, sizeof(double) * (size_t)n * h->np);
+    }
+    if (status) PB_CUDA(cudaMemcpy(status, h->d_status.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    if (stats) PB_CUDA(cudaMemcpy(stats, h->d_stats.p, sizeof(int64_t) * (size_t)n * NSTATS, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+// getModelOutputsAndSigmas (multiConditionProblem.cpp:506-563): all conditions, no sensitivities
+static int run_outputs(pb200_handle* h, const double* theta, double* d_out) {
+    const size_t ny_total = (size_t)h->nt_total * h->ny;
+    if (h->d_yout.n < ny_total || !h->d_yout.p) {
+        PB_CUDA(h->d_yout.alloc(ny_total > 0 ? ny_total : 1));
+        PB_CUDA(h->d_sout.alloc(ny_total > 0 ? ny_total : 1));
+    }
+    // conditions this partition does not simulate stay NaN
+    PB_CUDA(cudaMemsetAsync(h->d_yout.p, 0xFF, sizeof(double) * ny_total, h->stream));
+    PB_CUDA(cudaMemsetAsync(h->d_sout.p, 0xFF, sizeof(double) * ny_total, h->stream));
+    std::vector<int> all(h->C);
+    for (int c = 0; c < h->C; ++c) all[c] = c;
+    return enqueue_evaluation(h, theta, all.data(), h->C, 0, d_out, h->d_yout.p, h->d_sout.p, h->stream);
+}
+
+int pb200_get_model_outputs(pb200_handle* h, const double* theta, int n_opt, double* y_out, double* sigmay_out) {
+    if (!h || !theta) return fail(PB200_ERR_ARG, "null argument");
+    if (n_opt != h->n_opt) return fail(PB200_ERR_ARG, "parameter vector size does not match numParameters");
+    if (int rc = run_outputs(h, theta, h->d_out.p)) return rc;
+    const size_t ny_total = (size_t)h->nt_total * h->ny;
+    PB_CUDA(cudaMemcpyAsync(h->h_out.p, h->d_out.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stream));
+    if (y_out) PB_CUDA(cudaMemcpyAsync(y_out, h->d_yout.p, sizeof(double) * ny_total, cudaMemcpyDeviceToHost, h->stream));
+    if (sigmay_out) PB_CUDA(cudaMemcpyAsync(sigmay_out, h->d_sout.p, sizeof(double) * ny_total, cudaMemcpyDeviceToHost, h->stream));
+    PB_CUDA(cudaStreamSynchronize(h->stream));
+    return h->h_out.p[1] == 0.0 ? PB200_EVAL_SUCCESS : PB200_EVAL_FAILURE;
+}
+
+// ---- hierarchical optimisation (A15) -----------------------------------------------
+int pb200_hier_attach(pb200_handle* h, const pb200_hier_desc* hd) {
+    if (!h || !hd) return fail(PB200_ERR_ARG, "null argument");
+    PB_CUDA(cudaSetDevice(h->device));
+    hier_destroy(h->hier);
+    h->hier = nullptr;
+    std::string err;
+    HierDevice* hv = hier_create(*hd, h->C, h->n_opt, h->ny, h->t_offsets.data(), h->pscale_opt.data(), &err);
+    if (!hv) return fail(PB200_ERR_ARG, err);
+    h->hier = hv;
+    return 0;
+}
+
+int pb200_hier_num_outer(pb200_handle* h) {
+    if (!h || !h->hier) return fail(PB200_ERR_ARG, "no hierarchical description attached");
+    return h->n_opt - hier_num_inner(h->hier);
+}
+
+int pb200_hier_evaluate(pb200_handle* h, const double* theta_outer, int n_outer, double* fval, double* grad_outer,
+                        double* full_parameters, double* seconds) {
+    if (!h || !h->hier || !theta_outer || !fval) return fail(PB200_ERR_ARG, "null argument");
+    const int n_inner = hier_num_inner(h->hier);
+    // HierarchicalOptimizationWrapper::evaluate throws on size mismatch (hierarchicalOptimization.cpp:155-160)
+    if (n_outer != h->n_opt - n_inner) return fail(PB200_ERR_ARG, "reduced parameter vector size does not match numParameters");
+    PB_CUDA(cudaSetDevice(h->device));
+    double t_total = 0.0;
+    // pass 1: defaults for the inner parameters (scaling 1, offset 0, sigma 1 in linear scale)
+    std::vector<double> full(h->n_opt);
+    hier_splice_defaults(h->hier, theta_outer, full.data());
+    if (int rc = run_outputs(h, full.data(), h->d_out.p)) return rc;
+    PB_CUDA(cudaMemcpyAsync(h->h_out.p, h->d_out.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stream));
+    PB_CUDA(cudaStreamSynchronize(h->stream));
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop);
+        t_total += ms * 1e-3;
+    }
+    if (h->h_out.p[1] != 0.0) {  // "Function evaluation failed." -> functionEvaluationFailure
+        *fval = std::numeric_limits<double>::infinity();
+        return PB200_EVAL_FAILURE;
+    }
+    // analytic inner parameters on the device from the resident outputs
+    std::vector<double> inner_scaled;  // optimiser scale, order: scalings, offsets, sigmas
+    double nllh_analytic = 0.0;
+    std::string err;
+    if (!hier_compute(h->hier, h->d_my.p, h->d_yout.p, h->d_sout.p, h->stream, grad_outer == nullptr, &inner_scaled,
+                      &nllh_analytic, &err))
+        return fail(PB200_ERR_CUDA, err);
+    hier_splice(h->hier, theta_outer, inner_scaled.data(), full.data());
+    if (full_parameters) std::memcpy(full_parameters, full.data(), sizeof(double) * h->n_opt);
+    int status;
+    if (grad_outer) {
+        // pass 2: full evaluation with sensitivities, gradient filtered to the outer parameters
+        std::vector<int> all(h->C);
+        for (int c = 0; c < h->C; ++c) all[c] = c;
+        std::vector<double> full_grad(h->n_opt);
+        double sec2 = 0.0;
+        status = pb200_evaluate(h, full.data(), h->n_opt, all.data(), h->C, fval, full_grad.data(), &sec2);
+        t_total += sec2;
+        if (status < 0) return status;
+        if (status == PB200_EVAL_SUCCESS) hier_filter(h->hier, full_grad.data(), grad_outer);
+    } else {
+        *fval = nllh_analytic;
+        status = std::isfinite(*fval) ? PB200_EVAL_SUCCESS : PB200_EVAL_FAILURE;
+    }
+    if (seconds) *seconds = t_total;
+    return status;
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+"""Host-side mirror of the reference's interface for the hot path.
+
+``B200SummedGradientFunction`` plays the role of ``parpe::AmiciSummedGradientFunction``
+(``include/parpeamici/multiConditionProblem.h:95-237``): same method names and argument
+meaning (``evaluate(parameters, datasets) -> (status, fval, gradient)``,
+``numParameters``, ``getModelOutputsAndSigmas``, ``getAllMeasurements``,
+``getParameterScaling``), same error behaviour (simulation failure => ``fval = +inf`` and
+``functionEvaluationFailure``; wrong parameter-vector size raises).  It forwards to the
+C ABI; the numerics run in the CUDA library only.  The C++ adapter with the reference's
+exact signatures is ``parpe_b200/include/parpe_b200/b200SummedGradientFunction.h``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .tables import PB200_NSTATS, STAT_NAMES, ProblemTables
+
+functionEvaluationSuccess = 0
+functionEvaluationFailure = 1
+
+
+class B200SummedGradientFunction:
+    """``parpe::SummedGradientFunction<int>`` over a CUDA-resident multi-condition problem."""
+
+    def __init__(self, tables: ProblemTables, device: int = 0):
+        self.tables = tables
+        self._desc = tables.to_desc()
+        self._h = C.c_void_p()
+        L = capi.lib()
+        capi.check(L.pb200_create(C.byref(self._desc), device, C.byref(self._h)), "pb200_create")
+        self.device = device
+        self.rank, self.world = 0, 1
+        if tables.hier is not None:
+            self._hd = tables.hier.to_desc()
+            capi.check(L.pb200_hier_attach(self._h, C.byref(self._hd)), "pb200_hier_attach")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            capi.lib().pb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parpe::SummedGradientFunction<int> ------------------------------------
+    def numParameters(self) -> int:
+        return self.tables.n_opt
+
+    def getParameterScaling(self, parameterIndex: int) -> int:
+        return int(self.tables.pscale_opt[parameterIndex])
+
+    def getAllMeasurements(self):
+        T = self.tables
+        return [T.y_of(c).reshape(-1).copy() for c in range(T.n_conditions)]
+
+    def evaluate(self, parameters: Sequence[float], datasets=None, want_gradient: bool = True):
+        """-> (status, fval, gradient or None, seconds).  ``datasets``: one index or a list;
+        default = all conditions (SummedGradientFunctionGradientFunctionAdapter,
+        include/parpecommon/functions.h:144-153)."""
+        T = self.tables
+        theta = np.ascontiguousarray(parameters, dtype=np.float64)
+        if datasets is None:
+            idx = np.arange(T.n_conditions, dtype=np.int32)
+        else:
+            idx = np.ascontiguousarray(np.atleast_1d(datasets), dtype=np.int32)
+        fval = C.c_double()
+        sec = C.c_double()
+        grad = np.zeros(T.n_opt) if want_gradient else None
+        rc = capi.lib().pb200_evaluate(self._h, capi.dptr(theta), len(theta), capi.iptr(idx), len(idx),
+                                       C.byref(fval), capi.dptr(grad), C.byref(sec))
+        capi.check(rc, "pb200_evaluate")
+        return rc, fval.value, grad, sec.value
+
+    def evaluate_device(self, parameters, datasets, want_gradient: bool, d_out_ptr: int, stream_ptr: int = 0):
+        """Enqueue on ``stream``; partial (nllh, nerr, grad) lands in the device buffer."""
+        theta = np.ascontiguousarray(parameters, dtype=np.float64)
+        idx = np.ascontiguousarray(np.atleast_1d(datasets), dtype=np.int32)
+        rc = capi.lib().pb200_evaluate_device(self._h, capi.dptr(theta), len(theta), capi.iptr(idx), len(idx),
+                                              int(want_gradient), C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr))
+        capi.check(rc, "pb200_evaluate_device")
+
+    def getModelOutputsAndSigmas(self, parameters):
+        T = self.tables
+        theta = np.ascontiguousarray(parameters, dtype=np.float64)
+        y = np.zeros_like(T.y)
+        s = np.zeros_like(T.y)
+        rc = capi.check(capi.lib().pb200_get_model_outputs(self._h, capi.dptr(theta), len(theta), capi.dptr(y),
+                                                           capi.dptr(s)), "pb200_get_model_outputs")
+        return rc, y, s
+
+    # ---- beyond the reference interface -------------------------------------------
+    def set_partition(self, rank: int, world: int):
+        capi.check(capi.lib().pb200_set_partition(self._h, rank, world), "pb200_set_partition")
+        self.rank, self.world = rank, world
+
+    def condition_results(self):
+        """Per-condition result packages of the last evaluation (A7)."""
+        T = self.tables
+        cap = T.n_conditions if T.n_conditions > 0 else 1
+        L = capi.lib()
+        n = capi.check(L.pb200_get_condition_results(self._h, None, None, None, None), "pb200_get_condition_results")
+        n = max(n, 1)
+        llh = np.zeros(n)
+        sllh = np.zeros((n, T.np_))
+        status = np.zeros(n, dtype=np.int32)
+        stats = np.zeros((n, PB200_NSTATS), dtype=np.int64)
+        n2 = capi.check(L.pb200_get_condition_results(self._h, capi.dptr(llh), capi.dptr(sllh), capi.iptr(status),
+                                                      stats.ctypes.data_as(C.POINTER(C.c_int64))),
+                        "pb200_get_condition_results")
+        return dict(llh=llh[:n2], sllh=sllh[:n2], status=status[:n2], stats=stats[:n2],
+                    stat_names=STAT_NAMES)
+
+    def last_launch(self):
+        lanes, grid, block, sec = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        capi.lib().pb200_last_launch(self._h, C.byref(lanes), C.byref(grid), C.byref(block), C.byref(sec))
+        return dict(lanes=lanes.value, grid=grid.value, block=block.value, seconds=sec.value)
+
+    # ---- hierarchical wrapper (parpe::HierarchicalOptimizationWrapper) -------------
+    def hier_num_outer(self) -> int:
+        return capi.check(capi.lib().pb200_hier_num_outer(self._h), "pb200_hier_num_outer")
+
+    def hier_evaluate(self, reducedParameters, want_gradient: bool = True):
+        theta = np.ascontiguousarray(reducedParameters, dtype=np.float64)
+        fval, sec = C.c_double(), C.c_double()
+        grad = np.zeros(len(theta)) if want_gradient else None
+        full = np.zeros(self.tables.n_opt)
+        rc = capi.check(capi.lib().pb200_hier_evaluate(self._h, capi.dptr(theta), len(theta), C.byref(fval),
+                                                       capi.dptr(grad), capi.dptr(full), C.byref(sec)),
+                        "pb200_hier_evaluate")
+        return dict(status=rc, fval=fval.value, grad=grad, full_parameters=full, seconds=sec.value)

@@ -1,0 +1,25 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+LLH_RTOL = 1e-6    # north star: llh within 1e-6 relative
+GRAD_RTOL = 1e-4   # north star: gradient within 1e-4 relative
+
+
+def rel_err(a, b, floor=0.0):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return np.abs(a - b) / np.maximum(np.abs(b), floor if floor > 0 else 1e-300)
+
+
+def assert_llh_close(a, b, what="llh"):
+    e = float(np.max(rel_err(a, b)))
+    assert e <= LLH_RTOL, "%s: relative error %.3e > %.1e (%r vs %r)" % (what, e, LLH_RTOL, a, b)
+
+
+def assert_grad_close(a, b, what="gradient"):
+    """Relative to the entry, with a floor of 1e-4 * max|gradient| so that entries that are
+    zero up to integration error are compared on the gradient's own scale."""
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    scale = np.max(np.abs(b)) if b.size else 0.0
+    e = np.abs(a - b) / np.maximum(np.abs(b), 1e-4 * scale + 1e-300)
+    assert np.all(e <= GRAD_RTOL), "%s: max relative error %.3e > %.1e\n got %r\n ref %r" % (
+        what, float(np.max(e)), GRAD_RTOL, a, b)
