@@ -142,6 +142,10 @@ int pb200_model_info(const char* model_name, int* nx, int* np, int* nk, int* ny)
 /* last error message of the calling thread ("" if none) */
 const char* pb200_last_error(void);
 
+/* measured FP64 DFMA peak of `device` in TFLOP/s (roofline denominator; no reference
+ * counterpart) */
+int pb200_measure_fp64_peak(int device, double* tflops);
+
 /* lifetime ---------------------------------------------------------------- */
 /*
  * Replaces: construction of MultiConditionDataProviderHDF5 +

@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = [
     "pb200_abi_version", "pb200_device_count", "pb200_model_count", "pb200_model_name", "pb200_model_info",
     "pb200_last_error", "pb200_create", "pb200_destroy", "pb200_set_partition", "pb200_partition_bounds",
     "pb200_evaluate", "pb200_evaluate_device", "pb200_last_launch", "pb200_get_condition_results",
-    "pb200_get_model_outputs", "pb200_hier_attach", "pb200_hier_num_outer", "pb200_hier_evaluate",
+    "pb200_get_model_outputs", "pb200_measure_fp64_peak", "pb200_hier_attach", "pb200_hier_num_outer", "pb200_hier_evaluate",
 ]
 
 _lib = None
@@ -56,6 +56,7 @@ def lib():
     L.pb200_last_launch.argtypes = [C.c_void_p, ip, ip, ip, dp]
     L.pb200_get_condition_results.argtypes = [C.c_void_p, dp, dp, ip, C.POINTER(C.c_int64)]
     L.pb200_get_model_outputs.argtypes = [C.c_void_p, dp, C.c_int, dp, dp]
+    L.pb200_measure_fp64_peak.argtypes = [C.c_int, dp]
     L.pb200_hier_attach.argtypes = [C.c_void_p, C.POINTER(HierDesc)]
     L.pb200_hier_num_outer.argtypes = [C.c_void_p]
     L.pb200_hier_evaluate.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp, dp]
@@ -86,6 +87,12 @@ def models():
         L.pb200_model_info(name, C.byref(nx), C.byref(np_), C.byref(nk), C.byref(ny))
         out[name.decode()] = dict(nx=nx.value, np=np_.value, nk=nk.value, ny=ny.value)
     return out
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    v = C.c_double()
+    check(lib().pb200_measure_fp64_peak(device, C.byref(v)), "pb200_measure_fp64_peak")
+    return v.value
 
 
 def partition_bounds(n: int, rank: int, world: int):

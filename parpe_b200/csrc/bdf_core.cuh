@@ -170,6 +170,8 @@ struct GroupShared {
     double LU[NX * NX];      // factors of I - gamma*J
     double Jcur[NX * NX];    // J(tn, y_n) for the sensitivity right-hand sides
     double ysh[NX];          // state handed from the state lane to the sensitivity lanes
+    double yj[NX];           // state handed to the out-of-line model functions (xdot, Jacobian)
+    double fout[NX];         // xdot returned by eval_xdot_shared
     double p[M::NP > 0 ? M::NP : 1];  // unscaled model parameters
     double k[M::NK > 0 ? M::NK : 1];  // constants (fixed parameters)
     double l[cv::L_MAX + 1];
@@ -179,6 +181,212 @@ struct GroupShared {
     int piv[NX];
     int plist[M::NP > 0 ? M::NP : 1];
 };
+
+
+// ---- out-of-line helpers (one copy of the code each; they touch only group-shared
+//      memory and scalars, so a real call costs a few registers) ------------------------
+/// pow() out of line: the step-size formulas call it at several places
+PB_HD_NOINLINE static double pb_pow(double x, double y) { return pow(x, y); }
+
+PB_HD_NOINLINE static double pb_div(double a, double b) { return a / b; }
+PB_HD_NOINLINE static double pb_rcp(double a) { return 1.0 / a; }
+
+/// xdot(t, sh->yj) -> sh->fout; returns false if a component is not finite (AMICI checkFinite,
+/// deps/AMICI/src/solver_cvodes.cpp:1149-1173)
+template <class M>
+PB_HD_NOINLINE static bool eval_xdot_shared(GroupShared<M>* sh, double t) {
+    M::xdot(sh->fout, t, sh->yj, sh->p, sh->k);
+    bool ok = true;
+    for (int i = 0; i < M::NX; ++i) ok = ok && isfinite(sh->fout[i]);
+    return ok;
+}
+
+/// max over the lanes of a group of a local sum of squares, then sqrt(. / n): the WRMS norm
+/// max_columns sqrt(mean((v*w)^2)) (N_VWrmsNorm; cvSensNorm cvodes.c:9427-9441), one copy of the
+/// shuffle sequence for all call sites
+template <class Grp>
+PB_HD_NOINLINE static double group_wrms(const Grp& g, double ssq_local, int n) {
+    return sqrt(g.max(ssq_local) / n);
+}
+
+/// J(t, y) -> Jdst (dense column-major, NX*NX), everything in group-shared memory
+template <class M>
+PB_HD_NOINLINE static bool eval_jac_shared(double* Jdst, double t, const double* y, const GroupShared<M>* sh) {
+    for (int i = 0; i < M::NX * M::NX; ++i) Jdst[i] = 0.0;
+    M::jac(Jdst, t, y, sh->p, sh->k);
+    bool ok = true;
+    for (int i = 0; i < M::NX * M::NX; ++i) ok = ok && isfinite(Jdst[i]);
+    return ok;
+}
+
+/// LU = I - gamma*Jsaved, factorised in place with partial pivoting, column-oriented
+/// (SUNDlsMat_denseGETRF, sundials_dense.c:82-148); the pivots are stored as reciprocals.
+/// Returns 0, or 1 on a zero pivot.
+template <class M>
+PB_HD_NOINLINE static int lu_factor_shared(GroupShared<M>* sh, double gamma) {
+    constexpr int NX = M::NX;
+    for (int c = 0; c < NX; ++c)
+        for (int r = 0; r < NX; ++r) sh->LU[r + c * NX] = (r == c ? 1.0 : 0.0) - gamma * sh->Jsaved[r + c * NX];
+    for (int k = 0; k < NX; ++k) {
+        double* col_k = sh->LU + k * NX;
+        int l = k;
+        for (int i = k + 1; i < NX; ++i)
+            if (fabs(col_k[i]) > fabs(col_k[l])) l = i;
+        sh->piv[k] = l;
+        if (col_k[l] == 0.0) return 1;
+        if (l != k) {
+            for (int i = 0; i < NX; ++i) {
+                const double t_ = sh->LU[l + i * NX];
+                sh->LU[l + i * NX] = sh->LU[k + i * NX];
+                sh->LU[k + i * NX] = t_;
+            }
+        }
+        const double mult = 1.0 / col_k[k];
+        for (int i = k + 1; i < NX; ++i) col_k[i] *= mult;
+        for (int j = k + 1; j < NX; ++j) {
+            double* col_j = sh->LU + j * NX;
+            const double a_kj = col_j[k];
+            if (a_kj != 0.0)
+                for (int i = k + 1; i < NX; ++i) col_j[i] -= a_kj * col_k[i];
+        }
+        col_k[k] = mult;
+    }
+    return 0;
+}
+
+/// cvSLdet (cvodes.c:8256-8556): dominant characteristic root from the STALD history (out of line)
+PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
+    int kmin = 0, kflag = 0;
+    double rat[5][4], rav[4], qkr[4], sigsq[4], smax[4], ssmax[4];
+    double drr[4], rrc[4], sqmx[4], qjk[4][4], vrat[5], qc[6][4], qco[6][4];
+    const double rrcut = 0.98, vrrtol = 1.0e-4, vrrt2 = 5.0e-4, sqtol = 1.0e-3, rrtol = 1.0e-2;
+    double rr = 0.0, sqmin = 0.0;
+    double ss[6][4];
+    for (int i = 1; i <= 5; ++i)
+        for (int k = 1; k <= 3; ++k) ss[i][k] = ssdat[i][k];
+    for (int k = 1; k <= 3; ++k) {
+        double smink = ss[1][k], smaxk = 0.0;
+        for (int i = 1; i <= 5; ++i) {
+            smink = fmin(smink, ss[i][k]);
+            smaxk = fmax(smaxk, ss[i][k]);
+        }
+        if (smink < cv::TINY * smaxk) return -1;
+        smax[k] = smaxk;
+        ssmax[k] = smaxk * smaxk;
+        double sumrat = 0.0, sumrsq = 0.0;
+        for (int i = 1; i <= 4; ++i) {
+            rat[i][k] = ss[i][k] / ss[i + 1][k];
+            sumrat += rat[i][k];
+            sumrsq += rat[i][k] * rat[i][k];
+        }
+        rav[k] = 0.25 * sumrat;
+        vrat[k] = fabs(0.25 * sumrsq - rav[k] * rav[k]);
+        qc[5][k] = ss[1][k] * ss[3][k] - ss[2][k] * ss[2][k];
+        qc[4][k] = ss[2][k] * ss[3][k] - ss[1][k] * ss[4][k];
+        qc[3][k] = 0.0;
+        qc[2][k] = ss[2][k] * ss[5][k] - ss[3][k] * ss[4][k];
+        qc[1][k] = ss[4][k] * ss[4][k] - ss[3][k] * ss[5][k];
+        for (int i = 1; i <= 5; ++i) qco[i][k] = qc[i][k];
+    }
+    const double vmin = fmin(vrat[1], fmin(vrat[2], vrat[3]));
+    const double vmax = fmax(vrat[1], fmax(vrat[2], vrat[3]));
+    if (vmin < vrrtol * vrrtol) {
+        if (vmax > vrrt2 * vrrt2) return -2;
+        rr = (rav[1] + rav[2] + rav[3]) / 3.0;
+        double drrmax = 0.0;
+        for (int k = 1; k <= 3; ++k) drrmax = fmax(drrmax, fabs(rav[k] - rr));
+        if (drrmax > vrrt2) return -3;
+        kflag = 1;
+    } else {
+        if (fabs(qco[1][1]) < cv::TINY * ssmax[1]) return -4;
+        double tem = qco[1][2] / qco[1][1];
+        for (int i = 2; i <= 5; ++i) qco[i][2] -= tem * qco[i][1];
+        qco[1][2] = 0.0;
+        tem = qco[1][3] / qco[1][1];
+        for (int i = 2; i <= 5; ++i) qco[i][3] -= tem * qco[i][1];
+        qco[1][3] = 0.0;
+        if (fabs(qco[2][2]) < cv::TINY * ssmax[2]) return -4;
+        tem = qco[2][3] / qco[2][2];
+        for (int i = 3; i <= 5; ++i) qco[i][3] -= tem * qco[i][2];
+        if (fabs(qco[4][3]) < cv::TINY * ssmax[3]) return -4;
+        rr = -qco[5][3] / qco[4][3];
+        if (rr < cv::TINY || rr > 100.0) return -5;
+        for (int k = 1; k <= 3; ++k) qkr[k] = qc[5][k] + rr * (qc[4][k] + rr * rr * (qc[2][k] + rr * qc[1][k]));
+        double sqmax = 0.0;
+        for (int k = 1; k <= 3; ++k) {
+            const double saqk = fabs(qkr[k]) / ssmax[k];
+            if (saqk > sqmax) sqmax = saqk;
+        }
+        if (sqmax < sqtol) {
+            kflag = 2;
+        } else {
+            for (int it = 1; it <= 3; ++it) {
+                for (int k = 1; k <= 3; ++k) {
+                    const double qp = qc[4][k] + rr * rr * (3.0 * qc[2][k] + rr * 4.0 * qc[1][k]);
+                    drr[k] = 0.0;
+                    if (fabs(qp) > cv::TINY * ssmax[k]) drr[k] = -qkr[k] / qp;
+                    rrc[k] = rr + drr[k];
+                }
+                for (int k = 1; k <= 3; ++k) {
+                    const double s = rrc[k];
+                    double sqmaxk = 0.0;
+                    for (int j = 1; j <= 3; ++j) {
+                        qjk[j][k] = qc[5][j] + s * (qc[4][j] + s * s * (qc[2][j] + s * qc[1][j]));
+                        const double saqj = fabs(qjk[j][k]) / ssmax[j];
+                        if (saqj > sqmaxk) sqmaxk = saqj;
+                    }
+                    sqmx[k] = sqmaxk;
+                }
+                sqmin = sqmx[1] + 1.0;
+                for (int k = 1; k <= 3; ++k) {
+                    if (sqmx[k] < sqmin) {
+                        kmin = k;
+                        sqmin = sqmx[k];
+                    }
+                }
+                rr = rrc[kmin];
+                if (sqmin < sqtol) {
+                    kflag = 3;
+                    break;
+                } else {
+                    for (int j = 1; j <= 3; ++j) qkr[j] = qjk[j][kmin];
+                }
+            }
+            if (sqmin > sqtol) return -6;
+        }
+    }
+    for (int k = 1; k <= 3; ++k) {
+        const double rsa = ss[1][k];
+        const double rsb = ss[2][k] * rr;
+        const double rsc = ss[3][k] * rr * rr;
+        const double rsd = ss[4][k] * rr * rr * rr;
+        const double rd1a = rsa - rsb, rd1b = rsb - rsc, rd1c = rsc - rsd;
+        const double rd2a = rd1a - rd1b, rd2b = rd1b - rd1c;
+        const double rd3a = rd2a - rd2b;
+        if (fabs(rd1b) < cv::TINY * smax[k]) return -7;
+        const double cest1 = -rd3a / rd1b;
+        if (cest1 < cv::TINY || cest1 > 4.0) return -7;
+        const double corr1 = (rd2b / cest1) / (rr * rr);
+        sigsq[k] = ss[3][k] + corr1;
+    }
+    if (sigsq[2] < cv::TINY) return -8;
+    const double ratp = sigsq[3] / sigsq[2];
+    const double ratm = sigsq[1] / sigsq[2];
+    const double qfac1 = 0.25 * (q * q - 1.0);
+    const double qfac2 = 2.0 / (q - 1.0);
+    const double bb = ratp * ratm - 1.0 - qfac1 * ratp;
+    const double tem = 1.0 - qfac2 * bb;
+    if (fabs(tem) < cv::TINY) return -8;
+    const double rrb = 1.0 / tem;
+    if (fabs(rrb - rr) > rrtol) return -9;
+    if (rr > rrcut) {
+        if (kflag == 1) kflag = 4;
+        if (kflag == 2) kflag = 5;
+        if (kflag == 3) kflag = 6;
+    }
+    return kflag;
+}
+
 
 /// Per-condition inputs (device pointers into the resident tables).
 struct ConditionIO {
@@ -198,6 +406,7 @@ template <class M, class Grp, int CPL>
 struct Bdf {
     static constexpr int NX = M::NX, NP = M::NP, NK = M::NK, NY = M::NY;
     static constexpr int G = Grp::G;
+    enum { PH_STATE = 0, PH_SENS = 1 };
 
     Grp g;
     GroupShared<M>* sh;
@@ -223,99 +432,49 @@ struct Bdf {
     int nfe, nsetups, nje, nni, nniS, nfSe, netf, netfS, ncfn, ncfnS, nor, qsum;
 
     PB_HD bool is_state(int m) const { return m == 0 && g.lane() == 0; }
+    /// column m of this lane takes part in the given phase (state corrector / sensitivity corrector)
+    PB_HD bool in_phase(int m, int phase) const { return act[m] && (is_state(m) == (phase == PH_STATE)); }
 
-    // ---------------------------------------------------------------- helpers
-    PB_HD static bool finite_vec(const double* v) {
-        bool ok = true;
-        PB_UNROLL
-        for (int i = 0; i < NX; ++i) ok = ok && isfinite(v[i]);
-        return ok;
-    }
-
-    /// WRMS norms of v: state column -> *ns_, max over sensitivity columns -> *nS
-    PB_HD void norms(const double (&v)[CPL][NX], double& nstate, double& nsens) const {
-        double ls = 0.0, lS = 0.0;
-        PB_UNROLL
+    // ---------------------------------------------------------------- norms
+    /// WRMS norm over the selected columns: max_c sqrt(mean((v_c*ewt_c)^2)).  Selecting only the
+    /// state column gives N_VWrmsNorm(v, ewt); only sensitivities gives cvSensNorm; both gives
+    /// cvSensUpdateNorm (cvodes.c:9427-9457).
+    PB_HD double wnorm(const double (&v)[CPL][NX], bool with_state, bool with_sens) const {
+        double loc = 0.0;
+        PB_ROLL
         for (int m = 0; m < CPL; ++m) {
             if (!act[m]) continue;
+            if (is_state(m) ? !with_state : !with_sens) continue;
             double s = 0.0;
             PB_UNROLL
             for (int i = 0; i < NX; ++i) {
                 const double prod = v[m][i] * ewt[m][i];
                 s += prod * prod;
             }
-            s = sqrt(s / NX);
-            if (is_state(m)) ls = s;
-            else if (s > lS) lS = s;
+            if (s > loc) loc = s;
         }
-        nstate = g.bcast0(ls);
-        nsens = sensi ? g.max(lS) : 0.0;
+        return group_wrms(g, loc, NX);
     }
-    PB_HD double norm_state(const double (&v)[CPL][NX]) const {
-        double ls = 0.0;
-        if (g.lane() == 0) {
-            double s = 0.0;
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) {
-                const double prod = v[0][i] * ewt[0][i];
-                s += prod * prod;
-            }
-            ls = sqrt(s / NX);
-        }
-        return g.bcast0(ls);
-    }
-    PB_HD double norm_sens(const double (&v)[CPL][NX]) const {
-        double lS = 0.0;
-        PB_UNROLL
-        for (int m = 0; m < CPL; ++m) {
-            if (!act[m] || is_state(m)) continue;
-            double s = 0.0;
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) {
-                const double prod = v[m][i] * ewt[m][i];
-                s += prod * prod;
-            }
-            s = sqrt(s / NX);
-            if (s > lS) lS = s;
-        }
-        return g.max(lS);
+    PB_HD double norm_phase(const double (&v)[CPL][NX], int phase) const {
+        return wnorm(v, phase == PH_STATE, phase == PH_SENS);
     }
     /// norm over all variables in the error test: state, plus sensitivities if errconS
-    PB_HD double norm_all(const double (&v)[CPL][NX]) const {
-        if (sensi && opt.errconS) {
-            double a, s;
-            norms(v, a, s);
-            return a > s ? a : s;  // cvSensUpdateNorm, cvodes.c:9449-9457
-        }
-        return norm_state(v);
-    }
+    PB_HD double norm_all(const double (&v)[CPL][NX]) const { return wnorm(v, true, sensi && opt.errconS); }
 
     /// cvEwtSetSS / cvSensEwtSetSS (cvodes.c:9118-9129, 9263-9279)
     PB_HD bool ewt_set() {
         bool ok = true;
-        PB_UNROLL
+        PB_ROLL
         for (int m = 0; m < CPL; ++m) {
             if (!act[m]) continue;
             PB_UNROLL
             for (int i = 0; i < NX; ++i) {
                 const double w = opt.rtol * fabs(zn[0][m][i]) + opt.atol;
                 ok = ok && (w > 0.0);
-                ewt[m][i] = 1.0 / w;
+                ewt[m][i] = pb_rcp(w);
             }
         }
         return g.max(ok ? 0.0 : 1.0) == 0.0;
-    }
-
-    /// state right-hand side on the state lane; returns 0 or RHSFUNC_RECVR (checkFinite,
-    /// deps/AMICI/src/solver_cvodes.cpp:1149-1173)
-    PB_HD int f_state(double t, const double* y, double* out) {
-        int bad = 0;
-        if (g.lane() == 0) {
-            M::xdot(out, t, y, sh->p, sh->k);
-            bad = finite_vec(out) ? 0 : 1;
-        }
-        nfe++;
-        return g.bcast0(bad) ? cv::RHSFUNC_RECVR : 0;
     }
 
     /// hand the state lane's vector to every lane through shared memory
@@ -331,86 +490,89 @@ struct Bdf {
     /// J(t, ysh) -> sh->Jcur by the state lane (Model_ODE::fsxdot at ip == 0,
     /// deps/AMICI/src/model_ode.cpp:492-498)
     PB_HD void refresh_Jcur(double t) {
-        if (g.lane() == 0) {
-            PB_UNROLL
-            for (int i = 0; i < NX * NX; ++i) sh->Jcur[i] = 0.0;
-            M::jac(sh->Jcur, t, sh->ysh, sh->p, sh->k);
-        }
+        if (g.lane() == 0) eval_jac_shared<M>(sh->Jcur, t, sh->ysh, sh);
         g.sync();
     }
 
-    /// sensitivity right-hand sides for all columns: out = dxdotdp(ip) + Jcur * s
-    /// (Model_ODE::fsxdot, model_ode.cpp:486-515); state is sh->ysh.
-    PB_HD int f_sens(double t, const double (&s)[CPL][NX], double (&out)[CPL][NX]) {
+    // ---------------------------------------------------------------- right-hand sides
+    /// THE right-hand-side evaluation (single copy in the instruction stream).  For the columns
+    /// of `phase`:  tmp = zn[0] + acor;  F = f(t, tmp)  (state: xdot; sensitivities:
+    /// dxdotdp(ip) + Jcur*tmp, Model_ODE::fsxdot model_ode.cpp:486-515, with sh->ysh / sh->Jcur
+    /// prepared by the caller);  b = raw ? F : rl1*zn[1] + acor - gamma*F  (cvNlsResidual
+    /// cvodes_nls.c:344-371; cvNlsResidualSensStg cvodes_nls_stg.c:377-421).
+    /// Returns 0, RHSFUNC_RECVR or SRHSFUNC_RECVR (non-finite result).
+    PB_HD int rhs(int phase, double t, bool raw) {
         double bad = 0.0;
-        PB_UNROLL
+        PB_ROLL
         for (int m = 0; m < CPL; ++m) {
-            if (!act[m] || is_state(m)) continue;
+            if (!in_phase(m, phase)) continue;
             PB_UNROLL
-            for (int i = 0; i < NX; ++i) out[m][i] = 0.0;
-            M::dxdotdp(out[m], t, sh->ysh, sh->p, sh->k, ipar[m]);
-            PB_UNROLL
-            for (int j = 0; j < NX; ++j) {
-                const double sj = s[m][j];
+            for (int i = 0; i < NX; ++i) tmp[m][i] = zn[0][m][i] + acor[m][i];
+            double F[NX];
+            if (phase == PH_STATE) {
                 PB_UNROLL
-                for (int r = 0; r < NX; ++r) out[m][r] += sh->Jcur[r + j * NX] * sj;
+                for (int i = 0; i < NX; ++i) sh->yj[i] = tmp[m][i];
+                if (!eval_xdot_shared<M>(sh, t)) bad = 1.0;
+                PB_UNROLL
+                for (int i = 0; i < NX; ++i) F[i] = sh->fout[i];
+            } else {
+                PB_UNROLL
+                for (int i = 0; i < NX; ++i) F[i] = 0.0;
+                M::dxdotdp(F, t, sh->ysh, sh->p, sh->k, ipar[m]);
+                PB_UNROLL
+                for (int j = 0; j < NX; ++j) {
+                    const double sj = tmp[m][j];
+                    PB_UNROLL
+                    for (int r = 0; r < NX; ++r) F[r] += sh->Jcur[r + j * NX] * sj;
+                }
+                bool ok = true;
+                PB_UNROLL
+                for (int i = 0; i < NX; ++i) ok = ok && isfinite(F[i]);
+                if (!ok) bad = 1.0;
             }
-            if (!finite_vec(out[m])) bad = 1.0;
+            PB_UNROLL
+            for (int i = 0; i < NX; ++i) b[m][i] = raw ? F[i] : (rl1 * zn[1][m][i] + acor[m][i]) - gamma * F[i];
         }
-        nfSe += ns;
-        return g.max(bad) != 0.0 ? cv::SRHSFUNC_RECVR : 0;
+        if (phase == PH_STATE) nfe++;
+        else nfSe += ns;
+        if (g.max(bad) != 0.0) return phase == PH_STATE ? cv::RHSFUNC_RECVR : cv::SRHSFUNC_RECVR;
+        return 0;
+    }
+
+    /// f(t, zn[0] + acor) for the state (into b), then -- if sensitivities take part -- the
+    /// sensitivity right-hand sides at that state with a fresh Jacobian (cvSensRhsWrapper with
+    /// AMICI's fsxdot).  Used by the cold paths: initialisation, cvHin, order-1 restart.
+    PB_HD int rhs_all_raw(double t, bool with_sens) {
+        int r = 0;
+        for (int phase_ = PH_STATE; phase_ <= PH_SENS; ++phase_) {
+            int phase = phase_;
+            PB_OPAQUE_INT(phase);
+            if (phase == PH_SENS) {
+                if (!with_sens) break;
+                publish_state(tmp[0]);
+                refresh_Jcur(t);
+            }
+            r = rhs(phase, t, true);
+            if (r) break;
+        }
+        return r;
     }
 
     // ---------------------------------------------------------------- linear algebra
-    /// cvLsSetup + cvLsLinSys + dense GETRF (cvodes_ls.c:1611-1708,1386-1470;
-    /// sundials_dense.c:82-148).  y = state the Jacobian is evaluated at.
-    PB_HD int lsetup(const double* y) {
-        const double dgamma = fabs((gamma / gammap) - 1.0);
+    /// cvLsSetup + cvLsLinSys + dense GETRF (cvodes_ls.c:1611-1708,1386-1470); the state the
+    /// Jacobian is evaluated at is sh->yj.
+    PB_HD int lsetup() {
+        const double dgamma = fabs(pb_div(gamma, gammap) - 1.0);
         const bool jbad = (nst == 0) || (nst >= nstlj + cv::MSBJ) ||
                           ((convfail == cv::FAIL_BAD_J) && (dgamma < cv::DGMAX_JBAD)) ||
                           (convfail == cv::FAIL_OTHER);
         int ret = 0;
+        g.sync();
         if (g.lane() == 0) {
             if (jbad) {
-                PB_UNROLL
-                for (int i = 0; i < NX * NX; ++i) sh->Jsaved[i] = 0.0;
-                M::jac(sh->Jsaved, tn, y, sh->p, sh->k);
-                bool ok = true;
-                for (int i = 0; i < NX * NX; ++i) ok = ok && isfinite(sh->Jsaved[i]);
-                if (!ok) ret = 1;
+                if (!eval_jac_shared<M>(sh->Jsaved, tn, sh->yj, sh)) ret = 1;
             }
-            if (ret == 0) {
-                // A = I - gamma*J
-                for (int c = 0; c < NX; ++c)
-                    for (int r = 0; r < NX; ++r)
-                        sh->LU[r + c * NX] = (r == c ? 1.0 : 0.0) - gamma * sh->Jsaved[r + c * NX];
-                // LU with partial pivoting, column-oriented
-                for (int k = 0; k < NX; ++k) {
-                    double* col_k = sh->LU + k * NX;
-                    int l = k;
-                    for (int i = k + 1; i < NX; ++i)
-                        if (fabs(col_k[i]) > fabs(col_k[l])) l = i;
-                    sh->piv[k] = l;
-                    if (col_k[l] == 0.0) { ret = 1; break; }
-                    if (l != k) {
-                        for (int i = 0; i < NX; ++i) {
-                            const double t_ = sh->LU[l + i * NX];
-                            sh->LU[l + i * NX] = sh->LU[k + i * NX];
-                            sh->LU[k + i * NX] = t_;
-                        }
-                    }
-                    const double mult = 1.0 / col_k[k];
-                    for (int i = k + 1; i < NX; ++i) col_k[i] *= mult;
-                    for (int j = k + 1; j < NX; ++j) {
-                        double* col_j = sh->LU + j * NX;
-                        const double a_kj = col_j[k];
-                        if (a_kj != 0.0)
-                            for (int i = k + 1; i < NX; ++i) col_j[i] -= a_kj * col_k[i];
-                    }
-                    // the back-substitution multiplies by the reciprocal pivot
-                    col_k[k] = mult;
-                }
-            }
+            if (ret == 0) ret = lu_factor_shared<M>(sh, gamma);
         }
         if (jbad) { nje++; nstlj = nst; }
         jcur = jbad;
@@ -444,108 +606,87 @@ struct Bdf {
         }
         x[0] *= sh->LU[0];
         if (gamrat != 1.0) {
-            const double sc = 2.0 / (1.0 + gamrat);
+            const double sc = pb_div(2.0, 1.0 + gamrat);
             PB_UNROLL
             for (int i = 0; i < NX; ++i) x[i] *= sc;
         }
     }
 
     // ---------------------------------------------------------------- BDF coefficients
-    /// cvSetBDF + cvSetTqBDF + cvSet (cvodes.c:6788-6879, 6617-6629); coefficients are
-    /// computed redundantly by every lane (a few dozen flops) and kept in shared memory.
+    /// cvSetBDF + cvSetTqBDF + cvSet (cvodes.c:6788-6879, 6617-6629); computed redundantly by
+    /// every lane (a few dozen flops), the arrays are kept in shared memory.
     PB_HD void cvset() {
         double l_[cv::L_MAX + 1];
         double alpha0, alpha0_hat, xi_inv, xistar_inv, hsum;
         l_[0] = l_[1] = xi_inv = xistar_inv = 1.0;
-        for (int i = 2; i <= cv::Q_MAX; ++i) l_[i] = 0.0;
-        l_[cv::L_MAX] = 0.0;
+        for (int i = 2; i <= cv::L_MAX; ++i) l_[i] = 0.0;
         alpha0 = alpha0_hat = -1.0;
         hsum = h;
         if (q > 1) {
             for (int j = 2; j < q; ++j) {
                 hsum += sh->tau[j - 1];
-                xi_inv = h / hsum;
-                alpha0 -= 1.0 / j;
+                xi_inv = pb_div(h, hsum);
+                alpha0 -= pb_rcp((double)j);
                 for (int i = j; i >= 1; --i) l_[i] += l_[i - 1] * xi_inv;
             }
-            alpha0 -= 1.0 / q;
+            alpha0 -= pb_rcp((double)q);
             xistar_inv = -l_[1] - alpha0;
             hsum += sh->tau[q - 1];
-            xi_inv = h / hsum;
+            xi_inv = pb_div(h, hsum);
             alpha0_hat = -l_[1] - xi_inv;
             for (int i = q; i >= 1; --i) l_[i] += l_[i - 1] * xistar_inv;
         }
-        // cvSetTqBDF
-        double tq_[6];
-        tq_[1] = sh->tq[1];
-        tq_[3] = sh->tq[3];
+        double tq1 = sh->tq[1], tq3 = sh->tq[3];
         const double A1 = 1.0 - alpha0_hat + alpha0;
         const double A2 = 1.0 + q * A1;
-        tq_[2] = fabs(A1 / (alpha0 * A2));
-        tq_[5] = fabs(A2 * xistar_inv / (l_[q] * xi_inv));
+        const double tq2 = fabs(pb_div(A1, alpha0 * A2));
+        const double tq5 = fabs(pb_div(A2 * xistar_inv, l_[q] * xi_inv));
         if (qwait == 1) {
             if (q > 1) {
-                const double C = xistar_inv / l_[q];
-                const double A3 = alpha0 + 1.0 / q;
+                const double C = pb_div(xistar_inv, l_[q]);
+                const double A3 = alpha0 + pb_rcp((double)q);
                 const double A4 = alpha0_hat + xi_inv;
-                const double Cpinv = (1.0 - A4 + A3) / A3;
-                tq_[1] = fabs(C * Cpinv);
+                const double Cpinv = pb_div(1.0 - A4 + A3, A3);
+                tq1 = fabs(C * Cpinv);
             } else {
-                tq_[1] = 1.0;
+                tq1 = 1.0;
             }
             hsum += sh->tau[q];
-            xi_inv = h / hsum;
-            const double A5 = alpha0 - (1.0 / (q + 1));
+            xi_inv = pb_div(h, hsum);
+            const double A5 = alpha0 - pb_rcp((double)(q + 1));
             const double A6 = alpha0_hat - xi_inv;
-            const double Cppinv = (1.0 - A6 + A5) / A2;
-            tq_[3] = fabs(Cppinv / (xi_inv * (q + 2) * A5));
+            const double Cppinv = pb_div(1.0 - A6 + A5, A2);
+            tq3 = fabs(pb_div(Cppinv, xi_inv * (q + 2) * A5));
         }
-        tq_[4] = cv::CORTES / tq_[2];
         g.sync();
         if (g.lane() == 0) {
             for (int i = 0; i <= cv::L_MAX; ++i) sh->l[i] = l_[i];
-            for (int i = 1; i <= 5; ++i) sh->tq[i] = tq_[i];
+            sh->tq[1] = tq1;
+            sh->tq[2] = tq2;
+            sh->tq[3] = tq3;
+            sh->tq[4] = pb_div(cv::CORTES, tq2);
+            sh->tq[5] = tq5;
         }
         g.sync();
-        rl1 = 1.0 / l_[1];
+        rl1 = pb_rcp(l_[1]);
         gamma = h * rl1;
         if (nst == 0) gammap = gamma;
-        gamrat = (nst > 0) ? gamma / gammap : 1.0;
+        gamrat = (nst > 0) ? pb_div(gamma, gammap) : 1.0;
     }
 
     // ---------------------------------------------------------------- history array
-    /// cvPredict (cvodes.c:6507-6597)
-    PB_HD void predict() {
-        tn += h;
-        if (tstopset) {
-            if ((tn - tstop) * h > 0.0) tn = tstop;
-        }
+    /// cvPredict (sgn = +1, cvodes.c:6507-6597: also advances tn) and cvRestore (sgn = -1,
+    /// cvodes.c:7373-7424) share one copy of the Pascal-triangle sweep.
+    PB_HD void shift_history(double sgn) {
         PB_UNROLL
         for (int k = 1; k <= cv::Q_MAX; ++k) {
             PB_UNROLL
             for (int j = cv::Q_MAX; j >= 1; --j) {
                 if (j >= k && j <= q && k <= q) {
-                    PB_UNROLL
+                    PB_ROLL
                     for (int m = 0; m < CPL; ++m) {
                         PB_UNROLL
-                        for (int i = 0; i < NX; ++i) zn[j - 1][m][i] += zn[j][m][i];
-                    }
-                }
-            }
-        }
-    }
-    /// cvRestore (cvodes.c:7373-7424)
-    PB_HD void restore(double saved_t) {
-        tn = saved_t;
-        PB_UNROLL
-        for (int k = 1; k <= cv::Q_MAX; ++k) {
-            PB_UNROLL
-            for (int j = cv::Q_MAX; j >= 1; --j) {
-                if (j >= k && j <= q && k <= q) {
-                    PB_UNROLL
-                    for (int m = 0; m < CPL; ++m) {
-                        PB_UNROLL
-                        for (int i = 0; i < NX; ++i) zn[j - 1][m][i] -= zn[j][m][i];
+                        for (int i = 0; i < NX; ++i) zn[j - 1][m][i] += sgn * zn[j][m][i];
                     }
                 }
             }
@@ -557,7 +698,7 @@ struct Bdf {
         PB_UNROLL
         for (int j = 1; j <= cv::Q_MAX; ++j) {
             if (j <= q) {
-                PB_UNROLL
+                PB_ROLL
                 for (int m = 0; m < CPL; ++m) {
                     PB_UNROLL
                     for (int i = 0; i < NX; ++i) zn[j][m][i] *= factor;
@@ -569,16 +710,59 @@ struct Bdf {
         hscale = h;
         nscon = 0;
     }
-    /// zn[j] += c_j * zn[src] for j = 2..jmax (N_VScaleAddMulti on columns 2..)
-    PB_HD void add_multiple_of(int src, const double* coef, int jmax) {
+    /// cvAdjustOrder -> cvIncreaseBDF / cvDecreaseBDF (cvodes.c:6134-6143, 6256-6351, 6363-6415),
+    /// one copy of the column update zn[j] += c_j * zn[src], j = 2..jmax.
+    PB_HD void adjust_order(int deltaq) {
+        if ((q == 2) && (deltaq != 1)) return;
+        double lc[cv::L_MAX + 1];
+        for (int i = 0; i <= cv::L_MAX; ++i) lc[i] = 0.0;
+        lc[2] = 1.0;
+        int src, jmax;
+        if (deltaq == 1) {
+            double alpha1 = 1.0, prod = 1.0, xiold = 1.0, alpha0 = -1.0;
+            double hsum = hscale;
+            for (int j = 1; j < q; ++j) {
+                hsum += sh->tau[j + 1];
+                const double xi = pb_div(hsum, hscale);
+                prod *= xi;
+                alpha0 -= pb_rcp((double)(j + 1));
+                alpha1 += pb_rcp(xi);
+                for (int i = j + 2; i >= 2; --i) lc[i] = lc[i] * xiold + lc[i - 1];
+                xiold = xi;
+            }
+            const double A1 = pb_div(-alpha0 - alpha1, prod);
+            // new column zn[L] = A1 * (saved correction in zn[qmax]); L = q+1 <= qmax
+            PB_UNROLL
+            for (int j = 2; j <= cv::Q_MAX; ++j) {
+                if (j == L) {
+                    PB_ROLL
+                    for (int m = 0; m < CPL; ++m) {
+                        PB_UNROLL
+                        for (int i = 0; i < NX; ++i) zn[j][m][i] = A1 * zn[cv::Q_MAX][m][i];
+                    }
+                }
+            }
+            src = L;
+            jmax = q;        // N_VScaleAddMulti(q-1, l+2, zn[L], zn+2, zn+2)
+        } else {
+            double hsum = 0.0;
+            for (int j = 1; j <= q - 2; ++j) {
+                hsum += sh->tau[j];
+                const double xi = pb_div(hsum, hscale);
+                for (int i = j + 2; i >= 2; --i) lc[i] = lc[i] * xi + lc[i - 1];
+            }
+            for (int j = 2; j < q; ++j) lc[j] = -lc[j];
+            src = q;
+            jmax = q - 1;    // zn[j] -= l[j]*zn[q], j = 2..q-1
+        }
         PB_UNROLL
         for (int s = 2; s <= cv::Q_MAX; ++s) {
             if (s != src) continue;
             PB_UNROLL
             for (int j = 2; j <= cv::Q_MAX; ++j) {
                 if (j <= jmax && j != s) {
-                    const double cj = coef[j];
-                    PB_UNROLL
+                    const double cj = lc[j];
+                    PB_ROLL
                     for (int m = 0; m < CPL; ++m) {
                         PB_UNROLL
                         for (int i = 0; i < NX; ++i) zn[j][m][i] += cj * zn[s][m][i];
@@ -587,339 +771,118 @@ struct Bdf {
             }
         }
     }
-    /// cvIncreaseBDF (cvodes.c:6256-6351): new column zn[L] from the saved correction zn[qmax]
-    PB_HD void increase_order() {
-        double lc[cv::L_MAX + 1];
-        for (int i = 0; i <= cv::L_MAX; ++i) lc[i] = 0.0;
-        double alpha1 = 1.0, prod = 1.0, xiold = 1.0, alpha0 = -1.0, xi;
-        lc[2] = 1.0;
-        double hsum = hscale;
-        if (q > 1) {
-            for (int j = 1; j < q; ++j) {
-                hsum += sh->tau[j + 1];
-                xi = hsum / hscale;
-                prod *= xi;
-                alpha0 -= 1.0 / (j + 1);
-                alpha1 += 1.0 / xi;
-                for (int i = j + 2; i >= 2; --i) lc[i] = lc[i] * xiold + lc[i - 1];
-                xiold = xi;
-            }
-        }
-        const double A1 = (-alpha0 - alpha1) / prod;
-        // zn[L] = A1 * zn[indx_acor = qmax]   (L = q+1 <= qmax)
-        PB_UNROLL
-        for (int j = 2; j <= cv::Q_MAX; ++j) {
-            if (j == L) {
-                PB_UNROLL
-                for (int m = 0; m < CPL; ++m) {
-                    PB_UNROLL
-                    for (int i = 0; i < NX; ++i) zn[j][m][i] = A1 * zn[cv::Q_MAX][m][i];
-                }
-            }
-        }
-        if (q > 1) add_multiple_of(L, lc, q);
-    }
-    /// cvDecreaseBDF (cvodes.c:6363-6415)
-    PB_HD void decrease_order() {
-        double lc[cv::L_MAX + 1];
-        for (int i = 0; i <= cv::L_MAX; ++i) lc[i] = 0.0;
-        lc[2] = 1.0;
-        double hsum = 0.0;
-        for (int j = 1; j <= q - 2; ++j) {
-            hsum += sh->tau[j];
-            const double xi = hsum / hscale;
-            for (int i = j + 2; i >= 2; --i) lc[i] = lc[i] * xi + lc[i - 1];
-        }
-        if (q > 2) {
-            for (int j = 2; j < q; ++j) lc[j] = -lc[j];
-            add_multiple_of(q, lc, q - 1);
-        }
-    }
-    /// cvAdjustOrder (cvodes.c:6134-6143)
-    PB_HD void adjust_order(int deltaq) {
-        if ((q == 2) && (deltaq != 1)) return;
-        if (deltaq == 1) increase_order();
-        else if (deltaq == -1) decrease_order();
-    }
-    /// cvAdjustParams (cvodes.c:6112-6122)
-    PB_HD void adjust_params() {
-        if (qprime != q) {
-            adjust_order(qprime - q);
-            q = qprime;
-            L = q + 1;
-            qwait = L;
-        }
-        rescale();
-    }
 
-    // ---------------------------------------------------------------- nonlinear solves
-    /// cvNlsResidual (cvodes_nls.c:344-371): b(state) = rl1*zn1 + acor - gamma*f(tn, zn0+acor)
-    PB_HD int residual_state() {
-        if (g.lane() == 0) {
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) tmp[0][i] = zn[0][0][i] + acor[0][i];
+    // ---------------------------------------------------------------- nonlinear solve
+    /// cvNls / cvStgrNls + SUNNonlinSolSolve_Newton + cvNlsConvTest{,SensStg} for the columns of
+    /// `phase` (cvodes.c:6894-7007, 7167-7210; sunnonlinsol_newton.c:176-335; cvodes_nls.c:
+    /// 298-342; cvodes_nls_stg.c:238-375).  The state corrector and the staggered sensitivity
+    /// corrector are the same Newton iteration on different columns with the same factors, so
+    /// they share one copy of the code.  On success the corrected vector is zn[0]+acor (left in
+    /// tmp for the state column).
+    PB_HD int nls(int phase, int nflag) {
+        bool setup_pending = false;
+        if (phase == PH_STATE) {
+            convfail = ((nflag == cv::FIRST_CALL) || (nflag == cv::PREV_ERR_FAIL)) ? cv::NO_FAILURES : cv::FAIL_OTHER;
+            setup_pending = (nflag == cv::PREV_CONV_FAIL) || (nflag == cv::PREV_ERR_FAIL) || (nst == 0) ||
+                            (nst >= nstlp + cv::MSBP) || (fabs(gamrat - 1.0) > cv::DGMAX_LSETUP);
         }
-        double ft[NX];
-        const int r = f_state(tn, tmp[0], ft);
-        if (r) return r;
-        if (g.lane() == 0) {
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) {
-                const double r1 = rl1 * zn[1][0][i] + acor[0][i];
-                b[0][i] = -gamma * ft[i] + r1;
-            }
-        }
-        return 0;
-    }
-
-    /// cvNls + SUNNonlinSolSolve_Newton for the state (cvodes.c:6894-7007;
-    /// sunnonlinsol_newton.c:176-335; cvNlsConvTest cvodes_nls.c:298-342)
-    PB_HD int nls_state(int nflag) {
-        convfail = ((nflag == cv::FIRST_CALL) || (nflag == cv::PREV_ERR_FAIL)) ? cv::NO_FAILURES : cv::FAIL_OTHER;
-        bool callSetup = (nflag == cv::PREV_CONV_FAIL) || (nflag == cv::PREV_ERR_FAIL) || (nst == 0) ||
-                         (nst >= nstlp + cv::MSBP) || (fabs(gamrat - 1.0) > cv::DGMAX_LSETUP);
-        if (g.lane() == 0) {
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) acor[0][i] = 0.0;
-        }
-        bool jbad = false;
-        int ret;
-        for (;;) {
-            ret = residual_state();
-            if (ret == 0 && callSetup) {
-                if (jbad) convfail = cv::FAIL_BAD_J;
-                const int lr = lsetup(tmp[0]);
-                jcurNLS = jcur;
-                gamrat = 1.0;
-                gammap = gamma;
-                crate = 1.0;
-                crateS = 1.0;
-                nstlp = nst;
-                if (lr != 0) ret = cv::CONV_RECVR;
-            }
-            if (ret == 0) {
-                int m = 0;
-                for (;;) {
-                    nni++;
-                    double del = 0.0;
-                    if (g.lane() == 0) {
-                        PB_UNROLL
-                        for (int i = 0; i < NX; ++i) b[0][i] = -b[0][i];
-                        lsolve_col(b[0]);
-                        PB_UNROLL
-                        for (int i = 0; i < NX; ++i) acor[0][i] += b[0][i];
-                    }
-                    del = norm_state(b);
-                    if (m > 0) crate = fmax(cv::CRDOWN * crate, del / delp);
-                    const double dcon = del * fmin(1.0, crate) / sh->tq[4];
-                    if (dcon <= 1.0) {
-                        acnrm = (m == 0) ? del : norm_state(acor);
-                        jcurNLS = false;
-                        // y = zn0 + acor; Jacobian data no longer current
-                        if (g.lane() == 0) {
-                            PB_UNROLL
-                            for (int i = 0; i < NX; ++i) tmp[0][i] = zn[0][0][i] + acor[0][i];
-                        }
-                        jcur = false;
-                        return 0;
-                    }
-                    if ((m >= 1) && (del > cv::RDIV * delp)) { ret = cv::CONV_RECVR; break; }
-                    delp = del;
-                    m++;
-                    if (m >= cv::NLS_MAXCOR) { ret = cv::CONV_RECVR; break; }
-                    ret = residual_state();
-                    if (ret != 0) break;
-                }
-            }
-            if ((ret > 0) && !jcurNLS) {
-                callSetup = true;
-                jbad = true;
-                if (g.lane() == 0) {
-                    PB_UNROLL
-                    for (int i = 0; i < NX; ++i) acor[0][i] = 0.0;
-                }
-                continue;
-            }
-            break;
-        }
-        return ret;
-    }
-
-    /// cvNlsResidualSensStg (cvodes_nls_stg.c:377-421) for every sensitivity column
-    PB_HD int residual_sens() {
-        PB_UNROLL
+        PB_ROLL
         for (int m = 0; m < CPL; ++m) {
-            if (!act[m] || is_state(m)) continue;
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) tmp[m][i] = zn[0][m][i] + acor[m][i];
-        }
-        double fs[CPL][NX];
-        const int r = f_sens(tn, tmp, fs);
-        if (r) return r;
-        PB_UNROLL
-        for (int m = 0; m < CPL; ++m) {
-            if (!act[m] || is_state(m)) continue;
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) b[m][i] = rl1 * zn[1][m][i] + acor[m][i] - gamma * fs[m][i];
-        }
-        return 0;
-    }
-
-    /// cvStgrNls + Newton for all sensitivities at once with the state's factors
-    /// (cvodes.c:7167-7210; cvodes_nls_stg.c:238-375).  y_n is in tmp[state] / sh->ysh.
-    PB_HD int nls_sens() {
-        bool callSetup = false;
-        bool jbad = false;
-        PB_UNROLL
-        for (int m = 0; m < CPL; ++m) {
-            if (!act[m] || is_state(m)) continue;
+            if (!in_phase(m, phase)) continue;
             PB_UNROLL
             for (int i = 0; i < NX; ++i) acor[m][i] = 0.0;
         }
-        int ret;
+        bool jbad = false;
+        bool top = true;  // residual at the top of a solve attempt: failures there are final
+        int m_it = 0;
         for (;;) {
-            ret = residual_sens();
-            if (ret == 0 && callSetup) {
+            int ret = rhs(phase, tn, false);
+            if (ret != 0 && top) return ret;
+            if (ret == 0 && setup_pending) {
                 if (jbad) convfail = cv::FAIL_BAD_J;
-                double ycur[NX];
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) ycur[i] = sh->ysh[i];
-                const int lr = lsetup(ycur);
-                jcurNLSS = jcur;
+                if (phase == PH_SENS) {  // Jacobian at the converged state (cv_y), cvodes_nls_stg.c:252
+                    g.sync();
+                    if (g.lane() == 0) {
+                        PB_UNROLL
+                        for (int i = 0; i < NX; ++i) sh->yj[i] = sh->ysh[i];
+                    }
+                }  // state phase: rhs() has just put zn[0]+acor into sh->yj
+                const int lr = lsetup();
+                setup_pending = false;
+                if (phase == PH_STATE) jcurNLS = jcur;
+                else jcurNLSS = jcur;
                 gamrat = 1.0;
                 gammap = gamma;
                 crate = 1.0;
                 crateS = 1.0;
                 nstlp = nst;
-                if (lr != 0) ret = cv::CONV_RECVR;
+                if (lr != 0) return cv::CONV_RECVR;
             }
+            top = false;
             if (ret == 0) {
-                int m_it = 0;
-                for (;;) {
-                    nniS++;
+                if (phase == PH_STATE) nni++;
+                else nniS++;
+                PB_ROLL
+                for (int m = 0; m < CPL; ++m) {
+                    if (!in_phase(m, phase)) continue;
                     PB_UNROLL
-                    for (int m = 0; m < CPL; ++m) {
-                        if (!act[m] || is_state(m)) continue;
-                        PB_UNROLL
-                        for (int i = 0; i < NX; ++i) b[m][i] = -b[m][i];
-                        lsolve_col(b[m]);
-                        PB_UNROLL
-                        for (int i = 0; i < NX; ++i) acor[m][i] += b[m][i];
-                    }
-                    const double Del = norm_sens(b);
-                    if (m_it > 0) crateS = fmax(cv::CRDOWN * crateS, Del / delp);
-                    const double dcon = Del * fmin(1.0, crateS) / sh->tq[4];
-                    if (dcon <= 1.0) {
-                        if (opt.errconS) acnrmS = (m_it == 0) ? Del : norm_sens(acor);
+                    for (int i = 0; i < NX; ++i) b[m][i] = -b[m][i];
+                    lsolve_col(b[m]);
+                    PB_UNROLL
+                    for (int i = 0; i < NX; ++i) acor[m][i] += b[m][i];
+                }
+                const double del = norm_phase(b, phase);
+                double cr = (phase == PH_STATE) ? crate : crateS;
+                if (m_it > 0) cr = fmax(cv::CRDOWN * cr, pb_div(del, delp));
+                if (phase == PH_STATE) crate = cr;
+                else crateS = cr;
+                const double dcon = pb_div(del * fmin(1.0, cr), sh->tq[4]);
+                if (dcon <= 1.0) {
+                    const double an = (m_it == 0) ? del : norm_phase(acor, phase);
+                    if (phase == PH_STATE) {
+                        acnrm = an;
+                        jcurNLS = false;
+                        PB_ROLL
+                        for (int m = 0; m < CPL; ++m) {
+                            if (!in_phase(m, phase)) continue;
+                            PB_UNROLL
+                            for (int i = 0; i < NX; ++i) tmp[m][i] = zn[0][m][i] + acor[m][i];
+                        }
+                    } else {
+                        if (opt.errconS) acnrmS = an;
                         jcurNLSS = false;
-                        jcur = false;
-                        return 0;
                     }
-                    if ((m_it >= 1) && (Del > cv::RDIV * delp)) { ret = cv::CONV_RECVR; break; }
-                    delp = Del;
+                    jcur = false;
+                    return 0;
+                }
+                if ((m_it >= 1) && (del > cv::RDIV * delp)) {
+                    ret = cv::CONV_RECVR;
+                } else {
+                    delp = del;
                     m_it++;
-                    if (m_it >= cv::NLS_MAXCOR) { ret = cv::CONV_RECVR; break; }
-                    ret = residual_sens();
-                    if (ret != 0) break;
+                    if (m_it >= cv::NLS_MAXCOR) ret = cv::CONV_RECVR;
+                    else continue;
                 }
             }
-            if ((ret > 0) && !jcurNLSS) {
-                callSetup = true;
+            // failure inside the iteration: retry once with a fresh Jacobian if it was stale
+            if ((ret > 0) && !((phase == PH_STATE) ? jcurNLS : jcurNLSS)) {
+                setup_pending = true;
                 jbad = true;
-                PB_UNROLL
+                top = true;
+                m_it = 0;
+                PB_ROLL
                 for (int m = 0; m < CPL; ++m) {
-                    if (!act[m] || is_state(m)) continue;
+                    if (!in_phase(m, phase)) continue;
                     PB_UNROLL
                     for (int i = 0; i < NX; ++i) acor[m][i] = 0.0;
                 }
                 continue;
             }
-            break;
+            return ret;
         }
-        return ret;
     }
 
     // ---------------------------------------------------------------- step control
-    /// cvHandleNFlag (cvodes.c:7309-7363)
-    PB_HD int handle_nflag(int& nflag, double saved_t, int& ncf, int& ncfn_total) {
-        if (nflag == 0) return cv::DO_ERROR_TEST;
-        ncfn_total++;
-        restore(saved_t);
-        if (nflag < 0) return nflag;
-        ncf++;
-        etamax = 1.0;
-        if ((fabs(h) <= 0.0 * cv::ONEPSM) || (ncf == cv::MXNCF)) {
-            if (nflag == cv::CONV_RECVR) return SIM_CONV_FAILURE;
-            if (nflag == cv::RHSFUNC_RECVR) return SIM_REPTD_RHSFUNC_ERR;
-            if (nflag == cv::SRHSFUNC_RECVR) return SIM_REPTD_SRHSFUNC_ERR;
-        }
-        eta = fmax(cv::ETA_CF, 0.0 / fabs(h));
-        nflag = cv::PREV_CONV_FAIL;
-        rescale();
-        return cv::PREDICT_AGAIN;
-    }
-
-    /// full sensitivity right-hand side at (t, y) incl. a fresh Jacobian (cvSensRhsWrapper with
-    /// AMICI's fsxdot): used at initialisation, in cvHin and on the order-1 restart
-    PB_HD int sens_rhs_at(double t, const double* y_state_lane, const double (&s)[CPL][NX], double (&out)[CPL][NX]) {
-        publish_state(y_state_lane);
-        refresh_Jcur(t);
-        return f_sens(t, s, out);
-    }
-
-    /// cvDoErrorTest (cvodes.c:7461-7614)
-    PB_HD int do_error_test(int& nflag, double saved_t, double acor_nrm, int& nef, int& netf_total, double& dsm) {
-        dsm = acor_nrm * sh->tq[2];
-        if (dsm <= 1.0) return 0;
-        nef++;
-        netf_total++;
-        nflag = cv::PREV_ERR_FAIL;
-        restore(saved_t);
-        if ((fabs(h) <= 0.0 * cv::ONEPSM) || (nef == cv::MXNEF)) return SIM_ERR_FAILURE;
-        etamax = 1.0;
-        if (nef <= cv::MXNEF1) {
-            eta = 1.0 / (pow(cv::BIAS2 * dsm, 1.0 / L) + cv::ADDON);
-            eta = fmax(cv::ETA_MIN_EF, fmax(eta, 0.0 / fabs(h)));
-            if (nef >= cv::SMALL_NEF) eta = fmin(eta, cv::ETA_MAX_EF);
-            rescale();
-            return cv::TRY_AGAIN;
-        }
-        if (q > 1) {
-            eta = fmax(cv::ETA_MIN_EF, 0.0 / fabs(h));
-            adjust_order(-1);
-            L = q;
-            q--;
-            qwait = L;
-            rescale();
-            return cv::TRY_AGAIN;
-        }
-        // already at order 1: restart, reload zn[1] from scratch
-        eta = fmax(cv::ETA_MIN_EF, 0.0 / fabs(h));
-        h *= eta;
-        hscale = h;
-        qwait = cv::LONG_WAIT;
-        nscon = 0;
-        double ft[NX];
-        int r = f_state(tn, zn[0][0], ft);
-        if (r) return SIM_UNREC_RHSFUNC_ERR;
-        if (g.lane() == 0) {
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) zn[1][0][i] = h * ft[i];
-        }
-        if (sensi) {
-            double fs[CPL][NX];
-            r = sens_rhs_at(tn, zn[0][0], zn[0], fs);
-            if (r) return SIM_UNREC_SRHSFUNC_ERR;
-            PB_UNROLL
-            for (int m = 0; m < CPL; ++m) {
-                if (!act[m] || is_state(m)) continue;
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) zn[1][m][i] = h * fs[m][i];
-            }
-        }
-        return cv::TRY_AGAIN;
-    }
-
     /// cvCompleteStep (cvodes.c:7634-7736)
     PB_HD void complete_step() {
         nst++;
@@ -936,7 +899,7 @@ struct Bdf {
         for (int j = 0; j <= cv::Q_MAX; ++j) {
             if (j <= q) {
                 const double lj = sh->l[j];
-                PB_UNROLL
+                PB_ROLL
                 for (int m = 0; m < CPL; ++m) {
                     PB_UNROLL
                     for (int i = 0; i < NX; ++i) zn[j][m][i] += lj * acor[m][i];
@@ -945,7 +908,7 @@ struct Bdf {
         }
         qwait--;
         if ((qwait == 1) && (q != cv::Q_MAX)) {
-            PB_UNROLL
+            PB_ROLL
             for (int m = 0; m < CPL; ++m) {
                 PB_UNROLL
                 for (int i = 0; i < NX; ++i) zn[cv::Q_MAX][m][i] = acor[m][i];
@@ -954,24 +917,7 @@ struct Bdf {
         }
     }
 
-    /// cvSetEta (cvodes.c:7798-7827)
-    PB_HD void set_eta() {
-        if ((eta > cv::ETA_MIN_FX) && (eta < cv::ETA_MAX_FX)) {
-            eta = 1.0;
-            hprime = h;
-        } else {
-            if (eta >= cv::ETA_MAX_FX) {
-                eta = fmin(eta, etamax);
-                // hmax_inv = 0: no upper bound on the step
-            } else {
-                eta = fmax(eta, cv::ETA_MIN);
-            }
-            hprime = h * eta;
-            if (qprime < q) nscon = 0;
-        }
-    }
-
-    /// cvPrepareNextStep with cvComputeEtaqm1 / cvComputeEtaqp1 / cvChooseEta
+    /// cvPrepareNextStep with cvSetEta, cvComputeEtaqm1 / cvComputeEtaqp1 / cvChooseEta
     /// (cvodes.c:7747-8000)
     PB_HD void prepare_next_step(double dsm) {
         if (etamax == 1.0) {
@@ -981,198 +927,71 @@ struct Bdf {
             eta = 1.0;
             return;
         }
-        etaq = 1.0 / (pow(cv::BIAS2 * dsm, 1.0 / L) + cv::ADDON);
-        if (qwait != 0) {
-            eta = etaq;
-            qprime = q;
-            set_eta();
-            return;
-        }
-        qwait = 2;
-        // etaqm1
-        etaqm1 = 0.0;
-        if (q > 1) {
-            double ddn = 0.0;
-            PB_UNROLL
-            for (int j = 2; j <= cv::Q_MAX; ++j)
-                if (j == q) ddn = norm_all(zn[j]);
-            ddn = ddn * sh->tq[1];
-            etaqm1 = 1.0 / (pow(cv::BIAS1 * ddn, 1.0 / q) + cv::ADDON);
-        }
-        // etaqp1
-        etaqp1 = 0.0;
-        if (q != cv::Q_MAX) {
-            if (saved_tq5 != 0.0) {
-                double hr = h / sh->tau[2], hp = 1.0;
-                for (int i = 0; i < L; ++i) hp *= hr;  // SUNRpowerI
-                const double cquot = (sh->tq[5] / saved_tq5) * hp;
+        etaq = pb_rcp(pb_pow(cv::BIAS2 * dsm, pb_rcp((double)L)) + cv::ADDON);
+        qprime = q;
+        eta = etaq;
+        if (qwait == 0) {
+            qwait = 2;
+            etaqm1 = 0.0;
+            if (q > 1) {
+                double ddn = 0.0;
                 PB_UNROLL
-                for (int m = 0; m < CPL; ++m) {
-                    PB_UNROLL
-                    for (int i = 0; i < NX; ++i) tmp[m][i] = -cquot * zn[cv::Q_MAX][m][i] + acor[m][i];
+                for (int j = 2; j <= cv::Q_MAX; ++j)
+                    if (j == q) ddn = norm_all(zn[j]);
+                ddn = ddn * sh->tq[1];
+                etaqm1 = pb_rcp(pb_pow(cv::BIAS1 * ddn, pb_rcp((double)q)) + cv::ADDON);
+            }
+            etaqp1 = 0.0;
+            if (q != cv::Q_MAX) {
+                if (saved_tq5 != 0.0) {
+                    const double hr = pb_div(h, sh->tau[2]);
+                    double hp = 1.0;
+                    for (int i = 0; i < L; ++i) hp *= hr;  // SUNRpowerI
+                    const double cquot = pb_div(sh->tq[5], saved_tq5) * hp;
+                    PB_ROLL
+                    for (int m = 0; m < CPL; ++m) {
+                        PB_UNROLL
+                        for (int i = 0; i < NX; ++i) tmp[m][i] = -cquot * zn[cv::Q_MAX][m][i] + acor[m][i];
+                    }
+                    double dup = norm_all(tmp);
+                    dup = dup * sh->tq[3];
+                    etaqp1 = pb_rcp(pb_pow(cv::BIAS3 * dup, pb_rcp((double)(L + 1))) + cv::ADDON);
                 }
-                double dup = norm_all(tmp);
-                dup = dup * sh->tq[3];
-                etaqp1 = 1.0 / (pow(cv::BIAS3 * dup, 1.0 / (L + 1)) + cv::ADDON);
             }
-        }
-        // cvChooseEta
-        const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
-        if ((etam > cv::ETA_MIN_FX) && (etam < cv::ETA_MAX_FX)) {
-            eta = 1.0;
-            qprime = q;
-        } else if (etam == etaq) {
-            eta = etaq;
-            qprime = q;
-        } else if (etam == etaqm1) {
-            eta = etaqm1;
-            qprime = q - 1;
-        } else {
-            eta = etaqp1;
-            qprime = q + 1;
-            // store Delta_n in zn[qmax] for the order increase (state always; sensitivities
-            // only if they take part in the error test, cvodes.c:7973-7987)
-            PB_UNROLL
-            for (int m = 0; m < CPL; ++m) {
-                if (!is_state(m) && !opt.errconS) continue;
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) zn[cv::Q_MAX][m][i] = acor[m][i];
-            }
-        }
-        set_eta();
-    }
-
-    /// cvSLdet (cvodes.c:8256-8556): dominant characteristic root from the STALD history
-    PB_HD int sldet() const {
-        int kmin = 0, kflag = 0;
-        double rat[5][4], rav[4], qkr[4], sigsq[4], smax[4], ssmax[4];
-        double drr[4], rrc[4], sqmx[4], qjk[4][4], vrat[5], qc[6][4], qco[6][4];
-        const double rrcut = 0.98, vrrtol = 1.0e-4, vrrt2 = 5.0e-4, sqtol = 1.0e-3, rrtol = 1.0e-2;
-        double rr = 0.0, sqmin = 0.0;
-        double ss[6][4];
-        for (int i = 1; i <= 5; ++i)
-            for (int k = 1; k <= 3; ++k) ss[i][k] = sh->ssdat[i][k];
-        for (int k = 1; k <= 3; ++k) {
-            double smink = ss[1][k], smaxk = 0.0;
-            for (int i = 1; i <= 5; ++i) {
-                smink = fmin(smink, ss[i][k]);
-                smaxk = fmax(smaxk, ss[i][k]);
-            }
-            if (smink < cv::TINY * smaxk) return -1;
-            smax[k] = smaxk;
-            ssmax[k] = smaxk * smaxk;
-            double sumrat = 0.0, sumrsq = 0.0;
-            for (int i = 1; i <= 4; ++i) {
-                rat[i][k] = ss[i][k] / ss[i + 1][k];
-                sumrat += rat[i][k];
-                sumrsq += rat[i][k] * rat[i][k];
-            }
-            rav[k] = 0.25 * sumrat;
-            vrat[k] = fabs(0.25 * sumrsq - rav[k] * rav[k]);
-            qc[5][k] = ss[1][k] * ss[3][k] - ss[2][k] * ss[2][k];
-            qc[4][k] = ss[2][k] * ss[3][k] - ss[1][k] * ss[4][k];
-            qc[3][k] = 0.0;
-            qc[2][k] = ss[2][k] * ss[5][k] - ss[3][k] * ss[4][k];
-            qc[1][k] = ss[4][k] * ss[4][k] - ss[3][k] * ss[5][k];
-            for (int i = 1; i <= 5; ++i) qco[i][k] = qc[i][k];
-        }
-        const double vmin = fmin(vrat[1], fmin(vrat[2], vrat[3]));
-        const double vmax = fmax(vrat[1], fmax(vrat[2], vrat[3]));
-        if (vmin < vrrtol * vrrtol) {
-            if (vmax > vrrt2 * vrrt2) return -2;
-            rr = (rav[1] + rav[2] + rav[3]) / 3.0;
-            double drrmax = 0.0;
-            for (int k = 1; k <= 3; ++k) drrmax = fmax(drrmax, fabs(rav[k] - rr));
-            if (drrmax > vrrt2) return -3;
-            kflag = 1;
-        } else {
-            if (fabs(qco[1][1]) < cv::TINY * ssmax[1]) return -4;
-            double tem = qco[1][2] / qco[1][1];
-            for (int i = 2; i <= 5; ++i) qco[i][2] -= tem * qco[i][1];
-            qco[1][2] = 0.0;
-            tem = qco[1][3] / qco[1][1];
-            for (int i = 2; i <= 5; ++i) qco[i][3] -= tem * qco[i][1];
-            qco[1][3] = 0.0;
-            if (fabs(qco[2][2]) < cv::TINY * ssmax[2]) return -4;
-            tem = qco[2][3] / qco[2][2];
-            for (int i = 3; i <= 5; ++i) qco[i][3] -= tem * qco[i][2];
-            if (fabs(qco[4][3]) < cv::TINY * ssmax[3]) return -4;
-            rr = -qco[5][3] / qco[4][3];
-            if (rr < cv::TINY || rr > 100.0) return -5;
-            for (int k = 1; k <= 3; ++k) qkr[k] = qc[5][k] + rr * (qc[4][k] + rr * rr * (qc[2][k] + rr * qc[1][k]));
-            double sqmax = 0.0;
-            for (int k = 1; k <= 3; ++k) {
-                const double saqk = fabs(qkr[k]) / ssmax[k];
-                if (saqk > sqmax) sqmax = saqk;
-            }
-            if (sqmax < sqtol) {
-                kflag = 2;
+            // cvChooseEta
+            const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
+            if ((etam > cv::ETA_MIN_FX) && (etam < cv::ETA_MAX_FX)) {
+                eta = 1.0;
+                qprime = q;
+            } else if (etam == etaq) {
+                eta = etaq;
+                qprime = q;
+            } else if (etam == etaqm1) {
+                eta = etaqm1;
+                qprime = q - 1;
             } else {
-                for (int it = 1; it <= 3; ++it) {
-                    for (int k = 1; k <= 3; ++k) {
-                        const double qp = qc[4][k] + rr * rr * (3.0 * qc[2][k] + rr * 4.0 * qc[1][k]);
-                        drr[k] = 0.0;
-                        if (fabs(qp) > cv::TINY * ssmax[k]) drr[k] = -qkr[k] / qp;
-                        rrc[k] = rr + drr[k];
-                    }
-                    for (int k = 1; k <= 3; ++k) {
-                        const double s = rrc[k];
-                        double sqmaxk = 0.0;
-                        for (int j = 1; j <= 3; ++j) {
-                            qjk[j][k] = qc[5][j] + s * (qc[4][j] + s * s * (qc[2][j] + s * qc[1][j]));
-                            const double saqj = fabs(qjk[j][k]) / ssmax[j];
-                            if (saqj > sqmaxk) sqmaxk = saqj;
-                        }
-                        sqmx[k] = sqmaxk;
-                    }
-                    sqmin = sqmx[1] + 1.0;
-                    for (int k = 1; k <= 3; ++k) {
-                        if (sqmx[k] < sqmin) {
-                            kmin = k;
-                            sqmin = sqmx[k];
-                        }
-                    }
-                    rr = rrc[kmin];
-                    if (sqmin < sqtol) {
-                        kflag = 3;
-                        break;
-                    } else {
-                        for (int j = 1; j <= 3; ++j) qkr[j] = qjk[j][kmin];
-                    }
+                eta = etaqp1;
+                qprime = q + 1;
+                // store Delta_n in zn[qmax] for the order increase (state always; sensitivities
+                // only if they take part in the error test, cvodes.c:7973-7987)
+                PB_ROLL
+                for (int m = 0; m < CPL; ++m) {
+                    if (!is_state(m) && !opt.errconS) continue;
+                    PB_UNROLL
+                    for (int i = 0; i < NX; ++i) zn[cv::Q_MAX][m][i] = acor[m][i];
                 }
-                if (sqmin > sqtol) return -6;
             }
         }
-        for (int k = 1; k <= 3; ++k) {
-            const double rsa = ss[1][k];
-            const double rsb = ss[2][k] * rr;
-            const double rsc = ss[3][k] * rr * rr;
-            const double rsd = ss[4][k] * rr * rr * rr;
-            const double rd1a = rsa - rsb, rd1b = rsb - rsc, rd1c = rsc - rsd;
-            const double rd2a = rd1a - rd1b, rd2b = rd1b - rd1c;
-            const double rd3a = rd2a - rd2b;
-            if (fabs(rd1b) < cv::TINY * smax[k]) return -7;
-            const double cest1 = -rd3a / rd1b;
-            if (cest1 < cv::TINY || cest1 > 4.0) return -7;
-            const double corr1 = (rd2b / cest1) / (rr * rr);
-            sigsq[k] = ss[3][k] + corr1;
+        // cvSetEta (hmax_inv = 0, hmin = 0)
+        if ((eta > cv::ETA_MIN_FX) && (eta < cv::ETA_MAX_FX)) {
+            eta = 1.0;
+            hprime = h;
+        } else {
+            if (eta >= cv::ETA_MAX_FX) eta = fmin(eta, etamax);
+            else eta = fmax(eta, cv::ETA_MIN);
+            hprime = h * eta;
+            if (qprime < q) nscon = 0;
         }
-        if (sigsq[2] < cv::TINY) return -8;
-        const double ratp = sigsq[3] / sigsq[2];
-        const double ratm = sigsq[1] / sigsq[2];
-        const double qfac1 = 0.25 * (q * q - 1.0);
-        const double qfac2 = 2.0 / (q - 1.0);
-        const double bb = ratp * ratm - 1.0 - qfac1 * ratp;
-        const double tem = 1.0 - qfac2 * bb;
-        if (fabs(tem) < cv::TINY) return -8;
-        const double rrb = 1.0 / tem;
-        if (fabs(rrb - rr) > rrtol) return -9;
-        if (rr > rrcut) {
-            if (kflag == 1) kflag = 4;
-            if (kflag == 2) kflag = 5;
-            if (kflag == 3) kflag = 6;
-        }
-        return kflag;
     }
 
     /// cvBDFStab (cvodes.c:8158-8218)
@@ -1181,12 +1000,15 @@ struct Bdf {
             double sqm1 = 0.0, sqm2 = 0.0;
             PB_UNROLL
             for (int j = 2; j <= cv::Q_MAX; ++j) {
-                if (j == q) sqm1 = norm_state(zn[j]);
-                if (j == q - 1) sqm2 = norm_state(zn[j]);
+                if (j == q || j == q - 1) {
+                    const double v = wnorm(zn[j], true, false);
+                    if (j == q) sqm1 = v;
+                    else sqm2 = v;
+                }
             }
             int factorial = 1;
             for (int i = 1; i <= q - 1; ++i) factorial *= i;
-            const double sq = factorial * q * (q + 1) * acnrm / fmax(sh->tq[5], cv::TINY);
+            const double sq = pb_div(factorial * q * (q + 1) * acnrm, fmax(sh->tq[5], cv::TINY));
             sqm1 *= factorial * q;
             sqm2 *= factorial;
             g.sync();
@@ -1201,7 +1023,7 @@ struct Bdf {
         }
         if (qprime >= q) {
             if ((q >= 3) && (nscon >= q + 5)) {
-                const int ldflag = sldet();
+                const int ldflag = sldet_shared(sh->ssdat, q);
                 if (ldflag > 3) {
                     qprime = q - 1;
                     eta = etaqm1;
@@ -1215,50 +1037,127 @@ struct Bdf {
         }
     }
 
-    /// cvStep (cvodes.c:5800-6094)
+    /// cvStep (cvodes.c:5800-6094) with cvHandleNFlag (:7309-7363) and cvDoErrorTest
+    /// (:7461-7614) folded into ONE failure handler, and cvAdjustParams (:6112-6122) folded into
+    /// the top of the attempt loop, so that every history operation (Pascal sweep, order change,
+    /// rescale) and both correctors exist once in the instruction stream: the first version of
+    /// this kernel was instruction-cache bound (profiles/r01_a_summary.txt).  The sequence of
+    /// operations per attempt is the reference's.
     PB_HD int step() {
         int ncf = 0, nef = 0, ncfS = 0, nefS = 0;
-        double dsm = 0.0;
-        if ((nst > 0) && (hprime != h)) adjust_params();
+        double dsm = 0.0, dsmS = 0.0;
         const double saved_t = tn;
         int nflag = cv::FIRST_CALL;
+        bool do_rescale = (nst > 0) && (hprime != h);
+        int dq = do_rescale ? (qprime - q) : 0;
+        bool undo = false, restart = false;
         for (;;) {
-            predict();
-            cvset();
-            nflag = nls_state(nflag);
-            int kflag = handle_nflag(nflag, saved_t, ncf, ncfn);
-            if (kflag == cv::PREDICT_AGAIN) continue;
-            if (kflag != cv::DO_ERROR_TEST) return kflag;
-            int eflag = do_error_test(nflag, saved_t, acnrm, nef, netf, dsm);
-            if (eflag == cv::TRY_AGAIN) continue;
-            if (eflag != 0) return eflag;
-            if (sensi) {
-                ncf = nef = 0;
-                // f at the converged y (cvodes.c:5947-5955) -- AMICI's sensitivity RHS does
-                // not use it, the evaluation is kept for the recoverable-failure semantics
-                double ft[NX];
-                const int fr = f_state(tn, tmp[0], ft);
-                if (fr) {
-                    nflag = cv::PREV_CONV_FAIL;
-                    // cvodes.c:5951-5955 goes straight back to the prediction without
-                    // restoring; the predictor then acts on the predicted array.
-                    continue;
+            if (undo) {
+                tn = saved_t;  // cvRestore
+            } else {
+                if (restart) {
+                    // already at order 1 after MXNEF1 error-test failures: reload zn[1] from
+                    // scratch at the reduced step (cvodes.c:7536-7613)
+                    restart = false;
+                    h *= eta;
+                    hscale = h;
+                    qwait = cv::LONG_WAIT;
+                    nscon = 0;
+                    if (reload_zn1()) return sensi ? SIM_UNREC_SRHSFUNC_ERR : SIM_UNREC_RHSFUNC_ERR;
                 }
-                publish_state(tmp[0]);
-                refresh_Jcur(tn);
-                nflag = nls_sens();
-                kflag = handle_nflag(nflag, saved_t, ncfS, ncfnS);
-                if (kflag == cv::PREDICT_AGAIN) continue;
-                if (kflag != cv::DO_ERROR_TEST) return kflag;
-                if (opt.errconS) {
-                    double dsmS;
-                    eflag = do_error_test(nflag, saved_t, acnrmS, nefS, netfS, dsmS);
-                    if (eflag == cv::TRY_AGAIN) continue;
-                    if (eflag != 0) return eflag;
-                    if (dsmS > dsm) dsm = dsmS;
+                if (dq != 0) {
+                    adjust_order(dq);
+                    q += dq;
+                    L = q + 1;
+                    qwait = L;
+                    dq = 0;
+                }
+                if (do_rescale) {
+                    rescale();
+                    do_rescale = false;
+                }
+                tn += h;  // cvPredict
+                if (tstopset && ((tn - tstop) * h > 0.0)) tn = tstop;
+            }
+            double sgn = undo ? -1.0 : 1.0;
+            PB_OPAQUE_F64(sgn);
+            shift_history(sgn);
+            if (undo) {
+                undo = false;
+                continue;
+            }
+            cvset();
+            int fail = 0;  // 1/3: corrector failure (state/sens); 2/4: error-test failure (state/sens)
+            int ret = 0;
+            for (int phase_ = PH_STATE; phase_ <= PH_SENS; ++phase_) {
+                int phase = phase_;
+                PB_OPAQUE_INT(phase);
+                if (phase == PH_SENS) {
+                    if (fail || !sensi) break;
+                    ncf = nef = 0;
+                    // f at the converged y (cvodes.c:5947-5955); AMICI's sensitivity RHS does not
+                    // use it -- kept for the recoverable-failure semantics
+                    if (g.lane() == 0) {
+                        PB_UNROLL
+                        for (int i = 0; i < NX; ++i) sh->yj[i] = tmp[0][i];
+                    }
+                    int bad = 0;
+                    if (g.lane() == 0) bad = eval_xdot_shared<M>(sh, tn) ? 0 : 1;
+                    nfe++;
+                    if (g.bcast0(bad)) { fail = 5; break; }
+                    publish_state(tmp[0]);
+                    refresh_Jcur(tn);
+                }
+                ret = nls(phase, nflag);
+                if (ret != 0) {
+                    fail = 1 + 2 * phase;
+                } else if (phase == PH_STATE) {
+                    dsm = acnrm * sh->tq[2];
+                    if (dsm > 1.0) fail = 2;
+                } else if (opt.errconS) {
+                    dsmS = acnrmS * sh->tq[2];
+                    if (dsmS > 1.0) fail = 4;
+                    else if (dsmS > dsm) dsm = dsmS;
                 }
             }
-            break;
+            if (!fail) break;
+            if (fail == 5) {  // cvodes.c:5951-5955: straight back to the prediction, no restore
+                nflag = cv::PREV_CONV_FAIL;
+                continue;
+            }
+            undo = true;
+            if (fail == 1 || fail == 3) {  // cvHandleNFlag
+                if (fail == 1) { ncfn++; ncf++; } else { ncfnS++; ncfS++; }
+                if (ret < 0) return ret;
+                etamax = 1.0;
+                if ((fabs(h) <= 0.0) || ((fail == 1 ? ncf : ncfS) == cv::MXNCF)) {
+                    if (ret == cv::CONV_RECVR) return SIM_CONV_FAILURE;
+                    if (ret == cv::RHSFUNC_RECVR) return SIM_REPTD_RHSFUNC_ERR;
+                    return SIM_REPTD_SRHSFUNC_ERR;
+                }
+                eta = cv::ETA_CF;  // max(eta_cf, hmin/|h|), hmin = 0
+                nflag = cv::PREV_CONV_FAIL;
+                do_rescale = true;
+            } else {  // cvDoErrorTest
+                int e;
+                if (fail == 2) { e = ++nef; netf++; } else { e = ++nefS; netfS++; }
+                nflag = cv::PREV_ERR_FAIL;
+                if ((fabs(h) <= 0.0) || (e == cv::MXNEF)) return SIM_ERR_FAILURE;
+                etamax = 1.0;
+                if (e <= cv::MXNEF1) {
+                    eta = pb_rcp(pb_pow(cv::BIAS2 * (fail == 2 ? dsm : dsmS), pb_rcp((double)L)) + cv::ADDON);
+                    eta = fmax(cv::ETA_MIN_EF, eta);
+                    if (e >= cv::SMALL_NEF) eta = fmin(eta, cv::ETA_MAX_EF);
+                    do_rescale = true;
+                } else if (q > 1) {
+                    eta = cv::ETA_MIN_EF;
+                    dq = -1;
+                    do_rescale = true;
+                } else {
+                    eta = cv::ETA_MIN_EF;
+                    restart = true;
+                }
+            }
         }
         complete_step();
         prepare_next_step(dsm);
@@ -1268,70 +1167,26 @@ struct Bdf {
         return 0;
     }
 
-    // ---------------------------------------------------------------- initial step
-    /// cvYddNorm (cvodes.c:5676-5773)
-    PB_HD int ydd_norm(double hg, double& yddnrm) {
-        if (g.lane() == 0) {
+    /// zn[1] = h * f(tn, zn[0]) for the state and (if any) the sensitivities; acor is scratch
+    PB_HD int reload_zn1() {
+        PB_ROLL
+        for (int m = 0; m < CPL; ++m) {
             PB_UNROLL
-            for (int i = 0; i < NX; ++i) tmp[0][i] = hg * zn[1][0][i] + zn[0][0][i];
+            for (int i = 0; i < NX; ++i) acor[m][i] = 0.0;
         }
-        const bool withS = sensi && opt.errconS;
-        if (withS) {
-            PB_UNROLL
-            for (int m = 0; m < CPL; ++m) {
-                if (!act[m] || is_state(m)) continue;
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) tmp[m][i] = hg * zn[1][m][i] + zn[0][m][i];
-            }
-        }
-        double ft[NX];
-        int r = f_state(tn + hg, tmp[0], ft);
+        const int r = rhs_all_raw(tn, sensi);
         if (r) return r;
-        double fs[CPL][NX];
-        if (withS) {
-            r = sens_rhs_at(tn + hg, tmp[0], tmp, fs);
-            if (r) return r;
-        }
-        PB_UNROLL
+        PB_ROLL
         for (int m = 0; m < CPL; ++m) {
             if (!act[m]) continue;
-            if (is_state(m)) {
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) b[m][i] = (1.0 / hg) * ft[i] + (-1.0 / hg) * zn[1][m][i];
-            } else if (withS) {
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) b[m][i] = (1.0 / hg) * fs[m][i] + (-1.0 / hg) * zn[1][m][i];
-            } else {
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) b[m][i] = 0.0;
-            }
+            PB_UNROLL
+            for (int i = 0; i < NX; ++i) zn[1][m][i] = h * b[m][i];
         }
-        yddnrm = norm_all(b);
         return 0;
     }
 
-    /// cvUpperBoundH0 (cvodes.c:5558-5665)
-    PB_HD double upper_bound_h0(double tdist) const {
-        double hub_inv = 0.0;
-        const bool withS = sensi && opt.errconS;
-        PB_UNROLL
-        for (int m = 0; m < CPL; ++m) {
-            if (!act[m]) continue;
-            if (!is_state(m) && !withS) continue;
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) {
-                const double den = cv::HUB_FACTOR * fabs(zn[0][m][i]) + 1.0 / ewt[m][i];
-                const double v = fabs(zn[1][m][i]) / den;
-                if (v > hub_inv) hub_inv = v;
-            }
-        }
-        hub_inv = g.max(hub_inv);
-        double hub = cv::HUB_FACTOR * tdist;
-        if (hub * hub_inv > 1.0) hub = 1.0 / hub_inv;
-        return hub;
-    }
-
-    /// cvHin (cvodes.c:5436-5549)
+    // ---------------------------------------------------------------- initial step
+    /// cvHin with cvUpperBoundH0 and cvYddNorm (cvodes.c:5436-5773); zn[1] holds y'(t0) unscaled.
     PB_HD int hin(double tout) {
         const double tdiff = tout - tn;
         if (tdiff == 0.0) return SIM_TOO_CLOSE;
@@ -1340,22 +1195,59 @@ struct Bdf {
         const double tround = cv::UROUND * fmax(fabs(tn), fabs(tout));
         if (tdist < 2.0 * tround) return SIM_TOO_CLOSE;
         const double hlb = cv::HLB_FACTOR * tround;
-        const double hub = upper_bound_h0(tdist);
+        const bool withS = sensi && opt.errconS;
+        // cvUpperBoundH0
+        double hub_inv = 0.0;
+        PB_ROLL
+        for (int m = 0; m < CPL; ++m) {
+            if (!act[m]) continue;
+            if (!is_state(m) && !withS) continue;
+            PB_UNROLL
+            for (int i = 0; i < NX; ++i) {
+                const double den = cv::HUB_FACTOR * fabs(zn[0][m][i]) + pb_rcp(ewt[m][i]);
+                const double v = pb_div(fabs(zn[1][m][i]), den);
+                if (v > hub_inv) hub_inv = v;
+            }
+        }
+        hub_inv = g.max(hub_inv);
+        double hub = cv::HUB_FACTOR * tdist;
+        if (hub * hub_inv > 1.0) hub = pb_rcp(hub_inv);
         double hg = sqrt(hlb * hub);
         if (hub < hlb) {
             h = (sign == -1) ? -hg : hg;
             return 0;
         }
-        double hs = hg, hnew = hg, yddnrm = 0.0;
+        double hs = hg, hnew = hg;
         for (int count1 = 1; count1 <= cv::HIN_MAX_ITERS; ++count1) {
             bool hgOK = false;
             int retval = 0;
+            double yddnrm = 0.0;
             for (int count2 = 1; count2 <= cv::HIN_MAX_ITERS; ++count2) {
+                // cvYddNorm: f at (tn + hg, zn0 + hg*zn1), difference quotient, WRMS norm
                 const double hgs = hg * sign;
-                retval = ydd_norm(hgs, yddnrm);
-                if (retval < 0) return retval;
-                if (retval == 0) { hgOK = true; break; }
+                PB_ROLL
+                for (int m = 0; m < CPL; ++m) {
+                    PB_UNROLL
+                    for (int i = 0; i < NX; ++i) acor[m][i] = hgs * zn[1][m][i];
+                }
+                retval = rhs_all_raw(tn + hgs, withS);
+                if (retval == 0) {
+                    const double hinv = pb_rcp(hgs);
+                    PB_ROLL
+                    for (int m = 0; m < CPL; ++m) {
+                        PB_UNROLL
+                        for (int i = 0; i < NX; ++i) b[m][i] = hinv * b[m][i] + (-hinv) * zn[1][m][i];
+                    }
+                    yddnrm = norm_all(b);
+                    hgOK = true;
+                    break;
+                }
                 hg *= 0.2;
+            }
+            PB_ROLL
+            for (int m = 0; m < CPL; ++m) {
+                PB_UNROLL
+                for (int i = 0; i < NX; ++i) acor[m][i] = 0.0;
             }
             if (!hgOK) {
                 if (count1 <= 2) return retval == cv::RHSFUNC_RECVR ? SIM_REPTD_RHSFUNC_ERR : SIM_REPTD_SRHSFUNC_ERR;
@@ -1363,9 +1255,9 @@ struct Bdf {
                 break;
             }
             hs = hg;
-            hnew = (yddnrm * hub * hub > 2.0) ? sqrt(2.0 / yddnrm) : sqrt(hg * hub);
+            hnew = (yddnrm * hub * hub > 2.0) ? sqrt(pb_div(2.0, yddnrm)) : sqrt(hg * hub);
             if (count1 == cv::HIN_MAX_ITERS) break;
-            const double hrat = hnew / hg;
+            const double hrat = pb_div(hnew, hg);
             if ((hrat > 0.5) && (hrat < 2.0)) break;
             if ((count1 > 1) && (hrat > 2.0)) { hnew = hg; break; }
             hg = hnew;
@@ -1390,31 +1282,16 @@ struct Bdf {
         const int mxstep = opt.maxsteps - nst;
         if (nst == 0) {
             if (!ewt_set()) return SIM_ILL_INPUT;
-            double ft[NX];
-            int r = f_state(tn, zn[0][0], ft);
-            if (r) return SIM_FIRST_RHSFUNC_ERR;
-            if (g.lane() == 0) {
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) zn[1][0][i] = ft[i];
-            }
-            if (sensi) {
-                double fs[CPL][NX];
-                r = sens_rhs_at(tn, zn[0][0], zn[0], fs);
-                if (r) return SIM_FIRST_SRHSFUNC_ERR;
-                PB_UNROLL
-                for (int m = 0; m < CPL; ++m) {
-                    if (!act[m] || is_state(m)) continue;
-                    PB_UNROLL
-                    for (int i = 0; i < NX; ++i) zn[1][m][i] = fs[m][i];
-                }
-            }
+            h = 1.0;  // zn[1] = f(t0, y0), znS[1] = fS(t0, y0, yS0), unscaled
+            const int r = reload_zn1();
+            if (r) return r == cv::RHSFUNC_RECVR ? SIM_FIRST_RHSFUNC_ERR : SIM_FIRST_SRHSFUNC_ERR;
             if ((tstop - tn) * (tout - tn) <= 0.0) return SIM_ILL_INPUT;
             const int hr = hin(tout);
             if (hr != 0) return hr;
             if ((tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
             hscale = h;
             hprime = h;
-            PB_UNROLL
+            PB_ROLL
             for (int m = 0; m < CPL; ++m) {
                 PB_UNROLL
                 for (int i = 0; i < NX; ++i) zn[1][m][i] *= h;
@@ -1427,7 +1304,7 @@ struct Bdf {
                 return cv::TSTOP_RETURN;
             } else if ((tn + hprime - tstop) * h > 0.0) {
                 hprime = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
-                eta = hprime / h;
+                eta = pb_div(hprime, h);
             }
         }
         int nstloc = 0;
@@ -1448,7 +1325,7 @@ struct Bdf {
                 return cv::TSTOP_RETURN;
             } else if ((tn + hprime - tstop) * h > 0.0) {
                 hprime = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
-                eta = hprime / h;
+                eta = pb_div(hprime, h);
             }
             if ((tn - tout) * h >= 0.0) return cv::TSTOP_RETURN;
         }
@@ -1522,7 +1399,7 @@ struct Bdf {
                 dJydx[ix] = a;
             }
         }
-        PB_UNROLL
+        PB_ROLL
         for (int m = 0; m < CPL; ++m) {
             if (!act[m] || is_state(m)) continue;
             double dydp[NY], dsdp[NY];
@@ -1551,7 +1428,7 @@ struct Bdf {
         opt.atol = atol;
         ns = io.ns;
         sensi = ns > 0;
-        PB_UNROLL
+        PB_ROLL
         for (int m = 0; m < CPL; ++m) {
             const int c = g.lane() + m * G;
             act[m] = c <= ns;
@@ -1560,13 +1437,13 @@ struct Bdf {
         // Model::initialize: x0, sx0 (deps/AMICI/src/model.cpp:249-275)
         PB_UNROLL
         for (int j = 0; j < cv::L_MAX; ++j) {
-            PB_UNROLL
+            PB_ROLL
             for (int m = 0; m < CPL; ++m) {
                 PB_UNROLL
                 for (int i = 0; i < NX; ++i) zn[j][m][i] = 0.0;
             }
         }
-        PB_UNROLL
+        PB_ROLL
         for (int m = 0; m < CPL; ++m) {
             PB_UNROLL
             for (int i = 0; i < NX; ++i) { acor[m][i] = 0.0; ewt[m][i] = 1.0; tmp[m][i] = 0.0; b[m][i] = 0.0; }
@@ -1598,7 +1475,7 @@ struct Bdf {
 
         double llh = 0.0;
         double sllh[CPL];
-        PB_UNROLL
+        PB_ROLL
         for (int m = 0; m < CPL; ++m) sllh[m] = 0.0;
         int status = SIM_SUCCESS;
         for (int it = 0; it < io.nt; ++it) {
@@ -1632,7 +1509,7 @@ struct Bdf {
             // parameter-scale factor (it owns pscale); nothing to do here.
         }
         llh_out = g.bcast0(llh);
-        PB_UNROLL
+        PB_ROLL
         for (int m = 0; m < CPL; ++m) sllh_out[m] = sllh[m];
         return status;
     }

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(THREADS) simulate_kernel(const KernelArgs a) {
                 a.sllh[(size_t)r * M::NP + i] = 0.0;
             }
             grp.sync();
-#pragma unroll
+#pragma unroll 1
             for (int m = 0; m < CPL; ++m) {
                 const int col = lane + m * G;
                 if (col < 1 || col > io.ns) continue;
@@ -266,6 +266,10 @@ int launch_model(const KernelArgs& a, int lanes, int sm_count, cudaStream_t stre
     if (!a.want_grad) {
         if (lanes_used) *lanes_used = 1;
         return launch_one<M, 1, 1>(a, sm_count, stream, grid_used, block_used);
+    }
+    if (lanes == 1) {  // one thread per condition: all columns in the thread's local memory
+        if (lanes_used) *lanes_used = 1;
+        return launch_one<M, 1, NCOL>(a, sm_count, stream, grid_used, block_used);
     }
     if (lanes == 32 && G0 != 32) {
         if (lanes_used) *lanes_used = 32;

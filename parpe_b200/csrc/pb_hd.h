@@ -10,10 +10,25 @@
 #define PB_HD __host__ __device__ __forceinline__
 #define PB_HD_NOINLINE __host__ __device__ __noinline__
 #define PB_UNROLL _Pragma("unroll")
+// loops over the columns of a lane: never unrolled.  With one column per lane the trip count
+// is 1 and the loop folds away; with several columns per lane (few lanes per condition) the
+// body is emitted once and the columns live in local memory.
+#define PB_ROLL _Pragma("unroll 1")
 #else
 #define PB_HD inline
 #define PB_HD_NOINLINE
 #define PB_UNROLL
+#define PB_ROLL
+#endif
+
+// Make a value opaque to the optimiser: stops it from cloning a large code region once per
+// possible value of a flag (the kernels are instruction-cache sensitive).
+#if defined(__CUDA_ARCH__)
+#define PB_OPAQUE_INT(v) asm volatile("" : "+r"(v))
+#define PB_OPAQUE_F64(v) asm volatile("" : "+d"(v))
+#else
+#define PB_OPAQUE_INT(v) asm volatile("" : "+r"(v))
+#define PB_OPAQUE_F64(v) asm volatile("" : "+x"(v))
 #endif
 
 #endif
