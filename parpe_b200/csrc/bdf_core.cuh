@@ -19,15 +19,19 @@
 //
 //   * a condition is owned by a group of G lanes of one warp (G = 1..32);
 //   * the state vector and every sensitivity vector is a *column*; column c is
-//     held by lane (c mod G), entirely in registers, for all Nordsieck orders
-//     (zn[0..5][column][NX]); CPL = ceil((1+NP)/G) columns per lane;
-//   * vector operations are therefore lane-local and fully unrolled; norms are
-//     warp-shuffle reductions (max over sensitivity columns, broadcast of the
-//     state column);
+//     processed by lane (c mod G);
+//   * the Nordsieck history zn[0..5], the accumulated correction and the error
+//     weights of all columns live in the group's slice of shared memory as
+//     [order][state index][column] with the column index fastest, so the lanes of
+//     a group touch consecutive 8-byte words (conflict-free) and every history
+//     operation is a short rolled loop: the first version of this kernel kept
+//     the columns in registers with fully unrolled code and was instruction-fetch
+//     bound (profiles/r01_a_summary.txt);
+//   * norms are warp-shuffle reductions (max over the lanes of a group);
 //   * the Jacobian, its LU factors and the group-uniform BDF coefficient arrays
-//     live once per group in shared memory (GroupShared); the state lane
-//     factorises, every lane back-substitutes its own columns against the same
-//     factors (the staggered corrector's "same matrix, nplist right-hand sides");
+//     live once per group in shared memory; the state lane factorises, every
+//     lane back-substitutes its own columns against the same factors (the
+//     staggered corrector's "same matrix, nplist right-hand sides");
 //   * model functions are the generated __host__ __device__ code of
 //     csrc/models/<name>.cuh.
 //
@@ -162,14 +166,22 @@ struct LaneGroup {
 };
 #endif
 
-/// Group-uniform state: one copy per condition (shared memory on the device).
+/// Per-condition working set: one copy per lane group (shared memory on the device).
 template <class M>
 struct GroupShared {
     static constexpr int NX = M::NX;
+    static constexpr int NC = M::NP + 1;  // columns: state + one per model parameter
+    // column data, [..][state index][column], column fastest
+    double zn[cv::L_MAX][NX][NC];  // Nordsieck history
+    double acor[NX][NC];           // accumulated corrector update
+    double ewt[NX][NC];            // error weights
+    double b[NX][NC];              // residual / Newton update
+    double sllh[NC];               // d llh / d p accumulator per sensitivity column
+    // group-uniform data
     double Jsaved[NX * NX];  // Jacobian at its last evaluation (cvLs savedJ)
     double LU[NX * NX];      // factors of I - gamma*J
     double Jcur[NX * NX];    // J(tn, y_n) for the sensitivity right-hand sides
-    double ysh[NX];          // state handed from the state lane to the sensitivity lanes
+    double ysh[NX];          // converged state, read by the sensitivity lanes
     double yj[NX];           // state handed to the out-of-line model functions (xdot, Jacobian)
     double fout[NX];         // xdot returned by eval_xdot_shared
     double p[M::NP > 0 ? M::NP : 1];  // unscaled model parameters
@@ -179,15 +191,13 @@ struct GroupShared {
     double tq[6];
     double ssdat[6][4];      // STALD history (cvBDFStab)
     int piv[NX];
+    int perm[NX];            // row order after all pivot swaps: (P b)[i] = b[perm[i]]
     int plist[M::NP > 0 ? M::NP : 1];
 };
 
-
 // ---- out-of-line helpers (one copy of the code each; they touch only group-shared
 //      memory and scalars, so a real call costs a few registers) ------------------------
-/// pow() out of line: the step-size formulas call it at several places
 PB_HD_NOINLINE static double pb_pow(double x, double y) { return pow(x, y); }
-
 PB_HD_NOINLINE static double pb_div(double a, double b) { return a / b; }
 PB_HD_NOINLINE static double pb_rcp(double a) { return 1.0 / a; }
 
@@ -197,13 +207,16 @@ template <class M>
 PB_HD_NOINLINE static bool eval_xdot_shared(GroupShared<M>* sh, double t) {
     M::xdot(sh->fout, t, sh->yj, sh->p, sh->k);
     bool ok = true;
+    PB_ROLL
     for (int i = 0; i < M::NX; ++i) ok = ok && isfinite(sh->fout[i]);
     return ok;
 }
 
+template <class Grp>
+PB_HD_NOINLINE static double group_max(const Grp& g, double v) { return g.max(v); }
+
 /// max over the lanes of a group of a local sum of squares, then sqrt(. / n): the WRMS norm
-/// max_columns sqrt(mean((v*w)^2)) (N_VWrmsNorm; cvSensNorm cvodes.c:9427-9441), one copy of the
-/// shuffle sequence for all call sites
+/// max_columns sqrt(mean((v*w)^2)) (N_VWrmsNorm; cvSensNorm cvodes.c:9427-9441)
 template <class Grp>
 PB_HD_NOINLINE static double group_wrms(const Grp& g, double ssq_local, int n) {
     return sqrt(g.max(ssq_local) / n);
@@ -212,9 +225,11 @@ PB_HD_NOINLINE static double group_wrms(const Grp& g, double ssq_local, int n) {
 /// J(t, y) -> Jdst (dense column-major, NX*NX), everything in group-shared memory
 template <class M>
 PB_HD_NOINLINE static bool eval_jac_shared(double* Jdst, double t, const double* y, const GroupShared<M>* sh) {
+    PB_ROLL
     for (int i = 0; i < M::NX * M::NX; ++i) Jdst[i] = 0.0;
     M::jac(Jdst, t, y, sh->p, sh->k);
     bool ok = true;
+    PB_ROLL
     for (int i = 0; i < M::NX * M::NX; ++i) ok = ok && isfinite(Jdst[i]);
     return ok;
 }
@@ -225,16 +240,21 @@ PB_HD_NOINLINE static bool eval_jac_shared(double* Jdst, double t, const double*
 template <class M>
 PB_HD_NOINLINE static int lu_factor_shared(GroupShared<M>* sh, double gamma) {
     constexpr int NX = M::NX;
+    PB_ROLL
     for (int c = 0; c < NX; ++c)
+        PB_ROLL
         for (int r = 0; r < NX; ++r) sh->LU[r + c * NX] = (r == c ? 1.0 : 0.0) - gamma * sh->Jsaved[r + c * NX];
+    PB_ROLL
     for (int k = 0; k < NX; ++k) {
         double* col_k = sh->LU + k * NX;
         int l = k;
+        PB_ROLL
         for (int i = k + 1; i < NX; ++i)
             if (fabs(col_k[i]) > fabs(col_k[l])) l = i;
         sh->piv[k] = l;
         if (col_k[l] == 0.0) return 1;
         if (l != k) {
+            PB_ROLL
             for (int i = 0; i < NX; ++i) {
                 const double t_ = sh->LU[l + i * NX];
                 sh->LU[l + i * NX] = sh->LU[k + i * NX];
@@ -242,14 +262,25 @@ PB_HD_NOINLINE static int lu_factor_shared(GroupShared<M>* sh, double gamma) {
             }
         }
         const double mult = 1.0 / col_k[k];
+        PB_ROLL
         for (int i = k + 1; i < NX; ++i) col_k[i] *= mult;
+        PB_ROLL
         for (int j = k + 1; j < NX; ++j) {
             double* col_j = sh->LU + j * NX;
             const double a_kj = col_j[k];
             if (a_kj != 0.0)
+                PB_ROLL
                 for (int i = k + 1; i < NX; ++i) col_j[i] -= a_kj * col_k[i];
         }
         col_k[k] = mult;
+    }
+    PB_ROLL
+    for (int i = 0; i < NX; ++i) sh->perm[i] = i;
+    PB_ROLL
+    for (int k = 0; k < NX; ++k) {
+        const int t_ = sh->perm[k];
+        sh->perm[k] = sh->perm[sh->piv[k]];
+        sh->perm[sh->piv[k]] = t_;
     }
     return 0;
 }
@@ -262,10 +293,14 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
     const double rrcut = 0.98, vrrtol = 1.0e-4, vrrt2 = 5.0e-4, sqtol = 1.0e-3, rrtol = 1.0e-2;
     double rr = 0.0, sqmin = 0.0;
     double ss[6][4];
+    PB_ROLL
     for (int i = 1; i <= 5; ++i)
+        PB_ROLL
         for (int k = 1; k <= 3; ++k) ss[i][k] = ssdat[i][k];
+    PB_ROLL
     for (int k = 1; k <= 3; ++k) {
         double smink = ss[1][k], smaxk = 0.0;
+        PB_ROLL
         for (int i = 1; i <= 5; ++i) {
             smink = fmin(smink, ss[i][k]);
             smaxk = fmax(smaxk, ss[i][k]);
@@ -274,6 +309,7 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
         smax[k] = smaxk;
         ssmax[k] = smaxk * smaxk;
         double sumrat = 0.0, sumrsq = 0.0;
+        PB_ROLL
         for (int i = 1; i <= 4; ++i) {
             rat[i][k] = ss[i][k] / ss[i + 1][k];
             sumrat += rat[i][k];
@@ -286,6 +322,7 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
         qc[3][k] = 0.0;
         qc[2][k] = ss[2][k] * ss[5][k] - ss[3][k] * ss[4][k];
         qc[1][k] = ss[4][k] * ss[4][k] - ss[3][k] * ss[5][k];
+        PB_ROLL
         for (int i = 1; i <= 5; ++i) qco[i][k] = qc[i][k];
     }
     const double vmin = fmin(vrat[1], fmin(vrat[2], vrat[3]));
@@ -294,25 +331,31 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
         if (vmax > vrrt2 * vrrt2) return -2;
         rr = (rav[1] + rav[2] + rav[3]) / 3.0;
         double drrmax = 0.0;
+        PB_ROLL
         for (int k = 1; k <= 3; ++k) drrmax = fmax(drrmax, fabs(rav[k] - rr));
         if (drrmax > vrrt2) return -3;
         kflag = 1;
     } else {
         if (fabs(qco[1][1]) < cv::TINY * ssmax[1]) return -4;
         double tem = qco[1][2] / qco[1][1];
+        PB_ROLL
         for (int i = 2; i <= 5; ++i) qco[i][2] -= tem * qco[i][1];
         qco[1][2] = 0.0;
         tem = qco[1][3] / qco[1][1];
+        PB_ROLL
         for (int i = 2; i <= 5; ++i) qco[i][3] -= tem * qco[i][1];
         qco[1][3] = 0.0;
         if (fabs(qco[2][2]) < cv::TINY * ssmax[2]) return -4;
         tem = qco[2][3] / qco[2][2];
+        PB_ROLL
         for (int i = 3; i <= 5; ++i) qco[i][3] -= tem * qco[i][2];
         if (fabs(qco[4][3]) < cv::TINY * ssmax[3]) return -4;
         rr = -qco[5][3] / qco[4][3];
         if (rr < cv::TINY || rr > 100.0) return -5;
+        PB_ROLL
         for (int k = 1; k <= 3; ++k) qkr[k] = qc[5][k] + rr * (qc[4][k] + rr * rr * (qc[2][k] + rr * qc[1][k]));
         double sqmax = 0.0;
+        PB_ROLL
         for (int k = 1; k <= 3; ++k) {
             const double saqk = fabs(qkr[k]) / ssmax[k];
             if (saqk > sqmax) sqmax = saqk;
@@ -320,16 +363,20 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
         if (sqmax < sqtol) {
             kflag = 2;
         } else {
+            PB_ROLL
             for (int it = 1; it <= 3; ++it) {
+                PB_ROLL
                 for (int k = 1; k <= 3; ++k) {
                     const double qp = qc[4][k] + rr * rr * (3.0 * qc[2][k] + rr * 4.0 * qc[1][k]);
                     drr[k] = 0.0;
                     if (fabs(qp) > cv::TINY * ssmax[k]) drr[k] = -qkr[k] / qp;
                     rrc[k] = rr + drr[k];
                 }
+                PB_ROLL
                 for (int k = 1; k <= 3; ++k) {
                     const double s = rrc[k];
                     double sqmaxk = 0.0;
+                    PB_ROLL
                     for (int j = 1; j <= 3; ++j) {
                         qjk[j][k] = qc[5][j] + s * (qc[4][j] + s * s * (qc[2][j] + s * qc[1][j]));
                         const double saqj = fabs(qjk[j][k]) / ssmax[j];
@@ -338,6 +385,7 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
                     sqmx[k] = sqmaxk;
                 }
                 sqmin = sqmx[1] + 1.0;
+                PB_ROLL
                 for (int k = 1; k <= 3; ++k) {
                     if (sqmx[k] < sqmin) {
                         kmin = k;
@@ -349,12 +397,14 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
                     kflag = 3;
                     break;
                 } else {
+                    PB_ROLL
                     for (int j = 1; j <= 3; ++j) qkr[j] = qjk[j][kmin];
                 }
             }
             if (sqmin > sqtol) return -6;
         }
     }
+    PB_ROLL
     for (int k = 1; k <= 3; ++k) {
         const double rsa = ss[1][k];
         const double rsb = ss[2][k] * rr;
@@ -388,6 +438,29 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
 }
 
 
+
+/// WRMS norm max_c sqrt(mean_i(((ca*A[i][c] + cb*B[i][c]) * ewt[i][c])^2)) over the columns
+/// [cmin, cmax] of [NX][NC] arrays in group-shared memory: N_VWrmsNorm for the state column,
+/// cvSensNorm for the sensitivities, cvSensUpdateNorm for both (cvodes.c:9427-9457).  One copy
+/// of the code serves every call site.
+template <class M, class Grp>
+PB_HD_NOINLINE static double wnorm_shared(const GroupShared<M>* sh, const Grp& g, int cmin, int cmax, const double* A,
+                                          double ca, const double* B, double cb) {
+    constexpr int NX = M::NX, NC = GroupShared<M>::NC;
+    double loc = 0.0;
+    for (int c = g.lane(); c <= cmax; c += Grp::G) {
+        if (c < cmin) continue;
+        double s = 0.0;
+        PB_UNROLL_X
+        for (int i = 0; i < NX; ++i) {
+            const double prod = (ca * A[i * NC + c] + cb * B[i * NC + c]) * sh->ewt[i][c];
+            s += prod * prod;
+        }
+        if (s > loc) loc = s;
+    }
+    return sqrt(g.max(loc) / NX);
+}
+
 /// Per-condition inputs (device pointers into the resident tables).
 struct ConditionIO {
     int nt;
@@ -402,7 +475,7 @@ struct ConditionIO {
 #endif
 };
 
-template <class M, class Grp, int CPL>
+template <class M, class Grp>
 struct Bdf {
     static constexpr int NX = M::NX, NP = M::NP, NK = M::NK, NY = M::NY;
     static constexpr int G = Grp::G;
@@ -411,17 +484,8 @@ struct Bdf {
     Grp g;
     GroupShared<M>* sh;
     SolverOptions opt;
-    int ns;            // sensitivity columns
-    bool sensi;        // ns > 0
-    bool act[CPL];     // column exists
-    int ipar[CPL];     // model-parameter index of a sensitivity column (-1: state column)
-
-    // columns in registers
-    double zn[cv::L_MAX][CPL][NX];
-    double acor[CPL][NX];
-    double ewt[CPL][NX];
-    double tmp[CPL][NX];  // y / yS work vector
-    double b[CPL][NX];    // residual -> Newton update
+    int ns;      // sensitivity columns (columns 1..ns; column 0 is the state)
+    bool sensi;  // ns > 0
 
     // integrator scalars (uniform within the group)
     double tn, h, hprime, hscale, eta, etamax, etaq, etaqm1, etaqp1;
@@ -431,97 +495,72 @@ struct Bdf {
     // counters
     int nfe, nsetups, nje, nni, nniS, nfSe, netf, netfS, ncfn, ncfnS, nor, qsum;
 
-    PB_HD bool is_state(int m) const { return m == 0 && g.lane() == 0; }
-    /// column m of this lane takes part in the given phase (state corrector / sensitivity corrector)
-    PB_HD bool in_phase(int m, int phase) const { return act[m] && (is_state(m) == (phase == PH_STATE)); }
+// columns of this lane in [cmin, cmax]
+#define PB_FOR_COLS(c, cmin, cmax) \
+    for (int c = g.lane(); c <= (cmax); c += G) \
+        if (c >= (cmin))
+#define PB_FOR_ALL_COLS(c) for (int c = g.lane(); c <= ns; c += G)
+
+    PB_HD int phase_cmin(int phase) const { return phase == PH_STATE ? 0 : 1; }
+    PB_HD int phase_cmax(int phase) const { return phase == PH_STATE ? 0 : ns; }
 
     // ---------------------------------------------------------------- norms
-    /// WRMS norm over the selected columns: max_c sqrt(mean((v_c*ewt_c)^2)).  Selecting only the
-    /// state column gives N_VWrmsNorm(v, ewt); only sensitivities gives cvSensNorm; both gives
-    /// cvSensUpdateNorm (cvodes.c:9427-9457).
-    PB_HD double wnorm(const double (&v)[CPL][NX], bool with_state, bool with_sens) const {
-        double loc = 0.0;
-        PB_ROLL
-        for (int m = 0; m < CPL; ++m) {
-            if (!act[m]) continue;
-            if (is_state(m) ? !with_state : !with_sens) continue;
-            double s = 0.0;
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) {
-                const double prod = v[m][i] * ewt[m][i];
-                s += prod * prod;
-            }
-            if (s > loc) loc = s;
-        }
-        return group_wrms(g, loc, NX);
+    PB_HD double wnorm1(int cmin, int cmax, const double (&A)[NX][GroupShared<M>::NC]) const {
+        return wnorm_shared<M, Grp>(sh, g, cmin, cmax, &A[0][0], 1.0, &A[0][0], 0.0);
     }
-    PB_HD double norm_phase(const double (&v)[CPL][NX], int phase) const {
-        return wnorm(v, phase == PH_STATE, phase == PH_SENS);
+    PB_HD double wnorm2(int cmin, int cmax, const double (&A)[NX][GroupShared<M>::NC], double ca,
+                        const double (&B)[NX][GroupShared<M>::NC], double cb) const {
+        return wnorm_shared<M, Grp>(sh, g, cmin, cmax, &A[0][0], ca, &B[0][0], cb);
     }
-    /// norm over all variables in the error test: state, plus sensitivities if errconS
-    PB_HD double norm_all(const double (&v)[CPL][NX]) const { return wnorm(v, true, sensi && opt.errconS); }
+    /// columns in the error test: state, plus sensitivities if errconS
+    PB_HD int errtest_cmax() const { return (sensi && opt.errconS) ? ns : 0; }
 
     /// cvEwtSetSS / cvSensEwtSetSS (cvodes.c:9118-9129, 9263-9279)
     PB_HD bool ewt_set() {
         bool ok = true;
-        PB_ROLL
-        for (int m = 0; m < CPL; ++m) {
-            if (!act[m]) continue;
-            PB_UNROLL
+        PB_FOR_ALL_COLS(c) {
+            PB_UNROLL_X
             for (int i = 0; i < NX; ++i) {
-                const double w = opt.rtol * fabs(zn[0][m][i]) + opt.atol;
+                const double w = opt.rtol * fabs(sh->zn[0][i][c]) + opt.atol;
                 ok = ok && (w > 0.0);
-                ewt[m][i] = pb_rcp(w);
+                sh->ewt[i][c] = pb_rcp(w);
             }
         }
-        return g.max(ok ? 0.0 : 1.0) == 0.0;
-    }
-
-    /// hand the state lane's vector to every lane through shared memory
-    PB_HD void publish_state(const double* y) {
-        g.sync();
-        if (g.lane() == 0) {
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) sh->ysh[i] = y[i];
-        }
-        g.sync();
+        return group_max(g, ok ? 0.0 : 1.0) == 0.0;
     }
 
     /// J(t, ysh) -> sh->Jcur by the state lane (Model_ODE::fsxdot at ip == 0,
     /// deps/AMICI/src/model_ode.cpp:492-498)
     PB_HD void refresh_Jcur(double t) {
+        g.sync();
         if (g.lane() == 0) eval_jac_shared<M>(sh->Jcur, t, sh->ysh, sh);
         g.sync();
     }
 
     // ---------------------------------------------------------------- right-hand sides
     /// THE right-hand-side evaluation (single copy in the instruction stream).  For the columns
-    /// of `phase`:  tmp = zn[0] + acor;  F = f(t, tmp)  (state: xdot; sensitivities:
-    /// dxdotdp(ip) + Jcur*tmp, Model_ODE::fsxdot model_ode.cpp:486-515, with sh->ysh / sh->Jcur
+    /// of `phase`:  v = zn[0] + acor;  F = f(t, v)  (state: xdot; sensitivities:
+    /// dxdotdp(ip) + Jcur*v, Model_ODE::fsxdot model_ode.cpp:486-515, with sh->ysh / sh->Jcur
     /// prepared by the caller);  b = raw ? F : rl1*zn[1] + acor - gamma*F  (cvNlsResidual
     /// cvodes_nls.c:344-371; cvNlsResidualSensStg cvodes_nls_stg.c:377-421).
     /// Returns 0, RHSFUNC_RECVR or SRHSFUNC_RECVR (non-finite result).
     PB_HD int rhs(int phase, double t, bool raw) {
         double bad = 0.0;
-        PB_ROLL
-        for (int m = 0; m < CPL; ++m) {
-            if (!in_phase(m, phase)) continue;
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) tmp[m][i] = zn[0][m][i] + acor[m][i];
+        PB_FOR_COLS(c, phase_cmin(phase), phase_cmax(phase)) {
             double F[NX];
-            if (phase == PH_STATE) {
+            if (c == 0) {
                 PB_UNROLL
-                for (int i = 0; i < NX; ++i) sh->yj[i] = tmp[m][i];
+                for (int i = 0; i < NX; ++i) sh->yj[i] = sh->zn[0][i][0] + sh->acor[i][0];
                 if (!eval_xdot_shared<M>(sh, t)) bad = 1.0;
                 PB_UNROLL
                 for (int i = 0; i < NX; ++i) F[i] = sh->fout[i];
             } else {
                 PB_UNROLL
                 for (int i = 0; i < NX; ++i) F[i] = 0.0;
-                M::dxdotdp(F, t, sh->ysh, sh->p, sh->k, ipar[m]);
-                PB_UNROLL
+                M::dxdotdp(F, t, sh->ysh, sh->p, sh->k, sh->plist[c - 1]);
+                PB_ROLL
                 for (int j = 0; j < NX; ++j) {
-                    const double sj = tmp[m][j];
+                    const double sj = sh->zn[0][j][c] + sh->acor[j][c];
                     PB_UNROLL
                     for (int r = 0; r < NX; ++r) F[r] += sh->Jcur[r + j * NX] * sj;
                 }
@@ -531,15 +570,26 @@ struct Bdf {
                 if (!ok) bad = 1.0;
             }
             PB_UNROLL
-            for (int i = 0; i < NX; ++i) b[m][i] = raw ? F[i] : (rl1 * zn[1][m][i] + acor[m][i]) - gamma * F[i];
+            for (int i = 0; i < NX; ++i)
+                sh->b[i][c] = raw ? F[i] : (rl1 * sh->zn[1][i][c] + sh->acor[i][c]) - gamma * F[i];
         }
         if (phase == PH_STATE) nfe++;
         else nfSe += ns;
-        if (g.max(bad) != 0.0) return phase == PH_STATE ? cv::RHSFUNC_RECVR : cv::SRHSFUNC_RECVR;
+        if (group_max(g, bad) != 0.0) return phase == PH_STATE ? cv::RHSFUNC_RECVR : cv::SRHSFUNC_RECVR;
         return 0;
     }
 
-    /// f(t, zn[0] + acor) for the state (into b), then -- if sensitivities take part -- the
+    /// state lane: sh->ysh = zn[0] + acor of the state column (the corrected state y_n)
+    PB_HD void publish_state() {
+        g.sync();
+        if (g.lane() == 0) {
+            PB_UNROLL_X
+            for (int i = 0; i < NX; ++i) sh->ysh[i] = sh->zn[0][i][0] + sh->acor[i][0];
+        }
+        g.sync();
+    }
+
+    /// b = f(t, zn[0] + acor) for the state, then -- if sensitivities take part -- the
     /// sensitivity right-hand sides at that state with a fresh Jacobian (cvSensRhsWrapper with
     /// AMICI's fsxdot).  Used by the cold paths: initialisation, cvHin, order-1 restart.
     PB_HD int rhs_all_raw(double t, bool with_sens) {
@@ -549,7 +599,7 @@ struct Bdf {
             PB_OPAQUE_INT(phase);
             if (phase == PH_SENS) {
                 if (!with_sens) break;
-                publish_state(tmp[0]);
+                publish_state();
                 refresh_Jcur(t);
             }
             r = rhs(phase, t, true);
@@ -581,18 +631,12 @@ struct Bdf {
         return g.bcast0(ret);
     }
 
-    /// dense GETRS on one register column + cvLsSolve's gamma-ratio scaling
-    /// (sundials_dense.c:150-182; cvodes_ls.c:1849-1854)
-    PB_HD void lsolve_col(double* x) const {
+    /// dense GETRS for column c (sundials_dense.c:150-182) + cvLsSolve's gamma-ratio scaling
+    /// (cvodes_ls.c:1849-1854): x = -(P b)[.] gathered through the stored row order, forward and
+    /// backward substitution in registers against the group's factors.
+    PB_HD void lsolve_neg_b(int c, double* x) const {
         PB_UNROLL
-        for (int k = 0; k < NX; ++k) {
-            const int pk = sh->piv[k];
-            const double xk = x[k];
-            PB_UNROLL
-            for (int j = k + 1; j < NX; ++j) {
-                if (pk == j) { x[k] = x[j]; x[j] = xk; }
-            }
-        }
+        for (int i = 0; i < NX; ++i) x[i] = -sh->b[sh->perm[i]][c];
         PB_UNROLL
         for (int k = 0; k < NX - 1; ++k) {
             PB_UNROLL
@@ -619,14 +663,17 @@ struct Bdf {
         double l_[cv::L_MAX + 1];
         double alpha0, alpha0_hat, xi_inv, xistar_inv, hsum;
         l_[0] = l_[1] = xi_inv = xistar_inv = 1.0;
+        PB_ROLL
         for (int i = 2; i <= cv::L_MAX; ++i) l_[i] = 0.0;
         alpha0 = alpha0_hat = -1.0;
         hsum = h;
         if (q > 1) {
+            PB_ROLL
             for (int j = 2; j < q; ++j) {
                 hsum += sh->tau[j - 1];
                 xi_inv = pb_div(h, hsum);
                 alpha0 -= pb_rcp((double)j);
+                PB_ROLL
                 for (int i = j; i >= 1; --i) l_[i] += l_[i - 1] * xi_inv;
             }
             alpha0 -= pb_rcp((double)q);
@@ -634,6 +681,7 @@ struct Bdf {
             hsum += sh->tau[q - 1];
             xi_inv = pb_div(h, hsum);
             alpha0_hat = -l_[1] - xi_inv;
+            PB_ROLL
             for (int i = q; i >= 1; --i) l_[i] += l_[i - 1] * xistar_inv;
         }
         double tq1 = sh->tq[1], tq3 = sh->tq[3];
@@ -660,6 +708,7 @@ struct Bdf {
         }
         g.sync();
         if (g.lane() == 0) {
+            PB_ROLL
             for (int i = 0; i <= cv::L_MAX; ++i) sh->l[i] = l_[i];
             sh->tq[1] = tq1;
             sh->tq[2] = tq2;
@@ -675,34 +724,36 @@ struct Bdf {
     }
 
     // ---------------------------------------------------------------- history array
-    /// cvPredict (sgn = +1, cvodes.c:6507-6597: also advances tn) and cvRestore (sgn = -1,
-    /// cvodes.c:7373-7424) share one copy of the Pascal-triangle sweep.
+    /// cvPredict (sgn = +1, cvodes.c:6507-6597) and cvRestore (sgn = -1, cvodes.c:7373-7424):
+    /// the Pascal-triangle sweep zn[j-1] += sgn*zn[j], k = 1..q, j = q..k, done per element in
+    /// registers (one load and one store of the q+1 history entries).
     PB_HD void shift_history(double sgn) {
-        PB_UNROLL
-        for (int k = 1; k <= cv::Q_MAX; ++k) {
-            PB_UNROLL
-            for (int j = cv::Q_MAX; j >= 1; --j) {
-                if (j >= k && j <= q && k <= q) {
-                    PB_ROLL
-                    for (int m = 0; m < CPL; ++m) {
-                        PB_UNROLL
-                        for (int i = 0; i < NX; ++i) zn[j - 1][m][i] += sgn * zn[j][m][i];
+        PB_FOR_ALL_COLS(c) {
+            PB_ROLL
+            for (int i = 0; i < NX; ++i) {
+                double z[cv::L_MAX];
+                PB_UNROLL
+                for (int j = 0; j < cv::L_MAX; ++j) z[j] = (j <= q) ? sh->zn[j][i][c] : 0.0;
+                PB_UNROLL
+                for (int k = 1; k <= cv::Q_MAX; ++k) {
+                    PB_UNROLL
+                    for (int j = cv::Q_MAX; j >= k; --j) {
+                        if (j <= q && k <= q) z[j - 1] += sgn * z[j];
                     }
                 }
+                PB_UNROLL
+                for (int j = 0; j < cv::Q_MAX; ++j)
+                    if (j < q) sh->zn[j][i][c] = z[j];
             }
         }
     }
     /// cvRescale (cvodes.c:6425-6495)
     PB_HD void rescale() {
-        double factor = eta;
-        PB_UNROLL
-        for (int j = 1; j <= cv::Q_MAX; ++j) {
-            if (j <= q) {
-                PB_ROLL
-                for (int m = 0; m < CPL; ++m) {
-                    PB_UNROLL
-                    for (int i = 0; i < NX; ++i) zn[j][m][i] *= factor;
-                }
+        PB_FOR_ALL_COLS(c) {
+            double factor = eta;
+            for (int j = 1; j <= q; ++j) {
+                PB_UNROLL_X
+                for (int i = 0; i < NX; ++i) sh->zn[j][i][c] *= factor;
                 factor *= eta;
             }
         }
@@ -710,14 +761,14 @@ struct Bdf {
         hscale = h;
         nscon = 0;
     }
-    /// cvAdjustOrder -> cvIncreaseBDF / cvDecreaseBDF (cvodes.c:6134-6143, 6256-6351, 6363-6415),
-    /// one copy of the column update zn[j] += c_j * zn[src], j = 2..jmax.
+    /// cvAdjustOrder -> cvIncreaseBDF / cvDecreaseBDF (cvodes.c:6134-6143, 6256-6351, 6363-6415)
     PB_HD void adjust_order(int deltaq) {
         if ((q == 2) && (deltaq != 1)) return;
         double lc[cv::L_MAX + 1];
         for (int i = 0; i <= cv::L_MAX; ++i) lc[i] = 0.0;
         lc[2] = 1.0;
         int src, jmax;
+        double A1 = 0.0;
         if (deltaq == 1) {
             double alpha1 = 1.0, prod = 1.0, xiold = 1.0, alpha0 = -1.0;
             double hsum = hscale;
@@ -730,20 +781,9 @@ struct Bdf {
                 for (int i = j + 2; i >= 2; --i) lc[i] = lc[i] * xiold + lc[i - 1];
                 xiold = xi;
             }
-            const double A1 = pb_div(-alpha0 - alpha1, prod);
-            // new column zn[L] = A1 * (saved correction in zn[qmax]); L = q+1 <= qmax
-            PB_UNROLL
-            for (int j = 2; j <= cv::Q_MAX; ++j) {
-                if (j == L) {
-                    PB_ROLL
-                    for (int m = 0; m < CPL; ++m) {
-                        PB_UNROLL
-                        for (int i = 0; i < NX; ++i) zn[j][m][i] = A1 * zn[cv::Q_MAX][m][i];
-                    }
-                }
-            }
-            src = L;
-            jmax = q;        // N_VScaleAddMulti(q-1, l+2, zn[L], zn+2, zn+2)
+            A1 = pb_div(-alpha0 - alpha1, prod);
+            src = L;   // new column zn[L] = A1 * (saved correction in zn[qmax]); L = q+1 <= qmax
+            jmax = q;  // N_VScaleAddMulti(q-1, l+2, zn[L], zn+2, zn+2)
         } else {
             double hsum = 0.0;
             for (int j = 1; j <= q - 2; ++j) {
@@ -753,21 +793,14 @@ struct Bdf {
             }
             for (int j = 2; j < q; ++j) lc[j] = -lc[j];
             src = q;
-            jmax = q - 1;    // zn[j] -= l[j]*zn[q], j = 2..q-1
+            jmax = q - 1;  // zn[j] -= l[j]*zn[q], j = 2..q-1
         }
-        PB_UNROLL
-        for (int s = 2; s <= cv::Q_MAX; ++s) {
-            if (s != src) continue;
-            PB_UNROLL
-            for (int j = 2; j <= cv::Q_MAX; ++j) {
-                if (j <= jmax && j != s) {
-                    const double cj = lc[j];
-                    PB_ROLL
-                    for (int m = 0; m < CPL; ++m) {
-                        PB_UNROLL
-                        for (int i = 0; i < NX; ++i) zn[j][m][i] += cj * zn[s][m][i];
-                    }
-                }
+        PB_FOR_ALL_COLS(c) {
+            PB_ROLL
+            for (int i = 0; i < NX; ++i) {
+                if (deltaq == 1) sh->zn[src][i][c] = A1 * sh->zn[cv::Q_MAX][i][c];
+                const double zs = sh->zn[src][i][c];
+                for (int j = 2; j <= jmax; ++j) sh->zn[j][i][c] += lc[j] * zs;
             }
         }
     }
@@ -777,20 +810,18 @@ struct Bdf {
     /// `phase` (cvodes.c:6894-7007, 7167-7210; sunnonlinsol_newton.c:176-335; cvodes_nls.c:
     /// 298-342; cvodes_nls_stg.c:238-375).  The state corrector and the staggered sensitivity
     /// corrector are the same Newton iteration on different columns with the same factors, so
-    /// they share one copy of the code.  On success the corrected vector is zn[0]+acor (left in
-    /// tmp for the state column).
+    /// they share one copy of the code.  On success the corrected vector is zn[0]+acor.
     PB_HD int nls(int phase, int nflag) {
+        const int cmin = phase_cmin(phase), cmax = phase_cmax(phase);
         bool setup_pending = false;
         if (phase == PH_STATE) {
             convfail = ((nflag == cv::FIRST_CALL) || (nflag == cv::PREV_ERR_FAIL)) ? cv::NO_FAILURES : cv::FAIL_OTHER;
             setup_pending = (nflag == cv::PREV_CONV_FAIL) || (nflag == cv::PREV_ERR_FAIL) || (nst == 0) ||
                             (nst >= nstlp + cv::MSBP) || (fabs(gamrat - 1.0) > cv::DGMAX_LSETUP);
         }
-        PB_ROLL
-        for (int m = 0; m < CPL; ++m) {
-            if (!in_phase(m, phase)) continue;
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) acor[m][i] = 0.0;
+        PB_FOR_COLS(c, cmin, cmax) {
+            PB_UNROLL_X
+            for (int i = 0; i < NX; ++i) sh->acor[i][c] = 0.0;
         }
         bool jbad = false;
         bool top = true;  // residual at the top of a solve attempt: failures there are final
@@ -803,7 +834,7 @@ struct Bdf {
                 if (phase == PH_SENS) {  // Jacobian at the converged state (cv_y), cvodes_nls_stg.c:252
                     g.sync();
                     if (g.lane() == 0) {
-                        PB_UNROLL
+                        PB_UNROLL_X
                         for (int i = 0; i < NX; ++i) sh->yj[i] = sh->ysh[i];
                     }
                 }  // state phase: rhs() has just put zn[0]+acor into sh->yj
@@ -822,32 +853,30 @@ struct Bdf {
             if (ret == 0) {
                 if (phase == PH_STATE) nni++;
                 else nniS++;
-                PB_ROLL
-                for (int m = 0; m < CPL; ++m) {
-                    if (!in_phase(m, phase)) continue;
+                double loc = 0.0;  // max over own columns of sum((delta*ewt)^2)
+                PB_FOR_COLS(c, cmin, cmax) {
+                    double x[NX];
+                    lsolve_neg_b(c, x);
+                    double s = 0.0;
                     PB_UNROLL
-                    for (int i = 0; i < NX; ++i) b[m][i] = -b[m][i];
-                    lsolve_col(b[m]);
-                    PB_UNROLL
-                    for (int i = 0; i < NX; ++i) acor[m][i] += b[m][i];
+                    for (int i = 0; i < NX; ++i) {
+                        sh->acor[i][c] += x[i];
+                        const double prod = x[i] * sh->ewt[i][c];
+                        s += prod * prod;
+                    }
+                    if (s > loc) loc = s;
                 }
-                const double del = norm_phase(b, phase);
+                const double del = group_wrms(g, loc, NX);
                 double cr = (phase == PH_STATE) ? crate : crateS;
                 if (m_it > 0) cr = fmax(cv::CRDOWN * cr, pb_div(del, delp));
                 if (phase == PH_STATE) crate = cr;
                 else crateS = cr;
                 const double dcon = pb_div(del * fmin(1.0, cr), sh->tq[4]);
                 if (dcon <= 1.0) {
-                    const double an = (m_it == 0) ? del : norm_phase(acor, phase);
+                    const double an = (m_it == 0) ? del : wnorm1(cmin, cmax, sh->acor);
                     if (phase == PH_STATE) {
                         acnrm = an;
                         jcurNLS = false;
-                        PB_ROLL
-                        for (int m = 0; m < CPL; ++m) {
-                            if (!in_phase(m, phase)) continue;
-                            PB_UNROLL
-                            for (int i = 0; i < NX; ++i) tmp[m][i] = zn[0][m][i] + acor[m][i];
-                        }
                     } else {
                         if (opt.errconS) acnrmS = an;
                         jcurNLSS = false;
@@ -870,11 +899,9 @@ struct Bdf {
                 jbad = true;
                 top = true;
                 m_it = 0;
-                PB_ROLL
-                for (int m = 0; m < CPL; ++m) {
-                    if (!in_phase(m, phase)) continue;
-                    PB_UNROLL
-                    for (int i = 0; i < NX; ++i) acor[m][i] = 0.0;
+                PB_FOR_COLS(c, cmin, cmax) {
+                    PB_UNROLL_X
+                    for (int i = 0; i < NX; ++i) sh->acor[i][c] = 0.0;
                 }
                 continue;
             }
@@ -895,26 +922,17 @@ struct Bdf {
             sh->tau[1] = h;
         }
         g.sync();
-        PB_UNROLL
-        for (int j = 0; j <= cv::Q_MAX; ++j) {
-            if (j <= q) {
-                const double lj = sh->l[j];
-                PB_ROLL
-                for (int m = 0; m < CPL; ++m) {
-                    PB_UNROLL
-                    for (int i = 0; i < NX; ++i) zn[j][m][i] += lj * acor[m][i];
-                }
-            }
-        }
         qwait--;
-        if ((qwait == 1) && (q != cv::Q_MAX)) {
+        const bool save = (qwait == 1) && (q != cv::Q_MAX);
+        PB_FOR_ALL_COLS(c) {
             PB_ROLL
-            for (int m = 0; m < CPL; ++m) {
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) zn[cv::Q_MAX][m][i] = acor[m][i];
+            for (int i = 0; i < NX; ++i) {
+                const double a = sh->acor[i][c];
+                for (int j = 0; j <= q; ++j) sh->zn[j][i][c] += sh->l[j] * a;
+                if (save) sh->zn[cv::Q_MAX][i][c] = a;
             }
-            saved_tq5 = sh->tq[5];
         }
+        if (save) saved_tq5 = sh->tq[5];
     }
 
     /// cvPrepareNextStep with cvSetEta, cvComputeEtaqm1 / cvComputeEtaqp1 / cvChooseEta
@@ -932,12 +950,11 @@ struct Bdf {
         eta = etaq;
         if (qwait == 0) {
             qwait = 2;
+            const int ecmax = errtest_cmax();
             etaqm1 = 0.0;
             if (q > 1) {
-                double ddn = 0.0;
-                PB_UNROLL
-                for (int j = 2; j <= cv::Q_MAX; ++j)
-                    if (j == q) ddn = norm_all(zn[j]);
+                const int qq = q;
+                double ddn = wnorm1(0, ecmax, sh->zn[qq]);
                 ddn = ddn * sh->tq[1];
                 etaqm1 = pb_rcp(pb_pow(cv::BIAS1 * ddn, pb_rcp((double)q)) + cv::ADDON);
             }
@@ -948,12 +965,7 @@ struct Bdf {
                     double hp = 1.0;
                     for (int i = 0; i < L; ++i) hp *= hr;  // SUNRpowerI
                     const double cquot = pb_div(sh->tq[5], saved_tq5) * hp;
-                    PB_ROLL
-                    for (int m = 0; m < CPL; ++m) {
-                        PB_UNROLL
-                        for (int i = 0; i < NX; ++i) tmp[m][i] = -cquot * zn[cv::Q_MAX][m][i] + acor[m][i];
-                    }
-                    double dup = norm_all(tmp);
+                    double dup = wnorm2(0, ecmax, sh->zn[cv::Q_MAX], -cquot, sh->acor, 1.0);
                     dup = dup * sh->tq[3];
                     etaqp1 = pb_rcp(pb_pow(cv::BIAS3 * dup, pb_rcp((double)(L + 1))) + cv::ADDON);
                 }
@@ -974,11 +986,9 @@ struct Bdf {
                 qprime = q + 1;
                 // store Delta_n in zn[qmax] for the order increase (state always; sensitivities
                 // only if they take part in the error test, cvodes.c:7973-7987)
-                PB_ROLL
-                for (int m = 0; m < CPL; ++m) {
-                    if (!is_state(m) && !opt.errconS) continue;
-                    PB_UNROLL
-                    for (int i = 0; i < NX; ++i) zn[cv::Q_MAX][m][i] = acor[m][i];
+                PB_FOR_COLS(c, 0, ecmax) {
+                    PB_UNROLL_X
+                    for (int i = 0; i < NX; ++i) sh->zn[cv::Q_MAX][i][c] = sh->acor[i][c];
                 }
             }
         }
@@ -997,20 +1007,16 @@ struct Bdf {
     /// cvBDFStab (cvodes.c:8158-8218)
     PB_HD void bdf_stab() {
         if (q >= 3) {
-            double sqm1 = 0.0, sqm2 = 0.0;
-            PB_UNROLL
-            for (int j = 2; j <= cv::Q_MAX; ++j) {
-                if (j == q || j == q - 1) {
-                    const double v = wnorm(zn[j], true, false);
-                    if (j == q) sqm1 = v;
-                    else sqm2 = v;
-                }
+            double sqv[2];
+            for (int w = 0; w < 2; ++w) {
+                const int jj = q - w;
+                sqv[w] = wnorm1(0, 0, sh->zn[jj]);
             }
             int factorial = 1;
             for (int i = 1; i <= q - 1; ++i) factorial *= i;
             const double sq = pb_div(factorial * q * (q + 1) * acnrm, fmax(sh->tq[5], cv::TINY));
-            sqm1 *= factorial * q;
-            sqm2 *= factorial;
+            const double sqm1 = sqv[0] * (factorial * q);
+            const double sqm2 = sqv[1] * factorial;
             g.sync();
             if (g.lane() == 0) {
                 for (int k = 1; k <= 3; ++k)
@@ -1037,11 +1043,25 @@ struct Bdf {
         }
     }
 
+    /// zn[1] = h * f(tn, zn[0]) for the state and (if any) the sensitivities; acor is scratch
+    PB_HD int reload_zn1() {
+        PB_FOR_ALL_COLS(c) {
+            PB_UNROLL_X
+            for (int i = 0; i < NX; ++i) sh->acor[i][c] = 0.0;
+        }
+        const int r = rhs_all_raw(tn, sensi);
+        if (r) return r;
+        PB_FOR_ALL_COLS(c) {
+            PB_UNROLL_X
+            for (int i = 0; i < NX; ++i) sh->zn[1][i][c] = h * sh->b[i][c];
+        }
+        return 0;
+    }
+
     /// cvStep (cvodes.c:5800-6094) with cvHandleNFlag (:7309-7363) and cvDoErrorTest
     /// (:7461-7614) folded into ONE failure handler, and cvAdjustParams (:6112-6122) folded into
     /// the top of the attempt loop, so that every history operation (Pascal sweep, order change,
-    /// rescale) and both correctors exist once in the instruction stream: the first version of
-    /// this kernel was instruction-cache bound (profiles/r01_a_summary.txt).  The sequence of
+    /// rescale) and both correctors exist once in the instruction stream.  The sequence of
     /// operations per attempt is the reference's.
     PB_HD int step() {
         int ncf = 0, nef = 0, ncfS = 0, nefS = 0;
@@ -1095,17 +1115,17 @@ struct Bdf {
                 if (phase == PH_SENS) {
                     if (fail || !sensi) break;
                     ncf = nef = 0;
+                    publish_state();
                     // f at the converged y (cvodes.c:5947-5955); AMICI's sensitivity RHS does not
                     // use it -- kept for the recoverable-failure semantics
+                    int bad = 0;
                     if (g.lane() == 0) {
                         PB_UNROLL
-                        for (int i = 0; i < NX; ++i) sh->yj[i] = tmp[0][i];
+                        for (int i = 0; i < NX; ++i) sh->yj[i] = sh->ysh[i];
+                        bad = eval_xdot_shared<M>(sh, tn) ? 0 : 1;
                     }
-                    int bad = 0;
-                    if (g.lane() == 0) bad = eval_xdot_shared<M>(sh, tn) ? 0 : 1;
                     nfe++;
                     if (g.bcast0(bad)) { fail = 5; break; }
-                    publish_state(tmp[0]);
                     refresh_Jcur(tn);
                 }
                 ret = nls(phase, nflag);
@@ -1167,24 +1187,6 @@ struct Bdf {
         return 0;
     }
 
-    /// zn[1] = h * f(tn, zn[0]) for the state and (if any) the sensitivities; acor is scratch
-    PB_HD int reload_zn1() {
-        PB_ROLL
-        for (int m = 0; m < CPL; ++m) {
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) acor[m][i] = 0.0;
-        }
-        const int r = rhs_all_raw(tn, sensi);
-        if (r) return r;
-        PB_ROLL
-        for (int m = 0; m < CPL; ++m) {
-            if (!act[m]) continue;
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) zn[1][m][i] = h * b[m][i];
-        }
-        return 0;
-    }
-
     // ---------------------------------------------------------------- initial step
     /// cvHin with cvUpperBoundH0 and cvYddNorm (cvodes.c:5436-5773); zn[1] holds y'(t0) unscaled.
     PB_HD int hin(double tout) {
@@ -1196,20 +1198,18 @@ struct Bdf {
         if (tdist < 2.0 * tround) return SIM_TOO_CLOSE;
         const double hlb = cv::HLB_FACTOR * tround;
         const bool withS = sensi && opt.errconS;
+        const int ecmax = errtest_cmax();
         // cvUpperBoundH0
         double hub_inv = 0.0;
-        PB_ROLL
-        for (int m = 0; m < CPL; ++m) {
-            if (!act[m]) continue;
-            if (!is_state(m) && !withS) continue;
-            PB_UNROLL
+        PB_FOR_COLS(c, 0, ecmax) {
+            PB_UNROLL_X
             for (int i = 0; i < NX; ++i) {
-                const double den = cv::HUB_FACTOR * fabs(zn[0][m][i]) + pb_rcp(ewt[m][i]);
-                const double v = pb_div(fabs(zn[1][m][i]), den);
+                const double den = cv::HUB_FACTOR * fabs(sh->zn[0][i][c]) + pb_rcp(sh->ewt[i][c]);
+                const double v = pb_div(fabs(sh->zn[1][i][c]), den);
                 if (v > hub_inv) hub_inv = v;
             }
         }
-        hub_inv = g.max(hub_inv);
+        hub_inv = group_max(g, hub_inv);
         double hub = cv::HUB_FACTOR * tdist;
         if (hub * hub_inv > 1.0) hub = pb_rcp(hub_inv);
         double hg = sqrt(hlb * hub);
@@ -1225,29 +1225,22 @@ struct Bdf {
             for (int count2 = 1; count2 <= cv::HIN_MAX_ITERS; ++count2) {
                 // cvYddNorm: f at (tn + hg, zn0 + hg*zn1), difference quotient, WRMS norm
                 const double hgs = hg * sign;
-                PB_ROLL
-                for (int m = 0; m < CPL; ++m) {
-                    PB_UNROLL
-                    for (int i = 0; i < NX; ++i) acor[m][i] = hgs * zn[1][m][i];
+                PB_FOR_ALL_COLS(c) {
+                    PB_UNROLL_X
+                    for (int i = 0; i < NX; ++i) sh->acor[i][c] = hgs * sh->zn[1][i][c];
                 }
                 retval = rhs_all_raw(tn + hgs, withS);
                 if (retval == 0) {
                     const double hinv = pb_rcp(hgs);
-                    PB_ROLL
-                    for (int m = 0; m < CPL; ++m) {
-                        PB_UNROLL
-                        for (int i = 0; i < NX; ++i) b[m][i] = hinv * b[m][i] + (-hinv) * zn[1][m][i];
-                    }
-                    yddnrm = norm_all(b);
+                    yddnrm = wnorm2(0, ecmax, sh->b, hinv, sh->zn[1], -hinv);
                     hgOK = true;
                     break;
                 }
                 hg *= 0.2;
             }
-            PB_ROLL
-            for (int m = 0; m < CPL; ++m) {
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) acor[m][i] = 0.0;
+            PB_FOR_ALL_COLS(c) {
+                PB_UNROLL_X
+                for (int i = 0; i < NX; ++i) sh->acor[i][c] = 0.0;
             }
             if (!hgOK) {
                 if (count1 <= 2) return retval == cv::RHSFUNC_RECVR ? SIM_REPTD_RHSFUNC_ERR : SIM_REPTD_SRHSFUNC_ERR;
@@ -1291,10 +1284,9 @@ struct Bdf {
             if ((tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
             hscale = h;
             hprime = h;
-            PB_ROLL
-            for (int m = 0; m < CPL; ++m) {
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) zn[1][m][i] *= h;
+            PB_FOR_ALL_COLS(c) {
+                PB_UNROLL_X
+                for (int i = 0; i < NX; ++i) sh->zn[1][i][c] *= h;
             }
         } else {
             const double troundoff = cv::FUZZ_FACTOR * cv::UROUND * (fabs(tn) + fabs(h));
@@ -1313,7 +1305,7 @@ struct Bdf {
                 if (!ewt_set()) return SIM_ILL_INPUT;
             }
             if (nstloc >= mxstep) return SIM_TOO_MUCH_WORK;
-            const double nrm = norm_all(zn[0]);
+            const double nrm = wnorm1(0, errtest_cmax(), sh->zn[0]);
             if (cv::UROUND * nrm > 1.0) return SIM_TOO_MUCH_ACC;
             const int kflag = step();
             if (kflag != 0) return kflag;
@@ -1335,11 +1327,17 @@ struct Bdf {
     /// One output time: llh and sllh contributions (Model::addObservableObjective /
     /// addObservableObjectiveSensitivity, deps/AMICI/src/model.cpp:1106-1152 with
     /// fsigmay :2087-2119, fdJydy/fdJydsigma/fdJydp/fdJydx :2184-2392; Jy formulas
-    /// deps/AMICI/models/model_steadystate/{Jy,dJydy,dJydsigma}.cpp).
-    /// Returns false if a sigma is not positive (Model::checkSigmaPositivity throws).
-    PB_HD bool data_point(double t, const double* my, const double* sd, double& llh, double (&sllh)[CPL],
-                          double* y_out, double* sigmay_out) {
-        publish_state(zn[0][0]);
+    /// deps/AMICI/models/model_steadystate/{Jy,dJydy,dJydsigma}.cpp).  The state at the output
+    /// time is zn[0] of column 0.  Returns false if a sigma is not positive
+    /// (Model::checkSigmaPositivity throws).
+    PB_HD bool data_point(double t, const double* my, const double* sd, double& llh, double* y_out,
+                          double* sigmay_out) {
+        g.sync();
+        if (g.lane() == 0) {
+            PB_UNROLL
+            for (int i = 0; i < NX; ++i) sh->ysh[i] = sh->zn[0][i][0];
+        }
+        g.sync();
         double y[NY], sig[NY];
         M::y(y, t, sh->ysh, sh->p, sh->k);
         M::sigmay(sig, t, sh->p, sh->k);
@@ -1399,14 +1397,13 @@ struct Bdf {
                 dJydx[ix] = a;
             }
         }
-        PB_ROLL
-        for (int m = 0; m < CPL; ++m) {
-            if (!act[m] || is_state(m)) continue;
+        PB_FOR_COLS(c, 1, ns) {
             double dydp[NY], dsdp[NY];
             PB_UNROLL
             for (int iy = 0; iy < NY; ++iy) { dydp[iy] = 0.0; dsdp[iy] = 0.0; }
-            M::dydp(dydp, t, sh->ysh, sh->p, sh->k, ipar[m]);
-            M::dsigmaydp(dsdp, t, sh->p, sh->k, ipar[m]);
+            const int ip = sh->plist[c - 1];
+            M::dydp(dydp, t, sh->ysh, sh->p, sh->k, ip);
+            M::dsigmaydp(dsdp, t, sh->p, sh->k, ip);
             double dJydp = 0.0;
             PB_UNROLL
             for (int iy = 0; iy < NY; ++iy) dJydp += dJydy[iy] * dydp[iy];
@@ -1414,42 +1411,38 @@ struct Bdf {
             for (int iy = 0; iy < NY; ++iy) dJydp += dJyds[iy] * dsdp[iy];
             double a = dJydp;
             PB_UNROLL
-            for (int ix = 0; ix < NX; ++ix) a += dJydx[ix] * zn[0][m][ix];
-            sllh[m] -= a;
+            for (int ix = 0; ix < NX; ++ix) a += dJydx[ix] * sh->zn[0][ix][c];
+            sh->sllh[c] -= a;
         }
         return true;
     }
 
     // ---------------------------------------------------------------- one simulation
     /// ForwardProblem::workForwardProblem + ReturnData for one condition at the given
-    /// tolerances.  sh->p / sh->k / sh->plist must be set.  Returns the AMICI status.
-    PB_HD int simulate(const ConditionIO& io, double rtol, double atol, double& llh_out, double (&sllh_out)[CPL]) {
+    /// tolerances.  sh->p / sh->k / sh->plist must be set.  Returns the AMICI status; the llh is
+    /// returned, d llh / d p (w.r.t. the unscaled parameter) is left in sh->sllh[1..ns].
+    PB_HD int simulate(const ConditionIO& io, double rtol, double atol, double& llh_out) {
         opt.rtol = rtol;
         opt.atol = atol;
         ns = io.ns;
         sensi = ns > 0;
-        PB_ROLL
-        for (int m = 0; m < CPL; ++m) {
-            const int c = g.lane() + m * G;
-            act[m] = c <= ns;
-            ipar[m] = (c >= 1 && c <= ns) ? sh->plist[c - 1] : -1;
-        }
+        g.sync();
         // Model::initialize: x0, sx0 (deps/AMICI/src/model.cpp:249-275)
-        PB_UNROLL
-        for (int j = 0; j < cv::L_MAX; ++j) {
-            PB_ROLL
-            for (int m = 0; m < CPL; ++m) {
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) zn[j][m][i] = 0.0;
-            }
-        }
-        PB_ROLL
-        for (int m = 0; m < CPL; ++m) {
+        PB_FOR_ALL_COLS(c) {
+            double v[NX];
             PB_UNROLL
-            for (int i = 0; i < NX; ++i) { acor[m][i] = 0.0; ewt[m][i] = 1.0; tmp[m][i] = 0.0; b[m][i] = 0.0; }
-            if (!act[m]) continue;
-            if (is_state(m)) M::x0(zn[0][m], opt.t0, sh->p, sh->k);
-            else M::sx0(zn[0][m], opt.t0, sh->p, sh->k, ipar[m]);
+            for (int i = 0; i < NX; ++i) v[i] = 0.0;
+            if (c == 0) M::x0(v, opt.t0, sh->p, sh->k);
+            else M::sx0(v, opt.t0, sh->p, sh->k, sh->plist[c - 1]);
+            PB_UNROLL
+            for (int i = 0; i < NX; ++i) {
+                sh->zn[0][i][c] = v[i];
+                for (int j = 1; j < cv::L_MAX; ++j) sh->zn[j][i][c] = 0.0;
+                sh->acor[i][c] = 0.0;
+                sh->ewt[i][c] = 1.0;
+                sh->b[i][c] = 0.0;
+            }
+            sh->sllh[c] = 0.0;
         }
         // CVodeInit (cvodes.c:677-830)
         tn = opt.t0;
@@ -1464,7 +1457,6 @@ struct Bdf {
         jcur = jcurNLS = jcurNLSS = false;
         tstopset = false; tstop = 0.0;
         nfe = nsetups = nje = nni = nniS = nfSe = netf = netfS = ncfn = ncfnS = nor = qsum = 0;
-        g.sync();
         if (g.lane() == 0) {
             for (int i = 0; i <= cv::L_MAX; ++i) { sh->l[i] = 0.0; sh->tau[i] = 0.0; }
             for (int i = 0; i < 6; ++i) sh->tq[i] = 0.0;
@@ -1474,9 +1466,6 @@ struct Bdf {
         g.sync();
 
         double llh = 0.0;
-        double sllh[CPL];
-        PB_ROLL
-        for (int m = 0; m < CPL; ++m) sllh[m] = 0.0;
         int status = SIM_SUCCESS;
         for (int it = 0; it < io.nt; ++it) {
             const double tout = io.t[it];
@@ -1497,20 +1486,14 @@ struct Bdf {
 #if defined(PB200_HOST_TRACE)
             if (io.trace) { io.trace[2 * it] = nst; io.trace[2 * it + 1] = q; }
 #endif
-            if (!data_point(tout, io.my + (size_t)it * NY, io.sd + (size_t)it * NY, llh, sllh, yo, so)) {
+            if (!data_point(tout, io.my + (size_t)it * NY, io.sd + (size_t)it * NY, llh, yo, so)) {
                 status = SIM_ERROR;
                 break;
             }
         }
-        if (status != SIM_SUCCESS) {
-            llh = NAN;  // ReturnData::invalidate (rdata.cpp)
-        } else if (sensi) {
-            // applyChainRuleFactorToSimulationResults: caller multiplies by the
-            // parameter-scale factor (it owns pscale); nothing to do here.
-        }
+        if (status != SIM_SUCCESS) llh = NAN;  // ReturnData::invalidate (rdata.cpp)
+        g.sync();
         llh_out = g.bcast0(llh);
-        PB_ROLL
-        for (int m = 0; m < CPL; ++m) sllh_out[m] = sllh[m];
         return status;
     }
 
@@ -1520,6 +1503,8 @@ struct Bdf {
         s[STAT_NETFS] = netfS; s[STAT_NCFN] = ncfn; s[STAT_NCFNS] = ncfnS; s[STAT_NOR] = nor;
         s[STAT_TRIALS] = trials; s[STAT_QSUM] = qsum; s[14] = 0; s[15] = 0;
     }
+#undef PB_FOR_COLS
+#undef PB_FOR_ALL_COLS
 };
 
 }  // namespace pb200

@@ -59,24 +59,23 @@ struct KernelArgs {
 };
 
 constexpr double PB_LN10 = 2.302585092994046;
+#ifndef PB_MIN_BLOCKS
+#define PB_MIN_BLOCKS 7
+#endif
 
-/// Where a group's uniform state lives: shared memory for multi-lane groups; for a
-/// one-lane group it is private to the thread (a __shared__ array of THREADS copies would
-/// exceed the static shared-memory limit).
+/// One lane group per condition, persistent CTAs, in-kernel work queue.  The group's working
+/// set (GroupShared<M>: Nordsieck history of all columns, Jacobian, LU, ...) lives in dynamic
+/// shared memory for multi-lane groups; a one-lane group (cost-only evaluations) keeps it in
+/// the thread's local memory.
 template <class M, int G, int THREADS>
-__device__ __forceinline__ GroupShared<M>* group_storage_shared() {
-    __shared__ GroupShared<M> shm[THREADS / G];
-    return &shm[threadIdx.x / G];
-}
-
-template <class M, int G, int CPL, int THREADS>
-__global__ void __launch_bounds__(THREADS) simulate_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(THREADS, PB_MIN_BLOCKS) simulate_kernel(const KernelArgs a) {
+    extern __shared__ __align__(16) unsigned char pb_smem_raw[];
     LaneGroup<G> grp;
     typename std::conditional<G == 1, GroupShared<M>, char>::type priv_storage_;
     GroupShared<M>* sh;
     if constexpr (G == 1) sh = &priv_storage_;
-    else sh = group_storage_shared<M, G, THREADS>();
-    Bdf<M, LaneGroup<G>, CPL> bdf;
+    else sh = reinterpret_cast<GroupShared<M>*>(pb_smem_raw) + (threadIdx.x / G);
+    Bdf<M, LaneGroup<G>> bdf;
     bdf.sh = sh;
     bdf.opt = a.opt;
     const int lane = grp.lane();
@@ -118,12 +117,11 @@ __global__ void __launch_bounds__(THREADS) simulate_kernel(const KernelArgs a) {
 
         // ---- A8: runAndLogSimulation retry loop (multiConditionProblem.cpp:369-465) ----
         double llh = NAN;
-        double sllh[CPL];
         int status = SIM_ERROR;
         int trial = 1;
         double relax = 1.0;
         for (; trial <= a.num_trials; ++trial) {
-            status = bdf.simulate(io, a.opt.rtol * relax, a.opt.atol * relax, llh, sllh);
+            status = bdf.simulate(io, a.opt.rtol * relax, a.opt.atol * relax, llh);
             if (status == SIM_SUCCESS) break;
             // next trial: tolerances * relaxation^(trial) relative to the template
             relax = 1.0;
@@ -143,16 +141,14 @@ __global__ void __launch_bounds__(THREADS) simulate_kernel(const KernelArgs a) {
                 a.sllh[(size_t)r * M::NP + i] = 0.0;
             }
             grp.sync();
-#pragma unroll 1
-            for (int m = 0; m < CPL; ++m) {
-                const int col = lane + m * G;
-                if (col < 1 || col > io.ns) continue;
+            for (int col = lane; col <= io.ns; col += G) {
+                if (col < 1) continue;
                 const int ip = sh->plist[col - 1];
                 const int ssim = a.pscale_sim[cp + ip];
                 const int jopt = a.mapping[cp + ip];
                 const double pu = sh->p[ip];
                 // ReturnData::applyChainRuleFactorToSimulationResults (rdata.cpp:672-686, 706-708)
-                double s = sllh[m];
+                double s = sh->sllh[col];
                 if (ssim == 2) s *= pu * PB_LN10;
                 else if (ssim == 1) s *= pu;
                 a.sllh[(size_t)r * M::NP + (col - 1)] = s;
@@ -232,51 +228,59 @@ const ModelOps* find_model(const char* name);
 int model_count();
 const ModelOps* model_at(int i);
 
-constexpr int PB_THREADS = 128;
+constexpr int PB_THREADS = 64;
 
-template <class M, int G, int CPL>
+template <class M, int G>
 int launch_one(const KernelArgs& a, int sm_count, cudaStream_t stream, int* grid_used, int* block_used) {
-    auto kern = simulate_kernel<M, G, CPL, PB_THREADS>;
+    auto kern = simulate_kernel<M, G, PB_THREADS>;
+    const int groups_per_block = PB_THREADS / G;
+    const size_t smem = (G == 1) ? 0 : sizeof(GroupShared<M>) * groups_per_block;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set && smem > 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PB_THREADS, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PB_THREADS, smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) per_sm = 1;
-    const int groups_per_block = PB_THREADS / G;
     int grid = sm_count * per_sm;  // persistent: one resident wave, work queue inside
     const int needed = (a.n + groups_per_block - 1) / groups_per_block;
     if (grid > needed) grid = needed;
     if (grid < 1) grid = 1;
-    kern<<<grid, PB_THREADS, 0, stream>>>(a);
+    kern<<<grid, PB_THREADS, smem, stream>>>(a);
     if (grid_used) *grid_used = grid;
     if (block_used) *block_used = PB_THREADS;
     return (int)cudaGetLastError();
 }
 
 constexpr int pb_pow2_at_least(int n) { return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32; }
-constexpr int pb_cpl(int ncol, int g) { return (ncol + g - 1) / g; }
 
-/// Instantiations offered per model: cost-only (G=1, one column), and for gradients the
-/// default group size G0 = pow2 >= NP+1 (capped at 32, one column per lane when it fits)
-/// plus a full-warp variant (G=32).
+/// Instantiations offered per model: cost-only (G=1: the only column is the state), and for
+/// gradients the default group size G0 = pow2 >= NP+1 (capped at 32: one column per lane when
+/// it fits), plus G0/2 (two columns on some lanes, twice the conditions per warp) and a
+/// full-warp variant.
 template <class M>
 int launch_model(const KernelArgs& a, int lanes, int sm_count, cudaStream_t stream, int* lanes_used, int* grid_used,
                  int* block_used) {
     constexpr int NCOL = M::NP + 1;
     constexpr int G0 = pb_pow2_at_least(NCOL);
+    constexpr int GH = G0 >= 4 ? G0 / 2 : G0;
     if (!a.want_grad) {
         if (lanes_used) *lanes_used = 1;
-        return launch_one<M, 1, 1>(a, sm_count, stream, grid_used, block_used);
-    }
-    if (lanes == 1) {  // one thread per condition: all columns in the thread's local memory
-        if (lanes_used) *lanes_used = 1;
-        return launch_one<M, 1, NCOL>(a, sm_count, stream, grid_used, block_used);
+        return launch_one<M, 1>(a, sm_count, stream, grid_used, block_used);
     }
     if (lanes == 32 && G0 != 32) {
         if (lanes_used) *lanes_used = 32;
-        return launch_one<M, 32, pb_cpl(NCOL, 32)>(a, sm_count, stream, grid_used, block_used);
+        return launch_one<M, 32>(a, sm_count, stream, grid_used, block_used);
+    }
+    if (lanes == GH && GH != G0) {
+        if (lanes_used) *lanes_used = GH;
+        return launch_one<M, GH>(a, sm_count, stream, grid_used, block_used);
     }
     if (lanes_used) *lanes_used = G0;
-    return launch_one<M, G0, pb_cpl(NCOL, G0)>(a, sm_count, stream, grid_used, block_used);
+    return launch_one<M, G0>(a, sm_count, stream, grid_used, block_used);
 }
 
 template <class M>

@@ -14,11 +14,21 @@
 // is 1 and the loop folds away; with several columns per lane (few lanes per condition) the
 // body is emitted once and the columns live in local memory.
 #define PB_ROLL _Pragma("unroll 1")
+// loops over the state index in the hot path: partially unrolled only -- the kernels are
+// instruction-fetch bound when warps on an SM run different conditions, so the static size of
+// the step loop matters more than loop overhead (profiles/r01_b_summary.txt)
+#ifndef PB_X_UNROLL
+#define PB_X_UNROLL 2
+#endif
+#define PB_STR_(x) #x
+#define PB_STR(x) PB_STR_(x)
+#define PB_UNROLL_X _Pragma(PB_STR(unroll PB_X_UNROLL))
 #else
 #define PB_HD inline
 #define PB_HD_NOINLINE
 #define PB_UNROLL
 #define PB_ROLL
+#define PB_UNROLL_X
 #endif
 
 // Make a value opaque to the optimiser: stops it from cloning a large code region once per

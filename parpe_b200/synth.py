@@ -33,7 +33,9 @@ def condition_constants(model: str, C: int, rng: np.random.Generator) -> np.ndar
     elif model == "fujita":
         k[:, 0] = np.array([0.1, 0.3, 1.0, 3.0, 10.0, 30.0])[np.arange(C) % 6]
     elif model == "boehm":
-        k[:, 0] = 0.693 * (1.0 + 0.02 * rng.standard_normal(C))
+        import os
+        if not os.environ.get("PB200_IDENTICAL_CONDITIONS"):
+            k[:, 0] = 0.693 * (1.0 + 0.02 * rng.standard_normal(C))
     return k
 
 

@@ -21,9 +21,8 @@ template <class M>
 static int run(const double* p_unscaled, const double* k, const int* plist, int ns, int nt, const double* t,
                const double* my, const double* sd, double t0, double rtol, double atol, int maxsteps, int stldet,
                int errconS, double* llh, double* sllh, int64_t* stats, double* y_out, double* sigmay_out, int* trace) {
-    constexpr int CPL = M::NP + 1;
     static thread_local GroupShared<M> sh;
-    static thread_local Bdf<M, SingleLane, CPL> bdf;
+    static thread_local Bdf<M, SingleLane> bdf;
     bdf.sh = &sh;
     for (int i = 0; i < M::NP; ++i) sh.p[i] = p_unscaled[i];
     for (int i = 0; i < M::NK; ++i) sh.k[i] = k[i];
@@ -33,9 +32,8 @@ static int run(const double* p_unscaled, const double* k, const int* plist, int 
     bdf.opt.stldet = stldet;
     bdf.opt.errconS = errconS;
     ConditionIO io{nt, t, my, sd, ns, y_out, sigmay_out, trace};
-    double s[CPL];
-    int status = bdf.simulate(io, rtol, atol, *llh, s);
-    for (int j = 0; j < ns; ++j) sllh[j] = s[j + 1];
+    int status = bdf.simulate(io, rtol, atol, *llh);
+    for (int j = 0; j < ns; ++j) sllh[j] = sh.sllh[j + 1];
     bdf.export_stats(stats, 1);
     return status;
 }
