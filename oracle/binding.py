@@ -48,6 +48,17 @@ def lib():
             f.argtypes = [C.c_double, C.c_int]
         L.ora_apply_chain_rule.restype = C.c_double
         L.ora_apply_chain_rule.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
+        i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+        L.ora_hier_compute_one.restype = C.c_double
+        L.ora_hier_compute_one.argtypes = [C.c_int, C.c_int, C.c_int, i32p, C.c_int, C.c_int, i64p, dp, dp, C.c_int]
+        L.ora_hier_apply_one.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, i32p, C.c_int, C.c_int, i64p, dp, C.c_int]
+        L.ora_hier_nllh.restype = C.c_double
+        L.ora_hier_nllh.argtypes = [C.c_int, i64p, dp, dp, dp]
+        L.ora_hier_splice.argtypes = [dp, C.c_int, i32p, C.c_int, i32p, C.c_int, i32p, C.c_int, dp, dp, dp, dp]
+        L.ora_hier_filter.argtypes = [dp, C.c_int, i32p, C.c_int, dp]
+        for f in (L.ora_hier_default_scaling, L.ora_hier_default_offset):
+            f.restype = C.c_double
+            f.argtypes = [C.c_int]
         L.ora_hier_attach.argtypes = [C.c_void_p, C.POINTER(HierDesc)]
         L.ora_hier_num_outer.argtypes = [C.c_void_p]
         L.ora_hier_evaluate.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_int]
@@ -143,3 +154,66 @@ class OracleProblem:
         if rc < 0:
             raise RuntimeError(lib().ora_last_error().decode())
         return dict(status=rc, fval=fval.value, grad=grad, full_parameters=full)
+
+
+# ---- hierarchical free functions (restated reference functions) on plain lists ------------
+def _flatten(mat):
+    off = np.concatenate([[0], np.cumsum([len(r) for r in mat])]).astype(np.int64)
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.float64) for r in mat]))
+    return flat, off
+
+
+def _rows(rows):
+    return np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, 3)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def hier_compute(kind, param_idx, rows, outputs, measurements, ny):
+    """kind: 'scaling' | 'offset' | 'sigma' (computeAnalytical{Scalings,Offsets,Sigmas})."""
+    r = _rows(rows)
+    o, off = _flatten(outputs)
+    m, _ = _flatten(measurements)
+    n_param = int(r[:, 0].max()) + 1
+    k = {"scaling": 0, "offset": 1, "sigma": 2}[kind]
+    return lib().ora_hier_compute_one(k, param_idx, n_param, r.ctypes.data_as(C.POINTER(C.c_int32)), len(r),
+                                      len(outputs), off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(o), _dp(m), ny)
+
+
+def hier_apply(mode, param_idx, value, rows, outputs, ny):
+    """mode: 'scaling' | 'offset' (applyOptimalScaling / applyOptimalOffset); returns new outputs."""
+    r = _rows(rows)
+    o, off = _flatten(outputs)
+    n_param = int(r[:, 0].max()) + 1
+    lib().ora_hier_apply_one(0 if mode == "scaling" else 1, param_idx, float(value), n_param,
+                             r.ctypes.data_as(C.POINTER(C.c_int32)), len(r), len(outputs),
+                             off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(o), ny)
+    return [o[off[c]:off[c + 1]].tolist() for c in range(len(outputs))]
+
+
+def hier_nllh(measurements, outputs, sigmas):
+    m, off = _flatten(measurements)
+    o, _ = _flatten(outputs)
+    s, _ = _flatten(sigmas)
+    return lib().ora_hier_nllh(len(measurements), off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(m), _dp(o), _dp(s))
+
+
+def hier_splice(reduced, scaling_idx, offset_idx, sigma_idx, scalings, offsets, sigmas):
+    red = np.ascontiguousarray(reduced, dtype=np.float64)
+    si, oi, gi = _i32(scaling_idx), _i32(offset_idx), _i32(sigma_idx)
+    sv, ov, gv = (np.ascontiguousarray(v, dtype=np.float64) for v in (scalings, offsets, sigmas))
+    full = np.zeros(len(red) + len(si) + len(oi) + len(gi))
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    lib().ora_hier_splice(_dp(red), len(red), P(si), len(si), P(oi), len(oi), P(gi), len(gi), _dp(sv), _dp(ov),
+                          _dp(gv), _dp(full))
+    return full
+
+
+def hier_filter(values, sorted_excl):
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    e = _i32(sorted_excl)
+    out = np.zeros(len(v) - len(e))
+    lib().ora_hier_filter(_dp(v), len(v), e.ctypes.data_as(C.POINTER(C.c_int32)), len(e), _dp(out))
+    return out

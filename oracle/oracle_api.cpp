@@ -190,6 +190,57 @@ double ora_apply_chain_rule(double g, double p, int oldScale, int newScale) {
     return applyChainRule(g, p, oldScale, newScale);
 }
 
+// ---- hierarchical free functions on caller-supplied outputs (known-answer tests) ----------
+// outputs / measurements: [n_conditions][nt_c * ny] flattened with offsets[n_conditions+1]
+namespace {
+Matrix toMatrix(const double* flat, const int64_t* off, int C) {
+    Matrix m(C);
+    for (int c = 0; c < C; ++c) m[c].assign(flat + off[c], flat + off[c + 1]);
+    return m;
+}
+AnalyticalParameterProvider provider(int n_param, const int32_t* rows, int n_rows) {
+    std::vector<int32_t> idx(n_param);
+    for (int i = 0; i < n_param; ++i) idx[i] = i;
+    return AnalyticalParameterProvider::fromRows(idx.data(), n_param, rows, n_rows);
+}
+}  // namespace
+
+// kind: 0 scaling, 1 offset, 2 sigma
+double ora_hier_compute_one(int kind, int param_idx, int n_param, const int32_t* rows, int n_rows, int C,
+                            const int64_t* off, const double* outputs, const double* measurements, int ny) {
+    auto prov = provider(n_param, rows, n_rows);
+    auto out = toMatrix(outputs, off, C), mes = toMatrix(measurements, off, C);
+    if (kind == 0) return computeAnalyticalScalings(param_idx, out, mes, prov, ny);
+    if (kind == 1) return computeAnalyticalOffsets(param_idx, out, mes, prov, ny);
+    return computeAnalyticalSigmas(param_idx, out, mes, prov, ny);
+}
+// mode: 0 scaling (multiply), 1 offset (add); outputs modified in place
+void ora_hier_apply_one(int mode, int param_idx, double value, int n_param, const int32_t* rows, int n_rows, int C,
+                        const int64_t* off, double* outputs, int ny) {
+    auto prov = provider(n_param, rows, n_rows);
+    auto out = toMatrix(outputs, off, C);
+    if (mode == 0) applyOptimalScaling(param_idx, value, out, prov, ny);
+    else applyOptimalOffset(param_idx, value, out, prov, ny);
+    for (int c = 0; c < C; ++c) std::memcpy(outputs + off[c], out[c].data(), out[c].size() * sizeof(double));
+}
+double ora_hier_nllh(int C, const int64_t* off, const double* measurements, const double* outputs,
+                     const double* sigmas) {
+    return computeNegLogLikelihood(toMatrix(measurements, off, C), toMatrix(outputs, off, C), toMatrix(sigmas, off, C));
+}
+void ora_hier_splice(const double* reduced, int n_reduced, const int32_t* si, int ns, const int32_t* oi, int no,
+                     const int32_t* gi, int ng, const double* sv, const double* ov, const double* gv, double* full) {
+    auto f = spliceParameters(std::vector<double>(reduced, reduced + n_reduced), std::vector<int>(si, si + ns),
+                              std::vector<int>(oi, oi + no), std::vector<int>(gi, gi + ng),
+                              std::vector<double>(sv, sv + ns), std::vector<double>(ov, ov + no),
+                              std::vector<double>(gv, gv + ng));
+    std::memcpy(full, f.data(), f.size() * sizeof(double));
+}
+void ora_hier_filter(const double* values, int n, const int32_t* excl, int n_excl, double* result) {
+    fillFilteredParams(std::vector<double>(values, values + n), std::vector<int>(excl, excl + n_excl), result);
+}
+double ora_hier_default_scaling(int scale) { return getDefaultScalingFactor(scale); }
+double ora_hier_default_offset(int scale) { return getDefaultOffsetParameter(scale); }
+
 // ---- hierarchical (A15) --------------------------------------------------
 int ora_hier_attach(ora_problem* h, const pb200_hier_desc* hd) {
     try {

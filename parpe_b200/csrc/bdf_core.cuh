@@ -219,19 +219,14 @@ PB_HD_NOINLINE static double group_max(const Grp& g, double v) { return g.max(v)
 /// max_columns sqrt(mean((v*w)^2)) (N_VWrmsNorm; cvSensNorm cvodes.c:9427-9441)
 template <class Grp>
 PB_HD_NOINLINE static double group_wrms(const Grp& g, double ssq_local, int n) {
-    return sqrt(g.max(ssq_local) / n);
+    return sqrt(pb_div(g.max(ssq_local), (double)n));
 }
 
-/// J(t, y) -> Jdst (dense column-major, NX*NX), everything in group-shared memory
+/// J(t, y) -> the structurally non-zero entries of Jdst (dense column-major, NX*NX), everything
+/// in group-shared memory; the structural zeros are written once per condition (simulate()).
 template <class M>
-PB_HD_NOINLINE static bool eval_jac_shared(double* Jdst, double t, const double* y, const GroupShared<M>* sh) {
-    PB_ROLL
-    for (int i = 0; i < M::NX * M::NX; ++i) Jdst[i] = 0.0;
+PB_HD_NOINLINE static void eval_jac_shared(double* Jdst, double t, const double* y, const GroupShared<M>* sh) {
     M::jac(Jdst, t, y, sh->p, sh->k);
-    bool ok = true;
-    PB_ROLL
-    for (int i = 0; i < M::NX * M::NX; ++i) ok = ok && isfinite(Jdst[i]);
-    return ok;
 }
 
 /// LU = I - gamma*Jsaved, factorised in place with partial pivoting, column-oriented
@@ -261,7 +256,7 @@ PB_HD_NOINLINE static int lu_factor_shared(GroupShared<M>* sh, double gamma) {
                 sh->LU[k + i * NX] = t_;
             }
         }
-        const double mult = 1.0 / col_k[k];
+        const double mult = pb_rcp(col_k[k]);
         PB_ROLL
         for (int i = k + 1; i < NX; ++i) col_k[i] *= mult;
         PB_ROLL
@@ -311,7 +306,7 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
         double sumrat = 0.0, sumrsq = 0.0;
         PB_ROLL
         for (int i = 1; i <= 4; ++i) {
-            rat[i][k] = ss[i][k] / ss[i + 1][k];
+            rat[i][k] = pb_div(ss[i][k], ss[i + 1][k]);
             sumrat += rat[i][k];
             sumrsq += rat[i][k] * rat[i][k];
         }
@@ -329,7 +324,7 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
     const double vmax = fmax(vrat[1], fmax(vrat[2], vrat[3]));
     if (vmin < vrrtol * vrrtol) {
         if (vmax > vrrt2 * vrrt2) return -2;
-        rr = (rav[1] + rav[2] + rav[3]) / 3.0;
+        rr = pb_div(rav[1] + rav[2] + rav[3], 3.0);
         double drrmax = 0.0;
         PB_ROLL
         for (int k = 1; k <= 3; ++k) drrmax = fmax(drrmax, fabs(rav[k] - rr));
@@ -337,27 +332,27 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
         kflag = 1;
     } else {
         if (fabs(qco[1][1]) < cv::TINY * ssmax[1]) return -4;
-        double tem = qco[1][2] / qco[1][1];
+        double tem = pb_div(qco[1][2], qco[1][1]);
         PB_ROLL
         for (int i = 2; i <= 5; ++i) qco[i][2] -= tem * qco[i][1];
         qco[1][2] = 0.0;
-        tem = qco[1][3] / qco[1][1];
+        tem = pb_div(qco[1][3], qco[1][1]);
         PB_ROLL
         for (int i = 2; i <= 5; ++i) qco[i][3] -= tem * qco[i][1];
         qco[1][3] = 0.0;
         if (fabs(qco[2][2]) < cv::TINY * ssmax[2]) return -4;
-        tem = qco[2][3] / qco[2][2];
+        tem = pb_div(qco[2][3], qco[2][2]);
         PB_ROLL
         for (int i = 3; i <= 5; ++i) qco[i][3] -= tem * qco[i][2];
         if (fabs(qco[4][3]) < cv::TINY * ssmax[3]) return -4;
-        rr = -qco[5][3] / qco[4][3];
+        rr = pb_div(-qco[5][3], qco[4][3]);
         if (rr < cv::TINY || rr > 100.0) return -5;
         PB_ROLL
         for (int k = 1; k <= 3; ++k) qkr[k] = qc[5][k] + rr * (qc[4][k] + rr * rr * (qc[2][k] + rr * qc[1][k]));
         double sqmax = 0.0;
         PB_ROLL
         for (int k = 1; k <= 3; ++k) {
-            const double saqk = fabs(qkr[k]) / ssmax[k];
+            const double saqk = pb_div(fabs(qkr[k]), ssmax[k]);
             if (saqk > sqmax) sqmax = saqk;
         }
         if (sqmax < sqtol) {
@@ -369,7 +364,7 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
                 for (int k = 1; k <= 3; ++k) {
                     const double qp = qc[4][k] + rr * rr * (3.0 * qc[2][k] + rr * 4.0 * qc[1][k]);
                     drr[k] = 0.0;
-                    if (fabs(qp) > cv::TINY * ssmax[k]) drr[k] = -qkr[k] / qp;
+                    if (fabs(qp) > cv::TINY * ssmax[k]) drr[k] = pb_div(-qkr[k], qp);
                     rrc[k] = rr + drr[k];
                 }
                 PB_ROLL
@@ -379,7 +374,7 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
                     PB_ROLL
                     for (int j = 1; j <= 3; ++j) {
                         qjk[j][k] = qc[5][j] + s * (qc[4][j] + s * s * (qc[2][j] + s * qc[1][j]));
-                        const double saqj = fabs(qjk[j][k]) / ssmax[j];
+                        const double saqj = pb_div(fabs(qjk[j][k]), ssmax[j]);
                         if (saqj > sqmaxk) sqmaxk = saqj;
                     }
                     sqmx[k] = sqmaxk;
@@ -414,20 +409,20 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
         const double rd2a = rd1a - rd1b, rd2b = rd1b - rd1c;
         const double rd3a = rd2a - rd2b;
         if (fabs(rd1b) < cv::TINY * smax[k]) return -7;
-        const double cest1 = -rd3a / rd1b;
+        const double cest1 = pb_div(-rd3a, rd1b);
         if (cest1 < cv::TINY || cest1 > 4.0) return -7;
-        const double corr1 = (rd2b / cest1) / (rr * rr);
+        const double corr1 = pb_div(pb_div(rd2b, cest1), rr * rr);
         sigsq[k] = ss[3][k] + corr1;
     }
     if (sigsq[2] < cv::TINY) return -8;
-    const double ratp = sigsq[3] / sigsq[2];
-    const double ratm = sigsq[1] / sigsq[2];
+    const double ratp = pb_div(sigsq[3], sigsq[2]);
+    const double ratm = pb_div(sigsq[1], sigsq[2]);
     const double qfac1 = 0.25 * (q * q - 1.0);
-    const double qfac2 = 2.0 / (q - 1.0);
+    const double qfac2 = pb_div(2.0, q - 1.0);
     const double bb = ratp * ratm - 1.0 - qfac1 * ratp;
     const double tem = 1.0 - qfac2 * bb;
     if (fabs(tem) < cv::TINY) return -8;
-    const double rrb = 1.0 / tem;
+    const double rrb = pb_rcp(tem);
     if (fabs(rrb - rr) > rrtol) return -9;
     if (rr > rrcut) {
         if (kflag == 1) kflag = 4;
@@ -458,7 +453,7 @@ PB_HD_NOINLINE static double wnorm_shared(const GroupShared<M>* sh, const Grp& g
         }
         if (s > loc) loc = s;
     }
-    return sqrt(g.max(loc) / NX);
+    return sqrt(pb_div(g.max(loc), (double)NX));
 }
 
 /// Per-condition inputs (device pointers into the resident tables).
@@ -618,12 +613,16 @@ struct Bdf {
                           (convfail == cv::FAIL_OTHER);
         int ret = 0;
         g.sync();
-        if (g.lane() == 0) {
-            if (jbad) {
-                if (!eval_jac_shared<M>(sh->Jsaved, tn, sh->yj, sh)) ret = 1;
-            }
-            if (ret == 0) ret = lu_factor_shared<M>(sh, gamma);
+        if (jbad) {
+            if (g.lane() == 0) eval_jac_shared<M>(sh->Jsaved, tn, sh->yj, sh);
+            g.sync();
+            // AMICI's fJ callback returns checkFinite(J): recoverable if not finite
+            double bad = 0.0;
+            for (int e = g.lane(); e < NX * NX; e += G)
+                if (!isfinite(sh->Jsaved[e])) bad = 1.0;
+            if (group_max(g, bad) != 0.0) ret = 1;
         }
+        if (g.lane() == 0 && ret == 0) ret = lu_factor_shared<M>(sh, gamma);
         if (jbad) { nje++; nstlj = nst; }
         jcur = jbad;
         nsetups++;
@@ -1457,6 +1456,10 @@ struct Bdf {
         jcur = jcurNLS = jcurNLSS = false;
         tstopset = false; tstop = 0.0;
         nfe = nsetups = nje = nni = nniS = nfSe = netf = netfS = ncfn = ncfnS = nor = qsum = 0;
+        for (int e = g.lane(); e < NX * NX; e += G) {
+            sh->Jsaved[e] = 0.0;
+            sh->Jcur[e] = 0.0;
+        }
         if (g.lane() == 0) {
             for (int i = 0; i <= cv::L_MAX; ++i) { sh->l[i] = 0.0; sh->tau[i] = 0.0; }
             for (int i = 0; i < 6; ++i) sh->tq[i] = 0.0;

@@ -155,3 +155,38 @@ def fujita_hierarchical(n_conditions: int, seed: int = 0, **kw) -> ProblemTables
     tab.hier = HierTables(scaling_idx=sc, offset_idx=[], sigma_idx=sg, scaling_map=rows(),
                           offset_map=np.zeros((0, 3), np.int32), sigma_map=rows())
     return tab
+
+
+def steadystate_hierarchical(n_conditions: int, seed: int = 0, **kw) -> ProblemTables:
+    """parPE's steadystate example with hierarchical optimisation (BASELINE config 0,
+    examples/parpeamici/steadystate/create_steadystate_amici_model.py): one scaling parameter
+    (obs_x1_scaled, log10), two batch-specific offsets (obs_x2_offsetted, linear; odd and even
+    conditions), one sigma (obs_x1withsigma, log10)."""
+    tab = make_problem("steadystate_scaled", n_conditions, scale="log10", seed=seed, condition_specific=0, **kw)
+    spec = get_spec("steadystate_scaled")
+    names = [str(s) for s in spec.params]
+    i_scal = names.index("observableParameter1_obs_x1_scaled")
+    i_off = names.index("observableParameter1_obs_x2_offsetted")
+    i_sig = names.index("noiseParameter1_obs_x1withsigma")
+    C = n_conditions
+    n_opt = tab.np_ + 1
+    mapping = tab.mapping.copy()
+    mapping[1::2, i_off] = tab.np_  # second batch -> its own offset parameter
+    pscale_opt = np.full(n_opt, SCALE_LOG10, dtype=np.int32)
+    pscale_opt[[i_off, tab.np_]] = SCALE_NONE
+    pscale_sim = np.full((C, tab.np_), SCALE_LOG10, dtype=np.int32)
+    pscale_sim[:, i_off] = SCALE_NONE
+    sigma = tab.sigma.reshape(-1, tab.ny).copy()
+    sigma[:, :5] = 0.1      # sigmas from the data table, except the observable with a sigma parameter
+    sigma[:, 5] = np.nan
+    new = ProblemTables(model_name=tab.model_name, np_=tab.np_, nk=tab.nk, ny=tab.ny, n_opt=n_opt,
+                        t_offsets=tab.t_offsets, t=tab.t, y=tab.y, sigma=sigma, k=tab.k, mapping=mapping,
+                        pscale_sim=pscale_sim, pscale_opt=pscale_opt, rtol=tab.rtol, atol=tab.atol)
+    even = [c for c in range(C) if c % 2 == 0]
+    odd = [c for c in range(C) if c % 2 == 1]
+    new.hier = HierTables(
+        scaling_idx=[i_scal], offset_idx=[i_off, tab.np_], sigma_idx=[i_sig],
+        scaling_map=[[0, c, 3] for c in range(C)],
+        offset_map=[[0, c, 4] for c in even] + [[1, c, 4] for c in odd],
+        sigma_map=[[0, c, 5] for c in range(C)])
+    return new

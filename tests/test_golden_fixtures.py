@@ -1,0 +1,80 @@
+"""Committed reference outputs (tests/golden/*.json, made by tools/make_golden.py with the reference's
+own AMICI/CVODES build) against: the oracle as built now, the host build of the device core, and --
+on a GPU -- the CUDA path through the C ABI.  The GPU box has no /root/reference; these fixtures are
+how reference outputs reach it."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from parpe_b200 import synth
+from parpe_b200.tables import SCALE_LN, SCALE_LOG10
+from tests.util import assert_grad_close, assert_llh_close
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.json")))
+
+
+def _load(path):
+    doc = json.load(open(path))
+    tab = synth.make_problem(doc["model"], doc["n_conditions"], **doc["kwargs"])
+    return doc, tab, np.array(doc["theta"])
+
+
+def test_fixtures_exist():
+    assert len(FILES) >= 4
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-5] for f in FILES])
+def test_oracle_reproduces_fixture(oracle_available, path):
+    from oracle.binding import OracleProblem
+    doc, tab, theta = _load(path)
+    r = OracleProblem(tab).evaluate(theta)
+    assert r["fval"] == pytest.approx(doc["nllh"], rel=1e-10)
+    np.testing.assert_allclose(r["grad"], doc["grad"], rtol=1e-7, atol=1e-9 * np.max(np.abs(doc["grad"])))
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-5] for f in FILES])
+def test_host_core_against_fixture(path):
+    """No oracle library needed: device algorithm (host build) vs committed reference outputs."""
+    from tests.host_harness.binding import simulate
+    doc, tab, theta = _load(path)
+    for c in range(tab.n_conditions):
+        p = np.empty(tab.np_)
+        for i in range(tab.np_):
+            j = tab.mapping[c, i]
+            lin = 10.0 ** theta[j] if tab.pscale_opt[j] == SCALE_LOG10 else (
+                np.exp(theta[j]) if tab.pscale_opt[j] == SCALE_LN else theta[j])
+            p[i] = lin
+        plist = [i for i in range(tab.np_) if tab.mapping[c, i] >= 0]
+        lo, hi = tab.t_offsets[c], tab.t_offsets[c + 1]
+        r = simulate(doc["model"], p, tab.k[c], plist, tab.t[lo:hi], tab.y_of(c), tab.sigma_of(c))
+        assert r["status"] == 0
+        assert_llh_close(r["llh"], doc["llh"][c])
+        fac = np.array([p[i] * np.log(10) if tab.pscale_sim[c, i] == SCALE_LOG10 else
+                        (p[i] if tab.pscale_sim[c, i] == SCALE_LN else 1.0) for i in plist])
+        assert_grad_close(r["sllh"] * fac, np.array(doc["sllh"][c])[:len(plist)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-5] for f in FILES])
+def test_cuda_path_against_fixture(path):
+    from parpe_b200.problem import B200SummedGradientFunction
+    doc, tab, theta = _load(path)
+    gpu = B200SummedGradientFunction(tab)
+    st, fval, grad, _ = gpu.evaluate(theta)
+    assert st == 0
+    assert_llh_close(fval, doc["nllh"])
+    assert_grad_close(grad, doc["grad"])
+    res = gpu.condition_results()
+    assert_llh_close(res["llh"], doc["llh"])
+    st, fs, gs, _ = gpu.evaluate(theta, doc["subset"])
+    assert_llh_close(fs, doc["subset_nllh"])
+    assert_grad_close(gs, doc["subset_grad"])
+    rc, y, s = gpu.getModelOutputsAndSigmas(theta)
+    assert rc == 0
+    yref = np.array([np.nan if v is None else v for v in doc["y"]])
+    np.testing.assert_allclose(y, yref, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(s, np.array([np.nan if v is None else v for v in doc["sigmay"]]), rtol=1e-12)

@@ -16,7 +16,7 @@ for line in sass.split("\n"):
         kern = m.group(1); continue
     if re.match(r'\s+/\*[0-9a-f]{4,}\*/', line) and kern and pat in kern:
         counts[cur] += 1
-root = os.path.dirname(os.path.abspath(__file__))
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = open(os.path.join(root, "parpe_b200/csrc/bdf_core.cuh")).read().split('\n')
 funcs = []
 for i, l in enumerate(src, 1):
