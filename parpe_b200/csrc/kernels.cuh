@@ -271,11 +271,16 @@ int launch_model(const KernelArgs& a, int lanes, int sm_count, cudaStream_t stre
         if (lanes_used) *lanes_used = 1;
         return launch_one<M, 1>(a, sm_count, stream, grid_used, block_used);
     }
-    if (lanes == 32 && G0 != 32) {
+    // default: one warp per condition once there are >= 9 columns (measured: with divergent
+    // trajectories a full warp per condition beats two half-warp groups that serialise,
+    // profiles/r01_c_summary.txt); the pow2 group for narrower models
+    constexpr int GDEF = (NCOL >= 9) ? 32 : G0;
+    const int want = lanes > 0 ? lanes : GDEF;
+    if (want == 32 || G0 == 32) {
         if (lanes_used) *lanes_used = 32;
         return launch_one<M, 32>(a, sm_count, stream, grid_used, block_used);
     }
-    if (lanes == GH && GH != G0) {
+    if (want == GH && GH != G0) {
         if (lanes_used) *lanes_used = GH;
         return launch_one<M, GH>(a, sm_count, stream, grid_used, block_used);
     }
@@ -288,7 +293,7 @@ ModelOps make_ops() {
     ModelOps o;
     o.name = M::NAME;
     o.nx = M::NX; o.np = M::NP; o.nk = M::NK; o.ny = M::NY;
-    o.default_lanes = pb_pow2_at_least(M::NP + 1);
+    o.default_lanes = (M::NP + 1 >= 9) ? 32 : pb_pow2_at_least(M::NP + 1);
     o.flops_xdot = M::FLOPS_XDOT; o.flops_J = M::FLOPS_J; o.flops_dxdotdp = M::FLOPS_DXDOTDP; o.nnzJ = M::NNZ;
     o.launch = &launch_model<M>;
     return o;

@@ -1,0 +1,219 @@
+// b200SummedGradientFunction.h -- header-only C++ host side of the drop-in boundary.
+//
+// parpe::B200SummedGradientFunction implements parpe::SummedGradientFunction<int> with the public
+// surface of parpe::AmiciSummedGradientFunction that callers use
+// (include/parpeamici/multiConditionProblem.h:95-237): evaluate (vector and single-index
+// overloads), numParameters, getParameterIds, getModelOutputsAndSigmas, getAllMeasurements,
+// getParameterScaling.  parpe::B200HierarchicalOptimizationWrapper implements
+// parpe::GradientFunction with the behaviour of parpe::HierarchicalOptimizationWrapper::evaluate
+// (src/parpeamici/hierarchicalOptimization.cpp:142-238).  Both only forward to the C ABI
+// (include/parpe_b200.h); all numerics run in libparpe_b200.so on the GPU.
+//
+// Error conventions are the reference's: a failed simulation yields fval = +infinity and
+// functionEvaluationFailure (multiConditionProblem.cpp:669-672); API misuse (wrong vector
+// sizes) throws, as gsl Expects / ParPEException do in parPE.
+#ifndef PB200_B200_SUMMED_GRADIENT_FUNCTION_H
+#define PB200_B200_SUMMED_GRADIENT_FUNCTION_H
+
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/parpe_b200.h"
+#include "parpe_interfaces.h"
+
+namespace parpe {
+
+/// In-memory problem description: what MultiConditionDataProviderHDF5 serves from the HDF5 input
+/// (doc/hdf5.md), owned as std::vectors; desc() views it as the C struct.
+struct B200ProblemTables {
+    std::string modelName;
+    int numConditions = 0, numOptimizationParameters = 0, np = 0, nk = 0, ny = 0;
+    std::vector<int64_t> tOffsets;            // [C+1]
+    std::vector<double> t, y, sigma;          // y/sigma: row-major obs + it*ny per condition
+    std::vector<double> k;                    // [C*nk]
+    std::vector<int32_t> mapping, pscaleSim;  // [C*np]
+    std::vector<int32_t> pscaleOpt;           // [n_opt]
+    std::vector<double> overrides;            // [C*np] or empty
+    std::vector<std::string> parameterIds;    // /parameters/parameterNames
+    double t0 = 0.0, atol = 1e-16, rtol = 1e-8;
+    int maxSteps = 10000;
+    bool stabilityLimitDetection = true;
+    int numSimulationTrials = 6;                         // PARPE_NUM_SIMULATION_TRIALS
+    double integrationToleranceRelaxationFactor = 100.0; // PARPE_INTEGRATION_TOLERANCE_RELAXATION_FACTOR
+    int lanesPerCondition = 0;
+
+    pb200_problem_desc desc() const {
+        pb200_problem_desc d{};
+        d.abi_version = PB200_ABI_VERSION;
+        d.model_name = modelName.c_str();
+        d.n_conditions = numConditions;
+        d.n_opt = numOptimizationParameters;
+        d.np = np; d.nk = nk; d.ny = ny;
+        d.t_offsets = tOffsets.data();
+        d.t = t.data(); d.y = y.data(); d.sigma = sigma.data(); d.k = k.data();
+        d.mapping = mapping.data(); d.pscale_sim = pscaleSim.data(); d.pscale_opt = pscaleOpt.data();
+        d.overrides = overrides.empty() ? nullptr : overrides.data();
+        d.t0 = t0; d.atol = atol; d.rtol = rtol;
+        d.maxsteps = maxSteps;
+        d.stldet = stabilityLimitDetection ? 1 : 0;
+        d.sensi_errcon = 1;
+        d.num_trials = numSimulationTrials;
+        d.relaxation_factor = integrationToleranceRelaxationFactor;
+        d.lanes_per_condition = lanesPerCondition;
+        return d;
+    }
+};
+
+class B200SummedGradientFunction : public SummedGradientFunction<int> {
+  public:
+    explicit B200SummedGradientFunction(B200ProblemTables tables, int device = 0) : tables_(std::move(tables)) {
+        pb200_problem_desc d = tables_.desc();
+        if (pb200_create(&d, device, &handle_) != 0)
+            throw std::runtime_error(std::string("pb200_create: ") + pb200_last_error());
+    }
+    ~B200SummedGradientFunction() override { pb200_destroy(handle_); }
+    B200SummedGradientFunction(const B200SummedGradientFunction&) = delete;
+    B200SummedGradientFunction& operator=(const B200SummedGradientFunction&) = delete;
+
+    FunctionEvaluationStatus evaluate(gsl::span<const double> parameters, int dataset, double& fval,
+                                      gsl::span<double> gradient, Logger* logger, double* cpuTime) const override {
+        return evaluate(parameters, std::vector<int>{dataset}, fval, gradient, logger, cpuTime);
+    }
+
+    FunctionEvaluationStatus evaluate(gsl::span<const double> parameters, std::vector<int> datasets, double& fval,
+                                      gsl::span<double> gradient, Logger* /*logger*/,
+                                      double* cpuTime) const override {
+        if (!gradient.empty() && gradient.size() != parameters.size())
+            throw std::invalid_argument("gradient size does not match parameter vector");
+        double seconds = 0.0;
+        const int rc = pb200_evaluate(handle_, parameters.data(), static_cast<int>(parameters.size()),
+                                      datasets.data(), static_cast<int>(datasets.size()), &fval,
+                                      gradient.empty() ? nullptr : gradient.data(), &seconds);
+        if (rc < 0) throw std::runtime_error(std::string("pb200_evaluate: ") + pb200_last_error());
+        if (cpuTime) *cpuTime = seconds;
+        return rc == PB200_EVAL_SUCCESS ? functionEvaluationSuccess : functionEvaluationFailure;
+    }
+
+    int numParameters() const override { return tables_.numOptimizationParameters; }
+    std::vector<std::string> getParameterIds() const override { return tables_.parameterIds; }
+
+    /// AmiciSummedGradientFunction::getModelOutputsAndSigmas (multiConditionProblem.cpp:506-563)
+    virtual FunctionEvaluationStatus getModelOutputsAndSigmas(gsl::span<const double> parameters,
+                                                              std::vector<std::vector<double>>& modelOutputs,
+                                                              std::vector<std::vector<double>>& modelSigmas,
+                                                              Logger* /*logger*/, double* /*cpuTime*/) const {
+        const size_t n = tables_.y.size();
+        std::vector<double> y(n), s(n);
+        const int rc = pb200_get_model_outputs(handle_, parameters.data(), static_cast<int>(parameters.size()),
+                                               y.data(), s.data());
+        if (rc < 0) throw std::runtime_error(std::string("pb200_get_model_outputs: ") + pb200_last_error());
+        modelOutputs.assign(tables_.numConditions, {});
+        modelSigmas.assign(tables_.numConditions, {});
+        for (int c = 0; c < tables_.numConditions; ++c) {
+            const auto lo = tables_.tOffsets[c] * tables_.ny, hi = tables_.tOffsets[c + 1] * tables_.ny;
+            modelOutputs[c].assign(y.begin() + lo, y.begin() + hi);
+            modelSigmas[c].assign(s.begin() + lo, s.begin() + hi);
+        }
+        return rc == PB200_EVAL_SUCCESS ? functionEvaluationSuccess : functionEvaluationFailure;
+    }
+
+    virtual std::vector<std::vector<double>> getAllMeasurements() const {
+        std::vector<std::vector<double>> m(tables_.numConditions);
+        for (int c = 0; c < tables_.numConditions; ++c)
+            m[c].assign(tables_.y.begin() + tables_.tOffsets[c] * tables_.ny,
+                        tables_.y.begin() + tables_.tOffsets[c + 1] * tables_.ny);
+        return m;
+    }
+
+    /// amici::ParameterScaling of an optimisation parameter: 0 none, 1 ln, 2 log10
+    virtual int getParameterScaling(int parameterIndex) const { return tables_.pscaleOpt.at(parameterIndex); }
+
+    /// all condition indices, as MultiConditionProblem::getTrainingData returns them
+    std::vector<int> getTrainingData() const {
+        std::vector<int> idx(tables_.numConditions);
+        for (int i = 0; i < tables_.numConditions; ++i) idx[i] = i;
+        return idx;
+    }
+
+    pb200_handle* handle() const { return handle_; }
+    const B200ProblemTables& tables() const { return tables_; }
+
+  private:
+    B200ProblemTables tables_;
+    pb200_handle* handle_ = nullptr;
+};
+
+/// (inner parameter, condition, observable) row tables of the hierarchical problem
+struct B200HierarchicalTables {
+    std::vector<int32_t> scalingIdx, offsetIdx, sigmaIdx;  // optimisation-parameter indices, ascending
+    std::vector<int32_t> scalingMap, offsetMap, sigmaMap;  // rows of 3, row-major
+    pb200_hier_desc desc() const {
+        pb200_hier_desc d{};
+        d.n_scaling = static_cast<int32_t>(scalingIdx.size());
+        d.n_offset = static_cast<int32_t>(offsetIdx.size());
+        d.n_sigma = static_cast<int32_t>(sigmaIdx.size());
+        d.scaling_idx = scalingIdx.data(); d.offset_idx = offsetIdx.data(); d.sigma_idx = sigmaIdx.data();
+        d.n_scaling_rows = static_cast<int32_t>(scalingMap.size() / 3);
+        d.n_offset_rows = static_cast<int32_t>(offsetMap.size() / 3);
+        d.n_sigma_rows = static_cast<int32_t>(sigmaMap.size() / 3);
+        d.scaling_map = scalingMap.data(); d.offset_map = offsetMap.data(); d.sigma_map = sigmaMap.data();
+        return d;
+    }
+};
+
+class B200HierarchicalOptimizationWrapper : public GradientFunction {
+  public:
+    B200HierarchicalOptimizationWrapper(B200SummedGradientFunction* wrapped, const B200HierarchicalTables& h)
+        : wrapped_(wrapped) {
+        pb200_hier_desc d = h.desc();
+        if (pb200_hier_attach(wrapped_->handle(), &d) != 0)
+            throw std::runtime_error(std::string("pb200_hier_attach: ") + pb200_last_error());
+        numOuter_ = pb200_hier_num_outer(wrapped_->handle());
+        std::vector<int32_t> inner(h.scalingIdx);
+        inner.insert(inner.end(), h.offsetIdx.begin(), h.offsetIdx.end());
+        inner.insert(inner.end(), h.sigmaIdx.begin(), h.sigmaIdx.end());
+        auto all = wrapped_->getParameterIds();
+        for (int i = 0; i < static_cast<int>(all.size()); ++i) {
+            bool isInner = false;
+            for (auto j : inner) isInner = isInner || (j == i);
+            if (!isInner) outerIds_.push_back(all[i]);
+        }
+    }
+    using GradientFunction::evaluate;
+    FunctionEvaluationStatus evaluate(gsl::span<double const> reducedParameters, double& fval,
+                                      gsl::span<double> gradient, Logger* /*logger*/,
+                                      double* cpuTime) const override {
+        std::vector<double> full;
+        return evaluate(reducedParameters, fval, gradient, full, cpuTime);
+    }
+    /// also returns the spliced full parameter vector (HierarchicalOptimizationWrapper::evaluate
+    /// with fullParameters, hierarchicalOptimization.cpp:142-150)
+    FunctionEvaluationStatus evaluate(gsl::span<double const> reducedParameters, double& fval,
+                                      gsl::span<double> gradient, std::vector<double>& fullParameters,
+                                      double* cpuTime) const {
+        if (static_cast<int>(reducedParameters.size()) != numOuter_)
+            throw std::invalid_argument("Reduced parameter vector size " + std::to_string(reducedParameters.size()) +
+                                        " does not match numParameters " + std::to_string(numOuter_));
+        fullParameters.resize(wrapped_->numParameters());
+        double seconds = 0.0;
+        const int rc = pb200_hier_evaluate(wrapped_->handle(), reducedParameters.data(), numOuter_, &fval,
+                                           gradient.empty() ? nullptr : gradient.data(), fullParameters.data(),
+                                           &seconds);
+        if (rc < 0) throw std::runtime_error(std::string("pb200_hier_evaluate: ") + pb200_last_error());
+        if (cpuTime) *cpuTime += seconds;
+        return rc == PB200_EVAL_SUCCESS ? functionEvaluationSuccess : functionEvaluationFailure;
+    }
+    int numParameters() const override { return numOuter_; }
+    std::vector<std::string> getParameterIds() const override { return outerIds_; }
+
+  private:
+    B200SummedGradientFunction* wrapped_;
+    int numOuter_ = 0;
+    std::vector<std::string> outerIds_;
+};
+
+}  // namespace parpe
+#endif
