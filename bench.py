@@ -46,6 +46,8 @@ def workload_name(n_gpus):
 def make_tables(n_conditions):
     from parpe_b200 import synth
     tab = synth.make_problem(MODEL, n_conditions, scale="log10", seed=0)
+    if os.environ.get("PB200_BENCH_STLDET"):  # experiments only; AMICI's default (on) is the benchmark setting
+        tab.stldet = int(os.environ["PB200_BENCH_STLDET"])
     theta = synth.random_theta(tab, seed=1, width=0.5)
     return tab, theta
 

@@ -251,6 +251,11 @@ def emit_device_header(d: Derived, path: str) -> None:
     A("        (void)t; (void)p; (void)k; (void)x; (void)out;")
     L.extend(_switch_ip(pr, s.nx, d.dxdotdp, "out", "        "))
     A("    }")
+    A("    // all columns of d xdot / d p at once: out[r + ip*NX], structural non-zeros only (caller zero-fills once)")
+    A("    PB_HD static void dxdotdp_dense(double* __restrict__ out, %s) {" % sig)
+    A("        (void)t; (void)p; (void)k; (void)x; (void)out;")
+    L.extend(_nonzero_assign(pr, "out[%d]", [(r + c * s.nx, d.dxdotdp[r, c]) for c in range(s.np) for r in range(s.nx)], "        "))
+    A("    }")
     A("    PB_HD static void y(double* __restrict__ y, %s) {" % sig)
     A("        (void)t; (void)p; (void)k; (void)x;")
     L.extend(_cse_block(pr, ["y[%d]" % i for i in range(s.ny)], list(s.observables), "        "))

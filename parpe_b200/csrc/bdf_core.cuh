@@ -138,6 +138,7 @@ struct SingleLane {
     PB_HD double max(double v) const { return v; }
     PB_HD double bcast0(double v) const { return v; }
     PB_HD int bcast0(int v) const { return v; }
+    PB_HD bool any(bool p) const { return p; }
     PB_HD void sync() const {}
 };
 
@@ -162,6 +163,7 @@ struct LaneGroup {
     }
     __device__ __forceinline__ double bcast0(double v) const { return __shfl_sync(mask, v, base); }
     __device__ __forceinline__ int bcast0(int v) const { return __shfl_sync(mask, v, base); }
+    __device__ __forceinline__ bool any(bool p) const { return (__ballot_sync(mask, p) & mask) != 0u; }
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 };
 #endif
@@ -172,15 +174,19 @@ struct GroupShared {
     static constexpr int NX = M::NX;
     static constexpr int NC = M::NP + 1;  // columns: state + one per model parameter
     // column data, [..][state index][column], column fastest
-    double zn[cv::L_MAX][NX][NC];  // Nordsieck history
-    double acor[NX][NC];           // accumulated corrector update
-    double ewt[NX][NC];            // error weights
-    double b[NX][NC];              // residual / Newton update
+    // element (state index i, column c) of a vector lives at [i * ncol + c], ncol = 1 + number of
+    // sensitivity columns of the current condition: the active elements are contiguous, so the
+    // element-wise history operations run over a flat index with all lanes busy
+    double zn[cv::L_MAX][NX * NC];  // Nordsieck history
+    double acor[NX * NC];           // accumulated corrector update
+    double ewt[NX * NC];            // error weights
+    double b[NX * NC];              // residual / Newton update
     double sllh[NC];               // d llh / d p accumulator per sensitivity column
     // group-uniform data
     double Jsaved[NX * NX];  // Jacobian at its last evaluation (cvLs savedJ)
     double LU[NX * NX];      // factors of I - gamma*J
     double Jcur[NX * NX];    // J(tn, y_n) for the sensitivity right-hand sides
+    double dfdp[NX * (M::NP > 0 ? M::NP : 1)];  // d xdot / d p at (tn, y_n), column ip at [ip*NX]
     double ysh[NX];          // converged state, read by the sensitivity lanes
     double yj[NX];           // state handed to the out-of-line model functions (xdot, Jacobian)
     double fout[NX];         // xdot returned by eval_xdot_shared
@@ -227,6 +233,12 @@ PB_HD_NOINLINE static double group_wrms(const Grp& g, double ssq_local, int n) {
 template <class M>
 PB_HD_NOINLINE static void eval_jac_shared(double* Jdst, double t, const double* y, const GroupShared<M>* sh) {
     M::jac(Jdst, t, y, sh->p, sh->k);
+}
+
+/// d xdot / d p (all columns) at (t, y) -> sh->dfdp, structural non-zeros only
+template <class M>
+PB_HD_NOINLINE static void eval_dfdp_shared(GroupShared<M>* sh, double t, const double* y) {
+    M::dxdotdp_dense(sh->dfdp, t, y, sh->p, sh->k);
 }
 
 /// LU = I - gamma*Jsaved, factorised in place with partial pivoting, column-oriented
@@ -439,16 +451,16 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
 /// cvSensNorm for the sensitivities, cvSensUpdateNorm for both (cvodes.c:9427-9457).  One copy
 /// of the code serves every call site.
 template <class M, class Grp>
-PB_HD_NOINLINE static double wnorm_shared(const GroupShared<M>* sh, const Grp& g, int cmin, int cmax, const double* A,
-                                          double ca, const double* B, double cb) {
-    constexpr int NX = M::NX, NC = GroupShared<M>::NC;
+PB_HD_NOINLINE static double wnorm_shared(const GroupShared<M>* sh, const Grp& g, int NC, int cmin, int cmax,
+                                          const double* A, double ca, const double* B, double cb) {
+    constexpr int NX = M::NX;
     double loc = 0.0;
     for (int c = g.lane(); c <= cmax; c += Grp::G) {
         if (c < cmin) continue;
         double s = 0.0;
         PB_UNROLL_X
         for (int i = 0; i < NX; ++i) {
-            const double prod = (ca * A[i * NC + c] + cb * B[i * NC + c]) * sh->ewt[i][c];
+            const double prod = (ca * A[i * NC + c] + cb * B[i * NC + c]) * sh->ewt[i * NC + c];
             s += prod * prod;
         }
         if (s > loc) loc = s;
@@ -480,6 +492,7 @@ struct Bdf {
     GroupShared<M>* sh;
     SolverOptions opt;
     int ns;      // sensitivity columns (columns 1..ns; column 0 is the state)
+    int ncol;    // 1 + ns: row stride of the column data in shared memory
     bool sensi;  // ns > 0
 
     // integrator scalars (uniform within the group)
@@ -489,23 +502,30 @@ struct Bdf {
     bool jcur, jcurNLS, jcurNLSS, tstopset;
     // counters
     int nfe, nsetups, nje, nni, nniS, nfSe, netf, netfS, ncfn, ncfnS, nor, qsum;
+    // re-entrant driver state (begin()/advance(): one step attempt per call, so that the groups of
+    // a warp -- and the warps of a CTA -- can be kept in lock-step per attempt)
+    ConditionIO io_;
+    double llh_, tout_, saved_t_, dsm_, dsmS_;
+    int it_, sim_status_, nstloc_, mxstep_, ncf_, nef_, ncfS_, nefS_, nflag_, dq_;
+    bool in_cvode_, in_step_, do_rescale_, undo_, restart_;
 
 // columns of this lane in [cmin, cmax]
 #define PB_FOR_COLS(c, cmin, cmax) \
     for (int c = g.lane(); c <= (cmax); c += G) \
         if (c >= (cmin))
 #define PB_FOR_ALL_COLS(c) for (int c = g.lane(); c <= ns; c += G)
+// all (state index, column) elements of the active columns, flat: every lane busy
+#define PB_FOR_ELEMS(e) for (int e = g.lane(); e < NX * ncol; e += G)
 
     PB_HD int phase_cmin(int phase) const { return phase == PH_STATE ? 0 : 1; }
     PB_HD int phase_cmax(int phase) const { return phase == PH_STATE ? 0 : ns; }
 
     // ---------------------------------------------------------------- norms
-    PB_HD double wnorm1(int cmin, int cmax, const double (&A)[NX][GroupShared<M>::NC]) const {
-        return wnorm_shared<M, Grp>(sh, g, cmin, cmax, &A[0][0], 1.0, &A[0][0], 0.0);
+    PB_HD double wnorm1(int cmin, int cmax, const double* A) const {
+        return wnorm_shared<M, Grp>(sh, g, ncol, cmin, cmax, A, 1.0, A, 0.0);
     }
-    PB_HD double wnorm2(int cmin, int cmax, const double (&A)[NX][GroupShared<M>::NC], double ca,
-                        const double (&B)[NX][GroupShared<M>::NC], double cb) const {
-        return wnorm_shared<M, Grp>(sh, g, cmin, cmax, &A[0][0], ca, &B[0][0], cb);
+    PB_HD double wnorm2(int cmin, int cmax, const double* A, double ca, const double* B, double cb) const {
+        return wnorm_shared<M, Grp>(sh, g, ncol, cmin, cmax, A, ca, B, cb);
     }
     /// columns in the error test: state, plus sensitivities if errconS
     PB_HD int errtest_cmax() const { return (sensi && opt.errconS) ? ns : 0; }
@@ -513,22 +533,22 @@ struct Bdf {
     /// cvEwtSetSS / cvSensEwtSetSS (cvodes.c:9118-9129, 9263-9279)
     PB_HD bool ewt_set() {
         bool ok = true;
-        PB_FOR_ALL_COLS(c) {
-            PB_UNROLL_X
-            for (int i = 0; i < NX; ++i) {
-                const double w = opt.rtol * fabs(sh->zn[0][i][c]) + opt.atol;
-                ok = ok && (w > 0.0);
-                sh->ewt[i][c] = pb_rcp(w);
-            }
+        PB_FOR_ELEMS(e) {
+            const double w = opt.rtol * fabs(sh->zn[0][e]) + opt.atol;
+            ok = ok && (w > 0.0);
+            sh->ewt[e] = pb_rcp(w);
         }
-        return group_max(g, ok ? 0.0 : 1.0) == 0.0;
+        return !g.any(!ok);
     }
 
     /// J(t, ysh) -> sh->Jcur by the state lane (Model_ODE::fsxdot at ip == 0,
     /// deps/AMICI/src/model_ode.cpp:492-498)
     PB_HD void refresh_Jcur(double t) {
         g.sync();
-        if (g.lane() == 0) eval_jac_shared<M>(sh->Jcur, t, sh->ysh, sh);
+        if (g.lane() == 0) {
+            eval_jac_shared<M>(sh->Jcur, t, sh->ysh, sh);
+            eval_dfdp_shared<M>(sh, t, sh->ysh);
+        }
         g.sync();
     }
 
@@ -540,37 +560,37 @@ struct Bdf {
     /// cvodes_nls.c:344-371; cvNlsResidualSensStg cvodes_nls_stg.c:377-421).
     /// Returns 0, RHSFUNC_RECVR or SRHSFUNC_RECVR (non-finite result).
     PB_HD int rhs(int phase, double t, bool raw) {
-        double bad = 0.0;
+        bool bad = false;
         PB_FOR_COLS(c, phase_cmin(phase), phase_cmax(phase)) {
             double F[NX];
             if (c == 0) {
                 PB_UNROLL
-                for (int i = 0; i < NX; ++i) sh->yj[i] = sh->zn[0][i][0] + sh->acor[i][0];
-                if (!eval_xdot_shared<M>(sh, t)) bad = 1.0;
+                for (int i = 0; i < NX; ++i) sh->yj[i] = sh->zn[0][(i) * ncol + (0)] + sh->acor[(i) * ncol + (0)];
+                if (!eval_xdot_shared<M>(sh, t)) bad = true;
                 PB_UNROLL
                 for (int i = 0; i < NX; ++i) F[i] = sh->fout[i];
             } else {
+                const double* dcol = sh->dfdp + sh->plist[c - 1] * NX;
                 PB_UNROLL
-                for (int i = 0; i < NX; ++i) F[i] = 0.0;
-                M::dxdotdp(F, t, sh->ysh, sh->p, sh->k, sh->plist[c - 1]);
+                for (int i = 0; i < NX; ++i) F[i] = dcol[i];
                 PB_ROLL
                 for (int j = 0; j < NX; ++j) {
-                    const double sj = sh->zn[0][j][c] + sh->acor[j][c];
+                    const double sj = sh->zn[0][(j) * ncol + (c)] + sh->acor[(j) * ncol + (c)];
                     PB_UNROLL
                     for (int r = 0; r < NX; ++r) F[r] += sh->Jcur[r + j * NX] * sj;
                 }
                 bool ok = true;
                 PB_UNROLL
                 for (int i = 0; i < NX; ++i) ok = ok && isfinite(F[i]);
-                if (!ok) bad = 1.0;
+                if (!ok) bad = true;
             }
             PB_UNROLL
             for (int i = 0; i < NX; ++i)
-                sh->b[i][c] = raw ? F[i] : (rl1 * sh->zn[1][i][c] + sh->acor[i][c]) - gamma * F[i];
+                sh->b[(i) * ncol + (c)] = raw ? F[i] : (rl1 * sh->zn[1][(i) * ncol + (c)] + sh->acor[(i) * ncol + (c)]) - gamma * F[i];
         }
         if (phase == PH_STATE) nfe++;
         else nfSe += ns;
-        if (group_max(g, bad) != 0.0) return phase == PH_STATE ? cv::RHSFUNC_RECVR : cv::SRHSFUNC_RECVR;
+        if (g.any(bad)) return phase == PH_STATE ? cv::RHSFUNC_RECVR : cv::SRHSFUNC_RECVR;
         return 0;
     }
 
@@ -579,7 +599,7 @@ struct Bdf {
         g.sync();
         if (g.lane() == 0) {
             PB_UNROLL_X
-            for (int i = 0; i < NX; ++i) sh->ysh[i] = sh->zn[0][i][0] + sh->acor[i][0];
+            for (int i = 0; i < NX; ++i) sh->ysh[i] = sh->zn[0][(i) * ncol + (0)] + sh->acor[(i) * ncol + (0)];
         }
         g.sync();
     }
@@ -617,10 +637,10 @@ struct Bdf {
             if (g.lane() == 0) eval_jac_shared<M>(sh->Jsaved, tn, sh->yj, sh);
             g.sync();
             // AMICI's fJ callback returns checkFinite(J): recoverable if not finite
-            double bad = 0.0;
+            bool bad = false;
             for (int e = g.lane(); e < NX * NX; e += G)
-                if (!isfinite(sh->Jsaved[e])) bad = 1.0;
-            if (group_max(g, bad) != 0.0) ret = 1;
+                if (!isfinite(sh->Jsaved[e])) bad = true;
+            if (g.any(bad)) ret = 1;
         }
         if (g.lane() == 0 && ret == 0) ret = lu_factor_shared<M>(sh, gamma);
         if (jbad) { nje++; nstlj = nst; }
@@ -635,7 +655,7 @@ struct Bdf {
     /// backward substitution in registers against the group's factors.
     PB_HD void lsolve_neg_b(int c, double* x) const {
         PB_UNROLL
-        for (int i = 0; i < NX; ++i) x[i] = -sh->b[sh->perm[i]][c];
+        for (int i = 0; i < NX; ++i) x[i] = -sh->b[sh->perm[i] * ncol + c];
         PB_UNROLL
         for (int k = 0; k < NX - 1; ++k) {
             PB_UNROLL
@@ -727,32 +747,28 @@ struct Bdf {
     /// the Pascal-triangle sweep zn[j-1] += sgn*zn[j], k = 1..q, j = q..k, done per element in
     /// registers (one load and one store of the q+1 history entries).
     PB_HD void shift_history(double sgn) {
-        PB_FOR_ALL_COLS(c) {
-            PB_ROLL
-            for (int i = 0; i < NX; ++i) {
-                double z[cv::L_MAX];
+        PB_FOR_ELEMS(e) {
+            double z[cv::L_MAX];
+            PB_UNROLL
+            for (int j = 0; j < cv::L_MAX; ++j) z[j] = (j <= q) ? sh->zn[j][e] : 0.0;
+            PB_UNROLL
+            for (int k = 1; k <= cv::Q_MAX; ++k) {
                 PB_UNROLL
-                for (int j = 0; j < cv::L_MAX; ++j) z[j] = (j <= q) ? sh->zn[j][i][c] : 0.0;
-                PB_UNROLL
-                for (int k = 1; k <= cv::Q_MAX; ++k) {
-                    PB_UNROLL
-                    for (int j = cv::Q_MAX; j >= k; --j) {
-                        if (j <= q && k <= q) z[j - 1] += sgn * z[j];
-                    }
+                for (int j = cv::Q_MAX; j >= k; --j) {
+                    if (j <= q && k <= q) z[j - 1] += sgn * z[j];
                 }
-                PB_UNROLL
-                for (int j = 0; j < cv::Q_MAX; ++j)
-                    if (j < q) sh->zn[j][i][c] = z[j];
             }
+            PB_UNROLL
+            for (int j = 0; j < cv::Q_MAX; ++j)
+                if (j < q) sh->zn[j][e] = z[j];
         }
     }
     /// cvRescale (cvodes.c:6425-6495)
     PB_HD void rescale() {
-        PB_FOR_ALL_COLS(c) {
+        PB_FOR_ELEMS(e) {
             double factor = eta;
             for (int j = 1; j <= q; ++j) {
-                PB_UNROLL_X
-                for (int i = 0; i < NX; ++i) sh->zn[j][i][c] *= factor;
+                sh->zn[j][e] *= factor;
                 factor *= eta;
             }
         }
@@ -794,13 +810,10 @@ struct Bdf {
             src = q;
             jmax = q - 1;  // zn[j] -= l[j]*zn[q], j = 2..q-1
         }
-        PB_FOR_ALL_COLS(c) {
-            PB_ROLL
-            for (int i = 0; i < NX; ++i) {
-                if (deltaq == 1) sh->zn[src][i][c] = A1 * sh->zn[cv::Q_MAX][i][c];
-                const double zs = sh->zn[src][i][c];
-                for (int j = 2; j <= jmax; ++j) sh->zn[j][i][c] += lc[j] * zs;
-            }
+        PB_FOR_ELEMS(e) {
+            if (deltaq == 1) sh->zn[src][e] = A1 * sh->zn[cv::Q_MAX][e];
+            const double zs = sh->zn[src][e];
+            for (int j = 2; j <= jmax; ++j) sh->zn[j][e] += lc[j] * zs;
         }
     }
 
@@ -820,7 +833,7 @@ struct Bdf {
         }
         PB_FOR_COLS(c, cmin, cmax) {
             PB_UNROLL_X
-            for (int i = 0; i < NX; ++i) sh->acor[i][c] = 0.0;
+            for (int i = 0; i < NX; ++i) sh->acor[(i) * ncol + (c)] = 0.0;
         }
         bool jbad = false;
         bool top = true;  // residual at the top of a solve attempt: failures there are final
@@ -859,8 +872,8 @@ struct Bdf {
                     double s = 0.0;
                     PB_UNROLL
                     for (int i = 0; i < NX; ++i) {
-                        sh->acor[i][c] += x[i];
-                        const double prod = x[i] * sh->ewt[i][c];
+                        sh->acor[(i) * ncol + (c)] += x[i];
+                        const double prod = x[i] * sh->ewt[(i) * ncol + (c)];
                         s += prod * prod;
                     }
                     if (s > loc) loc = s;
@@ -900,7 +913,7 @@ struct Bdf {
                 m_it = 0;
                 PB_FOR_COLS(c, cmin, cmax) {
                     PB_UNROLL_X
-                    for (int i = 0; i < NX; ++i) sh->acor[i][c] = 0.0;
+                    for (int i = 0; i < NX; ++i) sh->acor[(i) * ncol + (c)] = 0.0;
                 }
                 continue;
             }
@@ -923,13 +936,10 @@ struct Bdf {
         g.sync();
         qwait--;
         const bool save = (qwait == 1) && (q != cv::Q_MAX);
-        PB_FOR_ALL_COLS(c) {
-            PB_ROLL
-            for (int i = 0; i < NX; ++i) {
-                const double a = sh->acor[i][c];
-                for (int j = 0; j <= q; ++j) sh->zn[j][i][c] += sh->l[j] * a;
-                if (save) sh->zn[cv::Q_MAX][i][c] = a;
-            }
+        PB_FOR_ELEMS(e) {
+            const double a = sh->acor[e];
+            for (int j = 0; j <= q; ++j) sh->zn[j][e] += sh->l[j] * a;
+            if (save) sh->zn[cv::Q_MAX][e] = a;
         }
         if (save) saved_tq5 = sh->tq[5];
     }
@@ -987,7 +997,7 @@ struct Bdf {
                 // only if they take part in the error test, cvodes.c:7973-7987)
                 PB_FOR_COLS(c, 0, ecmax) {
                     PB_UNROLL_X
-                    for (int i = 0; i < NX; ++i) sh->zn[cv::Q_MAX][i][c] = sh->acor[i][c];
+                    for (int i = 0; i < NX; ++i) sh->zn[cv::Q_MAX][(i) * ncol + (c)] = sh->acor[(i) * ncol + (c)];
                 }
             }
         }
@@ -1044,16 +1054,10 @@ struct Bdf {
 
     /// zn[1] = h * f(tn, zn[0]) for the state and (if any) the sensitivities; acor is scratch
     PB_HD int reload_zn1() {
-        PB_FOR_ALL_COLS(c) {
-            PB_UNROLL_X
-            for (int i = 0; i < NX; ++i) sh->acor[i][c] = 0.0;
-        }
+        PB_FOR_ELEMS(e) sh->acor[e] = 0.0;
         const int r = rhs_all_raw(tn, sensi);
         if (r) return r;
-        PB_FOR_ALL_COLS(c) {
-            PB_UNROLL_X
-            for (int i = 0; i < NX; ++i) sh->zn[1][i][c] = h * sh->b[i][c];
-        }
+        PB_FOR_ELEMS(e) sh->zn[1][e] = h * sh->b[e];
         return 0;
     }
 
@@ -1062,128 +1066,134 @@ struct Bdf {
     /// the top of the attempt loop, so that every history operation (Pascal sweep, order change,
     /// rescale) and both correctors exist once in the instruction stream.  The sequence of
     /// operations per attempt is the reference's.
-    PB_HD int step() {
-        int ncf = 0, nef = 0, ncfS = 0, nefS = 0;
-        double dsm = 0.0, dsmS = 0.0;
-        const double saved_t = tn;
-        int nflag = cv::FIRST_CALL;
-        bool do_rescale = (nst > 0) && (hprime != h);
-        int dq = do_rescale ? (qprime - q) : 0;
-        bool undo = false, restart = false;
+    PB_HD void step_begin() {
+        ncf_ = nef_ = ncfS_ = nefS_ = 0;
+        dsm_ = dsmS_ = 0.0;
+        saved_t_ = tn;
+        nflag_ = cv::FIRST_CALL;
+        do_rescale_ = (nst > 0) && (hprime != h);
+        dq_ = do_rescale_ ? (qprime - q) : 0;
+        undo_ = restart_ = false;
+    }
+
+    /// One attempt of the step (after a failed attempt: first the restore pass).  Returns 0 when
+    /// the step was completed (history updated, next step/order chosen), 1 when another attempt
+    /// is needed, or a negative failure code.
+    PB_HD int step_attempt() {
         for (;;) {
-            if (undo) {
-                tn = saved_t;  // cvRestore
+            if (undo_) {
+                tn = saved_t_;  // cvRestore
             } else {
-                if (restart) {
+                if (restart_) {
                     // already at order 1 after MXNEF1 error-test failures: reload zn[1] from
                     // scratch at the reduced step (cvodes.c:7536-7613)
-                    restart = false;
+                    restart_ = false;
                     h *= eta;
                     hscale = h;
                     qwait = cv::LONG_WAIT;
                     nscon = 0;
                     if (reload_zn1()) return sensi ? SIM_UNREC_SRHSFUNC_ERR : SIM_UNREC_RHSFUNC_ERR;
                 }
-                if (dq != 0) {
-                    adjust_order(dq);
-                    q += dq;
+                if (dq_ != 0) {
+                    adjust_order(dq_);
+                    q += dq_;
                     L = q + 1;
                     qwait = L;
-                    dq = 0;
+                    dq_ = 0;
                 }
-                if (do_rescale) {
+                if (do_rescale_) {
                     rescale();
-                    do_rescale = false;
+                    do_rescale_ = false;
                 }
                 tn += h;  // cvPredict
                 if (tstopset && ((tn - tstop) * h > 0.0)) tn = tstop;
             }
-            double sgn = undo ? -1.0 : 1.0;
+            double sgn = undo_ ? -1.0 : 1.0;
             PB_OPAQUE_F64(sgn);
             shift_history(sgn);
-            if (undo) {
-                undo = false;
-                continue;
+            if (!undo_) break;
+            undo_ = false;
+        }
+        cvset();
+        int fail = 0;  // 1/3: corrector failure (state/sens); 2/4: error-test failure (state/sens)
+        int ret = 0;
+        for (int phase_ = PH_STATE; phase_ <= PH_SENS; ++phase_) {
+            int phase = phase_;
+            PB_OPAQUE_INT(phase);
+            if (phase == PH_SENS) {
+                if (fail || !sensi) break;
+                ncf_ = nef_ = 0;
+                publish_state();
+                // f at the converged y (cvodes.c:5947-5955); AMICI's sensitivity RHS does not
+                // use it -- kept for the recoverable-failure semantics
+                int bad = 0;
+                if (g.lane() == 0) {
+                    PB_UNROLL_X
+                    for (int i = 0; i < NX; ++i) sh->yj[i] = sh->ysh[i];
+                    bad = eval_xdot_shared<M>(sh, tn) ? 0 : 1;
+                }
+                nfe++;
+                if (g.bcast0(bad)) { fail = 5; break; }
+                refresh_Jcur(tn);
             }
-            cvset();
-            int fail = 0;  // 1/3: corrector failure (state/sens); 2/4: error-test failure (state/sens)
-            int ret = 0;
-            for (int phase_ = PH_STATE; phase_ <= PH_SENS; ++phase_) {
-                int phase = phase_;
-                PB_OPAQUE_INT(phase);
-                if (phase == PH_SENS) {
-                    if (fail || !sensi) break;
-                    ncf = nef = 0;
-                    publish_state();
-                    // f at the converged y (cvodes.c:5947-5955); AMICI's sensitivity RHS does not
-                    // use it -- kept for the recoverable-failure semantics
-                    int bad = 0;
-                    if (g.lane() == 0) {
-                        PB_UNROLL
-                        for (int i = 0; i < NX; ++i) sh->yj[i] = sh->ysh[i];
-                        bad = eval_xdot_shared<M>(sh, tn) ? 0 : 1;
-                    }
-                    nfe++;
-                    if (g.bcast0(bad)) { fail = 5; break; }
-                    refresh_Jcur(tn);
-                }
-                ret = nls(phase, nflag);
-                if (ret != 0) {
-                    fail = 1 + 2 * phase;
-                } else if (phase == PH_STATE) {
-                    dsm = acnrm * sh->tq[2];
-                    if (dsm > 1.0) fail = 2;
-                } else if (opt.errconS) {
-                    dsmS = acnrmS * sh->tq[2];
-                    if (dsmS > 1.0) fail = 4;
-                    else if (dsmS > dsm) dsm = dsmS;
-                }
-            }
-            if (!fail) break;
-            if (fail == 5) {  // cvodes.c:5951-5955: straight back to the prediction, no restore
-                nflag = cv::PREV_CONV_FAIL;
-                continue;
-            }
-            undo = true;
-            if (fail == 1 || fail == 3) {  // cvHandleNFlag
-                if (fail == 1) { ncfn++; ncf++; } else { ncfnS++; ncfS++; }
-                if (ret < 0) return ret;
-                etamax = 1.0;
-                if ((fabs(h) <= 0.0) || ((fail == 1 ? ncf : ncfS) == cv::MXNCF)) {
-                    if (ret == cv::CONV_RECVR) return SIM_CONV_FAILURE;
-                    if (ret == cv::RHSFUNC_RECVR) return SIM_REPTD_RHSFUNC_ERR;
-                    return SIM_REPTD_SRHSFUNC_ERR;
-                }
-                eta = cv::ETA_CF;  // max(eta_cf, hmin/|h|), hmin = 0
-                nflag = cv::PREV_CONV_FAIL;
-                do_rescale = true;
-            } else {  // cvDoErrorTest
-                int e;
-                if (fail == 2) { e = ++nef; netf++; } else { e = ++nefS; netfS++; }
-                nflag = cv::PREV_ERR_FAIL;
-                if ((fabs(h) <= 0.0) || (e == cv::MXNEF)) return SIM_ERR_FAILURE;
-                etamax = 1.0;
-                if (e <= cv::MXNEF1) {
-                    eta = pb_rcp(pb_pow(cv::BIAS2 * (fail == 2 ? dsm : dsmS), pb_rcp((double)L)) + cv::ADDON);
-                    eta = fmax(cv::ETA_MIN_EF, eta);
-                    if (e >= cv::SMALL_NEF) eta = fmin(eta, cv::ETA_MAX_EF);
-                    do_rescale = true;
-                } else if (q > 1) {
-                    eta = cv::ETA_MIN_EF;
-                    dq = -1;
-                    do_rescale = true;
-                } else {
-                    eta = cv::ETA_MIN_EF;
-                    restart = true;
-                }
+            ret = nls(phase, nflag_);
+            if (ret != 0) {
+                fail = 1 + 2 * phase;
+            } else if (phase == PH_STATE) {
+                dsm_ = acnrm * sh->tq[2];
+                if (dsm_ > 1.0) fail = 2;
+            } else if (opt.errconS) {
+                dsmS_ = acnrmS * sh->tq[2];
+                if (dsmS_ > 1.0) fail = 4;
+                else if (dsmS_ > dsm_) dsm_ = dsmS_;
             }
         }
-        complete_step();
-        prepare_next_step(dsm);
-        if (opt.stldet) bdf_stab();
-        etamax = (nst <= cv::SMALL_NST) ? cv::ETA_MAX_ES : cv::ETA_MAX_GS;
-        // acor *= tq[2] (local error estimate) is not used downstream and is skipped
-        return 0;
+        if (fail == 0) {
+            complete_step();
+            prepare_next_step(dsm_);
+            if (opt.stldet) bdf_stab();
+            etamax = (nst <= cv::SMALL_NST) ? cv::ETA_MAX_ES : cv::ETA_MAX_GS;
+            // acor *= tq[2] (local error estimate) is not used downstream and is skipped
+            return 0;
+        }
+        if (fail == 5) {  // cvodes.c:5951-5955: straight back to the prediction, no restore
+            nflag_ = cv::PREV_CONV_FAIL;
+            return 1;
+        }
+        undo_ = true;
+        if (fail == 1 || fail == 3) {  // cvHandleNFlag
+            if (fail == 1) { ncfn++; ncf_++; } else { ncfnS++; ncfS_++; }
+            if (ret < 0) return ret;
+            etamax = 1.0;
+            if ((fabs(h) <= 0.0) || ((fail == 1 ? ncf_ : ncfS_) == cv::MXNCF)) {
+                if (ret == cv::CONV_RECVR) return SIM_CONV_FAILURE;
+                if (ret == cv::RHSFUNC_RECVR) return SIM_REPTD_RHSFUNC_ERR;
+                return SIM_REPTD_SRHSFUNC_ERR;
+            }
+            eta = cv::ETA_CF;  // max(eta_cf, hmin/|h|), hmin = 0
+            nflag_ = cv::PREV_CONV_FAIL;
+            do_rescale_ = true;
+        } else {  // cvDoErrorTest
+            int e;
+            if (fail == 2) { e = ++nef_; netf++; } else { e = ++nefS_; netfS++; }
+            nflag_ = cv::PREV_ERR_FAIL;
+            if ((fabs(h) <= 0.0) || (e == cv::MXNEF)) return SIM_ERR_FAILURE;
+            etamax = 1.0;
+            if (e <= cv::MXNEF1) {
+                eta = pb_rcp(pb_pow(cv::BIAS2 * (fail == 2 ? dsm_ : dsmS_), pb_rcp((double)L)) + cv::ADDON);
+                eta = fmax(cv::ETA_MIN_EF, eta);
+                if (e >= cv::SMALL_NEF) eta = fmin(eta, cv::ETA_MAX_EF);
+                do_rescale_ = true;
+            } else if (q > 1) {
+                eta = cv::ETA_MIN_EF;
+                dq_ = -1;
+                do_rescale_ = true;
+            } else {
+                eta = cv::ETA_MIN_EF;
+                restart_ = true;
+            }
+        }
+        return 1;
     }
 
     // ---------------------------------------------------------------- initial step
@@ -1203,8 +1213,8 @@ struct Bdf {
         PB_FOR_COLS(c, 0, ecmax) {
             PB_UNROLL_X
             for (int i = 0; i < NX; ++i) {
-                const double den = cv::HUB_FACTOR * fabs(sh->zn[0][i][c]) + pb_rcp(sh->ewt[i][c]);
-                const double v = pb_div(fabs(sh->zn[1][i][c]), den);
+                const double den = cv::HUB_FACTOR * fabs(sh->zn[0][(i) * ncol + (c)]) + pb_rcp(sh->ewt[(i) * ncol + (c)]);
+                const double v = pb_div(fabs(sh->zn[1][(i) * ncol + (c)]), den);
                 if (v > hub_inv) hub_inv = v;
             }
         }
@@ -1224,10 +1234,7 @@ struct Bdf {
             for (int count2 = 1; count2 <= cv::HIN_MAX_ITERS; ++count2) {
                 // cvYddNorm: f at (tn + hg, zn0 + hg*zn1), difference quotient, WRMS norm
                 const double hgs = hg * sign;
-                PB_FOR_ALL_COLS(c) {
-                    PB_UNROLL_X
-                    for (int i = 0; i < NX; ++i) sh->acor[i][c] = hgs * sh->zn[1][i][c];
-                }
+                PB_FOR_ELEMS(e) sh->acor[e] = hgs * sh->zn[1][e];
                 retval = rhs_all_raw(tn + hgs, withS);
                 if (retval == 0) {
                     const double hinv = pb_rcp(hgs);
@@ -1237,10 +1244,7 @@ struct Bdf {
                 }
                 hg *= 0.2;
             }
-            PB_FOR_ALL_COLS(c) {
-                PB_UNROLL_X
-                for (int i = 0; i < NX; ++i) sh->acor[i][c] = 0.0;
-            }
+            PB_FOR_ELEMS(e) sh->acor[e] = 0.0;
             if (!hgOK) {
                 if (count1 <= 2) return retval == cv::RHSFUNC_RECVR ? SIM_REPTD_RHSFUNC_ERR : SIM_REPTD_SRHSFUNC_ERR;
                 hnew = hs;
@@ -1263,15 +1267,17 @@ struct Bdf {
     }
 
     // ---------------------------------------------------------------- CVode driver
-    /// CVode(tout) in CV_NORMAL mode with tstop = tout, as AMICI drives it
-    /// (cvodes.c:2890-3636; deps/AMICI/src/solver.cpp:108-161).  Returns TSTOP_RETURN
-    /// (tn == tout on exit) or a negative failure code.
-    PB_HD int cvode(double tout) {
+    /// Prologue of CVode(tout) in CV_NORMAL mode with tstop = tout, as AMICI drives it
+    /// (cvodes.c:2890-3347; deps/AMICI/src/solver.cpp:108-161): first-call initialisation (ewt,
+    /// zn[1], initial step) or the stop tests of a later call.  Returns 0 to enter the step loop,
+    /// TSTOP_RETURN if tn is already at tout, or a negative failure code.
+    PB_HD int cvode_begin(double tout) {
         // Solver::run -> setStopTime(tout); apply_max_num_steps()
         tstop = tout;
         tstopset = true;
         if (opt.maxsteps <= nst) return SIM_ERROR;
-        const int mxstep = opt.maxsteps - nst;
+        mxstep_ = opt.maxsteps - nst;
+        nstloc_ = 0;
         if (nst == 0) {
             if (!ewt_set()) return SIM_ILL_INPUT;
             h = 1.0;  // zn[1] = f(t0, y0), znS[1] = fS(t0, y0, yS0), unscaled
@@ -1283,10 +1289,7 @@ struct Bdf {
             if ((tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
             hscale = h;
             hprime = h;
-            PB_FOR_ALL_COLS(c) {
-                PB_UNROLL_X
-                for (int i = 0; i < NX; ++i) sh->zn[1][i][c] *= h;
-            }
+            PB_FOR_ELEMS(e) sh->zn[1][e] *= h;
         } else {
             const double troundoff = cv::FUZZ_FACTOR * cv::UROUND * (fabs(tn) + fabs(h));
             if (fabs(tn - tstop) <= troundoff) {
@@ -1298,28 +1301,7 @@ struct Bdf {
                 eta = pb_div(hprime, h);
             }
         }
-        int nstloc = 0;
-        for (;;) {
-            if (nst > 0) {
-                if (!ewt_set()) return SIM_ILL_INPUT;
-            }
-            if (nstloc >= mxstep) return SIM_TOO_MUCH_WORK;
-            const double nrm = wnorm1(0, errtest_cmax(), sh->zn[0]);
-            if (cv::UROUND * nrm > 1.0) return SIM_TOO_MUCH_ACC;
-            const int kflag = step();
-            if (kflag != 0) return kflag;
-            nstloc++;
-            const double troundoff = cv::FUZZ_FACTOR * cv::UROUND * (fabs(tn) + fabs(h));
-            if (fabs(tn - tstop) <= troundoff) {
-                tn = tstop;
-                tstopset = false;
-                return cv::TSTOP_RETURN;
-            } else if ((tn + hprime - tstop) * h > 0.0) {
-                hprime = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
-                eta = pb_div(hprime, h);
-            }
-            if ((tn - tout) * h >= 0.0) return cv::TSTOP_RETURN;
-        }
+        return 0;
     }
 
     // ---------------------------------------------------------------- likelihood
@@ -1334,7 +1316,7 @@ struct Bdf {
         g.sync();
         if (g.lane() == 0) {
             PB_UNROLL
-            for (int i = 0; i < NX; ++i) sh->ysh[i] = sh->zn[0][i][0];
+            for (int i = 0; i < NX; ++i) sh->ysh[i] = sh->zn[0][(i) * ncol + (0)];
         }
         g.sync();
         double y[NY], sig[NY];
@@ -1410,23 +1392,24 @@ struct Bdf {
             for (int iy = 0; iy < NY; ++iy) dJydp += dJyds[iy] * dsdp[iy];
             double a = dJydp;
             PB_UNROLL
-            for (int ix = 0; ix < NX; ++ix) a += dJydx[ix] * sh->zn[0][ix][c];
+            for (int ix = 0; ix < NX; ++ix) a += dJydx[ix] * sh->zn[0][(ix) * ncol + (c)];
             sh->sllh[c] -= a;
         }
         return true;
     }
 
     // ---------------------------------------------------------------- one simulation
-    /// ForwardProblem::workForwardProblem + ReturnData for one condition at the given
-    /// tolerances.  sh->p / sh->k / sh->plist must be set.  Returns the AMICI status; the llh is
-    /// returned, d llh / d p (w.r.t. the unscaled parameter) is left in sh->sllh[1..ns].
-    PB_HD int simulate(const ConditionIO& io, double rtol, double atol, double& llh_out) {
+    /// Start one simulation (ForwardProblem::workForwardProblem, forwardproblem.cpp:67-203) at
+    /// the given tolerances: x0/sx0 (Model::initialize, model.cpp:249-275), CVodeInit
+    /// (cvodes.c:677-830).  sh->p / sh->k / sh->plist must be set.
+    PB_HD void begin(const ConditionIO& io, double rtol, double atol) {
+        io_ = io;
         opt.rtol = rtol;
         opt.atol = atol;
         ns = io.ns;
+        ncol = ns + 1;
         sensi = ns > 0;
         g.sync();
-        // Model::initialize: x0, sx0 (deps/AMICI/src/model.cpp:249-275)
         PB_FOR_ALL_COLS(c) {
             double v[NX];
             PB_UNROLL
@@ -1435,15 +1418,14 @@ struct Bdf {
             else M::sx0(v, opt.t0, sh->p, sh->k, sh->plist[c - 1]);
             PB_UNROLL
             for (int i = 0; i < NX; ++i) {
-                sh->zn[0][i][c] = v[i];
-                for (int j = 1; j < cv::L_MAX; ++j) sh->zn[j][i][c] = 0.0;
-                sh->acor[i][c] = 0.0;
-                sh->ewt[i][c] = 1.0;
-                sh->b[i][c] = 0.0;
+                sh->zn[0][(i) * ncol + (c)] = v[i];
+                for (int j = 1; j < cv::L_MAX; ++j) sh->zn[j][(i) * ncol + (c)] = 0.0;
+                sh->acor[(i) * ncol + (c)] = 0.0;
+                sh->ewt[(i) * ncol + (c)] = 1.0;
+                sh->b[(i) * ncol + (c)] = 0.0;
             }
             sh->sllh[c] = 0.0;
         }
-        // CVodeInit (cvodes.c:677-830)
         tn = opt.t0;
         q = 1; L = 2; qwait = L; qprime = 1;
         etamax = cv::ETA_MAX_FS;
@@ -1460,6 +1442,7 @@ struct Bdf {
             sh->Jsaved[e] = 0.0;
             sh->Jcur[e] = 0.0;
         }
+        for (int e = g.lane(); e < NX * NP; e += G) sh->dfdp[e] = 0.0;
         if (g.lane() == 0) {
             for (int i = 0; i <= cv::L_MAX; ++i) { sh->l[i] = 0.0; sh->tau[i] = 0.0; }
             for (int i = 0; i < 6; ++i) sh->tq[i] = 0.0;
@@ -1467,37 +1450,91 @@ struct Bdf {
                 for (int k = 0; k < 4; ++k) sh->ssdat[i][k] = 0.0;
         }
         g.sync();
+        llh_ = 0.0;
+        it_ = 0;
+        sim_status_ = SIM_SUCCESS;
+        in_cvode_ = in_step_ = false;
+        step_begin();
+    }
 
-        double llh = 0.0;
-        int status = SIM_SUCCESS;
-        for (int it = 0; it < io.nt; ++it) {
-            const double tout = io.t[it];
-            if (isinf(tout)) break;  // post-equilibration time points are out of scope
-            if (tout > opt.t0) {
-                while (tn < tout) {
-                    // is_next_t_too_close, forwardproblem.cpp:23-35
-                    const double tdiff = tout - tn;
-                    if (tdiff == 0.0) break;
-                    if (fabs(tdiff) < 2.0 * cv::UROUND * fmax(fabs(tn), fabs(tout))) break;
-                    const int r = cvode(tout);
-                    if (r < 0) { status = r; break; }
-                }
-                if (status != SIM_SUCCESS) break;
-            }
-            double* yo = io.y_out ? io.y_out + (size_t)it * NY : nullptr;
-            double* so = io.sigmay_out ? io.sigmay_out + (size_t)it * NY : nullptr;
+    /// Advance the simulation by at most ONE step attempt (plus whatever bookkeeping precedes it:
+    /// output times that need no integration, the CVode prologue, the per-step checks of the CVode
+    /// loop cvodes.c:3366-3490, and after a completed step the tstop tests cvodes.c:3504-3605).
+    /// Returns true when the simulation has ended; status() / llh() then hold the result and
+    /// d llh / d p (w.r.t. the unscaled parameter) is in sh->sllh[1..ns].
+    PB_HD bool advance() {
+        if (!in_step_) {
+            if (!in_cvode_) {
+                for (;;) {
+                    if (it_ >= io_.nt) return finish(SIM_SUCCESS);
+                    tout_ = io_.t[it_];
+                    if (isinf(tout_)) return finish(SIM_SUCCESS);  // post-equilibration: out of scope
+                    bool integrate = (tout_ > opt.t0) && (tn < tout_);
+                    if (integrate) {  // is_next_t_too_close, forwardproblem.cpp:23-35
+                        const double tdiff = tout_ - tn;
+                        if (fabs(tdiff) < 2.0 * cv::UROUND * fmax(fabs(tn), fabs(tout_))) integrate = false;
+                    }
+                    if (integrate) break;
+                    double* yo = io_.y_out ? io_.y_out + (size_t)it_ * NY : nullptr;
+                    double* so = io_.sigmay_out ? io_.sigmay_out + (size_t)it_ * NY : nullptr;
 #if defined(PB200_HOST_TRACE)
-            if (io.trace) { io.trace[2 * it] = nst; io.trace[2 * it + 1] = q; }
+                    if (io_.trace) { io_.trace[2 * it_] = nst; io_.trace[2 * it_ + 1] = q; }
 #endif
-            if (!data_point(tout, io.my + (size_t)it * NY, io.sd + (size_t)it * NY, llh, yo, so)) {
-                status = SIM_ERROR;
-                break;
+                    if (!data_point(tout_, io_.my + (size_t)it_ * NY, io_.sd + (size_t)it_ * NY, llh_, yo, so))
+                        return finish(SIM_ERROR);
+                    it_++;
+                }
+                const int r = cvode_begin(tout_);
+                if (r < 0) return finish(r);
+                if (r == cv::TSTOP_RETURN) return false;  // already at tout: data point on the next call
+                in_cvode_ = true;
             }
+            // top of the CVode step loop
+            if (nst > 0) {
+                if (!ewt_set()) return finish(SIM_ILL_INPUT);
+            }
+            if (nstloc_ >= mxstep_) return finish(SIM_TOO_MUCH_WORK);
+            const double nrm = wnorm1(0, errtest_cmax(), sh->zn[0]);
+            if (cv::UROUND * nrm > 1.0) return finish(SIM_TOO_MUCH_ACC);
+            step_begin();
+            in_step_ = true;
         }
-        if (status != SIM_SUCCESS) llh = NAN;  // ReturnData::invalidate (rdata.cpp)
+        const int r = step_attempt();
+        if (r == 1) return false;
+        in_step_ = false;
+        if (r < 0) return finish(r);
+        nstloc_++;
+        const double troundoff = cv::FUZZ_FACTOR * cv::UROUND * (fabs(tn) + fabs(h));
+        if (fabs(tn - tstop) <= troundoff) {
+            tn = tstop;
+            tstopset = false;
+            in_cvode_ = false;
+        } else {
+            if ((tn + hprime - tstop) * h > 0.0) {
+                hprime = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
+                eta = pb_div(hprime, h);
+            }
+            if ((tn - tout_) * h >= 0.0) in_cvode_ = false;
+        }
+        return false;
+    }
+
+    PB_HD bool finish(int status) {
+        sim_status_ = status;
+        if (status != SIM_SUCCESS) llh_ = NAN;  // ReturnData::invalidate (rdata.cpp)
         g.sync();
-        llh_out = g.bcast0(llh);
-        return status;
+        llh_ = g.bcast0(llh_);
+        return true;
+    }
+    PB_HD int status() const { return sim_status_; }
+    PB_HD double llh() const { return llh_; }
+
+    /// Whole simulation in one call (host harness, and the non-lock-step kernel variant).
+    PB_HD int simulate(const ConditionIO& io, double rtol, double atol, double& llh_out) {
+        begin(io, rtol, atol);
+        while (!advance()) {}
+        llh_out = llh_;
+        return sim_status_;
     }
 
     PB_HD void export_stats(int64_t* s, int trials) const {
@@ -1508,6 +1545,7 @@ struct Bdf {
     }
 #undef PB_FOR_COLS
 #undef PB_FOR_ALL_COLS
+#undef PB_FOR_ELEMS
 };
 
 }  // namespace pb200

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "bdf_core.cuh"
@@ -59,16 +60,21 @@ struct KernelArgs {
 };
 
 constexpr double PB_LN10 = 2.302585092994046;
-#ifndef PB_MIN_BLOCKS
-#define PB_MIN_BLOCKS 7
-#endif
+// register cap: at most 128 registers per thread (64-thread CTAs: 7 per SM, 256-thread CTAs: 2)
+#define PB_MIN_BLOCKS_FOR(T) ((T) <= 64 ? 7 : ((T) <= 128 ? 4 : 2))
 
 /// One lane group per condition, persistent CTAs, in-kernel work queue.  The group's working
 /// set (GroupShared<M>: Nordsieck history of all columns, Jacobian, LU, ...) lives in dynamic
 /// shared memory for multi-lane groups; a one-lane group (cost-only evaluations) keeps it in
 /// the thread's local memory.
-template <class M, int G, int THREADS>
-__global__ void __launch_bounds__(THREADS, PB_MIN_BLOCKS) simulate_kernel(const KernelArgs a) {
+///
+/// Every trip of the main loop advances each group by ONE step attempt (Bdf::advance).  With
+/// CTA_SYNC the warps of a CTA meet at a barrier per attempt, so they walk through the same
+/// instructions at about the same time: the kernel is instruction-fetch bound when every warp
+/// is somewhere else in the step loop (profiles/README.md), and an instruction line fetched for
+/// one warp is then reused by the others.
+template <class M, int G, int THREADS, bool CTA_SYNC>
+__global__ void __launch_bounds__(THREADS, PB_MIN_BLOCKS_FOR(THREADS)) simulate_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char pb_smem_raw[];
     LaneGroup<G> grp;
     typename std::conditional<G == 1, GroupShared<M>, char>::type priv_storage_;
@@ -80,91 +86,103 @@ __global__ void __launch_bounds__(THREADS, PB_MIN_BLOCKS) simulate_kernel(const 
     bdf.opt = a.opt;
     const int lane = grp.lane();
 
+    bool active = false, done = false;
+    int r = 0, trial = 1;
+    size_t cp = 0;
+    ConditionIO io;
     for (;;) {
-        int pos = 0;
-        if (lane == 0) pos = atomicAdd(a.counter, 1);
-        pos = grp.bcast0(pos);
-        if (pos >= a.n) break;
-        const int r = a.order ? a.order[pos] : pos;
-        const int c = a.idx[r];
-        const size_t cp = (size_t)c * M::NP;
-
-        // ---- A5: optimisation -> simulation parameters (integer gather; the values come
-        //      from the host-computed table so they are bit-identical to the reference's
-        //      getScaledParameter(getUnscaledParameter(.)) chain) ----
-        grp.sync();
-        for (int i = lane; i < M::NP; i += G) {
-            const int j = a.mapping[cp + i];
-            double pu;
-            if (j >= 0) pu = a.theta_tab[((size_t)j * 3 + a.pscale_sim[cp + i]) * 2 + 1];
-            else if (a.ov_unscaled) pu = a.ov_unscaled[cp + i];
-            else pu = NAN;
-            sh->p[i] = pu;
-            sh->plist[i] = a.plist[cp + i];
-        }
-        for (int i = lane; i < M::NK; i += G) sh->k[i] = a.k[(size_t)c * M::NK + i];
-        grp.sync();
-
-        ConditionIO io;
-        const int64_t t0off = a.t_offsets[c];
-        io.nt = (int)(a.t_offsets[c + 1] - t0off);
-        io.t = a.t + t0off;
-        io.my = a.my + t0off * M::NY;
-        io.sd = a.sd + t0off * M::NY;
-        io.ns = a.want_grad ? a.nplist[c] : 0;
-        io.y_out = a.y_out ? a.y_out + t0off * M::NY : nullptr;
-        io.sigmay_out = a.sigmay_out ? a.sigmay_out + t0off * M::NY : nullptr;
-
-        // ---- A8: runAndLogSimulation retry loop (multiConditionProblem.cpp:369-465) ----
-        double llh = NAN;
-        int status = SIM_ERROR;
-        int trial = 1;
-        double relax = 1.0;
-        for (; trial <= a.num_trials; ++trial) {
-            status = bdf.simulate(io, a.opt.rtol * relax, a.opt.atol * relax, llh);
-            if (status == SIM_SUCCESS) break;
-            // next trial: tolerances * relaxation^(trial) relative to the template
-            relax = 1.0;
-            for (int e = 0; e < trial; ++e) relax *= a.relaxation_factor;
-        }
-        if (trial > a.num_trials) trial = a.num_trials;
-
-        // ---- outputs: A7 result package + A6 chain rule to the optimiser scale ----
-        if (lane == 0) {
-            a.llh[r] = llh;
-            a.status[r] = status;
-            bdf.export_stats(a.stats + (size_t)r * NSTATS, trial);
-        }
-        if (a.want_grad) {
-            for (int i = lane; i < M::NP; i += G) {
-                a.gcontrib[(size_t)r * M::NP + i] = 0.0;
-                a.sllh[(size_t)r * M::NP + i] = 0.0;
-            }
-            grp.sync();
-            for (int col = lane; col <= io.ns; col += G) {
-                if (col < 1) continue;
-                const int ip = sh->plist[col - 1];
-                const int ssim = a.pscale_sim[cp + ip];
-                const int jopt = a.mapping[cp + ip];
-                const double pu = sh->p[ip];
-                // ReturnData::applyChainRuleFactorToSimulationResults (rdata.cpp:672-686, 706-708)
-                double s = sh->sllh[col];
-                if (ssim == 2) s *= pu * PB_LN10;
-                else if (ssim == 1) s *= pu;
-                a.sllh[(size_t)r * M::NP + (col - 1)] = s;
-                // applyChainRule (multiConditionDataProvider.cpp:762-796), coefficient -1
-                const int sopt = a.pscale_opt[jopt];
-                double gr = s;
-                if (ssim != sopt) {
-                    if (ssim == 2) gr /= pu * PB_LN10;
-                    else if (ssim == 1) gr /= pu;
-                    if (sopt == 2) gr *= pu * PB_LN10;
-                    else if (sopt == 1) gr *= pu;
+        if (!active && !done) {
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(a.counter, 1);
+            pos = grp.bcast0(pos);
+            if (pos >= a.n) {
+                done = true;
+            } else {
+                r = a.order ? a.order[pos] : pos;
+                const int c = a.idx[r];
+                cp = (size_t)c * M::NP;
+                // ---- A5: optimisation -> simulation parameters (integer gather; the values come
+                //      from the host-computed table so they are bit-identical to the reference's
+                //      getScaledParameter(getUnscaledParameter(.)) chain) ----
+                grp.sync();
+                for (int i = lane; i < M::NP; i += G) {
+                    const int j = a.mapping[cp + i];
+                    double pu;
+                    if (j >= 0) pu = a.theta_tab[((size_t)j * 3 + a.pscale_sim[cp + i]) * 2 + 1];
+                    else if (a.ov_unscaled) pu = a.ov_unscaled[cp + i];
+                    else pu = NAN;
+                    sh->p[i] = pu;
+                    sh->plist[i] = a.plist[cp + i];
                 }
-                a.gcontrib[(size_t)r * M::NP + ip] = -1.0 * gr;
+                for (int i = lane; i < M::NK; i += G) sh->k[i] = a.k[(size_t)c * M::NK + i];
+                grp.sync();
+                const int64_t t0off = a.t_offsets[c];
+                io.nt = (int)(a.t_offsets[c + 1] - t0off);
+                io.t = a.t + t0off;
+                io.my = a.my + t0off * M::NY;
+                io.sd = a.sd + t0off * M::NY;
+                io.ns = a.want_grad ? a.nplist[c] : 0;
+                io.y_out = a.y_out ? a.y_out + t0off * M::NY : nullptr;
+                io.sigmay_out = a.sigmay_out ? a.sigmay_out + t0off * M::NY : nullptr;
+                trial = 1;
+                bdf.begin(io, a.opt.rtol, a.opt.atol);
+                active = true;
             }
         }
-        grp.sync();
+        if (active && bdf.advance()) {
+            const int status = bdf.status();
+            if (status != SIM_SUCCESS && trial < a.num_trials) {
+                // ---- A8: runAndLogSimulation retry (multiConditionProblem.cpp:369-465): trial t
+                //      runs at tolerances * relaxation^(t-1) relative to the template ----
+                double relax = 1.0;
+                for (int e = 0; e < trial; ++e) relax *= a.relaxation_factor;
+                ++trial;
+                bdf.begin(io, a.opt.rtol * relax, a.opt.atol * relax);
+            } else {
+                // ---- outputs: A7 result package + A6 chain rule to the optimiser scale ----
+                if (lane == 0) {
+                    a.llh[r] = bdf.llh();
+                    a.status[r] = status;
+                    bdf.export_stats(a.stats + (size_t)r * NSTATS, trial);
+                }
+                if (a.want_grad) {
+                    for (int i = lane; i < M::NP; i += G) {
+                        a.gcontrib[(size_t)r * M::NP + i] = 0.0;
+                        a.sllh[(size_t)r * M::NP + i] = 0.0;
+                    }
+                    grp.sync();
+                    for (int col = lane; col <= io.ns; col += G) {
+                        if (col < 1) continue;
+                        const int ip = sh->plist[col - 1];
+                        const int ssim = a.pscale_sim[cp + ip];
+                        const int jopt = a.mapping[cp + ip];
+                        const double pu = sh->p[ip];
+                        // ReturnData::applyChainRuleFactorToSimulationResults (rdata.cpp:672-686, 706-708)
+                        double s = sh->sllh[col];
+                        if (ssim == 2) s *= pu * PB_LN10;
+                        else if (ssim == 1) s *= pu;
+                        a.sllh[(size_t)r * M::NP + (col - 1)] = s;
+                        // applyChainRule (multiConditionDataProvider.cpp:762-796), coefficient -1
+                        const int sopt = a.pscale_opt[jopt];
+                        double gr = s;
+                        if (ssim != sopt) {
+                            if (ssim == 2) gr /= pu * PB_LN10;
+                            else if (ssim == 1) gr /= pu;
+                            if (sopt == 2) gr *= pu * PB_LN10;
+                            else if (sopt == 1) gr *= pu;
+                        }
+                        a.gcontrib[(size_t)r * M::NP + ip] = -1.0 * gr;
+                    }
+                }
+                grp.sync();
+                active = false;
+            }
+        }
+        if constexpr (CTA_SYNC) {
+            if (__syncthreads_and(done ? 1 : 0)) break;
+        } else {
+            if (done) break;
+        }
     }
 }
 
@@ -219,8 +237,8 @@ struct ModelOps {
     int default_lanes;  // G used for gradient evaluations unless overridden
     int flops_xdot, flops_J, flops_dxdotdp, nnzJ;
     // launches simulate_kernel; lanes: requested G (0 = default); returns cudaError_t as int
-    int (*launch)(const KernelArgs& a, int lanes, int sm_count, cudaStream_t stream, int* lanes_used, int* grid_used,
-                  int* block_used);
+    int (*launch)(const KernelArgs& a, int lanes, int variant, int sm_count, cudaStream_t stream, int* lanes_used,
+                  int* grid_used, int* block_used);
 };
 
 void register_model(const ModelOps& ops);
@@ -228,12 +246,10 @@ const ModelOps* find_model(const char* name);
 int model_count();
 const ModelOps* model_at(int i);
 
-constexpr int PB_THREADS = 64;
-
-template <class M, int G>
+template <class M, int G, int THREADS, bool CTA_SYNC>
 int launch_one(const KernelArgs& a, int sm_count, cudaStream_t stream, int* grid_used, int* block_used) {
-    auto kern = simulate_kernel<M, G, PB_THREADS>;
-    const int groups_per_block = PB_THREADS / G;
+    auto kern = simulate_kernel<M, G, THREADS, CTA_SYNC>;
+    const int groups_per_block = THREADS / G;
     const size_t smem = (G == 1) ? 0 : sizeof(GroupShared<M>) * groups_per_block;
     static bool attr_set = false;  // per instantiation
     if (!attr_set && smem > 0) {
@@ -242,50 +258,46 @@ int launch_one(const KernelArgs& a, int sm_count, cudaStream_t stream, int* grid
         attr_set = true;
     }
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PB_THREADS, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) per_sm = 1;
+    static const int cap = std::getenv("PB200_CTAS_PER_SM") ? std::atoi(std::getenv("PB200_CTAS_PER_SM")) : 0;  // experiments
+    if (cap > 0 && per_sm > cap) per_sm = cap;
     int grid = sm_count * per_sm;  // persistent: one resident wave, work queue inside
     const int needed = (a.n + groups_per_block - 1) / groups_per_block;
     if (grid > needed) grid = needed;
     if (grid < 1) grid = 1;
-    kern<<<grid, PB_THREADS, smem, stream>>>(a);
+    kern<<<grid, THREADS, smem, stream>>>(a);
     if (grid_used) *grid_used = grid;
-    if (block_used) *block_used = PB_THREADS;
+    if (block_used) *block_used = THREADS;
     return (int)cudaGetLastError();
 }
 
 constexpr int pb_pow2_at_least(int n) { return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32; }
 
 /// Instantiations offered per model: cost-only (G=1: the only column is the state), and for
-/// gradients the default group size G0 = pow2 >= NP+1 (capped at 32: one column per lane when
-/// it fits), plus G0/2 (two columns on some lanes, twice the conditions per warp) and a
-/// full-warp variant.
+/// gradients lane groups of G0 = pow2 >= NP+1 (capped at 32) or a full warp; `variant` selects
+/// the CTA shape: 0 = 256 threads with a barrier per step attempt (default), 1 = 64 threads
+/// free-running (the round-1 baseline, kept for comparison).
 template <class M>
-int launch_model(const KernelArgs& a, int lanes, int sm_count, cudaStream_t stream, int* lanes_used, int* grid_used,
-                 int* block_used) {
+int launch_model(const KernelArgs& a, int lanes, int variant, int sm_count, cudaStream_t stream, int* lanes_used,
+                 int* grid_used, int* block_used) {
     constexpr int NCOL = M::NP + 1;
     constexpr int G0 = pb_pow2_at_least(NCOL);
-    constexpr int GH = G0 >= 4 ? G0 / 2 : G0;
     if (!a.want_grad) {
         if (lanes_used) *lanes_used = 1;
-        return launch_one<M, 1>(a, sm_count, stream, grid_used, block_used);
+        return launch_one<M, 1, 64, false>(a, sm_count, stream, grid_used, block_used);
     }
-    // default: one warp per condition once there are >= 9 columns (measured: with divergent
-    // trajectories a full warp per condition beats two half-warp groups that serialise,
-    // profiles/r01_c_summary.txt); the pow2 group for narrower models
     constexpr int GDEF = (NCOL >= 9) ? 32 : G0;
     const int want = lanes > 0 ? lanes : GDEF;
-    if (want == 32 || G0 == 32) {
-        if (lanes_used) *lanes_used = 32;
-        return launch_one<M, 32>(a, sm_count, stream, grid_used, block_used);
+    const bool full = (want == 32 || G0 == 32);
+    if (lanes_used) *lanes_used = full ? 32 : G0;
+    if (variant == 1) {
+        if (full) return launch_one<M, 32, 64, false>(a, sm_count, stream, grid_used, block_used);
+        return launch_one<M, G0, 64, false>(a, sm_count, stream, grid_used, block_used);
     }
-    if (want == GH && GH != G0) {
-        if (lanes_used) *lanes_used = GH;
-        return launch_one<M, GH>(a, sm_count, stream, grid_used, block_used);
-    }
-    if (lanes_used) *lanes_used = G0;
-    return launch_one<M, G0>(a, sm_count, stream, grid_used, block_used);
+    if (full) return launch_one<M, 32, 256, true>(a, sm_count, stream, grid_used, block_used);
+    return launch_one<M, G0, 256, true>(a, sm_count, stream, grid_used, block_used);
 }
 
 template <class M>

@@ -10,6 +10,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -208,7 +209,8 @@ static int enqueue_evaluation(pb200_handle* h, const double* theta, const int* i
     a.sigmay_out = d_sout;
     PB_CUDA(cudaEventRecord(h->ev_start, stream));
     if (n > 0) {
-        int e = h->ops->launch(a, h->lanes, h->sm_count, stream, &h->last_lanes, &h->last_grid, &h->last_block);
+        static const int variant = std::getenv("PB200_KERNEL_VARIANT") ? std::atoi(std::getenv("PB200_KERNEL_VARIANT")) : 0;
+        int e = h->ops->launch(a, h->lanes, variant, h->sm_count, stream, &h->last_lanes, &h->last_grid, &h->last_block);
         if (e != 0) return fail(PB200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)e));
     }
     reduce_kernel<256><<<1 + h->n_opt, 256, 0, stream>>>(a, d_out);
