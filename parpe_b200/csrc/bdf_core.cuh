@@ -17,23 +17,29 @@
 // kept so that the step sequence stays close to the reference's; the data layout
 // and the execution model are not CVODES':
 //
-//   * a condition is owned by a group of G lanes of one warp (G = 1..32);
-//   * the state vector and every sensitivity vector is a *column*; column c is
-//     processed by lane (c mod G);
-//   * the Nordsieck history zn[0..5], the accumulated correction and the error
-//     weights of all columns live in the group's slice of shared memory as
-//     [order][state index][column] with the column index fastest, so the lanes of
-//     a group touch consecutive 8-byte words (conflict-free) and every history
-//     operation is a short rolled loop: the first version of this kernel kept
-//     the columns in registers with fully unrolled code and was instruction-fetch
-//     bound (profiles/r01_a_summary.txt);
-//   * norms are warp-shuffle reductions (max over the lanes of a group);
-//   * the Jacobian, its LU factors and the group-uniform BDF coefficient arrays
-//     live once per group in shared memory; the state lane factorises, every
-//     lane back-substitutes its own columns against the same factors (the
-//     staggered corrector's "same matrix, nplist right-hand sides");
-//   * model functions are the generated __host__ __device__ code of
-//     csrc/models/<name>.cuh.
+//   * a condition is owned by a group of G lanes of one warp (G = 1..32, normally the
+//     power of two >= nx), several conditions per warp, kept in step per step attempt;
+//   * the state vector and every sensitivity vector is a *column* of an nx x (1+nplist)
+//     array stored column by column (element (i, c) at [c*nx + i]).  Lane l owns the ROWS
+//     i = l, l+G, ... of every column: residuals, J*s products, Newton solves and updates are
+//     row-parallel loops over the columns, element-wise history operations (prediction,
+//     rescaling, order change, correction) run over the flat element index with every lane
+//     busy, and the lanes of a group always touch consecutive 8-byte words;
+//   * the Nordsieck history zn[0..5], the accumulated correction and the error weights of
+//     all columns live in the group's slice of shared memory (the first version of this
+//     kernel kept them in registers with fully unrolled code and was instruction-fetch
+//     bound, profiles/r01_a_summary.txt);
+//   * the Newton matrix I - gamma*J is INVERTED at every linear-solver setup (in-place
+//     Gauss-Jordan with partial pivoting, one matrix column per lane), so that each
+//     Newton iteration of the state and of all nplist sensitivities (the staggered
+//     corrector's "same matrix, nplist right-hand sides") is a row-parallel mat-vec with
+//     the lane's rows of the inverse in registers instead of two triangular solves;
+//   * WRMS norms: squared weighted entries go through a shared scratch array (odd column
+//     stride: conflict-free), one lane sums a column in CVODES' order, max over lanes by
+//     warp shuffles;
+//   * BDF coefficients (l, tq) live in registers, computed redundantly by every lane;
+//   * model functions are the generated __host__ __device__ code of csrc/models/<name>.cuh,
+//     evaluated by the group's first lane.
 //
 // The same source compiles for the host with the SingleLane group (G = 1); that
 // instantiation exists only in tests/host_harness to diff the algorithm against
@@ -169,35 +175,33 @@ struct LaneGroup {
 #endif
 
 /// Per-condition working set: one copy per lane group (shared memory on the device).
+/// Column data: element (state index i, column c) of a vector lives at [c*NX + i]; column 0 is
+/// the state, columns 1..ns the sensitivities of the current condition.
 template <class M>
 struct GroupShared {
     static constexpr int NX = M::NX;
     static constexpr int NC = M::NP + 1;  // columns: state + one per model parameter
-    // column data, [..][state index][column], column fastest
-    // element (state index i, column c) of a vector lives at [i * ncol + c], ncol = 1 + number of
-    // sensitivity columns of the current condition: the active elements are contiguous, so the
-    // element-wise history operations run over a flat index with all lanes busy
-    double zn[cv::L_MAX][NX * NC];  // Nordsieck history
-    double acor[NX * NC];           // accumulated corrector update
-    double ewt[NX * NC];            // error weights
-    double b[NX * NC];              // residual / Newton update
-    double sllh[NC];               // d llh / d p accumulator per sensitivity column
+    static constexpr int NXS = NX | 1;    // odd column stride of the norm scratch: conflict-free column sums
+    alignas(16) double zn[cv::L_MAX][NX * NC];  // Nordsieck history
+    alignas(16) double acor[NX * NC];           // accumulated corrector update
+    alignas(16) double ewt[NX * NC];            // error weights
+    alignas(16) double b[NX * NC];              // right-hand side / Newton residual (read by every lane)
+    // scratch: corrected sensitivities (stride NX), squared norm terms (stride NXS), STALD work arrays (45)
+    alignas(16) double scr[NC * (NX + 1) > 48 ? NC * (NX + 1) : 48];
     // group-uniform data
-    double Jsaved[NX * NX];  // Jacobian at its last evaluation (cvLs savedJ)
-    double LU[NX * NX];      // factors of I - gamma*J
-    double Jcur[NX * NX];    // J(tn, y_n) for the sensitivity right-hand sides
-    double dfdp[NX * (M::NP > 0 ? M::NP : 1)];  // d xdot / d p at (tn, y_n), column ip at [ip*NX]
-    double ysh[NX];          // converged state, read by the sensitivity lanes
+    alignas(16) double Jsaved[NX * NX];  // Jacobian at its last evaluation (cvLs savedJ), column-major
+    alignas(16) double Ainv[NX * NX];    // inverse of I - gamma*J, column-major
+    alignas(16) double Jcur[NX * NX];    // J(tn, y_n) for the sensitivity right-hand sides
+    alignas(16) double dfdp[NX * (M::NP > 0 ? M::NP : 1)];  // d xdot / d p at (tn, y_n), column ip at [ip*NX]
+    double sllh[NC];         // d llh / d p accumulator per sensitivity column
+    double ysh[NX];          // converged state, argument of the Jacobian / observable functions
     double yj[NX];           // state handed to the out-of-line model functions (xdot, Jacobian)
     double fout[NX];         // xdot returned by eval_xdot_shared
     double p[M::NP > 0 ? M::NP : 1];  // unscaled model parameters
     double k[M::NK > 0 ? M::NK : 1];  // constants (fixed parameters)
-    double l[cv::L_MAX + 1];
     double tau[cv::L_MAX + 1];
-    double tq[6];
     double ssdat[6][4];      // STALD history (cvBDFStab)
-    int piv[NX];
-    int perm[NX];            // row order after all pivot swaps: (P b)[i] = b[perm[i]]
+    int perm[NX];            // row order after the pivot swaps of the inversion
     int plist[M::NP > 0 ? M::NP : 1];
 };
 
@@ -205,195 +209,152 @@ struct GroupShared {
 //      memory and scalars, so a real call costs a few registers) ------------------------
 PB_HD_NOINLINE static double pb_pow(double x, double y) { return pow(x, y); }
 PB_HD_NOINLINE static double pb_div(double a, double b) { return a / b; }
-PB_HD_NOINLINE static double pb_rcp(double a) { return 1.0 / a; }
+PB_HD double pb_rcp(double a) { return pb_div(1.0, a); }
+/// 1.0 / n for the small integers of the BDF formulas
+PB_HD double pb_inv_int(int n) { return pb_rcp((double)n); }
 
 /// xdot(t, sh->yj) -> sh->fout; returns false if a component is not finite (AMICI checkFinite,
 /// deps/AMICI/src/solver_cvodes.cpp:1149-1173)
 template <class M>
 PB_HD_NOINLINE static bool eval_xdot_shared(GroupShared<M>* sh, double t) {
+    PB_ASSUME_SHARED(sh);
     M::xdot(sh->fout, t, sh->yj, sh->p, sh->k);
     bool ok = true;
-    PB_ROLL
+    PB_UNROLL
     for (int i = 0; i < M::NX; ++i) ok = ok && isfinite(sh->fout[i]);
     return ok;
 }
 
-template <class Grp>
-PB_HD_NOINLINE static double group_max(const Grp& g, double v) { return g.max(v); }
-
-/// max over the lanes of a group of a local sum of squares, then sqrt(. / n): the WRMS norm
-/// max_columns sqrt(mean((v*w)^2)) (N_VWrmsNorm; cvSensNorm cvodes.c:9427-9441)
-template <class Grp>
-PB_HD_NOINLINE static double group_wrms(const Grp& g, double ssq_local, int n) {
-    return sqrt(pb_div(g.max(ssq_local), (double)n));
-}
-
 /// J(t, y) -> the structurally non-zero entries of Jdst (dense column-major, NX*NX), everything
-/// in group-shared memory; the structural zeros are written once per condition (simulate()).
+/// in group-shared memory; the structural zeros are written once per condition (begin()).
 template <class M>
 PB_HD_NOINLINE static void eval_jac_shared(double* Jdst, double t, const double* y, const GroupShared<M>* sh) {
+    PB_ASSUME_SHARED(sh);
+    PB_ASSUME_SHARED(Jdst);
+    PB_ASSUME_SHARED(y);
     M::jac(Jdst, t, y, sh->p, sh->k);
 }
 
 /// d xdot / d p (all columns) at (t, y) -> sh->dfdp, structural non-zeros only
 template <class M>
 PB_HD_NOINLINE static void eval_dfdp_shared(GroupShared<M>* sh, double t, const double* y) {
+    PB_ASSUME_SHARED(sh);
+    PB_ASSUME_SHARED(y);
     M::dxdotdp_dense(sh->dfdp, t, y, sh->p, sh->k);
 }
 
-/// LU = I - gamma*Jsaved, factorised in place with partial pivoting, column-oriented
-/// (SUNDlsMat_denseGETRF, sundials_dense.c:82-148); the pivots are stored as reciprocals.
-/// Returns 0, or 1 on a zero pivot.
-template <class M>
-PB_HD_NOINLINE static int lu_factor_shared(GroupShared<M>* sh, double gamma) {
-    constexpr int NX = M::NX;
-    PB_ROLL
-    for (int c = 0; c < NX; ++c)
-        PB_ROLL
-        for (int r = 0; r < NX; ++r) sh->LU[r + c * NX] = (r == c ? 1.0 : 0.0) - gamma * sh->Jsaved[r + c * NX];
-    PB_ROLL
-    for (int k = 0; k < NX; ++k) {
-        double* col_k = sh->LU + k * NX;
-        int l = k;
-        PB_ROLL
-        for (int i = k + 1; i < NX; ++i)
-            if (fabs(col_k[i]) > fabs(col_k[l])) l = i;
-        sh->piv[k] = l;
-        if (col_k[l] == 0.0) return 1;
-        if (l != k) {
-            PB_ROLL
-            for (int i = 0; i < NX; ++i) {
-                const double t_ = sh->LU[l + i * NX];
-                sh->LU[l + i * NX] = sh->LU[k + i * NX];
-                sh->LU[k + i * NX] = t_;
-            }
-        }
-        const double mult = pb_rcp(col_k[k]);
-        PB_ROLL
-        for (int i = k + 1; i < NX; ++i) col_k[i] *= mult;
-        PB_ROLL
-        for (int j = k + 1; j < NX; ++j) {
-            double* col_j = sh->LU + j * NX;
-            const double a_kj = col_j[k];
-            if (a_kj != 0.0)
-                PB_ROLL
-                for (int i = k + 1; i < NX; ++i) col_j[i] -= a_kj * col_k[i];
-        }
-        col_k[k] = mult;
-    }
-    PB_ROLL
-    for (int i = 0; i < NX; ++i) sh->perm[i] = i;
-    PB_ROLL
-    for (int k = 0; k < NX; ++k) {
-        const int t_ = sh->perm[k];
-        sh->perm[k] = sh->perm[sh->piv[k]];
-        sh->perm[sh->piv[k]] = t_;
-    }
-    return 0;
-}
-
-/// cvSLdet (cvodes.c:8256-8556): dominant characteristic root from the STALD history (out of line)
-PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
-    int kmin = 0, kflag = 0;
-    double rat[5][4], rav[4], qkr[4], sigsq[4], smax[4], ssmax[4];
-    double drr[4], rrc[4], sqmx[4], qjk[4][4], vrat[5], qc[6][4], qco[6][4];
+/// cvSLdet (cvodes.c:8256-8556): dominant characteristic root from the STALD history.  The
+/// three data columns k = 1..3 (the scaled norms of the order q-2, q-1, q terms) are processed by
+/// three lanes of the group side by side; what one column needs from the others goes through the
+/// group's scratch array.  Every branch is taken on group-uniform values.  Out of line.
+template <class M, class Grp>
+PB_HD_NOINLINE static int sldet_shared(GroupShared<M>* sh, const Grp g, int q) {
+    PB_ASSUME_SHARED(sh);
+    constexpr int G = Grp::G;
     const double rrcut = 0.98, vrrtol = 1.0e-4, vrrt2 = 5.0e-4, sqtol = 1.0e-3, rrtol = 1.0e-2;
-    double rr = 0.0, sqmin = 0.0;
-    double ss[6][4];
-    PB_ROLL
-    for (int i = 1; i <= 5; ++i)
-        PB_ROLL
-        for (int k = 1; k <= 3; ++k) ss[i][k] = ssdat[i][k];
-    PB_ROLL
-    for (int k = 1; k <= 3; ++k) {
+    const double (*ss)[4] = sh->ssdat;
+    // scratch layout, three entries each (index k-1); qjk is [k-1][j-1]
+    double* const w = sh->scr;
+    double* const rav = w, * const vrat = w + 3, * const qc1 = w + 6, * const qc2 = w + 9, * const qc4 = w + 12;
+    double* const qc5 = w + 15, * const ssmax = w + 18, * const smax = w + 21, * const qkr = w + 24;
+    double* const rrc = w + 27, * const sqmx = w + 30, * const qjk = w + 33, * const sigsq = w + 42;
+#define PB_FOR_K(k) for (int k = 1 + g.lane(); k <= 3; k += G)
+    bool bad = false;
+    PB_FOR_K(k) {
         double smink = ss[1][k], smaxk = 0.0;
-        PB_ROLL
+        PB_UNROLL
         for (int i = 1; i <= 5; ++i) {
             smink = fmin(smink, ss[i][k]);
             smaxk = fmax(smaxk, ss[i][k]);
         }
-        if (smink < cv::TINY * smaxk) return -1;
-        smax[k] = smaxk;
-        ssmax[k] = smaxk * smaxk;
+        if (smink < cv::TINY * smaxk) bad = true;
+        smax[k - 1] = smaxk;
+        ssmax[k - 1] = smaxk * smaxk;
         double sumrat = 0.0, sumrsq = 0.0;
-        PB_ROLL
+        PB_UNROLL
         for (int i = 1; i <= 4; ++i) {
-            rat[i][k] = pb_div(ss[i][k], ss[i + 1][k]);
-            sumrat += rat[i][k];
-            sumrsq += rat[i][k] * rat[i][k];
+            const double rat = pb_div(ss[i][k], ss[i + 1][k]);
+            sumrat += rat;
+            sumrsq += rat * rat;
         }
-        rav[k] = 0.25 * sumrat;
-        vrat[k] = fabs(0.25 * sumrsq - rav[k] * rav[k]);
-        qc[5][k] = ss[1][k] * ss[3][k] - ss[2][k] * ss[2][k];
-        qc[4][k] = ss[2][k] * ss[3][k] - ss[1][k] * ss[4][k];
-        qc[3][k] = 0.0;
-        qc[2][k] = ss[2][k] * ss[5][k] - ss[3][k] * ss[4][k];
-        qc[1][k] = ss[4][k] * ss[4][k] - ss[3][k] * ss[5][k];
-        PB_ROLL
-        for (int i = 1; i <= 5; ++i) qco[i][k] = qc[i][k];
+        const double ravk = 0.25 * sumrat;
+        rav[k - 1] = ravk;
+        vrat[k - 1] = fabs(0.25 * sumrsq - ravk * ravk);
+        qc5[k - 1] = ss[1][k] * ss[3][k] - ss[2][k] * ss[2][k];
+        qc4[k - 1] = ss[2][k] * ss[3][k] - ss[1][k] * ss[4][k];
+        qc2[k - 1] = ss[2][k] * ss[5][k] - ss[3][k] * ss[4][k];
+        qc1[k - 1] = ss[4][k] * ss[4][k] - ss[3][k] * ss[5][k];
     }
-    const double vmin = fmin(vrat[1], fmin(vrat[2], vrat[3]));
-    const double vmax = fmax(vrat[1], fmax(vrat[2], vrat[3]));
+    if (g.any(bad)) return -1;  // (also orders the scratch writes before the reads below)
+    g.sync();
+    int kflag = 0;
+    double rr = 0.0;
+    const double vmin = fmin(vrat[0], fmin(vrat[1], vrat[2]));
+    const double vmax = fmax(vrat[0], fmax(vrat[1], vrat[2]));
     if (vmin < vrrtol * vrrtol) {
         if (vmax > vrrt2 * vrrt2) return -2;
-        rr = pb_div(rav[1] + rav[2] + rav[3], 3.0);
+        rr = pb_div(rav[0] + rav[1] + rav[2], 3.0);
         double drrmax = 0.0;
-        PB_ROLL
-        for (int k = 1; k <= 3; ++k) drrmax = fmax(drrmax, fabs(rav[k] - rr));
+        PB_UNROLL
+        for (int k = 0; k < 3; ++k) drrmax = fmax(drrmax, fabs(rav[k] - rr));
         if (drrmax > vrrt2) return -3;
         kflag = 1;
     } else {
-        if (fabs(qco[1][1]) < cv::TINY * ssmax[1]) return -4;
-        double tem = pb_div(qco[1][2], qco[1][1]);
-        PB_ROLL
-        for (int i = 2; i <= 5; ++i) qco[i][2] -= tem * qco[i][1];
-        qco[1][2] = 0.0;
-        tem = pb_div(qco[1][3], qco[1][1]);
-        PB_ROLL
-        for (int i = 2; i <= 5; ++i) qco[i][3] -= tem * qco[i][1];
-        qco[1][3] = 0.0;
-        if (fabs(qco[2][2]) < cv::TINY * ssmax[2]) return -4;
-        tem = pb_div(qco[2][3], qco[2][2]);
-        PB_ROLL
-        for (int i = 3; i <= 5; ++i) qco[i][3] -= tem * qco[i][2];
-        if (fabs(qco[4][3]) < cv::TINY * ssmax[3]) return -4;
-        rr = pb_div(-qco[5][3], qco[4][3]);
+        // Gaussian elimination on the 3 x 4 system of the quartics' coefficients (rows i = 1,2,4,5
+        // of qc; row 3 is zero), uniform
+        if (fabs(qc1[0]) < cv::TINY * ssmax[0]) return -4;
+        double tem = pb_div(qc1[1], qc1[0]);
+        const double q22 = qc2[1] - tem * qc2[0];
+        double q32 = 0.0 - tem * 0.0;
+        const double q42 = qc4[1] - tem * qc4[0], q52 = qc5[1] - tem * qc5[0];
+        tem = pb_div(qc1[2], qc1[0]);
+        double q23 = qc2[2] - tem * qc2[0];
+        double q33 = 0.0 - tem * 0.0;
+        double q43 = qc4[2] - tem * qc4[0], q53 = qc5[2] - tem * qc5[0];
+        if (fabs(q22) < cv::TINY * ssmax[1]) return -4;
+        tem = pb_div(q23, q22);
+        q33 -= tem * q32;
+        q43 -= tem * q42;
+        q53 -= tem * q52;
+        (void)q33;
+        if (fabs(q43) < cv::TINY * ssmax[2]) return -4;
+        rr = pb_div(-q53, q43);
         if (rr < cv::TINY || rr > 100.0) return -5;
-        PB_ROLL
-        for (int k = 1; k <= 3; ++k) qkr[k] = qc[5][k] + rr * (qc[4][k] + rr * rr * (qc[2][k] + rr * qc[1][k]));
-        double sqmax = 0.0;
-        PB_ROLL
-        for (int k = 1; k <= 3; ++k) {
-            const double saqk = pb_div(fabs(qkr[k]), ssmax[k]);
-            if (saqk > sqmax) sqmax = saqk;
+        double sq_own = 0.0;
+        PB_FOR_K(k) {
+            const double v = qc5[k - 1] + rr * (qc4[k - 1] + rr * rr * (qc2[k - 1] + rr * qc1[k - 1]));
+            qkr[k - 1] = v;
+            sq_own = fmax(sq_own, pb_div(fabs(v), ssmax[k - 1]));
         }
+        const double sqmax = g.max(sq_own);
+        double sqmin = 0.0;
         if (sqmax < sqtol) {
             kflag = 2;
         } else {
             PB_ROLL
             for (int it = 1; it <= 3; ++it) {
-                PB_ROLL
-                for (int k = 1; k <= 3; ++k) {
-                    const double qp = qc[4][k] + rr * rr * (3.0 * qc[2][k] + rr * 4.0 * qc[1][k]);
-                    drr[k] = 0.0;
-                    if (fabs(qp) > cv::TINY * ssmax[k]) drr[k] = pb_div(-qkr[k], qp);
-                    rrc[k] = rr + drr[k];
-                }
-                PB_ROLL
-                for (int k = 1; k <= 3; ++k) {
-                    const double s = rrc[k];
+                g.sync();
+                PB_FOR_K(k) {
+                    const double qp = qc4[k - 1] + rr * rr * (3.0 * qc2[k - 1] + rr * 4.0 * qc1[k - 1]);
+                    double drr = 0.0;
+                    if (fabs(qp) > cv::TINY * ssmax[k - 1]) drr = pb_div(-qkr[k - 1], qp);
+                    const double s = rr + drr;
+                    rrc[k - 1] = s;
                     double sqmaxk = 0.0;
-                    PB_ROLL
-                    for (int j = 1; j <= 3; ++j) {
-                        qjk[j][k] = qc[5][j] + s * (qc[4][j] + s * s * (qc[2][j] + s * qc[1][j]));
-                        const double saqj = pb_div(fabs(qjk[j][k]), ssmax[j]);
+                    PB_UNROLL
+                    for (int j = 0; j < 3; ++j) {
+                        const double v = qc5[j] + s * (qc4[j] + s * s * (qc2[j] + s * qc1[j]));
+                        qjk[(k - 1) * 3 + j] = v;
+                        const double saqj = pb_div(fabs(v), ssmax[j]);
                         if (saqj > sqmaxk) sqmaxk = saqj;
                     }
-                    sqmx[k] = sqmaxk;
+                    sqmx[k - 1] = sqmaxk;
                 }
-                sqmin = sqmx[1] + 1.0;
-                PB_ROLL
-                for (int k = 1; k <= 3; ++k) {
+                g.sync();
+                int kmin = 0;
+                sqmin = sqmx[0] + 1.0;
+                PB_UNROLL
+                for (int k = 0; k < 3; ++k) {
                     if (sqmx[k] < sqmin) {
                         kmin = k;
                         sqmin = sqmx[k];
@@ -403,16 +364,18 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
                 if (sqmin < sqtol) {
                     kflag = 3;
                     break;
-                } else {
-                    PB_ROLL
-                    for (int j = 1; j <= 3; ++j) qkr[j] = qjk[j][kmin];
                 }
+                double nq = 0.0;
+                PB_FOR_K(k) nq = qjk[kmin * 3 + (k - 1)];
+                g.sync();
+                PB_FOR_K(k) qkr[k - 1] = nq;
             }
             if (sqmin > sqtol) return -6;
         }
     }
-    PB_ROLL
-    for (int k = 1; k <= 3; ++k) {
+    g.sync();
+    bad = false;
+    PB_FOR_K(k) {
         const double rsa = ss[1][k];
         const double rsb = ss[2][k] * rr;
         const double rsc = ss[3][k] * rr * rr;
@@ -420,15 +383,18 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
         const double rd1a = rsa - rsb, rd1b = rsb - rsc, rd1c = rsc - rsd;
         const double rd2a = rd1a - rd1b, rd2b = rd1b - rd1c;
         const double rd3a = rd2a - rd2b;
-        if (fabs(rd1b) < cv::TINY * smax[k]) return -7;
+        if (fabs(rd1b) < cv::TINY * smax[k - 1]) bad = true;
         const double cest1 = pb_div(-rd3a, rd1b);
-        if (cest1 < cv::TINY || cest1 > 4.0) return -7;
+        if (cest1 < cv::TINY || cest1 > 4.0) bad = true;
         const double corr1 = pb_div(pb_div(rd2b, cest1), rr * rr);
-        sigsq[k] = ss[3][k] + corr1;
+        sigsq[k - 1] = ss[3][k] + corr1;
     }
-    if (sigsq[2] < cv::TINY) return -8;
-    const double ratp = pb_div(sigsq[3], sigsq[2]);
-    const double ratm = pb_div(sigsq[1], sigsq[2]);
+    if (g.any(bad)) return -7;
+    g.sync();
+#undef PB_FOR_K
+    if (sigsq[1] < cv::TINY) return -8;
+    const double ratp = pb_div(sigsq[2], sigsq[1]);
+    const double ratm = pb_div(sigsq[0], sigsq[1]);
     const double qfac1 = 0.25 * (q * q - 1.0);
     const double qfac2 = pb_div(2.0, q - 1.0);
     const double bb = ratp * ratm - 1.0 - qfac1 * ratp;
@@ -442,30 +408,6 @@ PB_HD_NOINLINE static int sldet_shared(const double (*ssdat)[4], int q) {
         if (kflag == 3) kflag = 6;
     }
     return kflag;
-}
-
-
-
-/// WRMS norm max_c sqrt(mean_i(((ca*A[i][c] + cb*B[i][c]) * ewt[i][c])^2)) over the columns
-/// [cmin, cmax] of [NX][NC] arrays in group-shared memory: N_VWrmsNorm for the state column,
-/// cvSensNorm for the sensitivities, cvSensUpdateNorm for both (cvodes.c:9427-9457).  One copy
-/// of the code serves every call site.
-template <class M, class Grp>
-PB_HD_NOINLINE static double wnorm_shared(const GroupShared<M>* sh, const Grp& g, int NC, int cmin, int cmax,
-                                          const double* A, double ca, const double* B, double cb) {
-    constexpr int NX = M::NX;
-    double loc = 0.0;
-    for (int c = g.lane(); c <= cmax; c += Grp::G) {
-        if (c < cmin) continue;
-        double s = 0.0;
-        PB_UNROLL_X
-        for (int i = 0; i < NX; ++i) {
-            const double prod = (ca * A[i * NC + c] + cb * B[i * NC + c]) * sh->ewt[i * NC + c];
-            s += prod * prod;
-        }
-        if (s > loc) loc = s;
-    }
-    return sqrt(pb_div(g.max(loc), (double)NX));
 }
 
 /// Per-condition inputs (device pointers into the resident tables).
@@ -482,22 +424,220 @@ struct ConditionIO {
 #endif
 };
 
+
+// ---- out-of-line group kernels: static functions of (shared working set, lane group, scalars)
+//      only -- a noinline MEMBER function would force the integrator object into local memory ----
+/// position of flat element e in the norm scratch (column stride NXS)
+template <class M>
+PB_HD int scr_pos(int e) { return (GroupShared<M>::NXS == M::NX) ? e : e + e / M::NX; }
+
+/// sqrt(max_c(sum_i scr[c][i]) / NX) over the columns [cmin, cmax] of the norm scratch: the
+/// WRMS norm (N_VWrmsNorm for the state column; cvSensNorm / cvSensUpdateNorm take the max
+/// over the columns, cvodes.c:9427-9457).  One lane sums a column in CVODES' order.
+template <class M, class Grp>
+PB_HD_NOINLINE static double colnorm_shared(GroupShared<M>* sh, const Grp g, int cmin, int cmax) {
+    constexpr int NX = M::NX, NXS = GroupShared<M>::NXS, G = Grp::G;
+    PB_ASSUME_SHARED(sh);
+    g.sync();
+    double loc = 0.0;
+    for (int c = cmin + g.lane(); c <= cmax; c += G) {
+        const double* col = sh->scr + c * NXS;
+        double s = 0.0;
+        PB_UNROLL
+        for (int i = 0; i < NX; ++i) s += col[i];
+        if (s > loc) loc = s;
+    }
+    const double m = g.max(loc);
+    g.sync();  // the scratch may be overwritten by its next user
+    return sqrt(pb_div(m, (double)NX));
+}
+/// WRMS norm of A over the columns [cmin, cmax]
+template <class M, class Grp>
+PB_HD_NOINLINE static double wnorm1_shared(GroupShared<M>* sh, const Grp g, int cmin, int cmax, const double* A) {
+    constexpr int NX = M::NX, G = Grp::G;
+    PB_ASSUME_SHARED(sh);
+    PB_ASSUME_SHARED(A);
+    for (int e = cmin * NX + g.lane(); e < (cmax + 1) * NX; e += G) {
+        const double prod = A[e] * sh->ewt[e];
+        sh->scr[scr_pos<M>(e)] = prod * prod;
+    }
+    return colnorm_shared<M, Grp>(sh, g, cmin, cmax);
+}
+/// WRMS norm of ca*A + cb*B
+template <class M, class Grp>
+PB_HD_NOINLINE static double wnorm2_shared(GroupShared<M>* sh, const Grp g, int cmin, int cmax, const double* A,
+                                           double ca, const double* B, double cb) {
+    constexpr int NX = M::NX, G = Grp::G;
+    PB_ASSUME_SHARED(sh);
+    PB_ASSUME_SHARED(A);
+    PB_ASSUME_SHARED(B);
+    for (int e = cmin * NX + g.lane(); e < (cmax + 1) * NX; e += G) {
+        const double prod = (ca * A[e] + cb * B[e]) * sh->ewt[e];
+        sh->scr[scr_pos<M>(e)] = prod * prod;
+    }
+    return colnorm_shared<M, Grp>(sh, g, cmin, cmax);
+}
+
+/// Ainv = (I - gamma*Jsaved)^-1 by in-place Gauss-Jordan elimination with partial pivoting
+/// (the pivot order of SUNDlsMat_denseGETRF, sundials_dense.c:82-148), one matrix column per
+/// lane.  Returns 0, or 1 on a zero pivot (group-uniform).
+template <class M, class Grp>
+PB_HD_NOINLINE static int invert_newton_matrix(GroupShared<M>* sh, const Grp g, const double gamma) {
+constexpr int NX = M::NX, G = Grp::G, RPL = (NX + G - 1) / G;
+    double* A = sh->Ainv;
+    for (int e = g.lane(); e < NX * NX; e += G) {
+        const int r = e % NX, c = e / NX;
+        A[e] = (r == c ? 1.0 : 0.0) - gamma * sh->Jsaved[e];
+    }
+    for (int i = g.lane(); i < NX; i += G) sh->perm[i] = i;
+    g.sync();
+    int fail = 0;
+    PB_ROLL
+    for (int k = 0; k < NX; ++k) {
+        // every lane: column k, pivot row l (first largest magnitude among rows >= k)
+        double colk[NX];
+        PB_UNROLL
+        for (int i = 0; i < NX; ++i) colk[i] = A[i + k * NX];
+        int lp = k;
+        double pv = A[k + k * NX];
+        PB_UNROLL
+        for (int i = 1; i < NX; ++i) {
+            if (i > k && fabs(colk[i]) > fabs(pv)) { pv = colk[i]; lp = i; }
+        }
+        if (pv == 0.0) { fail = 1; break; }
+        const double pinv = pb_rcp(pv);
+        // column k after the row swap k <-> lp
+        const double ck = A[k + k * NX];
+        PB_UNROLL
+        for (int i = 1; i < NX; ++i)
+            if (i == lp && i > k) colk[i] = ck;
+        g.sync();  // every lane has read column k
+        for (int j = g.lane(); j < NX; j += G) {
+            double* cj = A + j * NX;
+            if (lp != k) {
+                const double t_ = cj[lp];
+                cj[lp] = cj[k];
+                cj[k] = t_;
+            }
+            if (j == k) {
+                PB_UNROLL
+                for (int i = 0; i < NX; ++i) cj[i] = (i == k) ? pinv : -colk[i] * pinv;
+            } else {
+                const double akj = cj[k] * pinv;
+                PB_UNROLL
+                for (int i = 0; i < NX; ++i) {
+                    if (i == k) cj[i] = akj;
+                    else cj[i] -= colk[i] * akj;
+                }
+            }
+        }
+        if (g.lane() == 0 && lp != k) {
+            const int t_ = sh->perm[k];
+            sh->perm[k] = sh->perm[lp];
+            sh->perm[lp] = t_;
+        }
+        g.sync();
+    }
+    if (fail) return 1;
+    // A holds (P (I - gamma J))^-1 = (I - gamma J)^-1 P^T: its column j belongs at perm[j]
+    double mine[RPL][NX];
+    PB_UNROLL
+    for (int r = 0; r < RPL; ++r) {
+        const int j = g.lane() + r * G;
+        if (j < NX) {
+            PB_UNROLL
+            for (int i = 0; i < NX; ++i) mine[r][i] = A[i + j * NX];
+        }
+    }
+    g.sync();
+    PB_UNROLL
+    for (int r = 0; r < RPL; ++r) {
+        const int j = g.lane() + r * G;
+        if (j < NX) {
+            double* dst = A + sh->perm[j] * NX;
+            PB_UNROLL
+            for (int i = 0; i < NX; ++i) dst[i] = mine[r][i];
+        }
+    }
+    g.sync();
+    return 0;
+}
+
+
+/// cvAdjustOrder -> cvIncreaseBDF / cvDecreaseBDF (cvodes.c:6134-6143, 6256-6351, 6363-6415)
+template <class M, class Grp>
+PB_HD_NOINLINE static void adjust_order_shared(GroupShared<M>* sh, const Grp g, int ncol, int q, int L, double hscale,
+                                            int deltaq) {
+constexpr int NX = M::NX, G = Grp::G;
+PB_ASSUME_SHARED(sh);
+    if ((q == 2) && (deltaq != 1)) return;
+    double lc[cv::L_MAX + 1];
+    for (int i = 0; i <= cv::L_MAX; ++i) lc[i] = 0.0;
+    lc[2] = 1.0;
+    int src, jmax;
+    double A1 = 0.0;
+    if (deltaq == 1) {
+        double alpha1 = 1.0, prod = 1.0, xiold = 1.0, alpha0 = -1.0;
+        double hsum = hscale;
+        for (int j = 1; j < q; ++j) {
+            hsum += sh->tau[j + 1];
+            const double xi = pb_div(hsum, hscale);
+            prod *= xi;
+            alpha0 -= pb_inv_int(j + 1);
+            alpha1 += pb_rcp(xi);
+            for (int i = j + 2; i >= 2; --i) lc[i] = lc[i] * xiold + lc[i - 1];
+            xiold = xi;
+        }
+        A1 = pb_div(-alpha0 - alpha1, prod);
+        src = L;   // new column zn[L] = A1 * (saved correction in zn[qmax]); L = q+1 <= qmax
+        jmax = q;  // N_VScaleAddMulti(q-1, l+2, zn[L], zn+2, zn+2)
+    } else {
+        double hsum = 0.0;
+        for (int j = 1; j <= q - 2; ++j) {
+            hsum += sh->tau[j];
+            const double xi = pb_div(hsum, hscale);
+            for (int i = j + 2; i >= 2; --i) lc[i] = lc[i] * xi + lc[i - 1];
+        }
+        for (int j = 2; j < q; ++j) lc[j] = -lc[j];
+        src = q;
+        jmax = q - 1;  // zn[j] -= l[j]*zn[q], j = 2..q-1
+    }
+    for (int e = g.lane(); e < NX * ncol; e += G) {
+        if (deltaq == 1) sh->zn[src][e] = A1 * sh->zn[cv::Q_MAX][e];
+        const double zs = sh->zn[src][e];
+        for (int j = 2; j <= jmax; ++j) sh->zn[j][e] += lc[j] * zs;
+    }
+}
+
+
 template <class M, class Grp>
 struct Bdf {
     static constexpr int NX = M::NX, NP = M::NP, NK = M::NK, NY = M::NY;
     static constexpr int G = Grp::G;
+    // 2-D lane mapping of the row-parallel kernels: the G lanes of a group are LR "row lanes"
+    // (the power of two >= NX, at most G) times CG "column groups"; lane l works on the rows
+    // (l % LR) + r*LR, r < RPL, of the columns c = cmin + (l / LR), + CG, ...
+    static constexpr int NXP2 = NX <= 1 ? 1 : NX <= 2 ? 2 : NX <= 4 ? 4 : NX <= 8 ? 8 : NX <= 16 ? 16 : 32;
+    static constexpr int LR = G < NXP2 ? G : NXP2;
+    static constexpr int CG = G / LR;
+    static constexpr int RPL = (NX + LR - 1) / LR;  // rows (state indices) per lane
+    PB_HD int row_lane() const { return CG == 1 ? g.lane() : g.lane() % LR; }
+    PB_HD int col_group() const { return CG == 1 ? 0 : g.lane() / LR; }
+    static constexpr int NXS = GroupShared<M>::NXS;
     enum { PH_STATE = 0, PH_SENS = 1 };
 
     Grp g;
     GroupShared<M>* sh;
     SolverOptions opt;
     int ns;      // sensitivity columns (columns 1..ns; column 0 is the state)
-    int ncol;    // 1 + ns: row stride of the column data in shared memory
+    int ncol;    // 1 + ns
     bool sensi;  // ns > 0
 
     // integrator scalars (uniform within the group)
     double tn, h, hprime, hscale, eta, etamax, etaq, etaqm1, etaqp1;
     double gamma, gammap, gamrat, rl1, crate, crateS, delp, acnrm, acnrmS, saved_tq5, tstop;
+    double l[cv::L_MAX];          // BDF polynomial coefficients l[0..q] (compile-time indices only)
+    double tq1, tq2, tq3, tq4, tq5;  // test quantities
     int q, qprime, L, qwait, nst, nscon, nstlp, nstlj, convfail;
     bool jcur, jcurNLS, jcurNLSS, tstopset;
     // counters
@@ -508,27 +648,39 @@ struct Bdf {
     double llh_, tout_, saved_t_, dsm_, dsmS_;
     int it_, sim_status_, nstloc_, mxstep_, ncf_, nef_, ncfS_, nefS_, nflag_, dq_;
     bool in_cvode_, in_step_, do_rescale_, undo_, restart_;
+    // stage of the attempt the state machine is in (stage_pre / stage_nls / stage_post)
+    enum { ST_PRE = 0, ST_NLS = 1, ST_DONE = 2 };
+    int stage_, fail_, ret_;
 
-// columns of this lane in [cmin, cmax]
+// columns of this lane in [cmin, cmax] (column-parallel cold paths: initial values, data points)
 #define PB_FOR_COLS(c, cmin, cmax) \
     for (int c = g.lane(); c <= (cmax); c += G) \
         if (c >= (cmin))
-#define PB_FOR_ALL_COLS(c) for (int c = g.lane(); c <= ns; c += G)
-// all (state index, column) elements of the active columns, flat: every lane busy
-#define PB_FOR_ELEMS(e) for (int e = g.lane(); e < NX * ncol; e += G)
+// flat element range [e0, e1) of the column data: every lane busy
+#define PB_FOR_RANGE(e, e0, e1) for (int e = (e0) + g.lane(); e < (e1); e += G)
+// all elements of the active columns
+#define PB_FOR_ELEMS(e) PB_FOR_RANGE(e, 0, NX * ncol)
+// the rows (state indices) owned by this lane: i = lane + r*G
+#define PB_FOR_ROWS(r, i) \
+    PB_UNROLL                \
+    for (int r = 0; r < RPL; ++r) \
+        for (int i = row_lane() + r * LR, once_ = 1; once_ && i < NX; once_ = 0)
+// the same, first column group only (single-column data)
+#define PB_FOR_ROWS0(r, i) \
+    if (col_group() == 0) PB_FOR_ROWS(r, i)
 
     PB_HD int phase_cmin(int phase) const { return phase == PH_STATE ? 0 : 1; }
     PB_HD int phase_cmax(int phase) const { return phase == PH_STATE ? 0 : ns; }
-
-    // ---------------------------------------------------------------- norms
-    PB_HD double wnorm1(int cmin, int cmax, const double* A) const {
-        return wnorm_shared<M, Grp>(sh, g, ncol, cmin, cmax, A, 1.0, A, 0.0);
-    }
-    PB_HD double wnorm2(int cmin, int cmax, const double* A, double ca, const double* B, double cb) const {
-        return wnorm_shared<M, Grp>(sh, g, ncol, cmin, cmax, A, ca, B, cb);
-    }
     /// columns in the error test: state, plus sensitivities if errconS
     PB_HD int errtest_cmax() const { return (sensi && opt.errconS) ? ns : 0; }
+    /// position of flat element e in the norm scratch (column stride NXS)
+
+    // ---------------------------------------------------------------- norms
+    PB_HD double wnorm1(int cmin, int cmax, const double* A) const { return wnorm1_shared<M, Grp>(sh, g, cmin, cmax, A); }
+    PB_HD double wnorm2(int cmin, int cmax, const double* A, double ca, const double* B, double cb) const {
+        return wnorm2_shared<M, Grp>(sh, g, cmin, cmax, A, ca, B, cb);
+    }
+    PB_HD double colnorm(int cmin, int cmax) const { return colnorm_shared<M, Grp>(sh, g, cmin, cmax); }
 
     /// cvEwtSetSS / cvSensEwtSetSS (cvodes.c:9118-9129, 9263-9279)
     PB_HD bool ewt_set() {
@@ -536,13 +688,13 @@ struct Bdf {
         PB_FOR_ELEMS(e) {
             const double w = opt.rtol * fabs(sh->zn[0][e]) + opt.atol;
             ok = ok && (w > 0.0);
-            sh->ewt[e] = pb_rcp(w);
+            sh->ewt[e] = 1.0 / w;
         }
         return !g.any(!ok);
     }
 
-    /// J(t, ysh) -> sh->Jcur by the state lane (Model_ODE::fsxdot at ip == 0,
-    /// deps/AMICI/src/model_ode.cpp:492-498)
+    /// J(t, ysh) and d xdot / d p -> sh->Jcur, sh->dfdp by the first lane (Model_ODE::fsxdot at
+    /// ip == 0, deps/AMICI/src/model_ode.cpp:492-498)
     PB_HD void refresh_Jcur(double t) {
         g.sync();
         if (g.lane() == 0) {
@@ -553,54 +705,63 @@ struct Bdf {
     }
 
     // ---------------------------------------------------------------- right-hand sides
-    /// THE right-hand-side evaluation (single copy in the instruction stream).  For the columns
-    /// of `phase`:  v = zn[0] + acor;  F = f(t, v)  (state: xdot; sensitivities:
-    /// dxdotdp(ip) + Jcur*v, Model_ODE::fsxdot model_ode.cpp:486-515, with sh->ysh / sh->Jcur
-    /// prepared by the caller);  b = raw ? F : rl1*zn[1] + acor - gamma*F  (cvNlsResidual
-    /// cvodes_nls.c:344-371; cvNlsResidualSensStg cvodes_nls_stg.c:377-421).
-    /// Returns 0, RHSFUNC_RECVR or SRHSFUNC_RECVR (non-finite result).
+    /// THE right-hand-side evaluation.  For the columns of `phase`:  v = zn[0] + acor;
+    /// F = f(t, v)  (state: xdot; sensitivities: dxdotdp(ip) + Jcur*v, Model_ODE::fsxdot
+    /// model_ode.cpp:486-515, with sh->ysh / sh->Jcur / sh->dfdp prepared by the caller);
+    /// b = raw ? F : rl1*zn[1] + acor - gamma*F  (cvNlsResidual cvodes_nls.c:344-371;
+    /// cvNlsResidualSensStg cvodes_nls_stg.c:377-421).  Row-parallel: every lane produces its
+    /// rows of every column.  Returns 0, RHSFUNC_RECVR or SRHSFUNC_RECVR (non-finite result).
     PB_HD int rhs(int phase, double t, bool raw) {
         bool bad = false;
-        PB_FOR_COLS(c, phase_cmin(phase), phase_cmax(phase)) {
-            double F[NX];
-            if (c == 0) {
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) sh->yj[i] = sh->zn[0][(i) * ncol + (0)] + sh->acor[(i) * ncol + (0)];
-                if (!eval_xdot_shared<M>(sh, t)) bad = true;
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) F[i] = sh->fout[i];
-            } else {
-                const double* dcol = sh->dfdp + sh->plist[c - 1] * NX;
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) F[i] = dcol[i];
-                PB_ROLL
-                for (int j = 0; j < NX; ++j) {
-                    const double sj = sh->zn[0][(j) * ncol + (c)] + sh->acor[(j) * ncol + (c)];
-                    PB_UNROLL
-                    for (int r = 0; r < NX; ++r) F[r] += sh->Jcur[r + j * NX] * sj;
-                }
-                bool ok = true;
-                PB_UNROLL
-                for (int i = 0; i < NX; ++i) ok = ok && isfinite(F[i]);
-                if (!ok) bad = true;
+        g.sync();  // element-wise writers of zn / acor may have been other lanes
+        if (phase == PH_STATE) {
+            PB_FOR_ROWS0(r, i) sh->yj[i] = sh->zn[0][i] + sh->acor[i];
+            g.sync();
+            int ok = 1;
+            if (g.lane() == 0) ok = eval_xdot_shared<M>(sh, t) ? 1 : 0;
+            g.sync();
+            bad = g.bcast0(ok) == 0;
+            PB_FOR_ROWS0(r, i) {
+                const double F = sh->fout[i];
+                sh->b[i] = raw ? F : (rl1 * sh->zn[1][i] + sh->acor[i]) - gamma * F;
             }
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i)
-                sh->b[(i) * ncol + (c)] = raw ? F[i] : (rl1 * sh->zn[1][(i) * ncol + (c)] + sh->acor[(i) * ncol + (c)]) - gamma * F[i];
+            nfe++;
+        } else {
+            // corrected sensitivities of all columns -> scratch (read by every lane below)
+            PB_FOR_RANGE(e, NX, NX * ncol) sh->scr[e] = sh->zn[0][e] + sh->acor[e];
+            double jrow[RPL][NX];
+            PB_FOR_ROWS(r, i) {
+                PB_UNROLL
+                for (int j = 0; j < NX; ++j) jrow[r][j] = sh->Jcur[i + j * NX];
+            }
+            g.sync();
+            PB_UNROLL_COLS
+            for (int c = 1 + col_group(); c <= ns; c += CG) {
+                const double* dcol = sh->dfdp + sh->plist[c - 1] * NX;
+                const double* sc = sh->scr + c * NX;
+                double sv[NX];
+                PB_UNROLL
+                for (int j = 0; j < NX; ++j) sv[j] = sc[j];
+                PB_FOR_ROWS(r, i) {
+                    double F = dcol[i];
+                    PB_UNROLL
+                    for (int j = 0; j < NX; ++j) F += jrow[r][j] * sv[j];
+                    if (!isfinite(F)) bad = true;
+                    const int e = c * NX + i;
+                    sh->b[e] = raw ? F : (rl1 * sh->zn[1][e] + sh->acor[e]) - gamma * F;
+                }
+            }
+            nfSe += ns;
         }
-        if (phase == PH_STATE) nfe++;
-        else nfSe += ns;
+        g.sync();
         if (g.any(bad)) return phase == PH_STATE ? cv::RHSFUNC_RECVR : cv::SRHSFUNC_RECVR;
         return 0;
     }
 
-    /// state lane: sh->ysh = zn[0] + acor of the state column (the corrected state y_n)
+    /// sh->ysh = zn[0] + acor of the state column (the corrected state y_n)
     PB_HD void publish_state() {
         g.sync();
-        if (g.lane() == 0) {
-            PB_UNROLL_X
-            for (int i = 0; i < NX; ++i) sh->ysh[i] = sh->zn[0][(i) * ncol + (0)] + sh->acor[(i) * ncol + (0)];
-        }
+        PB_FOR_ROWS0(r, i) sh->ysh[i] = sh->zn[0][i] + sh->acor[i];
         g.sync();
     }
 
@@ -624,7 +785,7 @@ struct Bdf {
     }
 
     // ---------------------------------------------------------------- linear algebra
-    /// cvLsSetup + cvLsLinSys + dense GETRF (cvodes_ls.c:1611-1708,1386-1470); the state the
+    /// cvLsSetup + cvLsLinSys (cvodes_ls.c:1611-1708,1386-1470) + the inversion; the state the
     /// Jacobian is evaluated at is sh->yj.
     PB_HD int lsetup() {
         const double dgamma = fabs(pb_div(gamma, gammap) - 1.0);
@@ -642,76 +803,85 @@ struct Bdf {
                 if (!isfinite(sh->Jsaved[e])) bad = true;
             if (g.any(bad)) ret = 1;
         }
-        if (g.lane() == 0 && ret == 0) ret = lu_factor_shared<M>(sh, gamma);
+        if (ret == 0) ret = invert_newton_matrix<M, Grp>(sh, g, gamma);
         if (jbad) { nje++; nstlj = nst; }
         jcur = jbad;
         nsetups++;
-        g.sync();
-        return g.bcast0(ret);
+        return ret;
     }
 
-    /// dense GETRS for column c (sundials_dense.c:150-182) + cvLsSolve's gamma-ratio scaling
-    /// (cvodes_ls.c:1849-1854): x = -(P b)[.] gathered through the stored row order, forward and
-    /// backward substitution in registers against the group's factors.
-    PB_HD void lsolve_neg_b(int c, double* x) const {
-        PB_UNROLL
-        for (int i = 0; i < NX; ++i) x[i] = -sh->b[sh->perm[i] * ncol + c];
-        PB_UNROLL
-        for (int k = 0; k < NX - 1; ++k) {
+    /// Newton update of the columns [cmin, cmax]: delta = -(I - gamma J)^-1 b (dense GETRS
+    /// sundials_dense.c:150-182 as a mat-vec with the inverse) with cvLsSolve's gamma-ratio
+    /// scaling (cvodes_ls.c:1849-1854); acor += delta; returns the WRMS norm of delta.
+    PB_HD double newton_update(int cmin, int cmax) {
+        double arow[RPL][NX];
+        PB_FOR_ROWS(r, i) {
             PB_UNROLL
-            for (int i = k + 1; i < NX; ++i) x[i] -= sh->LU[i + k * NX] * x[k];
+            for (int j = 0; j < NX; ++j) arow[r][j] = sh->Ainv[i + j * NX];
         }
-        PB_UNROLL
-        for (int k = NX - 1; k > 0; --k) {
-            x[k] *= sh->LU[k + k * NX];
+        const double nsc = (gamrat != 1.0) ? pb_div(-2.0, 1.0 + gamrat) : -1.0;
+        PB_UNROLL_COLS
+        for (int c = cmin + col_group(); c <= cmax; c += CG) {
+            const double* bc = sh->b + c * NX;
+            double bv[NX];
             PB_UNROLL
-            for (int i = 0; i < k; ++i) x[i] -= sh->LU[i + k * NX] * x[k];
+            for (int j = 0; j < NX; ++j) bv[j] = bc[j];
+            PB_FOR_ROWS(r, i) {
+                double acc = 0.0;
+                PB_UNROLL
+                for (int j = 0; j < NX; ++j) acc += arow[r][j] * bv[j];
+                const double x = nsc * acc;
+                const int e = c * NX + i;
+                sh->acor[e] += x;
+                const double prod = x * sh->ewt[e];
+                sh->scr[c * NXS + i] = prod * prod;
+            }
         }
-        x[0] *= sh->LU[0];
-        if (gamrat != 1.0) {
-            const double sc = pb_div(2.0, 1.0 + gamrat);
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) x[i] *= sc;
-        }
+        return colnorm(cmin, cmax);
     }
 
     // ---------------------------------------------------------------- BDF coefficients
     /// cvSetBDF + cvSetTqBDF + cvSet (cvodes.c:6788-6879, 6617-6629); computed redundantly by
-    /// every lane (a few dozen flops), the arrays are kept in shared memory.
+    /// every lane, fully unrolled so that l[] stays in registers.
     PB_HD void cvset() {
-        double l_[cv::L_MAX + 1];
         double alpha0, alpha0_hat, xi_inv, xistar_inv, hsum;
-        l_[0] = l_[1] = xi_inv = xistar_inv = 1.0;
-        PB_ROLL
-        for (int i = 2; i <= cv::L_MAX; ++i) l_[i] = 0.0;
+        l[0] = l[1] = xi_inv = xistar_inv = 1.0;
+        PB_UNROLL
+        for (int i = 2; i < cv::L_MAX; ++i) l[i] = 0.0;
         alpha0 = alpha0_hat = -1.0;
         hsum = h;
         if (q > 1) {
-            PB_ROLL
-            for (int j = 2; j < q; ++j) {
-                hsum += sh->tau[j - 1];
-                xi_inv = pb_div(h, hsum);
-                alpha0 -= pb_rcp((double)j);
-                PB_ROLL
-                for (int i = j; i >= 1; --i) l_[i] += l_[i - 1] * xi_inv;
+            PB_UNROLL
+            for (int j = 2; j < cv::Q_MAX; ++j) {
+                if (j < q) {
+                    hsum += sh->tau[j - 1];
+                    xi_inv = pb_div(h, hsum);
+                    alpha0 -= 1.0 / (double)j;
+                    PB_UNROLL
+                    for (int i = j; i >= 1; --i) l[i] += l[i - 1] * xi_inv;
+                }
             }
-            alpha0 -= pb_rcp((double)q);
-            xistar_inv = -l_[1] - alpha0;
+            alpha0 -= pb_inv_int(q);
+            xistar_inv = -l[1] - alpha0;
             hsum += sh->tau[q - 1];
             xi_inv = pb_div(h, hsum);
-            alpha0_hat = -l_[1] - xi_inv;
-            PB_ROLL
-            for (int i = q; i >= 1; --i) l_[i] += l_[i - 1] * xistar_inv;
+            alpha0_hat = -l[1] - xi_inv;
+            PB_UNROLL
+            for (int i = cv::Q_MAX; i >= 1; --i)
+                if (i <= q) l[i] += l[i - 1] * xistar_inv;
         }
-        double tq1 = sh->tq[1], tq3 = sh->tq[3];
+        double lq = l[1];
+        PB_UNROLL
+        for (int i = 2; i <= cv::Q_MAX; ++i)
+            if (i == q) lq = l[i];
         const double A1 = 1.0 - alpha0_hat + alpha0;
         const double A2 = 1.0 + q * A1;
-        const double tq2 = fabs(pb_div(A1, alpha0 * A2));
-        const double tq5 = fabs(pb_div(A2 * xistar_inv, l_[q] * xi_inv));
+        tq2 = fabs(pb_div(A1, alpha0 * A2));
+        tq5 = fabs(pb_div(A2 * xistar_inv, lq * xi_inv));
         if (qwait == 1) {
             if (q > 1) {
-                const double C = pb_div(xistar_inv, l_[q]);
-                const double A3 = alpha0 + pb_rcp((double)q);
+                const double C = pb_div(xistar_inv, lq);
+                const double A3 = alpha0 + pb_inv_int(q);
                 const double A4 = alpha0_hat + xi_inv;
                 const double Cpinv = pb_div(1.0 - A4 + A3, A3);
                 tq1 = fabs(C * Cpinv);
@@ -720,23 +890,13 @@ struct Bdf {
             }
             hsum += sh->tau[q];
             xi_inv = pb_div(h, hsum);
-            const double A5 = alpha0 - pb_rcp((double)(q + 1));
+            const double A5 = alpha0 - pb_inv_int(q + 1);
             const double A6 = alpha0_hat - xi_inv;
             const double Cppinv = pb_div(1.0 - A6 + A5, A2);
             tq3 = fabs(pb_div(Cppinv, xi_inv * (q + 2) * A5));
         }
-        g.sync();
-        if (g.lane() == 0) {
-            PB_ROLL
-            for (int i = 0; i <= cv::L_MAX; ++i) sh->l[i] = l_[i];
-            sh->tq[1] = tq1;
-            sh->tq[2] = tq2;
-            sh->tq[3] = tq3;
-            sh->tq[4] = pb_div(cv::CORTES, tq2);
-            sh->tq[5] = tq5;
-        }
-        g.sync();
-        rl1 = pb_rcp(l_[1]);
+        tq4 = pb_div(cv::CORTES, tq2);
+        rl1 = pb_rcp(l[1]);
         gamma = h * rl1;
         if (nst == 0) gammap = gamma;
         gamrat = (nst > 0) ? pb_div(gamma, gammap) : 1.0;
@@ -776,52 +936,14 @@ struct Bdf {
         hscale = h;
         nscon = 0;
     }
-    /// cvAdjustOrder -> cvIncreaseBDF / cvDecreaseBDF (cvodes.c:6134-6143, 6256-6351, 6363-6415)
-    PB_HD void adjust_order(int deltaq) {
-        if ((q == 2) && (deltaq != 1)) return;
-        double lc[cv::L_MAX + 1];
-        for (int i = 0; i <= cv::L_MAX; ++i) lc[i] = 0.0;
-        lc[2] = 1.0;
-        int src, jmax;
-        double A1 = 0.0;
-        if (deltaq == 1) {
-            double alpha1 = 1.0, prod = 1.0, xiold = 1.0, alpha0 = -1.0;
-            double hsum = hscale;
-            for (int j = 1; j < q; ++j) {
-                hsum += sh->tau[j + 1];
-                const double xi = pb_div(hsum, hscale);
-                prod *= xi;
-                alpha0 -= pb_rcp((double)(j + 1));
-                alpha1 += pb_rcp(xi);
-                for (int i = j + 2; i >= 2; --i) lc[i] = lc[i] * xiold + lc[i - 1];
-                xiold = xi;
-            }
-            A1 = pb_div(-alpha0 - alpha1, prod);
-            src = L;   // new column zn[L] = A1 * (saved correction in zn[qmax]); L = q+1 <= qmax
-            jmax = q;  // N_VScaleAddMulti(q-1, l+2, zn[L], zn+2, zn+2)
-        } else {
-            double hsum = 0.0;
-            for (int j = 1; j <= q - 2; ++j) {
-                hsum += sh->tau[j];
-                const double xi = pb_div(hsum, hscale);
-                for (int i = j + 2; i >= 2; --i) lc[i] = lc[i] * xi + lc[i - 1];
-            }
-            for (int j = 2; j < q; ++j) lc[j] = -lc[j];
-            src = q;
-            jmax = q - 1;  // zn[j] -= l[j]*zn[q], j = 2..q-1
-        }
-        PB_FOR_ELEMS(e) {
-            if (deltaq == 1) sh->zn[src][e] = A1 * sh->zn[cv::Q_MAX][e];
-            const double zs = sh->zn[src][e];
-            for (int j = 2; j <= jmax; ++j) sh->zn[j][e] += lc[j] * zs;
-        }
-    }
+    /// cvAdjustOrder (out of line, one copy)
+    PB_HD void adjust_order(int deltaq) { adjust_order_shared<M, Grp>(sh, g, ncol, q, L, hscale, deltaq); }
 
     // ---------------------------------------------------------------- nonlinear solve
     /// cvNls / cvStgrNls + SUNNonlinSolSolve_Newton + cvNlsConvTest{,SensStg} for the columns of
     /// `phase` (cvodes.c:6894-7007, 7167-7210; sunnonlinsol_newton.c:176-335; cvodes_nls.c:
     /// 298-342; cvodes_nls_stg.c:238-375).  The state corrector and the staggered sensitivity
-    /// corrector are the same Newton iteration on different columns with the same factors, so
+    /// corrector are the same Newton iteration on different columns with the same inverse, so
     /// they share one copy of the code.  On success the corrected vector is zn[0]+acor.
     PB_HD int nls(int phase, int nflag) {
         const int cmin = phase_cmin(phase), cmax = phase_cmax(phase);
@@ -831,10 +953,7 @@ struct Bdf {
             setup_pending = (nflag == cv::PREV_CONV_FAIL) || (nflag == cv::PREV_ERR_FAIL) || (nst == 0) ||
                             (nst >= nstlp + cv::MSBP) || (fabs(gamrat - 1.0) > cv::DGMAX_LSETUP);
         }
-        PB_FOR_COLS(c, cmin, cmax) {
-            PB_UNROLL_X
-            for (int i = 0; i < NX; ++i) sh->acor[(i) * ncol + (c)] = 0.0;
-        }
+        PB_FOR_RANGE(e, cmin * NX, (cmax + 1) * NX) sh->acor[e] = 0.0;
         bool jbad = false;
         bool top = true;  // residual at the top of a solve attempt: failures there are final
         int m_it = 0;
@@ -845,10 +964,7 @@ struct Bdf {
                 if (jbad) convfail = cv::FAIL_BAD_J;
                 if (phase == PH_SENS) {  // Jacobian at the converged state (cv_y), cvodes_nls_stg.c:252
                     g.sync();
-                    if (g.lane() == 0) {
-                        PB_UNROLL_X
-                        for (int i = 0; i < NX; ++i) sh->yj[i] = sh->ysh[i];
-                    }
+                    PB_FOR_ROWS0(r, i) sh->yj[i] = sh->ysh[i];
                 }  // state phase: rhs() has just put zn[0]+acor into sh->yj
                 const int lr = lsetup();
                 setup_pending = false;
@@ -865,25 +981,12 @@ struct Bdf {
             if (ret == 0) {
                 if (phase == PH_STATE) nni++;
                 else nniS++;
-                double loc = 0.0;  // max over own columns of sum((delta*ewt)^2)
-                PB_FOR_COLS(c, cmin, cmax) {
-                    double x[NX];
-                    lsolve_neg_b(c, x);
-                    double s = 0.0;
-                    PB_UNROLL
-                    for (int i = 0; i < NX; ++i) {
-                        sh->acor[(i) * ncol + (c)] += x[i];
-                        const double prod = x[i] * sh->ewt[(i) * ncol + (c)];
-                        s += prod * prod;
-                    }
-                    if (s > loc) loc = s;
-                }
-                const double del = group_wrms(g, loc, NX);
+                const double del = newton_update(cmin, cmax);
                 double cr = (phase == PH_STATE) ? crate : crateS;
                 if (m_it > 0) cr = fmax(cv::CRDOWN * cr, pb_div(del, delp));
                 if (phase == PH_STATE) crate = cr;
                 else crateS = cr;
-                const double dcon = pb_div(del * fmin(1.0, cr), sh->tq[4]);
+                const double dcon = pb_div(del * fmin(1.0, cr), tq4);
                 if (dcon <= 1.0) {
                     const double an = (m_it == 0) ? del : wnorm1(cmin, cmax, sh->acor);
                     if (phase == PH_STATE) {
@@ -911,10 +1014,8 @@ struct Bdf {
                 jbad = true;
                 top = true;
                 m_it = 0;
-                PB_FOR_COLS(c, cmin, cmax) {
-                    PB_UNROLL_X
-                    for (int i = 0; i < NX; ++i) sh->acor[(i) * ncol + (c)] = 0.0;
-                }
+                g.sync();
+                PB_FOR_RANGE(e, cmin * NX, (cmax + 1) * NX) sh->acor[e] = 0.0;
                 continue;
             }
             return ret;
@@ -933,15 +1034,17 @@ struct Bdf {
             if ((q == 1) && (nst > 1)) sh->tau[2] = sh->tau[1];
             sh->tau[1] = h;
         }
-        g.sync();
         qwait--;
         const bool save = (qwait == 1) && (q != cv::Q_MAX);
         PB_FOR_ELEMS(e) {
             const double a = sh->acor[e];
-            for (int j = 0; j <= q; ++j) sh->zn[j][e] += sh->l[j] * a;
+            PB_UNROLL
+            for (int j = 0; j < cv::L_MAX; ++j)
+                if (j <= q) sh->zn[j][e] += l[j] * a;
             if (save) sh->zn[cv::Q_MAX][e] = a;
         }
-        if (save) saved_tq5 = sh->tq[5];
+        g.sync();
+        if (save) saved_tq5 = tq5;
     }
 
     /// cvPrepareNextStep with cvSetEta, cvComputeEtaqm1 / cvComputeEtaqp1 / cvChooseEta
@@ -954,7 +1057,7 @@ struct Bdf {
             eta = 1.0;
             return;
         }
-        etaq = pb_rcp(pb_pow(cv::BIAS2 * dsm, pb_rcp((double)L)) + cv::ADDON);
+        etaq = pb_rcp(pb_pow(cv::BIAS2 * dsm, pb_inv_int(L)) + cv::ADDON);
         qprime = q;
         eta = etaq;
         if (qwait == 0) {
@@ -964,8 +1067,8 @@ struct Bdf {
             if (q > 1) {
                 const int qq = q;
                 double ddn = wnorm1(0, ecmax, sh->zn[qq]);
-                ddn = ddn * sh->tq[1];
-                etaqm1 = pb_rcp(pb_pow(cv::BIAS1 * ddn, pb_rcp((double)q)) + cv::ADDON);
+                ddn = ddn * tq1;
+                etaqm1 = pb_rcp(pb_pow(cv::BIAS1 * ddn, pb_inv_int(q)) + cv::ADDON);
             }
             etaqp1 = 0.0;
             if (q != cv::Q_MAX) {
@@ -973,10 +1076,10 @@ struct Bdf {
                     const double hr = pb_div(h, sh->tau[2]);
                     double hp = 1.0;
                     for (int i = 0; i < L; ++i) hp *= hr;  // SUNRpowerI
-                    const double cquot = pb_div(sh->tq[5], saved_tq5) * hp;
+                    const double cquot = pb_div(tq5, saved_tq5) * hp;
                     double dup = wnorm2(0, ecmax, sh->zn[cv::Q_MAX], -cquot, sh->acor, 1.0);
-                    dup = dup * sh->tq[3];
-                    etaqp1 = pb_rcp(pb_pow(cv::BIAS3 * dup, pb_rcp((double)(L + 1))) + cv::ADDON);
+                    dup = dup * tq3;
+                    etaqp1 = pb_rcp(pb_pow(cv::BIAS3 * dup, pb_inv_int(L + 1)) + cv::ADDON);
                 }
             }
             // cvChooseEta
@@ -995,10 +1098,8 @@ struct Bdf {
                 qprime = q + 1;
                 // store Delta_n in zn[qmax] for the order increase (state always; sensitivities
                 // only if they take part in the error test, cvodes.c:7973-7987)
-                PB_FOR_COLS(c, 0, ecmax) {
-                    PB_UNROLL_X
-                    for (int i = 0; i < NX; ++i) sh->zn[cv::Q_MAX][(i) * ncol + (c)] = sh->acor[(i) * ncol + (c)];
-                }
+                PB_FOR_RANGE(e, 0, (ecmax + 1) * NX) sh->zn[cv::Q_MAX][e] = sh->acor[e];
+                g.sync();
             }
         }
         // cvSetEta (hmax_inv = 0, hmin = 0)
@@ -1023,7 +1124,7 @@ struct Bdf {
             }
             int factorial = 1;
             for (int i = 1; i <= q - 1; ++i) factorial *= i;
-            const double sq = pb_div(factorial * q * (q + 1) * acnrm, fmax(sh->tq[5], cv::TINY));
+            const double sq = pb_div(factorial * q * (q + 1) * acnrm, fmax(tq5, cv::TINY));
             const double sqm1 = sqv[0] * (factorial * q);
             const double sqm2 = sqv[1] * factorial;
             g.sync();
@@ -1038,7 +1139,7 @@ struct Bdf {
         }
         if (qprime >= q) {
             if ((q >= 3) && (nscon >= q + 5)) {
-                const int ldflag = sldet_shared(sh->ssdat, q);
+                const int ldflag = sldet_shared<M, Grp>(sh, g, q);
                 if (ldflag > 3) {
                     qprime = q - 1;
                     eta = etaqm1;
@@ -1054,10 +1155,13 @@ struct Bdf {
 
     /// zn[1] = h * f(tn, zn[0]) for the state and (if any) the sensitivities; acor is scratch
     PB_HD int reload_zn1() {
+        g.sync();
         PB_FOR_ELEMS(e) sh->acor[e] = 0.0;
+        g.sync();
         const int r = rhs_all_raw(tn, sensi);
         if (r) return r;
         PB_FOR_ELEMS(e) sh->zn[1][e] = h * sh->b[e];
+        g.sync();
         return 0;
     }
 
@@ -1076,10 +1180,9 @@ struct Bdf {
         undo_ = restart_ = false;
     }
 
-    /// One attempt of the step (after a failed attempt: first the restore pass).  Returns 0 when
-    /// the step was completed (history updated, next step/order chosen), 1 when another attempt
-    /// is needed, or a negative failure code.
-    PB_HD int step_attempt() {
+    /// First part of a step attempt (after a failed attempt: first the restore pass): order /
+    /// step-size adjustment, prediction, BDF coefficients.  Returns 0 or a negative failure code.
+    PB_HD int attempt_predict() {
         for (;;) {
             if (undo_) {
                 tn = saved_t_;  // cvRestore
@@ -1115,39 +1218,48 @@ struct Bdf {
             undo_ = false;
         }
         cvset();
-        int fail = 0;  // 1/3: corrector failure (state/sens); 2/4: error-test failure (state/sens)
-        int ret = 0;
-        for (int phase_ = PH_STATE; phase_ <= PH_SENS; ++phase_) {
-            int phase = phase_;
-            PB_OPAQUE_INT(phase);
-            if (phase == PH_SENS) {
-                if (fail || !sensi) break;
-                ncf_ = nef_ = 0;
-                publish_state();
-                // f at the converged y (cvodes.c:5947-5955); AMICI's sensitivity RHS does not
-                // use it -- kept for the recoverable-failure semantics
-                int bad = 0;
-                if (g.lane() == 0) {
-                    PB_UNROLL_X
-                    for (int i = 0; i < NX; ++i) sh->yj[i] = sh->ysh[i];
-                    bad = eval_xdot_shared<M>(sh, tn) ? 0 : 1;
-                }
-                nfe++;
-                if (g.bcast0(bad)) { fail = 5; break; }
-                refresh_Jcur(tn);
-            }
-            ret = nls(phase, nflag_);
-            if (ret != 0) {
-                fail = 1 + 2 * phase;
-            } else if (phase == PH_STATE) {
-                dsm_ = acnrm * sh->tq[2];
-                if (dsm_ > 1.0) fail = 2;
-            } else if (opt.errconS) {
-                dsmS_ = acnrmS * sh->tq[2];
-                if (dsmS_ > 1.0) fail = 4;
-                else if (dsmS_ > dsm_) dsm_ = dsmS_;
-            }
+        fail_ = 0;  // 1/3: corrector failure (state/sens); 2/4: error-test failure (state/sens); 5: f(y_n) not finite
+        ret_ = 0;
+        return 0;
+    }
+
+    /// The corrector of one phase of the attempt (state, then -- staggered -- all sensitivities)
+    /// with its error test (cvodes.c:5905-6008).
+    PB_HD void attempt_correct(int phase) {
+        if (phase == PH_SENS) {
+            if (fail_ || !sensi) return;
+            ncf_ = nef_ = 0;
+            publish_state();
+            // f at the converged y (cvodes.c:5947-5955); AMICI's sensitivity RHS does not
+            // use it -- kept for the recoverable-failure semantics
+            int bad = 0;
+            PB_FOR_ROWS0(r, i) sh->yj[i] = sh->ysh[i];
+            g.sync();
+            if (g.lane() == 0) bad = eval_xdot_shared<M>(sh, tn) ? 0 : 1;
+            nfe++;
+            if (g.bcast0(bad)) { fail_ = 5; return; }
+            refresh_Jcur(tn);
         }
+        ret_ = nls(phase, nflag_);
+        if (ret_ != 0) {
+            fail_ = 1 + 2 * phase;
+        } else if (phase == PH_STATE) {
+            dsm_ = acnrm * tq2;
+            if (dsm_ > 1.0) fail_ = 2;
+        } else if (opt.errconS) {
+            dsmS_ = acnrmS * tq2;
+            if (dsmS_ > 1.0) fail_ = 4;
+            else if (dsmS_ > dsm_) dsm_ = dsmS_;
+        }
+    }
+
+    /// End of the attempt: cvCompleteStep / cvPrepareNextStep / cvBDFStab on success, otherwise
+    /// cvHandleNFlag (:7309-7363) and cvDoErrorTest (:7461-7614) folded into ONE failure handler.
+    /// Returns 0 when the step was completed, 1 when another attempt is needed, or a negative
+    /// failure code.
+    PB_HD int attempt_finish() {
+        const int fail = fail_;
+        const int ret = ret_;
         if (fail == 0) {
             complete_step();
             prepare_next_step(dsm_);
@@ -1180,7 +1292,7 @@ struct Bdf {
             if ((fabs(h) <= 0.0) || (e == cv::MXNEF)) return SIM_ERR_FAILURE;
             etamax = 1.0;
             if (e <= cv::MXNEF1) {
-                eta = pb_rcp(pb_pow(cv::BIAS2 * (fail == 2 ? dsm_ : dsmS_), pb_rcp((double)L)) + cv::ADDON);
+                eta = pb_rcp(pb_pow(cv::BIAS2 * (fail == 2 ? dsm_ : dsmS_), pb_inv_int(L)) + cv::ADDON);
                 eta = fmax(cv::ETA_MIN_EF, eta);
                 if (e >= cv::SMALL_NEF) eta = fmin(eta, cv::ETA_MAX_EF);
                 do_rescale_ = true;
@@ -1210,15 +1322,12 @@ struct Bdf {
         const int ecmax = errtest_cmax();
         // cvUpperBoundH0
         double hub_inv = 0.0;
-        PB_FOR_COLS(c, 0, ecmax) {
-            PB_UNROLL_X
-            for (int i = 0; i < NX; ++i) {
-                const double den = cv::HUB_FACTOR * fabs(sh->zn[0][(i) * ncol + (c)]) + pb_rcp(sh->ewt[(i) * ncol + (c)]);
-                const double v = pb_div(fabs(sh->zn[1][(i) * ncol + (c)]), den);
-                if (v > hub_inv) hub_inv = v;
-            }
+        PB_FOR_RANGE(e, 0, (ecmax + 1) * NX) {
+            const double den = cv::HUB_FACTOR * fabs(sh->zn[0][e]) + pb_rcp(sh->ewt[e]);
+            const double v = pb_div(fabs(sh->zn[1][e]), den);
+            if (v > hub_inv) hub_inv = v;
         }
-        hub_inv = group_max(g, hub_inv);
+        hub_inv = g.max(hub_inv);
         double hub = cv::HUB_FACTOR * tdist;
         if (hub * hub_inv > 1.0) hub = pb_rcp(hub_inv);
         double hg = sqrt(hlb * hub);
@@ -1234,6 +1343,7 @@ struct Bdf {
             for (int count2 = 1; count2 <= cv::HIN_MAX_ITERS; ++count2) {
                 // cvYddNorm: f at (tn + hg, zn0 + hg*zn1), difference quotient, WRMS norm
                 const double hgs = hg * sign;
+                g.sync();
                 PB_FOR_ELEMS(e) sh->acor[e] = hgs * sh->zn[1][e];
                 retval = rhs_all_raw(tn + hgs, withS);
                 if (retval == 0) {
@@ -1244,7 +1354,9 @@ struct Bdf {
                 }
                 hg *= 0.2;
             }
+            g.sync();
             PB_FOR_ELEMS(e) sh->acor[e] = 0.0;
+            g.sync();
             if (!hgOK) {
                 if (count1 <= 2) return retval == cv::RHSFUNC_RECVR ? SIM_REPTD_RHSFUNC_ERR : SIM_REPTD_SRHSFUNC_ERR;
                 hnew = hs;
@@ -1314,10 +1426,7 @@ struct Bdf {
     PB_HD bool data_point(double t, const double* my, const double* sd, double& llh, double* y_out,
                           double* sigmay_out) {
         g.sync();
-        if (g.lane() == 0) {
-            PB_UNROLL
-            for (int i = 0; i < NX; ++i) sh->ysh[i] = sh->zn[0][(i) * ncol + (0)];
-        }
+        PB_FOR_ROWS0(r, i) sh->ysh[i] = sh->zn[0][i];
         g.sync();
         double y[NY], sig[NY];
         M::y(y, t, sh->ysh, sh->p, sh->k);
@@ -1392,7 +1501,7 @@ struct Bdf {
             for (int iy = 0; iy < NY; ++iy) dJydp += dJyds[iy] * dsdp[iy];
             double a = dJydp;
             PB_UNROLL
-            for (int ix = 0; ix < NX; ++ix) a += dJydx[ix] * sh->zn[0][(ix) * ncol + (c)];
+            for (int ix = 0; ix < NX; ++ix) a += dJydx[ix] * sh->zn[0][c * NX + ix];
             sh->sllh[c] -= a;
         }
         return true;
@@ -1410,7 +1519,7 @@ struct Bdf {
         ncol = ns + 1;
         sensi = ns > 0;
         g.sync();
-        PB_FOR_ALL_COLS(c) {
+        PB_FOR_COLS(c, 0, ns) {
             double v[NX];
             PB_UNROLL
             for (int i = 0; i < NX; ++i) v[i] = 0.0;
@@ -1418,14 +1527,18 @@ struct Bdf {
             else M::sx0(v, opt.t0, sh->p, sh->k, sh->plist[c - 1]);
             PB_UNROLL
             for (int i = 0; i < NX; ++i) {
-                sh->zn[0][(i) * ncol + (c)] = v[i];
-                for (int j = 1; j < cv::L_MAX; ++j) sh->zn[j][(i) * ncol + (c)] = 0.0;
-                sh->acor[(i) * ncol + (c)] = 0.0;
-                sh->ewt[(i) * ncol + (c)] = 1.0;
-                sh->b[(i) * ncol + (c)] = 0.0;
+                const int e = c * NX + i;
+                sh->zn[0][e] = v[i];
+                for (int j = 1; j < cv::L_MAX; ++j) sh->zn[j][e] = 0.0;
+                sh->acor[e] = 0.0;
+                sh->ewt[e] = 1.0;
+                sh->b[e] = 0.0;
             }
             sh->sllh[c] = 0.0;
         }
+        PB_UNROLL
+        for (int j = 0; j < cv::L_MAX; ++j) l[j] = 0.0;
+        tq1 = tq2 = tq3 = tq4 = tq5 = 0.0;
         tn = opt.t0;
         q = 1; L = 2; qwait = L; qprime = 1;
         etamax = cv::ETA_MAX_FS;
@@ -1444,8 +1557,7 @@ struct Bdf {
         }
         for (int e = g.lane(); e < NX * NP; e += G) sh->dfdp[e] = 0.0;
         if (g.lane() == 0) {
-            for (int i = 0; i <= cv::L_MAX; ++i) { sh->l[i] = 0.0; sh->tau[i] = 0.0; }
-            for (int i = 0; i < 6; ++i) sh->tq[i] = 0.0;
+            for (int i = 0; i <= cv::L_MAX; ++i) sh->tau[i] = 0.0;
             for (int i = 0; i < 6; ++i)
                 for (int k = 0; k < 4; ++k) sh->ssdat[i][k] = 0.0;
         }
@@ -1454,21 +1566,28 @@ struct Bdf {
         it_ = 0;
         sim_status_ = SIM_SUCCESS;
         in_cvode_ = in_step_ = false;
+        stage_ = ST_PRE;
+        fail_ = ret_ = 0;
         step_begin();
     }
 
-    /// Advance the simulation by at most ONE step attempt (plus whatever bookkeeping precedes it:
-    /// output times that need no integration, the CVode prologue, the per-step checks of the CVode
-    /// loop cvodes.c:3366-3490, and after a completed step the tstop tests cvodes.c:3504-3605).
-    /// Returns true when the simulation has ended; status() / llh() then hold the result and
-    /// d llh / d p (w.r.t. the unscaled parameter) is in sh->sllh[1..ns].
-    PB_HD bool advance() {
+    /// The simulation advances by at most ONE step attempt per round of
+    ///     stage_pre();  stage_nls(PH_STATE);  stage_nls(PH_SENS);  stage_post();
+    /// Each stage returns to the caller, so that the kernel can re-converge the lane groups of a
+    /// warp (and the warps of a CTA) between the stages: every group then walks through the same
+    /// code at the same time, whatever happened to it in the previous stage.
+    ///
+    /// stage_pre: whatever bookkeeping precedes the attempt -- output times that need no
+    /// integration, the CVode prologue, the per-step checks of the CVode loop cvodes.c:3366-3490
+    /// -- then order/step adjustment, prediction and BDF coefficients.
+    PB_HD void stage_pre() {
+        if (stage_ != ST_PRE) return;
         if (!in_step_) {
             if (!in_cvode_) {
                 for (;;) {
-                    if (it_ >= io_.nt) return finish(SIM_SUCCESS);
+                    if (it_ >= io_.nt) { finish(SIM_SUCCESS); return; }
                     tout_ = io_.t[it_];
-                    if (isinf(tout_)) return finish(SIM_SUCCESS);  // post-equilibration: out of scope
+                    if (isinf(tout_)) { finish(SIM_SUCCESS); return; }  // post-equilibration: out of scope
                     bool integrate = (tout_ > opt.t0) && (tn < tout_);
                     if (integrate) {  // is_next_t_too_close, forwardproblem.cpp:23-35
                         const double tdiff = tout_ - tn;
@@ -1480,26 +1599,46 @@ struct Bdf {
 #if defined(PB200_HOST_TRACE)
                     if (io_.trace) { io_.trace[2 * it_] = nst; io_.trace[2 * it_ + 1] = q; }
 #endif
-                    if (!data_point(tout_, io_.my + (size_t)it_ * NY, io_.sd + (size_t)it_ * NY, llh_, yo, so))
-                        return finish(SIM_ERROR);
+                    if (!data_point(tout_, io_.my + (size_t)it_ * NY, io_.sd + (size_t)it_ * NY, llh_, yo, so)) {
+                        finish(SIM_ERROR);
+                        return;
+                    }
                     it_++;
                 }
                 const int r = cvode_begin(tout_);
-                if (r < 0) return finish(r);
-                if (r == cv::TSTOP_RETURN) return false;  // already at tout: data point on the next call
+                if (r < 0) { finish(r); return; }
+                if (r == cv::TSTOP_RETURN) return;  // already at tout: data point in the next round
                 in_cvode_ = true;
             }
             // top of the CVode step loop
             if (nst > 0) {
-                if (!ewt_set()) return finish(SIM_ILL_INPUT);
+                if (!ewt_set()) { finish(SIM_ILL_INPUT); return; }
             }
-            if (nstloc_ >= mxstep_) return finish(SIM_TOO_MUCH_WORK);
+            if (nstloc_ >= mxstep_) { finish(SIM_TOO_MUCH_WORK); return; }
             const double nrm = wnorm1(0, errtest_cmax(), sh->zn[0]);
-            if (cv::UROUND * nrm > 1.0) return finish(SIM_TOO_MUCH_ACC);
+            if (cv::UROUND * nrm > 1.0) { finish(SIM_TOO_MUCH_ACC); return; }
             step_begin();
             in_step_ = true;
         }
-        const int r = step_attempt();
+        const int r = attempt_predict();
+        if (r < 0) { finish(r); return; }
+        stage_ = ST_NLS;
+    }
+
+    /// stage_nls: the Newton corrector of one phase (state, then all sensitivities) + error test
+    PB_HD void stage_nls(int phase) {
+        if (stage_ != ST_NLS) return;
+        attempt_correct(phase);
+    }
+
+    /// stage_post: step completion or failure handling, then the tstop tests after a completed
+    /// step (cvodes.c:3504-3605).  Returns true when the simulation has ended; status() / llh()
+    /// then hold the result and d llh / d p (w.r.t. the unscaled parameter) is in sh->sllh[1..ns].
+    PB_HD bool stage_post() {
+        if (stage_ == ST_DONE) return true;
+        if (stage_ != ST_NLS) return false;
+        stage_ = ST_PRE;
+        const int r = attempt_finish();
         if (r == 1) return false;
         in_step_ = false;
         if (r < 0) return finish(r);
@@ -1519,7 +1658,15 @@ struct Bdf {
         return false;
     }
 
+    /// One round of the four stages (host harness)
+    PB_HD bool advance() {
+        stage_pre();
+        for (int phase = PH_STATE; phase <= PH_SENS; ++phase) stage_nls(phase);
+        return stage_post();
+    }
+
     PB_HD bool finish(int status) {
+        stage_ = ST_DONE;
         sim_status_ = status;
         if (status != SIM_SUCCESS) llh_ = NAN;  // ReturnData::invalidate (rdata.cpp)
         g.sync();
@@ -1544,7 +1691,9 @@ struct Bdf {
         s[STAT_TRIALS] = trials; s[STAT_QSUM] = qsum; s[14] = 0; s[15] = 0;
     }
 #undef PB_FOR_COLS
-#undef PB_FOR_ALL_COLS
+#undef PB_FOR_RANGE
+#undef PB_FOR_ROWS
+#undef PB_FOR_ROWS0
 #undef PB_FOR_ELEMS
 };
 

@@ -54,43 +54,46 @@ struct KernelArgs {
     double* y_out;                 // layout of my[] (by condition) or null
     double* sigmay_out;
     // --- options ---
+    int sync_period;               // CTA barrier every this many step attempts (>= 1)
+    int stage_sync;                // CTA barrier (instead of a warp barrier) between the stages of an attempt
     SolverOptions opt;
     int num_trials;
     double relaxation_factor;
 };
 
 constexpr double PB_LN10 = 2.302585092994046;
-// register cap: at most 128 registers per thread (64-thread CTAs: 7 per SM, 256-thread CTAs: 2)
-#define PB_MIN_BLOCKS_FOR(T) ((T) <= 64 ? 7 : ((T) <= 128 ? 4 : 2))
+// register cap: shared memory holds ~24 conditions per SM for a Boehm-sized model, so few warps
+// are resident and each may use up to 255 registers
+#define PB_MIN_BLOCKS_FOR(T, G) ((T) <= 32 ? 8 : ((T) <= 64 ? 4 : ((T) <= 128 ? 2 : 1)))
 
 /// One lane group per condition, persistent CTAs, in-kernel work queue.  The group's working
-/// set (GroupShared<M>: Nordsieck history of all columns, Jacobian, LU, ...) lives in dynamic
-/// shared memory for multi-lane groups; a one-lane group (cost-only evaluations) keeps it in
-/// the thread's local memory.
+/// set (GroupShared<M>: Nordsieck history of all columns, Jacobian, inverse Newton matrix, ...)
+/// lives in dynamic shared memory; the integrator's scalars live in registers.
 ///
-/// Every trip of the main loop advances each group by ONE step attempt (Bdf::advance).  With
-/// CTA_SYNC the warps of a CTA meet at a barrier per attempt, so they walk through the same
-/// instructions at about the same time: the kernel is instruction-fetch bound when every warp
-/// is somewhere else in the step loop (profiles/README.md), and an instruction line fetched for
-/// one warp is then reused by the others.
+/// Every trip of the main loop advances each group by ONE step attempt, in four stages
+/// (Bdf::stage_pre / stage_nls(state) / stage_nls(sensitivities) / stage_post) with a warp
+/// barrier between them, and -- with CTA_SYNC -- a CTA barrier per attempt: the warps of the CTA
+/// then walk through the same instructions at about the same time.  The step loop is far
+/// larger than the SM's instruction caches and is streamed from L2 every attempt
+/// (profiles/README.md); a line fetched for one warp is reused by the others only while they
+/// are close behind.
 template <class M, int G, int THREADS, bool CTA_SYNC>
-__global__ void __launch_bounds__(THREADS, PB_MIN_BLOCKS_FOR(THREADS)) simulate_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(THREADS, PB_MIN_BLOCKS_FOR(THREADS, G)) simulate_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char pb_smem_raw[];
     LaneGroup<G> grp;
-    typename std::conditional<G == 1, GroupShared<M>, char>::type priv_storage_;
-    GroupShared<M>* sh;
-    if constexpr (G == 1) sh = &priv_storage_;
-    else sh = reinterpret_cast<GroupShared<M>*>(pb_smem_raw) + (threadIdx.x / G);
+    GroupShared<M>* sh = reinterpret_cast<GroupShared<M>*>(pb_smem_raw) + (threadIdx.x / G);
     Bdf<M, LaneGroup<G>> bdf;
     bdf.sh = sh;
     bdf.opt = a.opt;
     const int lane = grp.lane();
 
     bool active = false, done = false;
+    int since_sync = 0;
     int r = 0, trial = 1;
     size_t cp = 0;
     ConditionIO io;
     for (;;) {
+        __syncwarp();  // the groups of a warp start every step attempt together
         if (!active && !done) {
             int pos = 0;
             if (lane == 0) pos = atomicAdd(a.counter, 1);
@@ -129,7 +132,20 @@ __global__ void __launch_bounds__(THREADS, PB_MIN_BLOCKS_FOR(THREADS)) simulate_
                 active = true;
             }
         }
-        if (active && bdf.advance()) {
+        // one step attempt in four stages; the groups of the warp re-converge between them, so
+        // whatever a group did in one stage (Jacobian setup, a second Newton iteration, an
+        // order change ...) costs the others that stage only
+        if (active) bdf.stage_pre();
+        for (int ph_ = 0; ph_ <= 1; ++ph_) {
+            int ph = ph_;
+            PB_OPAQUE_INT(ph);
+            if (CTA_SYNC && a.stage_sync) __syncthreads();
+            else __syncwarp();
+            if (active) bdf.stage_nls(ph);
+        }
+        if (CTA_SYNC && a.stage_sync) __syncthreads();
+        else __syncwarp();
+        if (active && bdf.stage_post()) {
             const int status = bdf.status();
             if (status != SIM_SUCCESS && trial < a.num_trials) {
                 // ---- A8: runAndLogSimulation retry (multiConditionProblem.cpp:369-465): trial t
@@ -179,7 +195,10 @@ __global__ void __launch_bounds__(THREADS, PB_MIN_BLOCKS_FOR(THREADS)) simulate_
             }
         }
         if constexpr (CTA_SYNC) {
-            if (__syncthreads_and(done ? 1 : 0)) break;
+            if (++since_sync >= a.sync_period) {
+                since_sync = 0;
+                if (__syncthreads_and(done ? 1 : 0)) break;
+            }
         } else {
             if (done) break;
         }
@@ -250,7 +269,7 @@ template <class M, int G, int THREADS, bool CTA_SYNC>
 int launch_one(const KernelArgs& a, int sm_count, cudaStream_t stream, int* grid_used, int* block_used) {
     auto kern = simulate_kernel<M, G, THREADS, CTA_SYNC>;
     const int groups_per_block = THREADS / G;
-    const size_t smem = (G == 1) ? 0 : sizeof(GroupShared<M>) * groups_per_block;
+    const size_t smem = sizeof(GroupShared<M>) * groups_per_block;
     static bool attr_set = false;  // per instantiation
     if (!attr_set && smem > 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -275,29 +294,47 @@ int launch_one(const KernelArgs& a, int sm_count, cudaStream_t stream, int* grid
 
 constexpr int pb_pow2_at_least(int n) { return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32; }
 
-/// Instantiations offered per model: cost-only (G=1: the only column is the state), and for
-/// gradients lane groups of G0 = pow2 >= NP+1 (capped at 32) or a full warp; `variant` selects
-/// the CTA shape: 0 = 256 threads with a barrier per step attempt (default), 1 = 64 threads
-/// free-running (the round-1 baseline, kept for comparison).
+/// Instantiations offered per model: lane groups of GN = pow2 >= NX lanes (one state index per
+/// lane, the default) or GN/2 (two per lane, twice the conditions per warp); `variant` selects
+/// the CTA shape: 0 = two warps with a barrier per step attempt (default), 1 = one free-running
+/// warp per CTA.  Cost-only evaluations use the same kernels with the state column alone.
+/// threads of the "one CTA per SM" shape: as many lane groups as fit the SM's shared memory,
+/// whole warps, at most 1024 threads
+template <class M, int G>
+constexpr int pb_big_cta_threads() {
+    int groups = (int)((227u * 1024u) / sizeof(GroupShared<M>));
+    if (groups > 1024 / G) groups = 1024 / G;
+    const int per_warp = 32 / G;
+    groups -= groups % per_warp;
+    if (groups < per_warp) groups = per_warp;
+    return groups * G;
+}
+
+/// CTA shapes: variant 2 (default) = ONE CTA per SM holding as many lane groups as fit the SM's
+/// shared memory, all warps meeting at a barrier per step attempt (the kernel streams its
+/// instructions from L2 -- profiles/README.md -- and warps that walk through the same code
+/// together share the fetched lines); variant 0 = two-warp CTAs with the same barrier.
+template <class M, int G>
+int launch_shape(const KernelArgs& a, int variant, int sm_count, cudaStream_t stream, int* grid_used, int* block_used) {
+    if (variant == 0) return launch_one<M, G, (G < 32 ? 64 : 128), true>(a, sm_count, stream, grid_used, block_used);
+    return launch_one<M, G, pb_big_cta_threads<M, G>(), true>(a, sm_count, stream, grid_used, block_used);
+}
+
+/// Lane-group widths offered per model: GN = pow2 >= NX lanes (one state index per lane, the
+/// default), GN/2 (two state indices per lane, twice the conditions per warp) and 2*GN (two
+/// column groups).  Cost-only evaluations use the same kernels with the state column alone.
 template <class M>
 int launch_model(const KernelArgs& a, int lanes, int variant, int sm_count, cudaStream_t stream, int* lanes_used,
                  int* grid_used, int* block_used) {
-    constexpr int NCOL = M::NP + 1;
-    constexpr int G0 = pb_pow2_at_least(NCOL);
-    if (!a.want_grad) {
-        if (lanes_used) *lanes_used = 1;
-        return launch_one<M, 1, 64, false>(a, sm_count, stream, grid_used, block_used);
-    }
-    constexpr int GDEF = (NCOL >= 9) ? 32 : G0;
-    const int want = lanes > 0 ? lanes : GDEF;
-    const bool full = (want == 32 || G0 == 32);
-    if (lanes_used) *lanes_used = full ? 32 : G0;
-    if (variant == 1) {
-        if (full) return launch_one<M, 32, 64, false>(a, sm_count, stream, grid_used, block_used);
-        return launch_one<M, G0, 64, false>(a, sm_count, stream, grid_used, block_used);
-    }
-    if (full) return launch_one<M, 32, 256, true>(a, sm_count, stream, grid_used, block_used);
-    return launch_one<M, G0, 256, true>(a, sm_count, stream, grid_used, block_used);
+    constexpr int GN = pb_pow2_at_least(M::NX);
+    constexpr int GH = GN >= 4 ? GN / 2 : GN;
+    constexpr int G2 = GN * 2 <= 32 ? GN * 2 : GN;
+    int G = GN;
+    if (lanes == GH || lanes == G2) G = lanes;
+    if (lanes_used) *lanes_used = G;
+    if (G == GH && GH != GN) return launch_shape<M, GH>(a, variant, sm_count, stream, grid_used, block_used);
+    if (G == G2 && G2 != GN) return launch_shape<M, G2>(a, variant, sm_count, stream, grid_used, block_used);
+    return launch_shape<M, GN>(a, variant, sm_count, stream, grid_used, block_used);
 }
 
 template <class M>
@@ -305,7 +342,7 @@ ModelOps make_ops() {
     ModelOps o;
     o.name = M::NAME;
     o.nx = M::NX; o.np = M::NP; o.nk = M::NK; o.ny = M::NY;
-    o.default_lanes = (M::NP + 1 >= 9) ? 32 : pb_pow2_at_least(M::NP + 1);
+    o.default_lanes = pb_pow2_at_least(M::NX);
     o.flops_xdot = M::FLOPS_XDOT; o.flops_J = M::FLOPS_J; o.flops_dxdotdp = M::FLOPS_DXDOTDP; o.nnzJ = M::NNZ;
     o.launch = &launch_model<M>;
     return o;

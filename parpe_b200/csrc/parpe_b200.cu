@@ -207,9 +207,15 @@ static int enqueue_evaluation(pb200_handle* h, const double* theta, const int* i
     a.stats = h->d_stats.p;
     a.y_out = d_yout;
     a.sigmay_out = d_sout;
+    {
+        static const int sp = std::getenv("PB200_SYNC_PERIOD") ? std::atoi(std::getenv("PB200_SYNC_PERIOD")) : 1;  // experiments
+        a.sync_period = sp > 0 ? sp : 1;
+        static const int ss = std::getenv("PB200_STAGE_SYNC") ? std::atoi(std::getenv("PB200_STAGE_SYNC")) : 0;
+        a.stage_sync = ss;
+    }
     PB_CUDA(cudaEventRecord(h->ev_start, stream));
     if (n > 0) {
-        static const int variant = std::getenv("PB200_KERNEL_VARIANT") ? std::atoi(std::getenv("PB200_KERNEL_VARIANT")) : 0;
+        static const int variant = std::getenv("PB200_KERNEL_VARIANT") ? std::atoi(std::getenv("PB200_KERNEL_VARIANT")) : 2;
         int e = h->ops->launch(a, h->lanes, variant, h->sm_count, stream, &h->last_lanes, &h->last_grid, &h->last_block);
         if (e != 0) return fail(PB200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)e));
     }

