@@ -449,6 +449,8 @@ PB_HD_NOINLINE static double colnorm_shared(GroupShared<M>* sh, const Grp g, int
     }
     const double m = g.max(loc);
     g.sync();  // the scratch may be overwritten by its next user
+    // mean over the NX entries: a power-of-two NX divides exactly, so the multiplication is the division
+    if ((NX & (NX - 1)) == 0) return sqrt(m * (1.0 / (double)NX));
     return sqrt(pb_div(m, (double)NX));
 }
 /// WRMS norm of A over the columns [cmin, cmax]
