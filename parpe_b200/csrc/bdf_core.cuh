@@ -629,7 +629,18 @@ struct Bdf {
     enum { PH_STATE = 0, PH_SENS = 1 };
 
     Grp g;
-    GroupShared<M>* sh;
+    GroupShared<M>* sh;  // host harness: the working set; device: unused, see S()
+    /// The group's working set.  On the device it is re-derived from the dynamic shared memory
+    /// base wherever it is used, so that the compiler always knows the address space (a pointer
+    /// that has been spilled and reloaded is a generic pointer: LD/ST instead of LDS/STS).
+    PB_HD GroupShared<M>* S() const {
+#if defined(__CUDA_ARCH__)
+        extern __shared__ __align__(16) unsigned char pb_smem_raw[];
+        return reinterpret_cast<GroupShared<M>*>(pb_smem_raw) + (threadIdx.x / G);
+#else
+        return sh;
+#endif
+    }
     SolverOptions opt;
     int ns;      // sensitivity columns (columns 1..ns; column 0 is the state)
     int ncol;    // 1 + ns
@@ -678,30 +689,30 @@ struct Bdf {
     /// position of flat element e in the norm scratch (column stride NXS)
 
     // ---------------------------------------------------------------- norms
-    PB_HD double wnorm1(int cmin, int cmax, const double* A) const { return wnorm1_shared<M, Grp>(sh, g, cmin, cmax, A); }
+    PB_HD double wnorm1(int cmin, int cmax, const double* A) const { return wnorm1_shared<M, Grp>(S(), g, cmin, cmax, A); }
     PB_HD double wnorm2(int cmin, int cmax, const double* A, double ca, const double* B, double cb) const {
-        return wnorm2_shared<M, Grp>(sh, g, cmin, cmax, A, ca, B, cb);
+        return wnorm2_shared<M, Grp>(S(), g, cmin, cmax, A, ca, B, cb);
     }
-    PB_HD double colnorm(int cmin, int cmax) const { return colnorm_shared<M, Grp>(sh, g, cmin, cmax); }
+    PB_HD double colnorm(int cmin, int cmax) const { return colnorm_shared<M, Grp>(S(), g, cmin, cmax); }
 
     /// cvEwtSetSS / cvSensEwtSetSS (cvodes.c:9118-9129, 9263-9279)
     PB_HD bool ewt_set() {
         bool ok = true;
         PB_FOR_ELEMS(e) {
-            const double w = opt.rtol * fabs(sh->zn[0][e]) + opt.atol;
+            const double w = opt.rtol * fabs(S()->zn[0][e]) + opt.atol;
             ok = ok && (w > 0.0);
-            sh->ewt[e] = 1.0 / w;
+            S()->ewt[e] = 1.0 / w;
         }
         return !g.any(!ok);
     }
 
-    /// J(t, ysh) and d xdot / d p -> sh->Jcur, sh->dfdp by the first lane (Model_ODE::fsxdot at
+    /// J(t, ysh) and d xdot / d p -> S()->Jcur, S()->dfdp by the first lane (Model_ODE::fsxdot at
     /// ip == 0, deps/AMICI/src/model_ode.cpp:492-498)
     PB_HD void refresh_Jcur(double t) {
         g.sync();
         if (g.lane() == 0) {
-            eval_jac_shared<M>(sh->Jcur, t, sh->ysh, sh);
-            eval_dfdp_shared<M>(sh, t, sh->ysh);
+            eval_jac_shared<M>(S()->Jcur, t, S()->ysh, S());
+            eval_dfdp_shared<M>(S(), t, S()->ysh);
         }
         g.sync();
     }
@@ -709,7 +720,7 @@ struct Bdf {
     // ---------------------------------------------------------------- right-hand sides
     /// THE right-hand-side evaluation.  For the columns of `phase`:  v = zn[0] + acor;
     /// F = f(t, v)  (state: xdot; sensitivities: dxdotdp(ip) + Jcur*v, Model_ODE::fsxdot
-    /// model_ode.cpp:486-515, with sh->ysh / sh->Jcur / sh->dfdp prepared by the caller);
+    /// model_ode.cpp:486-515, with S()->ysh / S()->Jcur / S()->dfdp prepared by the caller);
     /// b = raw ? F : rl1*zn[1] + acor - gamma*F  (cvNlsResidual cvodes_nls.c:344-371;
     /// cvNlsResidualSensStg cvodes_nls_stg.c:377-421).  Row-parallel: every lane produces its
     /// rows of every column.  Returns 0, RHSFUNC_RECVR or SRHSFUNC_RECVR (non-finite result).
@@ -717,30 +728,30 @@ struct Bdf {
         bool bad = false;
         g.sync();  // element-wise writers of zn / acor may have been other lanes
         if (phase == PH_STATE) {
-            PB_FOR_ROWS0(r, i) sh->yj[i] = sh->zn[0][i] + sh->acor[i];
+            PB_FOR_ROWS0(r, i) S()->yj[i] = S()->zn[0][i] + S()->acor[i];
             g.sync();
             int ok = 1;
-            if (g.lane() == 0) ok = eval_xdot_shared<M>(sh, t) ? 1 : 0;
+            if (g.lane() == 0) ok = eval_xdot_shared<M>(S(), t) ? 1 : 0;
             g.sync();
             bad = g.bcast0(ok) == 0;
             PB_FOR_ROWS0(r, i) {
-                const double F = sh->fout[i];
-                sh->b[i] = raw ? F : (rl1 * sh->zn[1][i] + sh->acor[i]) - gamma * F;
+                const double F = S()->fout[i];
+                S()->b[i] = raw ? F : (rl1 * S()->zn[1][i] + S()->acor[i]) - gamma * F;
             }
             nfe++;
         } else {
             // corrected sensitivities of all columns -> scratch (read by every lane below)
-            PB_FOR_RANGE(e, NX, NX * ncol) sh->scr[e] = sh->zn[0][e] + sh->acor[e];
+            PB_FOR_RANGE(e, NX, NX * ncol) S()->scr[e] = S()->zn[0][e] + S()->acor[e];
             double jrow[RPL][NX];
             PB_FOR_ROWS(r, i) {
                 PB_UNROLL
-                for (int j = 0; j < NX; ++j) jrow[r][j] = sh->Jcur[i + j * NX];
+                for (int j = 0; j < NX; ++j) jrow[r][j] = S()->Jcur[i + j * NX];
             }
             g.sync();
             PB_UNROLL_COLS
             for (int c = 1 + col_group(); c <= ns; c += CG) {
-                const double* dcol = sh->dfdp + sh->plist[c - 1] * NX;
-                const double* sc = sh->scr + c * NX;
+                const double* dcol = S()->dfdp + S()->plist[c - 1] * NX;
+                const double* sc = S()->scr + c * NX;
                 double sv[NX];
                 PB_UNROLL
                 for (int j = 0; j < NX; ++j) sv[j] = sc[j];
@@ -750,7 +761,7 @@ struct Bdf {
                     for (int j = 0; j < NX; ++j) F += jrow[r][j] * sv[j];
                     if (!isfinite(F)) bad = true;
                     const int e = c * NX + i;
-                    sh->b[e] = raw ? F : (rl1 * sh->zn[1][e] + sh->acor[e]) - gamma * F;
+                    S()->b[e] = raw ? F : (rl1 * S()->zn[1][e] + S()->acor[e]) - gamma * F;
                 }
             }
             nfSe += ns;
@@ -760,10 +771,10 @@ struct Bdf {
         return 0;
     }
 
-    /// sh->ysh = zn[0] + acor of the state column (the corrected state y_n)
+    /// S()->ysh = zn[0] + acor of the state column (the corrected state y_n)
     PB_HD void publish_state() {
         g.sync();
-        PB_FOR_ROWS0(r, i) sh->ysh[i] = sh->zn[0][i] + sh->acor[i];
+        PB_FOR_ROWS0(r, i) S()->ysh[i] = S()->zn[0][i] + S()->acor[i];
         g.sync();
     }
 
@@ -788,7 +799,7 @@ struct Bdf {
 
     // ---------------------------------------------------------------- linear algebra
     /// cvLsSetup + cvLsLinSys (cvodes_ls.c:1611-1708,1386-1470) + the inversion; the state the
-    /// Jacobian is evaluated at is sh->yj.
+    /// Jacobian is evaluated at is S()->yj.
     PB_HD int lsetup() {
         const double dgamma = fabs(pb_div(gamma, gammap) - 1.0);
         const bool jbad = (nst == 0) || (nst >= nstlj + cv::MSBJ) ||
@@ -797,15 +808,15 @@ struct Bdf {
         int ret = 0;
         g.sync();
         if (jbad) {
-            if (g.lane() == 0) eval_jac_shared<M>(sh->Jsaved, tn, sh->yj, sh);
+            if (g.lane() == 0) eval_jac_shared<M>(S()->Jsaved, tn, S()->yj, S());
             g.sync();
             // AMICI's fJ callback returns checkFinite(J): recoverable if not finite
             bool bad = false;
             for (int e = g.lane(); e < NX * NX; e += G)
-                if (!isfinite(sh->Jsaved[e])) bad = true;
+                if (!isfinite(S()->Jsaved[e])) bad = true;
             if (g.any(bad)) ret = 1;
         }
-        if (ret == 0) ret = invert_newton_matrix<M, Grp>(sh, g, gamma);
+        if (ret == 0) ret = invert_newton_matrix<M, Grp>(S(), g, gamma);
         if (jbad) { nje++; nstlj = nst; }
         jcur = jbad;
         nsetups++;
@@ -819,12 +830,12 @@ struct Bdf {
         double arow[RPL][NX];
         PB_FOR_ROWS(r, i) {
             PB_UNROLL
-            for (int j = 0; j < NX; ++j) arow[r][j] = sh->Ainv[i + j * NX];
+            for (int j = 0; j < NX; ++j) arow[r][j] = S()->Ainv[i + j * NX];
         }
         const double nsc = (gamrat != 1.0) ? pb_div(-2.0, 1.0 + gamrat) : -1.0;
         PB_UNROLL_COLS
         for (int c = cmin + col_group(); c <= cmax; c += CG) {
-            const double* bc = sh->b + c * NX;
+            const double* bc = S()->b + c * NX;
             double bv[NX];
             PB_UNROLL
             for (int j = 0; j < NX; ++j) bv[j] = bc[j];
@@ -834,9 +845,9 @@ struct Bdf {
                 for (int j = 0; j < NX; ++j) acc += arow[r][j] * bv[j];
                 const double x = nsc * acc;
                 const int e = c * NX + i;
-                sh->acor[e] += x;
-                const double prod = x * sh->ewt[e];
-                sh->scr[c * NXS + i] = prod * prod;
+                S()->acor[e] += x;
+                const double prod = x * S()->ewt[e];
+                S()->scr[c * NXS + i] = prod * prod;
             }
         }
         return colnorm(cmin, cmax);
@@ -856,7 +867,7 @@ struct Bdf {
             PB_UNROLL
             for (int j = 2; j < cv::Q_MAX; ++j) {
                 if (j < q) {
-                    hsum += sh->tau[j - 1];
+                    hsum += S()->tau[j - 1];
                     xi_inv = pb_div(h, hsum);
                     alpha0 -= 1.0 / (double)j;
                     PB_UNROLL
@@ -865,7 +876,7 @@ struct Bdf {
             }
             alpha0 -= pb_inv_int(q);
             xistar_inv = -l[1] - alpha0;
-            hsum += sh->tau[q - 1];
+            hsum += S()->tau[q - 1];
             xi_inv = pb_div(h, hsum);
             alpha0_hat = -l[1] - xi_inv;
             PB_UNROLL
@@ -890,7 +901,7 @@ struct Bdf {
             } else {
                 tq1 = 1.0;
             }
-            hsum += sh->tau[q];
+            hsum += S()->tau[q];
             xi_inv = pb_div(h, hsum);
             const double A5 = alpha0 - pb_inv_int(q + 1);
             const double A6 = alpha0_hat - xi_inv;
@@ -912,7 +923,7 @@ struct Bdf {
         PB_FOR_ELEMS(e) {
             double z[cv::L_MAX];
             PB_UNROLL
-            for (int j = 0; j < cv::L_MAX; ++j) z[j] = (j <= q) ? sh->zn[j][e] : 0.0;
+            for (int j = 0; j < cv::L_MAX; ++j) z[j] = (j <= q) ? S()->zn[j][e] : 0.0;
             PB_UNROLL
             for (int k = 1; k <= cv::Q_MAX; ++k) {
                 PB_UNROLL
@@ -922,7 +933,7 @@ struct Bdf {
             }
             PB_UNROLL
             for (int j = 0; j < cv::Q_MAX; ++j)
-                if (j < q) sh->zn[j][e] = z[j];
+                if (j < q) S()->zn[j][e] = z[j];
         }
     }
     /// cvRescale (cvodes.c:6425-6495)
@@ -930,7 +941,7 @@ struct Bdf {
         PB_FOR_ELEMS(e) {
             double factor = eta;
             for (int j = 1; j <= q; ++j) {
-                sh->zn[j][e] *= factor;
+                S()->zn[j][e] *= factor;
                 factor *= eta;
             }
         }
@@ -939,7 +950,7 @@ struct Bdf {
         nscon = 0;
     }
     /// cvAdjustOrder (out of line, one copy)
-    PB_HD void adjust_order(int deltaq) { adjust_order_shared<M, Grp>(sh, g, ncol, q, L, hscale, deltaq); }
+    PB_HD void adjust_order(int deltaq) { adjust_order_shared<M, Grp>(S(), g, ncol, q, L, hscale, deltaq); }
 
     // ---------------------------------------------------------------- nonlinear solve
     /// cvNls / cvStgrNls + SUNNonlinSolSolve_Newton + cvNlsConvTest{,SensStg} for the columns of
@@ -955,7 +966,7 @@ struct Bdf {
             setup_pending = (nflag == cv::PREV_CONV_FAIL) || (nflag == cv::PREV_ERR_FAIL) || (nst == 0) ||
                             (nst >= nstlp + cv::MSBP) || (fabs(gamrat - 1.0) > cv::DGMAX_LSETUP);
         }
-        PB_FOR_RANGE(e, cmin * NX, (cmax + 1) * NX) sh->acor[e] = 0.0;
+        PB_FOR_RANGE(e, cmin * NX, (cmax + 1) * NX) S()->acor[e] = 0.0;
         bool jbad = false;
         bool top = true;  // residual at the top of a solve attempt: failures there are final
         int m_it = 0;
@@ -966,8 +977,8 @@ struct Bdf {
                 if (jbad) convfail = cv::FAIL_BAD_J;
                 if (phase == PH_SENS) {  // Jacobian at the converged state (cv_y), cvodes_nls_stg.c:252
                     g.sync();
-                    PB_FOR_ROWS0(r, i) sh->yj[i] = sh->ysh[i];
-                }  // state phase: rhs() has just put zn[0]+acor into sh->yj
+                    PB_FOR_ROWS0(r, i) S()->yj[i] = S()->ysh[i];
+                }  // state phase: rhs() has just put zn[0]+acor into S()->yj
                 const int lr = lsetup();
                 setup_pending = false;
                 if (phase == PH_STATE) jcurNLS = jcur;
@@ -990,7 +1001,7 @@ struct Bdf {
                 else crateS = cr;
                 const double dcon = pb_div(del * fmin(1.0, cr), tq4);
                 if (dcon <= 1.0) {
-                    const double an = (m_it == 0) ? del : wnorm1(cmin, cmax, sh->acor);
+                    const double an = (m_it == 0) ? del : wnorm1(cmin, cmax, S()->acor);
                     if (phase == PH_STATE) {
                         acnrm = an;
                         jcurNLS = false;
@@ -1017,7 +1028,7 @@ struct Bdf {
                 top = true;
                 m_it = 0;
                 g.sync();
-                PB_FOR_RANGE(e, cmin * NX, (cmax + 1) * NX) sh->acor[e] = 0.0;
+                PB_FOR_RANGE(e, cmin * NX, (cmax + 1) * NX) S()->acor[e] = 0.0;
                 continue;
             }
             return ret;
@@ -1032,18 +1043,18 @@ struct Bdf {
         qsum += q;
         g.sync();
         if (g.lane() == 0) {
-            for (int i = q; i >= 2; --i) sh->tau[i] = sh->tau[i - 1];
-            if ((q == 1) && (nst > 1)) sh->tau[2] = sh->tau[1];
-            sh->tau[1] = h;
+            for (int i = q; i >= 2; --i) S()->tau[i] = S()->tau[i - 1];
+            if ((q == 1) && (nst > 1)) S()->tau[2] = S()->tau[1];
+            S()->tau[1] = h;
         }
         qwait--;
         const bool save = (qwait == 1) && (q != cv::Q_MAX);
         PB_FOR_ELEMS(e) {
-            const double a = sh->acor[e];
+            const double a = S()->acor[e];
             PB_UNROLL
             for (int j = 0; j < cv::L_MAX; ++j)
-                if (j <= q) sh->zn[j][e] += l[j] * a;
-            if (save) sh->zn[cv::Q_MAX][e] = a;
+                if (j <= q) S()->zn[j][e] += l[j] * a;
+            if (save) S()->zn[cv::Q_MAX][e] = a;
         }
         g.sync();
         if (save) saved_tq5 = tq5;
@@ -1068,18 +1079,18 @@ struct Bdf {
             etaqm1 = 0.0;
             if (q > 1) {
                 const int qq = q;
-                double ddn = wnorm1(0, ecmax, sh->zn[qq]);
+                double ddn = wnorm1(0, ecmax, S()->zn[qq]);
                 ddn = ddn * tq1;
                 etaqm1 = pb_rcp(pb_pow(cv::BIAS1 * ddn, pb_inv_int(q)) + cv::ADDON);
             }
             etaqp1 = 0.0;
             if (q != cv::Q_MAX) {
                 if (saved_tq5 != 0.0) {
-                    const double hr = pb_div(h, sh->tau[2]);
+                    const double hr = pb_div(h, S()->tau[2]);
                     double hp = 1.0;
                     for (int i = 0; i < L; ++i) hp *= hr;  // SUNRpowerI
                     const double cquot = pb_div(tq5, saved_tq5) * hp;
-                    double dup = wnorm2(0, ecmax, sh->zn[cv::Q_MAX], -cquot, sh->acor, 1.0);
+                    double dup = wnorm2(0, ecmax, S()->zn[cv::Q_MAX], -cquot, S()->acor, 1.0);
                     dup = dup * tq3;
                     etaqp1 = pb_rcp(pb_pow(cv::BIAS3 * dup, pb_inv_int(L + 1)) + cv::ADDON);
                 }
@@ -1100,7 +1111,7 @@ struct Bdf {
                 qprime = q + 1;
                 // store Delta_n in zn[qmax] for the order increase (state always; sensitivities
                 // only if they take part in the error test, cvodes.c:7973-7987)
-                PB_FOR_RANGE(e, 0, (ecmax + 1) * NX) sh->zn[cv::Q_MAX][e] = sh->acor[e];
+                PB_FOR_RANGE(e, 0, (ecmax + 1) * NX) S()->zn[cv::Q_MAX][e] = S()->acor[e];
                 g.sync();
             }
         }
@@ -1122,7 +1133,7 @@ struct Bdf {
             double sqv[2];
             for (int w = 0; w < 2; ++w) {
                 const int jj = q - w;
-                sqv[w] = wnorm1(0, 0, sh->zn[jj]);
+                sqv[w] = wnorm1(0, 0, S()->zn[jj]);
             }
             int factorial = 1;
             for (int i = 1; i <= q - 1; ++i) factorial *= i;
@@ -1132,16 +1143,16 @@ struct Bdf {
             g.sync();
             if (g.lane() == 0) {
                 for (int k = 1; k <= 3; ++k)
-                    for (int i = 5; i >= 2; --i) sh->ssdat[i][k] = sh->ssdat[i - 1][k];
-                sh->ssdat[1][1] = sqm2 * sqm2;
-                sh->ssdat[1][2] = sqm1 * sqm1;
-                sh->ssdat[1][3] = sq * sq;
+                    for (int i = 5; i >= 2; --i) S()->ssdat[i][k] = S()->ssdat[i - 1][k];
+                S()->ssdat[1][1] = sqm2 * sqm2;
+                S()->ssdat[1][2] = sqm1 * sqm1;
+                S()->ssdat[1][3] = sq * sq;
             }
             g.sync();
         }
         if (qprime >= q) {
             if ((q >= 3) && (nscon >= q + 5)) {
-                const int ldflag = sldet_shared<M, Grp>(sh, g, q);
+                const int ldflag = sldet_shared<M, Grp>(S(), g, q);
                 if (ldflag > 3) {
                     qprime = q - 1;
                     eta = etaqm1;
@@ -1158,11 +1169,11 @@ struct Bdf {
     /// zn[1] = h * f(tn, zn[0]) for the state and (if any) the sensitivities; acor is scratch
     PB_HD int reload_zn1() {
         g.sync();
-        PB_FOR_ELEMS(e) sh->acor[e] = 0.0;
+        PB_FOR_ELEMS(e) S()->acor[e] = 0.0;
         g.sync();
         const int r = rhs_all_raw(tn, sensi);
         if (r) return r;
-        PB_FOR_ELEMS(e) sh->zn[1][e] = h * sh->b[e];
+        PB_FOR_ELEMS(e) S()->zn[1][e] = h * S()->b[e];
         g.sync();
         return 0;
     }
@@ -1235,9 +1246,9 @@ struct Bdf {
             // f at the converged y (cvodes.c:5947-5955); AMICI's sensitivity RHS does not
             // use it -- kept for the recoverable-failure semantics
             int bad = 0;
-            PB_FOR_ROWS0(r, i) sh->yj[i] = sh->ysh[i];
+            PB_FOR_ROWS0(r, i) S()->yj[i] = S()->ysh[i];
             g.sync();
-            if (g.lane() == 0) bad = eval_xdot_shared<M>(sh, tn) ? 0 : 1;
+            if (g.lane() == 0) bad = eval_xdot_shared<M>(S(), tn) ? 0 : 1;
             nfe++;
             if (g.bcast0(bad)) { fail_ = 5; return; }
             refresh_Jcur(tn);
@@ -1325,8 +1336,8 @@ struct Bdf {
         // cvUpperBoundH0
         double hub_inv = 0.0;
         PB_FOR_RANGE(e, 0, (ecmax + 1) * NX) {
-            const double den = cv::HUB_FACTOR * fabs(sh->zn[0][e]) + pb_rcp(sh->ewt[e]);
-            const double v = pb_div(fabs(sh->zn[1][e]), den);
+            const double den = cv::HUB_FACTOR * fabs(S()->zn[0][e]) + pb_rcp(S()->ewt[e]);
+            const double v = pb_div(fabs(S()->zn[1][e]), den);
             if (v > hub_inv) hub_inv = v;
         }
         hub_inv = g.max(hub_inv);
@@ -1346,18 +1357,18 @@ struct Bdf {
                 // cvYddNorm: f at (tn + hg, zn0 + hg*zn1), difference quotient, WRMS norm
                 const double hgs = hg * sign;
                 g.sync();
-                PB_FOR_ELEMS(e) sh->acor[e] = hgs * sh->zn[1][e];
+                PB_FOR_ELEMS(e) S()->acor[e] = hgs * S()->zn[1][e];
                 retval = rhs_all_raw(tn + hgs, withS);
                 if (retval == 0) {
                     const double hinv = pb_rcp(hgs);
-                    yddnrm = wnorm2(0, ecmax, sh->b, hinv, sh->zn[1], -hinv);
+                    yddnrm = wnorm2(0, ecmax, S()->b, hinv, S()->zn[1], -hinv);
                     hgOK = true;
                     break;
                 }
                 hg *= 0.2;
             }
             g.sync();
-            PB_FOR_ELEMS(e) sh->acor[e] = 0.0;
+            PB_FOR_ELEMS(e) S()->acor[e] = 0.0;
             g.sync();
             if (!hgOK) {
                 if (count1 <= 2) return retval == cv::RHSFUNC_RECVR ? SIM_REPTD_RHSFUNC_ERR : SIM_REPTD_SRHSFUNC_ERR;
@@ -1403,7 +1414,7 @@ struct Bdf {
             if ((tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
             hscale = h;
             hprime = h;
-            PB_FOR_ELEMS(e) sh->zn[1][e] *= h;
+            PB_FOR_ELEMS(e) S()->zn[1][e] *= h;
         } else {
             const double troundoff = cv::FUZZ_FACTOR * cv::UROUND * (fabs(tn) + fabs(h));
             if (fabs(tn - tstop) <= troundoff) {
@@ -1428,11 +1439,11 @@ struct Bdf {
     PB_HD bool data_point(double t, const double* my, const double* sd, double& llh, double* y_out,
                           double* sigmay_out) {
         g.sync();
-        PB_FOR_ROWS0(r, i) sh->ysh[i] = sh->zn[0][i];
+        PB_FOR_ROWS0(r, i) S()->ysh[i] = S()->zn[0][i];
         g.sync();
         double y[NY], sig[NY];
-        M::y(y, t, sh->ysh, sh->p, sh->k);
-        M::sigmay(sig, t, sh->p, sh->k);
+        M::y(y, t, S()->ysh, S()->p, S()->k);
+        M::sigmay(sig, t, S()->p, S()->k);
         bool from_data[NY];
         bool ok = true;
         PB_UNROLL
@@ -1480,7 +1491,7 @@ struct Bdf {
             double dydx[NY * NX];
             PB_UNROLL
             for (int i = 0; i < NY * NX; ++i) dydx[i] = 0.0;
-            M::dydx(dydx, t, sh->ysh, sh->p, sh->k);
+            M::dydx(dydx, t, S()->ysh, S()->p, S()->k);
             PB_UNROLL
             for (int ix = 0; ix < NX; ++ix) {
                 double a = 0.0;
@@ -1493,9 +1504,9 @@ struct Bdf {
             double dydp[NY], dsdp[NY];
             PB_UNROLL
             for (int iy = 0; iy < NY; ++iy) { dydp[iy] = 0.0; dsdp[iy] = 0.0; }
-            const int ip = sh->plist[c - 1];
-            M::dydp(dydp, t, sh->ysh, sh->p, sh->k, ip);
-            M::dsigmaydp(dsdp, t, sh->p, sh->k, ip);
+            const int ip = S()->plist[c - 1];
+            M::dydp(dydp, t, S()->ysh, S()->p, S()->k, ip);
+            M::dsigmaydp(dsdp, t, S()->p, S()->k, ip);
             double dJydp = 0.0;
             PB_UNROLL
             for (int iy = 0; iy < NY; ++iy) dJydp += dJydy[iy] * dydp[iy];
@@ -1503,8 +1514,8 @@ struct Bdf {
             for (int iy = 0; iy < NY; ++iy) dJydp += dJyds[iy] * dsdp[iy];
             double a = dJydp;
             PB_UNROLL
-            for (int ix = 0; ix < NX; ++ix) a += dJydx[ix] * sh->zn[0][c * NX + ix];
-            sh->sllh[c] -= a;
+            for (int ix = 0; ix < NX; ++ix) a += dJydx[ix] * S()->zn[0][c * NX + ix];
+            S()->sllh[c] -= a;
         }
         return true;
     }
@@ -1512,7 +1523,7 @@ struct Bdf {
     // ---------------------------------------------------------------- one simulation
     /// Start one simulation (ForwardProblem::workForwardProblem, forwardproblem.cpp:67-203) at
     /// the given tolerances: x0/sx0 (Model::initialize, model.cpp:249-275), CVodeInit
-    /// (cvodes.c:677-830).  sh->p / sh->k / sh->plist must be set.
+    /// (cvodes.c:677-830).  S()->p / S()->k / S()->plist must be set.
     PB_HD void begin(const ConditionIO& io, double rtol, double atol) {
         io_ = io;
         opt.rtol = rtol;
@@ -1525,18 +1536,18 @@ struct Bdf {
             double v[NX];
             PB_UNROLL
             for (int i = 0; i < NX; ++i) v[i] = 0.0;
-            if (c == 0) M::x0(v, opt.t0, sh->p, sh->k);
-            else M::sx0(v, opt.t0, sh->p, sh->k, sh->plist[c - 1]);
+            if (c == 0) M::x0(v, opt.t0, S()->p, S()->k);
+            else M::sx0(v, opt.t0, S()->p, S()->k, S()->plist[c - 1]);
             PB_UNROLL
             for (int i = 0; i < NX; ++i) {
                 const int e = c * NX + i;
-                sh->zn[0][e] = v[i];
-                for (int j = 1; j < cv::L_MAX; ++j) sh->zn[j][e] = 0.0;
-                sh->acor[e] = 0.0;
-                sh->ewt[e] = 1.0;
-                sh->b[e] = 0.0;
+                S()->zn[0][e] = v[i];
+                for (int j = 1; j < cv::L_MAX; ++j) S()->zn[j][e] = 0.0;
+                S()->acor[e] = 0.0;
+                S()->ewt[e] = 1.0;
+                S()->b[e] = 0.0;
             }
-            sh->sllh[c] = 0.0;
+            S()->sllh[c] = 0.0;
         }
         PB_UNROLL
         for (int j = 0; j < cv::L_MAX; ++j) l[j] = 0.0;
@@ -1554,14 +1565,14 @@ struct Bdf {
         tstopset = false; tstop = 0.0;
         nfe = nsetups = nje = nni = nniS = nfSe = netf = netfS = ncfn = ncfnS = nor = qsum = 0;
         for (int e = g.lane(); e < NX * NX; e += G) {
-            sh->Jsaved[e] = 0.0;
-            sh->Jcur[e] = 0.0;
+            S()->Jsaved[e] = 0.0;
+            S()->Jcur[e] = 0.0;
         }
-        for (int e = g.lane(); e < NX * NP; e += G) sh->dfdp[e] = 0.0;
+        for (int e = g.lane(); e < NX * NP; e += G) S()->dfdp[e] = 0.0;
         if (g.lane() == 0) {
-            for (int i = 0; i <= cv::L_MAX; ++i) sh->tau[i] = 0.0;
+            for (int i = 0; i <= cv::L_MAX; ++i) S()->tau[i] = 0.0;
             for (int i = 0; i < 6; ++i)
-                for (int k = 0; k < 4; ++k) sh->ssdat[i][k] = 0.0;
+                for (int k = 0; k < 4; ++k) S()->ssdat[i][k] = 0.0;
         }
         g.sync();
         llh_ = 0.0;
@@ -1617,7 +1628,7 @@ struct Bdf {
                 if (!ewt_set()) { finish(SIM_ILL_INPUT); return; }
             }
             if (nstloc_ >= mxstep_) { finish(SIM_TOO_MUCH_WORK); return; }
-            const double nrm = wnorm1(0, errtest_cmax(), sh->zn[0]);
+            const double nrm = wnorm1(0, errtest_cmax(), S()->zn[0]);
             if (cv::UROUND * nrm > 1.0) { finish(SIM_TOO_MUCH_ACC); return; }
             step_begin();
             in_step_ = true;
@@ -1635,7 +1646,7 @@ struct Bdf {
 
     /// stage_post: step completion or failure handling, then the tstop tests after a completed
     /// step (cvodes.c:3504-3605).  Returns true when the simulation has ended; status() / llh()
-    /// then hold the result and d llh / d p (w.r.t. the unscaled parameter) is in sh->sllh[1..ns].
+    /// then hold the result and d llh / d p (w.r.t. the unscaled parameter) is in S()->sllh[1..ns].
     PB_HD bool stage_post() {
         if (stage_ == ST_DONE) return true;
         if (stage_ != ST_NLS) return false;

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(THREADS, PB_MIN_BLOCKS_FOR(THREADS, G)) simula
     extern __shared__ __align__(16) unsigned char pb_smem_raw[];
     LaneGroup<G> grp;
     GroupShared<M>* sh = reinterpret_cast<GroupShared<M>*>(pb_smem_raw) + (threadIdx.x / G);
+    PB_ASSUME_SHARED(sh);
     Bdf<M, LaneGroup<G>> bdf;
     bdf.sh = sh;
     bdf.opt = a.opt;
