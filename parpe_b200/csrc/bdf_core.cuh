@@ -883,10 +883,15 @@ struct Bdf {
             for (int i = cv::Q_MAX; i >= 1; --i)
                 if (i <= q) l[i] += l[i - 1] * xistar_inv;
         }
+        // l[q] with compile-time indices only (written out: inside `if (i == q)` of a loop the
+        // optimiser rewrites l[i] as l[q], and one dynamic index puts the whole integrator object
+        // into local memory)
         double lq = l[1];
-        PB_UNROLL
-        for (int i = 2; i <= cv::Q_MAX; ++i)
-            if (i == q) lq = l[i];
+        if (q == 2) lq = l[2];
+        if (q == 3) lq = l[3];
+        if (q == 4) lq = l[4];
+        if (q == 5) lq = l[5];
+        static_assert(cv::Q_MAX == 5, "l[q] selection is written out for q <= 5");
         const double A1 = 1.0 - alpha0_hat + alpha0;
         const double A2 = 1.0 + q * A1;
         tq2 = fabs(pb_div(A1, alpha0 * A2));
