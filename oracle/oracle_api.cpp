@@ -15,6 +15,10 @@
 #include "models/model_fujita.h"
 #include "models/model_steadystate.h"
 #include "models/model_steadystate_scaled.h"
+#include "net_model.hpp"
+#include "../parpe_b200/csrc/models/net_chen.h"
+#include "../parpe_b200/csrc/models/net_froehlich.h"
+#include "../parpe_b200/csrc/models/net_net32.h"
 
 #ifdef PB200_ORACLE_WITH_VENDORED
 // the reference's own pre-generated model (deps/AMICI/models/model_steadystate),
@@ -31,6 +35,9 @@ std::unique_ptr<amici::Model> makeModel(const std::string& name) {
     if (name == "steadystate_scaled") return create_steadystate_scaled();
     if (name == "boehm") return create_boehm();
     if (name == "fujita") return create_fujita();
+    if (name == "net32") return std::make_unique<NetworkModel>(pb200::nets::net32::tables());
+    if (name == "chen") return std::make_unique<NetworkModel>(pb200::nets::chen::tables());
+    if (name == "froehlich") return std::make_unique<NetworkModel>(pb200::nets::froehlich::tables());
 #ifdef PB200_ORACLE_WITH_VENDORED
     if (name == "steadystate_vendored")
         return std::make_unique<amici::model_model_steadystate::Model_model_steadystate>();

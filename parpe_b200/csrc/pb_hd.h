@@ -38,6 +38,9 @@
 #define PB_UNROLL_COLS
 #endif
 
+// finite test that does not depend on which of <math.h> / <cmath> the translation unit saw first
+#define PB_FINITE(v) (((v) - (v)) == 0.0)
+
 // Out-of-line device functions receive the group's working set through a generic pointer; tell
 // the compiler it is shared memory so that it emits LDS/STS (the kernels always place it there).
 #if defined(__CUDA_ARCH__)

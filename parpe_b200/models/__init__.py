@@ -12,8 +12,15 @@ REGISTRY = {
     "steadystate_scaled": 1,
     "boehm": 2,
     "fujita": 3,
+    # table-driven mass-action networks (large-model path, one CTA per condition)
+    "net32": 4,
+    "chen": 5,
+    "froehlich": 6,
 }
 
 
 def get_spec(name):
+    from .netmodels import NET_MODELS, spec as net_spec
+    if name in NET_MODELS:
+        return net_spec(name)
     return importlib.import_module("parpe_b200.models." + name).spec()
