@@ -1,0 +1,1274 @@
+// bdf_team.cuh -- the large-model integrator: stiff BDF with Newton iteration and staggered
+// forward sensitivities, ONE TEAM (thread block) per experimental condition.
+//
+// Same reference rows as bdf_core.cuh (ForwardProblem +
+// CVODES cvStep/cvNls/cvStgrNls/cvDoErrorTest/... + dense linear algebra + likelihood; the
+// file:line citations are on the corresponding functions of bdf_core.cuh and are not repeated
+// at every function here), for models whose working set does not fit an SM: nx in the hundreds
+// to low thousands (BASELINE configs 3-4, "Chen-shape" nx = 500, "Froehlich-shape" nx = 1200).
+// CVODES' heuristics and constants are kept; the execution model is different from both CVODES
+// and the small-model kernel:
+//
+//   * the Nordsieck history zn[0..5], accumulated correction, error weights and right-hand
+//     side of ALL 1+nplist columns (element (i, c) at [c*nx + i]) live in the team's slice of an
+//     HBM workspace; every vector operation is a coalesced team-wide sweep over the flat index;
+//   * model functions are evaluated by the whole team from tables (net_model.cuh): one thread
+//     per reaction / species / Jacobian entry; J and the sensitivity right-hand sides
+//     (dxdotdp + J*s for all columns at once) use the sparse pattern;
+//   * the Newton matrix I - gamma*J is dense and INVERTED at every linear-solver setup by a
+//     blocked in-place Gauss-Jordan elimination with partial pivoting: the n x NB panel is
+//     factored in shared memory, the rest of the matrix gets one rank-NB update per block step
+//     (each thread owns a matrix row, the panel row in registers, the pivot rows broadcast from
+//     shared memory).  Every Newton iteration -- of the state and of all nplist sensitivity
+//     columns together, the staggered corrector's "same matrix, nplist right-hand sides" -- is
+//     then ONE GEMM  delta = -(I - gamma J)^-1 * B  (rows owned by threads, streamed from
+//     HBM/L2 once per 26 columns, B tile broadcast from shared memory);
+//   * the integrator's scalars (step size, order, BDF coefficients, counters) are computed
+//     redundantly and identically by every thread; reductions are fixed-order.
+//
+// The same source compiles for the host with HostTeam (one thread); that instantiation exists
+// only in tests/host_harness to diff the algorithm against the CVODES oracle without a GPU.
+#ifndef PB200_BDF_TEAM_CUH
+#define PB200_BDF_TEAM_CUH
+
+#include "bdf_core.cuh"
+#include "net_model.cuh"
+#include "team.cuh"
+
+namespace pb200 {
+
+constexpr int TEAM_NB_MAX = 32;     // panel width of the blocked inversion
+constexpr int TEAM_CW = 64;         // columns per chunk of the rank-NB update
+constexpr int TEAM_RBUF = TEAM_NB_MAX * TEAM_CW;  // doubles in the broadcast tile
+constexpr int TEAM_TN = 26;         // right-hand-side columns per pass of the solve GEMM
+constexpr int TEAM_MAXNY = 16;
+
+/// Per-team working set: pointers into the team's slice of the HBM workspace plus the staging
+/// buffers (shared memory on the device).
+struct TeamWork {
+    double* zn[cv::L_MAX];
+    double *acor, *ewt, *b, *scr;
+    double *dfdp, *A, *Jsaved, *Jcur, *ysh, *yj, *fout, *vb, *v, *p, *k, *sllh;
+    int *plist, *perm;
+    double* panel;  // nx * NB
+    double* rbuf;   // TEAM_RBUF
+    double* rowk;   // TEAM_NB_MAX
+    int* piv;       // TEAM_NB_MAX
+    int NB;
+
+    /// doubles of HBM workspace one team needs
+    static size_t hbm_doubles(const NetTables& T) {
+        const size_t nxc = (size_t)T.nx * (T.np + 1);
+        size_t n = (cv::L_MAX + 4) * nxc + (size_t)T.nx * T.np + (size_t)T.nx * T.nx + 2 * (size_t)T.nnz + 3 * (size_t)T.nx +
+                   2 * (size_t)T.nr + T.np + T.nk + (T.np + 1);
+        n += ((size_t)T.np + T.nx + 1) / 2 + 1;  // plist, perm (ints)
+        return (n + 15) & ~(size_t)15;
+    }
+    PB_HD void carve(double* base, const NetTables& T) {
+        const size_t nxc = (size_t)T.nx * (T.np + 1);
+        double* q = base;
+        for (int j = 0; j < cv::L_MAX; ++j) { zn[j] = q; q += nxc; }
+        acor = q; q += nxc;
+        ewt = q; q += nxc;
+        b = q; q += nxc;
+        scr = q; q += nxc;
+        dfdp = q; q += (size_t)T.nx * T.np;
+        A = q; q += (size_t)T.nx * T.nx;
+        Jsaved = q; q += T.nnz;
+        Jcur = q; q += T.nnz;
+        ysh = q; q += T.nx;
+        yj = q; q += T.nx;
+        fout = q; q += T.nx;
+        vb = q; q += T.nr;
+        v = q; q += T.nr;
+        p = q; q += T.np;
+        k = q; q += T.nk;
+        sllh = q; q += T.np + 1;
+        plist = reinterpret_cast<int*>(q);
+        perm = plist + T.np;
+    }
+    /// panel width that fits `smem_doubles` of staging memory (after rbuf / rowk / piv)
+    static int panel_width(int nx, size_t panel_doubles) {
+        int nb = TEAM_NB_MAX;
+        while (nb > 1 && (size_t)nx * nb > panel_doubles) nb >>= 1;
+        return nb;
+    }
+};
+
+template <class Team>
+struct BdfTeam {
+    NetTables T;
+    Team tm;
+    TeamWork w;
+    SolverOptions opt;
+    int nx, ns, ncol;
+    bool sensi;
+    enum { PH_STATE = 0, PH_SENS = 1 };
+
+    // integrator scalars (identical in every thread)
+    double tn, h, hprime, hscale, eta, etamax, etaq, etaqm1, etaqp1;
+    double gamma, gammap, gamrat, rl1, crate, crateS, delp, acnrm, acnrmS, saved_tq5, tstop;
+    double l[cv::L_MAX], tq1, tq2, tq3, tq4, tq5;
+    double tau[cv::L_MAX + 1], ssdat[6][4];
+    int q, qprime, L, qwait, nst, nscon, nstlp, nstlj, convfail;
+    bool jcur, jcurNLS, jcurNLSS, tstopset;
+    int nfe, nsetups, nje, nni, nniS, nfSe, netf, netfS, ncfn, ncfnS, nor, qsum;
+    ConditionIO io_;
+    double llh_, tout_, saved_t_, dsm_, dsmS_;
+    int it_, sim_status_, nstloc_, mxstep_, ncf_, nef_, ncfS_, nefS_, nflag_, dq_;
+    bool do_rescale_, undo_, restart_;
+    int fail_, ret_;
+
+    PB_HD explicit BdfTeam(const Team& t) : tm(t) {}
+
+#define PT_FOR(e, e0, e1) for (int e = (e0) + tm.tid(); e < (e1); e += tm.size())
+#define PT_FOR_ELEMS(e) PT_FOR(e, 0, nx * ncol)
+
+    PB_HD int phase_cmin(int phase) const { return phase == PH_STATE ? 0 : 1; }
+    PB_HD int phase_cmax(int phase) const { return phase == PH_STATE ? 0 : ns; }
+    PB_HD int errtest_cmax() const { return (sensi && opt.errconS) ? ns : 0; }
+
+    // ---------------------------------------------------------------- norms
+    /// WRMS norm of ca*A + cb*B (B may be null) with weights ewt over the columns [cmin, cmax],
+    /// maximum over the columns (N_VWrmsNorm / cvSensNorm / cvSensUpdateNorm)
+    PB_HD double wnorm(int cmin, int cmax, const double* A, double ca, const double* B, double cb) const {
+        tm.sync();
+        double res;
+        if (cmin == cmax) {
+            double s = 0.0;
+            PT_FOR(e, cmin * nx, (cmin + 1) * nx) {
+                const double v = (B ? ca * A[e] + cb * B[e] : ca * A[e]) * w.ewt[e];
+                s += v * v;
+            }
+            res = tm.sum(s);
+        } else {
+            double loc = 0.0;
+            for (int c = cmin + tm.warp(); c <= cmax; c += tm.nwarps()) {
+                double s = 0.0;
+                for (int i = tm.lane(); i < nx; i += Team::WARP) {
+                    const int e = c * nx + i;
+                    const double v = (B ? ca * A[e] + cb * B[e] : ca * A[e]) * w.ewt[e];
+                    s += v * v;
+                }
+                s = tm.warp_sum(s);
+                if (s > loc) loc = s;
+            }
+            res = tm.max(loc);
+        }
+        return sqrt(res / (double)nx);
+    }
+    PB_HD double wnorm1(int cmin, int cmax, const double* A) const { return wnorm(cmin, cmax, A, 1.0, nullptr, 0.0); }
+
+    /// cvEwtSetSS / cvSensEwtSetSS
+    PB_HD bool ewt_set() {
+        bool ok = true;
+        tm.sync();
+        PT_FOR_ELEMS(e) {
+            const double wv = opt.rtol * fabs(w.zn[0][e]) + opt.atol;
+            ok = ok && (wv > 0.0);
+            w.ewt[e] = 1.0 / wv;
+        }
+        return !tm.any(!ok);
+    }
+
+    // ---------------------------------------------------------------- model
+    /// J(t, ysh) and d xdot / d p at the converged state (Model_ODE::fsxdot at ip == 0)
+    PB_HD void refresh_Jcur() {
+        tm.sync();
+        net::rates(T, tm, w.ysh, w.p, w.vb, (double*)nullptr);
+        net::jac_values(T, tm, w.ysh, w.p, w.Jcur);
+        tm.sync();
+        net::dxdotdp_dense(T, tm, w.vb, w.dfdp);
+        tm.sync();
+    }
+
+    /// xdot(w.yj) -> w.fout; team-uniform result
+    PB_HD bool eval_xdot() {
+        tm.sync();
+        net::rates(T, tm, w.yj, w.p, w.vb, w.v);
+        tm.sync();
+        const bool ok = net::xdot_from_rates(T, tm, w.v, w.fout);
+        nfe++;
+        return !tm.any(!ok);
+    }
+
+    /// Right-hand sides of the columns of `phase` at v = zn[0] + acor:
+    /// b = raw ? F : rl1*zn[1] + acor - gamma*F  (cvNlsResidual / cvNlsResidualSensStg)
+    PB_HD int rhs(int phase, bool raw) {
+        bool bad = false;
+        tm.sync();
+        if (phase == PH_STATE) {
+            PT_FOR(i, 0, nx) w.yj[i] = w.zn[0][i] + w.acor[i];
+            bad = !eval_xdot();
+            PT_FOR(i, 0, nx) {
+                const double F = w.fout[i];
+                w.b[i] = raw ? F : (rl1 * w.zn[1][i] + w.acor[i]) - gamma * F;
+            }
+        } else {
+            PT_FOR(e, nx, nx * ncol) w.scr[e] = w.zn[0][e] + w.acor[e];
+            tm.sync();
+            PT_FOR(e, nx, nx * ncol) {
+                const int c = e / nx, i = e - c * nx;
+                const double* s = w.scr + (size_t)c * nx;
+                double F = w.dfdp[i + (size_t)w.plist[c - 1] * nx];
+                for (int kk = T.j_ptr[i]; kk < T.j_ptr[i + 1]; ++kk) F += w.Jcur[kk] * s[T.j_col[kk]];
+                if (!PB_FINITE(F)) bad = true;
+                w.b[e] = raw ? F : (rl1 * w.zn[1][e] + w.acor[e]) - gamma * F;
+            }
+            nfSe += ns;
+            bad = tm.any(bad);
+        }
+        tm.sync();
+        if (bad) return phase == PH_STATE ? cv::RHSFUNC_RECVR : cv::SRHSFUNC_RECVR;
+        return 0;
+    }
+
+    PB_HD void publish_state() {
+        tm.sync();
+        PT_FOR(i, 0, nx) w.ysh[i] = w.zn[0][i] + w.acor[i];
+        tm.sync();
+    }
+
+    PB_HD int rhs_all_raw(bool with_sens) {
+        int r = rhs(PH_STATE, true);
+        if (r || !with_sens) return r;
+        publish_state();
+        refresh_Jcur();
+        return rhs(PH_SENS, true);
+    }
+
+    // ---------------------------------------------------------------- linear algebra
+    /// A = (P (I - gamma*Jsaved))^-1 by blocked in-place Gauss-Jordan elimination with partial
+    /// pivoting (pivot rule of SUNDlsMat_denseGETRF); w.perm records the row order P.
+    /// Returns 0, or 1 on a zero / non-finite pivot.
+    PB_HD int invert_newton_matrix() {
+        double* const A = w.A;
+        const int NB = w.NB;
+        tm.sync();
+        for (size_t e = tm.tid(); e < (size_t)nx * nx; e += tm.size()) A[e] = 0.0;
+        PT_FOR(i, 0, nx) w.perm[i] = i;
+        tm.sync();
+        PT_FOR(i, 0, nx) {
+            for (int kk = T.j_ptr[i]; kk < T.j_ptr[i + 1]; ++kk) {
+                const int j = T.j_col[kk];
+                A[i + (size_t)j * nx] = (i == j ? 1.0 : 0.0) - gamma * w.Jsaved[kk];
+            }
+        }
+        tm.sync();
+        for (int k0 = 0; k0 < nx; k0 += NB) {
+            const int nb = (nx - k0 < NB) ? nx - k0 : NB;
+            // 1. panel -> staging memory
+            PT_FOR(e, 0, nx * nb) w.panel[e] = A[(size_t)k0 * nx + e];
+            tm.sync();
+            // 2. Gauss-Jordan on the panel columns
+            for (int kk = 0; kk < nb; ++kk) {
+                const int k = k0 + kk;
+                double* const colk = w.panel + (size_t)kk * nx;
+                double best = -1.0;
+                int bi = 0x7fffffff;
+                for (int i = k + tm.tid(); i < nx; i += tm.size()) {
+                    const double m = fabs(colk[i]);
+                    if (m > best) { best = m; bi = i; }
+                }
+                best = tm.argmax(best, bi);
+                if (!(best > 0.0) || !PB_FINITE(best)) return 1;
+                const int lp = bi;
+                if (lp != k) {
+                    PT_FOR(c, 0, nb) {
+                        double* col = w.panel + (size_t)c * nx;
+                        const double t_ = col[lp];
+                        col[lp] = col[k];
+                        col[k] = t_;
+                    }
+                }
+                if (tm.tid() == 0) {
+                    w.piv[kk] = lp;
+                    const int t_ = w.perm[k];
+                    w.perm[k] = w.perm[lp];
+                    w.perm[lp] = t_;
+                }
+                tm.sync();
+                const double pinv = 1.0 / colk[k];
+                PT_FOR(c, 0, nb) w.rowk[c] = w.panel[k + (size_t)c * nx] * pinv;
+                tm.sync();
+                // other panel columns: rank-1 update; column kk itself afterwards
+                PT_FOR(e, 0, nx * nb) {
+                    const int c = e / nx, i = e - c * nx;
+                    if (c == kk) continue;
+                    if (i == k) w.panel[e] = w.rowk[c];
+                    else w.panel[e] -= colk[i] * w.rowk[c];
+                }
+                tm.sync();
+                PT_FOR(i, 0, nx) colk[i] = (i == k) ? pinv : -colk[i] * pinv;
+                tm.sync();
+            }
+            // 3. the row swaps of this block step, applied in order to the other columns
+            PT_FOR(j, 0, nx) {
+                if (j >= k0 && j < k0 + nb) continue;
+                double* col = A + (size_t)j * nx;
+                for (int kk = 0; kk < nb; ++kk) {
+                    const int lp = w.piv[kk];
+                    if (lp != k0 + kk) {
+                        const double t_ = col[lp];
+                        col[lp] = col[k0 + kk];
+                        col[k0 + kk] = t_;
+                    }
+                }
+            }
+            tm.sync();
+            // 4. rank-nb update of the other columns: A[:, j] = (rows of the block zeroed) + W * R[:, j]
+            //    with W = panel (this thread's row in registers) and R = the old pivot rows of A
+            for (int j0 = 0; j0 < nx; j0 += TEAM_CW) {
+                const int cw = (nx - j0 < TEAM_CW) ? nx - j0 : TEAM_CW;
+                PT_FOR(e, 0, TEAM_NB_MAX * cw) {
+                    const int jj = e / TEAM_NB_MAX, kk = e - jj * TEAM_NB_MAX;
+                    w.rbuf[e] = (kk < nb) ? A[(k0 + kk) + (size_t)(j0 + jj) * nx] : 0.0;
+                }
+                tm.sync();
+                for (int i = tm.tid(); i < nx; i += tm.size()) {
+                    double wr[TEAM_NB_MAX];
+                    PB_UNROLL
+                    for (int kk = 0; kk < TEAM_NB_MAX; ++kk) wr[kk] = (kk < nb) ? w.panel[i + (size_t)kk * nx] : 0.0;
+                    const bool in_block = (i >= k0 && i < k0 + nb);
+                    for (int jj = 0; jj < cw; ++jj) {
+                        const int j = j0 + jj;
+                        if (j >= k0 && j < k0 + nb) continue;
+                        const double* r = w.rbuf + jj * TEAM_NB_MAX;
+                        double x = in_block ? 0.0 : A[i + (size_t)j * nx];
+                        PB_UNROLL
+                        for (int kk = 0; kk < TEAM_NB_MAX; ++kk) x += wr[kk] * r[kk];
+                        A[i + (size_t)j * nx] = x;
+                    }
+                }
+                tm.sync();
+            }
+            // 5. the transformed panel replaces the block columns
+            PT_FOR(e, 0, nx * nb) A[(size_t)k0 * nx + e] = w.panel[e];
+            tm.sync();
+        }
+        return 0;
+    }
+
+    /// cvLsSetup + cvLsLinSys + the inversion; the Jacobian is evaluated at w.yj
+    PB_HD int lsetup() {
+        const double dgamma = fabs(gamma / gammap - 1.0);
+        const bool jbad = (nst == 0) || (nst >= nstlj + cv::MSBJ) ||
+                          ((convfail == cv::FAIL_BAD_J) && (dgamma < cv::DGMAX_JBAD)) || (convfail == cv::FAIL_OTHER);
+        int ret = 0;
+        tm.sync();
+        if (jbad) {
+            const bool ok = net::jac_values(T, tm, w.yj, w.p, w.Jsaved);
+            if (tm.any(!ok)) ret = 1;  // AMICI's fJ returns checkFinite(J): recoverable
+        }
+        if (ret == 0) ret = invert_newton_matrix();
+        if (jbad) { nje++; nstlj = nst; }
+        jcur = jbad;
+        nsetups++;
+        return ret;
+    }
+
+    /// scr[:, c0 .. c0+nc) = nsc * A * (P b)[:, c0 .. c0+nc): the solve GEMM.  Every thread owns
+    /// rows of A (streamed from HBM/L2, coalesced across the warp); the right-hand-side tile is
+    /// gathered through the pivot order into staging memory and broadcast.
+    template <int TN>
+    PB_HD void solve_pass(int c0, int nc, double nsc) {
+        constexpr int KC = (TEAM_RBUF / TN) < 64 ? (TEAM_RBUF / TN) : ((TN == 1) ? TEAM_RBUF : 64);
+        for (int row0 = 0; row0 < nx; row0 += tm.size()) {
+            const int i = row0 + tm.tid();
+            const bool active = i < nx;
+            double acc[TN];
+            PB_UNROLL
+            for (int cc = 0; cc < TN; ++cc) acc[cc] = 0.0;
+            for (int k0 = 0; k0 < nx; k0 += KC) {
+                const int kc = (nx - k0 < KC) ? nx - k0 : KC;
+                tm.sync();
+                PT_FOR(e, 0, kc * TN) {
+                    const int kk = e / TN, cc = e - kk * TN;
+                    w.rbuf[e] = (cc < nc) ? w.b[w.perm[k0 + kk] + (size_t)(c0 + cc) * nx] : 0.0;
+                }
+                tm.sync();
+                if (active) {
+                    const double* arow = w.A + i + (size_t)k0 * nx;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
+                    for (int kk = 0; kk < kc; ++kk) {
+                        const double a = arow[(size_t)kk * nx];
+                        const double* r = w.rbuf + kk * TN;
+                        PB_UNROLL
+                        for (int cc = 0; cc < TN; ++cc) acc[cc] += a * r[cc];
+                    }
+                }
+            }
+            if (active) {
+                PB_UNROLL
+                for (int cc = 0; cc < TN; ++cc)
+                    if (cc < nc) w.scr[i + (size_t)(c0 + cc) * nx] = nsc * acc[cc];
+            }
+        }
+    }
+
+    /// Newton update of the columns [cmin, cmax]: delta = -(I - gamma J)^-1 b with cvLsSolve's
+    /// gamma-ratio scaling; acor += delta; returns the WRMS norm of delta.
+    PB_HD double newton_update(int cmin, int cmax) {
+        const double nsc = (gamrat != 1.0) ? -2.0 / (1.0 + gamrat) : -1.0;
+        if (cmin == cmax) {
+            solve_pass<1>(cmin, 1, nsc);
+        } else {
+            for (int c0 = cmin; c0 <= cmax; c0 += TEAM_TN) {
+                const int nc = (cmax + 1 - c0 < TEAM_TN) ? cmax + 1 - c0 : TEAM_TN;
+                solve_pass<TEAM_TN>(c0, nc, nsc);
+            }
+        }
+        tm.sync();
+        PT_FOR(e, cmin * nx, (cmax + 1) * nx) w.acor[e] += w.scr[e];
+        return wnorm1(cmin, cmax, w.scr);
+    }
+
+    // ---------------------------------------------------------------- BDF coefficients
+    /// cvSetBDF + cvSetTqBDF + cvSet
+    PB_HD void cvset() {
+        double alpha0, alpha0_hat, xi_inv, xistar_inv, hsum;
+        l[0] = l[1] = xi_inv = xistar_inv = 1.0;
+        for (int i = 2; i <= q; ++i) l[i] = 0.0;
+        alpha0 = alpha0_hat = -1.0;
+        hsum = h;
+        if (q > 1) {
+            for (int j = 2; j < q; ++j) {
+                hsum += tau[j - 1];
+                xi_inv = h / hsum;
+                alpha0 -= 1.0 / (double)j;
+                for (int i = j; i >= 1; --i) l[i] += l[i - 1] * xi_inv;
+            }
+            alpha0 -= 1.0 / (double)q;
+            xistar_inv = -l[1] - alpha0;
+            hsum += tau[q - 1];
+            xi_inv = h / hsum;
+            alpha0_hat = -l[1] - xi_inv;
+            for (int i = q; i >= 1; --i) l[i] += l[i - 1] * xistar_inv;
+        }
+        const double A1 = 1.0 - alpha0_hat + alpha0;
+        const double A2 = 1.0 + q * A1;
+        tq2 = fabs(A1 / (alpha0 * A2));
+        tq5 = fabs(A2 * xistar_inv / (l[q] * xi_inv));
+        if (qwait == 1) {
+            if (q > 1) {
+                const double C = xistar_inv / l[q];
+                const double A3 = alpha0 + 1.0 / (double)q;
+                const double A4 = alpha0_hat + xi_inv;
+                const double Cpinv = (1.0 - A4 + A3) / A3;
+                tq1 = fabs(C * Cpinv);
+            } else {
+                tq1 = 1.0;
+            }
+            hsum += tau[q];
+            xi_inv = h / hsum;
+            const double A5 = alpha0 - 1.0 / (double)(q + 1);
+            const double A6 = alpha0_hat - xi_inv;
+            const double Cppinv = (1.0 - A6 + A5) / A2;
+            tq3 = fabs(Cppinv / (xi_inv * (q + 2) * A5));
+        }
+        tq4 = cv::CORTES / tq2;
+        rl1 = 1.0 / l[1];
+        gamma = h * rl1;
+        if (nst == 0) gammap = gamma;
+        gamrat = (nst > 0) ? gamma / gammap : 1.0;
+    }
+
+    // ---------------------------------------------------------------- history array
+    /// cvPredict (sgn = +1) / cvRestore (sgn = -1): Pascal-triangle sweep per element in registers
+    PB_HD void shift_history(double sgn) {
+        tm.sync();
+        PT_FOR_ELEMS(e) {
+            double z[cv::L_MAX];
+            for (int j = 0; j <= q; ++j) z[j] = w.zn[j][e];
+            for (int k = 1; k <= q; ++k)
+                for (int j = q; j >= k; --j) z[j - 1] += sgn * z[j];
+            for (int j = 0; j < q; ++j) w.zn[j][e] = z[j];
+        }
+        tm.sync();
+    }
+    /// cvRescale
+    PB_HD void rescale() {
+        tm.sync();
+        PT_FOR_ELEMS(e) {
+            double factor = eta;
+            for (int j = 1; j <= q; ++j) {
+                w.zn[j][e] *= factor;
+                factor *= eta;
+            }
+        }
+        h = hscale * eta;
+        hscale = h;
+        nscon = 0;
+        tm.sync();
+    }
+    /// cvAdjustOrder -> cvIncreaseBDF / cvDecreaseBDF
+    PB_HD void adjust_order(int deltaq) {
+        if ((q == 2) && (deltaq != 1)) return;
+        double lc[cv::L_MAX + 1];
+        for (int i = 0; i <= cv::L_MAX; ++i) lc[i] = 0.0;
+        lc[2] = 1.0;
+        int src, jmax;
+        double A1 = 0.0;
+        if (deltaq == 1) {
+            double alpha1 = 1.0, prod = 1.0, xiold = 1.0, alpha0 = -1.0;
+            double hsum = hscale;
+            for (int j = 1; j < q; ++j) {
+                hsum += tau[j + 1];
+                const double xi = hsum / hscale;
+                prod *= xi;
+                alpha0 -= 1.0 / (double)(j + 1);
+                alpha1 += 1.0 / xi;
+                for (int i = j + 2; i >= 2; --i) lc[i] = lc[i] * xiold + lc[i - 1];
+                xiold = xi;
+            }
+            A1 = (-alpha0 - alpha1) / prod;
+            src = L;
+            jmax = q;
+        } else {
+            double hsum = 0.0;
+            for (int j = 1; j <= q - 2; ++j) {
+                hsum += tau[j];
+                const double xi = hsum / hscale;
+                for (int i = j + 2; i >= 2; --i) lc[i] = lc[i] * xi + lc[i - 1];
+            }
+            for (int j = 2; j < q; ++j) lc[j] = -lc[j];
+            src = q;
+            jmax = q - 1;
+        }
+        tm.sync();
+        PT_FOR_ELEMS(e) {
+            if (deltaq == 1) w.zn[src][e] = A1 * w.zn[cv::Q_MAX][e];
+            const double zs = w.zn[src][e];
+            for (int j = 2; j <= jmax; ++j) w.zn[j][e] += lc[j] * zs;
+        }
+        tm.sync();
+    }
+
+    // ---------------------------------------------------------------- nonlinear solve
+    /// cvNls / cvStgrNls + SUNNonlinSolSolve_Newton + the convergence tests for the columns of
+    /// `phase`; on success the corrected vector is zn[0] + acor.
+    PB_HD int nls(int phase, int nflag) {
+        const int cmin = phase_cmin(phase), cmax = phase_cmax(phase);
+        bool setup_pending = false;
+        if (phase == PH_STATE) {
+            convfail = ((nflag == cv::FIRST_CALL) || (nflag == cv::PREV_ERR_FAIL)) ? cv::NO_FAILURES : cv::FAIL_OTHER;
+            setup_pending = (nflag == cv::PREV_CONV_FAIL) || (nflag == cv::PREV_ERR_FAIL) || (nst == 0) ||
+                            (nst >= nstlp + cv::MSBP) || (fabs(gamrat - 1.0) > cv::DGMAX_LSETUP);
+        }
+        tm.sync();
+        PT_FOR(e, cmin * nx, (cmax + 1) * nx) w.acor[e] = 0.0;
+        bool jbad = false;
+        bool top = true;
+        int m_it = 0;
+        for (;;) {
+            int ret = rhs(phase, false);
+            if (ret != 0 && top) return ret;
+            if (ret == 0 && setup_pending) {
+                if (jbad) convfail = cv::FAIL_BAD_J;
+                if (phase == PH_SENS) {  // Jacobian at the converged state
+                    tm.sync();
+                    PT_FOR(i, 0, nx) w.yj[i] = w.ysh[i];
+                }  // state phase: rhs() has just put zn[0]+acor into w.yj
+                const int lr = lsetup();
+                setup_pending = false;
+                if (phase == PH_STATE) jcurNLS = jcur;
+                else jcurNLSS = jcur;
+                gamrat = 1.0;
+                gammap = gamma;
+                crate = 1.0;
+                crateS = 1.0;
+                nstlp = nst;
+                if (lr != 0) return cv::CONV_RECVR;
+            }
+            top = false;
+            if (ret == 0) {
+                if (phase == PH_STATE) nni++;
+                else nniS++;
+                const double del = newton_update(cmin, cmax);
+                double cr = (phase == PH_STATE) ? crate : crateS;
+                if (m_it > 0) cr = fmax(cv::CRDOWN * cr, del / delp);
+                if (phase == PH_STATE) crate = cr;
+                else crateS = cr;
+                const double dcon = del * fmin(1.0, cr) / tq4;
+                if (dcon <= 1.0) {
+                    const double an = (m_it == 0) ? del : wnorm1(cmin, cmax, w.acor);
+                    if (phase == PH_STATE) {
+                        acnrm = an;
+                        jcurNLS = false;
+                    } else {
+                        if (opt.errconS) acnrmS = an;
+                        jcurNLSS = false;
+                    }
+                    jcur = false;
+                    return 0;
+                }
+                if ((m_it >= 1) && (del > cv::RDIV * delp)) {
+                    ret = cv::CONV_RECVR;
+                } else {
+                    delp = del;
+                    m_it++;
+                    if (m_it >= cv::NLS_MAXCOR) ret = cv::CONV_RECVR;
+                    else continue;
+                }
+            }
+            if ((ret > 0) && !((phase == PH_STATE) ? jcurNLS : jcurNLSS)) {
+                setup_pending = true;
+                jbad = true;
+                top = true;
+                m_it = 0;
+                tm.sync();
+                PT_FOR(e, cmin * nx, (cmax + 1) * nx) w.acor[e] = 0.0;
+                continue;
+            }
+            return ret;
+        }
+    }
+
+    // ---------------------------------------------------------------- step control
+    /// cvCompleteStep
+    PB_HD void complete_step() {
+        nst++;
+        nscon++;
+        qsum += q;
+        for (int i = q; i >= 2; --i) tau[i] = tau[i - 1];
+        if ((q == 1) && (nst > 1)) tau[2] = tau[1];
+        tau[1] = h;
+        qwait--;
+        const bool save = (qwait == 1) && (q != cv::Q_MAX);
+        tm.sync();
+        PT_FOR_ELEMS(e) {
+            const double a = w.acor[e];
+            for (int j = 0; j <= q; ++j) w.zn[j][e] += l[j] * a;
+            if (save) w.zn[cv::Q_MAX][e] = a;
+        }
+        tm.sync();
+        if (save) saved_tq5 = tq5;
+    }
+
+    /// cvPrepareNextStep with cvSetEta, cvComputeEtaqm1 / cvComputeEtaqp1 / cvChooseEta
+    PB_HD void prepare_next_step(double dsm) {
+        if (etamax == 1.0) {
+            qwait = qwait > 2 ? qwait : 2;
+            qprime = q;
+            hprime = h;
+            eta = 1.0;
+            return;
+        }
+        etaq = 1.0 / (pow(cv::BIAS2 * dsm, 1.0 / (double)L) + cv::ADDON);
+        qprime = q;
+        eta = etaq;
+        if (qwait == 0) {
+            qwait = 2;
+            const int ecmax = errtest_cmax();
+            etaqm1 = 0.0;
+            if (q > 1) {
+                double ddn = wnorm1(0, ecmax, w.zn[q]);
+                ddn = ddn * tq1;
+                etaqm1 = 1.0 / (pow(cv::BIAS1 * ddn, 1.0 / (double)q) + cv::ADDON);
+            }
+            etaqp1 = 0.0;
+            if (q != cv::Q_MAX) {
+                if (saved_tq5 != 0.0) {
+                    const double hr = h / tau[2];
+                    double hp = 1.0;
+                    for (int i = 0; i < L; ++i) hp *= hr;  // SUNRpowerI
+                    const double cquot = (tq5 / saved_tq5) * hp;
+                    double dup = wnorm(0, ecmax, w.zn[cv::Q_MAX], -cquot, w.acor, 1.0);
+                    dup = dup * tq3;
+                    etaqp1 = 1.0 / (pow(cv::BIAS3 * dup, 1.0 / (double)(L + 1)) + cv::ADDON);
+                }
+            }
+            const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
+            if ((etam > cv::ETA_MIN_FX) && (etam < cv::ETA_MAX_FX)) {
+                eta = 1.0;
+                qprime = q;
+            } else if (etam == etaq) {
+                eta = etaq;
+                qprime = q;
+            } else if (etam == etaqm1) {
+                eta = etaqm1;
+                qprime = q - 1;
+            } else {
+                eta = etaqp1;
+                qprime = q + 1;
+                tm.sync();
+                PT_FOR(e, 0, (ecmax + 1) * nx) w.zn[cv::Q_MAX][e] = w.acor[e];
+                tm.sync();
+            }
+        }
+        if ((eta > cv::ETA_MIN_FX) && (eta < cv::ETA_MAX_FX)) {
+            eta = 1.0;
+            hprime = h;
+        } else {
+            if (eta >= cv::ETA_MAX_FX) eta = fmin(eta, etamax);
+            else eta = fmax(eta, cv::ETA_MIN);
+            hprime = h * eta;
+            if (qprime < q) nscon = 0;
+        }
+    }
+
+    /// cvSLdet: every thread evaluates the (scalar) stability-limit detection redundantly
+    PB_HD int sldet() const {
+        const double rrcut = 0.98, vrrtol = 1.0e-4, vrrt2 = 5.0e-4, sqtol = 1.0e-3, rrtol = 1.0e-2;
+        double rav[4], vrat[4], qc1[4], qc2[4], qc4[4], qc5[4], ssmax[4], smax[4], qkr[4], rrc[4], sqmx[4];
+        double qjk[4][4], sigsq[4];
+        const double (*ss)[4] = ssdat;
+        for (int k = 1; k <= 3; ++k) {
+            double smink = ss[1][k], smaxk = 0.0;
+            for (int i = 1; i <= 5; ++i) {
+                smink = fmin(smink, ss[i][k]);
+                smaxk = fmax(smaxk, ss[i][k]);
+            }
+            if (smink < cv::TINY * smaxk) return -1;
+            smax[k] = smaxk;
+            ssmax[k] = smaxk * smaxk;
+            double sumrat = 0.0, sumrsq = 0.0;
+            for (int i = 1; i <= 4; ++i) {
+                const double rat = ss[i][k] / ss[i + 1][k];
+                sumrat += rat;
+                sumrsq += rat * rat;
+            }
+            rav[k] = 0.25 * sumrat;
+            vrat[k] = fabs(0.25 * sumrsq - rav[k] * rav[k]);
+            qc5[k] = ss[1][k] * ss[3][k] - ss[2][k] * ss[2][k];
+            qc4[k] = ss[2][k] * ss[3][k] - ss[1][k] * ss[4][k];
+            qc2[k] = ss[2][k] * ss[5][k] - ss[3][k] * ss[4][k];
+            qc1[k] = ss[4][k] * ss[4][k] - ss[3][k] * ss[5][k];
+        }
+        int kflag = 0;
+        double rr = 0.0;
+        const double vmin = fmin(vrat[1], fmin(vrat[2], vrat[3]));
+        const double vmax = fmax(vrat[1], fmax(vrat[2], vrat[3]));
+        if (vmin < vrrtol * vrrtol) {
+            if (vmax > vrrt2 * vrrt2) return -2;
+            rr = (rav[1] + rav[2] + rav[3]) / 3.0;
+            double drrmax = 0.0;
+            for (int k = 1; k <= 3; ++k) drrmax = fmax(drrmax, fabs(rav[k] - rr));
+            if (drrmax > vrrt2) return -3;
+            kflag = 1;
+        } else {
+            if (fabs(qc1[1]) < cv::TINY * ssmax[1]) return -4;
+            double tem = qc1[2] / qc1[1];
+            const double q22 = qc2[2] - tem * qc2[1];
+            const double q42 = qc4[2] - tem * qc4[1], q52 = qc5[2] - tem * qc5[1];
+            tem = qc1[3] / qc1[1];
+            const double q23 = qc2[3] - tem * qc2[1];
+            double q43 = qc4[3] - tem * qc4[1], q53 = qc5[3] - tem * qc5[1];
+            if (fabs(q22) < cv::TINY * ssmax[2]) return -4;
+            tem = q23 / q22;
+            q43 -= tem * q42;
+            q53 -= tem * q52;
+            if (fabs(q43) < cv::TINY * ssmax[3]) return -4;
+            rr = -q53 / q43;
+            if (rr < cv::TINY || rr > 100.0) return -5;
+            double sqmax = 0.0;
+            for (int k = 1; k <= 3; ++k) {
+                qkr[k] = qc5[k] + rr * (qc4[k] + rr * rr * (qc2[k] + rr * qc1[k]));
+                sqmax = fmax(sqmax, fabs(qkr[k]) / ssmax[k]);
+            }
+            double sqmin = 0.0;
+            if (sqmax < sqtol) {
+                kflag = 2;
+            } else {
+                for (int it = 1; it <= 3; ++it) {
+                    for (int k = 1; k <= 3; ++k) {
+                        const double qp = qc4[k] + rr * rr * (3.0 * qc2[k] + rr * 4.0 * qc1[k]);
+                        double drr = 0.0;
+                        if (fabs(qp) > cv::TINY * ssmax[k]) drr = -qkr[k] / qp;
+                        rrc[k] = rr + drr;
+                    }
+                    for (int k = 1; k <= 3; ++k) {
+                        const double s = rrc[k];
+                        double sqmaxk = 0.0;
+                        for (int j = 1; j <= 3; ++j) {
+                            qjk[j][k] = qc5[j] + s * (qc4[j] + s * s * (qc2[j] + s * qc1[j]));
+                            const double saqj = fabs(qjk[j][k]) / ssmax[j];
+                            if (saqj > sqmaxk) sqmaxk = saqj;
+                        }
+                        sqmx[k] = sqmaxk;
+                    }
+                    int kmin = 1;
+                    sqmin = sqmx[1] + 1.0;
+                    for (int k = 1; k <= 3; ++k) {
+                        if (sqmx[k] < sqmin) {
+                            kmin = k;
+                            sqmin = sqmx[k];
+                        }
+                    }
+                    rr = rrc[kmin];
+                    if (sqmin < sqtol) {
+                        kflag = 3;
+                        break;
+                    }
+                    for (int j = 1; j <= 3; ++j) qkr[j] = qjk[j][kmin];
+                }
+                if (sqmin > sqtol) return -6;
+            }
+        }
+        for (int k = 1; k <= 3; ++k) {
+            const double rsa = ss[1][k];
+            const double rsb = ss[2][k] * rr;
+            const double rsc = ss[3][k] * rr * rr;
+            const double rsd = ss[4][k] * rr * rr * rr;
+            const double rd1a = rsa - rsb, rd1b = rsb - rsc, rd1c = rsc - rsd;
+            const double rd2a = rd1a - rd1b, rd2b = rd1b - rd1c;
+            const double rd3a = rd2a - rd2b;
+            if (fabs(rd1b) < cv::TINY * smax[k]) return -7;
+            const double cest1 = -rd3a / rd1b;
+            if (cest1 < cv::TINY || cest1 > 4.0) return -7;
+            const double corr1 = (rd2b / cest1) / (rr * rr);
+            sigsq[k] = ss[3][k] + corr1;
+        }
+        if (sigsq[2] < cv::TINY) return -8;
+        const double ratp = sigsq[3] / sigsq[2];
+        const double ratm = sigsq[1] / sigsq[2];
+        const double qfac1 = 0.25 * (q * q - 1.0);
+        const double qfac2 = 2.0 / (q - 1.0);
+        const double bb = ratp * ratm - 1.0 - qfac1 * ratp;
+        const double tem = 1.0 - qfac2 * bb;
+        if (fabs(tem) < cv::TINY) return -8;
+        const double rrb = 1.0 / tem;
+        if (fabs(rrb - rr) > rrtol) return -9;
+        if (rr > rrcut) {
+            if (kflag == 1) kflag = 4;
+            if (kflag == 2) kflag = 5;
+            if (kflag == 3) kflag = 6;
+        }
+        return kflag;
+    }
+
+    /// cvBDFStab
+    PB_HD void bdf_stab() {
+        if (q >= 3) {
+            const double n0 = wnorm1(0, 0, w.zn[q]);
+            const double n1 = wnorm1(0, 0, w.zn[q - 1]);
+            int factorial = 1;
+            for (int i = 1; i <= q - 1; ++i) factorial *= i;
+            const double sq = factorial * q * (q + 1) * acnrm / fmax(tq5, cv::TINY);
+            const double sqm1 = n0 * (factorial * q);
+            const double sqm2 = n1 * factorial;
+            for (int k = 1; k <= 3; ++k)
+                for (int i = 5; i >= 2; --i) ssdat[i][k] = ssdat[i - 1][k];
+            ssdat[1][1] = sqm2 * sqm2;
+            ssdat[1][2] = sqm1 * sqm1;
+            ssdat[1][3] = sq * sq;
+        }
+        if (qprime >= q) {
+            if ((q >= 3) && (nscon >= q + 5)) {
+                const int ldflag = sldet();
+                if (ldflag > 3) {
+                    qprime = q - 1;
+                    eta = etaqm1;
+                    eta = fmin(eta, etamax);
+                    hprime = h * eta;
+                    nor++;
+                }
+            }
+        } else {
+            nscon = 0;
+        }
+    }
+
+    /// zn[1] = h * f(tn, zn[0]) for the state and (if any) the sensitivities; acor is scratch
+    PB_HD int reload_zn1() {
+        tm.sync();
+        PT_FOR_ELEMS(e) w.acor[e] = 0.0;
+        tm.sync();
+        const int r = rhs_all_raw(sensi);
+        if (r) return r;
+        PT_FOR_ELEMS(e) w.zn[1][e] = h * w.b[e];
+        tm.sync();
+        return 0;
+    }
+
+    PB_HD void step_begin() {
+        ncf_ = nef_ = ncfS_ = nefS_ = 0;
+        dsm_ = dsmS_ = 0.0;
+        saved_t_ = tn;
+        nflag_ = cv::FIRST_CALL;
+        do_rescale_ = (nst > 0) && (hprime != h);
+        dq_ = do_rescale_ ? (qprime - q) : 0;
+        undo_ = restart_ = false;
+    }
+
+    /// order / step-size adjustment, (after a failed attempt: restore,) prediction, coefficients
+    PB_HD int attempt_predict() {
+        for (;;) {
+            if (undo_) {
+                tn = saved_t_;
+            } else {
+                if (restart_) {
+                    restart_ = false;
+                    h *= eta;
+                    hscale = h;
+                    qwait = cv::LONG_WAIT;
+                    nscon = 0;
+                    if (reload_zn1()) return sensi ? SIM_UNREC_SRHSFUNC_ERR : SIM_UNREC_RHSFUNC_ERR;
+                }
+                if (dq_ != 0) {
+                    adjust_order(dq_);
+                    q += dq_;
+                    L = q + 1;
+                    qwait = L;
+                    dq_ = 0;
+                }
+                if (do_rescale_) {
+                    rescale();
+                    do_rescale_ = false;
+                }
+                tn += h;
+                if (tstopset && ((tn - tstop) * h > 0.0)) tn = tstop;
+            }
+            shift_history(undo_ ? -1.0 : 1.0);
+            if (!undo_) break;
+            undo_ = false;
+        }
+        cvset();
+        fail_ = 0;
+        ret_ = 0;
+        return 0;
+    }
+
+    PB_HD void attempt_correct(int phase) {
+        if (phase == PH_SENS) {
+            if (fail_ || !sensi) return;
+            ncf_ = nef_ = 0;
+            publish_state();
+            PT_FOR(i, 0, nx) w.yj[i] = w.ysh[i];
+            if (!eval_xdot()) { fail_ = 5; return; }
+            refresh_Jcur();
+        }
+        ret_ = nls(phase, nflag_);
+        if (ret_ != 0) {
+            fail_ = 1 + 2 * phase;
+        } else if (phase == PH_STATE) {
+            dsm_ = acnrm * tq2;
+            if (dsm_ > 1.0) fail_ = 2;
+        } else if (opt.errconS) {
+            dsmS_ = acnrmS * tq2;
+            if (dsmS_ > 1.0) fail_ = 4;
+            else if (dsmS_ > dsm_) dsm_ = dsmS_;
+        }
+    }
+
+    /// cvCompleteStep / cvPrepareNextStep / cvBDFStab on success, otherwise cvHandleNFlag and
+    /// cvDoErrorTest.  Returns 0 (step completed), 1 (another attempt) or a negative failure code.
+    PB_HD int attempt_finish() {
+        const int fail = fail_;
+        const int ret = ret_;
+        if (fail == 0) {
+            complete_step();
+            prepare_next_step(dsm_);
+            if (opt.stldet) bdf_stab();
+            etamax = (nst <= cv::SMALL_NST) ? cv::ETA_MAX_ES : cv::ETA_MAX_GS;
+            return 0;
+        }
+        if (fail == 5) {
+            nflag_ = cv::PREV_CONV_FAIL;
+            return 1;
+        }
+        undo_ = true;
+        if (fail == 1 || fail == 3) {
+            if (fail == 1) { ncfn++; ncf_++; } else { ncfnS++; ncfS_++; }
+            if (ret < 0) return ret;
+            etamax = 1.0;
+            if ((fabs(h) <= 0.0) || ((fail == 1 ? ncf_ : ncfS_) == cv::MXNCF)) {
+                if (ret == cv::CONV_RECVR) return SIM_CONV_FAILURE;
+                if (ret == cv::RHSFUNC_RECVR) return SIM_REPTD_RHSFUNC_ERR;
+                return SIM_REPTD_SRHSFUNC_ERR;
+            }
+            eta = cv::ETA_CF;
+            nflag_ = cv::PREV_CONV_FAIL;
+            do_rescale_ = true;
+        } else {
+            int e;
+            if (fail == 2) { e = ++nef_; netf++; } else { e = ++nefS_; netfS++; }
+            nflag_ = cv::PREV_ERR_FAIL;
+            if ((fabs(h) <= 0.0) || (e == cv::MXNEF)) return SIM_ERR_FAILURE;
+            etamax = 1.0;
+            if (e <= cv::MXNEF1) {
+                eta = 1.0 / (pow(cv::BIAS2 * (fail == 2 ? dsm_ : dsmS_), 1.0 / (double)L) + cv::ADDON);
+                eta = fmax(cv::ETA_MIN_EF, eta);
+                if (e >= cv::SMALL_NEF) eta = fmin(eta, cv::ETA_MAX_EF);
+                do_rescale_ = true;
+            } else if (q > 1) {
+                eta = cv::ETA_MIN_EF;
+                dq_ = -1;
+                do_rescale_ = true;
+            } else {
+                eta = cv::ETA_MIN_EF;
+                restart_ = true;
+            }
+        }
+        return 1;
+    }
+
+    // ---------------------------------------------------------------- initial step
+    /// cvHin with cvUpperBoundH0 and cvYddNorm; zn[1] holds y'(t0) unscaled
+    PB_HD int hin(double tout) {
+        const double tdiff = tout - tn;
+        if (tdiff == 0.0) return SIM_TOO_CLOSE;
+        const int sign = (tdiff > 0.0) ? 1 : -1;
+        const double tdist = fabs(tdiff);
+        const double tround = cv::UROUND * fmax(fabs(tn), fabs(tout));
+        if (tdist < 2.0 * tround) return SIM_TOO_CLOSE;
+        const double hlb = cv::HLB_FACTOR * tround;
+        const bool withS = sensi && opt.errconS;
+        const int ecmax = errtest_cmax();
+        double hub_inv = 0.0;
+        tm.sync();
+        PT_FOR(e, 0, (ecmax + 1) * nx) {
+            const double den = cv::HUB_FACTOR * fabs(w.zn[0][e]) + 1.0 / w.ewt[e];
+            const double v = fabs(w.zn[1][e]) / den;
+            if (v > hub_inv) hub_inv = v;
+        }
+        hub_inv = tm.max(hub_inv);
+        double hub = cv::HUB_FACTOR * tdist;
+        if (hub * hub_inv > 1.0) hub = 1.0 / hub_inv;
+        double hg = sqrt(hlb * hub);
+        if (hub < hlb) {
+            h = (sign == -1) ? -hg : hg;
+            return 0;
+        }
+        double hs = hg, hnew = hg;
+        for (int count1 = 1; count1 <= cv::HIN_MAX_ITERS; ++count1) {
+            bool hgOK = false;
+            int retval = 0;
+            double yddnrm = 0.0;
+            for (int count2 = 1; count2 <= cv::HIN_MAX_ITERS; ++count2) {
+                const double hgs = hg * sign;
+                tm.sync();
+                PT_FOR_ELEMS(e) w.acor[e] = hgs * w.zn[1][e];
+                // AMICI's right-hand sides do not depend on t explicitly for network models
+                retval = rhs_all_raw(withS);
+                if (retval == 0) {
+                    const double hinv = 1.0 / hgs;
+                    yddnrm = wnorm(0, ecmax, w.b, hinv, w.zn[1], -hinv);
+                    hgOK = true;
+                    break;
+                }
+                hg *= 0.2;
+            }
+            tm.sync();
+            PT_FOR_ELEMS(e) w.acor[e] = 0.0;
+            tm.sync();
+            if (!hgOK) {
+                if (count1 <= 2) return retval == cv::RHSFUNC_RECVR ? SIM_REPTD_RHSFUNC_ERR : SIM_REPTD_SRHSFUNC_ERR;
+                hnew = hs;
+                break;
+            }
+            hs = hg;
+            hnew = (yddnrm * hub * hub > 2.0) ? sqrt(2.0 / yddnrm) : sqrt(hg * hub);
+            if (count1 == cv::HIN_MAX_ITERS) break;
+            const double hrat = hnew / hg;
+            if ((hrat > 0.5) && (hrat < 2.0)) break;
+            if ((count1 > 1) && (hrat > 2.0)) { hnew = hg; break; }
+            hg = hnew;
+        }
+        double h0 = cv::H_BIAS * hnew;
+        if (h0 < hlb) h0 = hlb;
+        if (h0 > hub) h0 = hub;
+        if (sign == -1) h0 = -h0;
+        h = h0;
+        return 0;
+    }
+
+    /// Prologue of CVode(tout) in CV_NORMAL mode with tstop = tout, as AMICI drives it
+    PB_HD int cvode_begin(double tout) {
+        tstop = tout;
+        tstopset = true;
+        if (opt.maxsteps <= nst) return SIM_ERROR;
+        mxstep_ = opt.maxsteps - nst;
+        nstloc_ = 0;
+        if (nst == 0) {
+            if (!ewt_set()) return SIM_ILL_INPUT;
+            h = 1.0;
+            const int r = reload_zn1();
+            if (r) return r == cv::RHSFUNC_RECVR ? SIM_FIRST_RHSFUNC_ERR : SIM_FIRST_SRHSFUNC_ERR;
+            if ((tstop - tn) * (tout - tn) <= 0.0) return SIM_ILL_INPUT;
+            const int hr = hin(tout);
+            if (hr != 0) return hr;
+            if ((tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
+            hscale = h;
+            hprime = h;
+            tm.sync();
+            PT_FOR_ELEMS(e) w.zn[1][e] *= h;
+            tm.sync();
+        } else {
+            const double troundoff = cv::FUZZ_FACTOR * cv::UROUND * (fabs(tn) + fabs(h));
+            if (fabs(tn - tstop) <= troundoff) {
+                tstopset = false;
+                tn = tstop;
+                return cv::TSTOP_RETURN;
+            } else if ((tn + hprime - tstop) * h > 0.0) {
+                hprime = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
+                eta = hprime / h;
+            }
+        }
+        return 0;
+    }
+
+    // ---------------------------------------------------------------- likelihood
+    /// One output time: llh and sllh contributions (Model::addObservableObjective /
+    /// addObservableObjectiveSensitivity); the state at the output time is zn[0] of column 0.
+    /// Observables are linear in the state, sigmas are constants (dydp = dsigmaydp = 0).
+    PB_HD bool data_point(const double* my, const double* sd, double* y_out, double* sigmay_out) {
+        tm.sync();
+        const int ny = T.ny;
+        double dJydy[TEAM_MAXNY];
+        bool ok = true;
+        for (int iy = 0; iy < ny; ++iy) {
+            const double y = net::observable(T, iy, w.zn[0]);
+            double sig = T.sigma0[iy];
+            if (!isnan(sd[iy])) sig = sd[iy];
+            if (tm.tid() == 0) {
+                if (y_out) y_out[iy] = y;
+                if (sigmay_out) sigmay_out[iy] = sig;
+            }
+            dJydy[iy] = 0.0;
+            if (isnan(my[iy])) continue;
+            if (!(sig > 0.0) || !PB_FINITE(sig)) { ok = false; continue; }
+            const double s2 = sig * sig;
+            const double r = my[iy] - y;
+            llh_ -= log(s2 * 3.141592653589793 * 2.0) * 0.5 + 1.0 / s2 * (r * r) * 0.5;
+            dJydy[iy] = 1.0 / s2 * (my[iy] * 2.0 - y * 2.0) * -0.5;
+        }
+        if (!ok) return false;
+        if (!sensi) return true;
+        PT_FOR(c, 1, ns + 1) {
+            const double* sx = w.zn[0] + (size_t)c * nx;
+            double a = 0.0;
+            for (int iy = 0; iy < ny; ++iy) {
+                if (dJydy[iy] == 0.0) continue;
+                double d = 0.0;
+                for (int e = T.o_ptr[iy]; e < T.o_ptr[iy + 1]; ++e) d += T.o_w[e] * sx[T.o_idx[e]];
+                a += dJydy[iy] * d;
+            }
+            w.sllh[c] -= a;
+        }
+        return true;
+    }
+
+    // ---------------------------------------------------------------- one simulation
+    /// w.p / w.k / w.plist must be set (and synchronised) by the caller
+    PB_HD void begin(const ConditionIO& io, double rtol, double atol) {
+        io_ = io;
+        opt.rtol = rtol;
+        opt.atol = atol;
+        nx = T.nx;
+        ns = io.ns;
+        ncol = ns + 1;
+        sensi = ns > 0;
+        tm.sync();
+        net::x0(T, tm, w.k, w.zn[0]);
+        PT_FOR(e, nx, nx * ncol) w.zn[0][e] = 0.0;  // sx0 = 0: initial values do not depend on p
+        PT_FOR_ELEMS(e) {
+            for (int j = 1; j < cv::L_MAX; ++j) w.zn[j][e] = 0.0;
+            w.acor[e] = 0.0;
+            w.ewt[e] = 1.0;
+            w.b[e] = 0.0;
+        }
+        PT_FOR(c, 0, ncol) w.sllh[c] = 0.0;
+        for (size_t e = tm.tid(); e < (size_t)nx * T.np; e += tm.size()) w.dfdp[e] = 0.0;
+        for (int j = 0; j < cv::L_MAX; ++j) l[j] = 0.0;
+        for (int i = 0; i <= cv::L_MAX; ++i) tau[i] = 0.0;
+        for (int i = 0; i < 6; ++i)
+            for (int k = 0; k < 4; ++k) ssdat[i][k] = 0.0;
+        tq1 = tq2 = tq3 = tq4 = tq5 = 0.0;
+        tn = opt.t0;
+        q = 1; L = 2; qwait = L; qprime = 1;
+        etamax = cv::ETA_MAX_FS;
+        h = hprime = hscale = 0.0;
+        eta = 1.0; etaq = etaqm1 = etaqp1 = 0.0;
+        gamma = gammap = 0.0; gamrat = 1.0; rl1 = 1.0;
+        crate = crateS = 1.0; delp = 0.0; acnrm = acnrmS = 0.0; saved_tq5 = 0.0;
+        nst = nscon = nstlp = nstlj = 0;
+        convfail = cv::NO_FAILURES;
+        jcur = jcurNLS = jcurNLSS = false;
+        tstopset = false; tstop = 0.0;
+        nfe = nsetups = nje = nni = nniS = nfSe = netf = netfS = ncfn = ncfnS = nor = qsum = 0;
+        llh_ = 0.0;
+        it_ = 0;
+        sim_status_ = SIM_SUCCESS;
+        fail_ = ret_ = 0;
+        tm.sync();
+    }
+
+    /// ForwardProblem::workForwardProblem: output times in order, CVode(tout) with tstop = tout
+    PB_HD int simulate(const ConditionIO& io, double rtol, double atol) {
+        begin(io, rtol, atol);
+        const int ny = T.ny;
+        for (it_ = 0; it_ < io_.nt; ++it_) {
+            tout_ = io_.t[it_];
+            if (isinf(tout_)) break;  // post-equilibration: out of scope
+            bool integrate = (tout_ > opt.t0) && (tn < tout_);
+            if (integrate) {  // is_next_t_too_close
+                const double tdiff = tout_ - tn;
+                if (fabs(tdiff) < 2.0 * cv::UROUND * fmax(fabs(tn), fabs(tout_))) integrate = false;
+            }
+            if (integrate) {
+                int r = cvode_begin(tout_);
+                if (r < 0) return finish(r);
+                while (r != cv::TSTOP_RETURN) {
+                    // top of the CVode step loop
+                    if (nst > 0 && !ewt_set()) return finish(SIM_ILL_INPUT);
+                    if (nstloc_ >= mxstep_) return finish(SIM_TOO_MUCH_WORK);
+                    const double nrm = wnorm1(0, errtest_cmax(), w.zn[0]);
+                    if (cv::UROUND * nrm > 1.0) return finish(SIM_TOO_MUCH_ACC);
+                    step_begin();
+                    for (;;) {
+                        int a = attempt_predict();
+                        if (a < 0) return finish(a);
+                        attempt_correct(PH_STATE);
+                        attempt_correct(PH_SENS);
+                        a = attempt_finish();
+                        if (a < 0) return finish(a);
+                        if (a == 0) break;
+                    }
+                    nstloc_++;
+                    const double troundoff = cv::FUZZ_FACTOR * cv::UROUND * (fabs(tn) + fabs(h));
+                    if (fabs(tn - tstop) <= troundoff) {
+                        tn = tstop;
+                        tstopset = false;
+                        break;
+                    }
+                    if ((tn + hprime - tstop) * h > 0.0) {
+                        hprime = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
+                        eta = hprime / h;
+                    }
+                    if ((tn - tout_) * h >= 0.0) break;
+                }
+            }
+#if defined(PB200_HOST_TRACE)
+            if (io_.trace) { io_.trace[2 * it_] = nst; io_.trace[2 * it_ + 1] = q; }
+#endif
+            double* yo = io_.y_out ? io_.y_out + (size_t)it_ * ny : nullptr;
+            double* so = io_.sigmay_out ? io_.sigmay_out + (size_t)it_ * ny : nullptr;
+            if (!data_point(io_.my + (size_t)it_ * ny, io_.sd + (size_t)it_ * ny, yo, so)) return finish(SIM_ERROR);
+        }
+        return finish(SIM_SUCCESS);
+    }
+
+    PB_HD int finish(int status) {
+        sim_status_ = status;
+        if (status != SIM_SUCCESS) llh_ = NAN;
+        tm.sync();
+        return status;
+    }
+    PB_HD int status() const { return sim_status_; }
+    PB_HD double llh() const { return llh_; }
+
+    PB_HD void export_stats(int64_t* s, int trials) const {
+        s[STAT_NST] = nst; s[STAT_NFE] = nfe; s[STAT_NSETUPS] = nsetups; s[STAT_NJE] = nje;
+        s[STAT_NNI] = nni; s[STAT_NNIS] = nniS; s[STAT_NFSE] = nfSe; s[STAT_NETF] = netf;
+        s[STAT_NETFS] = netfS; s[STAT_NCFN] = ncfn; s[STAT_NCFNS] = ncfnS; s[STAT_NOR] = nor;
+        s[STAT_TRIALS] = trials; s[STAT_QSUM] = qsum; s[14] = 0; s[15] = 0;
+    }
+#undef PT_FOR
+#undef PT_FOR_ELEMS
+};
+
+}  // namespace pb200
+#endif
