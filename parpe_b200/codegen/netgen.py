@@ -220,4 +220,9 @@ def emit_tables_header(s: NetworkSpec, path: str) -> None:
 
 
 def generate(spec: NetworkSpec, repo_root: str) -> None:
-    emit_tables_header(spec, os.path.join(repo_root, "parpe_b200", "csrc", "models", "net_%s.h" % spec.name))
+    mdir = os.path.join(repo_root, "parpe_b200", "csrc", "models")
+    emit_tables_header(spec, os.path.join(mdir, "net_%s.h" % spec.name))
+    with open(os.path.join(mdir, "inst_net_%s.cu" % spec.name), "w") as fh:
+        fh.write("// GENERATED by parpe_b200/codegen/netgen.py -- team-kernel registration for network model %s.\n"
+                 "#include \"../team_kernels.cuh\"\n#include \"net_%s.h\"\nPB200_REGISTER_NET(%s)\n"
+                 % (spec.name, spec.name, spec.name))

@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include <cstdlib>
+#include <string>
 #include <type_traits>
 
 #include "bdf_core.cuh"
@@ -258,7 +259,11 @@ struct ModelOps {
     int flops_xdot, flops_J, flops_dxdotdp, nnzJ;
     // launches simulate_kernel; lanes: requested G (0 = default); returns cudaError_t as int
     int (*launch)(const KernelArgs& a, int lanes, int variant, int sm_count, cudaStream_t stream, int* lanes_used,
-                  int* grid_used, int* block_used);
+                  int* grid_used, int* block_used, void* state);
+    // optional per-handle device state (large-model path: device copy of the model tables + the
+    // teams' HBM workspace); null for the small-model kernels
+    void* (*create_state)(int sm_count, std::string* err);
+    void (*destroy_state)(void* state);
 };
 
 void register_model(const ModelOps& ops);
@@ -326,7 +331,7 @@ int launch_shape(const KernelArgs& a, int variant, int sm_count, cudaStream_t st
 /// column groups).  Cost-only evaluations use the same kernels with the state column alone.
 template <class M>
 int launch_model(const KernelArgs& a, int lanes, int variant, int sm_count, cudaStream_t stream, int* lanes_used,
-                 int* grid_used, int* block_used) {
+                 int* grid_used, int* block_used, void* /*state*/) {
     constexpr int GN = pb_pow2_at_least(M::NX);
     constexpr int GH = GN >= 4 ? GN / 2 : GN;
     constexpr int G2 = GN * 2 <= 32 ? GN * 2 : GN;
@@ -346,6 +351,8 @@ ModelOps make_ops() {
     o.default_lanes = pb_pow2_at_least(M::NX);
     o.flops_xdot = M::FLOPS_XDOT; o.flops_J = M::FLOPS_J; o.flops_dxdotdp = M::FLOPS_DXDOTDP; o.nnzJ = M::NNZ;
     o.launch = &launch_model<M>;
+    o.create_state = nullptr;
+    o.destroy_state = nullptr;
     return o;
 }
 

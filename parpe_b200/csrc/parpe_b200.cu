@@ -140,6 +140,8 @@ struct pb200_handle {
     bool staged_pending = false;
     // hierarchical
     HierDevice* hier = nullptr;
+    // large-model path: device tables + workspace (ModelOps::create_state)
+    void* model_state = nullptr;
 };
 
 static int ensure_capacity(pb200_handle* h, int n) {
@@ -216,7 +218,8 @@ static int enqueue_evaluation(pb200_handle* h, const double* theta, const int* i
     PB_CUDA(cudaEventRecord(h->ev_start, stream));
     if (n > 0) {
         static const int variant = std::getenv("PB200_KERNEL_VARIANT") ? std::atoi(std::getenv("PB200_KERNEL_VARIANT")) : 2;
-        int e = h->ops->launch(a, h->lanes, variant, h->sm_count, stream, &h->last_lanes, &h->last_grid, &h->last_block);
+        int e = h->ops->launch(a, h->lanes, variant, h->sm_count, stream, &h->last_lanes, &h->last_grid, &h->last_block,
+                               h->model_state);
         if (e != 0) return fail(PB200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)e));
     }
     reduce_kernel<256><<<1 + h->n_opt, 256, 0, stream>>>(a, d_out);
@@ -364,6 +367,11 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
     a.num_trials = d->num_trials > 0 ? d->num_trials : 1;
     a.relaxation_factor = d->relaxation_factor;
     if (int rc = ensure_capacity(h, C > 0 ? C : 1)) return rc;
+    if (ops->create_state) {
+        std::string err;
+        h->model_state = ops->create_state(h->sm_count, &err);
+        if (!h->model_state) return fail(PB200_ERR_CUDA, "model state: " + err);
+    }
     guard.release();
     *out = h;
     return 0;
@@ -374,6 +382,7 @@ void pb200_destroy(pb200_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     hier_destroy(h->hier);
+    if (h->model_state && h->ops && h->ops->destroy_state) h->ops->destroy_state(h->model_state);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_stop) cudaEventDestroy(h->ev_stop);
     if (h->ev_staged) cudaEventDestroy(h->ev_staged);

@@ -1,0 +1,228 @@
+// team_kernels.cuh -- the large-model path: one thread block (team) per experimental
+// condition, persistent CTAs with an in-kernel work queue (the same scheduler as
+// simulate_kernel: SURVEY.md rows A2-A4, A8-A14, for BASELINE configs 3-4).  The model is a
+// table-driven mass-action network (net_model.cuh) resident in HBM; the integrator is
+// bdf_team.cuh; the per-team working set lives in an HBM workspace owned by the handle.
+#ifndef PB200_TEAM_KERNELS_CUH
+#define PB200_TEAM_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "bdf_team.cuh"
+#include "kernels.cuh"
+
+namespace pb200 {
+
+constexpr int TEAM_THREADS = 512;
+
+/// shared-memory layout (doubles): reduction scratch | rowk | piv | rbuf | panel
+constexpr int TEAM_SM_RED = 0, TEAM_SM_ROWK = 64, TEAM_SM_PIV = 96, TEAM_SM_RBUF = 112,
+              TEAM_SM_PANEL = TEAM_SM_RBUF + TEAM_RBUF;
+
+template <int TEAM_THREADS_>
+__global__ void __launch_bounds__(TEAM_THREADS_, 1)
+simulate_team_kernel(const KernelArgs a, const NetTables T, double* __restrict__ workspace, size_t ws_stride, int NB) {
+    extern __shared__ __align__(16) double pb_team_smem[];
+    __shared__ int s_pos;
+    CtaTeam tm(pb_team_smem + TEAM_SM_RED);
+    BdfTeam<CtaTeam> bdf(tm);
+    bdf.T = T;
+    bdf.opt = a.opt;
+    bdf.w.carve(workspace + (size_t)blockIdx.x * ws_stride, T);
+    bdf.w.rowk = pb_team_smem + TEAM_SM_ROWK;
+    bdf.w.piv = reinterpret_cast<int*>(pb_team_smem + TEAM_SM_PIV);
+    bdf.w.rbuf = pb_team_smem + TEAM_SM_RBUF;
+    bdf.w.panel = pb_team_smem + TEAM_SM_PANEL;
+    bdf.w.NB = NB;
+    const int tid = threadIdx.x;
+    const int np = T.np;
+    for (;;) {
+        if (tid == 0) s_pos = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int pos = s_pos;
+        __syncthreads();
+        if (pos >= a.n) break;
+        const int r = a.order ? a.order[pos] : pos;
+        const int c = a.idx[r];
+        const size_t cp = (size_t)c * np;
+        // A5: optimisation -> simulation parameters (integer gather from the host-computed table)
+        for (int i = tid; i < np; i += TEAM_THREADS) {
+            const int j = a.mapping[cp + i];
+            double pu;
+            if (j >= 0) pu = a.theta_tab[((size_t)j * 3 + a.pscale_sim[cp + i]) * 2 + 1];
+            else if (a.ov_unscaled) pu = a.ov_unscaled[cp + i];
+            else pu = NAN;
+            bdf.w.p[i] = pu;
+            bdf.w.plist[i] = a.plist[cp + i];
+        }
+        for (int i = tid; i < T.nk; i += TEAM_THREADS) bdf.w.k[i] = a.k[(size_t)c * T.nk + i];
+        __syncthreads();
+        ConditionIO io;
+        const int64_t t0off = a.t_offsets[c];
+        io.nt = (int)(a.t_offsets[c + 1] - t0off);
+        io.t = a.t + t0off;
+        io.my = a.my + t0off * T.ny;
+        io.sd = a.sd + t0off * T.ny;
+        io.ns = a.want_grad ? a.nplist[c] : 0;
+        io.y_out = a.y_out ? a.y_out + t0off * T.ny : nullptr;
+        io.sigmay_out = a.sigmay_out ? a.sigmay_out + t0off * T.ny : nullptr;
+        // A8: runAndLogSimulation retries at relaxed tolerances
+        int trial = 1, status;
+        double relax = 1.0;
+        for (;;) {
+            status = bdf.simulate(io, a.opt.rtol * relax, a.opt.atol * relax);
+            if (status == SIM_SUCCESS || trial >= a.num_trials) break;
+            relax *= a.relaxation_factor;
+            ++trial;
+        }
+        // outputs: A7 result package + A6 chain rule to the optimiser scale
+        if (tid == 0) {
+            a.llh[r] = bdf.llh();
+            a.status[r] = status;
+            bdf.export_stats(a.stats + (size_t)r * NSTATS, trial);
+        }
+        if (a.want_grad) {
+            for (int i = tid; i < np; i += TEAM_THREADS) {
+                a.gcontrib[(size_t)r * np + i] = 0.0;
+                a.sllh[(size_t)r * np + i] = 0.0;
+            }
+            __syncthreads();
+            for (int col = 1 + tid; col <= io.ns; col += TEAM_THREADS) {
+                const int ip = bdf.w.plist[col - 1];
+                const int ssim = a.pscale_sim[cp + ip];
+                const int jopt = a.mapping[cp + ip];
+                const double pu = bdf.w.p[ip];
+                double s = bdf.w.sllh[col];  // ReturnData::applyChainRuleFactorToSimulationResults
+                if (ssim == 2) s *= pu * PB_LN10;
+                else if (ssim == 1) s *= pu;
+                a.sllh[(size_t)r * np + (col - 1)] = s;
+                const int sopt = a.pscale_opt[jopt];  // applyChainRule, coefficient -1
+                double gr = s;
+                if (ssim != sopt) {
+                    if (ssim == 2) gr /= pu * PB_LN10;
+                    else if (ssim == 1) gr /= pu;
+                    if (sopt == 2) gr *= pu * PB_LN10;
+                    else if (sopt == 1) gr *= pu;
+                }
+                a.gcontrib[(size_t)r * np + ip] = -1.0 * gr;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+/// Device copy of a network's tables + the teams' HBM workspace (owned by the handle).
+struct TeamState {
+    NetTables dev{};
+    std::vector<void*> allocs;
+    double* workspace = nullptr;
+    size_t ws_stride = 0;
+    int grid_cap = 0;
+    int NB = 0;
+    size_t smem = 0;
+};
+
+template <class V>
+static cudaError_t team_upload(TeamState* st, const V* src, size_t n, const V** dst) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (n > 0 ? n : 1) * sizeof(V));
+    if (e != cudaSuccess) return e;
+    st->allocs.push_back(p);
+    if (n > 0) e = cudaMemcpy(p, src, n * sizeof(V), cudaMemcpyHostToDevice);
+    *dst = static_cast<const V*>(p);
+    return e;
+}
+
+inline void team_destroy_state(void* s) {
+    auto* st = static_cast<TeamState*>(s);
+    if (!st) return;
+    for (void* p : st->allocs) cudaFree(p);
+    if (st->workspace) cudaFree(st->workspace);
+    delete st;
+}
+
+inline void* team_create_state(const NetTables& H, int sm_count, std::string* err) {
+    auto* st = new TeamState;
+    auto fail = [&](cudaError_t e) -> void* {
+        if (err) *err = cudaGetErrorString(e);
+        team_destroy_state(st);
+        return nullptr;
+    };
+    if (H.ny > TEAM_MAXNY) {
+        if (err) *err = "too many observables for the team kernel";
+        delete st;
+        return nullptr;
+    }
+    st->dev = H;
+    cudaError_t e;
+#define UP(field, n) if ((e = team_upload(st, H.field, (size_t)(n), &st->dev.field)) != cudaSuccess) return fail(e)
+    UP(r_a, H.nr); UP(r_b, H.nr); UP(kappa, H.nr); UP(pidx, H.nr);
+    UP(s_ptr, H.nx + 1); UP(s_reac, H.n_s); UP(s_coef, H.n_s);
+    UP(j_ptr, H.nx + 1); UP(j_col, H.nnz); UP(jt_ptr, H.nnz + 1); UP(jt_reac, H.n_jt); UP(jt_other, H.n_jt); UP(jt_coef, H.n_jt);
+    UP(csc_ptr, H.nx + 1); UP(csc_row, H.nnz); UP(csc_from_csr, H.nnz);
+    UP(x0_base, H.nx); UP(x0_kidx, H.nx); UP(o_ptr, H.ny + 1); UP(o_idx, H.n_o); UP(o_w, H.n_o); UP(sigma0, H.ny);
+#undef UP
+    // staging memory: as wide a panel as fits the SM's shared memory next to the fixed buffers
+    const size_t max_smem = 227u * 1024u;
+    const size_t panel_doubles = (max_smem - (size_t)TEAM_SM_PANEL * sizeof(double)) / sizeof(double);
+    st->NB = TeamWork::panel_width(H.nx, panel_doubles);
+    st->smem = ((size_t)TEAM_SM_PANEL + (size_t)H.nx * st->NB) * sizeof(double);
+    if ((size_t)H.nx * st->NB > panel_doubles) {
+        if (err) *err = "model too large for the team kernel's shared-memory panel";
+        team_destroy_state(st);
+        return nullptr;
+    }
+    e = cudaFuncSetAttribute(simulate_team_kernel<TEAM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem);
+    if (e != cudaSuccess) return fail(e);
+    st->ws_stride = TeamWork::hbm_doubles(H);
+    st->grid_cap = sm_count;
+    e = cudaMalloc((void**)&st->workspace, st->ws_stride * sizeof(double) * (size_t)st->grid_cap);
+    if (e != cudaSuccess) return fail(e);
+    return st;
+}
+
+inline int team_launch(const KernelArgs& a, void* state, cudaStream_t stream, int* lanes_used, int* grid_used,
+                       int* block_used) {
+    auto* st = static_cast<TeamState*>(state);
+    if (!st) return (int)cudaErrorInvalidValue;
+    int grid = st->grid_cap;  // persistent: one team per SM, work queue inside
+    if (grid > a.n) grid = a.n;
+    if (grid < 1) grid = 1;
+    simulate_team_kernel<TEAM_THREADS><<<grid, TEAM_THREADS, st->smem, stream>>>(a, st->dev, st->workspace, st->ws_stride, st->NB);
+    if (lanes_used) *lanes_used = TEAM_THREADS;
+    if (grid_used) *grid_used = grid;
+    if (block_used) *block_used = TEAM_THREADS;
+    return (int)cudaGetLastError();
+}
+
+#define PB200_REGISTER_NET(NAME)                                                                              \
+    namespace {                                                                                               \
+    void* create_##NAME(int sm_count, std::string* err) {                                                     \
+        return pb200::team_create_state(pb200::nets::NAME::tables(), sm_count, err);                          \
+    }                                                                                                         \
+    int launch_##NAME(const pb200::KernelArgs& a, int, int, int, cudaStream_t stream, int* lanes_used,        \
+                      int* grid_used, int* block_used, void* state) {                                         \
+        return pb200::team_launch(a, state, stream, lanes_used, grid_used, block_used);                       \
+    }                                                                                                         \
+    struct RegNet_##NAME {                                                                                    \
+        RegNet_##NAME() {                                                                                     \
+            const pb200::NetTables T = pb200::nets::NAME::tables();                                           \
+            pb200::ModelOps o{};                                                                              \
+            o.name = T.name;                                                                                  \
+            o.nx = T.nx; o.np = T.np; o.nk = T.nk; o.ny = T.ny;                                               \
+            o.default_lanes = pb200::TEAM_THREADS;                                                            \
+            o.flops_xdot = T.flops_xdot; o.flops_J = T.flops_J; o.flops_dxdotdp = T.flops_dxdotdp;            \
+            o.nnzJ = T.nnz;                                                                                   \
+            o.launch = &launch_##NAME;                                                                        \
+            o.create_state = &create_##NAME;                                                                  \
+            o.destroy_state = &pb200::team_destroy_state;                                                     \
+            pb200::register_model(o);                                                                         \
+        }                                                                                                     \
+    } reg_net_instance_##NAME;                                                                                \
+    }
+
+}  // namespace pb200
+#endif
