@@ -33,12 +33,21 @@ import numpy as np  # noqa: E402
 
 METRIC = "forward-sensitivity ODE solves/sec per obj+grad eval"
 UNIT = "solves/s"
-MODEL = "boehm"
+MODEL = "boehm"   # --workload: boehm (the metric's configuration, default) | chen | froehlich | net32 | fujita ...
+DEFAULT_CONDITIONS = {"chen": 296, "froehlich": 148, "net32": 4736}
 CONDITIONS_PER_GPU = int(os.environ.get("PB200_BENCH_CONDITIONS", 16384))
+LARGE_MODELS = ("chen", "froehlich", "net32")
 CPU_SAMPLE_SECONDS = float(os.environ.get("PB200_BENCH_CPU_SECONDS", 15.0))
 
 
 def workload_name(n_gpus):
+    if MODEL != "boehm":
+        from parpe_b200.models import get_spec
+        sp = get_spec(MODEL)
+        shape = {"chen": "Chen_MSB2009-shape", "froehlich": "Froehlich_CellSystems2018-shape"}.get(MODEL, MODEL)
+        return ("%s generated mass-action network (nx=%d, np=%d, ny=%d, nt=8), forward sensitivities, obj+grad, "
+                "%d conditions/GPU x %d GPU" % (shape, sp.nx, sp.np, sp.ny, CONDITIONS_PER_GPU, n_gpus)
+                if MODEL in LARGE_MODELS else "%s, %d conditions/GPU x %d GPU" % (MODEL, CONDITIONS_PER_GPU, n_gpus))
     return ("Boehm_JProteomeRes2014-shape (nx=8, np=9, ny=3, nt=16), forward sensitivities, obj+grad, "
             "%d conditions/GPU x %d GPU" % (CONDITIONS_PER_GPU, n_gpus))
 
@@ -130,7 +139,21 @@ def algorithmic_bytes(tab, n, want_grad=True):
 def model_op_counts():
     from parpe_b200.codegen.modelgen import count_flops, derive
     from parpe_b200.models import get_spec
+    if MODEL in LARGE_MODELS:
+        return get_spec(MODEL).flops()
     return count_flops(derive(get_spec(MODEL)))
+
+
+def algorithmic_bytes_large(stats, nx, nplist, nnz, tab, n):
+    """Large-nx regime (state not cache-resident), SURVEY.md 8(d):
+    B = 8*[nst*(1+nplist)*nx*(2(q+1) + 2(q+1) + 6) + (nni + nniS)*nx^2 + nsetups*2*nx^2 + nje*nnzJ]
+        + inputs + outputs."""
+    from parpe_b200.tables import STAT_NAMES
+    s = {nm: stats[:, i].astype(np.float64) for i, nm in enumerate(STAT_NAMES)}
+    q = np.where(s["nst"] > 0, s["qsum"] / np.maximum(s["nst"], 1), 1.0)
+    B = 8.0 * (s["nst"] * (1 + nplist) * nx * (4 * (q + 1) + 6) + (s["nni"] + s["nniS"]) * nx ** 2
+               + s["nsetups"] * 2 * nx ** 2 + s["nje"] * nnz)
+    return float(np.sum(B)) + algorithmic_bytes(tab, n)
 
 
 def cpu_baseline(tab, theta, seconds=CPU_SAMPLE_SECONDS, nthreads=0):
@@ -141,7 +164,7 @@ def cpu_baseline(tab, theta, seconds=CPU_SAMPLE_SECONDS, nthreads=0):
         return None
     ncores = os.cpu_count() or 1
     o = ob.OracleProblem(tab, ob.ISM_STAGGERED, ob.LINSOL_KLU)
-    n0 = min(tab.n_conditions, 8 * ncores)
+    n0 = min(tab.n_conditions, (1 if MODEL in LARGE_MODELS else 8) * ncores)
     t0 = time.perf_counter()
     o.evaluate(theta, idx=np.arange(n0, dtype=np.int32), nthreads=nthreads)
     dt = time.perf_counter() - t0
@@ -168,7 +191,7 @@ def run_reference(args):
     ncores = os.cpu_count() or 1
     o = ob.OracleProblem(tab, ob.ISM_STAGGERED, ob.LINSOL_KLU)
     # bounded sample per step: sized from a probe so that the whole run ends within minutes
-    n0 = min(tab.n_conditions, 8 * ncores)
+    n0 = min(tab.n_conditions, (1 if MODEL in LARGE_MODELS else 8) * ncores)
     t0 = time.perf_counter()
     o.evaluate(theta, idx=np.arange(n0, dtype=np.int32))
     rate = n0 / (time.perf_counter() - t0)
@@ -204,7 +227,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lanes", type=int, default=0, help="lanes per condition (0 = model default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="boehm",
+                    help="boehm = the configuration the metric is quoted on (default); chen / froehlich = the "
+                         "large-model path (one CTA per condition), reported for DESIGN.md, not the driver's line")
     args = ap.parse_args()
+    global MODEL, CONDITIONS_PER_GPU
+    MODEL = args.workload
+    if "PB200_BENCH_CONDITIONS" not in os.environ:
+        CONDITIONS_PER_GPU = DEFAULT_CONDITIONS.get(MODEL, CONDITIONS_PER_GPU)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -301,7 +331,9 @@ def main():
         res = fun.condition_results()
         lo, hi = capi.partition_bounds(n_total, rank, world)
         ops_info = model_op_counts()
-        flops, mean_stats = algorithmic_flops(res["stats"], ops_info, 8, tab.np_)
+        from parpe_b200.models import get_spec
+        nx_model = get_spec(MODEL).nx
+        flops, mean_stats = algorithmic_flops(res["stats"], ops_info, nx_model, tab.np_)
         kern_avg = float(np.mean(kernel_s)) if kernel_s else total_s / args.steps
         peak_tf = capi.measure_fp64_peak(local_rank)
         peaks = {}
@@ -310,12 +342,16 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        abytes = algorithmic_bytes(tab, hi - lo)
+        if MODEL in LARGE_MODELS:
+            abytes = algorithmic_bytes_large(res["stats"], nx_model, tab.np_, ops_info["nnzJ"], tab, hi - lo)
+        else:
+            abytes = algorithmic_bytes(tab, hi - lo)
         roofline = {
             "bound": "fp64", "achieved": flops / kern_avg / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": flops / kern_avg / 1e12 / peak_tf, "traffic": None,
             "peak_source": "DFMA microbenchmark measured live on this device (MEASURED_PEAKS.json has no FP64 figure)",
-            "kernel": "simulate_kernel<Model_boehm,G=%d>" % fun.last_launch()["lanes"],
+            "kernel": ("simulate_team_kernel<%d> (%s)" % (fun.last_launch()["block"], MODEL)) if MODEL in LARGE_MODELS
+            else "simulate_kernel<Model_%s,G=%d>" % (MODEL, fun.last_launch()["lanes"]),
             "kernel_ms": 1e3 * kern_avg, "algorithmic_flops_per_launch": flops,
             "hbm": {"achieved": abytes / kern_avg / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": abytes / kern_avg / 1e9 / hbm_peak,

@@ -42,19 +42,44 @@ constexpr int TEAM_CW = 64;         // columns per chunk of the rank-NB update
 constexpr int TEAM_RBUF = TEAM_NB_MAX * TEAM_CW;  // doubles in the broadcast tile
 constexpr int TEAM_TN = 26;         // right-hand-side columns per pass of the solve GEMM
 constexpr int TEAM_MAXNY = 16;
+/// shared-memory layout of the team kernel (doubles): reduction scratch | pivot row | displaced row |
+/// pivots | row-permutation lists | two broadcast tiles (double buffered) | panel (generic path only)
+constexpr int TEAM_SM_RED = 0, TEAM_SM_ROWK = 64, TEAM_SM_XBUF2 = 96, TEAM_SM_PIV = 128, TEAM_SM_TL = 144,
+              TEAM_SM_NT = 208, TEAM_SM_RBUF = 224, TEAM_SM_RBUF1 = TEAM_SM_RBUF + TEAM_RBUF,
+              TEAM_SM_PANEL = TEAM_SM_RBUF1 + TEAM_RBUF;
+/// rows path (nx <= 512): ring of matrix elements in flight (cp.async), TEAM_ST stages of TEAM_GC
+/// columns x 512 rows; aliases the panel of the generic path (a launch uses one of the two)
+constexpr int TEAM_GC = 8, TEAM_ST = 4, TEAM_SM_XSTAGE = TEAM_SM_PANEL,
+              TEAM_SM_ROWS_END = TEAM_SM_XSTAGE + TEAM_ST * TEAM_GC * 512;
+
+#if defined(__CUDA_ARCH__)
+/// 8-byte asynchronous global -> shared copy (LDGSTS); nbytes = 0 writes zeros without reading
+__device__ __forceinline__ void pb_cp_async8(double* smem_dst, const double* gsrc, int nbytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void pb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void pb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
 
 /// Per-team working set: pointers into the team's slice of the HBM workspace plus the staging
 /// buffers (shared memory on the device).
 struct TeamWork {
-    double* zn[cv::L_MAX];
+    double* znbase;  // Nordsieck history zn[0..5], each nxc doubles
+    size_t nxc;
     double *acor, *ewt, *b, *scr;
     double *dfdp, *A, *Jsaved, *Jcur, *ysh, *yj, *fout, *vb, *v, *p, *k, *sllh;
     int *plist, *perm;
+    // staging buffers: host harness only -- on the device they are derived from the dynamic
+    // shared memory base at every use (BdfTeam::panel() ...), so that the compiler knows the
+    // address space (LDS/STS instead of generic LD/ST)
     double* panel;  // nx * NB
     double* rbuf;   // TEAM_RBUF
     double* rowk;   // TEAM_NB_MAX
     int* piv;       // TEAM_NB_MAX
     int NB;
+    PB_HD double* zn(int j) const { return znbase + (size_t)j * nxc; }
 
     /// doubles of HBM workspace one team needs
     static size_t hbm_doubles(const NetTables& T) {
@@ -67,7 +92,8 @@ struct TeamWork {
     PB_HD void carve(double* base, const NetTables& T) {
         const size_t nxc = (size_t)T.nx * (T.np + 1);
         double* q = base;
-        for (int j = 0; j < cv::L_MAX; ++j) { zn[j] = q; q += nxc; }
+        znbase = q; q += cv::L_MAX * nxc;
+        this->nxc = nxc;
         acor = q; q += nxc;
         ewt = q; q += nxc;
         b = q; q += nxc;
@@ -118,10 +144,47 @@ struct BdfTeam {
     int it_, sim_status_, nstloc_, mxstep_, ncf_, nef_, ncfS_, nefS_, nflag_, dq_;
     bool do_rescale_, undo_, restart_;
     int fail_, ret_;
+    // phase cycle counters (device: clock64 of thread 0's SM; exported in stats[14..15] packed as
+    // two 32-bit fields of kilo-cycles each: [14] = inversion panel | inversion update, [15] = solve GEMM | model+rhs)
+    long long cyc_panel, cyc_update, cyc_solve, cyc_rhs;
+    PB_HD static long long now() {
+#if defined(__CUDA_ARCH__)
+        return clock64();
+#else
+        return 0;
+#endif
+    }
 
     PB_HD explicit BdfTeam(const Team& t) : tm(t) {}
 
-#define PT_FOR(e, e0, e1) for (int e = (e0) + tm.tid(); e < (e1); e += tm.size())
+    // staging buffers: shared memory on the device (layout: TEAM_SM_* below), plain arrays on the host
+#if defined(__CUDA_ARCH__)
+    __device__ __forceinline__ double* smem_base() const {
+        extern __shared__ __align__(16) double pb_team_smem[];
+        return pb_team_smem;
+    }
+    __device__ __forceinline__ double* rowk() const { return smem_base() + TEAM_SM_ROWK; }
+    __device__ __forceinline__ int* piv() const { return reinterpret_cast<int*>(smem_base() + TEAM_SM_PIV); }
+    __device__ __forceinline__ double* rbuf() const { return smem_base() + TEAM_SM_RBUF; }
+    __device__ __forceinline__ double* panel() const { return smem_base() + TEAM_SM_PANEL; }
+#else
+    double* rowk() const { return w.rowk; }
+    int* piv() const { return w.piv; }
+    double* rbuf() const { return w.rbuf; }
+    double* panel() const { return w.panel; }
+#endif
+
+// Team-wide strided sweeps.  Every sweep streams from HBM/L2 with ~50 elements per thread, so what
+// matters is the number of independent loads in flight: loops whose stores go to another array
+// than their loads use __restrict__ pointers and are unrolled by 4 (PT_FOR); in-place updates load
+// a batch of PT_U elements into registers before the first store (PT_FOR_BATCH).
+#if defined(__CUDA_ARCH__)
+#define PT_UNROLL4 _Pragma("unroll 4")
+#else
+#define PT_UNROLL4
+#endif
+#define PT_FOR(e, e0, e1) PT_UNROLL4 for (int e = (e0) + tm.tid(); e < (e1); e += tm.size())
+#define PT_FOR_BATCH(eb, e0, e1, U) for (int eb = (e0) + tm.tid(); eb < (e1); eb += (U) * tm.size())
 #define PT_FOR_ELEMS(e) PT_FOR(e, 0, nx * ncol)
 
     PB_HD int phase_cmin(int phase) const { return phase == PH_STATE ? 0 : 1; }
@@ -145,6 +208,7 @@ struct BdfTeam {
             double loc = 0.0;
             for (int c = cmin + tm.warp(); c <= cmax; c += tm.nwarps()) {
                 double s = 0.0;
+                PT_UNROLL4
                 for (int i = tm.lane(); i < nx; i += Team::WARP) {
                     const int e = c * nx + i;
                     const double v = (B ? ca * A[e] + cb * B[e] : ca * A[e]) * w.ewt[e];
@@ -163,10 +227,12 @@ struct BdfTeam {
     PB_HD bool ewt_set() {
         bool ok = true;
         tm.sync();
+        const double* __restrict__ z0 = w.zn(0);
+        double* __restrict__ ew = w.ewt;
         PT_FOR_ELEMS(e) {
-            const double wv = opt.rtol * fabs(w.zn[0][e]) + opt.atol;
+            const double wv = opt.rtol * fabs(z0[e]) + opt.atol;
             ok = ok && (wv > 0.0);
-            w.ewt[e] = 1.0 / wv;
+            ew[e] = 1.0 / wv;
         }
         return !tm.any(!ok);
     }
@@ -196,36 +262,50 @@ struct BdfTeam {
     /// b = raw ? F : rl1*zn[1] + acor - gamma*F  (cvNlsResidual / cvNlsResidualSensStg)
     PB_HD int rhs(int phase, bool raw) {
         bool bad = false;
+        const long long t_r0 = now();
         tm.sync();
         if (phase == PH_STATE) {
-            PT_FOR(i, 0, nx) w.yj[i] = w.zn[0][i] + w.acor[i];
+            PT_FOR(i, 0, nx) w.yj[i] = w.zn(0)[i] + w.acor[i];
             bad = !eval_xdot();
             PT_FOR(i, 0, nx) {
                 const double F = w.fout[i];
-                w.b[i] = raw ? F : (rl1 * w.zn[1][i] + w.acor[i]) - gamma * F;
+                w.b[i] = raw ? F : (rl1 * w.zn(1)[i] + w.acor[i]) - gamma * F;
             }
         } else {
-            PT_FOR(e, nx, nx * ncol) w.scr[e] = w.zn[0][e] + w.acor[e];
+            const double* __restrict__ z0 = w.zn(0);
+            const double* __restrict__ z1 = w.zn(1);
+            const double* __restrict__ ac = w.acor;
+            const double* __restrict__ jc = w.Jcur;
+            const double* __restrict__ dfdp = w.dfdp;
+            {
+                double* __restrict__ sc = w.scr;
+                PT_FOR(e, nx, nx * ncol) sc[e] = z0[e] + ac[e];
+            }
             tm.sync();
+            const double* __restrict__ sc = w.scr;
+            double* __restrict__ bb = w.b;
             PT_FOR(e, nx, nx * ncol) {
                 const int c = e / nx, i = e - c * nx;
-                const double* s = w.scr + (size_t)c * nx;
-                double F = w.dfdp[i + (size_t)w.plist[c - 1] * nx];
-                for (int kk = T.j_ptr[i]; kk < T.j_ptr[i + 1]; ++kk) F += w.Jcur[kk] * s[T.j_col[kk]];
+                const double* s = sc + (size_t)c * nx;
+                double F = dfdp[i + (size_t)w.plist[c - 1] * nx];
+                const int k1 = T.j_ptr[i + 1];
+                PT_UNROLL4
+                for (int kk = T.j_ptr[i]; kk < k1; ++kk) F += jc[kk] * s[T.j_col[kk]];
                 if (!PB_FINITE(F)) bad = true;
-                w.b[e] = raw ? F : (rl1 * w.zn[1][e] + w.acor[e]) - gamma * F;
+                bb[e] = raw ? F : (rl1 * z1[e] + ac[e]) - gamma * F;
             }
             nfSe += ns;
             bad = tm.any(bad);
         }
         tm.sync();
+        cyc_rhs += now() - t_r0;
         if (bad) return phase == PH_STATE ? cv::RHSFUNC_RECVR : cv::SRHSFUNC_RECVR;
         return 0;
     }
 
     PB_HD void publish_state() {
         tm.sync();
-        PT_FOR(i, 0, nx) w.ysh[i] = w.zn[0][i] + w.acor[i];
+        PT_FOR(i, 0, nx) w.ysh[i] = w.zn(0)[i] + w.acor[i];
         tm.sync();
     }
 
@@ -255,15 +335,19 @@ struct BdfTeam {
             }
         }
         tm.sync();
+#if defined(__CUDA_ARCH__)
+        if (nx <= tm.size()) return invert_rows();
+#endif
         for (int k0 = 0; k0 < nx; k0 += NB) {
             const int nb = (nx - k0 < NB) ? nx - k0 : NB;
             // 1. panel -> staging memory
-            PT_FOR(e, 0, nx * nb) w.panel[e] = A[(size_t)k0 * nx + e];
+            const long long t_p0 = now();
+            PT_FOR(e, 0, nx * nb) panel()[e] = A[(size_t)k0 * nx + e];
             tm.sync();
             // 2. Gauss-Jordan on the panel columns
             for (int kk = 0; kk < nb; ++kk) {
                 const int k = k0 + kk;
-                double* const colk = w.panel + (size_t)kk * nx;
+                double* const colk = panel() + (size_t)kk * nx;
                 double best = -1.0;
                 int bi = 0x7fffffff;
                 for (int i = k + tm.tid(); i < nx; i += tm.size()) {
@@ -275,39 +359,41 @@ struct BdfTeam {
                 const int lp = bi;
                 if (lp != k) {
                     PT_FOR(c, 0, nb) {
-                        double* col = w.panel + (size_t)c * nx;
+                        double* col = panel() + (size_t)c * nx;
                         const double t_ = col[lp];
                         col[lp] = col[k];
                         col[k] = t_;
                     }
                 }
                 if (tm.tid() == 0) {
-                    w.piv[kk] = lp;
+                    piv()[kk] = lp;
                     const int t_ = w.perm[k];
                     w.perm[k] = w.perm[lp];
                     w.perm[lp] = t_;
                 }
                 tm.sync();
                 const double pinv = 1.0 / colk[k];
-                PT_FOR(c, 0, nb) w.rowk[c] = w.panel[k + (size_t)c * nx] * pinv;
+                PT_FOR(c, 0, nb) rowk()[c] = panel()[k + (size_t)c * nx] * pinv;
                 tm.sync();
                 // other panel columns: rank-1 update; column kk itself afterwards
                 PT_FOR(e, 0, nx * nb) {
                     const int c = e / nx, i = e - c * nx;
                     if (c == kk) continue;
-                    if (i == k) w.panel[e] = w.rowk[c];
-                    else w.panel[e] -= colk[i] * w.rowk[c];
+                    if (i == k) panel()[e] = rowk()[c];
+                    else panel()[e] -= colk[i] * rowk()[c];
                 }
                 tm.sync();
                 PT_FOR(i, 0, nx) colk[i] = (i == k) ? pinv : -colk[i] * pinv;
                 tm.sync();
             }
+            const long long t_p1 = now();
+            cyc_panel += t_p1 - t_p0;
             // 3. the row swaps of this block step, applied in order to the other columns
             PT_FOR(j, 0, nx) {
                 if (j >= k0 && j < k0 + nb) continue;
                 double* col = A + (size_t)j * nx;
                 for (int kk = 0; kk < nb; ++kk) {
-                    const int lp = w.piv[kk];
+                    const int lp = piv()[kk];
                     if (lp != k0 + kk) {
                         const double t_ = col[lp];
                         col[lp] = col[k0 + kk];
@@ -320,34 +406,346 @@ struct BdfTeam {
             //    with W = panel (this thread's row in registers) and R = the old pivot rows of A
             for (int j0 = 0; j0 < nx; j0 += TEAM_CW) {
                 const int cw = (nx - j0 < TEAM_CW) ? nx - j0 : TEAM_CW;
-                PT_FOR(e, 0, TEAM_NB_MAX * cw) {
+                PT_FOR(e, 0, TEAM_NB_MAX * ((cw + 1) & ~1)) {
                     const int jj = e / TEAM_NB_MAX, kk = e - jj * TEAM_NB_MAX;
-                    w.rbuf[e] = (kk < nb) ? A[(k0 + kk) + (size_t)(j0 + jj) * nx] : 0.0;
+                    rbuf()[e] = (kk < nb && jj < cw) ? A[(k0 + kk) + (size_t)(j0 + jj) * nx] : 0.0;
                 }
                 tm.sync();
                 for (int i = tm.tid(); i < nx; i += tm.size()) {
                     double wr[TEAM_NB_MAX];
                     PB_UNROLL
-                    for (int kk = 0; kk < TEAM_NB_MAX; ++kk) wr[kk] = (kk < nb) ? w.panel[i + (size_t)kk * nx] : 0.0;
+                    for (int kk = 0; kk < TEAM_NB_MAX; ++kk) wr[kk] = (kk < nb) ? panel()[i + (size_t)kk * nx] : 0.0;
                     const bool in_block = (i >= k0 && i < k0 + nb);
-                    for (int jj = 0; jj < cw; ++jj) {
+                    // two columns per trip: two independent accumulation chains
+                    for (int jj = 0; jj < cw; jj += 2) {
                         const int j = j0 + jj;
-                        if (j >= k0 && j < k0 + nb) continue;
-                        const double* r = w.rbuf + jj * TEAM_NB_MAX;
-                        double x = in_block ? 0.0 : A[i + (size_t)j * nx];
+                        const bool do0 = !(j >= k0 && j < k0 + nb);
+                        const bool do1 = (jj + 1 < cw) && !(j + 1 >= k0 && j + 1 < k0 + nb);
+                        double x0 = (in_block || !do0) ? 0.0 : A[i + (size_t)j * nx];
+                        double x1 = (in_block || !do1) ? 0.0 : A[i + (size_t)(j + 1) * nx];
+#if defined(__CUDA_ARCH__)
+                        const double2* r0 = reinterpret_cast<const double2*>(rbuf() + jj * TEAM_NB_MAX);
+                        const double2* r1 = r0 + TEAM_NB_MAX / 2;  // next column (inside rbuf: cw is padded to even)
                         PB_UNROLL
-                        for (int kk = 0; kk < TEAM_NB_MAX; ++kk) x += wr[kk] * r[kk];
-                        A[i + (size_t)j * nx] = x;
+                        for (int k2 = 0; k2 < TEAM_NB_MAX / 2; ++k2) {
+                            const double2 a = r0[k2], bq = r1[k2];
+                            x0 += wr[2 * k2] * a.x;
+                            x1 += wr[2 * k2] * bq.x;
+                            x0 += wr[2 * k2 + 1] * a.y;
+                            x1 += wr[2 * k2 + 1] * bq.y;
+                        }
+#else
+                        const double* r0 = rbuf() + jj * TEAM_NB_MAX;
+                        const double* r1 = r0 + TEAM_NB_MAX;
+                        for (int kk = 0; kk < TEAM_NB_MAX; ++kk) {
+                            x0 += wr[kk] * r0[kk];
+                            if (do1) x1 += wr[kk] * r1[kk];
+                        }
+#endif
+                        if (do0) A[i + (size_t)j * nx] = x0;
+                        if (do1) A[i + (size_t)(j + 1) * nx] = x1;
                     }
                 }
                 tm.sync();
             }
             // 5. the transformed panel replaces the block columns
-            PT_FOR(e, 0, nx * nb) A[(size_t)k0 * nx + e] = w.panel[e];
+            PT_FOR(e, 0, nx * nb) A[(size_t)k0 * nx + e] = panel()[e];
             tm.sync();
+            cyc_update += now() - t_p1;
         }
         return 0;
     }
+
+#if defined(__CUDA_ARCH__)
+    /// The same blocked Gauss-Jordan inversion for nx <= blockDim.x: thread i owns matrix row i.
+    /// Its row of the panel lives in REGISTERS from the panel factorisation through the rank-NB
+    /// update (no panel in shared memory): per pivot one arg-max reduction and one exchange of the
+    /// pivot row through shared memory; the row swaps of a block step are composed into one
+    /// permutation and applied to the other columns with independent loads; the rank-NB update
+    /// streams the matrix once per block step with the next 8 columns prefetched and the pivot-row
+    /// tile double-buffered in shared memory.
+    __device__ __noinline__ int invert_rows() {
+        constexpr int NB = TEAM_NB_MAX;
+        double* const A = w.A;
+        const int i = threadIdx.x;
+        const bool rowok = i < nx;
+        double* const sm = smem_base();
+        double* const xbuf = sm + TEAM_SM_ROWK;
+        double* const xbuf2 = sm + TEAM_SM_XBUF2;
+        int* const pv = reinterpret_cast<int*>(sm + TEAM_SM_PIV);
+        int* const tlist = reinterpret_cast<int*>(sm + TEAM_SM_TL);
+        int* const tsrc = tlist + 2 * NB;
+        int* const ntp = reinterpret_cast<int*>(sm + TEAM_SM_NT);
+        for (int k0 = 0; k0 < nx; k0 += NB) {
+            const int nb = (nx - k0 < NB) ? nx - k0 : NB;
+            const long long t_p0 = now();
+            double prow[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) prow[c] = (rowok && c < nb) ? A[i + (size_t)(k0 + c) * nx] : 0.0;
+            // ---- panel: Gauss-Jordan on the block columns, rows in registers
+#pragma unroll
+            for (int kk = 0; kk < NB; ++kk) {
+                if (kk < nb) {
+                    const int k = k0 + kk;
+                    const double mag = (rowok && i >= k) ? fabs(prow[kk]) : -1.0;
+                    int bi = i;
+                    const double best = tm.argmax(mag, bi);
+                    if (!(best > 0.0) || !PB_FINITE(best)) return 1;
+                    const int lp = bi;
+                    if (i == lp) {
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) xbuf[c] = prow[c];
+                    }
+                    if (lp != k && i == k) {
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) xbuf2[c] = prow[c];
+                    }
+                    if (i == 0) {
+                        pv[kk] = lp;
+                        const int t_ = w.perm[k];
+                        w.perm[k] = w.perm[lp];
+                        w.perm[lp] = t_;
+                    }
+                    __syncthreads();
+                    if (lp != k && i == lp) {
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) prow[c] = xbuf2[c];
+                    }
+                    const double pinv = 1.0 / xbuf[kk];
+                    if (i == k) {
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) prow[c] = (c == kk) ? pinv : xbuf[c] * pinv;
+                    } else {
+                        const double m = prow[kk] * pinv;
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) prow[c] = (c == kk) ? -m : prow[c] - m * xbuf[c];
+                    }
+                }
+            }
+            // ---- the row swaps of this block step as one permutation: position tlist[t] receives
+            //      the row that was at tsrc[t] when the block step began
+            if (i == 0) {
+                int n = 0;
+                for (int kk = 0; kk < nb; ++kk) {
+                    const int k = k0 + kk, lp = pv[kk];
+                    if (lp == k) continue;
+                    int a = -1, b = -1;
+                    for (int t = 0; t < n; ++t) {
+                        if (tlist[t] == k) a = t;
+                        if (tlist[t] == lp) b = t;
+                    }
+                    if (a < 0) { a = n; tlist[n] = k; tsrc[n] = k; ++n; }
+                    if (b < 0) { b = n; tlist[n] = lp; tsrc[n] = lp; ++n; }
+                    const int t_ = tsrc[a];
+                    tsrc[a] = tsrc[b];
+                    tsrc[b] = t_;
+                }
+                *ntp = n;
+            }
+            __syncthreads();
+            const int nt = *ntp;
+            if (nt > 0) {
+                for (int j = i; j < nx; j += blockDim.x) {
+                    if (j >= k0 && j < k0 + nb) continue;
+                    double* col = A + (size_t)j * nx;
+                    double v[2 * NB];
+                    for (int t = 0; t < nt; ++t) v[t] = col[tsrc[t]];
+                    for (int t = 0; t < nt; ++t)
+                        if (tsrc[t] != tlist[t]) col[tlist[t]] = v[t];
+                }
+            }
+            __syncthreads();
+            const long long t_p1 = now();
+            cyc_panel += t_p1 - t_p0;
+            // ---- rank-nb update of the other columns
+            const bool in_block = (i >= k0 && i < k0 + nb);
+            const int nchunks = (nx + TEAM_CW - 1) / TEAM_CW;
+            double* const xs = sm + TEAM_SM_XSTAGE;
+            auto r_entry = [&](int ch, int e) -> double {  // entry e of the pivot-row tile of chunk ch
+                const int jj = e / NB, kk = e - jj * NB;
+                const int j = ch * TEAM_CW + jj;
+                return (kk < nb && j < nx) ? A[(k0 + kk) + (size_t)j * nx] : 0.0;
+            };
+            {
+                double* const b0 = sm + TEAM_SM_RBUF;
+#pragma unroll
+                for (int u = 0; u < TEAM_RBUF / 512; ++u) {
+                    const int e = i + u * 512;
+                    b0[e] = r_entry(0, e);
+                }
+            }
+            __syncthreads();
+            // this thread's elements of the next TEAM_ST-1 column groups are always in flight
+            // (cp.async into its own slots of the ring: no barrier needed to read them back)
+            constexpr int GC = TEAM_GC, ST = TEAM_ST;
+            const int ngroups = (nx + GC - 1) / GC;
+            auto col_ok = [&](int j) { return j < nx && !(j >= k0 && j < k0 + nb); };
+            auto issue = [&](int g) {
+                if (g < ngroups) {
+                    double* dst = xs + (size_t)((g % ST) * GC) * 512 + i;
+#pragma unroll
+                    for (int u = 0; u < GC; ++u) {
+                        const int j = g * GC + u;
+                        const bool ok = rowok && !in_block && col_ok(j);
+                        pb_cp_async8(dst + u * 512, ok ? A + i + (size_t)j * nx : A, ok ? 8 : 0);
+                    }
+                }
+                pb_cp_async_commit();
+            };
+#pragma unroll
+            for (int g = 0; g < ST - 1; ++g) issue(g);
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const double* const cur = sm + ((ch & 1) ? TEAM_SM_RBUF1 : TEAM_SM_RBUF);
+                double* const nxt = sm + ((ch & 1) ? TEAM_SM_RBUF : TEAM_SM_RBUF1);
+                double rpre[TEAM_RBUF / 512];
+                if (ch + 1 < nchunks) {
+#pragma unroll
+                    for (int u = 0; u < TEAM_RBUF / 512; ++u) rpre[u] = r_entry(ch + 1, i + u * 512);
+                }
+                for (int gl = 0; gl < TEAM_CW / GC; ++gl) {
+                    const int g = ch * (TEAM_CW / GC) + gl;
+                    if (g >= ngroups) break;
+                    issue(g + ST - 1);
+                    pb_cp_async_wait<ST - 1>();
+                    const double* src = xs + (size_t)((g % ST) * GC) * 512 + i;
+                    double xc[GC];
+#pragma unroll
+                    for (int u = 0; u < GC; ++u) xc[u] = src[u * 512];
+                    const double2* r2 = reinterpret_cast<const double2*>(cur + gl * GC * NB);
+#pragma unroll
+                    for (int k2 = 0; k2 < NB / 2; ++k2) {
+#pragma unroll
+                        for (int u = 0; u < GC; ++u) {
+                            const double2 rv = r2[u * (NB / 2) + k2];
+                            xc[u] += prow[2 * k2] * rv.x;
+                            xc[u] += prow[2 * k2 + 1] * rv.y;
+                        }
+                    }
+                    if (rowok) {
+#pragma unroll
+                        for (int u = 0; u < GC; ++u)
+                            if (col_ok(g * GC + u)) A[i + (size_t)(g * GC + u) * nx] = xc[u];
+                    }
+                }
+                if (ch + 1 < nchunks) {
+#pragma unroll
+                    for (int u = 0; u < TEAM_RBUF / 512; ++u) nxt[i + u * 512] = rpre[u];
+                }
+                __syncthreads();
+            }
+            pb_cp_async_wait<0>();
+            // ---- the transformed panel replaces the block columns
+            if (rowok) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c < nb) A[i + (size_t)(k0 + c) * nx] = prow[c];
+            }
+            __syncthreads();
+            cyc_update += now() - t_p1;
+        }
+        return 0;
+    }
+
+    /// The solve GEMM for nx <= blockDim.x (one matrix row per thread): the right-hand-side tile of
+    /// the next 64 rows is fetched (through the pivot order) while the current one is used, and the
+    /// thread's next 8 matrix entries are in flight while the current 8 are multiplied.
+    template <int TN>
+    __device__ __noinline__ void solve_pass_rows(int c0, int nc, double nsc) {
+        constexpr int KC = (TN == 1) ? 512 : 64;
+        constexpr int PRE = (KC * TN + 511) / 512;
+        static_assert(KC * TN <= TEAM_RBUF, "tile does not fit");
+        const int i = threadIdx.x;
+        const bool active = i < nx;
+        double* const sm = smem_base();
+        const double* const A = w.A;
+        const double* const b = w.b;
+        const int* const perm = w.perm;
+        auto b_entry = [&](int ch, int e) -> double {
+            const int kk = e / TN, cc = e - kk * TN;
+            const int k = ch * KC + kk;
+            return (k < nx && cc < nc && e < KC * TN) ? b[perm[k] + (size_t)(c0 + cc) * nx] : 0.0;
+        };
+        double acc[TN];
+#pragma unroll
+        for (int cc = 0; cc < TN; ++cc) acc[cc] = 0.0;
+        const int nchunks = (nx + KC - 1) / KC;
+        __syncthreads();
+        {
+            double* const b0 = sm + TEAM_SM_RBUF;
+#pragma unroll
+            for (int u = 0; u < PRE; ++u) {
+                const int e = i + u * 512;
+                if (e < KC * TN) b0[e] = b_entry(0, e);
+            }
+        }
+        __syncthreads();
+        constexpr int GK = TEAM_GC, ST = TEAM_ST;
+        double* const xs = sm + TEAM_SM_XSTAGE;
+        const double* arow = A + i;
+        const int ngk = (nx + GK - 1) / GK;  // groups of GK matrix columns (k indices)
+        auto issue = [&](int g) {
+            if (g < ngk) {
+                double* dst = xs + (size_t)((g % ST) * GK) * 512 + i;
+#pragma unroll
+                for (int u = 0; u < GK; ++u) {
+                    const int k = g * GK + u;
+                    const bool ok = active && k < nx;
+                    pb_cp_async8(dst + u * 512, ok ? arow + (size_t)k * nx : A, ok ? 8 : 0);
+                }
+            }
+            pb_cp_async_commit();
+        };
+#pragma unroll
+        for (int g = 0; g < ST - 1; ++g) issue(g);
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const double* const cur = sm + ((ch & 1) ? TEAM_SM_RBUF1 : TEAM_SM_RBUF);
+            double* const nxt = sm + ((ch & 1) ? TEAM_SM_RBUF : TEAM_SM_RBUF1);
+            double bpre[PRE];
+            if (ch + 1 < nchunks) {
+#pragma unroll
+                for (int u = 0; u < PRE; ++u) bpre[u] = b_entry(ch + 1, i + u * 512);
+            }
+            for (int gl = 0; gl < KC / GK; ++gl) {
+                const int g = ch * (KC / GK) + gl;
+                if (g >= ngk) break;
+                issue(g + ST - 1);
+                pb_cp_async_wait<ST - 1>();
+                const double* src = xs + (size_t)((g % ST) * GK) * 512 + i;
+#pragma unroll
+                for (int u = 0; u < GK; ++u) {
+                    const double a = src[u * 512];
+                    if constexpr ((TN & 1) == 0) {
+                        const double2* r2 = reinterpret_cast<const double2*>(cur + (gl * GK + u) * TN);
+#pragma unroll
+                        for (int c2 = 0; c2 < TN / 2; ++c2) {
+                            const double2 rv = r2[c2];
+                            acc[2 * c2] += a * rv.x;
+                            acc[2 * c2 + 1] += a * rv.y;
+                        }
+                    } else {
+                        const double* r = cur + (gl * GK + u) * TN;
+#pragma unroll
+                        for (int cc = 0; cc < TN; ++cc) acc[cc] += a * r[cc];
+                    }
+                }
+            }
+            if (ch + 1 < nchunks) {
+#pragma unroll
+                for (int u = 0; u < PRE; ++u) {
+                    const int e = i + u * 512;
+                    if (e < KC * TN) nxt[e] = bpre[u];
+                }
+            }
+            __syncthreads();
+        }
+        pb_cp_async_wait<0>();
+        if (active) {
+#pragma unroll
+            for (int cc = 0; cc < TN; ++cc)
+                if (cc < nc) w.scr[i + (size_t)(c0 + cc) * nx] = nsc * acc[cc];
+        }
+    }
+#endif
 
     /// cvLsSetup + cvLsLinSys + the inversion; the Jacobian is evaluated at w.yj
     PB_HD int lsetup() {
@@ -384,7 +782,7 @@ struct BdfTeam {
                 tm.sync();
                 PT_FOR(e, 0, kc * TN) {
                     const int kk = e / TN, cc = e - kk * TN;
-                    w.rbuf[e] = (cc < nc) ? w.b[w.perm[k0 + kk] + (size_t)(c0 + cc) * nx] : 0.0;
+                    rbuf()[e] = (cc < nc) ? w.b[w.perm[k0 + kk] + (size_t)(c0 + cc) * nx] : 0.0;
                 }
                 tm.sync();
                 if (active) {
@@ -394,9 +792,22 @@ struct BdfTeam {
 #endif
                     for (int kk = 0; kk < kc; ++kk) {
                         const double a = arow[(size_t)kk * nx];
-                        const double* r = w.rbuf + kk * TN;
-                        PB_UNROLL
-                        for (int cc = 0; cc < TN; ++cc) acc[cc] += a * r[cc];
+#if defined(__CUDA_ARCH__)
+                        if constexpr ((TN & 1) == 0) {
+                            const double2* r2 = reinterpret_cast<const double2*>(rbuf() + kk * TN);
+                            PB_UNROLL
+                            for (int c2 = 0; c2 < TN / 2; ++c2) {
+                                const double2 rv = r2[c2];
+                                acc[2 * c2] += a * rv.x;
+                                acc[2 * c2 + 1] += a * rv.y;
+                            }
+                        } else
+#endif
+                        {
+                            const double* r = rbuf() + kk * TN;
+                            PB_UNROLL
+                            for (int cc = 0; cc < TN; ++cc) acc[cc] += a * r[cc];
+                        }
                     }
                 }
             }
@@ -412,16 +823,47 @@ struct BdfTeam {
     /// gamma-ratio scaling; acor += delta; returns the WRMS norm of delta.
     PB_HD double newton_update(int cmin, int cmax) {
         const double nsc = (gamrat != 1.0) ? -2.0 / (1.0 + gamrat) : -1.0;
+        const long long t_s0 = now();
+#if defined(__CUDA_ARCH__)
+        const bool rows_path = nx <= tm.size();
+#else
+        const bool rows_path = false;
+#endif
         if (cmin == cmax) {
-            solve_pass<1>(cmin, 1, nsc);
+#if defined(__CUDA_ARCH__)
+            if (rows_path) solve_pass_rows<1>(cmin, 1, nsc);
+            else
+#endif
+                solve_pass<1>(cmin, 1, nsc);
         } else {
             for (int c0 = cmin; c0 <= cmax; c0 += TEAM_TN) {
                 const int nc = (cmax + 1 - c0 < TEAM_TN) ? cmax + 1 - c0 : TEAM_TN;
-                solve_pass<TEAM_TN>(c0, nc, nsc);
+#if defined(__CUDA_ARCH__)
+                if (rows_path) solve_pass_rows<TEAM_TN>(c0, nc, nsc);
+                else
+#endif
+                    solve_pass<TEAM_TN>(c0, nc, nsc);
             }
         }
         tm.sync();
-        PT_FOR(e, cmin * nx, (cmax + 1) * nx) w.acor[e] += w.scr[e];
+        cyc_solve += now() - t_s0;
+        {
+            constexpr int U = 4;
+            const int e1 = (cmax + 1) * nx;
+            PT_FOR_BATCH(eb, cmin * nx, e1, U) {
+                double a[U];
+                PB_UNROLL
+                for (int u = 0; u < U; ++u) {
+                    const int e = eb + u * tm.size();
+                    a[u] = (e < e1) ? w.acor[e] + w.scr[e] : 0.0;
+                }
+                PB_UNROLL
+                for (int u = 0; u < U; ++u) {
+                    const int e = eb + u * tm.size();
+                    if (e < e1) w.acor[e] = a[u];
+                }
+            }
+        }
         return wnorm1(cmin, cmax, w.scr);
     }
 
@@ -479,23 +921,61 @@ struct BdfTeam {
     /// cvPredict (sgn = +1) / cvRestore (sgn = -1): Pascal-triangle sweep per element in registers
     PB_HD void shift_history(double sgn) {
         tm.sync();
-        PT_FOR_ELEMS(e) {
-            double z[cv::L_MAX];
-            for (int j = 0; j <= q; ++j) z[j] = w.zn[j][e];
-            for (int k = 1; k <= q; ++k)
-                for (int j = q; j >= k; --j) z[j - 1] += sgn * z[j];
-            for (int j = 0; j < q; ++j) w.zn[j][e] = z[j];
+        constexpr int U = 2;
+        const int e1 = nx * ncol;
+        double* const zb = w.znbase;
+        const size_t nxc = w.nxc;
+        PT_FOR_BATCH(eb, 0, e1, U) {
+            double z[U][cv::L_MAX];
+            PB_UNROLL
+            for (int u = 0; u < U; ++u) {
+                const int e = eb + u * tm.size();
+                PB_UNROLL
+                for (int j = 0; j < cv::L_MAX; ++j) z[u][j] = (j <= q && e < e1) ? zb[j * nxc + e] : 0.0;
+            }
+            PB_UNROLL
+            for (int u = 0; u < U; ++u) {
+                PB_UNROLL
+                for (int k = 1; k <= cv::Q_MAX; ++k) {
+                    PB_UNROLL
+                    for (int j = cv::Q_MAX; j >= k; --j)
+                        if (j <= q && k <= q) z[u][j - 1] += sgn * z[u][j];
+                }
+            }
+            PB_UNROLL
+            for (int u = 0; u < U; ++u) {
+                const int e = eb + u * tm.size();
+                PB_UNROLL
+                for (int j = 0; j < cv::Q_MAX; ++j)
+                    if (j < q && e < e1) zb[j * nxc + e] = z[u][j];
+            }
         }
         tm.sync();
     }
     /// cvRescale
     PB_HD void rescale() {
         tm.sync();
-        PT_FOR_ELEMS(e) {
-            double factor = eta;
-            for (int j = 1; j <= q; ++j) {
-                w.zn[j][e] *= factor;
-                factor *= eta;
+        constexpr int U = 2;
+        const int e1 = nx * ncol;
+        double* const zb = w.znbase;
+        const size_t nxc = w.nxc;
+        PT_FOR_BATCH(eb, 0, e1, U) {
+            double z[U][cv::L_MAX];
+            PB_UNROLL
+            for (int u = 0; u < U; ++u) {
+                const int e = eb + u * tm.size();
+                PB_UNROLL
+                for (int j = 1; j < cv::L_MAX; ++j) z[u][j] = (j <= q && e < e1) ? zb[j * nxc + e] : 0.0;
+            }
+            PB_UNROLL
+            for (int u = 0; u < U; ++u) {
+                const int e = eb + u * tm.size();
+                double factor = eta;
+                PB_UNROLL
+                for (int j = 1; j < cv::L_MAX; ++j) {
+                    if (j <= q && e < e1) zb[j * nxc + e] = z[u][j] * factor;
+                    factor *= eta;
+                }
             }
         }
         h = hscale * eta;
@@ -539,9 +1019,9 @@ struct BdfTeam {
         }
         tm.sync();
         PT_FOR_ELEMS(e) {
-            if (deltaq == 1) w.zn[src][e] = A1 * w.zn[cv::Q_MAX][e];
-            const double zs = w.zn[src][e];
-            for (int j = 2; j <= jmax; ++j) w.zn[j][e] += lc[j] * zs;
+            if (deltaq == 1) w.zn(src)[e] = A1 * w.zn(cv::Q_MAX)[e];
+            const double zs = w.zn(src)[e];
+            for (int j = 2; j <= jmax; ++j) w.zn(j)[e] += lc[j] * zs;
         }
         tm.sync();
     }
@@ -638,10 +1118,34 @@ struct BdfTeam {
         qwait--;
         const bool save = (qwait == 1) && (q != cv::Q_MAX);
         tm.sync();
-        PT_FOR_ELEMS(e) {
-            const double a = w.acor[e];
-            for (int j = 0; j <= q; ++j) w.zn[j][e] += l[j] * a;
-            if (save) w.zn[cv::Q_MAX][e] = a;
+        {
+            constexpr int U = 2;
+            const int e1 = nx * ncol;
+            double* const zb = w.znbase;
+            const size_t nxc = w.nxc;
+            double lr[cv::L_MAX];  // l[] in registers (compile-time indices below)
+            PB_UNROLL
+            for (int j = 0; j < cv::L_MAX; ++j) lr[j] = l[j];
+            PT_FOR_BATCH(eb, 0, e1, U) {
+                double z[U][cv::L_MAX], a[U];
+                PB_UNROLL
+                for (int u = 0; u < U; ++u) {
+                    const int e = eb + u * tm.size();
+                    a[u] = (e < e1) ? w.acor[e] : 0.0;
+                    PB_UNROLL
+                    for (int j = 0; j < cv::L_MAX; ++j) z[u][j] = (j <= q && e < e1) ? zb[j * nxc + e] : 0.0;
+                }
+                PB_UNROLL
+                for (int u = 0; u < U; ++u) {
+                    const int e = eb + u * tm.size();
+                    if (e < e1) {
+                        PB_UNROLL
+                        for (int j = 0; j < cv::L_MAX; ++j)
+                            if (j <= q) zb[j * nxc + e] = z[u][j] + lr[j] * a[u];
+                        if (save) zb[cv::Q_MAX * nxc + e] = a[u];
+                    }
+                }
+            }
         }
         tm.sync();
         if (save) saved_tq5 = tq5;
@@ -664,7 +1168,7 @@ struct BdfTeam {
             const int ecmax = errtest_cmax();
             etaqm1 = 0.0;
             if (q > 1) {
-                double ddn = wnorm1(0, ecmax, w.zn[q]);
+                double ddn = wnorm1(0, ecmax, w.zn(q));
                 ddn = ddn * tq1;
                 etaqm1 = 1.0 / (pow(cv::BIAS1 * ddn, 1.0 / (double)q) + cv::ADDON);
             }
@@ -675,7 +1179,7 @@ struct BdfTeam {
                     double hp = 1.0;
                     for (int i = 0; i < L; ++i) hp *= hr;  // SUNRpowerI
                     const double cquot = (tq5 / saved_tq5) * hp;
-                    double dup = wnorm(0, ecmax, w.zn[cv::Q_MAX], -cquot, w.acor, 1.0);
+                    double dup = wnorm(0, ecmax, w.zn(cv::Q_MAX), -cquot, w.acor, 1.0);
                     dup = dup * tq3;
                     etaqp1 = 1.0 / (pow(cv::BIAS3 * dup, 1.0 / (double)(L + 1)) + cv::ADDON);
                 }
@@ -694,7 +1198,7 @@ struct BdfTeam {
                 eta = etaqp1;
                 qprime = q + 1;
                 tm.sync();
-                PT_FOR(e, 0, (ecmax + 1) * nx) w.zn[cv::Q_MAX][e] = w.acor[e];
+                PT_FOR(e, 0, (ecmax + 1) * nx) w.zn(cv::Q_MAX)[e] = w.acor[e];
                 tm.sync();
             }
         }
@@ -842,8 +1346,8 @@ struct BdfTeam {
     /// cvBDFStab
     PB_HD void bdf_stab() {
         if (q >= 3) {
-            const double n0 = wnorm1(0, 0, w.zn[q]);
-            const double n1 = wnorm1(0, 0, w.zn[q - 1]);
+            const double n0 = wnorm1(0, 0, w.zn(q));
+            const double n1 = wnorm1(0, 0, w.zn(q - 1));
             int factorial = 1;
             for (int i = 1; i <= q - 1; ++i) factorial *= i;
             const double sq = factorial * q * (q + 1) * acnrm / fmax(tq5, cv::TINY);
@@ -878,7 +1382,7 @@ struct BdfTeam {
         tm.sync();
         const int r = rhs_all_raw(sensi);
         if (r) return r;
-        PT_FOR_ELEMS(e) w.zn[1][e] = h * w.b[e];
+        PT_FOR_ELEMS(e) w.zn(1)[e] = h * w.b[e];
         tm.sync();
         return 0;
     }
@@ -1020,8 +1524,8 @@ struct BdfTeam {
         double hub_inv = 0.0;
         tm.sync();
         PT_FOR(e, 0, (ecmax + 1) * nx) {
-            const double den = cv::HUB_FACTOR * fabs(w.zn[0][e]) + 1.0 / w.ewt[e];
-            const double v = fabs(w.zn[1][e]) / den;
+            const double den = cv::HUB_FACTOR * fabs(w.zn(0)[e]) + 1.0 / w.ewt[e];
+            const double v = fabs(w.zn(1)[e]) / den;
             if (v > hub_inv) hub_inv = v;
         }
         hub_inv = tm.max(hub_inv);
@@ -1040,12 +1544,12 @@ struct BdfTeam {
             for (int count2 = 1; count2 <= cv::HIN_MAX_ITERS; ++count2) {
                 const double hgs = hg * sign;
                 tm.sync();
-                PT_FOR_ELEMS(e) w.acor[e] = hgs * w.zn[1][e];
+                PT_FOR_ELEMS(e) w.acor[e] = hgs * w.zn(1)[e];
                 // AMICI's right-hand sides do not depend on t explicitly for network models
                 retval = rhs_all_raw(withS);
                 if (retval == 0) {
                     const double hinv = 1.0 / hgs;
-                    yddnrm = wnorm(0, ecmax, w.b, hinv, w.zn[1], -hinv);
+                    yddnrm = wnorm(0, ecmax, w.b, hinv, w.zn(1), -hinv);
                     hgOK = true;
                     break;
                 }
@@ -1094,7 +1598,7 @@ struct BdfTeam {
             hscale = h;
             hprime = h;
             tm.sync();
-            PT_FOR_ELEMS(e) w.zn[1][e] *= h;
+            PT_FOR_ELEMS(e) w.zn(1)[e] *= h;
             tm.sync();
         } else {
             const double troundoff = cv::FUZZ_FACTOR * cv::UROUND * (fabs(tn) + fabs(h));
@@ -1120,7 +1624,7 @@ struct BdfTeam {
         double dJydy[TEAM_MAXNY];
         bool ok = true;
         for (int iy = 0; iy < ny; ++iy) {
-            const double y = net::observable(T, iy, w.zn[0]);
+            const double y = net::observable(T, iy, w.zn(0));
             double sig = T.sigma0[iy];
             if (!isnan(sd[iy])) sig = sd[iy];
             if (tm.tid() == 0) {
@@ -1138,7 +1642,7 @@ struct BdfTeam {
         if (!ok) return false;
         if (!sensi) return true;
         PT_FOR(c, 1, ns + 1) {
-            const double* sx = w.zn[0] + (size_t)c * nx;
+            const double* sx = w.zn(0) + (size_t)c * nx;
             double a = 0.0;
             for (int iy = 0; iy < ny; ++iy) {
                 if (dJydy[iy] == 0.0) continue;
@@ -1162,10 +1666,10 @@ struct BdfTeam {
         ncol = ns + 1;
         sensi = ns > 0;
         tm.sync();
-        net::x0(T, tm, w.k, w.zn[0]);
-        PT_FOR(e, nx, nx * ncol) w.zn[0][e] = 0.0;  // sx0 = 0: initial values do not depend on p
+        net::x0(T, tm, w.k, w.zn(0));
+        PT_FOR(e, nx, nx * ncol) w.zn(0)[e] = 0.0;  // sx0 = 0: initial values do not depend on p
         PT_FOR_ELEMS(e) {
-            for (int j = 1; j < cv::L_MAX; ++j) w.zn[j][e] = 0.0;
+            for (int j = 1; j < cv::L_MAX; ++j) w.zn(j)[e] = 0.0;
             w.acor[e] = 0.0;
             w.ewt[e] = 1.0;
             w.b[e] = 0.0;
@@ -1193,6 +1697,7 @@ struct BdfTeam {
         it_ = 0;
         sim_status_ = SIM_SUCCESS;
         fail_ = ret_ = 0;
+        cyc_panel = cyc_update = cyc_solve = cyc_rhs = 0;
         tm.sync();
     }
 
@@ -1215,7 +1720,7 @@ struct BdfTeam {
                     // top of the CVode step loop
                     if (nst > 0 && !ewt_set()) return finish(SIM_ILL_INPUT);
                     if (nstloc_ >= mxstep_) return finish(SIM_TOO_MUCH_WORK);
-                    const double nrm = wnorm1(0, errtest_cmax(), w.zn[0]);
+                    const double nrm = wnorm1(0, errtest_cmax(), w.zn(0));
                     if (cv::UROUND * nrm > 1.0) return finish(SIM_TOO_MUCH_ACC);
                     step_begin();
                     for (;;) {
@@ -1264,7 +1769,9 @@ struct BdfTeam {
         s[STAT_NST] = nst; s[STAT_NFE] = nfe; s[STAT_NSETUPS] = nsetups; s[STAT_NJE] = nje;
         s[STAT_NNI] = nni; s[STAT_NNIS] = nniS; s[STAT_NFSE] = nfSe; s[STAT_NETF] = netf;
         s[STAT_NETFS] = netfS; s[STAT_NCFN] = ncfn; s[STAT_NCFNS] = ncfnS; s[STAT_NOR] = nor;
-        s[STAT_TRIALS] = trials; s[STAT_QSUM] = qsum; s[14] = 0; s[15] = 0;
+        s[STAT_TRIALS] = trials; s[STAT_QSUM] = qsum;
+        s[14] = ((cyc_panel >> 10) << 32) | ((cyc_update >> 10) & 0xffffffffll);
+        s[15] = ((cyc_solve >> 10) << 32) | ((cyc_rhs >> 10) & 0xffffffffll);
     }
 #undef PT_FOR
 #undef PT_FOR_ELEMS

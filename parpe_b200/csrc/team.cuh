@@ -33,8 +33,12 @@ struct HostTeam {
 /// warp over the per-warp partials), so results are run-to-run reproducible.
 struct CtaTeam {
     static constexpr int WARP = 32;
-    double* red;  // shared scratch, >= 2*32 doubles
-    __device__ __forceinline__ explicit CtaTeam(double* red_) : red(red_) {}
+    /// shared scratch (the first 64 doubles of the kernel's dynamic shared memory), derived from
+    /// the shared-memory base at every use so that the compiler emits LDS/STS
+    __device__ __forceinline__ static double* red_base() {
+        extern __shared__ __align__(16) double pb_team_smem[];
+        return pb_team_smem;
+    }
     __device__ __forceinline__ int tid() const { return threadIdx.x; }
     __device__ __forceinline__ int size() const { return blockDim.x; }
     __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
@@ -52,6 +56,7 @@ struct CtaTeam {
         return v;
     }
     __device__ __noinline__ double sum(double v) const {
+        double* const red = red_base();
         v = warp_sum(v);
         __syncthreads();  // red may still be read by the previous reduction
         if (lane() == 0) red[warp()] = v;
@@ -60,6 +65,7 @@ struct CtaTeam {
         return warp_sum(s);
     }
     __device__ __noinline__ double max(double v) const {
+        double* const red = red_base();
         v = warp_max(v);
         __syncthreads();
         if (lane() == 0) red[warp()] = v;
@@ -76,6 +82,7 @@ struct CtaTeam {
             if (vo > v || (vo == v && io < idx)) { v = vo; idx = io; }
         }
         __syncthreads();
+        double* const red = red_base();
         int* ired = reinterpret_cast<int*>(red + 32);
         if (lane() == 0) { red[warp()] = v; ired[warp()] = idx; }
         __syncthreads();

@@ -18,24 +18,16 @@ namespace pb200 {
 
 constexpr int TEAM_THREADS = 512;
 
-/// shared-memory layout (doubles): reduction scratch | rowk | piv | rbuf | panel
-constexpr int TEAM_SM_RED = 0, TEAM_SM_ROWK = 64, TEAM_SM_PIV = 96, TEAM_SM_RBUF = 112,
-              TEAM_SM_PANEL = TEAM_SM_RBUF + TEAM_RBUF;
-
 template <int TEAM_THREADS_>
 __global__ void __launch_bounds__(TEAM_THREADS_, 1)
 simulate_team_kernel(const KernelArgs a, const NetTables T, double* __restrict__ workspace, size_t ws_stride, int NB) {
     extern __shared__ __align__(16) double pb_team_smem[];
     __shared__ int s_pos;
-    CtaTeam tm(pb_team_smem + TEAM_SM_RED);
+    CtaTeam tm;
     BdfTeam<CtaTeam> bdf(tm);
     bdf.T = T;
     bdf.opt = a.opt;
     bdf.w.carve(workspace + (size_t)blockIdx.x * ws_stride, T);
-    bdf.w.rowk = pb_team_smem + TEAM_SM_ROWK;
-    bdf.w.piv = reinterpret_cast<int*>(pb_team_smem + TEAM_SM_PIV);
-    bdf.w.rbuf = pb_team_smem + TEAM_SM_RBUF;
-    bdf.w.panel = pb_team_smem + TEAM_SM_PANEL;
     bdf.w.NB = NB;
     const int tid = threadIdx.x;
     const int np = T.np;
@@ -170,6 +162,8 @@ inline void* team_create_state(const NetTables& H, int sm_count, std::string* er
     const size_t panel_doubles = (max_smem - (size_t)TEAM_SM_PANEL * sizeof(double)) / sizeof(double);
     st->NB = TeamWork::panel_width(H.nx, panel_doubles);
     st->smem = ((size_t)TEAM_SM_PANEL + (size_t)H.nx * st->NB) * sizeof(double);
+    if (H.nx <= TEAM_THREADS && st->smem < (size_t)TEAM_SM_ROWS_END * sizeof(double))
+        st->smem = (size_t)TEAM_SM_ROWS_END * sizeof(double);  // rows path: cp.async ring
     if ((size_t)H.nx * st->NB > panel_doubles) {
         if (err) *err = "model too large for the team kernel's shared-memory panel";
         team_destroy_state(st);

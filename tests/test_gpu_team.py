@@ -33,12 +33,17 @@ def test_team_evaluate_matches_oracle(oracle_available, model, C, ntp, kw):
     tab = synth.make_problem(model, C, seed=3, timepoints=synth.DEFAULT_TIMEPOINTS[model][:ntp], **kw)
     gpu, ora = _both(tab)
     theta = synth.random_theta(tab, seed=1, width=0.3)
-    ro = ora.evaluate(theta)
+    ro = ora.evaluate(theta, collect_stats=True)
     st, fval, grad, _ = gpu.evaluate(theta)
     assert st == ro["status"] == 0
     assert_llh_close(fval, ro["fval"], "nllh")
     assert_grad_close(grad, ro["grad"], "gradient")
     res = gpu.condition_results()
+    # a wrong inverse would still converge (Newton corrects itself) but with more iterations and
+    # convergence failures: the step counts must stay close to CVODES' and failures rare
+    nst, nst_ref = res["stats"][:, 0], ro["stats"][:, 0]
+    assert np.all(np.abs(nst - nst_ref) <= 0.1 * nst_ref + 5), (nst, nst_ref)
+    assert np.all(res["stats"][:, 9] + res["stats"][:, 10] <= 0.02 * nst + 2), res["stats"][:, 9:11]
     assert np.array_equal(res["status"], ro["cond_status"])
     assert_llh_close(res["llh"], ro["llh"], "per-condition llh")
     for c in range(min(C, 8)):

@@ -1,0 +1,124 @@
+"""The large-model integrator core (parpe_b200/csrc/bdf_team.cuh), compiled for the host with
+the one-thread team, against the CVODES oracle and numpy on the same inputs: the algorithm the
+CTA-per-condition kernel runs (blocked Gauss-Jordan inversion, solve GEMM through the pivot
+order, sparse right-hand sides, staggered sensitivities) is parity-checked on every CPU run; the
+GPU tests then check the CUDA build of the same source through the C ABI."""
+import numpy as np
+import pytest
+
+from parpe_b200 import synth
+from parpe_b200.models import get_spec
+from parpe_b200.tables import SCALE_LN, SCALE_LOG10
+from tests.util import assert_grad_close, assert_llh_close
+
+
+def _dense_jacobian(spec, Jv):
+    J = np.zeros((spec.nx, spec.nx))
+    rows = np.repeat(np.arange(spec.nx), np.diff(spec.j_ptr))
+    J[rows, spec.j_col] = Jv
+    return J
+
+
+@pytest.mark.parametrize("model,ncols,panel_widths", [("net32", 7, (0, 8, 4, 1)), ("chen", 51, (0, 16))])
+def test_blocked_inversion_and_solve_gemm(model, ncols, panel_widths):
+    """(I - gamma J)^-1 B for random values on the model's pattern vs numpy; every panel width
+    must give the same answer (NB = 16 is what nx = 1200 uses on the device)."""
+    from tests.host_harness.binding import team_solve
+    spec = get_spec(model)
+    rng = np.random.default_rng(0)
+    Jv = 10.0 * rng.standard_normal(spec.nnz)
+    gamma = 0.37
+    A = np.eye(spec.nx) - gamma * _dense_jacobian(spec, Jv)
+    B = rng.standard_normal((ncols, spec.nx))
+    Xref = np.linalg.solve(A, B.T).T
+    for nb in panel_widths:
+        X = team_solve(model, Jv, gamma, B, panel_width=nb)
+        assert np.max(np.abs(X - Xref)) <= 1e-11 * np.max(np.abs(Xref)), nb
+
+
+def test_singular_newton_matrix_is_reported():
+    from tests.host_harness.binding import team_solve
+    spec = get_spec("net32")
+    with pytest.raises(RuntimeError):
+        # gamma = 0 and J = 0 would be the identity; a pattern-wide zero with gamma*J = I on the
+        # diagonal makes the matrix exactly singular
+        Jv = np.zeros(spec.nnz)
+        rows = np.repeat(np.arange(spec.nx), np.diff(spec.j_ptr))
+        Jv[rows == spec.j_col] = 1.0
+        team_solve("net32", Jv, 1.0, np.ones((1, spec.nx)))
+
+
+def _unscaled_p(tab, c, theta, oracle):
+    p_sim = oracle.map_parameters(c, theta)
+    out = np.empty_like(p_sim)
+    for i, v in enumerate(p_sim):
+        s = tab.pscale_sim[c, i]
+        out[i] = 10.0 ** v if s == SCALE_LOG10 else (np.exp(v) if s == SCALE_LN else v)
+    return out
+
+
+@pytest.mark.parametrize("kw", [dict(scale="log10"), dict(scale="mixed", sigma_mode="mixed", missing_fraction=0.1)],
+                         ids=["log10", "mixed"])
+def test_host_team_core_matches_cvodes(oracle_available, kw):
+    from oracle.binding import OracleProblem
+    from tests.host_harness.binding import simulate_team
+    model = "net32"
+    tab = synth.make_problem(model, 3, seed=7, **kw)
+    ora = OracleProblem(tab, 2, 1)  # staggered, dense
+    theta = synth.random_theta(tab, seed=3, width=0.3)
+    ro = ora.evaluate(theta, collect_stats=True)
+    assert ro["status"] == 0
+    for c in range(tab.n_conditions):
+        p = _unscaled_p(tab, c, theta, ora)
+        plist = ora.plist(c)
+        lo, hi = tab.t_offsets[c], tab.t_offsets[c + 1]
+        r = simulate_team(model, p, tab.k[c], plist, tab.t[lo:hi], tab.y_of(c), tab.sigma_of(c), rtol=tab.rtol,
+                          atol=tab.atol, panel_width=8 if c == 1 else 0)
+        assert r["status"] == 0
+        assert_llh_close(r["llh"], ro["llh"][c])
+        fac = np.array([p[i] * np.log(10) if tab.pscale_sim[c, i] == SCALE_LOG10 else
+                        (p[i] if tab.pscale_sim[c, i] == SCALE_LN else 1.0) for i in plist])
+        assert_grad_close(r["sllh"] * fac, ro["sllh"][c][:len(plist)])
+        nst_ref = ro["stats"][c, 0]
+        assert abs(r["stats"][0] - nst_ref) <= 0.1 * nst_ref + 5
+        # cost only
+        r0 = simulate_team(model, p, tab.k[c], [], tab.t[lo:hi], tab.y_of(c), tab.sigma_of(c), rtol=tab.rtol,
+                           atol=tab.atol)
+        assert r0["status"] == 0
+        assert_llh_close(r0["llh"], ora.evaluate(theta, idx=[c], want_grad=False)["llh"][0])
+
+
+def test_network_tables_consistent():
+    """The emitted tables describe what the generator says: J is the derivative of xdot (finite
+    differences through the oracle-independent numpy restatement of the evaluator)."""
+    spec = get_spec("net32")
+    rng = np.random.default_rng(1)
+    x = rng.uniform(0.1, 2.0, spec.nx)
+    p = rng.uniform(0.5, 2.0, spec.np)
+
+    def xdot(x, p):
+        w = spec.kappa * p[spec.pidx]
+        w = w * np.where(spec.r_a >= 0, x[np.maximum(spec.r_a, 0)], 1.0) * np.where(spec.r_b >= 0, x[np.maximum(spec.r_b, 0)], 1.0)
+        out = np.zeros(spec.nx)
+        for i in range(spec.nx):
+            e = slice(spec.s_ptr[i], spec.s_ptr[i + 1])
+            out[i] = np.sum(spec.s_coef[e] * w[spec.s_reac[e]])
+        return out
+
+    Jv = np.zeros(spec.nnz)
+    for e in range(spec.nnz):
+        for t in range(spec.jt_ptr[e], spec.jt_ptr[e + 1]):
+            r = spec.jt_reac[t]
+            Jv[e] += spec.jt_coef[t] * spec.kappa[r] * p[spec.pidx[r]] * (x[spec.jt_other[t]] if spec.jt_other[t] >= 0 else 1.0)
+    J = _dense_jacobian(spec, Jv)
+    Jfd = np.zeros_like(J)
+    for j in range(spec.nx):
+        d = np.zeros(spec.nx)
+        d[j] = 1e-6
+        Jfd[:, j] = (xdot(x + d, p) - xdot(x - d, p)) / 2e-6
+    assert np.max(np.abs(J - Jfd)) <= 1e-6 * np.max(np.abs(J))
+    # CSC view addresses the same entries
+    rows = np.repeat(np.arange(spec.nx), np.diff(spec.j_ptr))
+    cols = np.repeat(np.arange(spec.nx), np.diff(spec.csc_ptr))
+    assert np.array_equal(spec.csc_row, rows[spec.csc_from_csr])
+    assert np.array_equal(cols, spec.j_col[spec.csc_from_csr])
