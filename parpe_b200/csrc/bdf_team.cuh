@@ -44,9 +44,11 @@ constexpr int TEAM_TN = 26;         // right-hand-side columns per pass of the s
 constexpr int TEAM_MAXNY = 16;
 /// shared-memory layout of the team kernel (doubles): reduction scratch | pivot row | displaced row |
 /// pivots | row-permutation lists | two broadcast tiles (double buffered) | panel (generic path only)
+/// (tiles read as tensor-core B fragments are padded: 64 x 36 / 32 x 68 doubles)
+constexpr int TEAM_RTILE = 2304, TEAM_RS = 36, TEAM_BS = 68;
 constexpr int TEAM_SM_RED = 0, TEAM_SM_ROWK = 64, TEAM_SM_XBUF2 = 96, TEAM_SM_PIV = 128, TEAM_SM_TL = 144,
-              TEAM_SM_NT = 208, TEAM_SM_RBUF = 224, TEAM_SM_RBUF1 = TEAM_SM_RBUF + TEAM_RBUF,
-              TEAM_SM_PANEL = TEAM_SM_RBUF1 + TEAM_RBUF;
+              TEAM_SM_NT = 208, TEAM_SM_RBUF = 224, TEAM_SM_RBUF1 = TEAM_SM_RBUF + TEAM_RTILE,
+              TEAM_SM_PANEL = TEAM_SM_RBUF1 + TEAM_RTILE;
 /// rows path (nx <= 512): ring of matrix elements in flight (cp.async), TEAM_ST stages of TEAM_GC
 /// columns x 512 rows; aliases the panel of the generic path (a launch uses one of the two)
 constexpr int TEAM_GC = 8, TEAM_ST = 4, TEAM_SM_XSTAGE = TEAM_SM_PANEL,
@@ -61,6 +63,12 @@ __device__ __forceinline__ void pb_cp_async8(double* smem_dst, const double* gsr
 __device__ __forceinline__ void pb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void pb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+/// FP64 tensor-core MMA, D(8x8) += A(8x4) * B(4x8).  Fragments: a = A[lane>>2][lane&3],
+/// b = B[lane&3][lane>>2], d0/d1 = D[lane>>2][2*(lane&3) + {0,1}]
+__device__ __forceinline__ void pb_dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 #endif
 
 /// Per-team working set: pointers into the team's slice of the HBM workspace plus the staging
@@ -557,37 +565,63 @@ struct BdfTeam {
             __syncthreads();
             const long long t_p1 = now();
             cyc_panel += t_p1 - t_p0;
-            // ---- rank-nb update of the other columns
-            const bool in_block = (i >= k0 && i < k0 + nb);
-            const int nchunks = (nx + TEAM_CW - 1) / TEAM_CW;
+            // ---- the transformed panel replaces the block columns (the update below does not touch
+            //      them), and goes to the tensor-core fragment layout through shared memory: warp w
+            //      owns rows 32w..32w+31 as four 8-row tiles, W fragments for all 8 k-steps in registers
             double* const xs = sm + TEAM_SM_XSTAGE;
+            if (rowok) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c < nb) A[i + (size_t)(k0 + c) * nx] = prow[c];
+            }
+#pragma unroll
+            for (int c = 0; c < NB; ++c) xs[c * 512 + i] = prow[c];
+            __syncwarp();
+            const int lane = i & 31, lq = lane & 3, lr = lane >> 2;
+            const int rbase = (i & ~31) + lr;  // row of m-tile 0 this lane's fragments belong to
+            double wfr[4][NB / 4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+                for (int ks = 0; ks < NB / 4; ++ks) wfr[mt][ks] = xs[(4 * ks + lq) * 512 + rbase + 8 * mt];
+            }
+            __syncwarp();  // the ring below reuses this staging area
+            // ---- rank-nb update of the other columns on the FP64 tensor cores:
+            //      C(32 rows of the warp x 8 columns) = C' + W(32 x nb) * R(nb x 8) per column group
+            const int nchunks = (nx + TEAM_CW - 1) / TEAM_CW;
             auto r_entry = [&](int ch, int e) -> double {  // entry e of the pivot-row tile of chunk ch
                 const int jj = e / NB, kk = e - jj * NB;
                 const int j = ch * TEAM_CW + jj;
                 return (kk < nb && j < nx) ? A[(k0 + kk) + (size_t)j * nx] : 0.0;
             };
+            auto r_pos = [&](int e) { return (e / NB) * TEAM_RS + (e % NB); };  // padded: conflict-free fragment reads
             {
                 double* const b0 = sm + TEAM_SM_RBUF;
 #pragma unroll
                 for (int u = 0; u < TEAM_RBUF / 512; ++u) {
                     const int e = i + u * 512;
-                    b0[e] = r_entry(0, e);
+                    b0[r_pos(e)] = r_entry(0, e);
                 }
             }
             __syncthreads();
-            // this thread's elements of the next TEAM_ST-1 column groups are always in flight
+            // this lane's fragment elements of the next TEAM_ST-1 column groups are always in flight
             // (cp.async into its own slots of the ring: no barrier needed to read them back)
             constexpr int GC = TEAM_GC, ST = TEAM_ST;
+            static_assert(GC == 8, "one 8-column tensor-core tile per group");
             const int ngroups = (nx + GC - 1) / GC;
             auto col_ok = [&](int j) { return j < nx && !(j >= k0 && j < k0 + nb); };
+            auto row_in_block = [&](int r) { return r >= k0 && r < k0 + nb; };
             auto issue = [&](int g) {
                 if (g < ngroups) {
                     double* dst = xs + (size_t)((g % ST) * GC) * 512 + i;
 #pragma unroll
-                    for (int u = 0; u < GC; ++u) {
-                        const int j = g * GC + u;
-                        const bool ok = rowok && !in_block && col_ok(j);
-                        pb_cp_async8(dst + u * 512, ok ? A + i + (size_t)j * nx : A, ok ? 8 : 0);
+                    for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int r = rbase + 8 * mt, j = g * GC + 2 * lq + e;
+                            const bool ok = r < nx && !row_in_block(r) && col_ok(j);
+                            pb_cp_async8(dst + (mt * 2 + e) * 512, ok ? A + r + (size_t)j * nx : A, ok ? 8 : 0);
+                        }
                     }
                 }
                 pb_cp_async_commit();
@@ -608,42 +642,145 @@ struct BdfTeam {
                     issue(g + ST - 1);
                     pb_cp_async_wait<ST - 1>();
                     const double* src = xs + (size_t)((g % ST) * GC) * 512 + i;
-                    double xc[GC];
+                    double c[4][2];
 #pragma unroll
-                    for (int u = 0; u < GC; ++u) xc[u] = src[u * 512];
-                    const double2* r2 = reinterpret_cast<const double2*>(cur + gl * GC * NB);
-#pragma unroll
-                    for (int k2 = 0; k2 < NB / 2; ++k2) {
-#pragma unroll
-                        for (int u = 0; u < GC; ++u) {
-                            const double2 rv = r2[u * (NB / 2) + k2];
-                            xc[u] += prow[2 * k2] * rv.x;
-                            xc[u] += prow[2 * k2 + 1] * rv.y;
-                        }
+                    for (int mt = 0; mt < 4; ++mt) {
+                        c[mt][0] = src[(mt * 2) * 512];
+                        c[mt][1] = src[(mt * 2 + 1) * 512];
                     }
-                    if (rowok) {
+                    const double* rt = cur + (gl * GC + lr) * TEAM_RS + lq;  // B fragment: R[4ks + lq][column lr]
 #pragma unroll
-                        for (int u = 0; u < GC; ++u)
-                            if (col_ok(g * GC + u)) A[i + (size_t)(g * GC + u) * nx] = xc[u];
+                    for (int ks = 0; ks < NB / 4; ++ks) {
+                        const double bf = rt[4 * ks];
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) pb_dmma(c[mt][0], c[mt][1], wfr[mt][ks], bf);
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int r = rbase + 8 * mt, j = g * GC + 2 * lq + e;
+                            if (r < nx && col_ok(j)) A[r + (size_t)j * nx] = c[mt][e];
+                        }
                     }
                 }
                 if (ch + 1 < nchunks) {
 #pragma unroll
-                    for (int u = 0; u < TEAM_RBUF / 512; ++u) nxt[i + u * 512] = rpre[u];
+                    for (int u = 0; u < TEAM_RBUF / 512; ++u) nxt[r_pos(i + u * 512)] = rpre[u];
                 }
                 __syncthreads();
             }
             pb_cp_async_wait<0>();
-            // ---- the transformed panel replaces the block columns
-            if (rowok) {
-#pragma unroll
-                for (int c = 0; c < NB; ++c)
-                    if (c < nb) A[i + (size_t)(k0 + c) * nx] = prow[c];
-            }
             __syncthreads();
             cyc_update += now() - t_p1;
         }
         return 0;
+    }
+
+    /// The solve GEMM of up to 32 right-hand sides for nx <= blockDim.x on the FP64 tensor cores:
+    /// warp w accumulates rows 32w..32w+31 (four 8-row tiles) x 32 columns (four 8-column tiles) in
+    /// registers; its fragments of the inverse stream from HBM/L2 through the cp.async ring (two
+    /// k-steps per group), the right-hand-side tile of the next 64 rows is fetched through the pivot
+    /// order while the current one is used.
+    __device__ __noinline__ void solve_pass_mma(int c0, int nc, double nsc) {
+        constexpr int KC = 64, NT = 4, PRE = (KC * 8 * NT) / 512;
+        static_assert(8 * NT * TEAM_BS <= TEAM_RTILE, "tile does not fit");
+        const int i = threadIdx.x;
+        const int lane = i & 31, lq = lane & 3, lr = lane >> 2;
+        const int rbase = (i & ~31) + lr;
+        double* const sm = smem_base();
+        const double* const A = w.A;
+        const double* const b = w.b;
+        const int* const perm = w.perm;
+        auto b_entry = [&](int ch, int e) -> double {
+            const int cc = e / KC, kk = e - cc * KC;
+            const int k = ch * KC + kk;
+            return (k < nx && cc < nc) ? b[perm[k] + (size_t)(c0 + cc) * nx] : 0.0;
+        };
+        auto b_pos = [&](int e) { return (e / KC) * TEAM_BS + (e % KC); };
+        double c[4][NT][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) c[mt][nt][0] = c[mt][nt][1] = 0.0;
+        const int nchunks = (nx + KC - 1) / KC;
+        __syncthreads();
+        {
+            double* const b0 = sm + TEAM_SM_RBUF;
+#pragma unroll
+            for (int u = 0; u < PRE; ++u) {
+                const int e = i + u * 512;
+                b0[b_pos(e)] = b_entry(0, e);
+            }
+        }
+        __syncthreads();
+        constexpr int GK = TEAM_GC, ST = TEAM_ST;
+        static_assert(GK == 8, "two k-steps per group");
+        double* const xs = sm + TEAM_SM_XSTAGE;
+        const int ngk = (nx + GK - 1) / GK;
+        auto issue = [&](int g) {
+            if (g < ngk) {
+                double* dst = xs + (size_t)((g % ST) * GK) * 512 + i;
+#pragma unroll
+                for (int ks2 = 0; ks2 < 2; ++ks2) {
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) {
+                        const int r = rbase + 8 * mt, k = g * GK + 4 * ks2 + lq;
+                        const bool ok = r < nx && k < nx;
+                        pb_cp_async8(dst + (ks2 * 4 + mt) * 512, ok ? A + r + (size_t)k * nx : A, ok ? 8 : 0);
+                    }
+                }
+            }
+            pb_cp_async_commit();
+        };
+#pragma unroll
+        for (int g = 0; g < ST - 1; ++g) issue(g);
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const double* const cur = sm + ((ch & 1) ? TEAM_SM_RBUF1 : TEAM_SM_RBUF);
+            double* const nxt = sm + ((ch & 1) ? TEAM_SM_RBUF : TEAM_SM_RBUF1);
+            double bpre[PRE];
+            if (ch + 1 < nchunks) {
+#pragma unroll
+                for (int u = 0; u < PRE; ++u) bpre[u] = b_entry(ch + 1, i + u * 512);
+            }
+            for (int gl = 0; gl < KC / GK; ++gl) {
+                const int g = ch * (KC / GK) + gl;
+                if (g >= ngk) break;
+                issue(g + ST - 1);
+                pb_cp_async_wait<ST - 1>();
+                const double* src = xs + (size_t)((g % ST) * GK) * 512 + i;
+#pragma unroll
+                for (int ks2 = 0; ks2 < 2; ++ks2) {
+                    double af[4];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) af[mt] = src[(ks2 * 4 + mt) * 512];
+                    const double* bt = cur + lr * TEAM_BS + gl * GK + 4 * ks2 + lq;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const double bf = bt[8 * nt * TEAM_BS];
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) pb_dmma(c[mt][nt][0], c[mt][nt][1], af[mt], bf);
+                    }
+                }
+            }
+            if (ch + 1 < nchunks) {
+#pragma unroll
+                for (int u = 0; u < PRE; ++u) nxt[b_pos(i + u * 512)] = bpre[u];
+            }
+            __syncthreads();
+        }
+        pb_cp_async_wait<0>();
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int r = rbase + 8 * mt, col = 8 * nt + 2 * lq + e;
+                    if (r < nx && col < nc) w.scr[r + (size_t)(c0 + col) * nx] = nsc * c[mt][nt][e];
+                }
+            }
+        }
     }
 
     /// The solve GEMM for nx <= blockDim.x (one matrix row per thread): the right-hand-side tile of
@@ -836,13 +973,19 @@ struct BdfTeam {
 #endif
                 solve_pass<1>(cmin, 1, nsc);
         } else {
-            for (int c0 = cmin; c0 <= cmax; c0 += TEAM_TN) {
-                const int nc = (cmax + 1 - c0 < TEAM_TN) ? cmax + 1 - c0 : TEAM_TN;
 #if defined(__CUDA_ARCH__)
-                if (rows_path) solve_pass_rows<TEAM_TN>(c0, nc, nsc);
-                else
+            if (rows_path) {
+                for (int c0 = cmin; c0 <= cmax; c0 += 32) {
+                    const int nc = (cmax + 1 - c0 < 32) ? cmax + 1 - c0 : 32;
+                    solve_pass_mma(c0, nc, nsc);
+                }
+            } else
 #endif
+            {
+                for (int c0 = cmin; c0 <= cmax; c0 += TEAM_TN) {
+                    const int nc = (cmax + 1 - c0 < TEAM_TN) ? cmax + 1 - c0 : TEAM_TN;
                     solve_pass<TEAM_TN>(c0, nc, nsc);
+                }
             }
         }
         tm.sync();
