@@ -48,6 +48,9 @@ class NetworkSpec:
     csc_ptr: np.ndarray   # the same pattern in CSC (AMICI's JSparse) ...
     csc_row: np.ndarray
     csc_from_csr: np.ndarray  # ... and where each CSC entry sits in the CSR value array
+    jell_w: int               # the same pattern in ELL form (device: coalesced row-parallel J*s):
+    jell_col: np.ndarray      # column of the t-th entry of row i at [t*nx + i], -1 = padding
+    jell_pos: np.ndarray      # position [t*nx + i] of CSR entry e
     x0_base: np.ndarray
     x0_kidx: np.ndarray   # constant multiplying the initial value, or -1
     o_ptr: np.ndarray     # observables: y_j = sum w * x_i
@@ -154,6 +157,14 @@ def make_network(name: str, nx: int, nr: int, np_: int, ny: int, seed: int, doc:
     csc_from_csr = order
     csc_ptr = np.concatenate([[0], np.cumsum(np.bincount(np.asarray(j_col), minlength=nx))])
 
+    jell_w = int(np.max(np.diff(j_ptr)))
+    jell_col = np.full(jell_w * nx, -1, np.int32)
+    jell_pos = np.zeros(nnz, np.int32)
+    for i in range(nx):
+        for t, e in enumerate(range(j_ptr[i], j_ptr[i + 1])):
+            jell_col[t * nx + i] = j_col[e]
+            jell_pos[e] = t * nx + i
+
     x0_base = rng.uniform(0.1, 2.0, nx)
     x0_kidx = np.full(nx, -1, np.int32)
     x0_kidx[0::10] = 0
@@ -170,6 +181,7 @@ def make_network(name: str, nx: int, nr: int, np_: int, ny: int, seed: int, doc:
         s_ptr=I32(s_ptr), s_reac=I32(s_reac), s_coef=F64(s_coef),
         j_ptr=I32(j_ptr), j_col=I32(j_col), jt_ptr=I32(jt_ptr), jt_reac=I32(jt_reac), jt_other=I32(jt_other),
         jt_coef=F64(jt_coef), csc_ptr=I32(csc_ptr), csc_row=I32(csc_row), csc_from_csr=I32(csc_from_csr),
+        jell_w=jell_w, jell_col=jell_col, jell_pos=jell_pos,
         x0_base=x0_base, x0_kidx=x0_kidx, o_ptr=I32(o_ptr), o_idx=I32(o_idx), o_w=F64(o_w),
         sigma0=np.full(ny, 0.1), p_nominal=[1.0] * np_, k_nominal=[1.0, 1.0], doc=doc)
 
@@ -197,17 +209,17 @@ def emit_tables_header(s: NetworkSpec, path: str) -> None:
     for nm, ct in [("r_a", "int"), ("r_b", "int"), ("kappa", "double"), ("pidx", "int"), ("s_ptr", "int"),
                    ("s_reac", "int"), ("s_coef", "double"), ("j_ptr", "int"), ("j_col", "int"), ("jt_ptr", "int"),
                    ("jt_reac", "int"), ("jt_other", "int"), ("jt_coef", "double"), ("csc_ptr", "int"),
-                   ("csc_row", "int"), ("csc_from_csr", "int"), ("x0_base", "double"), ("x0_kidx", "int"),
+                   ("csc_row", "int"), ("csc_from_csr", "int"), ("jell_col", "int"), ("jell_pos", "int"), ("x0_base", "double"), ("x0_kidx", "int"),
                    ("o_ptr", "int"), ("o_idx", "int"), ("o_w", "double"), ("sigma0", "double")]:
         A(_arr(nm, ct, getattr(s, nm)))
     A("inline NetTables tables() {")
     A("    NetTables t;")
     A('    t.name = "%s";' % s.name)
     A("    t.nx = %d; t.nr = %d; t.np = %d; t.nk = %d; t.ny = %d; t.nnz = %d;" % (s.nx, s.nr, s.np, s.nk, s.ny, s.nnz))
-    A("    t.n_s = %d; t.n_jt = %d; t.n_o = %d;" % (len(s.s_reac), len(s.jt_reac), len(s.o_idx)))
+    A("    t.n_s = %d; t.n_jt = %d; t.n_o = %d; t.jell_w = %d;" % (len(s.s_reac), len(s.jt_reac), len(s.o_idx), s.jell_w))
     A("    t.flops_xdot = %d; t.flops_J = %d; t.flops_dxdotdp = %d;" % (fl["xdot"], fl["J"], fl["dxdotdp"]))
     for nm in ["r_a", "r_b", "kappa", "pidx", "s_ptr", "s_reac", "s_coef", "j_ptr", "j_col", "jt_ptr", "jt_reac",
-               "jt_other", "jt_coef", "csc_ptr", "csc_row", "csc_from_csr", "x0_base", "x0_kidx", "o_ptr", "o_idx",
+               "jt_other", "jt_coef", "csc_ptr", "csc_row", "csc_from_csr", "jell_col", "jell_pos", "x0_base", "x0_kidx", "o_ptr", "o_idx",
                "o_w", "sigma0"]:
         A("    t.%s = %s;" % (nm, nm))
     A("    return t;")

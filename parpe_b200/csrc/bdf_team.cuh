@@ -42,6 +42,7 @@ constexpr int TEAM_CW = 64;         // columns per chunk of the rank-NB update
 constexpr int TEAM_RBUF = TEAM_NB_MAX * TEAM_CW;  // doubles in the broadcast tile
 constexpr int TEAM_TN = 26;         // right-hand-side columns per pass of the solve GEMM
 constexpr int TEAM_MAXNY = 16;
+constexpr int TEAM_JW_MAX = 24;     // widest Jacobian row (ELL width) the sensitivity right-hand side holds in registers
 /// shared-memory layout of the team kernel (doubles): reduction scratch | pivot row | displaced row |
 /// pivots | row-permutation lists | two broadcast tiles (double buffered) | panel (generic path only)
 /// (tiles read as tensor-core B fragments are padded: 64 x 36 / 32 x 68 doubles)
@@ -92,7 +93,7 @@ struct TeamWork {
     /// doubles of HBM workspace one team needs
     static size_t hbm_doubles(const NetTables& T) {
         const size_t nxc = (size_t)T.nx * (T.np + 1);
-        size_t n = (cv::L_MAX + 4) * nxc + (size_t)T.nx * T.np + (size_t)T.nx * T.nx + 2 * (size_t)T.nnz + 3 * (size_t)T.nx +
+        size_t n = (cv::L_MAX + 4) * nxc + (size_t)T.nx * T.np + (size_t)T.nx * T.nx + 2 * (size_t)T.jell_w * T.nx + 3 * (size_t)T.nx +
                    2 * (size_t)T.nr + T.np + T.nk + (T.np + 1);
         n += ((size_t)T.np + T.nx + 1) / 2 + 1;  // plist, perm (ints)
         return (n + 15) & ~(size_t)15;
@@ -108,8 +109,8 @@ struct TeamWork {
         scr = q; q += nxc;
         dfdp = q; q += (size_t)T.nx * T.np;
         A = q; q += (size_t)T.nx * T.nx;
-        Jsaved = q; q += T.nnz;
-        Jcur = q; q += T.nnz;
+        Jsaved = q; q += (size_t)T.jell_w * T.nx;  // Jacobians in ELL layout
+        Jcur = q; q += (size_t)T.jell_w * T.nx;
         ysh = q; q += T.nx;
         yj = q; q += T.nx;
         fout = q; q += T.nx;
@@ -191,6 +192,22 @@ struct BdfTeam {
 #else
 #define PT_UNROLL4
 #endif
+    /// staging area for the corrected sensitivity vectors of a batch of columns: 16 columns of 512
+    /// doubles in shared memory on the rows path (the ring, idle during right-hand sides), otherwise
+    /// all columns at once in the scratch array in HBM
+    PB_HD double* sens_stage(int& batch_cols, int& stride) const {
+#if defined(__CUDA_ARCH__)
+        if (nx <= 512) {
+            batch_cols = (TEAM_ST * TEAM_GC * 512) / 512 / 2;  // 16
+            stride = 512;
+            return smem_base() + TEAM_SM_XSTAGE;
+        }
+#endif
+        batch_cols = ns > 0 ? ns : 1;
+        stride = nx;
+        return w.scr;
+    }
+
 #define PT_FOR(e, e0, e1) PT_UNROLL4 for (int e = (e0) + tm.tid(); e < (e1); e += tm.size())
 #define PT_FOR_BATCH(eb, e0, e1, U) for (int eb = (e0) + tm.tid(); eb < (e1); eb += (U) * tm.size())
 #define PT_FOR_ELEMS(e) PT_FOR(e, 0, nx * ncol)
@@ -250,7 +267,7 @@ struct BdfTeam {
     PB_HD void refresh_Jcur() {
         tm.sync();
         net::rates(T, tm, w.ysh, w.p, w.vb, (double*)nullptr);
-        net::jac_values(T, tm, w.ysh, w.p, w.Jcur);
+        net::jac_values(T, tm, w.ysh, w.p, w.Jcur, true);
         tm.sync();
         net::dxdotdp_dense(T, tm, w.vb, w.dfdp);
         tm.sync();
@@ -264,6 +281,65 @@ struct BdfTeam {
         const bool ok = net::xdot_from_rates(T, tm, w.v, w.fout);
         nfe++;
         return !tm.any(!ok);
+    }
+
+    /// Sensitivity right-hand sides of all columns (out of line: its own register allocation).
+    /// Returns true if a value is not finite (thread-local; the caller reduces).
+#if defined(__CUDACC__)
+    __host__ __device__ __noinline__
+#endif
+    bool rhs_sens(bool raw) {
+        bool bad = false;
+        // Columns in batches: the corrected sensitivity vectors of a batch go to the staging area
+        // (shared memory on the rows path), then every thread produces elements of
+        // dxdotdp + J*s from the ELL Jacobian -- coalesced loads of the matrix entries shared by
+        // all columns, gathers from the staged vectors, four elements per thread in lock-step.
+        const double* __restrict__ z0 = w.zn(0);
+        const double* __restrict__ z1 = w.zn(1);
+        const double* __restrict__ ac = w.acor;
+        const double* __restrict__ jc = w.Jcur;
+        const double* __restrict__ dfdp = w.dfdp;
+        const int* __restrict__ jcol = T.jell_col;
+        double* __restrict__ bb = w.b;
+        const int jw = T.jell_w;
+        int CB, sstride;
+        double* const stage = sens_stage(CB, sstride);
+        for (int cb = 1; cb <= ns; cb += CB) {
+            const int ncb = (ns + 1 - cb < CB) ? ns + 1 - cb : CB;
+            const int nel = ncb * nx;
+            tm.sync();
+            PT_FOR(x, 0, nel) {
+                const int cl = x / nx, i = x - cl * nx;
+                const size_t e = (size_t)(cb + cl) * nx + i;
+                stage[(size_t)cl * sstride + i] = z0[e] + ac[e];
+            }
+            tm.sync();
+            // one matrix row per thread: its (padded) ELL entries in registers, reused for every
+            // column of the batch; padding entries carry the value 0 and gather element 0
+            for (int i = tm.tid(); i < nx; i += tm.size()) {
+                double jv[TEAM_JW_MAX];
+                int jn[TEAM_JW_MAX];
+                PB_UNROLL
+                for (int t = 0; t < TEAM_JW_MAX; ++t) {
+                    const int j = (t < jw) ? jcol[t * nx + i] : -1;
+                    jn[t] = j >= 0 ? j : 0;
+                    jv[t] = j >= 0 ? jc[t * nx + i] : 0.0;
+                }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
+                for (int cl = 0; cl < ncb; ++cl) {
+                    const size_t e = (size_t)(cb + cl) * nx + i;
+                    const double* sv = stage + (size_t)cl * sstride;
+                    double F = dfdp[i + (size_t)w.plist[cb + cl - 1] * nx];
+                    PB_UNROLL
+                    for (int t = 0; t < TEAM_JW_MAX; ++t) F += jv[t] * sv[jn[t]];
+                    if (!PB_FINITE(F)) bad = true;
+                    bb[e] = raw ? F : (rl1 * z1[e] + ac[e]) - gamma * F;
+                }
+            }
+        }
+        return bad;
     }
 
     /// Right-hand sides of the columns of `phase` at v = zn[0] + acor:
@@ -280,28 +356,7 @@ struct BdfTeam {
                 w.b[i] = raw ? F : (rl1 * w.zn(1)[i] + w.acor[i]) - gamma * F;
             }
         } else {
-            const double* __restrict__ z0 = w.zn(0);
-            const double* __restrict__ z1 = w.zn(1);
-            const double* __restrict__ ac = w.acor;
-            const double* __restrict__ jc = w.Jcur;
-            const double* __restrict__ dfdp = w.dfdp;
-            {
-                double* __restrict__ sc = w.scr;
-                PT_FOR(e, nx, nx * ncol) sc[e] = z0[e] + ac[e];
-            }
-            tm.sync();
-            const double* __restrict__ sc = w.scr;
-            double* __restrict__ bb = w.b;
-            PT_FOR(e, nx, nx * ncol) {
-                const int c = e / nx, i = e - c * nx;
-                const double* s = sc + (size_t)c * nx;
-                double F = dfdp[i + (size_t)w.plist[c - 1] * nx];
-                const int k1 = T.j_ptr[i + 1];
-                PT_UNROLL4
-                for (int kk = T.j_ptr[i]; kk < k1; ++kk) F += jc[kk] * s[T.j_col[kk]];
-                if (!PB_FINITE(F)) bad = true;
-                bb[e] = raw ? F : (rl1 * z1[e] + ac[e]) - gamma * F;
-            }
+            bad = rhs_sens(raw);
             nfSe += ns;
             bad = tm.any(bad);
         }
@@ -337,9 +392,9 @@ struct BdfTeam {
         PT_FOR(i, 0, nx) w.perm[i] = i;
         tm.sync();
         PT_FOR(i, 0, nx) {
-            for (int kk = T.j_ptr[i]; kk < T.j_ptr[i + 1]; ++kk) {
-                const int j = T.j_col[kk];
-                A[i + (size_t)j * nx] = (i == j ? 1.0 : 0.0) - gamma * w.Jsaved[kk];
+            for (int t = 0; t < T.jell_w; ++t) {
+                const int j = T.jell_col[t * nx + i];
+                if (j >= 0) A[i + (size_t)j * nx] = (i == j ? 1.0 : 0.0) - gamma * w.Jsaved[t * nx + i];
             }
         }
         tm.sync();
@@ -892,7 +947,7 @@ struct BdfTeam {
         int ret = 0;
         tm.sync();
         if (jbad) {
-            const bool ok = net::jac_values(T, tm, w.yj, w.p, w.Jsaved);
+            const bool ok = net::jac_values(T, tm, w.yj, w.p, w.Jsaved, true);
             if (tm.any(!ok)) ret = 1;  // AMICI's fJ returns checkFinite(J): recoverable
         }
         if (ret == 0) ret = invert_newton_matrix();

@@ -16,6 +16,7 @@ struct NetTables {
     const char* name;
     int nx, nr, np, nk, ny, nnz;
     int n_s, n_jt, n_o;
+    int jell_w;  // ELL width (max structural non-zeros per Jacobian row)
     int flops_xdot, flops_J, flops_dxdotdp;
     // reactions: v_r = kappa_r * p[pidx_r] * x[r_a] * x[r_b]   (index -1: factor 1)
     const int* r_a;
@@ -34,6 +35,10 @@ struct NetTables {
     const int* jt_reac;
     const int* jt_other;
     const double* jt_coef;
+    // ELL view (device: row-parallel J*s with coalesced loads): column of the t-th entry of row i at
+    // [t*nx + i] (-1 = padding); jell_pos[e] = that position for CSR entry e
+    const int* jell_col;
+    const int* jell_pos;
     // CSC view of the same pattern (oracle: AMICI's JSparse)
     const int* csc_ptr;
     const int* csc_row;
@@ -77,9 +82,9 @@ PB_HD bool xdot_from_rates(const NetTables& T, const Team& tm, const double* v, 
     return ok;
 }
 
-/// Jacobian values in CSR order
+/// Jacobian values in CSR order, or (ell) at the entries' ELL positions
 template <class Team>
-PB_HD bool jac_values(const NetTables& T, const Team& tm, const double* x, const double* p, double* Jv) {
+PB_HD bool jac_values(const NetTables& T, const Team& tm, const double* x, const double* p, double* Jv, bool ell = false) {
     bool ok = true;
     for (int e = tm.tid(); e < T.nnz; e += tm.size()) {
         double s = 0.0;
@@ -90,7 +95,7 @@ PB_HD bool jac_values(const NetTables& T, const Team& tm, const double* x, const
             if (o >= 0) w *= x[o];
             s += w;
         }
-        Jv[e] = s;
+        Jv[ell ? T.jell_pos[e] : e] = s;
         ok = ok && PB_FINITE(s);
     }
     return ok;

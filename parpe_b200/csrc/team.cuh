@@ -20,6 +20,7 @@ struct HostTeam {
     PB_HD int nwarps() const { return 1; }
     static constexpr int WARP = 1;
     PB_HD void sync() const {}
+    PB_HD void warp_sync() const {}
     PB_HD double warp_sum(double v) const { return v; }
     PB_HD double sum(double v) const { return v; }
     PB_HD double max(double v) const { return v; }
@@ -45,6 +46,7 @@ struct CtaTeam {
     __device__ __forceinline__ int warp() const { return threadIdx.x >> 5; }
     __device__ __forceinline__ int nwarps() const { return blockDim.x >> 5; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
     __device__ __forceinline__ double warp_sum(double v) const {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -143,8 +143,8 @@ inline void* team_create_state(const NetTables& H, int sm_count, std::string* er
         team_destroy_state(st);
         return nullptr;
     };
-    if (H.ny > TEAM_MAXNY) {
-        if (err) *err = "too many observables for the team kernel";
+    if (H.ny > TEAM_MAXNY || H.jell_w > TEAM_JW_MAX) {
+        if (err) *err = "too many observables / too wide a Jacobian row for the team kernel";
         delete st;
         return nullptr;
     }
@@ -154,7 +154,7 @@ inline void* team_create_state(const NetTables& H, int sm_count, std::string* er
     UP(r_a, H.nr); UP(r_b, H.nr); UP(kappa, H.nr); UP(pidx, H.nr);
     UP(s_ptr, H.nx + 1); UP(s_reac, H.n_s); UP(s_coef, H.n_s);
     UP(j_ptr, H.nx + 1); UP(j_col, H.nnz); UP(jt_ptr, H.nnz + 1); UP(jt_reac, H.n_jt); UP(jt_other, H.n_jt); UP(jt_coef, H.n_jt);
-    UP(csc_ptr, H.nx + 1); UP(csc_row, H.nnz); UP(csc_from_csr, H.nnz);
+    UP(jell_col, (size_t)H.jell_w * H.nx); UP(jell_pos, H.nnz); UP(csc_ptr, H.nx + 1); UP(csc_row, H.nnz); UP(csc_from_csr, H.nnz);
     UP(x0_base, H.nx); UP(x0_kidx, H.nx); UP(o_ptr, H.ny + 1); UP(o_idx, H.n_o); UP(o_w, H.n_o); UP(sigma0, H.ny);
 #undef UP
     // staging memory: as wide a panel as fits the SM's shared memory next to the fixed buffers

@@ -85,7 +85,7 @@ extern "C" int hs_team_solve(const char* model, const double* Jcsr, double gamma
     bdf.gamma = gamma;
     bdf.gamrat = 1.0;
     if (ncols > T.np + 1) return -2;
-    for (int e = 0; e < T.nnz; ++e) bdf.w.Jsaved[e] = Jcsr[e];
+    for (int e = 0; e < T.nnz; ++e) bdf.w.Jsaved[T.jell_pos[e]] = Jcsr[e];
     if (bdf.invert_newton_matrix() != 0) return 1;
     for (size_t e = 0; e < (size_t)T.nx * ncols; ++e) {
         bdf.w.b[e] = B[e];
