@@ -46,9 +46,9 @@ constexpr int TEAM_JW_MAX = 24;     // widest Jacobian row (ELL width) the sensi
 /// shared-memory layout of the team kernel (doubles): reduction scratch | pivot row | displaced row |
 /// pivots | row-permutation lists | two broadcast tiles (double buffered) | panel (generic path only)
 /// (tiles read as tensor-core B fragments are padded: 64 x 36 / 32 x 68 doubles)
-constexpr int TEAM_RTILE = 2304, TEAM_RS = 36, TEAM_BS = 68;
+constexpr int TEAM_RTILE = 3808, TEAM_RS = 36, TEAM_BS = 68;
 constexpr int TEAM_SM_RED = 0, TEAM_SM_ROWK = 64, TEAM_SM_XBUF2 = 96, TEAM_SM_PIV = 128, TEAM_SM_TL = 144,
-              TEAM_SM_NT = 208, TEAM_SM_RBUF = 224, TEAM_SM_RBUF1 = TEAM_SM_RBUF + TEAM_RTILE,
+              TEAM_SM_NT = 208, TEAM_SM_PERM = 224 /* 512 ints */, TEAM_SM_RBUF = 480, TEAM_SM_RBUF1 = TEAM_SM_RBUF + TEAM_RTILE,
               TEAM_SM_PANEL = TEAM_SM_RBUF1 + TEAM_RTILE;
 /// rows path (nx <= 512): ring of matrix elements in flight (cp.async), TEAM_ST stages of TEAM_GC
 /// columns x 512 rows; aliases the panel of the generic path (a launch uses one of the two)
@@ -539,6 +539,9 @@ struct BdfTeam {
         int* const tlist = reinterpret_cast<int*>(sm + TEAM_SM_TL);
         int* const tsrc = tlist + 2 * NB;
         int* const ntp = reinterpret_cast<int*>(sm + TEAM_SM_NT);
+        int* const perm_s = reinterpret_cast<int*>(sm + TEAM_SM_PERM);  // row order, written back at the end
+        perm_s[i] = i;
+        __syncthreads();
         for (int k0 = 0; k0 < nx; k0 += NB) {
             const int nb = (nx - k0 < NB) ? nx - k0 : NB;
             const long long t_p0 = now();
@@ -565,9 +568,9 @@ struct BdfTeam {
                     }
                     if (i == 0) {
                         pv[kk] = lp;
-                        const int t_ = w.perm[k];
-                        w.perm[k] = w.perm[lp];
-                        w.perm[lp] = t_;
+                        const int t_ = perm_s[k];
+                        perm_s[k] = perm_s[lp];
+                        perm_s[lp] = t_;
                     }
                     __syncthreads();
                     if (lp != k && i == lp) {
@@ -729,20 +732,23 @@ struct BdfTeam {
             __syncthreads();
             cyc_update += now() - t_p1;
         }
+        if (rowok) w.perm[i] = perm_s[i];
+        __syncthreads();
         return 0;
     }
 
-    /// The solve GEMM of up to 32 right-hand sides for nx <= blockDim.x on the FP64 tensor cores:
-    /// warp w accumulates rows 32w..32w+31 (four 8-row tiles) x 32 columns (four 8-column tiles) in
-    /// registers; its fragments of the inverse stream from HBM/L2 through the cp.async ring (two
-    /// k-steps per group), the right-hand-side tile of the next 64 rows is fetched through the pivot
-    /// order while the current one is used.
+    /// The solve GEMM of up to 8*NT right-hand sides for nx <= blockDim.x on the FP64 tensor cores.
+    /// Warp w owns rows 32w..32w+31 and sweeps over K twice, once per half of 16 rows (two 8-row
+    /// tiles x NT 8-column tiles accumulated in registers), so that every entry of the inverse is
+    /// read from HBM/L2 exactly once for all right-hand sides; its fragments stream through the
+    /// cp.async ring (four k-steps per group), the right-hand-side tile of the next 64 rows is
+    /// fetched through the pivot order while the current one is used.
+    template <int NT>
     __device__ __noinline__ void solve_pass_mma(int c0, int nc, double nsc) {
-        constexpr int KC = 64, NT = 4, PRE = (KC * 8 * NT) / 512;
+        constexpr int KC = 64, PRE = (KC * 8 * NT + 511) / 512;
         static_assert(8 * NT * TEAM_BS <= TEAM_RTILE, "tile does not fit");
         const int i = threadIdx.x;
         const int lane = i & 31, lq = lane & 3, lr = lane >> 2;
-        const int rbase = (i & ~31) + lr;
         double* const sm = smem_base();
         const double* const A = w.A;
         const double* const b = w.b;
@@ -750,89 +756,92 @@ struct BdfTeam {
         auto b_entry = [&](int ch, int e) -> double {
             const int cc = e / KC, kk = e - cc * KC;
             const int k = ch * KC + kk;
-            return (k < nx && cc < nc) ? b[perm[k] + (size_t)(c0 + cc) * nx] : 0.0;
+            return (e < KC * 8 * NT && k < nx && cc < nc) ? b[perm[k] + (size_t)(c0 + cc) * nx] : 0.0;
         };
         auto b_pos = [&](int e) { return (e / KC) * TEAM_BS + (e % KC); };
-        double c[4][NT][2];
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) c[mt][nt][0] = c[mt][nt][1] = 0.0;
         const int nchunks = (nx + KC - 1) / KC;
-        __syncthreads();
-        {
-            double* const b0 = sm + TEAM_SM_RBUF;
-#pragma unroll
-            for (int u = 0; u < PRE; ++u) {
-                const int e = i + u * 512;
-                b0[b_pos(e)] = b_entry(0, e);
-            }
-        }
-        __syncthreads();
-        constexpr int GK = TEAM_GC, ST = TEAM_ST;
-        static_assert(GK == 8, "two k-steps per group");
+        constexpr int GK = 16, ST = TEAM_ST;  // 16 k's = four k-steps per ring group
         double* const xs = sm + TEAM_SM_XSTAGE;
         const int ngk = (nx + GK - 1) / GK;
-        auto issue = [&](int g) {
-            if (g < ngk) {
-                double* dst = xs + (size_t)((g % ST) * GK) * 512 + i;
+        for (int half = 0; half < 2; ++half) {
+            const int rbase = (i & ~31) + 16 * half + lr;
+            double c[2][NT][2];
 #pragma unroll
-                for (int ks2 = 0; ks2 < 2; ++ks2) {
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                    for (int mt = 0; mt < 4; ++mt) {
-                        const int r = rbase + 8 * mt, k = g * GK + 4 * ks2 + lq;
-                        const bool ok = r < nx && k < nx;
-                        pb_cp_async8(dst + (ks2 * 4 + mt) * 512, ok ? A + r + (size_t)k * nx : A, ok ? 8 : 0);
-                    }
+                for (int nt = 0; nt < NT; ++nt) c[mt][nt][0] = c[mt][nt][1] = 0.0;
+            __syncthreads();
+            {
+                double* const b0 = sm + TEAM_SM_RBUF;
+#pragma unroll
+                for (int u = 0; u < PRE; ++u) {
+                    const int e = i + u * 512;
+                    if (e < KC * 8 * NT) b0[b_pos(e)] = b_entry(0, e);
                 }
-            }
-            pb_cp_async_commit();
-        };
-#pragma unroll
-        for (int g = 0; g < ST - 1; ++g) issue(g);
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const double* const cur = sm + ((ch & 1) ? TEAM_SM_RBUF1 : TEAM_SM_RBUF);
-            double* const nxt = sm + ((ch & 1) ? TEAM_SM_RBUF : TEAM_SM_RBUF1);
-            double bpre[PRE];
-            if (ch + 1 < nchunks) {
-#pragma unroll
-                for (int u = 0; u < PRE; ++u) bpre[u] = b_entry(ch + 1, i + u * 512);
-            }
-            for (int gl = 0; gl < KC / GK; ++gl) {
-                const int g = ch * (KC / GK) + gl;
-                if (g >= ngk) break;
-                issue(g + ST - 1);
-                pb_cp_async_wait<ST - 1>();
-                const double* src = xs + (size_t)((g % ST) * GK) * 512 + i;
-#pragma unroll
-                for (int ks2 = 0; ks2 < 2; ++ks2) {
-                    double af[4];
-#pragma unroll
-                    for (int mt = 0; mt < 4; ++mt) af[mt] = src[(ks2 * 4 + mt) * 512];
-                    const double* bt = cur + lr * TEAM_BS + gl * GK + 4 * ks2 + lq;
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        const double bf = bt[8 * nt * TEAM_BS];
-#pragma unroll
-                        for (int mt = 0; mt < 4; ++mt) pb_dmma(c[mt][nt][0], c[mt][nt][1], af[mt], bf);
-                    }
-                }
-            }
-            if (ch + 1 < nchunks) {
-#pragma unroll
-                for (int u = 0; u < PRE; ++u) nxt[b_pos(i + u * 512)] = bpre[u];
             }
             __syncthreads();
-        }
-        pb_cp_async_wait<0>();
+            auto issue = [&](int g) {
+                if (g < ngk) {
+                    double* dst = xs + (size_t)((g % ST) * 8) * 512 + i;
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
+                    for (int ks4 = 0; ks4 < 4; ++ks4) {
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
+                        for (int mt = 0; mt < 2; ++mt) {
+                            const int r = rbase + 8 * mt, k = g * GK + 4 * ks4 + lq;
+                            const bool ok = r < nx && k < nx;
+                            pb_cp_async8(dst + (ks4 * 2 + mt) * 512, ok ? A + r + (size_t)k * nx : A, ok ? 8 : 0);
+                        }
+                    }
+                }
+                pb_cp_async_commit();
+            };
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int r = rbase + 8 * mt, col = 8 * nt + 2 * lq + e;
-                    if (r < nx && col < nc) w.scr[r + (size_t)(c0 + col) * nx] = nsc * c[mt][nt][e];
+            for (int g = 0; g < ST - 1; ++g) issue(g);
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const double* const cur = sm + ((ch & 1) ? TEAM_SM_RBUF1 : TEAM_SM_RBUF);
+                double* const nxt = sm + ((ch & 1) ? TEAM_SM_RBUF : TEAM_SM_RBUF1);
+                double bpre[PRE];
+                if (ch + 1 < nchunks) {
+#pragma unroll
+                    for (int u = 0; u < PRE; ++u) bpre[u] = b_entry(ch + 1, i + u * 512);
+                }
+                for (int gl = 0; gl < KC / GK; ++gl) {
+                    const int g = ch * (KC / GK) + gl;
+                    if (g >= ngk) break;
+                    issue(g + ST - 1);
+                    pb_cp_async_wait<ST - 1>();
+                    const double* src = xs + (size_t)((g % ST) * 8) * 512 + i;
+#pragma unroll
+                    for (int ks4 = 0; ks4 < 4; ++ks4) {
+                        const double a0 = src[(ks4 * 2) * 512], a1 = src[(ks4 * 2 + 1) * 512];
+                        const double* bt = cur + lr * TEAM_BS + gl * GK + 4 * ks4 + lq;
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            const double bf = bt[8 * nt * TEAM_BS];
+                            pb_dmma(c[0][nt][0], c[0][nt][1], a0, bf);
+                            pb_dmma(c[1][nt][0], c[1][nt][1], a1, bf);
+                        }
+                    }
+                }
+                if (ch + 1 < nchunks) {
+#pragma unroll
+                    for (int u = 0; u < PRE; ++u) {
+                        const int e = i + u * 512;
+                        if (e < KC * 8 * NT) nxt[b_pos(e)] = bpre[u];
+                    }
+                }
+                __syncthreads();
+            }
+            pb_cp_async_wait<0>();
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int r = rbase + 8 * mt, col = 8 * nt + 2 * lq + e;
+                        if (r < nx && col < nc) w.scr[r + (size_t)(c0 + col) * nx] = nsc * c[mt][nt][e];
+                    }
                 }
             }
         }
@@ -1030,9 +1039,10 @@ struct BdfTeam {
         } else {
 #if defined(__CUDA_ARCH__)
             if (rows_path) {
-                for (int c0 = cmin; c0 <= cmax; c0 += 32) {
-                    const int nc = (cmax + 1 - c0 < 32) ? cmax + 1 - c0 : 32;
-                    solve_pass_mma(c0, nc, nsc);
+                for (int c0 = cmin; c0 <= cmax; c0 += 56) {
+                    const int nc = (cmax + 1 - c0 < 56) ? cmax + 1 - c0 : 56;
+                    if (nc > 24) solve_pass_mma<7>(c0, nc, nsc);
+                    else solve_pass_mma<3>(c0, nc, nsc);
                 }
             } else
 #endif
