@@ -24,7 +24,7 @@ def _load(path):
 
 
 def test_fixtures_exist():
-    assert len(FILES) >= 4
+    assert len(FILES) >= 5
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-5] for f in FILES])
@@ -39,8 +39,11 @@ def test_oracle_reproduces_fixture(oracle_available, path):
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-5] for f in FILES])
 def test_host_core_against_fixture(path):
     """No oracle library needed: device algorithm (host build) vs committed reference outputs."""
-    from tests.host_harness.binding import simulate
+    from tests.host_harness.binding import simulate, simulate_team
+    from parpe_b200.models.netmodels import NET_MODELS
     doc, tab, theta = _load(path)
+    if doc["model"] in NET_MODELS:  # large-model core (bdf_team.cuh with the one-thread team)
+        simulate = simulate_team
     for c in range(tab.n_conditions):
         p = np.empty(tab.np_)
         for i in range(tab.np_):

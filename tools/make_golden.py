@@ -25,6 +25,8 @@ CASES = {
                                                                condition_specific=2)),
     "boehm_log10": ("boehm", 4, dict(scale="log10", seed=13)),
     "fujita_log10": ("fujita", 6, dict(scale="log10", seed=14)),
+    # large-model path (table-driven mass-action network, one CTA per condition)
+    "net32_mixed": ("net32", 4, dict(scale="mixed", seed=15, sigma_mode="mixed", missing_fraction=0.1)),
 }
 
 
@@ -37,7 +39,7 @@ def build_case(name):
 
 def main():
     outdir = os.path.join(ROOT, "tests", "golden")
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):
         tab, theta = build_case(name)
         o = OracleProblem(tab, ISM_STAGGERED, LINSOL_KLU)  # AMICI's default linear solver
         r = o.evaluate(theta)
