@@ -223,6 +223,12 @@ def emit_device_header(d: Derived, path: str) -> None:
     A('    static constexpr const char* NAME = "%s";' % s.name)
     A("    static constexpr int NX = %d, NP = %d, NK = %d, NY = %d, NNZ = %d;" %
       (s.nx, s.np, max(s.nk, 0), s.ny, len(d.rowvals)))
+    dyn = [any(d.dxdotdp[r, c] != 0 for r in range(s.nx)) or any(d.sx0[r, c] != 0 for r in range(s.nx))
+           for c in range(s.np)]
+    A("    // parameters the state depends on (a non-zero column of dxdotdp or sx0): only their sensitivity")
+    A("    // columns are integrated; for the others sx == 0 identically (bit DYN_MASK >> ip)")
+    A("    static constexpr int NPD = %d;" % max(sum(dyn), 0))
+    A("    static constexpr unsigned DYN_MASK = 0x%xu;" % sum(1 << i for i, v in enumerate(dyn) if v))
     A("    // operation counts of the generated expressions (after CSE)")
     A("    static constexpr int FLOPS_XDOT = %d, FLOPS_J = %d, FLOPS_DXDOTDP = %d, NNZ_DXDOTDP = %d;" %
       (fl["xdot"], fl["J"], fl["dxdotdp"], fl["nnz_dxdotdp"]))
@@ -251,10 +257,16 @@ def emit_device_header(d: Derived, path: str) -> None:
     A("        (void)t; (void)p; (void)k; (void)x; (void)out;")
     L.extend(_switch_ip(pr, s.nx, d.dxdotdp, "out", "        "))
     A("    }")
-    A("    // all columns of d xdot / d p at once: out[r + ip*NX], structural non-zeros only (caller zero-fills once)")
+    A("    // all non-zero columns of d xdot / d p at once: out[r + ipd*NX] with ipd the rank of ip among the")
+    A("    // dynamic parameters (popcount of DYN_MASK below bit ip); structural non-zeros only (caller zero-fills once)")
     A("    PB_HD static void dxdotdp_dense(double* __restrict__ out, %s) {" % sig)
     A("        (void)t; (void)p; (void)k; (void)x; (void)out;")
-    L.extend(_nonzero_assign(pr, "out[%d]", [(r + c * s.nx, d.dxdotdp[r, c]) for c in range(s.np) for r in range(s.nx)], "        "))
+    rank = {}
+    for c in range(s.np):
+        if dyn[c]:
+            rank[c] = len(rank)
+    L.extend(_nonzero_assign(pr, "out[%d]", [(r + rank[c] * s.nx, d.dxdotdp[r, c]) for c in range(s.np) if dyn[c]
+                                             for r in range(s.nx)], "        "))
     A("    }")
     A("    PB_HD static void y(double* __restrict__ y, %s) {" % sig)
     A("        (void)t; (void)p; (void)k; (void)x;")

@@ -180,7 +180,12 @@ struct LaneGroup {
 template <class M>
 struct GroupShared {
     static constexpr int NX = M::NX;
-    static constexpr int NC = M::NP + 1;  // columns: state + one per model parameter
+    // columns: state + one per DYNAMIC model parameter (one the state depends on).  For the other
+    // parameters (noise / observable parameters) the sensitivity is identically zero -- sx0 = 0 and
+    // sxdot = J*0 + 0 -- so their columns contribute nothing to any norm or sum the reference
+    // computes and are not stored or integrated; d llh / d p for them comes from dydp / dsigmaydp.
+    static constexpr int NPD = M::NPD > 0 ? M::NPD : 0;
+    static constexpr int NC = NPD + 1;
     static constexpr int NXS = NX | 1;    // odd column stride of the norm scratch: conflict-free column sums
     alignas(16) double zn[cv::L_MAX][NX * NC];  // Nordsieck history
     alignas(16) double acor[NX * NC];           // accumulated corrector update
@@ -192,8 +197,10 @@ struct GroupShared {
     alignas(16) double Jsaved[NX * NX];  // Jacobian at its last evaluation (cvLs savedJ), column-major
     alignas(16) double Ainv[NX * NX];    // inverse of I - gamma*J, column-major
     alignas(16) double Jcur[NX * NX];    // J(tn, y_n) for the sensitivity right-hand sides
-    alignas(16) double dfdp[NX * (M::NP > 0 ? M::NP : 1)];  // d xdot / d p at (tn, y_n), column ip at [ip*NX]
-    double sllh[NC];         // d llh / d p accumulator per sensitivity column
+    // d xdot / d p at (tn, y_n): the columns of the dynamic parameters only, column of parameter ip at
+    // [rank(ip)*NX], rank = its position among the dynamic parameters
+    alignas(16) double dfdp[NX * (NPD > 0 ? NPD : 1)];
+    double sllh[(M::NP > 0 ? M::NP : 0) + 1];  // d llh / d p accumulator per plist position (index j + 1)
     double ysh[NX];          // converged state, argument of the Jacobian / observable functions
     double yj[NX];           // state handed to the out-of-line model functions (xdot, Jacobian)
     double fout[NX];         // xdot returned by eval_xdot_shared
@@ -202,7 +209,11 @@ struct GroupShared {
     double tau[cv::L_MAX + 1];
     double ssdat[6][4];      // STALD history (cvBDFStab)
     int perm[NX];            // row order after the pivot swaps of the inversion
-    int plist[M::NP > 0 ? M::NP : 1];
+    int plist[M::NP > 0 ? M::NP : 1];   // sensitivity parameter list of the condition (all entries)
+    int cplist[NPD > 0 ? NPD : 1];      // model parameter of sensitivity column c (index c - 1)
+    int cdcol[NPD > 0 ? NPD : 1];       // its column in dfdp
+    int colof[M::NP > 0 ? M::NP : 1];   // column of plist position j, 0 = not integrated (sx == 0)
+    int nsd;                            // number of integrated sensitivity columns
 };
 
 // ---- out-of-line helpers (one copy of the code each; they touch only group-shared
@@ -642,7 +653,8 @@ struct Bdf {
 #endif
     }
     SolverOptions opt;
-    int ns;      // sensitivity columns (columns 1..ns; column 0 is the state)
+    int ns;      // integrated sensitivity columns (columns 1..ns; column 0 is the state)
+    int nsall;   // plist entries of the condition (ns of them integrated, the others identically zero)
     int ncol;    // 1 + ns
     bool sensi;  // ns > 0
 
@@ -750,7 +762,7 @@ struct Bdf {
             g.sync();
             PB_UNROLL_COLS
             for (int c = 1 + col_group(); c <= ns; c += CG) {
-                const double* dcol = S()->dfdp + S()->plist[c - 1] * NX;
+                const double* dcol = S()->dfdp + S()->cdcol[c - 1] * NX;
                 const double* sc = S()->scr + c * NX;
                 double sv[NX];
                 PB_UNROLL
@@ -764,7 +776,7 @@ struct Bdf {
                     S()->b[e] = raw ? F : (rl1 * S()->zn[1][e] + S()->acor[e]) - gamma * F;
                 }
             }
-            nfSe += ns;
+            nfSe += nsall;  // counted as the reference does: one evaluation per plist entry
         }
         g.sync();
         if (g.any(bad)) return phase == PH_STATE ? cv::RHSFUNC_RECVR : cv::SRHSFUNC_RECVR;
@@ -1475,7 +1487,7 @@ struct Bdf {
             const double r = my[iy] - y[iy];
             llh -= log(s2 * 3.141592653589793 * 2.0) * 0.5 + 1.0 / s2 * (r * r) * 0.5;
         }
-        if (!sensi) return true;
+        if (nsall == 0) return true;
         double dJydy[NY], dJyds[NY];
         PB_UNROLL
         for (int iy = 0; iy < NY; ++iy) {
@@ -1505,11 +1517,12 @@ struct Bdf {
                 dJydx[ix] = a;
             }
         }
-        PB_FOR_COLS(c, 1, ns) {
+        PB_FOR_COLS(pj, 1, nsall) {
             double dydp[NY], dsdp[NY];
             PB_UNROLL
             for (int iy = 0; iy < NY; ++iy) { dydp[iy] = 0.0; dsdp[iy] = 0.0; }
-            const int ip = S()->plist[c - 1];
+            const int ip = S()->plist[pj - 1];
+            const int c = S()->colof[pj - 1];
             M::dydp(dydp, t, S()->ysh, S()->p, S()->k, ip);
             M::dsigmaydp(dsdp, t, S()->p, S()->k, ip);
             double dJydp = 0.0;
@@ -1518,9 +1531,11 @@ struct Bdf {
             PB_UNROLL
             for (int iy = 0; iy < NY; ++iy) dJydp += dJyds[iy] * dsdp[iy];
             double a = dJydp;
-            PB_UNROLL
-            for (int ix = 0; ix < NX; ++ix) a += dJydx[ix] * S()->zn[0][c * NX + ix];
-            S()->sllh[c] -= a;
+            if (c > 0) {
+                PB_UNROLL
+                for (int ix = 0; ix < NX; ++ix) a += dJydx[ix] * S()->zn[0][c * NX + ix];
+            }
+            S()->sllh[pj] -= a;
         }
         return true;
     }
@@ -1533,16 +1548,35 @@ struct Bdf {
         io_ = io;
         opt.rtol = rtol;
         opt.atol = atol;
-        ns = io.ns;
+        nsall = io.ns;
+        g.sync();
+        if (g.lane() == 0) {  // which plist entries get a sensitivity column
+            int c = 0;
+            for (int j = 0; j < nsall; ++j) {
+                const int ip = S()->plist[j];
+                if ((M::DYN_MASK >> ip) & 1u) {
+                    int rank = 0;
+                    for (int b_ = 0; b_ < ip; ++b_) rank += (int)((M::DYN_MASK >> b_) & 1u);
+                    S()->cdcol[c] = rank;
+                    S()->cplist[c] = ip;
+                    S()->colof[j] = ++c;
+                } else {
+                    S()->colof[j] = 0;
+                }
+            }
+            S()->nsd = c;
+        }
+        g.sync();
+        ns = S()->nsd;
         ncol = ns + 1;
         sensi = ns > 0;
-        g.sync();
+        for (int j = g.lane(); j <= nsall; j += G) S()->sllh[j] = 0.0;
         PB_FOR_COLS(c, 0, ns) {
             double v[NX];
             PB_UNROLL
             for (int i = 0; i < NX; ++i) v[i] = 0.0;
             if (c == 0) M::x0(v, opt.t0, S()->p, S()->k);
-            else M::sx0(v, opt.t0, S()->p, S()->k, S()->plist[c - 1]);
+            else M::sx0(v, opt.t0, S()->p, S()->k, S()->cplist[c - 1]);
             PB_UNROLL
             for (int i = 0; i < NX; ++i) {
                 const int e = c * NX + i;
@@ -1552,7 +1586,6 @@ struct Bdf {
                 S()->ewt[e] = 1.0;
                 S()->b[e] = 0.0;
             }
-            S()->sllh[c] = 0.0;
         }
         PB_UNROLL
         for (int j = 0; j < cv::L_MAX; ++j) l[j] = 0.0;
@@ -1573,7 +1606,7 @@ struct Bdf {
             S()->Jsaved[e] = 0.0;
             S()->Jcur[e] = 0.0;
         }
-        for (int e = g.lane(); e < NX * NP; e += G) S()->dfdp[e] = 0.0;
+        for (int e = g.lane(); e < NX * GroupShared<M>::NPD; e += G) S()->dfdp[e] = 0.0;
         if (g.lane() == 0) {
             for (int i = 0; i <= cv::L_MAX; ++i) S()->tau[i] = 0.0;
             for (int i = 0; i < 6; ++i)

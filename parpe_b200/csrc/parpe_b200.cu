@@ -8,6 +8,7 @@
 // There is no CPU fallback: without a CUDA device every compute entry point fails.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -126,7 +127,13 @@ struct pb200_handle {
     // per-evaluation buffers
     int cap = 0;
     DevBuf<double> d_llh, d_sllh, d_gcontrib, d_theta_tab, d_out, d_yout, d_sout;
-    DevBuf<int> d_status, d_idx, d_counter;
+    DevBuf<int> d_status, d_idx, d_counter, d_order;
+    // cost-aware processing order: positions sorted by the previous evaluation's step
+    // counts, valid while the index list is unchanged
+    std::vector<int> order_host;
+    std::vector<int64_t> stats_host;
+    bool order_valid = false;
+    int reorder = 0;  // 0 off, 1 = descending previous nst
     DevBuf<int64_t> d_stats;
     PinnedBuf<double> h_theta_tab, h_out;
     PinnedBuf<int> h_idx;
@@ -153,7 +160,9 @@ static int ensure_capacity(pb200_handle* h, int n) {
     PB_CUDA(h->d_status.alloc(cap));
     PB_CUDA(h->d_stats.alloc((size_t)cap * NSTATS));
     PB_CUDA(h->d_idx.alloc(cap));
+    PB_CUDA(h->d_order.alloc(cap));
     PB_CUDA(h->h_idx.alloc(cap));
+    h->order_valid = false;
     h->idx_cache.clear();
     h->cap = cap;
     return 0;
@@ -187,6 +196,7 @@ static int enqueue_evaluation(pb200_handle* h, const double* theta, const int* i
                             cudaMemcpyHostToDevice, stream));
     const bool same_idx = (int)h->idx_cache.size() == n && (n == 0 || !std::memcmp(h->idx_cache.data(), idx + lo, sizeof(int) * n));
     if (!same_idx) {
+        h->order_valid = false;
         std::memcpy(h->h_idx.p, idx + lo, sizeof(int) * n);
         PB_CUDA(cudaMemcpyAsync(h->d_idx.p, h->h_idx.p, sizeof(int) * n, cudaMemcpyHostToDevice, stream));
         h->idx_cache.assign(idx + lo, idx + hi);
@@ -198,7 +208,7 @@ static int enqueue_evaluation(pb200_handle* h, const double* theta, const int* i
     KernelArgs a = h->args;
     a.theta_tab = h->d_theta_tab.p;
     a.idx = h->d_idx.p;
-    a.order = nullptr;
+    a.order = (h->reorder && h->order_valid && want_grad == h->last_want_grad) ? h->d_order.p : nullptr;
     a.n = n;
     a.want_grad = want_grad;
     a.counter = h->d_counter.p;
@@ -302,6 +312,7 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
     h->nk = d->nk;
     h->ny = d->ny;
     h->lanes = d->lanes_per_condition;
+    h->reorder = std::getenv("PB200_REORDER") ? std::atoi(std::getenv("PB200_REORDER")) : 1;
     h->pscale_opt.assign(d->pscale_opt, d->pscale_opt + d->n_opt);
     h->t_offsets.assign(d->t_offsets, d->t_offsets + C + 1);
     h->nt_total = C > 0 ? d->t_offsets[C] : 0;
@@ -410,6 +421,34 @@ int pb200_evaluate(pb200_handle* h, const double* theta, int n_opt, const int* i
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop);
         *seconds = ms * 1e-3;
+    }
+    if (h->reorder && h->last_n > 1) {
+        // processing order of the next evaluation of the same index list: costliest conditions first
+        // (they also sit next to conditions of similar cost in a warp / CTA)
+        const int n = h->last_n;
+        h->stats_host.resize((size_t)n * NSTATS);
+        PB_CUDA(cudaMemcpyAsync(h->stats_host.data(), h->d_stats.p, sizeof(int64_t) * (size_t)n * NSTATS,
+                                cudaMemcpyDeviceToHost, h->stream));
+        PB_CUDA(cudaStreamSynchronize(h->stream));
+        h->order_host.resize(n);
+        for (int r = 0; r < n; ++r) h->order_host[r] = r;
+        const int64_t* st = h->stats_host.data();
+        const int mode = h->reorder;
+        std::stable_sort(h->order_host.begin(), h->order_host.end(), [st, mode](int x, int y) {
+            const int64_t* a = st + (size_t)x * NSTATS;
+            const int64_t* b = st + (size_t)y * NSTATS;
+            if (a[STAT_NST] != b[STAT_NST]) return a[STAT_NST] > b[STAT_NST];
+            if (mode >= 2) {  // conditions with the same history of setups / iterations / failures next to each other
+                if (a[STAT_NSETUPS] != b[STAT_NSETUPS]) return a[STAT_NSETUPS] > b[STAT_NSETUPS];
+                if (a[STAT_NNI] != b[STAT_NNI]) return a[STAT_NNI] > b[STAT_NNI];
+                if (a[STAT_NNIS] != b[STAT_NNIS]) return a[STAT_NNIS] > b[STAT_NNIS];
+                if (a[STAT_NETF] != b[STAT_NETF]) return a[STAT_NETF] > b[STAT_NETF];
+            }
+            return false;
+        });
+        PB_CUDA(cudaMemcpyAsync(h->d_order.p, h->order_host.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+        PB_CUDA(cudaStreamSynchronize(h->stream));
+        h->order_valid = true;
     }
     // A1: zero-filled outputs, then sums; any error or non-finite -> +inf, failure
     *fval = h->h_out.p[0];
