@@ -85,6 +85,10 @@ enum {
     PB200_STAT_NOR,       /* order reductions by STALD          */
     PB200_STAT_TRIALS,    /* tolerance-relaxation trials used   */
     PB200_STAT_QSUM,      /* sum over accepted steps of order q */
+    /* large-model kernel only (0 otherwise): device cycles of the phases of the solve, two 32-bit
+     * fields of kilo-cycles each -- diagnostics behind DESIGN.md 3.4's phase split */
+    PB200_STAT_CYC_INVERSION, /* (panel factorisation << 32) | rank-NB update */
+    PB200_STAT_CYC_NEWTON,    /* (solve GEMMs << 32) | right-hand sides       */
     PB200_NSTATS = 16
 };
 
