@@ -335,8 +335,11 @@ int launch_model(const KernelArgs& a, int lanes, int variant, int sm_count, cuda
     constexpr int GN = pb_pow2_at_least(M::NX);
     constexpr int GH = GN >= 4 ? GN / 2 : GN;
     constexpr int G2 = GN * 2 <= 32 ? GN * 2 : GN;
-    int G = GN;
-    if (lanes == GH || lanes == G2) G = lanes;
+    // default: one state index per lane; two per lane when that fills every lane (nx a power of two
+    // >= 8): half the warps walk the instruction stream for the same conditions (measured on the
+    // Boehm shape: +4.5 %; four per lane: -40 %)
+    int G = ((M::NX & (M::NX - 1)) == 0 && M::NX >= 8) ? GH : GN;
+    if (lanes == GN || lanes == GH || lanes == G2) G = lanes;
     if (lanes_used) *lanes_used = G;
     if (G == GH && GH != GN) return launch_shape<M, GH>(a, variant, sm_count, stream, grid_used, block_used);
     if (G == G2 && G2 != GN) return launch_shape<M, G2>(a, variant, sm_count, stream, grid_used, block_used);
@@ -348,7 +351,7 @@ ModelOps make_ops() {
     ModelOps o;
     o.name = M::NAME;
     o.nx = M::NX; o.np = M::NP; o.nk = M::NK; o.ny = M::NY;
-    o.default_lanes = pb_pow2_at_least(M::NX);
+    o.default_lanes = ((M::NX & (M::NX - 1)) == 0 && M::NX >= 8) ? pb_pow2_at_least(M::NX) / 2 : pb_pow2_at_least(M::NX);
     o.flops_xdot = M::FLOPS_XDOT; o.flops_J = M::FLOPS_J; o.flops_dxdotdp = M::FLOPS_DXDOTDP; o.nnzJ = M::NNZ;
     o.launch = &launch_model<M>;
     o.create_state = nullptr;
