@@ -222,3 +222,21 @@ def test_full_size_properties():
     assert_llh_close(f1 + f2, f)
     assert_grad_close(g1 + g2, g)
     assert f1 == f2 and np.array_equal(g1, g2)
+
+
+@pytest.mark.parametrize("model,lanes", [("boehm", 4), ("boehm", 8), ("boehm", 16), ("fujita", 8), ("fujita", 16),
+                                         ("steadystate", 2), ("steadystate", 4), ("steadystate", 8)])
+def test_every_lane_group_width_matches_oracle(oracle_available, model, lanes):
+    """All instantiated lane-group widths (G/2, G, 2G) run the same algorithm: each must meet the
+    parity tolerances on its own, whatever the default is."""
+    from oracle.binding import OracleProblem
+    from parpe_b200.problem import B200SummedGradientFunction
+    tab = synth.make_problem(model, 5, seed=21, lanes_per_condition=lanes)
+    theta = synth.random_theta(tab, seed=8, width=0.3)
+    gpu = B200SummedGradientFunction(tab)
+    st, fval, grad, _ = gpu.evaluate(theta)
+    assert gpu.last_launch()["lanes"] == lanes
+    ro = OracleProblem(tab).evaluate(theta)
+    assert st == ro["status"] == 0
+    assert_llh_close(fval, ro["fval"])
+    assert_grad_close(grad, ro["grad"])
