@@ -111,6 +111,22 @@ def make_network(name: str, nx: int, nr: int, np_: int, ny: int, seed: int, doc:
             ra.append(a); rb.append(b); prod.append([c])             # binding ...
             ra.append(c); rb.append(-1); prod.append([a, b])         # ... and its dissociation
     nr = len(ra)
+    # Species are numbered by decreasing number of Jacobian entries in their row, so that the 32 rows
+    # a warp works on have (nearly) the same length: the row-parallel J*s loops run to the longest
+    # row of the warp.
+    dep = [set([i]) for i in range(nx)]
+    for r in range(nr):
+        touched = [q for q in (ra[r], rb[r]) if q >= 0] + list(prod[r])
+        for sp_ in touched:
+            for q in (ra[r], rb[r]):
+                if q >= 0:
+                    dep[sp_].add(q)
+    order = sorted(range(nx), key=lambda i: (-len(dep[i]), i))
+    newidx = np.empty(nx, np.int64)
+    newidx[order] = np.arange(nx)
+    ra = [int(newidx[q]) if q >= 0 else -1 for q in ra]
+    rb = [int(newidx[q]) if q >= 0 else -1 for q in rb]
+    prod = [[int(newidx[q]) for q in pr_] for pr_ in prod]
     ra = np.asarray(ra, np.int32)
     rb = np.asarray(rb, np.int32)
     kappa = 10.0 ** rng.uniform(-4.0, 2.0, nr)

@@ -48,7 +48,7 @@ constexpr int TEAM_JW_MAX = 24;     // widest Jacobian row (ELL width) the sensi
 /// (tiles read as tensor-core B fragments are padded: 64 x 36 / 32 x 68 doubles)
 constexpr int TEAM_RTILE = 3808, TEAM_RS = 36, TEAM_BS = 68;
 constexpr int TEAM_SM_RED = 0, TEAM_SM_ROWK = 64, TEAM_SM_XBUF2 = 96, TEAM_SM_PIV = 128, TEAM_SM_TL = 144,
-              TEAM_SM_NT = 208, TEAM_SM_PERM = 224 /* 512 ints */, TEAM_SM_RBUF = 480, TEAM_SM_RBUF1 = TEAM_SM_RBUF + TEAM_RTILE,
+              TEAM_SM_NT = 208, TEAM_SM_PERM = 224 /* 512 ints */, TEAM_SM_SLOT = 480 /* 512 ints */, TEAM_SM_RBUF = 736, TEAM_SM_RBUF1 = TEAM_SM_RBUF + TEAM_RTILE,
               TEAM_SM_PANEL = TEAM_SM_RBUF1 + TEAM_RTILE;
 /// rows path (nx <= 512): ring of matrix elements in flight (cp.async), TEAM_ST stages of TEAM_GC
 /// columns x 512 rows; aliases the panel of the generic path (a launch uses one of the two)
@@ -188,7 +188,7 @@ struct BdfTeam {
 // than their loads use __restrict__ pointers and are unrolled by 4 (PT_FOR); in-place updates load
 // a batch of PT_U elements into registers before the first store (PT_FOR_BATCH).
 #if defined(__CUDA_ARCH__)
-#define PT_UNROLL4 _Pragma("unroll 4")
+#define PT_UNROLL4 _Pragma("unroll 8")
 #else
 #define PT_UNROLL4
 #endif
@@ -208,6 +208,12 @@ struct BdfTeam {
         return w.scr;
     }
 
+// out of line on the device: own register allocation for the sweeps that hold a batch in registers
+#if defined(__CUDACC__)
+#define PT_NOINLINE __host__ __device__ __noinline__
+#else
+#define PT_NOINLINE
+#endif
 #define PT_FOR(e, e0, e1) PT_UNROLL4 for (int e = (e0) + tm.tid(); e < (e1); e += tm.size())
 #define PT_FOR_BATCH(eb, e0, e1, U) for (int eb = (e0) + tm.tid(); eb < (e1); eb += (U) * tm.size())
 #define PT_FOR_ELEMS(e) PT_FOR(e, 0, nx * ncol)
@@ -316,15 +322,22 @@ struct BdfTeam {
             tm.sync();
             // one matrix row per thread: its (padded) ELL entries in registers, reused for every
             // column of the batch; padding entries carry the value 0 and gather element 0
-            for (int i = tm.tid(); i < nx; i += tm.size()) {
+            for (int i0 = 0; i0 < nx; i0 += tm.size()) {  // (whole warps enter: warp_max_int below)
+                const int i = i0 + tm.tid();
+                const bool rowok = i < nx;
                 double jv[TEAM_JW_MAX];
                 int jn[TEAM_JW_MAX];
+                int len = 0;
                 PB_UNROLL
                 for (int t = 0; t < TEAM_JW_MAX; ++t) {
-                    const int j = (t < jw) ? jcol[t * nx + i] : -1;
+                    const int j = (rowok && t < jw) ? jcol[t * nx + i] : -1;
                     jn[t] = j >= 0 ? j : 0;
                     jv[t] = j >= 0 ? jc[t * nx + i] : 0.0;
+                    if (j >= 0) len = t + 1;
                 }
+                // rows are numbered by decreasing length (netgen): the warp's longest row bounds the loop
+                const int wlen = tm.warp_max_int(len);
+                if (!rowok) continue;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 2
 #endif
@@ -333,7 +346,8 @@ struct BdfTeam {
                     const double* sv = stage + (size_t)cl * sstride;
                     double F = dfdp[i + (size_t)w.plist[cb + cl - 1] * nx];
                     PB_UNROLL
-                    for (int t = 0; t < TEAM_JW_MAX; ++t) F += jv[t] * sv[jn[t]];
+                    for (int t = 0; t < TEAM_JW_MAX; ++t)
+                        if (t < wlen) F += jv[t] * sv[jn[t]];
                     if (!PB_FINITE(F)) bad = true;
                     bb[e] = raw ? F : (rl1 * z1[e] + ac[e]) - gamma * F;
                 }
@@ -529,6 +543,9 @@ struct BdfTeam {
     /// tile double-buffered in shared memory.
     __device__ __noinline__ int invert_rows() {
         constexpr int NB = TEAM_NB_MAX;
+        // members used in the loops are copied to locals: the object is addressable (out-of-line member
+        // function), so a store through a generic pointer would force a reload of every member after it
+        const int nx = this->nx;
         double* const A = w.A;
         const int i = threadIdx.x;
         const bool rowok = i < nx;
@@ -540,7 +557,9 @@ struct BdfTeam {
         int* const tsrc = tlist + 2 * NB;
         int* const ntp = reinterpret_cast<int*>(sm + TEAM_SM_NT);
         int* const perm_s = reinterpret_cast<int*>(sm + TEAM_SM_PERM);  // row order, written back at the end
+        int* const slot_of = reinterpret_cast<int*>(sm + TEAM_SM_SLOT);
         perm_s[i] = i;
+        slot_of[i] = -1;
         __syncthreads();
         for (int k0 = 0; k0 < nx; k0 += NB) {
             const int nb = (nx - k0 < NB) ? nx - k0 : NB;
@@ -548,45 +567,60 @@ struct BdfTeam {
             double prow[NB];
 #pragma unroll
             for (int c = 0; c < NB; ++c) prow[c] = (rowok && c < nb) ? A[i + (size_t)(k0 + c) * nx] : 0.0;
-            // ---- panel: Gauss-Jordan on the block columns, rows in registers
+            // ---- panel: Gauss-Jordan on the block columns, rows in registers.  The loop over the
+            //      pivots is ROLLED (one copy of the body in the instruction cache: unrolled, its 32
+            //      copies ran once per block step each and were fetched from L2 every time): the
+            //      register array is rotated by one column per pivot, so the pivot column is always
+            //      element 0 and every index is a compile-time constant.
+#pragma unroll 1
+            for (int kk = 0; kk < nb; ++kk) {
+                const int k = k0 + kk;
+                const double mag = (rowok && i >= k) ? fabs(prow[0]) : -1.0;
+                int bi = i;
+                const double best = tm.argmax(mag, bi);
+                if (!(best > 0.0) || !PB_FINITE(best)) return 1;
+                const int lp = bi;
+                if (i == lp) {
 #pragma unroll
-            for (int kk = 0; kk < NB; ++kk) {
-                if (kk < nb) {
-                    const int k = k0 + kk;
-                    const double mag = (rowok && i >= k) ? fabs(prow[kk]) : -1.0;
-                    int bi = i;
-                    const double best = tm.argmax(mag, bi);
-                    if (!(best > 0.0) || !PB_FINITE(best)) return 1;
-                    const int lp = bi;
-                    if (i == lp) {
-#pragma unroll
-                        for (int c = 0; c < NB; ++c) xbuf[c] = prow[c];
-                    }
-                    if (lp != k && i == k) {
-#pragma unroll
-                        for (int c = 0; c < NB; ++c) xbuf2[c] = prow[c];
-                    }
-                    if (i == 0) {
-                        pv[kk] = lp;
-                        const int t_ = perm_s[k];
-                        perm_s[k] = perm_s[lp];
-                        perm_s[lp] = t_;
-                    }
-                    __syncthreads();
-                    if (lp != k && i == lp) {
-#pragma unroll
-                        for (int c = 0; c < NB; ++c) prow[c] = xbuf2[c];
-                    }
-                    const double pinv = 1.0 / xbuf[kk];
-                    if (i == k) {
-#pragma unroll
-                        for (int c = 0; c < NB; ++c) prow[c] = (c == kk) ? pinv : xbuf[c] * pinv;
-                    } else {
-                        const double m = prow[kk] * pinv;
-#pragma unroll
-                        for (int c = 0; c < NB; ++c) prow[c] = (c == kk) ? -m : prow[c] - m * xbuf[c];
-                    }
+                    for (int c = 0; c < NB; ++c) xbuf[c] = prow[c];
                 }
+                if (lp != k && i == k) {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) xbuf2[c] = prow[c];
+                }
+                if (i == 0) {
+                    pv[kk] = lp;
+                    const int t_ = perm_s[k];
+                    perm_s[k] = perm_s[lp];
+                    perm_s[lp] = t_;
+                }
+                __syncthreads();
+                if (lp != k && i == lp) {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) prow[c] = xbuf2[c];
+                }
+                const double pinv = 1.0 / xbuf[0];
+                double p0;
+                if (i == k) {
+#pragma unroll
+                    for (int c = 1; c < NB; ++c) prow[c] = xbuf[c] * pinv;
+                    p0 = pinv;
+                } else {
+                    const double m = prow[0] * pinv;
+#pragma unroll
+                    for (int c = 1; c < NB; ++c) prow[c] -= m * xbuf[c];
+                    p0 = -m;
+                }
+#pragma unroll
+                for (int c = 0; c < NB - 1; ++c) prow[c] = prow[c + 1];
+                prow[NB - 1] = p0;
+            }
+#pragma unroll 1
+            for (int r = nb; r < NB; ++r) {  // short last block: finish the turn of the register array
+                const double p0 = prow[0];
+#pragma unroll
+                for (int c = 0; c < NB - 1; ++c) prow[c] = prow[c + 1];
+                prow[NB - 1] = p0;
             }
             // ---- the row swaps of this block step as one permutation: position tlist[t] receives
             //      the row that was at tsrc[t] when the block step began
@@ -595,17 +629,14 @@ struct BdfTeam {
                 for (int kk = 0; kk < nb; ++kk) {
                     const int k = k0 + kk, lp = pv[kk];
                     if (lp == k) continue;
-                    int a = -1, b = -1;
-                    for (int t = 0; t < n; ++t) {
-                        if (tlist[t] == k) a = t;
-                        if (tlist[t] == lp) b = t;
-                    }
-                    if (a < 0) { a = n; tlist[n] = k; tsrc[n] = k; ++n; }
-                    if (b < 0) { b = n; tlist[n] = lp; tsrc[n] = lp; ++n; }
+                    int a = slot_of[k], b = slot_of[lp];  // list position of a row, -1 = not yet touched
+                    if (a < 0) { a = n; tlist[n] = k; tsrc[n] = k; slot_of[k] = n; ++n; }
+                    if (b < 0) { b = n; tlist[n] = lp; tsrc[n] = lp; slot_of[lp] = n; ++n; }
                     const int t_ = tsrc[a];
                     tsrc[a] = tsrc[b];
                     tsrc[b] = t_;
                 }
+                for (int t = 0; t < n; ++t) slot_of[tlist[t]] = -1;
                 *ntp = n;
             }
             __syncthreads();
@@ -615,7 +646,15 @@ struct BdfTeam {
                     if (j >= k0 && j < k0 + nb) continue;
                     double* col = A + (size_t)j * nx;
                     double v[2 * NB];
-                    for (int t = 0; t < nt; ++t) v[t] = col[tsrc[t]];
+                    // all sources are read before the first write (the permutation may chain); eight
+                    // independent loads are issued before their values are parked in local memory
+                    for (int t0 = 0; t0 < nt; t0 += 8) {
+                        double r8[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) r8[u] = (t0 + u < nt) ? col[tsrc[t0 + u]] : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) v[t0 + u] = r8[u];
+                    }
                     for (int t = 0; t < nt; ++t)
                         if (tsrc[t] != tlist[t]) col[tlist[t]] = v[t];
                 }
@@ -747,6 +786,8 @@ struct BdfTeam {
     __device__ __noinline__ void solve_pass_mma(int c0, int nc, double nsc) {
         constexpr int KC = 64, PRE = (KC * 8 * NT + 511) / 512;
         static_assert(8 * NT * TEAM_BS <= TEAM_RTILE, "tile does not fit");
+        const int nx = this->nx;  // (locals: see invert_rows)
+        double* const scr = w.scr;
         const int i = threadIdx.x;
         const int lane = i & 31, lq = lane & 3, lr = lane >> 2;
         double* const sm = smem_base();
@@ -840,7 +881,7 @@ struct BdfTeam {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int r = rbase + 8 * mt, col = 8 * nt + 2 * lq + e;
-                        if (r < nx && col < nc) w.scr[r + (size_t)(c0 + col) * nx] = nsc * c[mt][nt][e];
+                        if (r < nx && col < nc) scr[r + (size_t)(c0 + col) * nx] = nsc * c[mt][nt][e];
                     }
                 }
             }
@@ -855,6 +896,8 @@ struct BdfTeam {
         constexpr int KC = (TN == 1) ? 512 : 64;
         constexpr int PRE = (KC * TN + 511) / 512;
         static_assert(KC * TN <= TEAM_RBUF, "tile does not fit");
+        const int nx = this->nx;  // (locals: see invert_rows)
+        double* const scr = w.scr;
         const int i = threadIdx.x;
         const bool active = i < nx;
         double* const sm = smem_base();
@@ -943,7 +986,7 @@ struct BdfTeam {
         if (active) {
 #pragma unroll
             for (int cc = 0; cc < TN; ++cc)
-                if (cc < nc) w.scr[i + (size_t)(c0 + cc) * nx] = nsc * acc[cc];
+                if (cc < nc) scr[i + (size_t)(c0 + cc) * nx] = nsc * acc[cc];
         }
     }
 #endif
@@ -1127,9 +1170,10 @@ struct BdfTeam {
 
     // ---------------------------------------------------------------- history array
     /// cvPredict (sgn = +1) / cvRestore (sgn = -1): Pascal-triangle sweep per element in registers
-    PB_HD void shift_history(double sgn) {
+    PT_NOINLINE void shift_history(double sgn) {
         tm.sync();
-        constexpr int U = 2;
+        constexpr int U = 4;
+        const int q = this->q;  // (locals: see invert_rows)
         const int e1 = nx * ncol;
         double* const zb = w.znbase;
         const size_t nxc = w.nxc;
@@ -1161,9 +1205,11 @@ struct BdfTeam {
         tm.sync();
     }
     /// cvRescale
-    PB_HD void rescale() {
+    PT_NOINLINE void rescale() {
         tm.sync();
-        constexpr int U = 2;
+        constexpr int U = 4;
+        const int q = this->q;  // (locals: see invert_rows)
+        const double eta = this->eta;
         const int e1 = nx * ncol;
         double* const zb = w.znbase;
         const size_t nxc = w.nxc;
@@ -1316,7 +1362,7 @@ struct BdfTeam {
 
     // ---------------------------------------------------------------- step control
     /// cvCompleteStep
-    PB_HD void complete_step() {
+    PT_NOINLINE void complete_step() {
         nst++;
         nscon++;
         qsum += q;
@@ -1327,7 +1373,9 @@ struct BdfTeam {
         const bool save = (qwait == 1) && (q != cv::Q_MAX);
         tm.sync();
         {
-            constexpr int U = 2;
+            constexpr int U = 4;
+            const int q = this->q;  // (locals: see invert_rows)
+            const double* const acor = w.acor;
             const int e1 = nx * ncol;
             double* const zb = w.znbase;
             const size_t nxc = w.nxc;
@@ -1339,7 +1387,7 @@ struct BdfTeam {
                 PB_UNROLL
                 for (int u = 0; u < U; ++u) {
                     const int e = eb + u * tm.size();
-                    a[u] = (e < e1) ? w.acor[e] : 0.0;
+                    a[u] = (e < e1) ? acor[e] : 0.0;
                     PB_UNROLL
                     for (int j = 0; j < cv::L_MAX; ++j) z[u][j] = (j <= q && e < e1) ? zb[j * nxc + e] : 0.0;
                 }

@@ -22,6 +22,7 @@ struct HostTeam {
     PB_HD void sync() const {}
     PB_HD void warp_sync() const {}
     PB_HD double warp_sum(double v) const { return v; }
+    PB_HD int warp_max_int(int v) const { return v; }
     PB_HD double sum(double v) const { return v; }
     PB_HD double max(double v) const { return v; }
     PB_HD bool any(bool p) const { return p; }
@@ -50,6 +51,14 @@ struct CtaTeam {
     __device__ __forceinline__ double warp_sum(double v) const {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ __forceinline__ int warp_max_int(int v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int u = __shfl_xor_sync(0xffffffffu, v, o);
+            v = u > v ? u : v;
+        }
         return v;
     }
     __device__ __forceinline__ double warp_max(double v) const {
