@@ -92,6 +92,14 @@ int main() {
         printf("DFMA, 1 operand LDS.128 bc : %.2f TFLOP/s\n", 2.0 * sms * 512 * 16 * iters / ms / 1e9);
     }
     {
+        double ms = time_ms([&] { k_dmma<2><<<sms, 512>>>(d, iters); });
+        printf("DMMA m8n8k4 (2 tiles/warp) : %.2f TFLOP/s\n", 2.0 * sms * 16 * 2 * 256.0 * iters / ms / 1e9);
+    }
+    {
+        double ms = time_ms([&] { k_dmma<4><<<sms, 512>>>(d, iters); });
+        printf("DMMA m8n8k4 (4 tiles/warp) : %.2f TFLOP/s\n", 2.0 * sms * 16 * 4 * 256.0 * iters / ms / 1e9);
+    }
+    {
         double ms = time_ms([&] { k_dmma<8><<<sms, 512>>>(d, iters); });
         printf("DMMA m8n8k4 (8 tiles/warp) : %.2f TFLOP/s\n", 2.0 * sms * 16 * 8 * 256.0 * iters / ms / 1e9);
     }
