@@ -64,6 +64,8 @@ __device__ __forceinline__ void pb_cp_async8(double* smem_dst, const double* gsr
 __device__ __forceinline__ void pb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void pb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+/// L2 prefetch of the line holding *p (no register, no shared memory: extends the reach of the ring)
+__device__ __forceinline__ void pb_prefetch_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 /// FP64 tensor-core MMA, D(8x8) += A(8x4) * B(4x8).  Fragments: a = A[lane>>2][lane&3],
 /// b = B[lane&3][lane>>2], d0/d1 = D[lane>>2][2*(lane&3) + {0,1}]
 __device__ __forceinline__ void pb_dmma(double& d0, double& d1, double a, double b) {
@@ -577,7 +579,7 @@ struct BdfTeam {
                 const int k = k0 + kk;
                 const double mag = (rowok && i >= k) ? fabs(prow[0]) : -1.0;
                 int bi = i;
-                const double best = tm.argmax(mag, bi);
+                const double best = tm.argmax_inline(mag, bi);
                 if (!(best > 0.0) || !PB_FINITE(best)) return 1;
                 const int lp = bi;
                 if (i == lp) {
@@ -708,6 +710,7 @@ struct BdfTeam {
             const int ngroups = (nx + GC - 1) / GC;
             auto col_ok = [&](int j) { return j < nx && !(j >= k0 && j < k0 + nb); };
             auto row_in_block = [&](int r) { return r >= k0 && r < k0 + nb; };
+            constexpr int PF = 10;  // column groups the L2 prefetch runs ahead of the ring
             auto issue = [&](int g) {
                 if (g < ngroups) {
                     double* dst = xs + (size_t)((g % ST) * GC) * 512 + i;
@@ -720,6 +723,17 @@ struct BdfTeam {
                             pb_cp_async8(dst + (mt * 2 + e) * 512, ok ? A + r + (size_t)j * nx : A, ok ? 8 : 0);
                         }
                     }
+                    // one lane per 64-byte row segment asks L2 for the same elements PF groups ahead
+                    if (g + PF < ngroups && (lr == 0)) {
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int r = rbase + 8 * mt, j = (g + PF) * GC + 2 * lq + e;
+                                if (r < nx && j < nx) pb_prefetch_l2(A + r + (size_t)j * nx);
+                            }
+                        }
+                    }
                 }
                 pb_cp_async_commit();
             };
@@ -728,10 +742,18 @@ struct BdfTeam {
             for (int ch = 0; ch < nchunks; ++ch) {
                 const double* const cur = sm + ((ch & 1) ? TEAM_SM_RBUF1 : TEAM_SM_RBUF);
                 double* const nxt = sm + ((ch & 1) ? TEAM_SM_RBUF : TEAM_SM_RBUF1);
-                double rpre[TEAM_RBUF / 512];
                 if (ch + 1 < nchunks) {
+                    // the pivot-row tile of the next chunk travels with the ring's next commit group
+                    // (no registers): complete for this thread at its next wait, visible to the block
+                    // after the barrier at the end of the chunk
 #pragma unroll
-                    for (int u = 0; u < TEAM_RBUF / 512; ++u) rpre[u] = r_entry(ch + 1, i + u * 512);
+                    for (int u = 0; u < TEAM_RBUF / 512; ++u) {
+                        const int e = i + u * 512;
+                        const int jj = e / NB, kk = e - jj * NB;
+                        const int j = (ch + 1) * TEAM_CW + jj;
+                        const bool ok = kk < nb && j < nx;
+                        pb_cp_async8(nxt + r_pos(e), ok ? A + (k0 + kk) + (size_t)j * nx : A, ok ? 8 : 0);
+                    }
                 }
                 for (int gl = 0; gl < TEAM_CW / GC; ++gl) {
                     const int g = ch * (TEAM_CW / GC) + gl;
@@ -761,10 +783,7 @@ struct BdfTeam {
                         }
                     }
                 }
-                if (ch + 1 < nchunks) {
-#pragma unroll
-                    for (int u = 0; u < TEAM_RBUF / 512; ++u) nxt[r_pos(i + u * 512)] = rpre[u];
-                }
+                pb_cp_async_wait<ST - 1>();  // includes the tile copies issued at the top of this chunk
                 __syncthreads();
             }
             pb_cp_async_wait<0>();

@@ -85,7 +85,9 @@ struct CtaTeam {
         return warp_max(s);
     }
     __device__ __forceinline__ bool any(bool p) const { return __syncthreads_or(p ? 1 : 0) != 0; }
-    __device__ __noinline__ double argmax(double v, int& idx) const {
+    __device__ __noinline__ double argmax(double v, int& idx) const { return argmax_inline(v, idx); }
+    /// the same, inlined (callers that hold many live registers: a call would spill them around it)
+    __device__ __forceinline__ double argmax_inline(double v, int& idx) const {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double vo = __shfl_xor_sync(0xffffffffu, v, o);
