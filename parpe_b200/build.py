@@ -18,7 +18,7 @@ LIB = os.path.join(CSRC, "libparpe_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
-         "-ccbin", "/usr/bin/g++"]
+         "-ccbin", "/usr/bin/g++"] + os.environ.get("PB200_NVCC_EXTRA", "").split()
 
 
 def _sources():
