@@ -53,7 +53,8 @@ constexpr int TEAM_SM_RED = 0, TEAM_SM_ROWK = 64, TEAM_SM_XBUF2 = 96, TEAM_SM_PI
 /// rows path (nx <= 512): ring of matrix elements in flight (cp.async), TEAM_ST stages of TEAM_GC
 /// columns x 512 rows; aliases the panel of the generic path (a launch uses one of the two)
 constexpr int TEAM_GC = 8, TEAM_ST = 4, TEAM_SM_XSTAGE = TEAM_SM_PANEL,
-              TEAM_SM_ROWS_END = TEAM_SM_XSTAGE + TEAM_ST * TEAM_GC * 512;
+              TEAM_XCS = 514,  // column stride of a ring slot read as tensor-core C fragments (conflict-free)
+              TEAM_SM_ROWS_END = TEAM_SM_XSTAGE + TEAM_ST * TEAM_GC * TEAM_XCS;
 
 #if defined(__CUDA_ARCH__)
 /// 8-byte asynchronous global -> shared copy (LDGSTS); nbytes = 0 writes zeros without reading
@@ -62,6 +63,11 @@ __device__ __forceinline__ void pb_cp_async8(double* smem_dst, const double* gsr
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(nbytes) : "memory");
 }
 __device__ __forceinline__ void pb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+/// 16-byte variant (both addresses 16-byte aligned)
+__device__ __forceinline__ void pb_cp_async16(double* smem_dst, const double* gsrc, int nbytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(nbytes) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void pb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 /// L2 prefetch of the line holding *p (no register, no shared memory: extends the reach of the ring)
@@ -710,17 +716,34 @@ struct BdfTeam {
             const int ngroups = (nx + GC - 1) / GC;
             auto col_ok = [&](int j) { return j < nx && !(j >= k0 && j < k0 + nb); };
             auto row_in_block = [&](int r) { return r >= k0 && r < k0 + nb; };
-            constexpr int PF = 10;  // column groups the L2 prefetch runs ahead of the ring
+            // A ring slot holds the 8 columns of a group as [column][512 rows] (column stride TEAM_XCS).
+            // For even nx the warp copies its 32 rows x 8 columns cooperatively in 16-byte pieces (two
+            // consecutive rows of one column: half the asynchronous-copy operations of a per-element
+            // copy, which ran at about one 8-byte element per clock per SM); a lane then reads its
+            // fragment elements from what the warp copied, after __syncwarp.
+            const bool wide = (nx & 1) == 0;
+            const int wrow0 = i & ~31;  // first row of this warp
+            constexpr int PF = 10;      // column groups the L2 prefetch runs ahead of the ring
             auto issue = [&](int g) {
+                __syncwarp();  // the slot written below was read by the warp in the previous trip
                 if (g < ngroups) {
-                    double* dst = xs + (size_t)((g % ST) * GC) * 512 + i;
+                    double* slot = xs + (size_t)((g % ST) * GC) * TEAM_XCS;
+                    if (wide) {
 #pragma unroll
-                    for (int mt = 0; mt < 4; ++mt) {
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int r = rbase + 8 * mt, j = g * GC + 2 * lq + e;
+                        for (int u = 0; u < 4; ++u) {
+                            const int q = lane + 32 * u, col = q >> 4, r = wrow0 + 2 * (q & 15), j = g * GC + col;
                             const bool ok = r < nx && !row_in_block(r) && col_ok(j);
-                            pb_cp_async8(dst + (mt * 2 + e) * 512, ok ? A + r + (size_t)j * nx : A, ok ? 8 : 0);
+                            pb_cp_async16(slot + col * TEAM_XCS + r, ok ? A + r + (size_t)j * nx : A, ok ? 16 : 0);
+                        }
+                    } else {
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int r = rbase + 8 * mt, col = 2 * lq + e, j = g * GC + col;
+                                const bool ok = r < nx && !row_in_block(r) && col_ok(j);
+                                pb_cp_async8(slot + col * TEAM_XCS + r, ok ? A + r + (size_t)j * nx : A, ok ? 8 : 0);
+                            }
                         }
                     }
                     // one lane per 64-byte row segment asks L2 for the same elements PF groups ahead
@@ -760,12 +783,13 @@ struct BdfTeam {
                     if (g >= ngroups) break;
                     issue(g + ST - 1);
                     pb_cp_async_wait<ST - 1>();
-                    const double* src = xs + (size_t)((g % ST) * GC) * 512 + i;
+                    __syncwarp();  // pieces copied by the other lanes of the warp
+                    const double* src = xs + (size_t)((g % ST) * GC) * TEAM_XCS + (2 * lq) * TEAM_XCS + rbase;
                     double c[4][2];
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt) {
-                        c[mt][0] = src[(mt * 2) * 512];
-                        c[mt][1] = src[(mt * 2 + 1) * 512];
+                        c[mt][0] = src[8 * mt];
+                        c[mt][1] = src[TEAM_XCS + 8 * mt];
                     }
                     const double* rt = cur + (gl * GC + lr) * TEAM_RS + lq;  // B fragment: R[4ks + lq][column lr]
 #pragma unroll
