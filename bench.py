@@ -350,10 +350,10 @@ def main():
             "bound": "fp64", "achieved": flops / kern_avg / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": flops / kern_avg / 1e12 / peak_tf,
             # DRAM bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
-            # capture of this kernel (profiles/r01_f_summary.txt: 5 074 944 B for 4736 conditions), scaled
+            # capture of this kernel (profiles/r01_g_summary.txt: 5 435 648 B for 4736 conditions), scaled
             # to the conditions of this launch; the large-model workloads have no full-length capture
-            "traffic": (5074944.0 / 4736.0) * (hi - lo) if MODEL == "boehm" else None,
-            "traffic_source": "profiles/r01_f_summary.txt (ncu, 4736 conditions), scaled per condition" if MODEL == "boehm" else None,
+            "traffic": (5435648.0 / 4736.0) * (hi - lo) if MODEL == "boehm" else None,
+            "traffic_source": "profiles/r01_g_summary.txt (ncu, 4736 conditions), scaled per condition" if MODEL == "boehm" else None,
             "peak_source": "DFMA microbenchmark measured live on this device (MEASURED_PEAKS.json has no FP64 figure)",
             "kernel": ("simulate_team_kernel<%d> (%s)" % (fun.last_launch()["block"], MODEL)) if MODEL in LARGE_MODELS
             else "simulate_kernel<Model_%s,G=%d>" % (MODEL, fun.last_launch()["lanes"]),
