@@ -36,7 +36,7 @@ UNIT = "solves/s"
 MODEL = "boehm"   # --workload: boehm (the metric's configuration, default) | chen | froehlich | net32 | fujita ...
 DEFAULT_CONDITIONS = {"chen": 296, "froehlich": 148, "net32": 4736}
 CONDITIONS_PER_GPU = int(os.environ.get("PB200_BENCH_CONDITIONS", 16384))
-LARGE_MODELS = ("chen", "froehlich", "net32")
+LARGE_MODELS = ("chen", "froehlich", "net32", "net31")
 CPU_SAMPLE_SECONDS = float(os.environ.get("PB200_BENCH_CPU_SECONDS", 15.0))
 
 

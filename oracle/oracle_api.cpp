@@ -18,6 +18,7 @@
 #include "net_model.hpp"
 #include "../parpe_b200/csrc/models/net_chen.h"
 #include "../parpe_b200/csrc/models/net_froehlich.h"
+#include "../parpe_b200/csrc/models/net_net31.h"
 #include "../parpe_b200/csrc/models/net_net32.h"
 
 #ifdef PB200_ORACLE_WITH_VENDORED
@@ -36,6 +37,7 @@ std::unique_ptr<amici::Model> makeModel(const std::string& name) {
     if (name == "boehm") return create_boehm();
     if (name == "fujita") return create_fujita();
     if (name == "net32") return std::make_unique<NetworkModel>(pb200::nets::net32::tables());
+    if (name == "net31") return std::make_unique<NetworkModel>(pb200::nets::net31::tables());
     if (name == "chen") return std::make_unique<NetworkModel>(pb200::nets::chen::tables());
     if (name == "froehlich") return std::make_unique<NetworkModel>(pb200::nets::froehlich::tables());
 #ifdef PB200_ORACLE_WITH_VENDORED

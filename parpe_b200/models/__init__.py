@@ -16,6 +16,7 @@ REGISTRY = {
     "net32": 4,
     "chen": 5,
     "froehlich": 6,
+    "net31": 7,
 }
 
 

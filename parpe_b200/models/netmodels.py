@@ -5,7 +5,7 @@
 real PEtab problems are not vendored in the reference tree and cannot be imported
 offline, so the networks are generated (fixed seeds) with the dimensions and sparsity
 SURVEY.md 8(d) names: nnz(J) ~ 10 nx, rate constants log-uniform over six decades,
-nplist = 50 / 100.  ``net32`` is a small member of the same family for fast tests.
+nplist = 50 / 100.  ``net32`` and ``net31`` are small members of the same family for fast tests.
 """
 import functools
 
@@ -14,6 +14,7 @@ from ..codegen.netgen import make_network
 NET_MODELS = {
     # name: (nx, nr, np, ny, seed)
     "net32": (32, 112, 6, 4, 11),
+    "net31": (31, 100, 5, 3, 14),   # odd nx, one short block: the fallback paths of the rows kernel
     "chen": (500, 2000, 50, 8, 12),
     "froehlich": (1200, 4800, 100, 8, 13),
 }

@@ -21,6 +21,7 @@ DEFAULT_TIMEPOINTS = {
     "fujita": np.array([0, 60, 120, 180, 300, 600, 900, 1200, 1800, 2400, 3000, 3600], dtype=float),
     # mass-action networks (nt = 8)
     "net32": np.array([0.1, 0.3, 1, 3, 10, 30, 100, 300], dtype=float),
+    "net31": np.array([0.1, 0.3, 1, 3, 10, 30, 100, 300], dtype=float),
     "chen": np.array([0.1, 0.3, 1, 3, 10, 30, 100, 300], dtype=float),
     "froehlich": np.array([0.1, 0.3, 1, 3, 10, 30, 100, 300], dtype=float),
 }
@@ -36,7 +37,7 @@ def condition_constants(model: str, C: int, rng: np.random.Generator) -> np.ndar
         k[:, 0] = 1.0 + 0.1 * (np.arange(C) % 4)
     elif model == "fujita":
         k[:, 0] = np.array([0.1, 0.3, 1.0, 3.0, 10.0, 30.0])[np.arange(C) % 6]
-    elif model in ("net32", "chen", "froehlich"):
+    elif model in ("net32", "net31", "chen", "froehlich"):
         k[:, 0] = np.array([0.5, 1.0, 1.5, 2.0])[np.arange(C) % 4]
         k[:, 1] = 1.0 + 0.05 * rng.standard_normal(C)
     elif model == "boehm":

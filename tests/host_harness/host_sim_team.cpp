@@ -14,12 +14,14 @@
 #include "../../parpe_b200/csrc/bdf_team.cuh"
 #include "../../parpe_b200/csrc/models/net_chen.h"
 #include "../../parpe_b200/csrc/models/net_froehlich.h"
+#include "../../parpe_b200/csrc/models/net_net31.h"
 #include "../../parpe_b200/csrc/models/net_net32.h"
 
 using namespace pb200;
 
 static bool tables_for(const char* model, NetTables* T) {
     if (!std::strcmp(model, "net32")) { *T = nets::net32::tables(); return true; }
+    if (!std::strcmp(model, "net31")) { *T = nets::net31::tables(); return true; }
     if (!std::strcmp(model, "chen")) { *T = nets::chen::tables(); return true; }
     if (!std::strcmp(model, "froehlich")) { *T = nets::froehlich::tables(); return true; }
     return false;

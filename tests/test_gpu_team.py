@@ -24,6 +24,7 @@ CASES = [
     ("net32", 5, 8, dict(scale="log10")),
     ("net32", 7, 8, dict(scale="mixed", sigma_mode="mixed", missing_fraction=0.1, ragged=True)),
     ("net32", 300, 4, dict(scale="log10")),       # more conditions than SMs: work queue
+    ("net31", 6, 6, dict(scale="log10")),         # odd nx (8-byte tile copies), one short block (nb = 31)
     ("chen", 3, 3, dict(scale="log10")),          # nx = 500, nplist = 50: rows path (tensor-core GEMMs)
     ("froehlich", 2, 1, dict(scale="log10")),     # nx = 1200, nplist = 100: generic path (panel in shared memory)
 ]

@@ -19,7 +19,8 @@ def _dense_jacobian(spec, Jv):
     return J
 
 
-@pytest.mark.parametrize("model,ncols,panel_widths", [("net32", 7, (0, 8, 4, 1)), ("chen", 51, (0, 16))])
+@pytest.mark.parametrize("model,ncols,panel_widths", [("net32", 7, (0, 8, 4, 1)), ("net31", 6, (0, 8)),
+                                                      ("chen", 51, (0, 16))])
 def test_blocked_inversion_and_solve_gemm(model, ncols, panel_widths):
     """(I - gamma J)^-1 B for random values on the model's pattern vs numpy; every panel width
     must give the same answer (NB = 16 is what nx = 1200 uses on the device)."""
