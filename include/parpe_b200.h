@@ -254,6 +254,21 @@ int pb200_hier_attach(pb200_handle* h, const pb200_hier_desc* hd);
 /* number of outer (numerically optimised) parameters = n_opt - n_inner */
 int pb200_hier_num_outer(pb200_handle* h);
 /*
+ * Collective hook for partitioned (multi-GPU / multi-process) HIERARCHICAL evaluation: with
+ * pb200_set_partition(rank, world > 1) every rank simulates its share of the conditions, and the
+ * analytic inner parameters need sums over ALL conditions (hierarchicalOptimization.cpp:311-441 run
+ * on the master over all results).  The library calls fn(user, buf, n, op) on HOST buffers at the
+ * reduction points -- error count of pass 1, scaling/offset sums, sigma sums and maxima, analytic
+ * nllh, and (nllh, #errors, gradient) of pass 2 -- and expects the element-wise all-reduce in place
+ * (op: PB200_REDUCE_SUM / PB200_REDUCE_MAX); every rank must call pb200_hier_evaluate with the same
+ * arguments.  The caller implements fn with its own transport (MPI_Allreduce in parPE, NCCL or gloo
+ * through torch.distributed in this repository).  NULL (default) = single rank.
+ */
+enum { PB200_REDUCE_SUM = 0, PB200_REDUCE_MAX = 1 };
+typedef void (*pb200_allreduce_fn)(void* user, double* buf, int n, int op);
+int pb200_set_allreduce(pb200_handle* h, pb200_allreduce_fn fn, void* user);
+
+/*
  * Replaces: HierarchicalOptimizationWrapper::evaluate (hierarchicalOptimization.cpp:
  * 142-238).  theta_outer[n_outer] -> fval, grad_outer[n_outer] (NULL => cost only);
  * full_parameters[n_opt] (nullable) receives the spliced vector incl. the optimal

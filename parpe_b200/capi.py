@@ -18,10 +18,13 @@ EXPORTED_SYMBOLS = [
     "pb200_abi_version", "pb200_device_count", "pb200_model_count", "pb200_model_name", "pb200_model_info",
     "pb200_last_error", "pb200_create", "pb200_destroy", "pb200_set_partition", "pb200_partition_bounds",
     "pb200_evaluate", "pb200_evaluate_device", "pb200_last_launch", "pb200_get_condition_results",
-    "pb200_get_model_outputs", "pb200_measure_fp64_peak", "pb200_hier_attach", "pb200_hier_num_outer", "pb200_hier_evaluate",
+    "pb200_get_model_outputs", "pb200_measure_fp64_peak", "pb200_set_allreduce", "pb200_hier_attach", "pb200_hier_num_outer", "pb200_hier_evaluate",
 ]
 
 _lib = None
+# void (*pb200_allreduce_fn)(void* user, double* buf, int n, int op)
+ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_int)
+REDUCE_SUM, REDUCE_MAX = 0, 1
 
 
 class B200LibraryError(RuntimeError):
@@ -57,6 +60,7 @@ def lib():
     L.pb200_get_condition_results.argtypes = [C.c_void_p, dp, dp, ip, C.POINTER(C.c_int64)]
     L.pb200_get_model_outputs.argtypes = [C.c_void_p, dp, C.c_int, dp, dp]
     L.pb200_measure_fp64_peak.argtypes = [C.c_int, dp]
+    L.pb200_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p]
     L.pb200_hier_attach.argtypes = [C.c_void_p, C.POINTER(HierDesc)]
     L.pb200_hier_num_outer.argtypes = [C.c_void_p]
     L.pb200_hier_evaluate.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp, dp]

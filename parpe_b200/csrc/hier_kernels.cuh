@@ -23,6 +23,8 @@
 #include <string>
 #include <vector>
 
+#include <functional>
+
 #include "../../include/parpe_b200.h"
 
 namespace pb200 {
@@ -55,7 +57,7 @@ template <int KIND, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 hier_sums_kernel(const int64_t* __restrict__ ptr, const int* __restrict__ cond, const int* __restrict__ obs,
                  const int64_t* __restrict__ t_offsets, int ny, const double* __restrict__ mes,
-                 const double* __restrict__ sim, double* __restrict__ sums) {
+                 const double* __restrict__ sim, double* __restrict__ sums, int partitioned) {
     __shared__ double r0[THREADS], r1[THREADS], r2[THREADS];
     const int p = blockIdx.x, tid = threadIdx.x;
     double num = 0.0, den = 0.0, mx = 0.0;
@@ -66,6 +68,7 @@ hier_sums_kernel(const int64_t* __restrict__ ptr, const int* __restrict__ cond, 
             const double m = mes[it * ny + o];
             if (isnan(m)) continue;
             double s = sim[it * ny + o];
+            if (partitioned && isnan(s)) continue;  // a condition another rank simulates
             if (KIND == HIER_SCALING) {
                 if (s < 0 && s > -1e-18) s = 0.0;
                 num += s * m;
@@ -122,7 +125,7 @@ hier_apply_kernel(const int64_t* __restrict__ ptr, const int* __restrict__ cond,
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 hier_nllh_kernel(int64_t first, int64_t last, const double* __restrict__ mes, const double* __restrict__ sim,
-                 const double* __restrict__ sig, double* __restrict__ partial) {
+                 const double* __restrict__ sig, double* __restrict__ partial, int partitioned) {
     __shared__ double r0[THREADS];
     const int tid = threadIdx.x;
     double acc = 0.0;
@@ -130,6 +133,7 @@ hier_nllh_kernel(int64_t first, int64_t last, const double* __restrict__ mes, co
         const double m = mes[i];
         if (isnan(m)) continue;
         const double s = sim[i];
+        if (partitioned && isnan(s)) continue;  // a condition another rank simulates
         const double s2 = sig[i] * sig[i];
         if (isnan(s) || isnan(s2) || s2 < 0.0) {
             acc = NAN;
@@ -273,8 +277,20 @@ inline void hier_filter(const HierDevice* h, const double* full, double* outer) 
 /// Steps 3-4 of HierarchicalOptimizationWrapper::evaluate (:184-238).  d_y (pass-1 outputs)
 /// is scaled/offset in place; d_sig receives the analytic sigmas when the analytic nllh is
 /// requested.  inner_scaled: scalings, offsets, sigmas in the optimiser's parameter scale.
+/// reduce(buf, n, op): element-wise all-reduce over the ranks of a partitioned evaluation (null: one rank)
 inline bool hier_compute(HierDevice* h, const double* d_mes, double* d_y, double* d_sig, cudaStream_t stream,
-                         bool want_nllh, std::vector<double>* inner_scaled, double* nllh, std::string* err) {
+                         bool want_nllh, std::vector<double>* inner_scaled, double* nllh, std::string* err,
+                         const std::function<void(double*, int, int)>& reduce = nullptr) {
+    const int partitioned = reduce ? 1 : 0;
+    // sums of one kind over all ranks: entries 0,1 are sums, entry 2 a maximum
+    auto reduce_kind = [&](std::vector<double>& host, int n) {
+        if (!reduce || n == 0) return;
+        std::vector<double> sm(2 * (size_t)n), mx(n);
+        for (int i = 0; i < n; ++i) { sm[2 * i] = host[3 * i]; sm[2 * i + 1] = host[3 * i + 1]; mx[i] = host[3 * i + 2]; }
+        reduce(sm.data(), 2 * n, PB200_REDUCE_SUM);
+        reduce(mx.data(), n, PB200_REDUCE_MAX);
+        for (int i = 0; i < n; ++i) { host[3 * i] = sm[2 * i]; host[3 * i + 1] = sm[2 * i + 1]; host[3 * i + 2] = mx[i]; }
+    };
     using namespace hier_detail;
     constexpr int T = 256;
     auto check = [&](cudaError_t e, const char* what) {
@@ -294,9 +310,11 @@ inline bool hier_compute(HierDevice* h, const double* d_mes, double* d_y, double
     };
     HierKind &S = h->scaling, &O = h->offset, &G = h->sigma;
     std::vector<double> hs, ho, hg;
-    if (S.n) hier_sums_kernel<HIER_SCALING, T><<<S.n, T, 0, stream>>>(S.d_ptr, S.d_cond, S.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, S.d_sums);
-    if (O.n) hier_sums_kernel<HIER_OFFSET, T><<<O.n, T, 0, stream>>>(O.d_ptr, O.d_cond, O.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, O.d_sums);
+    if (S.n) hier_sums_kernel<HIER_SCALING, T><<<S.n, T, 0, stream>>>(S.d_ptr, S.d_cond, S.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, S.d_sums, partitioned);
+    if (O.n) hier_sums_kernel<HIER_OFFSET, T><<<O.n, T, 0, stream>>>(O.d_ptr, O.d_cond, O.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, O.d_sums, partitioned);
     if (!check(cudaGetLastError(), "hier_sums_kernel") || !fetch(S, hs) || !fetch(O, ho)) return false;
+    reduce_kind(hs, S.n);
+    reduce_kind(ho, O.n);
     std::vector<double> scal(S.n), offs(O.n), sig(G.n), lin;
     for (int i = 0; i < S.n; ++i) {
         const double den = hs[i * 3 + 1];
@@ -317,8 +335,9 @@ inline bool hier_compute(HierDevice* h, const double* d_mes, double* d_y, double
     for (int i = 0; i < O.n; ++i) lin[i] = unscale(offs[i], h->pscale_opt[O.idx[i]]);
     if (!push(O, lin)) return false;
     if (O.n) hier_apply_kernel<1, T><<<O.n, T, 0, stream>>>(O.d_ptr, O.d_cond, O.d_obs, h->d_t_offsets, h->ny, O.d_vals, d_y);
-    if (G.n) hier_sums_kernel<HIER_SIGMA, T><<<G.n, T, 0, stream>>>(G.d_ptr, G.d_cond, G.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, G.d_sums);
+    if (G.n) hier_sums_kernel<HIER_SIGMA, T><<<G.n, T, 0, stream>>>(G.d_ptr, G.d_cond, G.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, G.d_sums, partitioned);
     if (!check(cudaGetLastError(), "hier kernels") || !fetch(G, hg)) return false;
+    reduce_kind(hg, G.n);
     for (int i = 0; i < G.n; ++i) {
         double sigma = std::sqrt(hg[i * 3] / hg[i * 3 + 1]);
         const double eps = std::max(0.01 * hg[i * 3 + 2], 1e-12);
@@ -334,7 +353,7 @@ inline bool hier_compute(HierDevice* h, const double* d_mes, double* d_y, double
         for (int i = 0; i < G.n; ++i) lin[i] = unscale(sig[i], h->pscale_opt[G.idx[i]]);
         if (!push(G, lin)) return false;
         if (G.n) hier_apply_kernel<2, T><<<G.n, T, 0, stream>>>(G.d_ptr, G.d_cond, G.d_obs, h->d_t_offsets, h->ny, G.d_vals, d_sig);
-        hier_nllh_kernel<T><<<h->n_partial, T, 0, stream>>>(0, h->nt_total * h->ny, d_mes, d_y, d_sig, h->d_partial);
+        hier_nllh_kernel<T><<<h->n_partial, T, 0, stream>>>(0, h->nt_total * h->ny, d_mes, d_y, d_sig, h->d_partial, partitioned);
         std::vector<double> part(h->n_partial);
         if (!check(cudaGetLastError(), "hier_nllh_kernel") ||
             !check(cudaMemcpyAsync(part.data(), h->d_partial, sizeof(double) * h->n_partial, cudaMemcpyDeviceToHost, stream), "memcpy") ||
@@ -342,6 +361,7 @@ inline bool hier_compute(HierDevice* h, const double* d_mes, double* d_y, double
             return false;
         double acc = 0.0;
         for (double v : part) acc += v;
+        if (reduce) reduce(&acc, 1, PB200_REDUCE_SUM);
         *nllh = acc / 2.0;
     }
     return true;

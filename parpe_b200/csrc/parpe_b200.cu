@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <memory>
 #include <string>
@@ -147,6 +148,9 @@ struct pb200_handle {
     bool staged_pending = false;
     // hierarchical
     HierDevice* hier = nullptr;
+    // collective hook of partitioned hierarchical evaluations (pb200_set_allreduce)
+    pb200_allreduce_fn allreduce = nullptr;
+    void* allreduce_user = nullptr;
     // large-model path: device tables + workspace (ModelOps::create_state)
     void* model_state = nullptr;
 };
@@ -409,6 +413,13 @@ int pb200_set_partition(pb200_handle* h, int rank, int world) {
     return 0;
 }
 
+int pb200_set_allreduce(pb200_handle* h, pb200_allreduce_fn fn, void* user) {
+    if (!h) return fail(PB200_ERR_ARG, "null handle");
+    h->allreduce = fn;
+    h->allreduce_user = user;
+    return 0;
+}
+
 int pb200_evaluate(pb200_handle* h, const double* theta, int n_opt, const int* idx, int n_idx, double* fval,
                    double* grad, double* seconds) {
     if (!h || !theta || !fval || (n_idx > 0 && !idx)) return fail(PB200_ERR_ARG, "null argument");
@@ -551,7 +562,15 @@ int pb200_hier_evaluate(pb200_handle* h, const double* theta_outer, int n_outer,
     const int n_inner = hier_num_inner(h->hier);
     // HierarchicalOptimizationWrapper::evaluate throws on size mismatch (hierarchicalOptimization.cpp:155-160)
     if (n_outer != h->n_opt - n_inner) return fail(PB200_ERR_ARG, "reduced parameter vector size does not match numParameters");
+    if (h->world > 1 && !h->allreduce)
+        return fail(PB200_ERR_ARG, "partitioned hierarchical evaluation needs pb200_set_allreduce");
     PB_CUDA(cudaSetDevice(h->device));
+    std::function<void(double*, int, int)> reduce;
+    if (h->world > 1) {
+        pb200_allreduce_fn fn = h->allreduce;
+        void* user = h->allreduce_user;
+        reduce = [fn, user](double* buf, int n, int op) { fn(user, buf, n, op); };
+    }
     double t_total = 0.0;
     // pass 1: defaults for the inner parameters (scaling 1, offset 0, sigma 1 in linear scale)
     std::vector<double> full(h->n_opt);
@@ -564,7 +583,9 @@ int pb200_hier_evaluate(pb200_handle* h, const double* theta_outer, int n_outer,
         cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop);
         t_total += ms * 1e-3;
     }
-    if (h->h_out.p[1] != 0.0) {  // "Function evaluation failed." -> functionEvaluationFailure
+    double nerr1 = h->h_out.p[1];
+    if (reduce) reduce(&nerr1, 1, PB200_REDUCE_SUM);
+    if (nerr1 != 0.0) {  // "Function evaluation failed." -> functionEvaluationFailure
         *fval = std::numeric_limits<double>::infinity();
         return PB200_EVAL_FAILURE;
     }
@@ -573,7 +594,7 @@ int pb200_hier_evaluate(pb200_handle* h, const double* theta_outer, int n_outer,
     double nllh_analytic = 0.0;
     std::string err;
     if (!hier_compute(h->hier, h->d_my.p, h->d_yout.p, h->d_sout.p, h->stream, grad_outer == nullptr, &inner_scaled,
-                      &nllh_analytic, &err))
+                      &nllh_analytic, &err, reduce))
         return fail(PB200_ERR_CUDA, err);
     hier_splice(h->hier, theta_outer, inner_scaled.data(), full.data());
     if (full_parameters) std::memcpy(full_parameters, full.data(), sizeof(double) * h->n_opt);
@@ -584,9 +605,27 @@ int pb200_hier_evaluate(pb200_handle* h, const double* theta_outer, int n_outer,
         for (int c = 0; c < h->C; ++c) all[c] = c;
         std::vector<double> full_grad(h->n_opt);
         double sec2 = 0.0;
-        status = pb200_evaluate(h, full.data(), h->n_opt, all.data(), h->C, fval, full_grad.data(), &sec2);
+        if (!reduce) {
+            status = pb200_evaluate(h, full.data(), h->n_opt, all.data(), h->C, fval, full_grad.data(), &sec2);
+            if (status < 0) return status;
+        } else {
+            // partial (nllh, #errors, gradient) of this rank, all-reduced, then A1's failure rule
+            if (int rc = enqueue_evaluation(h, full.data(), all.data(), h->C, 1, h->d_out.p, nullptr, nullptr, h->stream)) return rc;
+            PB_CUDA(cudaMemcpyAsync(h->h_out.p, h->d_out.p, sizeof(double) * (2 + h->n_opt), cudaMemcpyDeviceToHost, h->stream));
+            PB_CUDA(cudaStreamSynchronize(h->stream));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop);
+            sec2 = ms * 1e-3;
+            reduce(h->h_out.p, 2 + h->n_opt, PB200_REDUCE_SUM);
+            *fval = h->h_out.p[0];
+            for (int j = 0; j < h->n_opt; ++j) full_grad[j] = h->h_out.p[2 + j];
+            status = PB200_EVAL_SUCCESS;
+            if (h->h_out.p[1] != 0.0 || !std::isfinite(*fval)) {
+                *fval = std::numeric_limits<double>::infinity();
+                status = PB200_EVAL_FAILURE;
+            }
+        }
         t_total += sec2;
-        if (status < 0) return status;
         if (status == PB200_EVAL_SUCCESS) hier_filter(h->hier, full_grad.data(), grad_outer);
     } else {
         *fval = nllh_analytic;

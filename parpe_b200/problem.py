@@ -100,6 +100,22 @@ class B200SummedGradientFunction:
         capi.check(capi.lib().pb200_set_partition(self._h, rank, world), "pb200_set_partition")
         self.rank, self.world = rank, world
 
+    def set_allreduce(self, fn):
+        """Collective hook of partitioned hierarchical evaluations: ``fn(array, op)`` all-reduces the
+        numpy view ``array`` in place over the ranks (op: ``capi.REDUCE_SUM`` / ``capi.REDUCE_MAX``);
+        ``None`` removes it.  With torch.distributed: ``lambda a, op: dist.all_reduce(torch.from_numpy(a),
+        op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX)`` (gloo) or through a device buffer (NCCL)."""
+        if fn is None:
+            self._allreduce_cb = None
+            capi.check(capi.lib().pb200_set_allreduce(self._h, C.cast(None, capi.ALLREDUCE_FN), None),
+                       "pb200_set_allreduce")
+            return
+
+        def _cb(_user, buf, n, op):
+            fn(np.ctypeslib.as_array(buf, shape=(n,)), int(op))
+        self._allreduce_cb = capi.ALLREDUCE_FN(_cb)  # keep alive
+        capi.check(capi.lib().pb200_set_allreduce(self._h, self._allreduce_cb, None), "pb200_set_allreduce")
+
     def condition_results(self):
         """Per-condition result packages of the last evaluation (A7)."""
         T = self.tables

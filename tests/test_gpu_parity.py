@@ -240,3 +240,61 @@ def test_every_lane_group_width_matches_oracle(oracle_available, model, lanes):
     assert st == ro["status"] == 0
     assert_llh_close(fval, ro["fval"])
     assert_grad_close(grad, ro["grad"])
+
+
+@pytest.mark.parametrize("maker,C", [(synth.steadystate_hierarchical, 10), (synth.fujita_hierarchical, 12)],
+                         ids=["steadystate", "fujita"])
+def test_hierarchical_partitioned_over_two_ranks(maker, C):
+    """Hierarchical evaluation with the conditions split over two ranks (two handles with
+    pb200_set_partition, the collective hook implemented with a thread barrier): the analytic inner
+    parameters need sums over ALL conditions, so every rank must arrive at the single-rank result."""
+    import threading
+    from parpe_b200 import capi
+    from parpe_b200.problem import B200SummedGradientFunction
+    tab = maker(C, seed=2)
+    full = synth.random_theta(tab, seed=5, width=0.2)
+    outer = np.delete(full, tab.hier.inner_idx)
+    ref = B200SummedGradientFunction(tab).hier_evaluate(outer, want_gradient=True)
+    ref0 = B200SummedGradientFunction(tab).hier_evaluate(outer, want_gradient=False)
+    assert ref["status"] == 0
+
+    world = 2
+    barrier = threading.Barrier(world)
+    slots = [None] * world
+
+    def make_allreduce(rank):
+        def allreduce(arr, op):
+            slots[rank] = arr.copy()
+            barrier.wait()
+            stacked = np.stack(slots)
+            out = stacked.sum(axis=0) if op == capi.REDUCE_SUM else stacked.max(axis=0)
+            barrier.wait()
+            arr[:] = out
+        return allreduce
+
+    results = [None] * world
+    results0 = [None] * world
+
+    def run(rank):
+        f = B200SummedGradientFunction(tab)
+        f.set_partition(rank, world)
+        f.set_allreduce(make_allreduce(rank))
+        results[rank] = f.hier_evaluate(outer, want_gradient=True)
+        results0[rank] = f.hier_evaluate(outer, want_gradient=False)
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    for r in range(world):
+        assert results[r] is not None and results[r]["status"] == 0
+        assert abs(results[r]["fval"] - ref["fval"]) <= 1e-10 * abs(ref["fval"])
+        np.testing.assert_allclose(results[r]["grad"], ref["grad"], rtol=1e-9, atol=1e-10 * np.max(np.abs(ref["grad"])))
+        np.testing.assert_allclose(results[r]["full_parameters"], ref["full_parameters"], rtol=1e-10)
+        assert abs(results0[r]["fval"] - ref0["fval"]) <= 1e-10 * abs(ref0["fval"])
+    # a partitioned hierarchical evaluation without the hook is refused
+    f = B200SummedGradientFunction(tab)
+    f.set_partition(0, 2)
+    with pytest.raises(capi.B200LibraryError):
+        f.hier_evaluate(outer)
