@@ -138,6 +138,20 @@ class B200SummedGradientFunction : public SummedGradientFunction<int> {
         return idx;
     }
 
+    /// This process simulates the share `rank` of `world` of every index list and returns partial sums
+    /// (what LoadBalancerMaster/Worker distribute over MPI ranks in the reference); the caller
+    /// all-reduces fval and gradient.
+    void setPartition(int rank, int world) {
+        if (pb200_set_partition(handle_, rank, world) != 0)
+            throw std::runtime_error(std::string("pb200_set_partition: ") + pb200_last_error());
+    }
+    /// Collective hook the hierarchical wrapper needs when the conditions are partitioned
+    /// (include/parpe_b200.h: pb200_set_allreduce), e.g. a function calling MPI_Allreduce in place.
+    void setAllreduce(pb200_allreduce_fn fn, void* user) {
+        if (pb200_set_allreduce(handle_, fn, user) != 0)
+            throw std::runtime_error(std::string("pb200_set_allreduce: ") + pb200_last_error());
+    }
+
     pb200_handle* handle() const { return handle_; }
     const B200ProblemTables& tables() const { return tables_; }
 
