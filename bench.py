@@ -279,6 +279,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (`value`) --------------------------------------
+    # one evaluation through the host API first: it leaves the cost-aware processing order (previous
+    # evaluation's step counts) in the handle, which the device-resident path then uses as the
+    # host path does from its second evaluation on
+    fun.evaluate(theta, idx)
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -371,6 +375,8 @@ def main():
             "config": {"workload": workload_name(world), "conditions_total": n_total, "rtol": tab.rtol,
                        "atol": tab.atol, "l2": "flushed between timed steps (256 MiB fill, untimed)",
                        "timing": "CUDA events on the launching stream per step, max over ranks",
+                       "order": "positions handed out by the previous evaluation's step counts, costliest first "
+                                "(PB200_REORDER=0: index order); results do not depend on it",
                        "lanes_per_condition": fun.last_launch()["lanes"], "grid": fun.last_launch()["grid"],
                        "block": fun.last_launch()["block"]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 48 * n_opt,
