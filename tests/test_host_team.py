@@ -123,3 +123,42 @@ def test_network_tables_consistent():
     cols = np.repeat(np.arange(spec.nx), np.diff(spec.csc_ptr))
     assert np.array_equal(spec.csc_row, rows[spec.csc_from_csr])
     assert np.array_equal(cols, spec.j_col[spec.csc_from_csr])
+
+
+def test_network_evaluator_against_independent_integration(oracle_available):
+    """The oracle's network model and the device share one evaluator (net_model.cuh), so it is pinned
+    separately: a numpy restatement of the mass-action right-hand side, integrated by scipy's BDF,
+    must reproduce the observables the oracle (AMICI/CVODES over the C evaluator) returns."""
+    from scipy.integrate import solve_ivp
+    from oracle.binding import OracleProblem
+    model = "net32"
+    spec = get_spec(model)
+    tab = synth.make_problem(model, 2, seed=3, timepoints=synth.DEFAULT_TIMEPOINTS[model][:4])
+    theta = synth.random_theta(tab, seed=2, width=0.3)
+    ora = OracleProblem(tab)
+    rc, y_ora, _ = ora.get_model_outputs(theta)
+    assert rc == 0
+    ra, rb = spec.r_a, spec.r_b
+
+    def rates(x, p):
+        w = spec.kappa * p[spec.pidx]
+        return w * np.where(ra >= 0, x[np.maximum(ra, 0)], 1.0) * np.where(rb >= 0, x[np.maximum(rb, 0)], 1.0)
+
+    S = np.zeros((spec.nx, spec.nr))
+    for i in range(spec.nx):
+        for e in range(spec.s_ptr[i], spec.s_ptr[i + 1]):
+            S[i, spec.s_reac[e]] += spec.s_coef[e]
+    O = np.zeros((spec.ny, spec.nx))
+    for j in range(spec.ny):
+        for e in range(spec.o_ptr[j], spec.o_ptr[j + 1]):
+            O[j, spec.o_idx[e]] += spec.o_w[e]
+    for c in range(tab.n_conditions):
+        p = _unscaled_p(tab, c, theta, ora)
+        k = tab.k[c]
+        x0 = spec.x0_base * np.where(spec.x0_kidx >= 0, k[np.maximum(spec.x0_kidx, 0)], 1.0)
+        lo, hi = tab.t_offsets[c], tab.t_offsets[c + 1]
+        t = tab.t[lo:hi]
+        sol = solve_ivp(lambda _t, x: S @ rates(x, p), (0.0, t[-1]), x0, method="BDF", t_eval=t, rtol=1e-10, atol=1e-13)
+        assert sol.success
+        y_ref = (O @ sol.y).T
+        np.testing.assert_allclose(y_ora[lo * spec.ny:hi * spec.ny].reshape(-1, spec.ny), y_ref, rtol=2e-6, atol=1e-9)
