@@ -9,7 +9,7 @@ dataIndices, fval, gradient) -- over one batch of synthetic conditions.
 
 Workload (BASELINE.json configs[1]): Boehm_JProteomeRes2014-shape model (8 states, 9
 parameters, 3 observables, 16 output times), forward sensitivities w.r.t. all 9
-parameters, rtol 1e-8 / atol 1e-12, random parameters in bounds, CONDITIONS_PER_GPU
+parameters, rtol 1e-8 / atol 1e-12, random parameters in bounds, CONDITIONS_PER_GPU (18 944)
 conditions per GPU (weak scaling: the global problem has N x that many conditions, each
 rank simulates its contiguous share and one NCCL all-reduce combines nllh and gradient).
 The real PEtab problem is not vendored in the reference tree: model structure is a
@@ -35,7 +35,10 @@ METRIC = "forward-sensitivity ODE solves/sec per obj+grad eval"
 UNIT = "solves/s"
 MODEL = "boehm"   # --workload: boehm (the metric's configuration, default) | chen | froehlich | net32 | fujita ...
 DEFAULT_CONDITIONS = {"chen": 296, "froehlich": 148, "net32": 4736}
-CONDITIONS_PER_GPU = int(os.environ.get("PB200_BENCH_CONDITIONS", 16384))
+# conditions per GPU: four resident waves of the small-model kernel on a B200 (148 SMs x 32 conditions per SM);
+# any number works -- the kernel pulls conditions from a queue -- but a partial last wave costs a whole one
+# (16 384 conditions = 3.46 waves run at 145 k solves/s, whole waves at 163 k)
+CONDITIONS_PER_GPU = int(os.environ.get("PB200_BENCH_CONDITIONS", 4 * 148 * 32))
 LARGE_MODELS = ("chen", "froehlich", "net32", "net31")
 CPU_SAMPLE_SECONDS = float(os.environ.get("PB200_BENCH_CPU_SECONDS", 15.0))
 
