@@ -162,3 +162,25 @@ def test_network_evaluator_against_independent_integration(oracle_available):
         assert sol.success
         y_ref = (O @ sol.y).T
         np.testing.assert_allclose(y_ora[lo * spec.ny:hi * spec.ny].reshape(-1, spec.ny), y_ref, rtol=2e-6, atol=1e-9)
+
+
+def test_host_team_output_time_edge_cases(oracle_available):
+    """Output times at t0 (no integration, data point on the initial state) and repeated output times
+    (second one within round-off of the current time: no further step), as ForwardProblem handles them
+    (forwardproblem.cpp:23-35,152-159)."""
+    from oracle.binding import OracleProblem
+    from tests.host_harness.binding import simulate_team
+    tab = synth.make_problem("net32", 2, seed=7, timepoints=np.array([0.0, 0.5, 0.5, 2.0]))
+    theta = synth.random_theta(tab, seed=3, width=0.3)
+    ora = OracleProblem(tab, 2, 1)
+    ro = ora.evaluate(theta)
+    assert ro["status"] == 0
+    for c in range(tab.n_conditions):
+        p = _unscaled_p(tab, c, theta, ora)
+        plist = ora.plist(c)
+        lo, hi = tab.t_offsets[c], tab.t_offsets[c + 1]
+        r = simulate_team("net32", p, tab.k[c], plist, tab.t[lo:hi], tab.y_of(c), tab.sigma_of(c))
+        assert r["status"] == 0
+        assert_llh_close(r["llh"], ro["llh"][c])
+        fac = np.array([p[i] * np.log(10) for i in plist])
+        assert_grad_close(r["sllh"] * fac, ro["sllh"][c][:len(plist)])
