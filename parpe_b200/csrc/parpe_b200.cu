@@ -212,7 +212,8 @@ static int enqueue_evaluation(pb200_handle* h, const double* theta, const int* i
     KernelArgs a = h->args;
     a.theta_tab = h->d_theta_tab.p;
     a.idx = h->d_idx.p;
-    a.order = (h->reorder && h->order_valid && want_grad == h->last_want_grad) ? h->d_order.p : nullptr;
+    // (any permutation is valid; the ranking by step counts holds with and without sensitivities)
+    a.order = (h->reorder && h->order_valid) ? h->d_order.p : nullptr;
     a.n = n;
     a.want_grad = want_grad;
     a.counter = h->d_counter.p;
