@@ -314,6 +314,29 @@ def main():
     out_host = d_out.cpu().numpy()
     value = args.steps * n_total / total_s
 
+    # ---- objective only (gradient.empty() in the reference): same workload, no sensitivities ----
+    def step_cost_only():
+        fun.evaluate_device(theta, idx, False, d_out.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.all_reduce(d_out)
+    for _ in range(2):
+        step_cost_only()
+    barrier()
+    ev0 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        ev0[k][0].record(stream)
+        step_cost_only()
+        ev0[k][1].record(stream)
+    barrier()
+    cost_s = torch.tensor([sum(a.elapsed_time(b) for a, b in ev0) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cost_s, op=dist.ReduceOp.MAX)
+    cost_only_value = args.steps * n_total / float(cost_s.item())
+    # leave the gradient evaluation's per-condition results in the handle (read below)
+    step_device()
+    barrier()
+
     # ---- end to end through the public API with host buffers (`e2e`) ----------------
     h_out = torch.empty(2 + n_opt, dtype=torch.float64).pin_memory()
     e2e_t = []
@@ -386,6 +409,8 @@ def main():
                     "d2h_bytes_per_step": 8 * (2 + n_opt),
                     "note": "pb200_evaluate with host theta/idx/fval/gradient; the index list is re-uploaded "
                             "only when it changes (4 B/condition)"},
+            "cost_only": {"value": cost_only_value, "unit": UNIT,
+                          "note": "objective without gradient (no sensitivity columns), device-resident, same timing rules"},
             "gpu_launches": 2 * args.steps, "clocks": clocks, "roofline": roofline,
             "nllh": float(out_host[0]), "failed_conditions": nerr, "wall_s": wall,
         }
