@@ -438,26 +438,16 @@ int pb200_evaluate(pb200_handle* h, const double* theta, int n_opt, const int* i
         // processing order of the next evaluation of the same index list: costliest conditions first
         // (they also sit next to conditions of similar cost in a warp / CTA)
         const int n = h->last_n;
-        h->stats_host.resize((size_t)n * NSTATS);
-        PB_CUDA(cudaMemcpyAsync(h->stats_host.data(), h->d_stats.p, sizeof(int64_t) * (size_t)n * NSTATS,
-                                cudaMemcpyDeviceToHost, h->stream));
+        // only the step counts travel (one int64 out of the 16 of each record)
+        h->stats_host.resize((size_t)n);
+        PB_CUDA(cudaMemcpy2DAsync(h->stats_host.data(), sizeof(int64_t), h->d_stats.p + STAT_NST,
+                                  sizeof(int64_t) * NSTATS, sizeof(int64_t), (size_t)n, cudaMemcpyDeviceToHost,
+                                  h->stream));
         PB_CUDA(cudaStreamSynchronize(h->stream));
         h->order_host.resize(n);
         for (int r = 0; r < n; ++r) h->order_host[r] = r;
         const int64_t* st = h->stats_host.data();
-        const int mode = h->reorder;
-        std::stable_sort(h->order_host.begin(), h->order_host.end(), [st, mode](int x, int y) {
-            const int64_t* a = st + (size_t)x * NSTATS;
-            const int64_t* b = st + (size_t)y * NSTATS;
-            if (a[STAT_NST] != b[STAT_NST]) return a[STAT_NST] > b[STAT_NST];
-            if (mode >= 2) {  // conditions with the same history of setups / iterations / failures next to each other
-                if (a[STAT_NSETUPS] != b[STAT_NSETUPS]) return a[STAT_NSETUPS] > b[STAT_NSETUPS];
-                if (a[STAT_NNI] != b[STAT_NNI]) return a[STAT_NNI] > b[STAT_NNI];
-                if (a[STAT_NNIS] != b[STAT_NNIS]) return a[STAT_NNIS] > b[STAT_NNIS];
-                if (a[STAT_NETF] != b[STAT_NETF]) return a[STAT_NETF] > b[STAT_NETF];
-            }
-            return false;
-        });
+        std::stable_sort(h->order_host.begin(), h->order_host.end(), [st](int x, int y) { return st[x] > st[y]; });
         PB_CUDA(cudaMemcpyAsync(h->d_order.p, h->order_host.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
         PB_CUDA(cudaStreamSynchronize(h->stream));
         h->order_valid = true;
