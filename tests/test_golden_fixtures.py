@@ -24,7 +24,7 @@ def _load(path):
 
 
 def test_fixtures_exist():
-    assert len(FILES) >= 5
+    assert len(FILES) >= 6
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-5] for f in FILES])

@@ -27,6 +27,8 @@ CASES = {
     "fujita_log10": ("fujita", 6, dict(scale="log10", seed=14)),
     # large-model path (table-driven mass-action network, one CTA per condition)
     "net32_mixed": ("net32", 4, dict(scale="mixed", seed=15, sigma_mode="mixed", missing_fraction=0.1)),
+    # nx = 500, nplist = 50 (Chen shape), first two output times
+    "chen_log10": ("chen", 1, dict(scale="log10", seed=16, timepoints=[0.1, 0.3])),
 }
 
 
