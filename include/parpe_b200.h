@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PB200_ABI_VERSION 1
+#define PB200_ABI_VERSION 2
 
 /* parpe::FunctionEvaluationStatus (include/parpecommon/functions.h:16-20) */
 #define PB200_EVAL_SUCCESS 0
@@ -89,7 +89,10 @@ enum {
      * fields of kilo-cycles each -- diagnostics behind DESIGN.md 3.4's phase split */
     PB200_STAT_CYC_INVERSION, /* (panel factorisation << 32) | rank-NB update */
     PB200_STAT_CYC_NEWTON,    /* (solve GEMMs << 32) | right-hand sides       */
-    PB200_NSTATS = 16
+    PB200_STAT_NFALLBACK,     /* setups whose sparse factorisation met a weak diagonal pivot and were
+                                 redone by the dense path with partial pivoting */
+    PB200_STAT_CYC_SPARSE,    /* (sparse numeric factorisation << 32) | sparse triangular solves */
+    PB200_NSTATS = 20
 };
 
 /*
@@ -160,14 +163,57 @@ int pb200_create(const pb200_problem_desc* desc, int device, pb200_handle** out)
 void pb200_destroy(pb200_handle* h);
 
 /*
- * Shard the data indices of every evaluation over `world` processes: this handle
- * then simulates positions [floor(rank*n/world), floor((rank+1)*n/world)) of the
- * index list only and returns PARTIAL sums (the caller all-reduces them).
+ * Shard the data indices of every evaluation over `world` handles (one per GPU /
+ * process): this handle then simulates positions [floor(rank*n/world),
+ * floor((rank+1)*n/world)) of the index list only.
  * Replaces: LoadBalancerMaster's dynamic assignment of packages to MPI workers
  * (src/parpeloadbalancer/loadBalancerMaster.cpp:104-134) by a static contiguous
  * partition in index order (amiciSimulationRunner.cpp:49-80 chunk order).
+ * pb200_evaluate on a partitioned handle returns the GLOBAL fval / gradient /
+ * status on every rank (the reference master sums all workers' results before
+ * evaluate returns: multiConditionProblem.cpp:738-748,775-824) and therefore
+ * needs a collective: pb200_nccl_init (in-library NCCL all-reduce of 2 + n_opt
+ * doubles on the device) or pb200_set_allreduce (the caller's host transport,
+ * e.g. MPI_Allreduce).  Without one it fails with PB200_ERR_ARG, unless
+ * rank-local partial sums were requested with PB200_OPT_PARTIAL_SUMS.
  */
 int pb200_set_partition(pb200_handle* h, int rank, int world);
+
+/*
+ * In-library collective: one NCCL communicator over the `world` handles of a
+ * partitioned problem (one handle per GPU; the handles may live in different
+ * processes or in different threads of one process).  Rank 0 obtains a 128-byte
+ * id with pb200_nccl_unique_id and distributes it by any means (MPI_Bcast in
+ * parPE; a thread-shared buffer in a single process); every rank then calls
+ * pb200_nccl_init, which also sets the partition (rank, world).  From then on
+ * pb200_evaluate, pb200_evaluate_device and pb200_hier_evaluate combine the
+ * ranks' (nllh, #errors, gradient[n_opt]) with ONE ncclAllReduce on the
+ * handle's stream before the +inf / failure rule is applied.  libnccl.so.2 is
+ * resolved at run time (dlopen); PB200_ERR_CUDA if it is absent.
+ */
+int pb200_nccl_unique_id(char* id128);
+int pb200_nccl_init(pb200_handle* h, const char* id128, int rank, int world);
+
+/*
+ * Tuning / experiment switches.  The library never reads the environment; these
+ * are set per handle by the caller (tools/ scripts set them for experiments).
+ */
+enum {
+    PB200_OPT_REORDER = 1,        /* 1 (default): conditions are handed out costliest first, by the
+                                     step counts of an earlier evaluation of the same index list;
+                                     0: index order.  Results do not depend on it. */
+    PB200_OPT_ORDER_REFRESH = 2,  /* refresh that order every this many evaluations (default 16) */
+    PB200_OPT_KERNEL_VARIANT = 3, /* small-model kernel CTA shape: 2 (default) one CTA per SM, 0 two-warp CTAs */
+    PB200_OPT_CTAS_PER_SM = 4,    /* cap on resident CTAs per SM (0 = occupancy limit) */
+    PB200_OPT_SYNC_PERIOD = 5,    /* CTA barrier every this many step attempts (default 1) */
+    PB200_OPT_STAGE_SYNC = 6,     /* CTA barrier between the stages of a step attempt (default 0) */
+    PB200_OPT_PARTIAL_SUMS = 7,   /* 1: pb200_evaluate on a partitioned handle without a collective
+                                     returns rank-local partial sums instead of failing (tests) */
+    PB200_OPT_LINSOL = 8          /* large-model path: 0 automatic (by fill of the symbolic factorisation),
+                                     1 dense inverse (amici LinearSolver::dense), 2 sparse fixed-pattern LU
+                                     with a dense Schur block (LinearSolver::KLU's role) */
+};
+int pb200_set_option(pb200_handle* h, int key, int value);
 /* [lo,hi) of an n-long index list owned by (rank, world): the assignment rule */
 void pb200_partition_bounds(int n, int rank, int world, int* lo, int* hi);
 
@@ -192,11 +238,29 @@ int pb200_evaluate(pb200_handle* h, const double* theta, int n_opt, const int* i
  * d_out[0] = partial nllh, d_out[1] = number of failed conditions,
  * d_out[2..2+n_opt) = partial gradient (zeros if !want_grad).  theta and idx are
  * host pointers (the optimiser lives on the host; they are staged through pinned
- * memory).  Used for the multi-GPU path (NCCL all-reduce on d_out) and for
- * device-timed throughput.  The +inf / failure mapping is the caller's job.
+ * memory).  With pb200_nccl_init the all-reduce over the ranks is enqueued on the
+ * same stream and d_out holds the GLOBAL sums; otherwise the partial sums of this
+ * rank.  Used for device-timed throughput.  The +inf / failure mapping is the
+ * caller's job.
  */
 int pb200_evaluate_device(pb200_handle* h, const double* theta, int n_opt, const int* idx,
                           int n_idx, int want_grad, double* d_out, void* stream);
+
+/*
+ * Large-model path: what the one-time symbolic analysis of the Newton matrix's pattern produced
+ * (the klu_analyze role, sunlinsol_klu.c:259-330).  out[0..n): solver the automatic choice takes
+ * (1 dense inverse, 2 sparse LU + dense Schur block), nx, sparse pivots n1, dense block m, nnz(J),
+ * nnz(L), nnz(U) of the sparse part, multiply-adds of one numeric factorisation of the sparse part
+ * incl. the Schur assembly, levels of the forward / backward substitution, flops of one numeric
+ * factorisation (without the dense block), flops of the two triangular solves for one right-hand
+ * side, bytes of the factors (sparse values + dense block) written per setup / read per solve.
+ * Returns the number of entries written (0 for the small-model kernels).
+ */
+int pb200_linsol_info(pb200_handle* h, int64_t* out, int n);
+
+/* host<->device bytes moved by the most recent pb200_evaluate call on this handle (parameter table,
+ * index list if it changed, results, processing-order refresh): what bench.py reports as e2e bytes */
+int pb200_last_transfer_bytes(pb200_handle* h, int64_t* h2d_bytes, int64_t* d2h_bytes);
 
 /* launch geometry and device time of the most recent simulate+reduce launch pair */
 int pb200_last_launch(pb200_handle* h, int* lanes_per_condition, int* grid, int* block,

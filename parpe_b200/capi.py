@@ -19,7 +19,12 @@ EXPORTED_SYMBOLS = [
     "pb200_last_error", "pb200_create", "pb200_destroy", "pb200_set_partition", "pb200_partition_bounds",
     "pb200_evaluate", "pb200_evaluate_device", "pb200_last_launch", "pb200_get_condition_results",
     "pb200_get_model_outputs", "pb200_measure_fp64_peak", "pb200_set_allreduce", "pb200_hier_attach", "pb200_hier_num_outer", "pb200_hier_evaluate",
+    "pb200_set_option", "pb200_nccl_unique_id", "pb200_nccl_init", "pb200_last_transfer_bytes", "pb200_linsol_info",
 ]
+# pb200_set_option keys (include/parpe_b200.h)
+OPT_REORDER, OPT_ORDER_REFRESH, OPT_KERNEL_VARIANT, OPT_CTAS_PER_SM, OPT_SYNC_PERIOD, OPT_STAGE_SYNC = 1, 2, 3, 4, 5, 6
+OPT_PARTIAL_SUMS, OPT_LINSOL = 7, 8
+LINSOL_AUTO, LINSOL_DENSE, LINSOL_SPARSE = 0, 1, 2
 
 _lib = None
 # void (*pb200_allreduce_fn)(void* user, double* buf, int n, int op)
@@ -64,6 +69,11 @@ def lib():
     L.pb200_hier_attach.argtypes = [C.c_void_p, C.POINTER(HierDesc)]
     L.pb200_hier_num_outer.argtypes = [C.c_void_p]
     L.pb200_hier_evaluate.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp, dp]
+    L.pb200_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.pb200_nccl_unique_id.argtypes = [C.c_char_p]
+    L.pb200_nccl_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+    L.pb200_last_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.pb200_linsol_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
     _lib = L
     return L
 

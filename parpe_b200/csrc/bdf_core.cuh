@@ -76,7 +76,7 @@ enum : int {
 
 enum : int {
     STAT_NST = 0, STAT_NFE, STAT_NSETUPS, STAT_NJE, STAT_NNI, STAT_NNIS, STAT_NFSE, STAT_NETF, STAT_NETFS,
-    STAT_NCFN, STAT_NCFNS, STAT_NOR, STAT_TRIALS, STAT_QSUM, NSTATS = 16
+    STAT_NCFN, STAT_NCFNS, STAT_NOR, STAT_TRIALS, STAT_QSUM, STAT_NFALLBACK = 16, STAT_CYC_SPARSE = 17, NSTATS = 20
 };
 
 // ---- CVODES constants (cvodes_impl.h:57-131,202-204; cvodes.c:298-305;
@@ -1638,7 +1638,7 @@ struct Bdf {
                 for (;;) {
                     if (it_ >= io_.nt) { finish(SIM_SUCCESS); return; }
                     tout_ = io_.t[it_];
-                    if (isinf(tout_)) { finish(SIM_SUCCESS); return; }  // post-equilibration: out of scope
+                    if (!PB_FINITE(tout_)) { finish(SIM_ERROR); return; }  // t = inf (post-equilibration) is not implemented: an error, never a silently dropped point (pb200_create rejects such tables)
                     bool integrate = (tout_ > opt.t0) && (tn < tout_);
                     if (integrate) {  // is_next_t_too_close, forwardproblem.cpp:23-35
                         const double tdiff = tout_ - tn;
@@ -1739,7 +1739,8 @@ struct Bdf {
         s[STAT_NST] = nst; s[STAT_NFE] = nfe; s[STAT_NSETUPS] = nsetups; s[STAT_NJE] = nje;
         s[STAT_NNI] = nni; s[STAT_NNIS] = nniS; s[STAT_NFSE] = nfSe; s[STAT_NETF] = netf;
         s[STAT_NETFS] = netfS; s[STAT_NCFN] = ncfn; s[STAT_NCFNS] = ncfnS; s[STAT_NOR] = nor;
-        s[STAT_TRIALS] = trials; s[STAT_QSUM] = qsum; s[14] = 0; s[15] = 0;
+        s[STAT_TRIALS] = trials; s[STAT_QSUM] = qsum;
+        for (int j = 14; j < NSTATS; ++j) s[j] = 0;
     }
 #undef PB_FOR_COLS
 #undef PB_FOR_RANGE

@@ -33,6 +33,7 @@
 
 #include "bdf_core.cuh"
 #include "net_model.cuh"
+#include "sparse_lu.h"
 #include "team.cuh"
 
 namespace pb200 {
@@ -88,6 +89,12 @@ struct TeamWork {
     double *acor, *ewt, *b, *scr;
     double *dfdp, *A, *Jsaved, *Jcur, *ysh, *yj, *fout, *vb, *v, *p, *k, *sllh;
     int *plist, *perm;
+    // sparse path (sparse_lu.h): factor values V of the sparse part, and the row gather of the dense
+    // Schur solve (original row index of the k-th pivot row of the block)
+    double* luV;
+    int* gidx;
+    double* stage;      // host harness: staging area of the sparse triangular solves
+    int stage_doubles;  // its capacity (device: shared memory from TEAM_SM_RBUF to the end)
     // staging buffers: host harness only -- on the device they are derived from the dynamic
     // shared memory base at every use (BdfTeam::panel() ...), so that the compiler knows the
     // address space (LDS/STS instead of generic LD/ST)
@@ -99,14 +106,15 @@ struct TeamWork {
     PB_HD double* zn(int j) const { return znbase + (size_t)j * nxc; }
 
     /// doubles of HBM workspace one team needs
-    static size_t hbm_doubles(const NetTables& T) {
+    static size_t hbm_doubles(const NetTables& T, int nV = 0) {
         const size_t nxc = (size_t)T.nx * (T.np + 1);
         size_t n = (cv::L_MAX + 4) * nxc + (size_t)T.nx * T.np + (size_t)T.nx * T.nx + 2 * (size_t)T.jell_w * T.nx + 3 * (size_t)T.nx +
                    2 * (size_t)T.nr + T.np + T.nk + (T.np + 1);
-        n += ((size_t)T.np + T.nx + 1) / 2 + 1;  // plist, perm (ints)
+        n += (size_t)nV + 2;
+        n += ((size_t)T.np + 2 * (size_t)T.nx + 1) / 2 + 1;  // plist, perm, gidx (ints)
         return (n + 15) & ~(size_t)15;
     }
-    PB_HD void carve(double* base, const NetTables& T) {
+    PB_HD void carve(double* base, const NetTables& T, int nV = 0) {
         const size_t nxc = (size_t)T.nx * (T.np + 1);
         double* q = base;
         znbase = q; q += cv::L_MAX * nxc;
@@ -127,8 +135,10 @@ struct TeamWork {
         p = q; q += T.np;
         k = q; q += T.nk;
         sllh = q; q += T.np + 1;
+        luV = q; q += nV + 2;
         plist = reinterpret_cast<int*>(q);
         perm = plist + T.np;
+        gidx = perm + T.nx;
     }
     /// panel width that fits `smem_doubles` of staging memory (after rbuf / rowk / piv)
     static int panel_width(int nx, size_t panel_doubles) {
@@ -141,10 +151,15 @@ struct TeamWork {
 template <class Team>
 struct BdfTeam {
     NetTables T;
+    SparseLU SP{};   // symbolic factorisation (enabled = 0: dense path only)
     Team tm;
     TeamWork w;
     SolverOptions opt;
     int nx, ns, ncol;
+    int dn;          // dimension (= leading dimension) of the dense matrix in w.A: nx, or the Schur block's m
+    bool use_sparse = true;  // linear-solver choice of this launch (SP.enabled permitting)
+    bool lin_sparse; // the current factorisation is sparse part + dense Schur block
+    int nfallback;   // setups that fell back to the dense path (weak diagonal pivot)
     bool sensi;
     enum { PH_STATE = 0, PH_SENS = 1 };
 
@@ -163,7 +178,7 @@ struct BdfTeam {
     int fail_, ret_;
     // phase cycle counters (device: clock64 of thread 0's SM; exported in stats[14..15] packed as
     // two 32-bit fields of kilo-cycles each: [14] = inversion panel | inversion update, [15] = solve GEMM | model+rhs)
-    long long cyc_panel, cyc_update, cyc_solve, cyc_rhs;
+    long long cyc_panel, cyc_update, cyc_solve, cyc_rhs, cyc_spfactor, cyc_sptri;
     PB_HD static long long now() {
 #if defined(__CUDA_ARCH__)
         return clock64();
@@ -408,10 +423,8 @@ struct BdfTeam {
     /// Returns 0, or 1 on a zero / non-finite pivot.
     PB_HD int invert_newton_matrix() {
         double* const A = w.A;
-        const int NB = w.NB;
         tm.sync();
         for (size_t e = tm.tid(); e < (size_t)nx * nx; e += tm.size()) A[e] = 0.0;
-        PT_FOR(i, 0, nx) w.perm[i] = i;
         tm.sync();
         PT_FOR(i, 0, nx) {
             for (int t = 0; t < T.jell_w; ++t) {
@@ -419,6 +432,22 @@ struct BdfTeam {
                 if (j >= 0) A[i + (size_t)j * nx] = (i == j ? 1.0 : 0.0) - gamma * w.Jsaved[t * nx + i];
             }
         }
+        tm.sync();
+        dn = nx;
+        lin_sparse = false;
+        const int r = invert_dense();
+        if (r) return r;
+        PT_FOR(i, 0, nx) w.gidx[i] = w.perm[i];
+        tm.sync();
+        return 0;
+    }
+
+    /// In-place inversion (with row pivoting, order in w.perm) of the dn x dn column-major matrix in w.A
+    PB_HD int invert_dense() {
+        double* const A = w.A;
+        const int NB = w.NB;
+        const int nx = dn;  // (shadows the member: the dense dimension)
+        PT_FOR(i, 0, nx) w.perm[i] = i;
         tm.sync();
 #if defined(__CUDA_ARCH__)
         if (nx <= tm.size()) return invert_rows();
@@ -553,7 +582,7 @@ struct BdfTeam {
         constexpr int NB = TEAM_NB_MAX;
         // members used in the loops are copied to locals: the object is addressable (out-of-line member
         // function), so a store through a generic pointer would force a reload of every member after it
-        const int nx = this->nx;
+        const int nx = this->dn;  // dimension of the dense matrix (the whole Newton matrix or the Schur block)
         double* const A = w.A;
         const int i = threadIdx.x;
         const bool rowok = i < nx;
@@ -829,18 +858,20 @@ struct BdfTeam {
     __device__ __noinline__ void solve_pass_mma(int c0, int nc, double nsc) {
         constexpr int KC = 64, PRE = (KC * 8 * NT + 511) / 512;
         static_assert(8 * NT * TEAM_BS <= TEAM_RTILE, "tile does not fit");
-        const int nx = this->nx;  // (locals: see invert_rows)
+        const int nx = this->dn;  // (locals: see invert_rows) dense dimension
+        const int ldb = this->nx;  // leading dimension of the right-hand sides / solutions
         double* const scr = w.scr;
         const int i = threadIdx.x;
         const int lane = i & 31, lq = lane & 3, lr = lane >> 2;
         double* const sm = smem_base();
         const double* const A = w.A;
         const double* const b = w.b;
-        const int* const perm = w.perm;
+        const int* const perm = w.gidx;
+        const int* const omap = lin_sparse ? SP.ord + SP.n1 : nullptr;  // solution row of block row r
         auto b_entry = [&](int ch, int e) -> double {
             const int cc = e / KC, kk = e - cc * KC;
             const int k = ch * KC + kk;
-            return (e < KC * 8 * NT && k < nx && cc < nc) ? b[perm[k] + (size_t)(c0 + cc) * nx] : 0.0;
+            return (e < KC * 8 * NT && k < nx && cc < nc) ? b[perm[k] + (size_t)(c0 + cc) * ldb] : 0.0;
         };
         auto b_pos = [&](int e) { return (e / KC) * TEAM_BS + (e % KC); };
         const int nchunks = (nx + KC - 1) / KC;
@@ -924,7 +955,7 @@ struct BdfTeam {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int r = rbase + 8 * mt, col = 8 * nt + 2 * lq + e;
-                        if (r < nx && col < nc) scr[r + (size_t)(c0 + col) * nx] = nsc * c[mt][nt][e];
+                        if (r < nx && col < nc) scr[(omap ? omap[r] : r) + (size_t)(c0 + col) * ldb] = nsc * c[mt][nt][e];
                     }
                 }
             }
@@ -939,18 +970,20 @@ struct BdfTeam {
         constexpr int KC = (TN == 1) ? 512 : 64;
         constexpr int PRE = (KC * TN + 511) / 512;
         static_assert(KC * TN <= TEAM_RBUF, "tile does not fit");
-        const int nx = this->nx;  // (locals: see invert_rows)
+        const int nx = this->dn;  // (locals: see invert_rows) dense dimension
+        const int ldb = this->nx;
         double* const scr = w.scr;
         const int i = threadIdx.x;
         const bool active = i < nx;
         double* const sm = smem_base();
         const double* const A = w.A;
         const double* const b = w.b;
-        const int* const perm = w.perm;
+        const int* const perm = w.gidx;
+        const int* const omap = lin_sparse ? SP.ord + SP.n1 : nullptr;
         auto b_entry = [&](int ch, int e) -> double {
             const int kk = e / TN, cc = e - kk * TN;
             const int k = ch * KC + kk;
-            return (k < nx && cc < nc && e < KC * TN) ? b[perm[k] + (size_t)(c0 + cc) * nx] : 0.0;
+            return (k < nx && cc < nc && e < KC * TN) ? b[perm[k] + (size_t)(c0 + cc) * ldb] : 0.0;
         };
         double acc[TN];
 #pragma unroll
@@ -1029,10 +1062,220 @@ struct BdfTeam {
         if (active) {
 #pragma unroll
             for (int cc = 0; cc < TN; ++cc)
-                if (cc < nc) scr[i + (size_t)(c0 + cc) * nx] = nsc * acc[cc];
+                if (cc < nc) scr[(omap ? omap[i] : i) + (size_t)(c0 + cc) * ldb] = nsc * acc[cc];
         }
     }
 #endif
+
+
+    // ---------------------------------------------------------------- sparse path (sparse_lu.h)
+    /// staging area of the sparse phases: shared memory from the broadcast tiles to the end of the
+    /// block's dynamic shared memory (idle while no dense GEMM runs); a heap array in the host build
+    PB_HD double* sp_stage() const {
+#if defined(__CUDA_ARCH__)
+        return smem_base() + TEAM_SM_RBUF;
+#else
+        return w.stage;
+#endif
+    }
+
+    /// Numeric factorisation on the fixed pattern (the klu_refactor role): sparse part entry by entry
+    /// over the dependency levels, then the Schur block assembled dense in w.A and inverted by the
+    /// dense path.  KLU keeps the diagonal as pivot unless |diag| < 0.001 max|column| (klu_factor's
+    /// tol; klu_refactor never re-pivots): the same bound is checked here on every multiplier, and
+    /// a violation (or a zero / non-finite pivot) returns 2 -- the caller then factors this matrix
+    /// by the dense path with partial pivoting instead.
+    PB_HD int factor_sparse() {
+        const int n1 = SP.n1, m = SP.m;
+        // V in shared memory while the levels run (every entry is read by later levels)
+        const bool v_staged = SP.nV <= w.stage_doubles;
+        double* const V = v_staged ? sp_stage() : w.luV;
+        const double* __restrict__ J = w.Jsaved;
+        const double gam = gamma;
+        bool bad = false;
+        const long long t_f0 = now();
+        tm.sync();
+        for (int l = 0; l < SP.n_tlevels; ++l) {
+            const int t1 = SP.tlevel_ptr[l + 1];
+            for (int t = SP.tlevel_ptr[l] + tm.tid(); t < t1; t += tm.size()) {
+                const int piv = SP.t_piv[t], src = SP.t_src[t];
+                double v = (piv == -2) ? 1.0 : 0.0;
+                if (src >= 0) v -= gam * J[src];
+                const int e1 = SP.t_pptr[t + 1];
+                for (int e = SP.t_pptr[t]; e < e1; ++e) v -= V[SP.p_l[e]] * V[SP.p_u[e]];
+                if (piv == -2) {
+                    if (!(fabs(v) > 0.0) || !PB_FINITE(v)) bad = true;
+                    v = 1.0 / v;
+                } else if (piv >= 0) {
+                    v *= V[piv];
+                    if (!(fabs(v) <= 1000.0)) bad = true;  // |pivot| < 0.001 |entry|, or not finite
+                }
+                V[SP.t_dst[t]] = v;
+            }
+            tm.sync();
+        }
+        if (tm.any(bad)) return 2;
+        // Schur block S = M22 - L21 U12, dense in w.A (leading dimension m)
+        double* const A = w.A;
+        for (size_t e = tm.tid(); e < (size_t)m * m; e += tm.size()) A[e] = 0.0;
+        tm.sync();
+        for (int t = tm.tid(); t < SP.n_starg; t += tm.size()) {
+            const int src = SP.s_src[t];
+            double v = SP.s_diag[t] ? 1.0 : 0.0;
+            if (src >= 0) v -= gam * J[src];
+            const int e1 = SP.s_pptr[t + 1];
+            for (int e = SP.s_pptr[t]; e < e1; ++e) v -= V[SP.p_l[e]] * V[SP.p_u[e]];
+            A[SP.s_dst[t]] = v;
+        }
+        if (v_staged) {
+            PT_FOR(e, 0, SP.nV) w.luV[e] = V[e];
+        }
+        tm.sync();
+        cyc_spfactor += now() - t_f0;
+        dn = m;
+        lin_sparse = true;
+        if (m > 0) {
+            const int r = invert_dense();
+            if (r) return 2;
+        }
+        PT_FOR(k, 0, m) w.gidx[k] = SP.ord[n1 + w.perm[k]];
+        tm.sync();
+        (void)n1;
+        return 0;
+    }
+
+    /// scr[:, c0 .. c0+nc) = nsc * M^-1 b[:, c0 .. c0+nc) through the sparse factors and the inverse
+    /// of the Schur block:  forward substitution with L (sparse rows in the staging area, all columns
+    /// of a batch side by side: one warp per row, lanes over the columns), Schur right-hand side,
+    /// dense GEMM with S^-1, backward substitution with U.
+    PB_HD void solve_sparse(int cmin, int cmax, double nsc) {
+        const int n1 = SP.n1, m = SP.m, nx = this->nx;
+        const int ncols = cmax - cmin + 1;
+        const double* __restrict__ V = w.luV;
+        const int* __restrict__ ord = SP.ord;
+        double* const Z = sp_stage();
+        double* const b = w.b;
+        double* const scr = w.scr;
+        int bc_max = w.stage_doubles / nx;
+        if (bc_max < 1) bc_max = 1;
+        const int nbatch = (ncols + bc_max - 1) / bc_max;
+        const int bc = (ncols + nbatch - 1) / nbatch;
+        const int nwt = (bc + Team::WARP - 1) / Team::WARP;  // warp tasks per row
+        const long long t_s0 = now();
+        // ---- forward: y = L11^-1 b1, b2' = b2 - L21 y
+        for (int c0 = cmin; c0 <= cmax; c0 += bc) {
+            const int nb = (cmax + 1 - c0 < bc) ? cmax + 1 - c0 : bc;
+            tm.sync();
+            PT_FOR(x, 0, n1 * nb) {
+                const int cl = x / n1, r = x - cl * n1;
+                Z[(size_t)r * bc + cl] = b[ord[r] + (size_t)(c0 + cl) * nx];
+            }
+            tm.sync();
+            for (int l = 0; l < SP.n_flev; ++l) {
+                const int r0 = SP.flev_ptr[l], nr = SP.flev_ptr[l + 1] - r0;
+                if (l > 0) {  // (level 0: rows without L entries)
+                    for (int task = tm.warp(); task < nr * nwt; task += tm.nwarps()) {
+                        const int r = SP.flev_rows[r0 + task / nwt];
+                        const int cl = (task % nwt) * Team::WARP + tm.lane();
+                        if (cl < nb) {
+                            double acc = Z[(size_t)r * bc + cl];
+                            const int e1 = SP.Lr_ptr[r + 1];
+                            for (int e = SP.Lr_ptr[r]; e < e1; ++e) acc -= V[n1 + e] * Z[(size_t)SP.Lr_col[e] * bc + cl];
+                            Z[(size_t)r * bc + cl] = acc;
+                        }
+                    }
+                    tm.sync();
+                }
+            }
+            // Schur rows (gather from the finished y) and write-back of y
+            for (int task = tm.warp(); task < m * nwt; task += tm.nwarps()) {
+                const int r = n1 + task / nwt;
+                const int cl = (task % nwt) * Team::WARP + tm.lane();
+                if (cl < nb) {
+                    const size_t g = ord[r] + (size_t)(c0 + cl) * nx;
+                    double acc = b[g];
+                    const int e1 = SP.Lr_ptr[r + 1];
+                    for (int e = SP.Lr_ptr[r]; e < e1; ++e) acc -= V[n1 + e] * Z[(size_t)SP.Lr_col[e] * bc + cl];
+                    b[g] = acc;
+                }
+            }
+            PT_FOR(x, 0, n1 * nb) {
+                const int cl = x / n1, r = x - cl * n1;
+                b[ord[r] + (size_t)(c0 + cl) * nx] = Z[(size_t)r * bc + cl];
+            }
+        }
+        tm.sync();
+        // ---- dense: x2 = S^-1 b2' (rows gathered through gidx, written to the Schur rows of scr)
+        const long long t_d0 = now();
+        if (m > 0) solve_dense(cmin, cmax, 1.0);
+        tm.sync();
+        const long long t_d1 = now();
+        // ---- backward: x1 = U11^-1 (y - U12 x2); scaled results to scr
+        const int nU0 = n1 + SP.nnzL;
+        for (int c0 = cmin; c0 <= cmax; c0 += bc) {
+            const int nb = (cmax + 1 - c0 < bc) ? cmax + 1 - c0 : bc;
+            tm.sync();
+            PT_FOR(x, 0, nx * nb) {
+                const int cl = x / nx, r = x - cl * nx;
+                const size_t g = ord[r] + (size_t)(c0 + cl) * nx;
+                Z[(size_t)r * bc + cl] = (r < n1) ? b[g] : scr[g];
+            }
+            tm.sync();
+            for (int l = 0; l < SP.n_blev; ++l) {
+                const int r0 = SP.blev_ptr[l], nr = SP.blev_ptr[l + 1] - r0;
+                for (int task = tm.warp(); task < nr * nwt; task += tm.nwarps()) {
+                    const int r = SP.blev_rows[r0 + task / nwt];
+                    const int cl = (task % nwt) * Team::WARP + tm.lane();
+                    if (cl < nb) {
+                        double acc = Z[(size_t)r * bc + cl];
+                        const int e1 = SP.Ur_ptr[r + 1];
+                        for (int e = SP.Ur_ptr[r]; e < e1; ++e) acc -= V[nU0 + e] * Z[(size_t)SP.Ur_col[e] * bc + cl];
+                        Z[(size_t)r * bc + cl] = acc * V[r];
+                    }
+                }
+                tm.sync();
+            }
+            PT_FOR(x, 0, nx * nb) {
+                const int cl = x / nx, r = x - cl * nx;
+                scr[ord[r] + (size_t)(c0 + cl) * nx] = nsc * Z[(size_t)r * bc + cl];
+            }
+        }
+        tm.sync();
+        cyc_sptri += (now() - t_s0) - (t_d1 - t_d0);
+    }
+
+    /// scr = nsc * (dense inverse) * b for the columns [cmin, cmax] (the whole matrix, or the Schur block
+    /// with its row gather / scatter maps)
+    PB_HD void solve_dense(int cmin, int cmax, double nsc) {
+#if defined(__CUDA_ARCH__)
+        const bool rows_path = dn <= tm.size();
+#else
+        const bool rows_path = false;
+#endif
+        if (cmin == cmax) {
+#if defined(__CUDA_ARCH__)
+            if (rows_path) solve_pass_rows<1>(cmin, 1, nsc);
+            else
+#endif
+                solve_pass<1>(cmin, 1, nsc);
+        } else {
+#if defined(__CUDA_ARCH__)
+            if (rows_path) {
+                for (int c0 = cmin; c0 <= cmax; c0 += 56) {
+                    const int nc = (cmax + 1 - c0 < 56) ? cmax + 1 - c0 : 56;
+                    if (nc > 24) solve_pass_mma<7>(c0, nc, nsc);
+                    else solve_pass_mma<3>(c0, nc, nsc);
+                }
+            } else
+#endif
+            {
+                for (int c0 = cmin; c0 <= cmax; c0 += TEAM_TN) {
+                    const int nc = (cmax + 1 - c0 < TEAM_TN) ? cmax + 1 - c0 : TEAM_TN;
+                    solve_pass<TEAM_TN>(c0, nc, nsc);
+                }
+            }
+        }
+    }
 
     /// cvLsSetup + cvLsLinSys + the inversion; the Jacobian is evaluated at w.yj
     PB_HD int lsetup() {
@@ -1045,7 +1288,17 @@ struct BdfTeam {
             const bool ok = net::jac_values(T, tm, w.yj, w.p, w.Jsaved, true);
             if (tm.any(!ok)) ret = 1;  // AMICI's fJ returns checkFinite(J): recoverable
         }
-        if (ret == 0) ret = invert_newton_matrix();
+        if (ret == 0) {
+            if (SP.enabled && use_sparse) {
+                ret = factor_sparse();
+                if (ret == 2) {  // weak diagonal pivot: this matrix by the dense path with partial pivoting
+                    nfallback++;
+                    ret = invert_newton_matrix();
+                }
+            } else {
+                ret = invert_newton_matrix();
+            }
+        }
         if (jbad) { nje++; nstlj = nst; }
         jcur = jbad;
         nsetups++;
@@ -1058,6 +1311,9 @@ struct BdfTeam {
     template <int TN>
     PB_HD void solve_pass(int c0, int nc, double nsc) {
         constexpr int KC = (TEAM_RBUF / TN) < 64 ? (TEAM_RBUF / TN) : ((TN == 1) ? TEAM_RBUF : 64);
+        const int ldb = this->nx;
+        const int nx = dn;  // (shadows the member: the dense dimension)
+        const int* const omap = lin_sparse ? SP.ord + SP.n1 : nullptr;
         for (int row0 = 0; row0 < nx; row0 += tm.size()) {
             const int i = row0 + tm.tid();
             const bool active = i < nx;
@@ -1069,7 +1325,7 @@ struct BdfTeam {
                 tm.sync();
                 PT_FOR(e, 0, kc * TN) {
                     const int kk = e / TN, cc = e - kk * TN;
-                    rbuf()[e] = (cc < nc) ? w.b[w.perm[k0 + kk] + (size_t)(c0 + cc) * nx] : 0.0;
+                    rbuf()[e] = (cc < nc) ? w.b[w.gidx[k0 + kk] + (size_t)(c0 + cc) * ldb] : 0.0;
                 }
                 tm.sync();
                 if (active) {
@@ -1101,7 +1357,7 @@ struct BdfTeam {
             if (active) {
                 PB_UNROLL
                 for (int cc = 0; cc < TN; ++cc)
-                    if (cc < nc) w.scr[i + (size_t)(c0 + cc) * nx] = nsc * acc[cc];
+                    if (cc < nc) w.scr[(omap ? omap[i] : i) + (size_t)(c0 + cc) * ldb] = nsc * acc[cc];
             }
         }
     }
@@ -1111,34 +1367,8 @@ struct BdfTeam {
     PB_HD double newton_update(int cmin, int cmax) {
         const double nsc = (gamrat != 1.0) ? -2.0 / (1.0 + gamrat) : -1.0;
         const long long t_s0 = now();
-#if defined(__CUDA_ARCH__)
-        const bool rows_path = nx <= tm.size();
-#else
-        const bool rows_path = false;
-#endif
-        if (cmin == cmax) {
-#if defined(__CUDA_ARCH__)
-            if (rows_path) solve_pass_rows<1>(cmin, 1, nsc);
-            else
-#endif
-                solve_pass<1>(cmin, 1, nsc);
-        } else {
-#if defined(__CUDA_ARCH__)
-            if (rows_path) {
-                for (int c0 = cmin; c0 <= cmax; c0 += 56) {
-                    const int nc = (cmax + 1 - c0 < 56) ? cmax + 1 - c0 : 56;
-                    if (nc > 24) solve_pass_mma<7>(c0, nc, nsc);
-                    else solve_pass_mma<3>(c0, nc, nsc);
-                }
-            } else
-#endif
-            {
-                for (int c0 = cmin; c0 <= cmax; c0 += TEAM_TN) {
-                    const int nc = (cmax + 1 - c0 < TEAM_TN) ? cmax + 1 - c0 : TEAM_TN;
-                    solve_pass<TEAM_TN>(c0, nc, nsc);
-                }
-            }
-        }
+        if (lin_sparse) solve_sparse(cmin, cmax, nsc);
+        else solve_dense(cmin, cmax, nsc);
         tm.sync();
         cyc_solve += now() - t_s0;
         {
@@ -1992,11 +2222,14 @@ struct BdfTeam {
         jcur = jcurNLS = jcurNLSS = false;
         tstopset = false; tstop = 0.0;
         nfe = nsetups = nje = nni = nniS = nfSe = netf = netfS = ncfn = ncfnS = nor = qsum = 0;
+        nfallback = 0;
+        dn = nx;
+        lin_sparse = false;
         llh_ = 0.0;
         it_ = 0;
         sim_status_ = SIM_SUCCESS;
         fail_ = ret_ = 0;
-        cyc_panel = cyc_update = cyc_solve = cyc_rhs = 0;
+        cyc_panel = cyc_update = cyc_solve = cyc_rhs = cyc_spfactor = cyc_sptri = 0;
         tm.sync();
     }
 
@@ -2006,7 +2239,7 @@ struct BdfTeam {
         const int ny = T.ny;
         for (it_ = 0; it_ < io_.nt; ++it_) {
             tout_ = io_.t[it_];
-            if (isinf(tout_)) break;  // post-equilibration: out of scope
+            if (!PB_FINITE(tout_)) return finish(SIM_ERROR);  // t = inf (post-equilibration) is not implemented: an error, never a silently dropped point
             bool integrate = (tout_ > opt.t0) && (tn < tout_);
             if (integrate) {  // is_next_t_too_close
                 const double tdiff = tout_ - tn;
@@ -2071,6 +2304,9 @@ struct BdfTeam {
         s[STAT_TRIALS] = trials; s[STAT_QSUM] = qsum;
         s[14] = ((cyc_panel >> 10) << 32) | ((cyc_update >> 10) & 0xffffffffll);
         s[15] = ((cyc_solve >> 10) << 32) | ((cyc_rhs >> 10) & 0xffffffffll);
+        s[STAT_NFALLBACK] = nfallback;
+        s[STAT_CYC_SPARSE] = ((cyc_spfactor >> 10) << 32) | ((cyc_sptri >> 10) & 0xffffffffll);
+        s[18] = s[19] = 0;
     }
 #undef PT_FOR
 #undef PT_FOR_ELEMS

@@ -46,6 +46,7 @@ struct HierDevice {
     std::vector<int> pscale_opt;
     std::vector<int> inner_sorted;  // all analytical parameter indices, ascending
     int64_t* d_t_offsets = nullptr;
+    std::vector<int64_t> t_offsets;  // host copy
     int64_t nt_total = 0;
     double* d_partial = nullptr;    // nllh partial sums
     int n_partial = 0;
@@ -57,18 +58,18 @@ template <int KIND, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 hier_sums_kernel(const int64_t* __restrict__ ptr, const int* __restrict__ cond, const int* __restrict__ obs,
                  const int64_t* __restrict__ t_offsets, int ny, const double* __restrict__ mes,
-                 const double* __restrict__ sim, double* __restrict__ sums, int partitioned) {
+                 const double* __restrict__ sim, double* __restrict__ sums, int c_lo, int c_hi) {
     __shared__ double r0[THREADS], r1[THREADS], r2[THREADS];
     const int p = blockIdx.x, tid = threadIdx.x;
     double num = 0.0, den = 0.0, mx = 0.0;
     for (int64_t e = ptr[p] + tid; e < ptr[p + 1]; e += THREADS) {
         const int c = cond[e], o = obs[e];
+        if (c < c_lo || c >= c_hi) continue;  // a condition another rank simulates (ownership by partition bounds)
         const int64_t lo = t_offsets[c], hi = t_offsets[c + 1];
         for (int64_t it = lo; it < hi; ++it) {
             const double m = mes[it * ny + o];
             if (isnan(m)) continue;
             double s = sim[it * ny + o];
-            if (partitioned && isnan(s)) continue;  // a condition another rank simulates
             if (KIND == HIER_SCALING) {
                 if (s < 0 && s > -1e-18) s = 0.0;
                 num += s * m;
@@ -121,11 +122,11 @@ hier_apply_kernel(const int64_t* __restrict__ ptr, const int* __restrict__ cond,
     }
 }
 
-/// computeNegLogLikelihood over the data points of conditions [c_lo, c_hi): per-block partials
+/// computeNegLogLikelihood over the data points [first, last) (those of this rank's conditions): per-block partials
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 hier_nllh_kernel(int64_t first, int64_t last, const double* __restrict__ mes, const double* __restrict__ sim,
-                 const double* __restrict__ sig, double* __restrict__ partial, int partitioned) {
+                 const double* __restrict__ sig, double* __restrict__ partial) {
     __shared__ double r0[THREADS];
     const int tid = threadIdx.x;
     double acc = 0.0;
@@ -133,7 +134,6 @@ hier_nllh_kernel(int64_t first, int64_t last, const double* __restrict__ mes, co
         const double m = mes[i];
         if (isnan(m)) continue;
         const double s = sim[i];
-        if (partitioned && isnan(s)) continue;  // a condition another rank simulates
         const double s2 = sig[i] * sig[i];
         if (isnan(s) || isnan(s2) || s2 < 0.0) {
             acc = NAN;
@@ -208,6 +208,7 @@ inline HierDevice* hier_create(const pb200_hier_desc& hd, int C, int n_opt, int 
     h->C = C; h->n_opt = n_opt; h->ny = ny;
     h->pscale_opt.assign(pscale_opt, pscale_opt + n_opt);
     h->nt_total = t_offsets[C];
+    h->t_offsets.assign(t_offsets, t_offsets + C + 1);
     bool ok = hier_build_kind(h->scaling, hd.scaling_idx, hd.n_scaling, hd.scaling_map, hd.n_scaling_rows, C, ny, n_opt, err) &&
               hier_build_kind(h->offset, hd.offset_idx, hd.n_offset, hd.offset_map, hd.n_offset_rows, C, ny, n_opt, err) &&
               hier_build_kind(h->sigma, hd.sigma_idx, hd.n_sigma, hd.sigma_map, hd.n_sigma_rows, C, ny, n_opt, err);
@@ -277,11 +278,13 @@ inline void hier_filter(const HierDevice* h, const double* full, double* outer) 
 /// Steps 3-4 of HierarchicalOptimizationWrapper::evaluate (:184-238).  d_y (pass-1 outputs)
 /// is scaled/offset in place; d_sig receives the analytic sigmas when the analytic nllh is
 /// requested.  inner_scaled: scalings, offsets, sigmas in the optimiser's parameter scale.
-/// reduce(buf, n, op): element-wise all-reduce over the ranks of a partitioned evaluation (null: one rank)
+/// reduce(buf, n, op): element-wise all-reduce over the ranks of a partitioned evaluation (null: one rank);
+/// [c_lo, c_hi): the conditions this rank simulated (the others' outputs are not touched: a genuine NaN
+/// output of an owned condition propagates, as in the reference)
 inline bool hier_compute(HierDevice* h, const double* d_mes, double* d_y, double* d_sig, cudaStream_t stream,
                          bool want_nllh, std::vector<double>* inner_scaled, double* nllh, std::string* err,
-                         const std::function<void(double*, int, int)>& reduce = nullptr) {
-    const int partitioned = reduce ? 1 : 0;
+                         const std::function<void(double*, int, int)>& reduce = nullptr, int c_lo = 0, int c_hi = -1) {
+    if (c_hi < 0) c_hi = h->C;
     // sums of one kind over all ranks: entries 0,1 are sums, entry 2 a maximum
     auto reduce_kind = [&](std::vector<double>& host, int n) {
         if (!reduce || n == 0) return;
@@ -310,8 +313,8 @@ inline bool hier_compute(HierDevice* h, const double* d_mes, double* d_y, double
     };
     HierKind &S = h->scaling, &O = h->offset, &G = h->sigma;
     std::vector<double> hs, ho, hg;
-    if (S.n) hier_sums_kernel<HIER_SCALING, T><<<S.n, T, 0, stream>>>(S.d_ptr, S.d_cond, S.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, S.d_sums, partitioned);
-    if (O.n) hier_sums_kernel<HIER_OFFSET, T><<<O.n, T, 0, stream>>>(O.d_ptr, O.d_cond, O.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, O.d_sums, partitioned);
+    if (S.n) hier_sums_kernel<HIER_SCALING, T><<<S.n, T, 0, stream>>>(S.d_ptr, S.d_cond, S.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, S.d_sums, c_lo, c_hi);
+    if (O.n) hier_sums_kernel<HIER_OFFSET, T><<<O.n, T, 0, stream>>>(O.d_ptr, O.d_cond, O.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, O.d_sums, c_lo, c_hi);
     if (!check(cudaGetLastError(), "hier_sums_kernel") || !fetch(S, hs) || !fetch(O, ho)) return false;
     reduce_kind(hs, S.n);
     reduce_kind(ho, O.n);
@@ -335,7 +338,7 @@ inline bool hier_compute(HierDevice* h, const double* d_mes, double* d_y, double
     for (int i = 0; i < O.n; ++i) lin[i] = unscale(offs[i], h->pscale_opt[O.idx[i]]);
     if (!push(O, lin)) return false;
     if (O.n) hier_apply_kernel<1, T><<<O.n, T, 0, stream>>>(O.d_ptr, O.d_cond, O.d_obs, h->d_t_offsets, h->ny, O.d_vals, d_y);
-    if (G.n) hier_sums_kernel<HIER_SIGMA, T><<<G.n, T, 0, stream>>>(G.d_ptr, G.d_cond, G.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, G.d_sums, partitioned);
+    if (G.n) hier_sums_kernel<HIER_SIGMA, T><<<G.n, T, 0, stream>>>(G.d_ptr, G.d_cond, G.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, G.d_sums, c_lo, c_hi);
     if (!check(cudaGetLastError(), "hier kernels") || !fetch(G, hg)) return false;
     reduce_kind(hg, G.n);
     for (int i = 0; i < G.n; ++i) {
@@ -353,7 +356,7 @@ inline bool hier_compute(HierDevice* h, const double* d_mes, double* d_y, double
         for (int i = 0; i < G.n; ++i) lin[i] = unscale(sig[i], h->pscale_opt[G.idx[i]]);
         if (!push(G, lin)) return false;
         if (G.n) hier_apply_kernel<2, T><<<G.n, T, 0, stream>>>(G.d_ptr, G.d_cond, G.d_obs, h->d_t_offsets, h->ny, G.d_vals, d_sig);
-        hier_nllh_kernel<T><<<h->n_partial, T, 0, stream>>>(0, h->nt_total * h->ny, d_mes, d_y, d_sig, h->d_partial, partitioned);
+        hier_nllh_kernel<T><<<h->n_partial, T, 0, stream>>>(h->t_offsets[c_lo] * h->ny, h->t_offsets[c_hi] * h->ny, d_mes, d_y, d_sig, h->d_partial);
         std::vector<double> part(h->n_partial);
         if (!check(cudaGetLastError(), "hier_nllh_kernel") ||
             !check(cudaMemcpyAsync(part.data(), h->d_partial, sizeof(double) * h->n_partial, cudaMemcpyDeviceToHost, stream), "memcpy") ||

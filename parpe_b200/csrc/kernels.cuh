@@ -38,6 +38,8 @@ struct KernelArgs {
     const double* ov_unscaled;     // [C*np] same, unscaled on the host at create time
     const int* plist;              // [C*np] sensitivity parameter list per condition
     const int* nplist;             // [C]
+    const int* inv_j;              // [C*np] optimisation indices a condition maps to, ascending (padding: INT_MAX)
+    const int* inv_i;              // [C*np] the model parameter of each entry of inv_j (ascending within equal j)
     // --- per evaluation ---
     const double* theta_tab;       // [n_opt*3*2]: for optimisation parameter j and simulation
                                    // scale s: (value in simulation scale, unscaled value)
@@ -57,6 +59,10 @@ struct KernelArgs {
     // --- options ---
     int sync_period;               // CTA barrier every this many step attempts (>= 1)
     int stage_sync;                // CTA barrier (instead of a warp barrier) between the stages of an attempt
+    int ctas_per_sm_cap;           // experiments (pb200_set_option): 0 = occupancy limit
+    int max_groups;                // lane groups of a CTA that pull work (launch geometry: few conditions are
+                                   // spread over all SMs instead of filling the first CTAs)
+    int linsol;                    // large-model path: 0 automatic, 1 dense inverse, 2 sparse LU + dense Schur block
     SolverOptions opt;
     int num_trials;
     double relaxation_factor;
@@ -89,7 +95,16 @@ __global__ void __launch_bounds__(THREADS, PB_MIN_BLOCKS_FOR(THREADS, G)) simula
     bdf.opt = a.opt;
     const int lane = grp.lane();
 
-    bool active = false, done = false;
+    // Launch geometry: with fewer conditions than lane groups on the GPU only the first a.max_groups
+    // groups of every CTA pull work, numbered round-robin over the warps (so that the busy groups are
+    // spread over the SM's four schedulers): the conditions cover all SMs instead of filling the first CTAs.
+    bool active = false;
+    bool done;
+    {
+        constexpr int GPW = 32 / G;  // groups per warp
+        const int g = threadIdx.x / G, wv = g / GPW, slot = g % GPW;
+        done = (slot * (THREADS / 32) + wv) >= a.max_groups;
+    }
     int since_sync = 0;
     int r = 0, trial = 1;
     size_t cp = 0;
@@ -221,13 +236,22 @@ __global__ void __launch_bounds__(THREADS) reduce_kernel(const KernelArgs a, dou
             acc2 += (a.status[r] != 0) ? 1.0 : 0.0;
         }
     } else {
+        // gradient entry j: the contributions of every position whose condition maps a model
+        // parameter to j, found by binary search in the condition's sorted inverse list (O(log np) per
+        // position instead of np; summation order as before: positions by stride, model parameters ascending)
         const int j = blockIdx.x - 1;
         if (a.want_grad) {
             for (int r = tid; r < a.n; r += THREADS) {
-                const size_t cp = (size_t)a.idx[r] * a.np;
+                const int* __restrict__ lj = a.inv_j + (size_t)a.idx[r] * a.np;
+                const int* __restrict__ li = a.inv_i + (size_t)a.idx[r] * a.np;
                 const size_t rp = (size_t)r * a.np;
-                for (int i = 0; i < a.np; ++i)
-                    if (a.mapping[cp + i] == j) acc += a.gcontrib[rp + i];
+                int lo = 0, hi = a.np;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (lj[mid] < j) lo = mid + 1;
+                    else hi = mid;
+                }
+                for (; lo < a.np && lj[lo] == j; ++lo) acc += a.gcontrib[rp + li[lo]];
             }
         }
     }
@@ -251,6 +275,10 @@ __global__ void __launch_bounds__(THREADS) reduce_kernel(const KernelArgs a, dou
     }
 }
 
+inline void launch_reduce(const KernelArgs& a, double* d_out, cudaStream_t stream) {
+    reduce_kernel<256><<<1 + a.n_opt, 256, 0, stream>>>(a, d_out);
+}
+
 // ---- per-model launch table ------------------------------------------------------
 struct ModelOps {
     const char* name;
@@ -264,6 +292,8 @@ struct ModelOps {
     // teams' HBM workspace); null for the small-model kernels
     void* (*create_state)(int sm_count, std::string* err);
     void (*destroy_state)(void* state);
+    // large-model path: description of the linear solver chosen at create (null otherwise)
+    int (*linsol_info)(void* state, int64_t* out, int n);
 };
 
 void register_model(const ModelOps& ops);
@@ -276,23 +306,26 @@ int launch_one(const KernelArgs& a, int sm_count, cudaStream_t stream, int* grid
     auto kern = simulate_kernel<M, G, THREADS, CTA_SYNC>;
     const int groups_per_block = THREADS / G;
     const size_t smem = sizeof(GroupShared<M>) * groups_per_block;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set && smem > 0) {
+    // the attribute is per device (context): set before every launch (cheap), not cached per process
+    if (smem > 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
     }
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) per_sm = 1;
-    static const int cap = std::getenv("PB200_CTAS_PER_SM") ? std::atoi(std::getenv("PB200_CTAS_PER_SM")) : 0;  // experiments
-    if (cap > 0 && per_sm > cap) per_sm = cap;
+    if (a.ctas_per_sm_cap > 0 && per_sm > a.ctas_per_sm_cap) per_sm = a.ctas_per_sm_cap;
     int grid = sm_count * per_sm;  // persistent: one resident wave, work queue inside
-    const int needed = (a.n + groups_per_block - 1) / groups_per_block;
-    if (grid > needed) grid = needed;
+    if (grid > a.n) grid = a.n;
     if (grid < 1) grid = 1;
-    kern<<<grid, THREADS, smem, stream>>>(a);
+    // n < (lane groups of a resident wave): spread the conditions over all SMs -- ceil(n / grid) groups
+    // per CTA pull work (the time of a step attempt is per SM and nearly independent of the number of
+    // resident conditions: DESIGN.md 3.1)
+    KernelArgs b = a;
+    b.max_groups = (a.n + grid - 1) / grid;
+    if (b.max_groups > groups_per_block) b.max_groups = groups_per_block;
+    kern<<<grid, THREADS, smem, stream>>>(b);
     if (grid_used) *grid_used = grid;
     if (block_used) *block_used = THREADS;
     return (int)cudaGetLastError();
@@ -356,6 +389,7 @@ ModelOps make_ops() {
     o.launch = &launch_model<M>;
     o.create_state = nullptr;
     o.destroy_state = nullptr;
+    o.linsol_info = nullptr;
     return o;
 }
 

@@ -22,6 +22,7 @@
 #include "../../include/parpe_b200.h"
 #include "hier_kernels.cuh"
 #include "kernels.cuh"
+#include "nccl_dyn.h"
 
 namespace pb200 {
 
@@ -124,7 +125,7 @@ struct pb200_handle {
     // resident tables
     DevBuf<int64_t> d_t_offsets;
     DevBuf<double> d_t, d_my, d_sd, d_k, d_ov_scaled, d_ov_unscaled;
-    DevBuf<int> d_mapping, d_pscale_sim, d_pscale_opt, d_plist, d_nplist;
+    DevBuf<int> d_mapping, d_pscale_sim, d_pscale_opt, d_plist, d_nplist, d_inv_j, d_inv_i;
     // per-evaluation buffers
     int cap = 0;
     DevBuf<double> d_llh, d_sllh, d_gcontrib, d_theta_tab, d_out, d_yout, d_sout;
@@ -148,9 +149,17 @@ struct pb200_handle {
     bool staged_pending = false;
     // hierarchical
     HierDevice* hier = nullptr;
-    // collective hook of partitioned hierarchical evaluations (pb200_set_allreduce)
+    // collectives of partitioned evaluations: a host hook (pb200_set_allreduce: the caller's transport,
+    // e.g. MPI_Allreduce) or an in-library NCCL communicator (pb200_nccl_init)
     pb200_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
+    NcclApi::Comm nccl = nullptr;
+    DevBuf<double> d_coll;  // staging buffer of the small NCCL reductions of the hierarchical passes
+    // tuning options (pb200_set_option; never read from the environment)
+    int opt_variant = 2, opt_ctas_per_sm = 0, opt_sync_period = 1, opt_stage_sync = 0, opt_partial_sums = 0;
+    int opt_linsol = 0, opt_order_refresh = 16;
+    int evals_since_order = 0;
+    int64_t last_h2d = 0, last_d2h = 0;
     // large-model path: device tables + workspace (ModelOps::create_state)
     void* model_state = nullptr;
 };
@@ -224,22 +233,28 @@ static int enqueue_evaluation(pb200_handle* h, const double* theta, const int* i
     a.stats = h->d_stats.p;
     a.y_out = d_yout;
     a.sigmay_out = d_sout;
-    {
-        static const int sp = std::getenv("PB200_SYNC_PERIOD") ? std::atoi(std::getenv("PB200_SYNC_PERIOD")) : 1;  // experiments
-        a.sync_period = sp > 0 ? sp : 1;
-        static const int ss = std::getenv("PB200_STAGE_SYNC") ? std::atoi(std::getenv("PB200_STAGE_SYNC")) : 0;
-        a.stage_sync = ss;
-    }
+    a.sync_period = h->opt_sync_period > 0 ? h->opt_sync_period : 1;
+    a.stage_sync = h->opt_stage_sync;
+    a.ctas_per_sm_cap = h->opt_ctas_per_sm;
+    a.linsol = h->opt_linsol;
     PB_CUDA(cudaEventRecord(h->ev_start, stream));
     if (n > 0) {
-        static const int variant = std::getenv("PB200_KERNEL_VARIANT") ? std::atoi(std::getenv("PB200_KERNEL_VARIANT")) : 2;
-        int e = h->ops->launch(a, h->lanes, variant, h->sm_count, stream, &h->last_lanes, &h->last_grid, &h->last_block,
-                               h->model_state);
+        int e = h->ops->launch(a, h->lanes, h->opt_variant, h->sm_count, stream, &h->last_lanes, &h->last_grid,
+                               &h->last_block, h->model_state);
         if (e != 0) return fail(PB200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)e));
     }
-    reduce_kernel<256><<<1 + h->n_opt, 256, 0, stream>>>(a, d_out);
+    launch_reduce(a, d_out, stream);
     PB_CUDA(cudaGetLastError());
+    // A6 over all ranks: the ONE all-reduce of (nllh, #errors, gradient) that replaces the master's
+    // summation of the workers' results (multiConditionProblem.cpp:738-748,775-824)
+    if (h->nccl) {
+        NcclApi& nc = NcclApi::get();
+        const int rc = nc.AllReduce(d_out, d_out, (size_t)(2 + h->n_opt), NcclApi::Float64, NcclApi::Sum, h->nccl, stream);
+        if (rc != NcclApi::Success) return fail(PB200_ERR_CUDA, std::string("ncclAllReduce: ") + nc.GetErrorString(rc));
+    }
     PB_CUDA(cudaEventRecord(h->ev_stop, stream));
+    h->last_h2d = (int64_t)sizeof(double) * 6 * h->n_opt + (same_idx ? 0 : (int64_t)sizeof(int) * n);
+    h->last_d2h = 0;
     h->last_n = n;
     h->last_want_grad = want_grad;
     return 0;
@@ -294,6 +309,15 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
     const int C = d->n_conditions;
     for (int c = 0; c < C; ++c) {
         if (d->t_offsets[c + 1] < d->t_offsets[c]) return fail(PB200_ERR_ARG, "t_offsets not monotone");
+        // Output times: finite and non-decreasing (amici::ExpData requires sorted time points).  t = inf
+        // (post-equilibration, steadystateproblem.cpp) is not implemented: rejected here rather than
+        // silently dropped from the objective.
+        for (int64_t it = d->t_offsets[c]; it < d->t_offsets[c + 1]; ++it) {
+            if (!std::isfinite(d->t[it]))
+                return fail(PB200_ERR_ARG, "non-finite output time (t = inf / post-equilibration is not supported)");
+            if (it > d->t_offsets[c] && d->t[it] < d->t[it - 1])
+                return fail(PB200_ERR_ARG, "output times of a condition must be non-decreasing");
+        }
         for (int i = 0; i < d->np; ++i) {
             const int j = d->mapping[(size_t)c * d->np + i];
             if (j >= d->n_opt) return fail(PB200_ERR_ARG, "mapping entry out of range");
@@ -317,7 +341,7 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
     h->nk = d->nk;
     h->ny = d->ny;
     h->lanes = d->lanes_per_condition;
-    h->reorder = std::getenv("PB200_REORDER") ? std::atoi(std::getenv("PB200_REORDER")) : 1;
+    h->reorder = 1;
     h->pscale_opt.assign(d->pscale_opt, d->pscale_opt + d->n_opt);
     h->t_offsets.assign(d->t_offsets, d->t_offsets + C + 1);
     h->nt_total = C > 0 ? d->t_offsets[C] : 0;
@@ -340,6 +364,26 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
     PB_CUDA(h->d_pscale_opt.upload(d->pscale_opt, d->n_opt));
     PB_CUDA(h->d_plist.upload(plist.data(), plist.size()));
     PB_CUDA(h->d_nplist.upload(nplist.data(), nplist.size()));
+    {
+        // per condition: (optimisation index, model parameter) pairs sorted by optimisation index -- the
+        // gradient reduction looks a gradient entry up by binary search instead of scanning the mapping
+        std::vector<int> inv_j((size_t)C * d->np, std::numeric_limits<int>::max()), inv_i((size_t)C * d->np, 0);
+        std::vector<std::pair<int, int>> tmp;
+        for (int c = 0; c < C; ++c) {
+            tmp.clear();
+            for (int i = 0; i < d->np; ++i) {
+                const int j = d->mapping[(size_t)c * d->np + i];
+                if (j >= 0) tmp.emplace_back(j, i);
+            }
+            std::sort(tmp.begin(), tmp.end());
+            for (size_t e = 0; e < tmp.size(); ++e) {
+                inv_j[(size_t)c * d->np + e] = tmp[e].first;
+                inv_i[(size_t)c * d->np + e] = tmp[e].second;
+            }
+        }
+        PB_CUDA(h->d_inv_j.upload(inv_j.data(), inv_j.size()));
+        PB_CUDA(h->d_inv_i.upload(inv_i.data(), inv_i.size()));
+    }
     if (d->overrides) {
         std::vector<double> ovu((size_t)C * d->np);
         for (size_t i = 0; i < ovu.size(); ++i) ovu[i] = unscale(d->overrides[i], d->pscale_sim[i]);
@@ -374,6 +418,8 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
     a.ov_unscaled = h->d_ov_unscaled.p;
     a.plist = h->d_plist.p;
     a.nplist = h->d_nplist.p;
+    a.inv_j = h->d_inv_j.p;
+    a.inv_i = h->d_inv_i.p;
     a.opt.t0 = d->t0;
     a.opt.rtol = d->rtol;
     a.opt.atol = d->atol;
@@ -398,6 +444,7 @@ void pb200_destroy(pb200_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     hier_destroy(h->hier);
+    if (h->nccl) NcclApi::get().CommDestroy(h->nccl);
     if (h->model_state && h->ops && h->ops->destroy_state) h->ops->destroy_state(h->model_state);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_stop) cudaEventDestroy(h->ev_stop);
@@ -421,20 +468,106 @@ int pb200_set_allreduce(pb200_handle* h, pb200_allreduce_fn fn, void* user) {
     return 0;
 }
 
+int pb200_set_option(pb200_handle* h, int key, int value) {
+    if (!h) return fail(PB200_ERR_ARG, "null handle");
+    switch (key) {
+    case PB200_OPT_REORDER: h->reorder = value != 0; h->order_valid = false; break;
+    case PB200_OPT_ORDER_REFRESH: h->opt_order_refresh = value > 0 ? value : 1; break;
+    case PB200_OPT_KERNEL_VARIANT: h->opt_variant = value; break;
+    case PB200_OPT_CTAS_PER_SM: h->opt_ctas_per_sm = value; break;
+    case PB200_OPT_SYNC_PERIOD: h->opt_sync_period = value; break;
+    case PB200_OPT_STAGE_SYNC: h->opt_stage_sync = value; break;
+    case PB200_OPT_PARTIAL_SUMS: h->opt_partial_sums = value != 0; break;
+    case PB200_OPT_LINSOL:
+        if (value < 0 || value > 2) return fail(PB200_ERR_ARG, "linear solver: 0 automatic, 1 dense, 2 sparse");
+        h->opt_linsol = value;
+        break;
+    default: return fail(PB200_ERR_ARG, "unknown option");
+    }
+    return 0;
+}
+
+int pb200_nccl_unique_id(char* id128) {
+    if (!id128) return fail(PB200_ERR_ARG, "null argument");
+    NcclApi& nc = NcclApi::get();
+    if (!nc.ok()) return fail(PB200_ERR_CUDA, nc.error);
+    NcclApi::UniqueId id;
+    const int rc = nc.GetUniqueId(&id);
+    if (rc != NcclApi::Success) return fail(PB200_ERR_CUDA, std::string("ncclGetUniqueId: ") + nc.GetErrorString(rc));
+    std::memcpy(id128, id.internal, 128);
+    return 0;
+}
+
+int pb200_nccl_init(pb200_handle* h, const char* id128, int rank, int world) {
+    if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return fail(PB200_ERR_ARG, "bad argument");
+    NcclApi& nc = NcclApi::get();
+    if (!nc.ok()) return fail(PB200_ERR_CUDA, nc.error);
+    PB_CUDA(cudaSetDevice(h->device));
+    if (h->nccl) {
+        nc.CommDestroy(h->nccl);
+        h->nccl = nullptr;
+    }
+    NcclApi::UniqueId id;
+    std::memcpy(id.internal, id128, 128);
+    const int rc = nc.CommInitRank(&h->nccl, world, id, rank);
+    if (rc != NcclApi::Success) {
+        h->nccl = nullptr;
+        return fail(PB200_ERR_CUDA, std::string("ncclCommInitRank: ") + nc.GetErrorString(rc));
+    }
+    PB_CUDA(h->d_coll.alloc(256));
+    return pb200_set_partition(h, rank, world);
+}
+
+/// all-reduce of a small HOST buffer over the ranks of a partitioned evaluation: NCCL through a device
+/// staging buffer if a communicator is set, otherwise the caller's hook
+static int collective_host(pb200_handle* h, double* buf, int n, int op) {
+    if (h->nccl) {
+        NcclApi& nc = NcclApi::get();
+        if ((size_t)n > h->d_coll.n) PB_CUDA(h->d_coll.alloc((size_t)n));
+        PB_CUDA(cudaMemcpyAsync(h->d_coll.p, buf, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+        const int rc = nc.AllReduce(h->d_coll.p, h->d_coll.p, (size_t)n, NcclApi::Float64,
+                                    op == PB200_REDUCE_MAX ? NcclApi::Max : NcclApi::Sum, h->nccl, h->stream);
+        if (rc != NcclApi::Success) return fail(PB200_ERR_CUDA, std::string("ncclAllReduce: ") + nc.GetErrorString(rc));
+        PB_CUDA(cudaMemcpyAsync(buf, h->d_coll.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+        PB_CUDA(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    if (h->allreduce) {
+        h->allreduce(h->allreduce_user, buf, n, op);
+        return 0;
+    }
+    return fail(PB200_ERR_ARG, "no collective set");
+}
+
 int pb200_evaluate(pb200_handle* h, const double* theta, int n_opt, const int* idx, int n_idx, double* fval,
                    double* grad, double* seconds) {
     if (!h || !theta || !fval || (n_idx > 0 && !idx)) return fail(PB200_ERR_ARG, "null argument");
     if (n_opt != h->n_opt) return fail(PB200_ERR_ARG, "parameter vector size does not match numParameters");
+    // A partitioned handle returns the GLOBAL fval / gradient / status (the reference master sums all
+    // workers' results before evaluate returns: multiConditionProblem.cpp:738-748,775-824); rank-local
+    // partial sums only on explicit request.
+    if (h->world > 1 && !h->nccl && !h->allreduce && !h->opt_partial_sums)
+        return fail(PB200_ERR_ARG, "partitioned evaluate needs a collective: pb200_nccl_init or pb200_set_allreduce "
+                                   "(or PB200_OPT_PARTIAL_SUMS for rank-local sums)");
     const int want_grad = grad != nullptr;
     if (int rc = enqueue_evaluation(h, theta, idx, n_idx, want_grad, h->d_out.p, nullptr, nullptr, h->stream)) return rc;
     PB_CUDA(cudaMemcpyAsync(h->h_out.p, h->d_out.p, sizeof(double) * (2 + h->n_opt), cudaMemcpyDeviceToHost, h->stream));
     PB_CUDA(cudaStreamSynchronize(h->stream));
+    h->last_d2h += (int64_t)sizeof(double) * (2 + h->n_opt);
     if (seconds) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop);
         *seconds = ms * 1e-3;
     }
-    if (h->reorder && h->last_n > 1) {
+    if (h->world > 1 && !h->nccl && h->allreduce)  // host transport; NCCL has reduced d_out on the stream already
+        h->allreduce(h->allreduce_user, h->h_out.p, 2 + h->n_opt, PB200_REDUCE_SUM);
+    // the processing order is refreshed when the index list changed and every opt_order_refresh
+    // evaluations after that (the ranking of the conditions by cost changes slowly with theta)
+    const bool refresh = !h->order_valid || ++h->evals_since_order >= h->opt_order_refresh;
+    if (h->reorder && h->last_n > 1 && refresh) {
+        h->evals_since_order = 0;
+        h->last_d2h += (int64_t)sizeof(int64_t) * h->last_n;
+        h->last_h2d += (int64_t)sizeof(int) * h->last_n;
         // processing order of the next evaluation of the same index list: costliest conditions first
         // (they also sit next to conditions of similar cost in a warp / CTA)
         const int n = h->last_n;
@@ -469,6 +602,19 @@ int pb200_evaluate_device(pb200_handle* h, const double* theta, int n_opt, const
     if (!h || !theta || !d_out || (n_idx > 0 && !idx)) return fail(PB200_ERR_ARG, "null argument");
     if (n_opt != h->n_opt) return fail(PB200_ERR_ARG, "parameter vector size does not match numParameters");
     return enqueue_evaluation(h, theta, idx, n_idx, want_grad, d_out, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int pb200_linsol_info(pb200_handle* h, int64_t* out, int n) {
+    if (!h || !out) return fail(PB200_ERR_ARG, "null argument");
+    if (!h->ops->linsol_info) return 0;
+    return h->ops->linsol_info(h->model_state, out, n);
+}
+
+int pb200_last_transfer_bytes(pb200_handle* h, int64_t* h2d, int64_t* d2h) {
+    if (!h) return fail(PB200_ERR_ARG, "null handle");
+    if (h2d) *h2d = h->last_h2d;
+    if (d2h) *d2h = h->last_d2h;
+    return 0;
 }
 
 int pb200_last_launch(pb200_handle* h, int* lanes, int* grid, int* block, double* seconds) {
@@ -553,15 +699,14 @@ int pb200_hier_evaluate(pb200_handle* h, const double* theta_outer, int n_outer,
     const int n_inner = hier_num_inner(h->hier);
     // HierarchicalOptimizationWrapper::evaluate throws on size mismatch (hierarchicalOptimization.cpp:155-160)
     if (n_outer != h->n_opt - n_inner) return fail(PB200_ERR_ARG, "reduced parameter vector size does not match numParameters");
-    if (h->world > 1 && !h->allreduce)
-        return fail(PB200_ERR_ARG, "partitioned hierarchical evaluation needs pb200_set_allreduce");
+    if (h->world > 1 && !h->allreduce && !h->nccl)
+        return fail(PB200_ERR_ARG, "partitioned hierarchical evaluation needs pb200_nccl_init or pb200_set_allreduce");
     PB_CUDA(cudaSetDevice(h->device));
     std::function<void(double*, int, int)> reduce;
-    if (h->world > 1) {
-        pb200_allreduce_fn fn = h->allreduce;
-        void* user = h->allreduce_user;
-        reduce = [fn, user](double* buf, int n, int op) { fn(user, buf, n, op); };
-    }
+    int coll_rc = 0;
+    if (h->world > 1) reduce = [h, &coll_rc](double* buf, int n, int op) { if (int rc = collective_host(h, buf, n, op)) coll_rc = rc; };
+    int c_lo = 0, c_hi = h->C;
+    pb200_partition_bounds(h->C, h->rank, h->world, &c_lo, &c_hi);
     double t_total = 0.0;
     // pass 1: defaults for the inner parameters (scaling 1, offset 0, sigma 1 in linear scale)
     std::vector<double> full(h->n_opt);
@@ -575,7 +720,7 @@ int pb200_hier_evaluate(pb200_handle* h, const double* theta_outer, int n_outer,
         t_total += ms * 1e-3;
     }
     double nerr1 = h->h_out.p[1];
-    if (reduce) reduce(&nerr1, 1, PB200_REDUCE_SUM);
+    if (reduce && !h->nccl) reduce(&nerr1, 1, PB200_REDUCE_SUM);  // (NCCL: reduced on the stream with d_out)
     if (nerr1 != 0.0) {  // "Function evaluation failed." -> functionEvaluationFailure
         *fval = std::numeric_limits<double>::infinity();
         return PB200_EVAL_FAILURE;
@@ -585,8 +730,9 @@ int pb200_hier_evaluate(pb200_handle* h, const double* theta_outer, int n_outer,
     double nllh_analytic = 0.0;
     std::string err;
     if (!hier_compute(h->hier, h->d_my.p, h->d_yout.p, h->d_sout.p, h->stream, grad_outer == nullptr, &inner_scaled,
-                      &nllh_analytic, &err, reduce))
+                      &nllh_analytic, &err, reduce, c_lo, c_hi))
         return fail(PB200_ERR_CUDA, err);
+    if (coll_rc) return coll_rc;
     hier_splice(h->hier, theta_outer, inner_scaled.data(), full.data());
     if (full_parameters) std::memcpy(full_parameters, full.data(), sizeof(double) * h->n_opt);
     int status;
@@ -596,26 +742,9 @@ int pb200_hier_evaluate(pb200_handle* h, const double* theta_outer, int n_outer,
         for (int c = 0; c < h->C; ++c) all[c] = c;
         std::vector<double> full_grad(h->n_opt);
         double sec2 = 0.0;
-        if (!reduce) {
-            status = pb200_evaluate(h, full.data(), h->n_opt, all.data(), h->C, fval, full_grad.data(), &sec2);
-            if (status < 0) return status;
-        } else {
-            // partial (nllh, #errors, gradient) of this rank, all-reduced, then A1's failure rule
-            if (int rc = enqueue_evaluation(h, full.data(), all.data(), h->C, 1, h->d_out.p, nullptr, nullptr, h->stream)) return rc;
-            PB_CUDA(cudaMemcpyAsync(h->h_out.p, h->d_out.p, sizeof(double) * (2 + h->n_opt), cudaMemcpyDeviceToHost, h->stream));
-            PB_CUDA(cudaStreamSynchronize(h->stream));
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop);
-            sec2 = ms * 1e-3;
-            reduce(h->h_out.p, 2 + h->n_opt, PB200_REDUCE_SUM);
-            *fval = h->h_out.p[0];
-            for (int j = 0; j < h->n_opt; ++j) full_grad[j] = h->h_out.p[2 + j];
-            status = PB200_EVAL_SUCCESS;
-            if (h->h_out.p[1] != 0.0 || !std::isfinite(*fval)) {
-                *fval = std::numeric_limits<double>::infinity();
-                status = PB200_EVAL_FAILURE;
-            }
-        }
+        // (a partitioned handle all-reduces (nllh, #errors, gradient) inside pb200_evaluate)
+        status = pb200_evaluate(h, full.data(), h->n_opt, all.data(), h->C, fval, full_grad.data(), &sec2);
+        if (status < 0) return status;
         t_total += sec2;
         if (status == PB200_EVAL_SUCCESS) hier_filter(h->hier, full_grad.data(), grad_outer);
     } else {

@@ -20,15 +20,19 @@ constexpr int TEAM_THREADS = 512;
 
 template <int TEAM_THREADS_>
 __global__ void __launch_bounds__(TEAM_THREADS_, 1)
-simulate_team_kernel(const KernelArgs a, const NetTables T, double* __restrict__ workspace, size_t ws_stride, int NB) {
+simulate_team_kernel(const KernelArgs a, const NetTables T, const SparseLU SP, double* __restrict__ workspace,
+                     size_t ws_stride, int NB, int stage_doubles, int use_sparse) {
     extern __shared__ __align__(16) double pb_team_smem[];
     __shared__ int s_pos;
     CtaTeam tm;
     BdfTeam<CtaTeam> bdf(tm);
     bdf.T = T;
+    bdf.SP = SP;
+    bdf.use_sparse = use_sparse != 0;
     bdf.opt = a.opt;
-    bdf.w.carve(workspace + (size_t)blockIdx.x * ws_stride, T);
+    bdf.w.carve(workspace + (size_t)blockIdx.x * ws_stride, T, SP.enabled ? SP.nV : 0);
     bdf.w.NB = NB;
+    bdf.w.stage_doubles = stage_doubles;
     const int tid = threadIdx.x;
     const int np = T.np;
     for (;;) {
@@ -109,6 +113,9 @@ simulate_team_kernel(const KernelArgs a, const NetTables T, double* __restrict__
 /// Device copy of a network's tables + the teams' HBM workspace (owned by the handle).
 struct TeamState {
     NetTables dev{};
+    SparseLU sp{};          // device view of the symbolic factorisation
+    SparseLUHost sp_host;   // host copy (counts for the roofline report)
+    bool sparse_default = false;
     std::vector<void*> allocs;
     double* workspace = nullptr;
     size_t ws_stride = 0;
@@ -169,9 +176,27 @@ inline void* team_create_state(const NetTables& H, int sm_count, std::string* er
         team_destroy_state(st);
         return nullptr;
     }
-    e = cudaFuncSetAttribute(simulate_team_kernel<TEAM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem);
-    if (e != cudaSuccess) return fail(e);
-    st->ws_stride = TeamWork::hbm_doubles(H);
+    // symbolic factorisation of the Newton matrix's pattern, once per model (the klu_analyze role)
+    {
+        const int deg_max = H.nx >= 128 ? 32 : (H.nx / 4 > 2 ? H.nx / 4 : 2);
+        st->sp_host = SparseLUHost::build(H.nx, H.j_ptr, H.j_col, H.jell_pos, deg_max, 2);
+        const SparseLUHost& S = st->sp_host;
+        st->sp = S.view();
+#define UPV(field, vec) if ((e = team_upload(st, S.vec.data(), S.vec.size(), &st->sp.field)) != cudaSuccess) return fail(e)
+        UPV(ord, ord); UPV(iord, iord);
+        UPV(tlevel_ptr, tlevel_ptr); UPV(t_dst, t_dst); UPV(t_src, t_src); UPV(t_piv, t_piv); UPV(t_pptr, t_pptr);
+        UPV(p_l, p_l); UPV(p_u, p_u);
+        UPV(s_dst, s_dst); UPV(s_src, s_src); UPV(s_diag, s_diag); UPV(s_pptr, s_pptr);
+        UPV(Lr_ptr, Lr_ptr); UPV(Lr_col, Lr_col); UPV(Ur_ptr, Ur_ptr); UPV(Ur_col, Ur_col);
+        UPV(flev_ptr, flev_ptr); UPV(flev_rows, flev_rows); UPV(blev_ptr, blev_ptr); UPV(blev_rows, blev_rows);
+#undef UPV
+        // automatic choice (PB200_OPT_LINSOL = 0): sparse where it removes a real part of the dense work --
+        // the dense block is at most 3/4 of the matrix -- dense for small or nearly full patterns
+        st->sparse_default = H.nx >= 128 && 4 * S.m <= 3 * H.nx;
+    }
+    if (st->sp.m <= TEAM_THREADS && st->smem < (size_t)TEAM_SM_ROWS_END * sizeof(double))
+        st->smem = (size_t)TEAM_SM_ROWS_END * sizeof(double);  // the Schur block takes the rows path
+    st->ws_stride = TeamWork::hbm_doubles(H, st->sp.nV);
     st->grid_cap = sm_count;
     e = cudaMalloc((void**)&st->workspace, st->ws_stride * sizeof(double) * (size_t)st->grid_cap);
     if (e != cudaSuccess) return fail(e);
@@ -185,11 +210,32 @@ inline int team_launch(const KernelArgs& a, void* state, cudaStream_t stream, in
     int grid = st->grid_cap;  // persistent: one team per SM, work queue inside
     if (grid > a.n) grid = a.n;
     if (grid < 1) grid = 1;
-    simulate_team_kernel<TEAM_THREADS><<<grid, TEAM_THREADS, st->smem, stream>>>(a, st->dev, st->workspace, st->ws_stride, st->NB);
+    // (the attribute is per device and per function: set at every launch, to this model's size)
+    cudaError_t e = cudaFuncSetAttribute(simulate_team_kernel<TEAM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(227u * 1024u));
+    if (e != cudaSuccess) return (int)e;
+    const int use_sparse = a.linsol == 2 ? 1 : (a.linsol == 1 ? 0 : (st->sparse_default ? 1 : 0));
+    const int stage_doubles = (int)(st->smem / sizeof(double)) - TEAM_SM_RBUF;
+    simulate_team_kernel<TEAM_THREADS><<<grid, TEAM_THREADS, st->smem, stream>>>(a, st->dev, st->sp, st->workspace, st->ws_stride,
+                                                                                st->NB, stage_doubles, use_sparse);
     if (lanes_used) *lanes_used = TEAM_THREADS;
     if (grid_used) *grid_used = grid;
     if (block_used) *block_used = TEAM_THREADS;
     return (int)cudaGetLastError();
+}
+
+/// description of the linear solver for reports (pb200_linsol_info): see parpe_b200/problem.py for the names
+inline int team_linsol_info(void* state, int64_t* v, int n) {
+    auto* st = static_cast<TeamState*>(state);
+    if (!st) return 0;
+    const SparseLUHost& S = st->sp_host;
+    const int64_t vals[14] = {st->sparse_default ? 2 : 1, S.nx, S.n1, S.m, S.nnzJ, S.nnzL, S.nnzU,
+                              S.n_pairs_sparse + S.n_pairs_schur, (int64_t)S.flev_ptr.size() - 1,
+                              (int64_t)S.blev_ptr.size() - 1, S.factor_flops(), S.solve_flops(),
+                              8 * ((int64_t)S.nV + (int64_t)S.m * S.m), 8 * ((int64_t)S.nV + (int64_t)S.m * S.m)};
+    int k = 0;
+    for (; k < 14 && k < n; ++k) v[k] = vals[k];
+    return k;
 }
 
 #define PB200_REGISTER_NET(NAME)                                                                              \
@@ -213,6 +259,7 @@ inline int team_launch(const KernelArgs& a, void* state, cudaStream_t stream, in
             o.launch = &launch_##NAME;                                                                        \
             o.create_state = &create_##NAME;                                                                  \
             o.destroy_state = &pb200::team_destroy_state;                                                     \
+            o.linsol_info = &pb200::team_linsol_info;                                                         \
             pb200::register_model(o);                                                                         \
         }                                                                                                     \
     } reg_net_instance_##NAME;                                                                                \

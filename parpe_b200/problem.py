@@ -96,9 +96,42 @@ class B200SummedGradientFunction:
         return rc, y, s
 
     # ---- beyond the reference interface -------------------------------------------
-    def set_partition(self, rank: int, world: int):
+    def set_partition(self, rank: int, world: int, partial_sums: bool = False):
+        """Shard every index list over ``world`` handles.  ``evaluate`` then returns the GLOBAL result and
+        needs a collective (``nccl_init`` or ``set_allreduce``); ``partial_sums=True`` makes it return the
+        rank-local sums instead (tests)."""
         capi.check(capi.lib().pb200_set_partition(self._h, rank, world), "pb200_set_partition")
+        self.set_option(capi.OPT_PARTIAL_SUMS, int(partial_sums))
         self.rank, self.world = rank, world
+
+    def set_option(self, key: int, value: int):
+        capi.check(capi.lib().pb200_set_option(self._h, key, value), "pb200_set_option")
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        capi.check(capi.lib().pb200_nccl_unique_id(buf), "pb200_nccl_unique_id")
+        return buf.raw
+
+    def nccl_init(self, unique_id: bytes, rank: int, world: int):
+        """In-library NCCL communicator over the ``world`` handles of a partitioned problem (also sets
+        the partition): evaluate / evaluate_device / hier_evaluate then return global sums."""
+        assert len(unique_id) == 128
+        capi.check(capi.lib().pb200_nccl_init(self._h, unique_id, rank, world), "pb200_nccl_init")
+        self.rank, self.world = rank, world
+
+    def last_transfer_bytes(self):
+        a, b = C.c_int64(), C.c_int64()
+        capi.check(capi.lib().pb200_last_transfer_bytes(self._h, C.byref(a), C.byref(b)), "pb200_last_transfer_bytes")
+        return a.value, b.value
+
+    def linsol_info(self):
+        """Linear-solver description of the large-model path (symbolic analysis done at create)."""
+        v = (C.c_int64 * 16)()
+        n = capi.check(capi.lib().pb200_linsol_info(self._h, v, 16), "pb200_linsol_info")
+        names = ["kind", "nx", "n_sparse", "m_dense", "nnz_J", "nnz_L", "nnz_U", "updates", "levels_fwd",
+                 "levels_bwd", "factor_flops", "solve_flops", "factor_bytes", "solve_bytes"]
+        return {k: int(v[i]) for i, k in enumerate(names[:n])}
 
     def set_allreduce(self, fn):
         """Collective hook of partitioned hierarchical evaluations: ``fn(array, op)`` all-reduces the

@@ -27,7 +27,7 @@ DEFAULT_TIMEPOINTS = {
 }
 
 
-def condition_constants(model: str, C: int, rng: np.random.Generator) -> np.ndarray:
+def condition_constants(model: str, C: int, rng: np.random.Generator, heterogeneous: bool = False) -> np.ndarray:
     spec = get_spec(model)
     k = np.tile(np.asarray(spec.k_nominal, dtype=float), (C, 1))
     if model == "steadystate":
@@ -41,12 +41,12 @@ def condition_constants(model: str, C: int, rng: np.random.Generator) -> np.ndar
         k[:, 0] = np.array([0.5, 1.0, 1.5, 2.0])[np.arange(C) % 4]
         k[:, 1] = 1.0 + 0.05 * rng.standard_normal(C)
     elif model == "boehm":
-        import os
-        if not os.environ.get("PB200_IDENTICAL_CONDITIONS"):
+        if heterogeneous:
+            # conditions that really differ (as the 6 doses of the Fujita problem span 300x): the constant
+            # is log-uniform over 2.5 decades, so step counts and Newton behaviour vary across the warp
+            k[:, 0] = 0.693 * 10.0 ** rng.uniform(-1.25, 1.25, C)
+        else:
             k[:, 0] = 0.693 * (1.0 + 0.02 * rng.standard_normal(C))
-            rep = int(os.environ.get("PB200_REPLICATE_CONDITIONS", "1"))  # experiments: blocks of identical conditions
-            if rep > 1:
-                k[:, 0] = k[(np.arange(C) // rep) * rep, 0]
     return k
 
 
@@ -55,7 +55,7 @@ def make_problem(model: str, n_conditions: int, *, scale: str = "log10", seed: i
                  simulate: Optional[Callable] = None, noise: float = 0.1,
                  missing_fraction: float = 0.0, ragged: bool = False,
                  condition_specific: int = 0, rtol: float = 1e-8, atol: float = 1e-12,
-                 **kw) -> ProblemTables:
+                 holes: int = 0, heterogeneous: bool = False, **kw) -> ProblemTables:
     """Build tables for ``model`` with ``n_conditions`` conditions.
 
     scale: 'log10' | 'lin' | 'mixed' (optimiser scale of every parameter; the
@@ -66,6 +66,10 @@ def make_problem(model: str, n_conditions: int, *, scale: str = "log10", seed: i
     condition_specific: number of leading model parameters that get their own
            optimisation parameter per group of conditions (c % 2), as the
            offset-by-batch construction of the reference example does.
+    holes: this many model parameters per condition (rotating with the condition index) are NOT mapped
+           to an optimisation parameter (mapping = -1): they take their value from
+           ``/parameters/parameterOverrides`` (a perturbed nominal value in the simulation scale) and drop
+           out of the sensitivity list (multiConditionDataProvider.cpp:84-102,126-169,323-339).
     simulate(tables, theta) -> y_flat: optional callable producing noise-free
            outputs to derive measurements from; without it measurements are
            positive pseudo-data (throughput work is independent of them).
@@ -95,13 +99,25 @@ def make_problem(model: str, n_conditions: int, *, scale: str = "log10", seed: i
     pscale_sim = pscale_opt[np.maximum(mapping, 0)].astype(np.int32)
     if scale == "mixed":
         pscale_sim[:, 1::2] = SCALE_NONE
-    k = condition_constants(model, C, rng)
+    k = condition_constants(model, C, rng, heterogeneous)
+    overrides = None
+    if holes:
+        pn = np.asarray(spec.p_nominal, dtype=float)
+        overrides = np.full((C, np_), np.nan)
+        hrng = np.random.default_rng(seed + 1000)
+        for c in range(C):
+            for h_ in range(holes):
+                i = (3 * c + 5 * h_ + 1) % np_
+                lin = pn[i] * (1.0 + 0.2 * hrng.uniform(-1, 1))
+                sc = pscale_sim[c, i]
+                overrides[c, i] = np.log10(lin) if sc == SCALE_LOG10 else (np.log(lin) if sc == 1 else lin)
+                mapping[c, i] = -1
 
     y = np.full(t.size * ny, 1.0)
     sigma = np.full(t.size * ny, np.nan)
     tab = ProblemTables(model_name=model, np_=np_, nk=nk, ny=ny, n_opt=n_opt, t_offsets=t_offsets, t=t, y=y,
                         sigma=sigma, k=k, mapping=mapping, pscale_sim=pscale_sim, pscale_opt=pscale_opt,
-                        rtol=rtol, atol=atol, **kw)
+                        overrides=overrides, rtol=rtol, atol=atol, **kw)
     theta = nominal_theta(tab)
     if simulate is not None:
         ysim = np.asarray(simulate(tab, theta), dtype=float).reshape(-1)

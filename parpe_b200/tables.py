@@ -14,8 +14,8 @@ from typing import Optional
 
 import numpy as np
 
-PB200_ABI_VERSION = 1
-PB200_NSTATS = 16
+PB200_ABI_VERSION = 2
+PB200_NSTATS = 20
 STAT_NAMES = ["nst", "nfe", "nsetups", "nje", "nni", "nniS", "nfSe", "netf", "netfS", "ncfn", "ncfnS", "nor",
               "trials", "qsum"]
 SCALE_NONE, SCALE_LN, SCALE_LOG10 = 0, 1, 2

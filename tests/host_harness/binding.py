@@ -39,7 +39,7 @@ def simulate(model, p_unscaled, k, plist, t, my, sd, t0=0.0, rtol=1e-8, atol=1e-
     ns = len(plist)
     llh = C.c_double()
     sllh = np.zeros(max(ns, 1))
-    stats = np.zeros(16, dtype=np.int64)
+    stats = np.zeros(20, dtype=np.int64)
     y = np.zeros(my.size) if want_outputs else None
     s = np.zeros(my.size) if want_outputs else None
     trace = np.zeros(2 * len(t), dtype=np.int32)
@@ -58,7 +58,8 @@ _lib_team = None
 def build_team(force=False):
     src = os.path.join(_HERE, "host_sim_team.cpp")
     cs = os.path.join(_HERE, "..", "..", "parpe_b200", "csrc")
-    deps = [src] + [os.path.join(cs, f) for f in ("bdf_team.cuh", "bdf_core.cuh", "net_model.cuh", "team.cuh", "pb_hd.h")]
+    deps = [src] + [os.path.join(cs, f) for f in ("bdf_team.cuh", "bdf_core.cuh", "net_model.cuh", "team.cuh", "pb_hd.h",
+                                                  "sparse_lu.h")]
     mdir = os.path.join(cs, "models")
     deps += [os.path.join(mdir, f) for f in os.listdir(mdir) if f.startswith("net_")]
     if force or not os.path.exists(LIB_TEAM) or any(os.path.getmtime(d) > os.path.getmtime(LIB_TEAM) for d in deps):
@@ -73,21 +74,21 @@ def lib_team():
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
         L.hs_team_simulate.argtypes = [C.c_char_p, dp, dp, ip, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double,
                                        C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int64),
-                                       dp, dp, ip]
-        L.hs_team_solve.argtypes = [C.c_char_p, dp, C.c_double, dp, C.c_int, C.c_int, dp]
+                                       dp, dp, ip, C.c_int, C.c_int, C.c_int]
+        L.hs_team_solve.argtypes = [C.c_char_p, dp, C.c_double, dp, C.c_int, C.c_int, dp, C.c_int, C.c_int, C.c_int, ip]
         _lib_team = L
     return _lib_team
 
 
 def simulate_team(model, p_unscaled, k, plist, t, my, sd, t0=0.0, rtol=1e-8, atol=1e-12, maxsteps=10000, stldet=1,
-                  errconS=1, want_outputs=False, panel_width=0):
+                  errconS=1, want_outputs=False, panel_width=0, sparse=False, deg_max=0, stage_doubles=0):
     d = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     p_unscaled, k, t, my, sd = d(p_unscaled), d(k), d(t), d(my).reshape(-1), d(sd).reshape(-1)
     plist = np.ascontiguousarray(plist, dtype=np.int32)
     ns = len(plist)
     llh = C.c_double()
     sllh = np.zeros(max(ns, 1))
-    stats = np.zeros(16, dtype=np.int64)
+    stats = np.zeros(20, dtype=np.int64)
     y = np.zeros(my.size) if want_outputs else None
     s = np.zeros(my.size) if want_outputs else None
     trace = np.zeros(2 * len(t), dtype=np.int32)
@@ -95,17 +96,23 @@ def simulate_team(model, p_unscaled, k, plist, t, my, sd, t0=0.0, rtol=1e-8, ato
     st = lib_team().hs_team_simulate(model.encode(), P(p_unscaled), P(k), plist.ctypes.data_as(C.POINTER(C.c_int)), ns,
                                      len(t), P(t), P(my), P(sd), t0, rtol, atol, maxsteps, stldet, errconS, panel_width,
                                      C.byref(llh), P(sllh), stats.ctypes.data_as(C.POINTER(C.c_int64)), P(y), P(s),
-                                     trace.ctypes.data_as(C.POINTER(C.c_int)))
+                                     trace.ctypes.data_as(C.POINTER(C.c_int)), int(sparse), deg_max, stage_doubles)
     return dict(numsteps=trace[0::2], order=trace[1::2], status=st, llh=llh.value, sllh=sllh[:ns], stats=stats, y=y, sigmay=s)
 
 
-def team_solve(model, Jcsr, gamma, B, panel_width=0):
-    """(I - gamma*J)^-1 B through the blocked Gauss-Jordan inversion and the solve GEMM; B is [ncols, nx]."""
+def team_solve(model, Jcsr, gamma, B, panel_width=0, sparse=False, deg_max=0, stage_doubles=0, want_info=False):
+    """(I - gamma*J)^-1 B through the blocked Gauss-Jordan inversion and the solve GEMM -- or, with
+    ``sparse``, through the sparse LU of the low-degree pivots + the inverse of the dense Schur block;
+    B is [ncols, nx]."""
     Jcsr = np.ascontiguousarray(Jcsr, dtype=np.float64)
     B = np.ascontiguousarray(B, dtype=np.float64)
     X = np.zeros_like(B)
+    info = np.zeros(8, dtype=np.int32)
     P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
-    rc = lib_team().hs_team_solve(model.encode(), P(Jcsr), gamma, P(B), B.shape[0], panel_width, P(X))
+    rc = lib_team().hs_team_solve(model.encode(), P(Jcsr), gamma, P(B), B.shape[0], panel_width, P(X), int(sparse),
+                                  deg_max, stage_doubles, info.ctypes.data_as(C.POINTER(C.c_int)))
     if rc != 0:
         raise RuntimeError("hs_team_solve failed: %d" % rc)
+    if want_info:
+        return X, dict(zip(["n1", "m", "nnzL", "nnzU", "pairs", "factor_levels", "fwd_levels", "bwd_levels"], info.tolist()))
     return X

@@ -27,24 +27,41 @@ static bool tables_for(const char* model, NetTables* T) {
     return false;
 }
 
+/// symbolic factorisation of a model's pattern, as team_create_state builds it (deg_max <= 0: its rule)
+static SparseLUHost symbolic_for(const NetTables& T, int deg_max) {
+    if (deg_max <= 0) deg_max = T.nx >= 128 ? 32 : (T.nx / 4 > 2 ? T.nx / 4 : 2);
+    return SparseLUHost::build(T.nx, T.j_ptr, T.j_col, T.jell_pos, deg_max, 2);
+}
+
+/// sparse != 0: sparse LU + dense Schur block (deg_max: largest degree of a sparse pivot, <= 0 = default);
+/// stage_doubles: capacity of the staging area of the triangular solves (small values force column batches)
 extern "C" int hs_team_simulate(const char* model, const double* p_unscaled, const double* k, const int* plist, int ns,
                                 int nt, const double* t, const double* my, const double* sd, double t0, double rtol,
                                 double atol, int maxsteps, int stldet, int errconS, int panel_width, double* llh,
-                                double* sllh, int64_t* stats, double* y_out, double* sigmay_out, int* trace) {
+                                double* sllh, int64_t* stats, double* y_out, double* sigmay_out, int* trace, int sparse,
+                                int deg_max, int stage_doubles) {
     NetTables T;
     if (!tables_for(model, &T)) return -12345;
-    std::vector<double> hbm(TeamWork::hbm_doubles(T), 0.0);
+    SparseLUHost SH;
+    if (sparse) SH = symbolic_for(T, deg_max);
+    std::vector<double> hbm(TeamWork::hbm_doubles(T, sparse ? SH.nV : 0), 0.0);
     const int NB = panel_width > 0 ? panel_width : TEAM_NB_MAX;
     std::vector<double> panel((size_t)T.nx * NB), rbuf(TEAM_RBUF), rowk(TEAM_NB_MAX);
     std::vector<int> piv(TEAM_NB_MAX);
+    if (stage_doubles <= 0) stage_doubles = 24064;
+    std::vector<double> stage(stage_doubles > T.nx ? stage_doubles : T.nx);
     HostTeam tm;
     BdfTeam<HostTeam> bdf(tm);
     bdf.T = T;
-    bdf.w.carve(hbm.data(), T);
+    if (sparse) bdf.SP = SH.view();
+    bdf.use_sparse = sparse != 0;
+    bdf.w.carve(hbm.data(), T, sparse ? SH.nV : 0);
     bdf.w.panel = panel.data();
     bdf.w.rbuf = rbuf.data();
     bdf.w.rowk = rowk.data();
     bdf.w.piv = piv.data();
+    bdf.w.stage = stage.data();
+    bdf.w.stage_doubles = stage_doubles;
     bdf.w.NB = NB;
     for (int i = 0; i < T.np; ++i) bdf.w.p[i] = p_unscaled[i];
     for (int i = 0; i < T.nk; ++i) bdf.w.k[i] = k[i];
@@ -65,22 +82,35 @@ extern "C" int hs_team_simulate(const char* model, const double* p_unscaled, con
 /// the model's sparsity pattern is not general enough for a unit test, so this entry point takes
 /// gamma and the CSR Jacobian values of `model` and returns (I - gamma J)^-1 B.
 extern "C" int hs_team_solve(const char* model, const double* Jcsr, double gamma, const double* B, int ncols,
-                             int panel_width, double* X) {
+                             int panel_width, double* X, int sparse, int deg_max, int stage_doubles, int* info) {
     NetTables T;
     if (!tables_for(model, &T)) return -12345;
-    std::vector<double> hbm(TeamWork::hbm_doubles(T), 0.0);
+    SparseLUHost SH;
+    if (sparse) SH = symbolic_for(T, deg_max);
+    std::vector<double> hbm(TeamWork::hbm_doubles(T, sparse ? SH.nV : 0), 0.0);
     const int NB = panel_width > 0 ? panel_width : TEAM_NB_MAX;
     std::vector<double> panel((size_t)T.nx * NB), rbuf(TEAM_RBUF), rowk(TEAM_NB_MAX);
     std::vector<int> piv(TEAM_NB_MAX);
+    if (stage_doubles <= 0) stage_doubles = 24064;
+    std::vector<double> stage(stage_doubles > T.nx ? stage_doubles : T.nx);
     HostTeam tm;
     BdfTeam<HostTeam> bdf(tm);
     bdf.T = T;
-    bdf.w.carve(hbm.data(), T);
+    if (sparse) bdf.SP = SH.view();
+    bdf.use_sparse = sparse != 0;
+    bdf.w.carve(hbm.data(), T, sparse ? SH.nV : 0);
     bdf.w.panel = panel.data();
     bdf.w.rbuf = rbuf.data();
     bdf.w.rowk = rowk.data();
     bdf.w.piv = piv.data();
+    bdf.w.stage = stage.data();
+    bdf.w.stage_doubles = stage_doubles;
     bdf.w.NB = NB;
+    if (info && sparse) {
+        info[0] = SH.n1; info[1] = SH.m; info[2] = SH.nnzL; info[3] = SH.nnzU;
+        info[4] = (int)(SH.n_pairs_sparse + SH.n_pairs_schur);
+        info[5] = (int)SH.tlevel_ptr.size() - 1; info[6] = (int)SH.flev_ptr.size() - 1; info[7] = (int)SH.blev_ptr.size() - 1;
+    }
     bdf.nx = T.nx;
     bdf.ns = ncols - 1;
     bdf.ncol = ncols;
@@ -88,7 +118,16 @@ extern "C" int hs_team_solve(const char* model, const double* Jcsr, double gamma
     bdf.gamrat = 1.0;
     if (ncols > T.np + 1) return -2;
     for (int e = 0; e < T.nnz; ++e) bdf.w.Jsaved[T.jell_pos[e]] = Jcsr[e];
-    if (bdf.invert_newton_matrix() != 0) return 1;
+    bdf.dn = T.nx;
+    bdf.lin_sparse = false;
+    bdf.nfallback = 0;
+    bdf.cyc_spfactor = bdf.cyc_sptri = bdf.cyc_panel = bdf.cyc_update = bdf.cyc_solve = 0;
+    if (sparse) {
+        const int r = bdf.factor_sparse();
+        if (r != 0) return 10 + r;
+    } else if (bdf.invert_newton_matrix() != 0) {
+        return 1;
+    }
     for (size_t e = 0; e < (size_t)T.nx * ncols; ++e) {
         bdf.w.b[e] = B[e];
         bdf.w.acor[e] = 0.0;

@@ -12,9 +12,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_contract_line(oracle_available):
-    env = dict(os.environ, PB200_BENCH_CONDITIONS="48")
+    env = dict(os.environ, OMP_NUM_THREADS="1")  # as torchrun exports it: the arm must not depend on it
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                          "--warmup", "0", "--workload", "boehm", "--conditions", "48"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
                          timeout=600, check=True).stdout.strip().splitlines()
     assert len(out) == 1
     line = json.loads(out[0])
@@ -23,15 +23,19 @@ def test_reference_arm_prints_contract_line(oracle_available):
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "solves/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["vs_baseline"] is None and line["gpu_launches"] == 0
-    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] == "reference"
+    # every host core is used whatever OMP_NUM_THREADS says (round 1: torchrun's OMP_NUM_THREADS=1 made the
+    # reference arm single-threaded at N > 1 while it reported all cores)
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert "%d OpenMP threads" % line["cpu_baseline"]["cores"] in line["cpu_baseline"]["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():
-    env = dict(os.environ, RANK="1", WORLD_SIZE="2", PB200_BENCH_CONDITIONS="8")
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
-                        "--steps", "1", "--warmup", "0"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                        "--steps", "1", "--warmup", "0", "--workload", "boehm", "--conditions", "8"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                        text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip() == ""
 
@@ -40,7 +44,7 @@ def test_algorithmic_counts_follow_the_survey_formulas():
     sys.path.insert(0, ROOT)
     import bench
     from parpe_b200.tables import STAT_NAMES
-    stats = np.zeros((2, 16), dtype=np.int64)
+    stats = np.zeros((2, 20), dtype=np.int64)
     vals = dict(nst=100, nfe=220, nsetups=15, nje=3, nni=110, nniS=105, nfSe=945, qsum=400)
     for k, v in vals.items():
         stats[:, STAT_NAMES.index(k)] = v

@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_abi_version_and_model_registry():
     L = capi.lib()
-    assert L.pb200_abi_version() == 1
+    assert L.pb200_abi_version() == 2
     m = capi.models()
     assert m["boehm"] == dict(nx=8, np=9, nk=2, ny=3)
     assert m["steadystate"] == dict(nx=3, np=5, nk=4, ny=3)

@@ -42,12 +42,21 @@ def test_host_core_against_fixture(path):
     from tests.host_harness.binding import simulate, simulate_team
     from parpe_b200.models.netmodels import NET_MODELS
     doc, tab, theta = _load(path)
+    if doc["case"] == "froehlich_full":
+        pytest.skip("nx = 1200 over the full horizon takes tens of minutes on one host thread; the CUDA path "
+                    "is checked against this fixture on the GPU")
     if doc["model"] in NET_MODELS:  # large-model core (bdf_team.cuh with the one-thread team)
-        simulate = simulate_team
+        import functools
+        # the full-horizon Chen-shape case runs with the sparse linear solver (as the CUDA path does by default)
+        simulate = functools.partial(simulate_team, sparse=True) if doc["case"] == "chen_full" else simulate_team
     for c in range(tab.n_conditions):
         p = np.empty(tab.np_)
         for i in range(tab.np_):
             j = tab.mapping[c, i]
+            if j < 0:  # unmapped: the override value, given in the simulation scale
+                v, sc = tab.overrides[c, i], tab.pscale_sim[c, i]
+                p[i] = 10.0 ** v if sc == SCALE_LOG10 else (np.exp(v) if sc == SCALE_LN else v)
+                continue
             lin = 10.0 ** theta[j] if tab.pscale_opt[j] == SCALE_LOG10 else (
                 np.exp(theta[j]) if tab.pscale_opt[j] == SCALE_LN else theta[j])
             p[i] = lin
@@ -73,6 +82,14 @@ def test_cuda_path_against_fixture(path):
     assert_grad_close(grad, doc["grad"])
     res = gpu.condition_results()
     assert_llh_close(res["llh"], doc["llh"])
+    for c in range(tab.n_conditions):
+        assert_grad_close(res["sllh"][c], doc["sllh"][c], "per-condition sllh[%d]" % c)
+    if "nst" in doc:  # step counts stay close to the reference's (a wrong factorisation converges, but slower)
+        nst_ref = np.array(doc["nst"])
+        assert np.all(np.abs(res["stats"][:, 0] - nst_ref) <= 0.1 * nst_ref + 5), (res["stats"][:, 0], nst_ref)
+        assert np.all(res["stats"][:, 16] == 0)  # no sparse-factorisation fallback
+    if doc["case"].endswith("_full") and doc["model"] == "froehlich":
+        return  # (the subset / output passes repeat the same integration: skipped for the nx = 1200 case)
     st, fs, gs, _ = gpu.evaluate(theta, doc["subset"])
     assert_llh_close(fs, doc["subset_nllh"])
     assert_grad_close(gs, doc["subset_grad"])

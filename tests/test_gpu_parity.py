@@ -131,7 +131,7 @@ def test_partition_sums_to_whole(oracle_available):
     fs, gs = 0.0, 0.0
     for r in range(2):
         part = B200SummedGradientFunction(tab)
-        part.set_partition(r, 2)
+        part.set_partition(r, 2, partial_sums=True)
         _, fr, gr, _ = part.evaluate(theta)
         fs, gs = fs + fr, gs + gr
     assert_llh_close(fs, f)

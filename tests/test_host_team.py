@@ -184,3 +184,97 @@ def test_host_team_output_time_edge_cases(oracle_available):
         assert_llh_close(r["llh"], ro["llh"][c])
         fac = np.array([p[i] * np.log(10) for i in plist])
         assert_grad_close(r["sllh"] * fac, ro["sllh"][c][:len(plist)])
+
+
+# ---- sparse fixed-pattern LU + dense Schur block (sparse_lu.h; the reference's KLU role) ----------
+def _diag_dominant_values(spec, rng):
+    """Random values on the pattern whose I - gamma*J keeps usable diagonal pivots (the sparse part pivots
+    on the diagonal, as KLU does unless |diag| < 0.001 max|column|)."""
+    Jv = rng.standard_normal(spec.nnz)
+    rows = np.repeat(np.arange(spec.nx), np.diff(spec.j_ptr))
+    Jv[rows == spec.j_col] = -np.abs(Jv[rows == spec.j_col]) - 3.0   # degradation-like diagonal
+    return Jv
+
+
+@pytest.mark.parametrize("model,ncols,deg_max,stage", [("net32", 7, 0, 0), ("net32", 7, 3, 0), ("net32", 7, 100, 0),
+                                                       ("net31", 6, 4, 0), ("net32", 7, 0, 70),
+                                                       ("chen", 51, 0, 0), ("chen", 51, 0, 6000), ("froehlich", 4, 0, 0)])
+def test_sparse_lu_with_dense_schur_block(model, ncols, deg_max, stage):
+    """(I - gamma J)^-1 B through the sparse factors (entry-wise numeric phase over dependency levels,
+    level-scheduled triangular solves) and the dense inverse of the Schur block vs numpy, for several
+    splits (deg_max = 100 on net32: everything sparse, m = 0) and column batch sizes."""
+    from tests.host_harness.binding import team_solve
+    spec = get_spec(model)
+    rng = np.random.default_rng(0)
+    Jv = _diag_dominant_values(spec, rng)
+    gamma = 0.37
+    A = np.eye(spec.nx) - gamma * _dense_jacobian(spec, Jv)
+    B = rng.standard_normal((ncols, spec.nx))
+    Xref = np.linalg.solve(A, B.T).T
+    X, info = team_solve(model, Jv, gamma, B, sparse=True, deg_max=deg_max, stage_doubles=stage, want_info=True)
+    assert info["n1"] + info["m"] == spec.nx and info["n1"] > 0
+    if deg_max == 100:
+        assert info["m"] == 0
+    assert np.max(np.abs(X - Xref)) <= 1e-10 * np.max(np.abs(Xref)), info
+    # the dense path gives the same answer
+    Xd = team_solve(model, Jv, gamma, B)
+    assert np.max(np.abs(X - Xd)) <= 1e-10 * np.max(np.abs(Xref))
+
+
+def test_sparse_lu_symbolic_matches_superlu_fill():
+    """The symbolic phase on the Chen-shape pattern: minimum degree on J + J^T leaves a dense block of
+    about half the matrix (no small separators in a random network) and a sparse part whose factors are
+    far smaller than the matrix; counts are what DESIGN.md's roofline uses."""
+    from tests.host_harness.binding import team_solve
+    spec = get_spec("chen")
+    rng = np.random.default_rng(1)
+    _, info = team_solve("chen", _diag_dominant_values(spec, rng), 0.1, rng.standard_normal((1, spec.nx)), sparse=True,
+                         want_info=True)
+    assert 200 <= info["m"] <= 300 and info["m"] % 2 == 0
+    assert info["nnzL"] + info["nnzU"] < 0.05 * spec.nx ** 2
+    assert info["fwd_levels"] < info["n1"] and info["bwd_levels"] < info["n1"]
+
+
+def test_sparse_lu_weak_pivot_falls_back_to_dense():
+    """A diagonal pivot below 0.001 of an entry of its column (KLU would leave the diagonal there) is
+    reported by the sparse numeric phase (return code 2 -> 12 through the harness), so that lsetup redoes
+    the matrix by the dense path with partial pivoting."""
+    from tests.host_harness.binding import team_solve
+    spec = get_spec("net32")
+    rng = np.random.default_rng(2)
+    Jv = _diag_dominant_values(spec, rng)
+    rows = np.repeat(np.arange(spec.nx), np.diff(spec.j_ptr))
+    gamma = 0.5
+    Jv[rows == spec.j_col] = 1.0 / gamma - 1e-9   # I - gamma*J has a (nearly) zero diagonal
+    with pytest.raises(RuntimeError, match="12"):
+        team_solve("net32", Jv, gamma, np.ones((1, spec.nx)), sparse=True)
+    X = team_solve("net32", Jv, gamma, np.ones((1, spec.nx)))  # dense path: partial pivoting copes
+    A = np.eye(spec.nx) - gamma * _dense_jacobian(spec, Jv)
+    np.testing.assert_allclose(A @ X[0], np.ones(spec.nx), rtol=0, atol=1e-8)
+
+
+@pytest.mark.parametrize("model,deg_max,stage", [("net32", 0, 0), ("net32", 3, 150), ("net32", 100, 0)])
+def test_host_team_sparse_path_matches_cvodes(oracle_available, model, deg_max, stage):
+    """Full simulations with the sparse linear solver against the CVODES oracle (KLU), and against
+    the dense path of the same core: same step counts within a few steps, results within tolerance."""
+    from oracle.binding import OracleProblem
+    from tests.host_harness.binding import simulate_team
+    tab = synth.make_problem(model, 2, seed=7, scale="mixed", sigma_mode="mixed", missing_fraction=0.1)
+    ora = OracleProblem(tab, 2, 9)  # staggered, KLU (the reference default)
+    theta = synth.random_theta(tab, seed=3, width=0.3)
+    ro = ora.evaluate(theta, collect_stats=True)
+    assert ro["status"] == 0
+    for c in range(tab.n_conditions):
+        p = _unscaled_p(tab, c, theta, ora)
+        plist = ora.plist(c)
+        lo, hi = tab.t_offsets[c], tab.t_offsets[c + 1]
+        args = (model, p, tab.k[c], plist, tab.t[lo:hi], tab.y_of(c), tab.sigma_of(c))
+        r = simulate_team(*args, rtol=tab.rtol, atol=tab.atol, sparse=True, deg_max=deg_max, stage_doubles=stage)
+        rd = simulate_team(*args, rtol=tab.rtol, atol=tab.atol)
+        assert r["status"] == 0
+        assert r["stats"][16] == 0  # no fallback to the dense path
+        assert_llh_close(r["llh"], ro["llh"][c])
+        fac = np.array([p[i] * np.log(10) if tab.pscale_sim[c, i] == SCALE_LOG10 else
+                        (p[i] if tab.pscale_sim[c, i] == SCALE_LN else 1.0) for i in plist])
+        assert_grad_close(r["sllh"] * fac, ro["sllh"][c][:len(plist)])
+        assert abs(int(r["stats"][0]) - int(rd["stats"][0])) <= 0.05 * rd["stats"][0] + 3

@@ -29,6 +29,14 @@ CASES = {
     "net32_mixed": ("net32", 4, dict(scale="mixed", seed=15, sigma_mode="mixed", missing_fraction=0.1)),
     # nx = 500, nplist = 50 (Chen shape), first two output times
     "chen_log10": ("chen", 1, dict(scale="log10", seed=16, timepoints=[0.1, 0.3])),
+    # A5 holes: unmapped model parameters (mapping = -1) take /parameters/parameterOverrides and leave the
+    # sensitivity list (nplist < np); small-model and large-model kernels
+    "boehm_holes_mixed": ("boehm", 5, dict(scale="mixed", seed=17, holes=2, sigma_mode="mixed")),
+    "net32_holes": ("net32", 4, dict(scale="log10", seed=18, holes=2)),
+    # the FULL horizon of the large-model workloads (all 8 output times to t = 300: the stiff part, hundreds of
+    # linear-solver setups per solve), two conditions each -- what bench.py integrates
+    "chen_full": ("chen", 2, dict(scale="log10", seed=19)),
+    "froehlich_full": ("froehlich", 2, dict(scale="log10", seed=20)),
 }
 
 
@@ -44,7 +52,7 @@ def main():
     for name in (sys.argv[1:] or CASES):
         tab, theta = build_case(name)
         o = OracleProblem(tab, ISM_STAGGERED, LINSOL_KLU)  # AMICI's default linear solver
-        r = o.evaluate(theta)
+        r = o.evaluate(theta, collect_stats=True)
         sub = [tab.n_conditions - 1, 0, 0]
         rs = o.evaluate(theta, idx=sub)
         rc, y, s = o.get_model_outputs(theta)
@@ -55,6 +63,7 @@ def main():
             case=name, model=CASES[name][0], n_conditions=CASES[name][1], kwargs=CASES[name][2],
             theta=theta.tolist(), nllh=r["fval"], grad=r["grad"].tolist(), llh=r["llh"].tolist(),
             sllh=r["sllh"].tolist(), subset=sub, subset_nllh=rs["fval"], subset_grad=rs["grad"].tolist(),
+            nst=r["stats"][:, 0].tolist(),
             y=np.where(np.isnan(y), None, y).tolist(), sigmay=np.where(np.isnan(s), None, s).tolist())
         with open(os.path.join(outdir, name + ".json"), "w") as fh:
             json.dump(doc, fh, indent=1)
