@@ -92,6 +92,8 @@ enum {
     PB200_STAT_NFALLBACK,     /* setups whose sparse factorisation met a weak diagonal pivot and were
                                  redone by the dense path with partial pivoting */
     PB200_STAT_CYC_SPARSE,    /* (sparse numeric factorisation << 32) | sparse triangular solves */
+    PB200_STAT_CYC_STEP,      /* (history sweeps << 32) | whole state phase of the step attempts */
+    PB200_STAT_CYC_SENS,      /* (whole sensitivity phase << 32) | whole simulation */
     PB200_NSTATS = 20
 };
 

@@ -18,6 +18,7 @@ LIB = os.path.join(CSRC, "libparpe_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
+         "-Werror", "cross-execution-space-call",  # a __host__ function called from device code must not build
          "-ccbin", "/usr/bin/g++"] + os.environ.get("PB200_NVCC_EXTRA", "").split()
 
 

@@ -44,6 +44,32 @@
 // The same source compiles for the host with the SingleLane group (G = 1); that
 // instantiation exists only in tests/host_harness to diff the algorithm against
 // the CVODES oracle without a GPU.  The product library has no host integrator.
+//
+// ATTRIBUTION.  The scalar step-control logic in this file (initial step size `hin`, BDF coefficient
+// setup `set_bdf` / `cvset`, error-test / convergence-failure handling, order and step-size selection
+// `prepare_next_step`, stability-limit detection `sldet`) restates the algorithm of CVODES
+// (SUNDIALS 7.1.1, src/cvodes/cvodes.c: cvHin, cvSetBDF, cvSetTqBDF, cvDoErrorTest, cvHandleNFlag,
+// cvPrepareNextStep, cvSLdet) with its constants and, where that helps a reader compare the two,
+// its local names -- it has to, so that the step sequence stays that of the reference.  SUNDIALS is
+// Copyright (c) 2002-2024, Lawrence Livermore National Security and Southern Methodist University,
+// all rights reserved, and distributed under the BSD 3-Clause License
+// (deps/AMICI/ThirdParty/sundials/LICENSE in the reference tree):
+//   Redistribution and use in source and binary forms, with or without modification, are permitted
+//   provided that the following conditions are met: (1) redistributions of source code must retain the
+//   above copyright notice, this list of conditions and the following disclaimer; (2) redistributions in
+//   binary form must reproduce the above copyright notice, this list of conditions and the following
+//   disclaimer in the documentation and/or other materials provided with the distribution; (3) neither
+//   the name of the copyright holder nor the names of its contributors may be used to endorse or promote
+//   products derived from this software without specific prior written permission.
+//   THIS SOFTWARE IS PROVIDED BY THE COPYRIGHT HOLDERS AND CONTRIBUTORS "AS IS" AND ANY EXPRESS OR
+//   IMPLIED WARRANTIES, INCLUDING, BUT NOT LIMITED TO, THE IMPLIED WARRANTIES OF MERCHANTABILITY AND
+//   FITNESS FOR A PARTICULAR PURPOSE ARE DISCLAIMED.  IN NO EVENT SHALL THE COPYRIGHT HOLDER OR
+//   CONTRIBUTORS BE LIABLE FOR ANY DIRECT, INDIRECT, INCIDENTAL, SPECIAL, EXEMPLARY, OR CONSEQUENTIAL
+//   DAMAGES (INCLUDING, BUT NOT LIMITED TO, PROCUREMENT OF SUBSTITUTE GOODS OR SERVICES; LOSS OF USE,
+//   DATA, OR PROFITS; OR BUSINESS INTERRUPTION) HOWEVER CAUSED AND ON ANY THEORY OF LIABILITY, WHETHER
+//   IN CONTRACT, STRICT LIABILITY, OR TORT (INCLUDING NEGLIGENCE OR OTHERWISE) ARISING IN ANY WAY OUT OF
+//   THE USE OF THIS SOFTWARE, EVEN IF ADVISED OF THE POSSIBILITY OF SUCH DAMAGE.
+// Data layout, lane mapping, staging, linear algebra and norms in this file are this project's own.
 #ifndef PB200_BDF_CORE_CUH
 #define PB200_BDF_CORE_CUH
 

@@ -28,6 +28,32 @@
 //
 // The same source compiles for the host with HostTeam (one thread); that instantiation exists
 // only in tests/host_harness to diff the algorithm against the CVODES oracle without a GPU.
+//
+// ATTRIBUTION.  The scalar step-control logic in this file (initial step size `hin`, BDF coefficient
+// setup `set_bdf` / `cvset`, error-test / convergence-failure handling, order and step-size selection
+// `prepare_next_step`, stability-limit detection `sldet`) restates the algorithm of CVODES
+// (SUNDIALS 7.1.1, src/cvodes/cvodes.c: cvHin, cvSetBDF, cvSetTqBDF, cvDoErrorTest, cvHandleNFlag,
+// cvPrepareNextStep, cvSLdet) with its constants and, where that helps a reader compare the two,
+// its local names -- it has to, so that the step sequence stays that of the reference.  SUNDIALS is
+// Copyright (c) 2002-2024, Lawrence Livermore National Security and Southern Methodist University,
+// all rights reserved, and distributed under the BSD 3-Clause License
+// (deps/AMICI/ThirdParty/sundials/LICENSE in the reference tree):
+//   Redistribution and use in source and binary forms, with or without modification, are permitted
+//   provided that the following conditions are met: (1) redistributions of source code must retain the
+//   above copyright notice, this list of conditions and the following disclaimer; (2) redistributions in
+//   binary form must reproduce the above copyright notice, this list of conditions and the following
+//   disclaimer in the documentation and/or other materials provided with the distribution; (3) neither
+//   the name of the copyright holder nor the names of its contributors may be used to endorse or promote
+//   products derived from this software without specific prior written permission.
+//   THIS SOFTWARE IS PROVIDED BY THE COPYRIGHT HOLDERS AND CONTRIBUTORS "AS IS" AND ANY EXPRESS OR
+//   IMPLIED WARRANTIES, INCLUDING, BUT NOT LIMITED TO, THE IMPLIED WARRANTIES OF MERCHANTABILITY AND
+//   FITNESS FOR A PARTICULAR PURPOSE ARE DISCLAIMED.  IN NO EVENT SHALL THE COPYRIGHT HOLDER OR
+//   CONTRIBUTORS BE LIABLE FOR ANY DIRECT, INDIRECT, INCIDENTAL, SPECIAL, EXEMPLARY, OR CONSEQUENTIAL
+//   DAMAGES (INCLUDING, BUT NOT LIMITED TO, PROCUREMENT OF SUBSTITUTE GOODS OR SERVICES; LOSS OF USE,
+//   DATA, OR PROFITS; OR BUSINESS INTERRUPTION) HOWEVER CAUSED AND ON ANY THEORY OF LIABILITY, WHETHER
+//   IN CONTRACT, STRICT LIABILITY, OR TORT (INCLUDING NEGLIGENCE OR OTHERWISE) ARISING IN ANY WAY OUT OF
+//   THE USE OF THIS SOFTWARE, EVEN IF ADVISED OF THE POSSIBILITY OF SUCH DAMAGE.
+// Data layout, lane mapping, staging, linear algebra and norms in this file are this project's own.
 #ifndef PB200_BDF_TEAM_CUH
 #define PB200_BDF_TEAM_CUH
 
@@ -95,6 +121,7 @@ struct TeamWork {
     int* gidx;
     double* stage;      // host harness: staging area of the sparse triangular solves
     int stage_doubles;  // its capacity (device: shared memory from TEAM_SM_RBUF to the end)
+    int panel_doubles;  // capacity of the generic dense path's panel (device: from TEAM_SM_PANEL to the end)
     // staging buffers: host harness only -- on the device they are derived from the dynamic
     // shared memory base at every use (BdfTeam::panel() ...), so that the compiler knows the
     // address space (LDS/STS instead of generic LD/ST)
@@ -141,7 +168,7 @@ struct TeamWork {
         gidx = perm + T.nx;
     }
     /// panel width that fits `smem_doubles` of staging memory (after rbuf / rowk / piv)
-    static int panel_width(int nx, size_t panel_doubles) {
+    PB_HD static int panel_width(int nx, size_t panel_doubles) {
         int nb = TEAM_NB_MAX;
         while (nb > 1 && (size_t)nx * nb > panel_doubles) nb >>= 1;
         return nb;
@@ -175,10 +202,15 @@ struct BdfTeam {
     double llh_, tout_, saved_t_, dsm_, dsmS_;
     int it_, sim_status_, nstloc_, mxstep_, ncf_, nef_, ncfS_, nefS_, nflag_, dq_;
     bool do_rescale_, undo_, restart_;
+    bool save_, pending_complete_, ahead_;
+    bool fuse_history = true;  // fused history pass between the steps of one CVode call (advance_fused)
+    bool fuse_newton = true;   // sparse path: right-hand sides + forward substitution, backward substitution + update + norm
+    bool b_forwarded_ = false; // w.b already holds the forward-substituted right-hand sides
+    bool fwd_ok_ = false;      // the factors in w.luV are the ones the coming solve uses (no setup pending)
     int fail_, ret_;
     // phase cycle counters (device: clock64 of thread 0's SM; exported in stats[14..15] packed as
     // two 32-bit fields of kilo-cycles each: [14] = inversion panel | inversion update, [15] = solve GEMM | model+rhs)
-    long long cyc_panel, cyc_update, cyc_solve, cyc_rhs, cyc_spfactor, cyc_sptri;
+    long long cyc_panel, cyc_update, cyc_solve, cyc_rhs, cyc_spfactor, cyc_sptri, cyc_hist, cyc_state, cyc_sens, cyc_total;
     PB_HD static long long now() {
 #if defined(__CUDA_ARCH__)
         return clock64();
@@ -379,6 +411,85 @@ struct BdfTeam {
         return bad;
     }
 
+    /// rhs_sens(false) fused with the forward substitution of the sparse solver: the right-hand sides of a
+    /// batch of columns are formed in the staging area (permuted rows, Z[row][column]), substituted there,
+    /// and reach w.b already as  y = L11^-1 b1 | b2' = b2 - L21 y  -- one write of w.b instead of a write, a
+    /// read and a second write.  Returns true if a value is not finite (thread-local; the caller reduces).
+#if defined(__CUDACC__)
+    __host__ __device__ __noinline__
+#endif
+    bool rhs_sens_fwd() {
+        bool bad = false;
+        const double* __restrict__ z0 = w.zn(0);
+        const double* __restrict__ z1 = w.zn(1);
+        const double* __restrict__ ac = w.acor;
+        const double* __restrict__ jc = w.Jcur;
+        const double* __restrict__ dfdp = w.dfdp;
+        const int* __restrict__ jcol = T.jell_col;
+        const int* __restrict__ iord = SP.iord;
+        double* __restrict__ bb = w.b;
+        const int jw = T.jell_w;
+        const int nx = this->nx;
+        // staging area: corrected sensitivity vectors of the batch S[column][row] | right-hand sides Z[row][column]
+        // | factor values
+        tm.sync();
+        int zcap;
+        const double* const V = sp_stage_values(zcap);
+        int CB = zcap / (2 * nx);
+        if (CB < 1) CB = 1;  // (the caller checked that two columns' worth of rows fit)
+        if (CB > ns) CB = ns;
+        double* const S = sp_stage();
+        double* const Z = S + (size_t)CB * nx;
+        for (int cb = 1; cb <= ns; cb += CB) {
+            const int ncb = (ns + 1 - cb < CB) ? ns + 1 - cb : CB;
+            const int nel = ncb * nx;
+            tm.sync();
+            PT_FOR(x, 0, nel) {
+                const int cl = x / nx, i = x - cl * nx;
+                const size_t e = (size_t)(cb + cl) * nx + i;
+                S[(size_t)cl * nx + i] = z0[e] + ac[e];
+            }
+            tm.sync();
+            for (int i0 = 0; i0 < nx; i0 += tm.size()) {  // (whole warps enter: warp_max_int below)
+                const int i = i0 + tm.tid();
+                const bool rowok = i < nx;
+                double jv[TEAM_JW_MAX];
+                int jn[TEAM_JW_MAX];
+                int len = 0;
+                PB_UNROLL
+                for (int t = 0; t < TEAM_JW_MAX; ++t) {
+                    const int j = (rowok && t < jw) ? jcol[t * nx + i] : -1;
+                    jn[t] = j >= 0 ? j : 0;
+                    jv[t] = j >= 0 ? jc[t * nx + i] : 0.0;
+                    if (j >= 0) len = t + 1;
+                }
+                const int wlen = tm.warp_max_int(len);
+                if (!rowok) continue;
+                const size_t zrow = (size_t)iord[i] * CB;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
+                for (int cl = 0; cl < ncb; ++cl) {
+                    const size_t e = (size_t)(cb + cl) * nx + i;
+                    const double* sv = S + (size_t)cl * nx;
+                    double F = dfdp[i + (size_t)w.plist[cb + cl - 1] * nx];
+                    PB_UNROLL
+                    for (int t = 0; t < TEAM_JW_MAX; ++t)
+                        if (t < wlen) F += jv[t] * sv[jn[t]];
+                    if (!PB_FINITE(F)) bad = true;
+                    Z[zrow + cl] = (rl1 * z1[e] + ac[e]) - gamma * F;
+                }
+            }
+            tm.sync();
+            sparse_forward_staged(Z, CB, ncb, V);
+            PT_FOR(x, 0, nel) {
+                const int cl = x / nx, i = x - cl * nx;
+                bb[(size_t)(cb + cl) * nx + i] = Z[(size_t)iord[i] * CB + cl];
+            }
+        }
+        return bad;
+    }
+
     /// Right-hand sides of the columns of `phase` at v = zn[0] + acor:
     /// b = raw ? F : rl1*zn[1] + acor - gamma*F  (cvNlsResidual / cvNlsResidualSensStg)
     PB_HD int rhs(int phase, bool raw) {
@@ -393,9 +504,13 @@ struct BdfTeam {
                 w.b[i] = raw ? F : (rl1 * w.zn(1)[i] + w.acor[i]) - gamma * F;
             }
         } else {
-            bad = rhs_sens(raw);
+            // (sparse solver, no setup pending: right-hand sides and forward substitution in one staging pass)
+            const bool fwd = fuse_newton && lin_sparse && !raw && fwd_ok_ &&
+                             w.stage_doubles - (2 * SP.nV > w.stage_doubles ? 0 : SP.nV) >= 2 * nx;
+            bad = fwd ? rhs_sens_fwd() : rhs_sens(raw);
             nfSe += ns;
             bad = tm.any(bad);
+            b_forwarded_ = fwd && !bad;
         }
         tm.sync();
         cyc_rhs += now() - t_r0;
@@ -445,8 +560,10 @@ struct BdfTeam {
     /// In-place inversion (with row pivoting, order in w.perm) of the dn x dn column-major matrix in w.A
     PB_HD int invert_dense() {
         double* const A = w.A;
-        const int NB = w.NB;
         const int nx = dn;  // (shadows the member: the dense dimension)
+        // panel width: as wide as the staging memory allows (host harness: w.NB > 0 asks for a width)
+        int NB = TeamWork::panel_width(nx, (size_t)w.panel_doubles);
+        if (w.NB > 0 && w.NB < NB) NB = w.NB;
         PT_FOR(i, 0, nx) w.perm[i] = i;
         tm.sync();
 #if defined(__CUDA_ARCH__)
@@ -710,16 +827,24 @@ struct BdfTeam {
             }
 #pragma unroll
             for (int c = 0; c < NB; ++c) xs[c * 512 + i] = prow[c];
-            __syncwarp();
+            // nx <= 256: only half of the warps own rows -- TWO warps then share a 32-row group and take
+            // every other column group of the update (rows 256.. of the ring slots are free for the second)
+            const bool split = nx <= 256;
+            if (split) __syncthreads();
+            else __syncwarp();
             const int lane = i & 31, lq = lane & 3, lr = lane >> 2;
-            const int rbase = (i & ~31) + lr;  // row of m-tile 0 this lane's fragments belong to
+            const int wrow0 = split ? ((i >> 5) & 7) * 32 : (i & ~31);  // first row of this warp's row group
+            const int gstep = split ? 2 : 1, goff = split ? (i >> 8) : 0;
+            const int rslot = split ? 256 * (i >> 8) : 0;                // row offset of this warp inside a ring slot
+            const int rbase = wrow0 + lr;  // row of m-tile 0 this lane's fragments belong to
             double wfr[4][NB / 4];
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) {
 #pragma unroll
                 for (int ks = 0; ks < NB / 4; ++ks) wfr[mt][ks] = xs[(4 * ks + lq) * 512 + rbase + 8 * mt];
             }
-            __syncwarp();  // the ring below reuses this staging area
+            if (split) __syncthreads();  // the ring below reuses this staging area
+            else __syncwarp();
             // ---- rank-nb update of the other columns on the FP64 tensor cores:
             //      C(32 rows of the warp x 8 columns) = C' + W(32 x nb) * R(nb x 8) per column group
             const int nchunks = (nx + TEAM_CW - 1) / TEAM_CW;
@@ -751,12 +876,11 @@ struct BdfTeam {
             // copy, which ran at about one 8-byte element per clock per SM); a lane then reads its
             // fragment elements from what the warp copied, after __syncwarp.
             const bool wide = (nx & 1) == 0;
-            const int wrow0 = i & ~31;  // first row of this warp
             constexpr int PF = 10;      // column groups the L2 prefetch runs ahead of the ring
             auto issue = [&](int g) {
                 __syncwarp();  // the slot written below was read by the warp in the previous trip
                 if (g < ngroups) {
-                    double* slot = xs + (size_t)((g % ST) * GC) * TEAM_XCS;
+                    double* slot = xs + (size_t)(((g / gstep) % ST) * GC) * TEAM_XCS + rslot;
                     if (wide) {
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -790,7 +914,7 @@ struct BdfTeam {
                 pb_cp_async_commit();
             };
 #pragma unroll
-            for (int g = 0; g < ST - 1; ++g) issue(g);
+            for (int g = 0; g < ST - 1; ++g) issue(goff + g * gstep);
             for (int ch = 0; ch < nchunks; ++ch) {
                 const double* const cur = sm + ((ch & 1) ? TEAM_SM_RBUF1 : TEAM_SM_RBUF);
                 double* const nxt = sm + ((ch & 1) ? TEAM_SM_RBUF : TEAM_SM_RBUF1);
@@ -807,13 +931,13 @@ struct BdfTeam {
                         pb_cp_async8(nxt + r_pos(e), ok ? A + (k0 + kk) + (size_t)j * nx : A, ok ? 8 : 0);
                     }
                 }
-                for (int gl = 0; gl < TEAM_CW / GC; ++gl) {
+                for (int gl = goff; gl < TEAM_CW / GC; gl += gstep) {
                     const int g = ch * (TEAM_CW / GC) + gl;
                     if (g >= ngroups) break;
-                    issue(g + ST - 1);
+                    issue(g + (ST - 1) * gstep);
                     pb_cp_async_wait<ST - 1>();
                     __syncwarp();  // pieces copied by the other lanes of the warp
-                    const double* src = xs + (size_t)((g % ST) * GC) * TEAM_XCS + (2 * lq) * TEAM_XCS + rbase;
+                    const double* src = xs + (size_t)(((g / gstep) % ST) * GC) * TEAM_XCS + (2 * lq) * TEAM_XCS + rslot + rbase;
                     double c[4][2];
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt) {
@@ -878,8 +1002,13 @@ struct BdfTeam {
         constexpr int GK = 16, ST = TEAM_ST;  // 16 k's = four k-steps per ring group
         double* const xs = sm + TEAM_SM_XSTAGE;
         const int ngk = (nx + GK - 1) / GK;
-        for (int half = 0; half < 2; ++half) {
-            const int rbase = (i & ~31) + 16 * half + lr;
+        // nx <= 256: only half of the warps own rows -- two warps then share a 32-row group, one half
+        // (16 rows) each, and the matrix is swept once instead of twice
+        const bool split = nx <= 256;
+        const int nsweeps = split ? 1 : 2;
+        for (int sweep = 0; sweep < nsweeps; ++sweep) {
+            const int half = split ? (i >> 8) : sweep;
+            const int rbase = (split ? ((i >> 5) & 7) * 32 : (i & ~31)) + 16 * half + lr;
             double c[2][NT][2];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
@@ -1148,100 +1277,152 @@ struct BdfTeam {
     /// of the Schur block:  forward substitution with L (sparse rows in the staging area, all columns
     /// of a batch side by side: one warp per row, lanes over the columns), Schur right-hand side,
     /// dense GEMM with S^-1, backward substitution with U.
-    PB_HD void solve_sparse(int cmin, int cmax, double nsc) {
-        const int n1 = SP.n1, m = SP.m, nx = this->nx;
+    /// The factor values of the sparse part, copied to the END of the staging area for the duration of one
+    /// substitution pass (every entry is read once per column batch, in a dependent chain per row: from
+    /// shared memory that chain costs tens of cycles per entry instead of an L2 round trip).  zcap receives
+    /// what is left for the column batches.  The caller synchronises before the first use.
+    PB_HD const double* sp_stage_values(int& zcap) {
+        zcap = w.stage_doubles;
+        if (2 * SP.nV > w.stage_doubles) return w.luV;  // (too large: read through the caches)
+        double* const Vs = sp_stage() + (w.stage_doubles - SP.nV);
+        const double* __restrict__ src = w.luV;
+        PT_FOR(e, 0, SP.nV) Vs[e] = src[e];
+        zcap = w.stage_doubles - SP.nV;
+        return Vs;
+    }
+
+    /// forward levels + Schur rows on a staged batch Z[row][column] (stride bc) of nb columns
+    PB_HD void sparse_forward_staged(double* Z, int bc, int nb, const double* V) {
+        const int n1 = SP.n1, m = SP.m;
+        // one thread per (row of the level, column): consecutive threads take consecutive columns of a row
+        // (same factor entries: broadcast; consecutive words of Z: conflict-free)
+        for (int l = 1; l < SP.n_flev; ++l) {  // (level 0: rows without L entries)
+            const int r0 = SP.flev_ptr[l], nr = SP.flev_ptr[l + 1] - r0;
+            for (int t = tm.tid(); t < nr * nb; t += tm.size()) {
+                const int rr = t / nb, cl = t - rr * nb;
+                const int r = SP.flev_rows[r0 + rr];
+                double acc = Z[(size_t)r * bc + cl];
+                const int e1 = SP.Lr_ptr[r + 1];
+                for (int e = SP.Lr_ptr[r]; e < e1; ++e) acc -= V[n1 + e] * Z[(size_t)SP.Lr_col[e] * bc + cl];
+                Z[(size_t)r * bc + cl] = acc;
+            }
+            tm.sync();
+        }
+        // Schur rows: gather from the finished y
+        for (int t = tm.tid(); t < m * nb; t += tm.size()) {
+            const int rr = t / nb, cl = t - rr * nb;
+            const int r = n1 + rr;
+            double acc = Z[(size_t)r * bc + cl];
+            const int e1 = SP.Lr_ptr[r + 1];
+            for (int e = SP.Lr_ptr[r]; e < e1; ++e) acc -= V[n1 + e] * Z[(size_t)SP.Lr_col[e] * bc + cl];
+            Z[(size_t)r * bc + cl] = acc;
+        }
+        tm.sync();
+    }
+
+    /// Forward substitution of the columns [cmin, cmax] of w.b in place: y = L11^-1 b1 in the sparse rows,
+    /// b2' = b2 - L21 y in the Schur rows.  A batch of columns, ALL nx rows in permuted order, lives in the
+    /// staging area as Z[row][column]: global memory is only touched by coalesced column sweeps (lanes along
+    /// the original row index), the substitution runs in shared memory with the lanes along the columns.
+    PB_HD void sparse_forward(int cmin, int cmax) {
+        const int nx = this->nx;
         const int ncols = cmax - cmin + 1;
-        const double* __restrict__ V = w.luV;
-        const int* __restrict__ ord = SP.ord;
+        const int* __restrict__ iord = SP.iord;
         double* const Z = sp_stage();
         double* const b = w.b;
-        double* const scr = w.scr;
-        int bc_max = w.stage_doubles / nx;
+        tm.sync();
+        int zcap;
+        const double* const V = sp_stage_values(zcap);
+        int bc_max = zcap / nx;
         if (bc_max < 1) bc_max = 1;
         const int nbatch = (ncols + bc_max - 1) / bc_max;
         const int bc = (ncols + nbatch - 1) / nbatch;
-        const int nwt = (bc + Team::WARP - 1) / Team::WARP;  // warp tasks per row
-        const long long t_s0 = now();
-        // ---- forward: y = L11^-1 b1, b2' = b2 - L21 y
-        for (int c0 = cmin; c0 <= cmax; c0 += bc) {
-            const int nb = (cmax + 1 - c0 < bc) ? cmax + 1 - c0 : bc;
-            tm.sync();
-            PT_FOR(x, 0, n1 * nb) {
-                const int cl = x / n1, r = x - cl * n1;
-                Z[(size_t)r * bc + cl] = b[ord[r] + (size_t)(c0 + cl) * nx];
-            }
-            tm.sync();
-            for (int l = 0; l < SP.n_flev; ++l) {
-                const int r0 = SP.flev_ptr[l], nr = SP.flev_ptr[l + 1] - r0;
-                if (l > 0) {  // (level 0: rows without L entries)
-                    for (int task = tm.warp(); task < nr * nwt; task += tm.nwarps()) {
-                        const int r = SP.flev_rows[r0 + task / nwt];
-                        const int cl = (task % nwt) * Team::WARP + tm.lane();
-                        if (cl < nb) {
-                            double acc = Z[(size_t)r * bc + cl];
-                            const int e1 = SP.Lr_ptr[r + 1];
-                            for (int e = SP.Lr_ptr[r]; e < e1; ++e) acc -= V[n1 + e] * Z[(size_t)SP.Lr_col[e] * bc + cl];
-                            Z[(size_t)r * bc + cl] = acc;
-                        }
-                    }
-                    tm.sync();
-                }
-            }
-            // Schur rows (gather from the finished y) and write-back of y
-            for (int task = tm.warp(); task < m * nwt; task += tm.nwarps()) {
-                const int r = n1 + task / nwt;
-                const int cl = (task % nwt) * Team::WARP + tm.lane();
-                if (cl < nb) {
-                    const size_t g = ord[r] + (size_t)(c0 + cl) * nx;
-                    double acc = b[g];
-                    const int e1 = SP.Lr_ptr[r + 1];
-                    for (int e = SP.Lr_ptr[r]; e < e1; ++e) acc -= V[n1 + e] * Z[(size_t)SP.Lr_col[e] * bc + cl];
-                    b[g] = acc;
-                }
-            }
-            PT_FOR(x, 0, n1 * nb) {
-                const int cl = x / n1, r = x - cl * n1;
-                b[ord[r] + (size_t)(c0 + cl) * nx] = Z[(size_t)r * bc + cl];
-            }
-        }
-        tm.sync();
-        // ---- dense: x2 = S^-1 b2' (rows gathered through gidx, written to the Schur rows of scr)
-        const long long t_d0 = now();
-        if (m > 0) solve_dense(cmin, cmax, 1.0);
-        tm.sync();
-        const long long t_d1 = now();
-        // ---- backward: x1 = U11^-1 (y - U12 x2); scaled results to scr
-        const int nU0 = n1 + SP.nnzL;
         for (int c0 = cmin; c0 <= cmax; c0 += bc) {
             const int nb = (cmax + 1 - c0 < bc) ? cmax + 1 - c0 : bc;
             tm.sync();
             PT_FOR(x, 0, nx * nb) {
-                const int cl = x / nx, r = x - cl * nx;
-                const size_t g = ord[r] + (size_t)(c0 + cl) * nx;
+                const int cl = x / nx, i = x - cl * nx;
+                Z[(size_t)iord[i] * bc + cl] = b[i + (size_t)(c0 + cl) * nx];
+            }
+            tm.sync();
+            sparse_forward_staged(Z, bc, nb, V);
+            PT_FOR(x, 0, nx * nb) {
+                const int cl = x / nx, i = x - cl * nx;
+                b[i + (size_t)(c0 + cl) * nx] = Z[(size_t)iord[i] * bc + cl];
+            }
+        }
+        tm.sync();
+    }
+
+    /// Backward substitution x1 = U11^-1 (y - U12 x2) of the columns [cmin, cmax] (y in the sparse rows of
+    /// w.b, x2 in the Schur rows of w.scr).  update = false: scr = nsc * x.  update = true: the Newton
+    /// update is fused -- acor += nsc * x and the WRMS norm of nsc * x (maximum over the columns) is
+    /// returned; scr is not written.
+    PB_HD double sparse_backward(int cmin, int cmax, double nsc, bool update) {
+        const int n1 = SP.n1, nx = this->nx;
+        const int ncols = cmax - cmin + 1;
+        const int* __restrict__ iord = SP.iord;
+        double* const Z = sp_stage();
+        const double* const b = w.b;
+        double* const scr = w.scr;
+        double* const acor = w.acor;
+        const double* const ewt = w.ewt;
+        tm.sync();
+        int zcap;
+        const double* const V = sp_stage_values(zcap);
+        int bc_max = zcap / nx;
+        if (bc_max < 1) bc_max = 1;
+        const int nbatch = (ncols + bc_max - 1) / bc_max;
+        const int bc = (ncols + nbatch - 1) / nbatch;
+        const int nU0 = n1 + SP.nnzL;
+        double loc = 0.0;
+        for (int c0 = cmin; c0 <= cmax; c0 += bc) {
+            const int nb = (cmax + 1 - c0 < bc) ? cmax + 1 - c0 : bc;
+            tm.sync();
+            PT_FOR(x, 0, nx * nb) {
+                const int cl = x / nx, i = x - cl * nx;
+                const int r = iord[i];
+                const size_t g = i + (size_t)(c0 + cl) * nx;
                 Z[(size_t)r * bc + cl] = (r < n1) ? b[g] : scr[g];
             }
             tm.sync();
             for (int l = 0; l < SP.n_blev; ++l) {
                 const int r0 = SP.blev_ptr[l], nr = SP.blev_ptr[l + 1] - r0;
-                for (int task = tm.warp(); task < nr * nwt; task += tm.nwarps()) {
-                    const int r = SP.blev_rows[r0 + task / nwt];
-                    const int cl = (task % nwt) * Team::WARP + tm.lane();
-                    if (cl < nb) {
-                        double acc = Z[(size_t)r * bc + cl];
-                        const int e1 = SP.Ur_ptr[r + 1];
-                        for (int e = SP.Ur_ptr[r]; e < e1; ++e) acc -= V[nU0 + e] * Z[(size_t)SP.Ur_col[e] * bc + cl];
-                        Z[(size_t)r * bc + cl] = acc * V[r];
-                    }
+                for (int t = tm.tid(); t < nr * nb; t += tm.size()) {
+                    const int rr = t / nb, cl = t - rr * nb;
+                    const int r = SP.blev_rows[r0 + rr];
+                    double acc = Z[(size_t)r * bc + cl];
+                    const int e1 = SP.Ur_ptr[r + 1];
+                    for (int e = SP.Ur_ptr[r]; e < e1; ++e) acc -= V[nU0 + e] * Z[(size_t)SP.Ur_col[e] * bc + cl];
+                    Z[(size_t)r * bc + cl] = acc * V[r];
                 }
                 tm.sync();
             }
-            PT_FOR(x, 0, nx * nb) {
-                const int cl = x / nx, r = x - cl * nx;
-                scr[ord[r] + (size_t)(c0 + cl) * nx] = nsc * Z[(size_t)r * bc + cl];
+            if (!update) {
+                PT_FOR(x, 0, nx * nb) {
+                    const int cl = x / nx, i = x - cl * nx;
+                    scr[i + (size_t)(c0 + cl) * nx] = nsc * Z[(size_t)iord[i] * bc + cl];
+                }
+            } else {
+                // one warp per column (coalesced, and the column's sum of squares is a warp reduction)
+                for (int cl = tm.warp(); cl < nb; cl += tm.nwarps()) {
+                    double sq = 0.0;
+                    PT_UNROLL4
+                    for (int i = tm.lane(); i < nx; i += Team::WARP) {
+                        const size_t g = i + (size_t)(c0 + cl) * nx;
+                        const double d = nsc * Z[(size_t)iord[i] * bc + cl];
+                        acor[g] += d;
+                        const double v = d * ewt[g];
+                        sq += v * v;
+                    }
+                    sq = tm.warp_sum(sq);
+                    if (sq > loc) loc = sq;
+                }
             }
         }
         tm.sync();
-        cyc_sptri += (now() - t_s0) - (t_d1 - t_d0);
+        if (!update) return 0.0;
+        return sqrt(tm.max(loc) / (double)nx);
     }
 
     /// scr = nsc * (dense inverse) * b for the columns [cmin, cmax] (the whole matrix, or the Schur block
@@ -1367,10 +1548,25 @@ struct BdfTeam {
     PB_HD double newton_update(int cmin, int cmax) {
         const double nsc = (gamrat != 1.0) ? -2.0 / (1.0 + gamrat) : -1.0;
         const long long t_s0 = now();
-        if (lin_sparse) solve_sparse(cmin, cmax, nsc);
-        else solve_dense(cmin, cmax, nsc);
-        tm.sync();
-        cyc_solve += now() - t_s0;
+        if (lin_sparse) {
+            // sparse factors + inverse of the Schur block (forward substitution already done by the fused
+            // right-hand side of the sensitivity phase)
+            if (!b_forwarded_) sparse_forward(cmin, cmax);
+            b_forwarded_ = false;
+            const long long t_d0 = now();
+            if (SP.m > 0) solve_dense(cmin, cmax, 1.0);
+            tm.sync();
+            const long long t_d1 = now();
+            const double del = sparse_backward(cmin, cmax, nsc, fuse_newton);
+            const long long t_e = now();
+            cyc_sptri += (t_e - t_s0) - (t_d1 - t_d0);
+            cyc_solve += t_e - t_s0;
+            if (fuse_newton) return del;
+        } else {
+            solve_dense(cmin, cmax, nsc);
+            tm.sync();
+            cyc_solve += now() - t_s0;
+        }
         {
             constexpr int U = 4;
             const int e1 = (cmax + 1) * nx;
@@ -1510,14 +1706,13 @@ struct BdfTeam {
         nscon = 0;
         tm.sync();
     }
-    /// cvAdjustOrder -> cvIncreaseBDF / cvDecreaseBDF
-    PB_HD void adjust_order(int deltaq) {
-        if ((q == 2) && (deltaq != 1)) return;
-        double lc[cv::L_MAX + 1];
+    /// cvAdjustOrder -> cvIncreaseBDF / cvDecreaseBDF: the polynomial coefficients (scalars).  Returns
+    /// false if the order change leaves the history untouched (q == 2, decrease).
+    PB_HD bool adjust_order_coeffs(int deltaq, double* lc, double& A1, int& src, int& jmax) const {
+        if ((q == 2) && (deltaq != 1)) return false;
         for (int i = 0; i <= cv::L_MAX; ++i) lc[i] = 0.0;
         lc[2] = 1.0;
-        int src, jmax;
-        double A1 = 0.0;
+        A1 = 0.0;
         if (deltaq == 1) {
             double alpha1 = 1.0, prod = 1.0, xiold = 1.0, alpha0 = -1.0;
             double hsum = hscale;
@@ -1544,6 +1739,12 @@ struct BdfTeam {
             src = q;
             jmax = q - 1;
         }
+        return true;
+    }
+    PB_HD void adjust_order(int deltaq) {
+        double lc[cv::L_MAX + 1], A1;
+        int src, jmax;
+        if (!adjust_order_coeffs(deltaq, lc, A1, src, jmax)) return;
         tm.sync();
         PT_FOR_ELEMS(e) {
             if (deltaq == 1) w.zn(src)[e] = A1 * w.zn(cv::Q_MAX)[e];
@@ -1570,7 +1771,9 @@ struct BdfTeam {
         bool top = true;
         int m_it = 0;
         for (;;) {
+            fwd_ok_ = (phase == PH_SENS) && !setup_pending;
             int ret = rhs(phase, false);
+            fwd_ok_ = false;
             if (ret != 0 && top) return ret;
             if (ret == 0 && setup_pending) {
                 if (jbad) convfail = cv::FAIL_BAD_J;
@@ -1634,8 +1837,12 @@ struct BdfTeam {
     }
 
     // ---------------------------------------------------------------- step control
-    /// cvCompleteStep
-    PT_NOINLINE void complete_step() {
+    /// cvCompleteStep, scalar part.  The element-wise part (zn[j] += l[j] * acor) is DEFERRED
+    /// (pending_complete_): when another step of the same CVode call follows it is fused with that
+    /// step's error weights, order change, rescaling and prediction into ONE pass over the history
+    /// (advance_fused); otherwise complete_elements() runs it alone.  The norms that cvPrepareNextStep and
+    /// cvBDFStab take of the completed history are formed as zn[j] + l[j] * acor on the fly.
+    PB_HD void complete_step_scalars() {
         nst++;
         nscon++;
         qsum += q;
@@ -1643,7 +1850,13 @@ struct BdfTeam {
         if ((q == 1) && (nst > 1)) tau[2] = tau[1];
         tau[1] = h;
         qwait--;
-        const bool save = (qwait == 1) && (q != cv::Q_MAX);
+        save_ = (qwait == 1) && (q != cv::Q_MAX);
+        if (save_) saved_tq5 = tq5;
+        pending_complete_ = true;
+    }
+    /// cvCompleteStep, element-wise part alone
+    PT_NOINLINE void complete_elements() {
+        const bool save = save_;
         tm.sync();
         {
             constexpr int U = 4;
@@ -1677,7 +1890,144 @@ struct BdfTeam {
             }
         }
         tm.sync();
-        if (save) saved_tq5 = tq5;
+        pending_complete_ = false;
+    }
+
+    /// The step that was just accepted is followed by another one of the same CVode call: ONE pass over
+    /// the history does, per element and in CVODES' order of operations,
+    ///   cvCompleteStep (zn[j] += l[j] acor) -> error weights of the new state (cvEwtSet; the CVode loop's
+    ///   checks) -> cvAdjustOrder -> cvRescale -> cvPredict
+    /// instead of five separate sweeps (7 + 2 + 2 + 10 + 11 array transfers at q = 5 become 13).  Scalars
+    /// (step_begin, q, h, tn) are advanced here as attempt_predict would.  Returns 0 or a failure status.
+    PT_NOINLINE int advance_fused() {
+        const long long t_h0 = now();
+        const int r = advance_fused_();
+        cyc_hist += now() - t_h0;
+        return r;
+    }
+    PT_NOINLINE int advance_fused_() {
+        step_begin();
+        // scalars of the order change / rescaling, from the state attempt_predict would see
+        double lc[cv::L_MAX + 1], A1 = 0.0;
+        int src = 0, jmax = 0;
+        const int dq = dq_;
+        const bool adj = (dq != 0) && adjust_order_coeffs(dq, lc, A1, src, jmax);
+        const int q_old = q;
+        const int q_new = q + dq;
+        const bool resc = do_rescale_;
+        const double eta_ = eta;
+        const bool save = save_;
+        bool ok = true;
+        double s_all = 0.0;
+        tm.sync();
+        {
+            constexpr int U = 4;
+            const double* const acor = w.acor;
+            const int e1 = nx * ncol;
+            double* const zb = w.znbase;
+            double* const ew = w.ewt;
+            const size_t nxc = w.nxc;
+            const double rtol = opt.rtol, atol = opt.atol;
+            double lr[cv::L_MAX], lcr[cv::L_MAX + 1];
+            PB_UNROLL
+            for (int j = 0; j < cv::L_MAX; ++j) lr[j] = l[j];
+            PB_UNROLL
+            for (int j = 0; j <= cv::L_MAX; ++j) lcr[j] = adj ? lc[j] : 0.0;
+            PT_FOR_BATCH(eb, 0, e1, U) {
+                double z[U][cv::L_MAX], a[U];
+                PB_UNROLL
+                for (int u = 0; u < U; ++u) {
+                    const int e = eb + u * tm.size();
+                    a[u] = (e < e1) ? acor[e] : 0.0;
+                    PB_UNROLL
+                    for (int j = 0; j < cv::L_MAX; ++j) z[u][j] = (j <= q_old && e < e1) ? zb[j * nxc + e] : 0.0;
+                    // order increase reads zn[Q_MAX] (saved correction); q_old < Q_MAX then, so slot Q_MAX is free
+                    if (adj && dq == 1 && e < e1) z[u][cv::Q_MAX] = zb[cv::Q_MAX * nxc + e];
+                }
+                PB_UNROLL
+                for (int u = 0; u < U; ++u) {
+                    const int e = eb + u * tm.size();
+                    if (e >= e1) continue;
+                    // cvCompleteStep
+                    const double zq = z[u][cv::Q_MAX];
+                    PB_UNROLL
+                    for (int j = 0; j < cv::L_MAX; ++j)
+                        if (j <= q_old) z[u][j] = z[u][j] + lr[j] * a[u];
+                    if (adj && dq == 1 && q_old < cv::Q_MAX) z[u][cv::Q_MAX] = zq;  // (not a history column yet)
+                    if (save) zb[cv::Q_MAX * nxc + e] = a[u];
+                    // cvEwtSet on the new state
+                    const double wv = rtol * fabs(z[u][0]) + atol;
+                    ok = ok && (wv > 0.0);
+                    const double ewv = 1.0 / wv;
+                    ew[e] = ewv;
+                    const double zw = z[u][0] * ewv;
+                    s_all += zw * zw;
+                    // cvAdjustOrder
+                    if (adj) {
+                        if (dq == 1) {
+                            const double zs = A1 * zq;
+                            PB_UNROLL
+                            for (int j = 0; j < cv::L_MAX; ++j) {
+                                if (j == src) z[u][j] = zs;
+                                if (j >= 2 && j <= jmax) z[u][j] += lcr[j] * zs;
+                            }
+                        } else {
+                            double zs = 0.0;
+                            PB_UNROLL
+                            for (int j = 0; j < cv::L_MAX; ++j)
+                                if (j == src) zs = z[u][j];
+                            PB_UNROLL
+                            for (int j = 0; j < cv::L_MAX; ++j)
+                                if (j >= 2 && j <= jmax) z[u][j] += lcr[j] * zs;
+                        }
+                    }
+                    // cvRescale
+                    if (resc) {
+                        double factor = eta_;
+                        PB_UNROLL
+                        for (int j = 1; j < cv::L_MAX; ++j) {
+                            if (j <= q_new) z[u][j] = z[u][j] * factor;
+                            factor *= eta_;
+                        }
+                    }
+                    // cvPredict
+                    PB_UNROLL
+                    for (int k = 1; k <= cv::Q_MAX; ++k) {
+                        PB_UNROLL
+                        for (int j = cv::Q_MAX; j >= k; --j)
+                            if (j <= q_new && k <= q_new) z[u][j - 1] += z[u][j];
+                    }
+                    PB_UNROLL
+                    for (int j = 0; j < cv::L_MAX; ++j)
+                        if (j <= q_new) zb[j * nxc + e] = z[u][j];
+                }
+            }
+        }
+        tm.sync();
+        pending_complete_ = false;
+        if (tm.any(!ok)) return SIM_ILL_INPUT;
+        // CVode's "too much accuracy requested" check takes max over the columns of the per-column WRMS norm
+        // of the new state; the sum over ALL columns formed above bounds it from above and is far below the
+        // threshold (|y| ewt < 1/rtol) for any rtol above a few ulps
+        s_all = tm.sum(s_all);
+        if (cv::UROUND * sqrt(s_all / (double)nx) > 1.0) return SIM_TOO_MUCH_ACC;
+        // scalars, as attempt_predict advances them
+        if (dq != 0) {
+            q += dq;
+            L = q + 1;
+            qwait = L;
+            dq_ = 0;
+        }
+        if (resc) {
+            h = hscale * eta_;
+            hscale = h;
+            nscon = 0;
+            do_rescale_ = false;
+        }
+        tn += h;
+        if (tstopset && ((tn - tstop) * h > 0.0)) tn = tstop;
+        ahead_ = true;
+        return 0;
     }
 
     /// cvPrepareNextStep with cvSetEta, cvComputeEtaqm1 / cvComputeEtaqp1 / cvChooseEta
@@ -1697,7 +2047,8 @@ struct BdfTeam {
             const int ecmax = errtest_cmax();
             etaqm1 = 0.0;
             if (q > 1) {
-                double ddn = wnorm1(0, ecmax, w.zn(q));
+                // (the completed zn[q] = zn[q] + l[q] * acor: cvCompleteStep's element-wise part is deferred)
+                double ddn = pending_complete_ ? wnorm(0, ecmax, w.zn(q), 1.0, w.acor, l[q]) : wnorm1(0, ecmax, w.zn(q));
                 ddn = ddn * tq1;
                 etaqm1 = 1.0 / (pow(cv::BIAS1 * ddn, 1.0 / (double)q) + cv::ADDON);
             }
@@ -1875,8 +2226,8 @@ struct BdfTeam {
     /// cvBDFStab
     PB_HD void bdf_stab() {
         if (q >= 3) {
-            const double n0 = wnorm1(0, 0, w.zn(q));
-            const double n1 = wnorm1(0, 0, w.zn(q - 1));
+            const double n0 = pending_complete_ ? wnorm(0, 0, w.zn(q), 1.0, w.acor, l[q]) : wnorm1(0, 0, w.zn(q));
+            const double n1 = pending_complete_ ? wnorm(0, 0, w.zn(q - 1), 1.0, w.acor, l[q - 1]) : wnorm1(0, 0, w.zn(q - 1));
             int factorial = 1;
             for (int i = 1; i <= q - 1; ++i) factorial *= i;
             const double sq = factorial * q * (q + 1) * acnrm / fmax(tq5, cv::TINY);
@@ -1928,6 +2279,13 @@ struct BdfTeam {
 
     /// order / step-size adjustment, (after a failed attempt: restore,) prediction, coefficients
     PB_HD int attempt_predict() {
+        if (ahead_) {  // advance_fused has done order change, rescaling and prediction of this attempt
+            ahead_ = false;
+            cvset();
+            fail_ = 0;
+            ret_ = 0;
+            return 0;
+        }
         for (;;) {
             if (undo_) {
                 tn = saved_t_;
@@ -1948,13 +2306,19 @@ struct BdfTeam {
                     dq_ = 0;
                 }
                 if (do_rescale_) {
+                    const long long t_h0 = now();
                     rescale();
+                    cyc_hist += now() - t_h0;
                     do_rescale_ = false;
                 }
                 tn += h;
                 if (tstopset && ((tn - tstop) * h > 0.0)) tn = tstop;
             }
-            shift_history(undo_ ? -1.0 : 1.0);
+            {
+                const long long t_h0 = now();
+                shift_history(undo_ ? -1.0 : 1.0);
+                cyc_hist += now() - t_h0;
+            }
             if (!undo_) break;
             undo_ = false;
         }
@@ -1965,6 +2329,12 @@ struct BdfTeam {
     }
 
     PB_HD void attempt_correct(int phase) {
+        const long long t_c0 = now();
+        attempt_correct_(phase);
+        if (phase == PH_STATE) cyc_state += now() - t_c0;
+        else cyc_sens += now() - t_c0;
+    }
+    PB_HD void attempt_correct_(int phase) {
         if (phase == PH_SENS) {
             if (fail_ || !sensi) return;
             ncf_ = nef_ = 0;
@@ -1992,7 +2362,8 @@ struct BdfTeam {
         const int fail = fail_;
         const int ret = ret_;
         if (fail == 0) {
-            complete_step();
+            complete_step_scalars();
+            if (!fuse_history) complete_elements();
             prepare_next_step(dsm_);
             if (opt.stldet) bdf_stab();
             etamax = (nst <= cv::SMALL_NST) ? cv::ETA_MAX_ES : cv::ETA_MAX_GS;
@@ -2222,6 +2593,7 @@ struct BdfTeam {
         jcur = jcurNLS = jcurNLSS = false;
         tstopset = false; tstop = 0.0;
         nfe = nsetups = nje = nni = nniS = nfSe = netf = netfS = ncfn = ncfnS = nor = qsum = 0;
+        save_ = pending_complete_ = ahead_ = false;
         nfallback = 0;
         dn = nx;
         lin_sparse = false;
@@ -2229,7 +2601,8 @@ struct BdfTeam {
         it_ = 0;
         sim_status_ = SIM_SUCCESS;
         fail_ = ret_ = 0;
-        cyc_panel = cyc_update = cyc_solve = cyc_rhs = cyc_spfactor = cyc_sptri = 0;
+        cyc_panel = cyc_update = cyc_solve = cyc_rhs = cyc_spfactor = cyc_sptri = cyc_hist = cyc_state = cyc_sens = 0;
+        cyc_total = now();
         tm.sync();
     }
 
@@ -2249,12 +2622,14 @@ struct BdfTeam {
                 int r = cvode_begin(tout_);
                 if (r < 0) return finish(r);
                 while (r != cv::TSTOP_RETURN) {
-                    // top of the CVode step loop
-                    if (nst > 0 && !ewt_set()) return finish(SIM_ILL_INPUT);
-                    if (nstloc_ >= mxstep_) return finish(SIM_TOO_MUCH_WORK);
-                    const double nrm = wnorm1(0, errtest_cmax(), w.zn(0));
-                    if (cv::UROUND * nrm > 1.0) return finish(SIM_TOO_MUCH_ACC);
-                    step_begin();
+                    // top of the CVode step loop (after a fused advance its checks are already done)
+                    if (!ahead_) {
+                        if (nst > 0 && !ewt_set()) return finish(SIM_ILL_INPUT);
+                        if (nstloc_ >= mxstep_) return finish(SIM_TOO_MUCH_WORK);
+                        const double nrm = wnorm1(0, errtest_cmax(), w.zn(0));
+                        if (cv::UROUND * nrm > 1.0) return finish(SIM_TOO_MUCH_ACC);
+                        step_begin();
+                    }
                     for (;;) {
                         int a = attempt_predict();
                         if (a < 0) return finish(a);
@@ -2276,6 +2651,17 @@ struct BdfTeam {
                         eta = hprime / h;
                     }
                     if ((tn - tout_) * h >= 0.0) break;
+                    // another step of this CVode call follows: complete this one and set up the next in one pass
+                    if (pending_complete_) {
+                        if (nstloc_ >= mxstep_) return finish(SIM_TOO_MUCH_WORK);
+                        const int af = advance_fused();
+                        if (af < 0) return finish(af);
+                    }
+                }
+                if (pending_complete_) {  // the output time is reached: the corrected history
+                    const long long t_h0 = now();
+                    complete_elements();
+                    cyc_hist += now() - t_h0;
                 }
             }
 #if defined(PB200_HOST_TRACE)
@@ -2306,7 +2692,8 @@ struct BdfTeam {
         s[15] = ((cyc_solve >> 10) << 32) | ((cyc_rhs >> 10) & 0xffffffffll);
         s[STAT_NFALLBACK] = nfallback;
         s[STAT_CYC_SPARSE] = ((cyc_spfactor >> 10) << 32) | ((cyc_sptri >> 10) & 0xffffffffll);
-        s[18] = s[19] = 0;
+        s[18] = ((cyc_hist >> 10) << 32) | ((cyc_state >> 10) & 0xffffffffll);
+        s[19] = ((cyc_sens >> 10) << 32) | (((now() - cyc_total) >> 10) & 0xffffffffll);
     }
 #undef PT_FOR
 #undef PT_FOR_ELEMS

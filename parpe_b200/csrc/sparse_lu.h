@@ -59,15 +59,20 @@ struct SparseLU {
     const int* s_diag;  // 1: diagonal entry of the matrix (identity contributes 1)
     const int* s_pptr;  // [n_starg + 1], pairs continue in p_l / p_u
     // row-wise views for the triangular solves
+    // (16-bit column / row numbers: nx < 65536; the team kernel keeps these tables in shared memory)
     const int* Lr_ptr;  // [nx + 1] L entries of permuted row r (columns k < min(r, n1)); value at V[n1 + e]
-    const int* Lr_col;
+    const unsigned short* Lr_col;
     const int* Ur_ptr;  // [n1 + 1] strict-upper entries of row r < n1; value at V[n1 + nnzL + e]
-    const int* Ur_col;
+    const unsigned short* Ur_col;
     int n_flev, n_blev;
     const int* flev_ptr;   // forward levels over the sparse rows
-    const int* flev_rows;
+    const unsigned short* flev_rows;
     const int* blev_ptr;   // backward levels
-    const int* blev_rows;
+    const unsigned short* blev_rows;
+    /// bytes of the solve tables (row pointers + 16-bit indices), the part worth keeping in shared memory
+    int solve_table_bytes() const {
+        return 4 * ((nx + 1) + (n1 + 1) + (n_flev + 1) + (n_blev + 1)) + 2 * (nnzL + nnzU + 2 * n1);
+    }
 };
 
 struct SparseLUHost {
@@ -77,6 +82,7 @@ struct SparseLUHost {
     std::vector<int> s_dst, s_src, s_diag, s_pptr;
     std::vector<int> Lr_ptr, Lr_col, Ur_ptr, Ur_col;
     std::vector<int> flev_ptr, flev_rows, blev_ptr, blev_rows;
+    std::vector<unsigned short> Lr_col16, Ur_col16, flev_rows16, blev_rows16;  // what the solves read
     int64_t n_pairs_sparse = 0, n_pairs_schur = 0;
 
     /// view over the host vectors (host harness)
@@ -90,10 +96,10 @@ struct SparseLUHost {
         s.t_pptr = t_pptr.data(); s.p_l = p_l.data(); s.p_u = p_u.data();
         s.n_starg = (int)s_dst.size();
         s.s_dst = s_dst.data(); s.s_src = s_src.data(); s.s_diag = s_diag.data(); s.s_pptr = s_pptr.data();
-        s.Lr_ptr = Lr_ptr.data(); s.Lr_col = Lr_col.data(); s.Ur_ptr = Ur_ptr.data(); s.Ur_col = Ur_col.data();
+        s.Lr_ptr = Lr_ptr.data(); s.Lr_col = Lr_col16.data(); s.Ur_ptr = Ur_ptr.data(); s.Ur_col = Ur_col16.data();
         s.n_flev = (int)flev_ptr.size() - 1; s.n_blev = (int)blev_ptr.size() - 1;
-        s.flev_ptr = flev_ptr.data(); s.flev_rows = flev_rows.data();
-        s.blev_ptr = blev_ptr.data(); s.blev_rows = blev_rows.data();
+        s.flev_ptr = flev_ptr.data(); s.flev_rows = flev_rows16.data();
+        s.blev_ptr = blev_ptr.data(); s.blev_rows = blev_rows16.data();
         return s;
     }
 
@@ -133,11 +139,20 @@ struct SparseLUHost {
         for (int i = 0; i < nx; ++i) deg[i] = popc(i);
         H.ord.clear();
         int n_alive = nx;
+        int extra = 0, over_budget = 0;
         while (n_alive > 0) {
             int best = -1;
             for (int i = 0; i < nx; ++i)
                 if (alive[i] && (best < 0 || deg[i] < deg[best])) best = i;
-            if (deg[best] > deg_max) break;
+            // past deg_max the elimination goes on only to bring the dense block down to a multiple of
+            // m_align (full warps / tensor-core tiles of the dense path), for at most m_align - 1 pivots of
+            // at most twice that degree
+            if (deg[best] > deg_max) {
+                const int over = n_alive % (m_align > 1 ? m_align : 1);
+                if (extra == 0) over_budget = over;
+                if (over == 0 || deg[best] > 2 * deg_max || extra >= over_budget) break;
+                ++extra;
+            }
             // eliminate `best`: its neighbours become a clique
             const int k = best;
             alive[k] = 0;
@@ -157,6 +172,7 @@ struct SparseLUHost {
         }
         // the dense block: what is left, in ascending original index; its dimension a multiple of m_align
         int n1 = (int)H.ord.size();
+        if (extra > 0 && m_align > 1 && (nx - n1) % m_align != 0) n1 -= extra;  // alignment not reached: undo the extras
         if (m_align > 1) {
             int m = nx - n1;
             const int m_up = ((m + m_align - 1) / m_align) * m_align;
@@ -360,6 +376,10 @@ struct SparseLUHost {
             for (int r = 0; r < n1; ++r) H.blev_rows[fill[bl[r]]++] = r;
             if (n1 == 0) { H.flev_ptr.assign(1, 0); H.blev_ptr.assign(1, 0); }
         }
+        H.Lr_col16.assign(H.Lr_col.begin(), H.Lr_col.end());
+        H.Ur_col16.assign(H.Ur_col.begin(), H.Ur_col.end());
+        H.flev_rows16.assign(H.flev_rows.begin(), H.flev_rows.end());
+        H.blev_rows16.assign(H.blev_rows.begin(), H.blev_rows.end());
         return H;
     }
 };

@@ -21,7 +21,7 @@ constexpr int TEAM_THREADS = 512;
 template <int TEAM_THREADS_>
 __global__ void __launch_bounds__(TEAM_THREADS_, 1)
 simulate_team_kernel(const KernelArgs a, const NetTables T, const SparseLU SP, double* __restrict__ workspace,
-                     size_t ws_stride, int NB, int stage_doubles, int use_sparse) {
+                     size_t ws_stride, int smem_doubles, int sp_tab_off, int use_sparse) {
     extern __shared__ __align__(16) double pb_team_smem[];
     __shared__ int s_pos;
     CtaTeam tm;
@@ -31,8 +31,32 @@ simulate_team_kernel(const KernelArgs a, const NetTables T, const SparseLU SP, d
     bdf.use_sparse = use_sparse != 0;
     bdf.opt = a.opt;
     bdf.w.carve(workspace + (size_t)blockIdx.x * ws_stride, T, SP.enabled ? SP.nV : 0);
-    bdf.w.NB = NB;
-    bdf.w.stage_doubles = stage_doubles;
+    bdf.w.NB = 0;  // panel width of the generic dense path: chosen per inversion from the panel capacity
+    // dynamic shared memory: [fixed buffers | tiles | ring / panel / sparse staging ...  | sparse solve tables]
+    const int stage_end = sp_tab_off >= 0 ? sp_tab_off : smem_doubles;
+    bdf.w.stage_doubles = stage_end - TEAM_SM_RBUF;
+    bdf.w.panel_doubles = stage_end - TEAM_SM_PANEL;
+    if (sp_tab_off >= 0) {
+        // the row pointers and 16-bit indices of the sparse triangular solves live in shared memory for the
+        // lifetime of the (persistent) block: every solve walks them, entry after entry
+        int* ip = reinterpret_cast<int*>(pb_team_smem + sp_tab_off);
+        const int n_lp = SP.nx + 1, n_up = SP.n1 + 1, n_fp = SP.n_flev + 1, n_bp = SP.n_blev + 1;
+        int* const s_lp = ip; int* const s_up = s_lp + n_lp; int* const s_fp = s_up + n_up; int* const s_bp = s_fp + n_fp;
+        unsigned short* const s_lc = reinterpret_cast<unsigned short*>(s_bp + n_bp);
+        unsigned short* const s_uc = s_lc + SP.nnzL;
+        unsigned short* const s_fr = s_uc + SP.nnzU;
+        unsigned short* const s_br = s_fr + SP.n1;
+        for (int e = threadIdx.x; e < n_lp; e += TEAM_THREADS_) s_lp[e] = SP.Lr_ptr[e];
+        for (int e = threadIdx.x; e < n_up; e += TEAM_THREADS_) s_up[e] = SP.Ur_ptr[e];
+        for (int e = threadIdx.x; e < n_fp; e += TEAM_THREADS_) s_fp[e] = SP.flev_ptr[e];
+        for (int e = threadIdx.x; e < n_bp; e += TEAM_THREADS_) s_bp[e] = SP.blev_ptr[e];
+        for (int e = threadIdx.x; e < SP.nnzL; e += TEAM_THREADS_) s_lc[e] = SP.Lr_col[e];
+        for (int e = threadIdx.x; e < SP.nnzU; e += TEAM_THREADS_) s_uc[e] = SP.Ur_col[e];
+        for (int e = threadIdx.x; e < SP.n1; e += TEAM_THREADS_) { s_fr[e] = SP.flev_rows[e]; s_br[e] = SP.blev_rows[e]; }
+        bdf.SP.Lr_ptr = s_lp; bdf.SP.Ur_ptr = s_up; bdf.SP.flev_ptr = s_fp; bdf.SP.blev_ptr = s_bp;
+        bdf.SP.Lr_col = s_lc; bdf.SP.Ur_col = s_uc; bdf.SP.flev_rows = s_fr; bdf.SP.blev_rows = s_br;
+        __syncthreads();
+    }
     const int tid = threadIdx.x;
     const int np = T.np;
     for (;;) {
@@ -120,8 +144,8 @@ struct TeamState {
     double* workspace = nullptr;
     size_t ws_stride = 0;
     int grid_cap = 0;
-    int NB = 0;
-    size_t smem = 0;
+    size_t smem = 0;      // dynamic shared memory of a block (bytes)
+    int sp_tab_off = -1;  // where the sparse solve tables start in it (doubles), -1: they stay in global memory
 };
 
 template <class V>
@@ -164,22 +188,10 @@ inline void* team_create_state(const NetTables& H, int sm_count, std::string* er
     UP(jell_col, (size_t)H.jell_w * H.nx); UP(jell_pos, H.nnz); UP(csc_ptr, H.nx + 1); UP(csc_row, H.nnz); UP(csc_from_csr, H.nnz);
     UP(x0_base, H.nx); UP(x0_kidx, H.nx); UP(o_ptr, H.ny + 1); UP(o_idx, H.n_o); UP(o_w, H.n_o); UP(sigma0, H.ny);
 #undef UP
-    // staging memory: as wide a panel as fits the SM's shared memory next to the fixed buffers
-    const size_t max_smem = 227u * 1024u;
-    const size_t panel_doubles = (max_smem - (size_t)TEAM_SM_PANEL * sizeof(double)) / sizeof(double);
-    st->NB = TeamWork::panel_width(H.nx, panel_doubles);
-    st->smem = ((size_t)TEAM_SM_PANEL + (size_t)H.nx * st->NB) * sizeof(double);
-    if (H.nx <= TEAM_THREADS && st->smem < (size_t)TEAM_SM_ROWS_END * sizeof(double))
-        st->smem = (size_t)TEAM_SM_ROWS_END * sizeof(double);  // rows path: cp.async ring
-    if ((size_t)H.nx * st->NB > panel_doubles) {
-        if (err) *err = "model too large for the team kernel's shared-memory panel";
-        team_destroy_state(st);
-        return nullptr;
-    }
     // symbolic factorisation of the Newton matrix's pattern, once per model (the klu_analyze role)
     {
         const int deg_max = H.nx >= 128 ? 32 : (H.nx / 4 > 2 ? H.nx / 4 : 2);
-        st->sp_host = SparseLUHost::build(H.nx, H.j_ptr, H.j_col, H.jell_pos, deg_max, 2);
+        st->sp_host = SparseLUHost::build(H.nx, H.j_ptr, H.j_col, H.jell_pos, deg_max, H.nx >= 128 ? 32 : 2);
         const SparseLUHost& S = st->sp_host;
         st->sp = S.view();
 #define UPV(field, vec) if ((e = team_upload(st, S.vec.data(), S.vec.size(), &st->sp.field)) != cudaSuccess) return fail(e)
@@ -187,15 +199,31 @@ inline void* team_create_state(const NetTables& H, int sm_count, std::string* er
         UPV(tlevel_ptr, tlevel_ptr); UPV(t_dst, t_dst); UPV(t_src, t_src); UPV(t_piv, t_piv); UPV(t_pptr, t_pptr);
         UPV(p_l, p_l); UPV(p_u, p_u);
         UPV(s_dst, s_dst); UPV(s_src, s_src); UPV(s_diag, s_diag); UPV(s_pptr, s_pptr);
-        UPV(Lr_ptr, Lr_ptr); UPV(Lr_col, Lr_col); UPV(Ur_ptr, Ur_ptr); UPV(Ur_col, Ur_col);
-        UPV(flev_ptr, flev_ptr); UPV(flev_rows, flev_rows); UPV(blev_ptr, blev_ptr); UPV(blev_rows, blev_rows);
+        UPV(Lr_ptr, Lr_ptr); UPV(Lr_col, Lr_col16); UPV(Ur_ptr, Ur_ptr); UPV(Ur_col, Ur_col16);
+        UPV(flev_ptr, flev_ptr); UPV(flev_rows, flev_rows16); UPV(blev_ptr, blev_ptr); UPV(blev_rows, blev_rows16);
 #undef UPV
         // automatic choice (PB200_OPT_LINSOL = 0): sparse where it removes a real part of the dense work --
         // the dense block is at most 3/4 of the matrix -- dense for small or nearly full patterns
         st->sparse_default = H.nx >= 128 && 4 * S.m <= 3 * H.nx;
     }
-    if (st->sp.m <= TEAM_THREADS && st->smem < (size_t)TEAM_SM_ROWS_END * sizeof(double))
-        st->smem = (size_t)TEAM_SM_ROWS_END * sizeof(double);  // the Schur block takes the rows path
+    // Dynamic shared memory: all a block may have (one block per SM); the sparse solve tables sit at its
+    // end when what is left still holds the rows path's ring (dense dimension <= 512) or a panel of at
+    // least 8 columns of the generic path.
+    {
+        const size_t total = (227u * 1024u - 1024u) / sizeof(double);  // (static shared memory + margin)
+        const size_t tab = ((size_t)st->sp.solve_table_bytes() + 15) / 16 * 2;
+        const int dense_max = H.nx;  // the dense path may be asked to take the whole matrix (fallback / option)
+        const size_t need = dense_max <= TEAM_THREADS ? (size_t)TEAM_SM_ROWS_END
+                                                      : (size_t)TEAM_SM_PANEL + (size_t)dense_max * 8;
+        st->smem = total * sizeof(double);
+        st->sp_tab_off = (total >= need + tab) ? (int)(total - tab) : -1;
+        const size_t avail = (st->sp_tab_off >= 0 ? (size_t)st->sp_tab_off : total);
+        if (avail < need || (st->sp.m <= TEAM_THREADS && avail < (size_t)TEAM_SM_ROWS_END)) {
+            if (err) *err = "model too large for the team kernel's shared-memory staging";
+            team_destroy_state(st);
+            return nullptr;
+        }
+    }
     st->ws_stride = TeamWork::hbm_doubles(H, st->sp.nV);
     st->grid_cap = sm_count;
     e = cudaMalloc((void**)&st->workspace, st->ws_stride * sizeof(double) * (size_t)st->grid_cap);
@@ -212,12 +240,12 @@ inline int team_launch(const KernelArgs& a, void* state, cudaStream_t stream, in
     if (grid < 1) grid = 1;
     // (the attribute is per device and per function: set at every launch, to this model's size)
     cudaError_t e = cudaFuncSetAttribute(simulate_team_kernel<TEAM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(227u * 1024u));
+                                         (int)st->smem);
     if (e != cudaSuccess) return (int)e;
     const int use_sparse = a.linsol == 2 ? 1 : (a.linsol == 1 ? 0 : (st->sparse_default ? 1 : 0));
-    const int stage_doubles = (int)(st->smem / sizeof(double)) - TEAM_SM_RBUF;
     simulate_team_kernel<TEAM_THREADS><<<grid, TEAM_THREADS, st->smem, stream>>>(a, st->dev, st->sp, st->workspace, st->ws_stride,
-                                                                                st->NB, stage_doubles, use_sparse);
+                                                                                (int)(st->smem / sizeof(double)), st->sp_tab_off,
+                                                                                use_sparse);
     if (lanes_used) *lanes_used = TEAM_THREADS;
     if (grid_used) *grid_used = grid;
     if (block_used) *block_used = TEAM_THREADS;

@@ -17,8 +17,10 @@
 
 #include <cstdint>
 #include <limits>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/parpe_b200.h"
@@ -138,18 +140,34 @@ class B200SummedGradientFunction : public SummedGradientFunction<int> {
         return idx;
     }
 
-    /// This process simulates the share `rank` of `world` of every index list and returns partial sums
-    /// (what LoadBalancerMaster/Worker distribute over MPI ranks in the reference); the caller
-    /// all-reduces fval and gradient.
+    /// This process simulates the share `rank` of `world` of every index list (what
+    /// LoadBalancerMaster/Worker distribute over MPI ranks in the reference).  evaluate() still returns
+    /// the GLOBAL fval / gradient / status on every rank -- as the reference master does after summing
+    /// all workers' results -- and therefore needs a collective: initNccl() or setAllreduce().
     void setPartition(int rank, int world) {
         if (pb200_set_partition(handle_, rank, world) != 0)
             throw std::runtime_error(std::string("pb200_set_partition: ") + pb200_last_error());
     }
-    /// Collective hook the hierarchical wrapper needs when the conditions are partitioned
-    /// (include/parpe_b200.h: pb200_set_allreduce), e.g. a function calling MPI_Allreduce in place.
+    /// Host-transport collective (include/parpe_b200.h: pb200_set_allreduce), e.g. a function calling
+    /// MPI_Allreduce in place: used by evaluate() and the hierarchical wrapper on a partitioned handle.
     void setAllreduce(pb200_allreduce_fn fn, void* user) {
         if (pb200_set_allreduce(handle_, fn, user) != 0)
             throw std::runtime_error(std::string("pb200_set_allreduce: ") + pb200_last_error());
+    }
+    /// 128-byte NCCL id, to be created on rank 0 and distributed to all ranks (MPI_Bcast in parPE)
+    static std::vector<char> ncclUniqueId() {
+        std::vector<char> id(128);
+        if (pb200_nccl_unique_id(id.data()) != 0)
+            throw std::runtime_error(std::string("pb200_nccl_unique_id: ") + pb200_last_error());
+        return id;
+    }
+    /// In-library collective: joins the NCCL communicator of the `world` handles of this problem and sets
+    /// the partition; from then on every evaluation all-reduces (nllh, #errors, gradient) on the device.
+    /// Must be called by all ranks concurrently (it blocks until the communicator is complete).
+    void initNccl(std::vector<char> const& id, int rank, int world) {
+        if (id.size() != 128) throw std::invalid_argument("NCCL unique id must have 128 bytes");
+        if (pb200_nccl_init(handle_, id.data(), rank, world) != 0)
+            throw std::runtime_error(std::string("pb200_nccl_init: ") + pb200_last_error());
     }
 
     pb200_handle* handle() const { return handle_; }
@@ -158,6 +176,77 @@ class B200SummedGradientFunction : public SummedGradientFunction<int> {
   private:
     B200ProblemTables tables_;
     pb200_handle* handle_ = nullptr;
+};
+
+/// The same objective over SEVERAL GPUs of one process -- what the reference reaches with MPI ranks
+/// (LoadBalancerMaster distributing packages to LoadBalancerWorkers, loadBalancerMaster.cpp:104-134,
+/// 200-244): one handle per device, every index list sharded contiguously over them, the partial
+/// (nllh, #errors, gradient) combined by ONE ncclAllReduce inside the library.  evaluate() drives all
+/// devices (a host thread per extra device for the duration of the call) and returns the global
+/// result; Ipopt / Ceres / the minibatch optimizer use it like any parpe::SummedGradientFunction<int>.
+class B200MultiGpuSummedGradientFunction : public SummedGradientFunction<int> {
+  public:
+    B200MultiGpuSummedGradientFunction(B200ProblemTables const& tables, std::vector<int> const& devices) {
+        if (devices.empty()) throw std::invalid_argument("no devices");
+        for (int d : devices) ranks_.push_back(std::make_unique<B200SummedGradientFunction>(tables, d));
+        const int world = static_cast<int>(devices.size());
+        if (world > 1) {
+            const std::vector<char> id = B200SummedGradientFunction::ncclUniqueId();
+            std::vector<std::string> errors(world);
+            std::vector<std::thread> th;
+            for (int r = 0; r < world; ++r)
+                th.emplace_back([&, r] {
+                    try { ranks_[r]->initNccl(id, r, world); } catch (std::exception const& e) { errors[r] = e.what(); }
+                });
+            for (auto& t : th) t.join();
+            for (auto& e : errors)
+                if (!e.empty()) throw std::runtime_error(e);
+        }
+    }
+
+    FunctionEvaluationStatus evaluate(gsl::span<const double> parameters, int dataset, double& fval,
+                                      gsl::span<double> gradient, Logger* logger, double* cpuTime) const override {
+        return evaluate(parameters, std::vector<int>{dataset}, fval, gradient, logger, cpuTime);
+    }
+
+    FunctionEvaluationStatus evaluate(gsl::span<const double> parameters, std::vector<int> datasets, double& fval,
+                                      gsl::span<double> gradient, Logger* logger, double* cpuTime) const override {
+        const int world = static_cast<int>(ranks_.size());
+        std::vector<FunctionEvaluationStatus> status(world, functionEvaluationFailure);
+        std::vector<double> fvals(world, 0.0), times(world, 0.0);
+        std::vector<std::vector<double>> grads(world, std::vector<double>(gradient.size()));
+        std::vector<std::string> errors(world);
+        auto run = [&](int r) {
+            try {
+                status[r] = ranks_[r]->evaluate(parameters, datasets, fvals[r],
+                                                gsl::span<double>(grads[r].data(), grads[r].size()), logger, &times[r]);
+            } catch (std::exception const& e) { errors[r] = e.what(); }
+        };
+        std::vector<std::thread> th;
+        for (int r = 1; r < world; ++r) th.emplace_back(run, r);
+        run(0);
+        for (auto& t : th) t.join();
+        for (auto& e : errors)
+            if (!e.empty()) throw std::runtime_error(e);
+        // every rank holds the same all-reduced numbers; rank 0's are returned
+        fval = fvals[0];
+        for (size_t j = 0; j < gradient.size(); ++j) gradient[j] = grads[0][j];
+        if (cpuTime) {
+            double t = 0.0;
+            for (double v : times) t = v > t ? v : t;
+            *cpuTime = t;
+        }
+        return status[0];
+    }
+
+    int numParameters() const override { return ranks_[0]->numParameters(); }
+    std::vector<std::string> getParameterIds() const override { return ranks_[0]->getParameterIds(); }
+    std::vector<int> getTrainingData() const { return ranks_[0]->getTrainingData(); }
+    int numDevices() const { return static_cast<int>(ranks_.size()); }
+    B200SummedGradientFunction& rank(int r) const { return *ranks_.at(r); }
+
+  private:
+    std::vector<std::unique_ptr<B200SummedGradientFunction>> ranks_;
 };
 
 /// (inner parameter, condition, observable) row tables of the hierarchical problem

@@ -74,14 +74,15 @@ def lib_team():
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
         L.hs_team_simulate.argtypes = [C.c_char_p, dp, dp, ip, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double,
                                        C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int64),
-                                       dp, dp, ip, C.c_int, C.c_int, C.c_int]
+                                       dp, dp, ip, C.c_int, C.c_int, C.c_int, C.c_int]
         L.hs_team_solve.argtypes = [C.c_char_p, dp, C.c_double, dp, C.c_int, C.c_int, dp, C.c_int, C.c_int, C.c_int, ip]
         _lib_team = L
     return _lib_team
 
 
 def simulate_team(model, p_unscaled, k, plist, t, my, sd, t0=0.0, rtol=1e-8, atol=1e-12, maxsteps=10000, stldet=1,
-                  errconS=1, want_outputs=False, panel_width=0, sparse=False, deg_max=0, stage_doubles=0):
+                  errconS=1, want_outputs=False, panel_width=0, sparse=False, deg_max=0, stage_doubles=0,
+                  fuse_history=True, fuse_newton=True):
     d = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     p_unscaled, k, t, my, sd = d(p_unscaled), d(k), d(t), d(my).reshape(-1), d(sd).reshape(-1)
     plist = np.ascontiguousarray(plist, dtype=np.int32)
@@ -96,7 +97,8 @@ def simulate_team(model, p_unscaled, k, plist, t, my, sd, t0=0.0, rtol=1e-8, ato
     st = lib_team().hs_team_simulate(model.encode(), P(p_unscaled), P(k), plist.ctypes.data_as(C.POINTER(C.c_int)), ns,
                                      len(t), P(t), P(my), P(sd), t0, rtol, atol, maxsteps, stldet, errconS, panel_width,
                                      C.byref(llh), P(sllh), stats.ctypes.data_as(C.POINTER(C.c_int64)), P(y), P(s),
-                                     trace.ctypes.data_as(C.POINTER(C.c_int)), int(sparse), deg_max, stage_doubles)
+                                     trace.ctypes.data_as(C.POINTER(C.c_int)), int(sparse), deg_max, stage_doubles,
+                                     int(fuse_history) + 2 * int(fuse_newton))
     return dict(numsteps=trace[0::2], order=trace[1::2], status=st, llh=llh.value, sllh=sllh[:ns], stats=stats, y=y, sigmay=s)
 
 

@@ -30,7 +30,7 @@ static bool tables_for(const char* model, NetTables* T) {
 /// symbolic factorisation of a model's pattern, as team_create_state builds it (deg_max <= 0: its rule)
 static SparseLUHost symbolic_for(const NetTables& T, int deg_max) {
     if (deg_max <= 0) deg_max = T.nx >= 128 ? 32 : (T.nx / 4 > 2 ? T.nx / 4 : 2);
-    return SparseLUHost::build(T.nx, T.j_ptr, T.j_col, T.jell_pos, deg_max, 2);
+    return SparseLUHost::build(T.nx, T.j_ptr, T.j_col, T.jell_pos, deg_max, T.nx >= 128 ? 32 : 2);
 }
 
 /// sparse != 0: sparse LU + dense Schur block (deg_max: largest degree of a sparse pivot, <= 0 = default);
@@ -39,7 +39,7 @@ extern "C" int hs_team_simulate(const char* model, const double* p_unscaled, con
                                 int nt, const double* t, const double* my, const double* sd, double t0, double rtol,
                                 double atol, int maxsteps, int stldet, int errconS, int panel_width, double* llh,
                                 double* sllh, int64_t* stats, double* y_out, double* sigmay_out, int* trace, int sparse,
-                                int deg_max, int stage_doubles) {
+                                int deg_max, int stage_doubles, int fuse_history) {
     NetTables T;
     if (!tables_for(model, &T)) return -12345;
     SparseLUHost SH;
@@ -55,6 +55,8 @@ extern "C" int hs_team_simulate(const char* model, const double* p_unscaled, con
     bdf.T = T;
     if (sparse) bdf.SP = SH.view();
     bdf.use_sparse = sparse != 0;
+    bdf.fuse_history = (fuse_history & 1) != 0;
+    bdf.fuse_newton = (fuse_history & 2) != 0;
     bdf.w.carve(hbm.data(), T, sparse ? SH.nV : 0);
     bdf.w.panel = panel.data();
     bdf.w.rbuf = rbuf.data();
@@ -62,6 +64,7 @@ extern "C" int hs_team_simulate(const char* model, const double* p_unscaled, con
     bdf.w.piv = piv.data();
     bdf.w.stage = stage.data();
     bdf.w.stage_doubles = stage_doubles;
+    bdf.w.panel_doubles = (int)panel.size();
     bdf.w.NB = NB;
     for (int i = 0; i < T.np; ++i) bdf.w.p[i] = p_unscaled[i];
     for (int i = 0; i < T.nk; ++i) bdf.w.k[i] = k[i];
@@ -98,6 +101,7 @@ extern "C" int hs_team_solve(const char* model, const double* Jcsr, double gamma
     bdf.T = T;
     if (sparse) bdf.SP = SH.view();
     bdf.use_sparse = sparse != 0;
+    bdf.fuse_newton = false;  // (this entry point reads the solution from w.scr through acor: either works; keep the plain path)
     bdf.w.carve(hbm.data(), T, sparse ? SH.nV : 0);
     bdf.w.panel = panel.data();
     bdf.w.rbuf = rbuf.data();
@@ -105,6 +109,7 @@ extern "C" int hs_team_solve(const char* model, const double* Jcsr, double gamma
     bdf.w.piv = piv.data();
     bdf.w.stage = stage.data();
     bdf.w.stage_doubles = stage_doubles;
+    bdf.w.panel_doubles = (int)panel.size();
     bdf.w.NB = NB;
     if (info && sparse) {
         info[0] = SH.n1; info[1] = SH.m; info[2] = SH.nnzL; info[3] = SH.nnzU;

@@ -278,3 +278,47 @@ def test_host_team_sparse_path_matches_cvodes(oracle_available, model, deg_max, 
                         (p[i] if tab.pscale_sim[c, i] == SCALE_LN else 1.0) for i in plist])
         assert_grad_close(r["sllh"] * fac, ro["sllh"][c][:len(plist)])
         assert abs(int(r["stats"][0]) - int(rd["stats"][0])) <= 0.05 * rd["stats"][0] + 3
+
+
+@pytest.mark.parametrize("ns_mode", ["sens", "cost"])
+def test_fused_history_pass_is_bit_identical(ns_mode):
+    """advance_fused (cvCompleteStep + error weights + cvAdjustOrder + cvRescale + cvPredict in ONE pass over
+    the history between the steps of a CVode call) performs CVODES' operations per element in CVODES' order:
+    the simulation is bit-identical to the one with separate sweeps -- same steps, orders, llh, sllh."""
+    from tests.host_harness.binding import simulate_team
+    tab = synth.make_problem("net32", 2, seed=7, scale="log10")
+    spec = get_spec("net32")
+    rng = np.random.default_rng(5)
+    for c in range(2):
+        p = np.asarray(spec.p_nominal) * 10.0 ** rng.uniform(-0.3, 0.3, spec.np)
+        plist = list(range(spec.np)) if ns_mode == "sens" else []
+        lo, hi = tab.t_offsets[c], tab.t_offsets[c + 1]
+        args = ("net32", p, tab.k[c], plist, tab.t[lo:hi], tab.y_of(c), tab.sigma_of(c))
+        a = simulate_team(*args, fuse_history=True)
+        b = simulate_team(*args, fuse_history=False)
+        assert a["status"] == b["status"] == 0
+        assert np.array_equal(a["stats"][:14], b["stats"][:14])
+        assert np.array_equal(a["numsteps"], b["numsteps"]) and np.array_equal(a["order"], b["order"])
+        assert a["llh"] == b["llh"] and np.array_equal(a["sllh"], b["sllh"])
+        assert a["stats"][0] > 500 and a["stats"][11] >= 0  # a long run with order changes up and down
+
+
+@pytest.mark.parametrize("stage", [0, 150, 40])
+def test_fused_newton_iteration_of_the_sparse_path(stage):
+    """Sparse solver: right-hand sides + forward substitution in one staging pass (rhs_sens_fwd) and backward
+    substitution + acor update + WRMS norm in another (sparse_backward(update)) -- same arithmetic per element
+    as the separate sweeps, so the one-thread host build must reproduce them bit for bit, for any batch size
+    (stage = 40 doubles < 2 nx: the fused right-hand side is not possible and the plain one runs)."""
+    from tests.host_harness.binding import simulate_team
+    tab = synth.make_problem("net32", 2, seed=7, scale="log10")
+    spec = get_spec("net32")
+    rng = np.random.default_rng(6)
+    for c in range(2):
+        p = np.asarray(spec.p_nominal) * 10.0 ** rng.uniform(-0.3, 0.3, spec.np)
+        lo, hi = tab.t_offsets[c], tab.t_offsets[c + 1]
+        args = ("net32", p, tab.k[c], list(range(spec.np)), tab.t[lo:hi], tab.y_of(c), tab.sigma_of(c))
+        a = simulate_team(*args, sparse=True, stage_doubles=stage, fuse_newton=True)
+        b = simulate_team(*args, sparse=True, stage_doubles=stage, fuse_newton=False)
+        assert a["status"] == b["status"] == 0
+        assert np.array_equal(a["stats"][:14], b["stats"][:14])
+        assert a["llh"] == b["llh"] and np.array_equal(a["sllh"], b["sllh"])
