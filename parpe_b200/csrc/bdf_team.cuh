@@ -426,10 +426,12 @@ struct BdfTeam {
         const double* __restrict__ jc = w.Jcur;
         const double* __restrict__ dfdp = w.dfdp;
         const int* __restrict__ jcol = T.jell_col;
-        const int* __restrict__ iord = SP.iord;
+        const unsigned short* __restrict__ iord = SP.iord16;
+        const int* __restrict__ plist = w.plist;
         double* __restrict__ bb = w.b;
         const int jw = T.jell_w;
         const int nx = this->nx;
+        const double rl1 = this->rl1, gamma = this->gamma;
         // staging area: corrected sensitivity vectors of the batch S[column][row] | right-hand sides Z[row][column]
         // | factor values
         tm.sync();
@@ -444,12 +446,17 @@ struct BdfTeam {
             const int ncb = (ns + 1 - cb < CB) ? ns + 1 - cb : CB;
             const int nel = ncb * nx;
             tm.sync();
+            // flat, coalesced: S = zn[0] + acor (what J multiplies), Z = rl1 zn[1] + acor (the rest of the residual)
             PT_FOR(x, 0, nel) {
                 const int cl = x / nx, i = x - cl * nx;
                 const size_t e = (size_t)(cb + cl) * nx + i;
-                S[(size_t)cl * nx + i] = z0[e] + ac[e];
+                const double a = ac[e];
+                S[(size_t)cl * nx + i] = z0[e] + a;
+                Z[(size_t)iord[i] * CB + cl] = rl1 * z1[e] + a;
             }
             tm.sync();
+            // one matrix row per thread (ELL entries in registers); the only global loads of the loop over the
+            // columns -- the entries of dxdotdp -- are issued four columns ahead of their use
             for (int i0 = 0; i0 < nx; i0 += tm.size()) {  // (whole warps enter: warp_max_int below)
                 const int i = i0 + tm.tid();
                 const bool rowok = i < nx;
@@ -466,18 +473,25 @@ struct BdfTeam {
                 const int wlen = tm.warp_max_int(len);
                 if (!rowok) continue;
                 const size_t zrow = (size_t)iord[i] * CB;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 2
-#endif
-                for (int cl = 0; cl < ncb; ++cl) {
-                    const size_t e = (size_t)(cb + cl) * nx + i;
-                    const double* sv = S + (size_t)cl * nx;
-                    double F = dfdp[i + (size_t)w.plist[cb + cl - 1] * nx];
+                constexpr int UC = 4;
+                for (int cl0 = 0; cl0 < ncb; cl0 += UC) {
+                    double d[UC];
                     PB_UNROLL
-                    for (int t = 0; t < TEAM_JW_MAX; ++t)
-                        if (t < wlen) F += jv[t] * sv[jn[t]];
-                    if (!PB_FINITE(F)) bad = true;
-                    Z[zrow + cl] = (rl1 * z1[e] + ac[e]) - gamma * F;
+                    for (int u = 0; u < UC; ++u)
+                        d[u] = (cl0 + u < ncb) ? dfdp[i + (size_t)plist[cb + cl0 + u - 1] * nx] : 0.0;
+                    PB_UNROLL
+                    for (int u = 0; u < UC; ++u) {
+                        const int cl = cl0 + u;
+                        if (cl < ncb) {
+                            const double* sv = S + (size_t)cl * nx;
+                            double F = d[u];
+                            PB_UNROLL
+                            for (int t = 0; t < TEAM_JW_MAX; ++t)
+                                if (t < wlen) F += jv[t] * sv[jn[t]];
+                            if (!PB_FINITE(F)) bad = true;
+                            Z[zrow + cl] = Z[zrow + cl] - gamma * F;
+                        }
+                    }
                 }
             }
             tm.sync();
@@ -1208,6 +1222,24 @@ struct BdfTeam {
 #endif
     }
 
+    /// v - sum_e V[pl[e]] * V[pu[e]] over e in [e0, e1), products subtracted in ascending order; the loads of
+    /// four products are issued together
+    PB_HD static double pair_chain(double v, const double* V, const int* __restrict__ pl, const int* __restrict__ pu, int e0, int e1) {
+        int e = e0;
+        for (; e + 4 <= e1; e += 4) {
+            const int l0 = pl[e], l1 = pl[e + 1], l2 = pl[e + 2], l3 = pl[e + 3];
+            const int u0 = pu[e], u1 = pu[e + 1], u2 = pu[e + 2], u3 = pu[e + 3];
+            const double a0 = V[l0], a1 = V[l1], a2 = V[l2], a3 = V[l3];
+            const double b0 = V[u0], b1 = V[u1], b2 = V[u2], b3 = V[u3];
+            v -= a0 * b0;
+            v -= a1 * b1;
+            v -= a2 * b2;
+            v -= a3 * b3;
+        }
+        for (; e < e1; ++e) v -= V[pl[e]] * V[pu[e]];
+        return v;
+    }
+
     /// Numeric factorisation on the fixed pattern (the klu_refactor role): sparse part entry by entry
     /// over the dependency levels, then the Schur block assembled dense in w.A and inverted by the
     /// dense path.  KLU keeps the diagonal as pivot unless |diag| < 0.001 max|column| (klu_factor's
@@ -1226,12 +1258,24 @@ struct BdfTeam {
         tm.sync();
         for (int l = 0; l < SP.n_tlevels; ++l) {
             const int t1 = SP.tlevel_ptr[l + 1];
-            for (int t = SP.tlevel_ptr[l] + tm.tid(); t < t1; t += tm.size()) {
+            // long pair lists (the late, dense-ish pivots): a warp per target, products spread over the lanes
+            // (coalesced index loads), fixed shuffle tree; otherwise one thread per target
+            const bool lng = SP.tlev_long[l] != 0;
+            const int tstart = SP.tlevel_ptr[l] + (lng ? tm.warp() : tm.tid());
+            const int tstep = lng ? tm.nwarps() : tm.size();
+            for (int t = tstart; t < t1; t += tstep) {
                 const int piv = SP.t_piv[t], src = SP.t_src[t];
                 double v = (piv == -2) ? 1.0 : 0.0;
                 if (src >= 0) v -= gam * J[src];
-                const int e1 = SP.t_pptr[t + 1];
-                for (int e = SP.t_pptr[t]; e < e1; ++e) v -= V[SP.p_l[e]] * V[SP.p_u[e]];
+                if (lng) {
+                    double acc = 0.0;
+                    const int e1 = SP.t_pptr[t + 1];
+                    PT_UNROLL4
+                    for (int e = SP.t_pptr[t] + tm.lane(); e < e1; e += Team::WARP) acc += V[SP.p_l[e]] * V[SP.p_u[e]];
+                    v -= tm.warp_sum(acc);
+                } else {
+                    v = pair_chain(v, V, SP.p_l, SP.p_u, SP.t_pptr[t], SP.t_pptr[t + 1]);
+                }
                 if (piv == -2) {
                     if (!(fabs(v) > 0.0) || !PB_FINITE(v)) bad = true;
                     v = 1.0 / v;
@@ -1239,7 +1283,7 @@ struct BdfTeam {
                     v *= V[piv];
                     if (!(fabs(v) <= 1000.0)) bad = true;  // |pivot| < 0.001 |entry|, or not finite
                 }
-                V[SP.t_dst[t]] = v;
+                if (!lng || tm.lane() == 0) V[SP.t_dst[t]] = v;
             }
             tm.sync();
         }
@@ -1252,9 +1296,7 @@ struct BdfTeam {
             const int src = SP.s_src[t];
             double v = SP.s_diag[t] ? 1.0 : 0.0;
             if (src >= 0) v -= gam * J[src];
-            const int e1 = SP.s_pptr[t + 1];
-            for (int e = SP.s_pptr[t]; e < e1; ++e) v -= V[SP.p_l[e]] * V[SP.p_u[e]];
-            A[SP.s_dst[t]] = v;
+            A[SP.s_dst[t]] = pair_chain(v, V, SP.p_l, SP.p_u, SP.s_pptr[t], SP.s_pptr[t + 1]);
         }
         if (v_staged) {
             PT_FOR(e, 0, SP.nV) w.luV[e] = V[e];
@@ -1291,6 +1333,54 @@ struct BdfTeam {
         return Vs;
     }
 
+    /// acc - sum_e V[v0 + e] * Z[col[e] * bc + cl] over e in [e0, e1), terms subtracted in ascending order; the
+    /// index and value loads of four entries are issued together (they may come from global memory)
+    PB_HD static double row_chain(double acc, const double* __restrict__ V, int v0, const unsigned short* __restrict__ col,
+                                  const double* Z, int e0, int e1, int bc, int cl) {
+        int e = e0;
+        for (; e + 4 <= e1; e += 4) {
+            const int c0 = col[e], c1 = col[e + 1], c2 = col[e + 2], c3 = col[e + 3];
+            const double a0 = V[v0 + e], a1 = V[v0 + e + 1], a2 = V[v0 + e + 2], a3 = V[v0 + e + 3];
+            const double z0 = Z[(size_t)c0 * bc + cl], z1 = Z[(size_t)c1 * bc + cl], z2 = Z[(size_t)c2 * bc + cl],
+                         z3 = Z[(size_t)c3 * bc + cl];
+            acc -= a0 * z0;
+            acc -= a1 * z1;
+            acc -= a2 * z2;
+            acc -= a3 * z3;
+        }
+        for (; e < e1; ++e) acc -= V[v0 + e] * Z[(size_t)col[e] * bc + cl];
+        return acc;
+    }
+
+    /// The rows [rows[0..nr)) (or n1 + 0..nr when rows == nullptr) of a level whose chains are LONG: a warp takes
+    /// two columns of a row, the chain of each is split over 16 lanes (consecutive entries on consecutive
+    /// lanes: coalesced factor loads) and reduced by a fixed shuffle tree.  scale != nullptr: result * scale[r].
+    PB_HD void level_long_rows(double* Z, int bc, int nb, const double* __restrict__ V, int v0,
+                               const int* __restrict__ rptr, const unsigned short* __restrict__ rcol,
+                               const unsigned short* rows, int row0, int nr, const double* scale) {
+        constexpr int P = Team::WARP >= 32 ? 16 : 1;  // lanes per chain
+        constexpr int CPW = Team::WARP / P;           // columns per warp
+        const int part = tm.lane() % P, which = tm.lane() / P;
+        const int ncp = (nb + CPW - 1) / CPW;
+        for (int task = tm.warp(); task < nr * ncp; task += tm.nwarps()) {
+            const int rr = task / ncp, cp = task - rr * ncp;
+            const int r = rows ? (int)rows[rr] : row0 + rr;
+            const int cl = cp * CPW + which;
+            const bool ok = cl < nb;
+            double acc = 0.0;
+            if (ok) {
+                const int e1 = rptr[r + 1];
+                PT_UNROLL4
+                for (int e = rptr[r] + part; e < e1; e += P) acc += V[v0 + e] * Z[(size_t)rcol[e] * bc + cl];
+            }
+            acc = tm.sum16(acc);
+            if (ok && part == 0) {
+                const double v = Z[(size_t)r * bc + cl] - acc;
+                Z[(size_t)r * bc + cl] = scale ? v * scale[r] : v;
+            }
+        }
+    }
+
     /// forward levels + Schur rows on a staged batch Z[row][column] (stride bc) of nb columns
     PB_HD void sparse_forward_staged(double* Z, int bc, int nb, const double* V) {
         const int n1 = SP.n1, m = SP.m;
@@ -1298,24 +1388,26 @@ struct BdfTeam {
         // (same factor entries: broadcast; consecutive words of Z: conflict-free)
         for (int l = 1; l < SP.n_flev; ++l) {  // (level 0: rows without L entries)
             const int r0 = SP.flev_ptr[l], nr = SP.flev_ptr[l + 1] - r0;
-            for (int t = tm.tid(); t < nr * nb; t += tm.size()) {
-                const int rr = t / nb, cl = t - rr * nb;
-                const int r = SP.flev_rows[r0 + rr];
-                double acc = Z[(size_t)r * bc + cl];
-                const int e1 = SP.Lr_ptr[r + 1];
-                for (int e = SP.Lr_ptr[r]; e < e1; ++e) acc -= V[n1 + e] * Z[(size_t)SP.Lr_col[e] * bc + cl];
-                Z[(size_t)r * bc + cl] = acc;
+            if (SP.flev_long[l]) {
+                level_long_rows(Z, bc, nb, V, n1, SP.Lr_ptr, SP.Lr_col, SP.flev_rows + r0, 0, nr, nullptr);
+            } else {
+                for (int t = tm.tid(); t < nr * nb; t += tm.size()) {
+                    const int rr = t / nb, cl = t - rr * nb;
+                    const int r = SP.flev_rows[r0 + rr];
+                    Z[(size_t)r * bc + cl] = row_chain(Z[(size_t)r * bc + cl], V, n1, SP.Lr_col, Z, SP.Lr_ptr[r], SP.Lr_ptr[r + 1], bc, cl);
+                }
             }
             tm.sync();
         }
         // Schur rows: gather from the finished y
-        for (int t = tm.tid(); t < m * nb; t += tm.size()) {
-            const int rr = t / nb, cl = t - rr * nb;
-            const int r = n1 + rr;
-            double acc = Z[(size_t)r * bc + cl];
-            const int e1 = SP.Lr_ptr[r + 1];
-            for (int e = SP.Lr_ptr[r]; e < e1; ++e) acc -= V[n1 + e] * Z[(size_t)SP.Lr_col[e] * bc + cl];
-            Z[(size_t)r * bc + cl] = acc;
+        if (m > 0 && SP.flev_long[SP.n_flev]) {
+            level_long_rows(Z, bc, nb, V, n1, SP.Lr_ptr, SP.Lr_col, nullptr, n1, m, nullptr);
+        } else {
+            for (int t = tm.tid(); t < m * nb; t += tm.size()) {
+                const int rr = t / nb, cl = t - rr * nb;
+                const int r = n1 + rr;
+                Z[(size_t)r * bc + cl] = row_chain(Z[(size_t)r * bc + cl], V, n1, SP.Lr_col, Z, SP.Lr_ptr[r], SP.Lr_ptr[r + 1], bc, cl);
+            }
         }
         tm.sync();
     }
@@ -1327,7 +1419,7 @@ struct BdfTeam {
     PB_HD void sparse_forward(int cmin, int cmax) {
         const int nx = this->nx;
         const int ncols = cmax - cmin + 1;
-        const int* __restrict__ iord = SP.iord;
+        const unsigned short* __restrict__ iord = SP.iord16;
         double* const Z = sp_stage();
         double* const b = w.b;
         tm.sync();
@@ -1361,12 +1453,12 @@ struct BdfTeam {
     PB_HD double sparse_backward(int cmin, int cmax, double nsc, bool update) {
         const int n1 = SP.n1, nx = this->nx;
         const int ncols = cmax - cmin + 1;
-        const int* __restrict__ iord = SP.iord;
+        const unsigned short* __restrict__ iord = SP.iord16;
         double* const Z = sp_stage();
-        const double* const b = w.b;
+        const double* __restrict__ b = w.b;
         double* const scr = w.scr;
         double* const acor = w.acor;
-        const double* const ewt = w.ewt;
+        const double* __restrict__ ewt = w.ewt;
         tm.sync();
         int zcap;
         const double* const V = sp_stage_values(zcap);
@@ -1379,22 +1471,28 @@ struct BdfTeam {
         for (int c0 = cmin; c0 <= cmax; c0 += bc) {
             const int nb = (cmax + 1 - c0 < bc) ? cmax + 1 - c0 : bc;
             tm.sync();
-            PT_FOR(x, 0, nx * nb) {
-                const int cl = x / nx, i = x - cl * nx;
-                const int r = iord[i];
-                const size_t g = i + (size_t)(c0 + cl) * nx;
-                Z[(size_t)r * bc + cl] = (r < n1) ? b[g] : scr[g];
+            {
+                const double* __restrict__ xs2 = scr;
+                PT_FOR(x, 0, nx * nb) {
+                    const int cl = x / nx, i = x - cl * nx;
+                    const int r = iord[i];
+                    const size_t g = i + (size_t)(c0 + cl) * nx;
+                    const double* __restrict__ src = (r < n1) ? b : xs2;
+                    Z[(size_t)r * bc + cl] = src[g];
+                }
             }
             tm.sync();
             for (int l = 0; l < SP.n_blev; ++l) {
                 const int r0 = SP.blev_ptr[l], nr = SP.blev_ptr[l + 1] - r0;
-                for (int t = tm.tid(); t < nr * nb; t += tm.size()) {
-                    const int rr = t / nb, cl = t - rr * nb;
-                    const int r = SP.blev_rows[r0 + rr];
-                    double acc = Z[(size_t)r * bc + cl];
-                    const int e1 = SP.Ur_ptr[r + 1];
-                    for (int e = SP.Ur_ptr[r]; e < e1; ++e) acc -= V[nU0 + e] * Z[(size_t)SP.Ur_col[e] * bc + cl];
-                    Z[(size_t)r * bc + cl] = acc * V[r];
+                if (SP.blev_long[l]) {
+                    level_long_rows(Z, bc, nb, V, nU0, SP.Ur_ptr, SP.Ur_col, SP.blev_rows + r0, 0, nr, V);
+                } else {
+                    for (int t = tm.tid(); t < nr * nb; t += tm.size()) {
+                        const int rr = t / nb, cl = t - rr * nb;
+                        const int r = SP.blev_rows[r0 + rr];
+                        const double acc = row_chain(Z[(size_t)r * bc + cl], V, nU0, SP.Ur_col, Z, SP.Ur_ptr[r], SP.Ur_ptr[r + 1], bc, cl);
+                        Z[(size_t)r * bc + cl] = acc * V[r];
+                    }
                 }
                 tm.sync();
             }
@@ -1404,17 +1502,40 @@ struct BdfTeam {
                     scr[i + (size_t)(c0 + cl) * nx] = nsc * Z[(size_t)iord[i] * bc + cl];
                 }
             } else {
-                // one warp per column (coalesced, and the column's sum of squares is a warp reduction)
+                // flat and coalesced, a batch of independent loads ahead of the stores: acor += delta; the
+                // squared weighted entries replace Z, so that the per-column sums can be formed in a FIXED order
+                constexpr int U = 4;
+                const int nel = nx * nb;
+                PT_FOR_BATCH(xb, 0, nel, U) {
+                    double a[U], ew[U], d[U];
+                    int zi[U];
+                    size_t g[U];
+                    PB_UNROLL
+                    for (int u = 0; u < U; ++u) {
+                        const int x = xb + u * tm.size();
+                        const bool ok = x < nel;
+                        const int cl = ok ? x / nx : 0, i = ok ? x - cl * nx : 0;
+                        g[u] = i + (size_t)(c0 + cl) * nx;
+                        zi[u] = (int)iord[i] * bc + cl;
+                        a[u] = ok ? acor[g[u]] : 0.0;
+                        ew[u] = ok ? ewt[g[u]] : 0.0;
+                        d[u] = ok ? nsc * Z[zi[u]] : 0.0;
+                    }
+                    PB_UNROLL
+                    for (int u = 0; u < U; ++u) {
+                        const int x = xb + u * tm.size();
+                        if (x < nel) {
+                            acor[g[u]] = a[u] + d[u];
+                            const double v = d[u] * ew[u];
+                            Z[zi[u]] = v * v;
+                        }
+                    }
+                }
+                tm.sync();
+                // one warp per column: lane-strided partial sums in ascending row order, then the shuffle tree
                 for (int cl = tm.warp(); cl < nb; cl += tm.nwarps()) {
                     double sq = 0.0;
-                    PT_UNROLL4
-                    for (int i = tm.lane(); i < nx; i += Team::WARP) {
-                        const size_t g = i + (size_t)(c0 + cl) * nx;
-                        const double d = nsc * Z[(size_t)iord[i] * bc + cl];
-                        acor[g] += d;
-                        const double v = d * ewt[g];
-                        sq += v * v;
-                    }
+                    for (int i = tm.lane(); i < nx; i += Team::WARP) sq += Z[(size_t)iord[i] * bc + cl];
                     sq = tm.warp_sum(sq);
                     if (sq > loc) loc = sq;
                 }

@@ -36,7 +36,7 @@ struct HierKind {
     std::vector<int> cond, obs;  // pairs: conditions ascending per parameter, observables in row order
     int64_t* d_ptr = nullptr;
     int *d_cond = nullptr, *d_obs = nullptr;
-    double* d_sums = nullptr;    // [n*3]
+    double* d_sums = nullptr;    // [n * HIER_SLICES * 3]: per inner parameter and slice of its pair list
     double* d_vals = nullptr;    // [n] linear-scale values to apply
 };
 
@@ -53,6 +53,9 @@ struct HierDevice {
 };
 
 enum { HIER_SCALING = 0, HIER_OFFSET = 1, HIER_SIGMA = 2 };
+/// every inner parameter's (condition, observable) pair list is summed by this many blocks (a fixed split:
+/// the partial sums are combined on the host in slice order, so results do not depend on the launch)
+constexpr int HIER_SLICES = 32;
 
 template <int KIND, int THREADS>
 __global__ void __launch_bounds__(THREADS)
@@ -60,9 +63,13 @@ hier_sums_kernel(const int64_t* __restrict__ ptr, const int* __restrict__ cond, 
                  const int64_t* __restrict__ t_offsets, int ny, const double* __restrict__ mes,
                  const double* __restrict__ sim, double* __restrict__ sums, int c_lo, int c_hi) {
     __shared__ double r0[THREADS], r1[THREADS], r2[THREADS];
-    const int p = blockIdx.x, tid = threadIdx.x;
+    const int p = blockIdx.x, slice = blockIdx.y, tid = threadIdx.x;
     double num = 0.0, den = 0.0, mx = 0.0;
-    for (int64_t e = ptr[p] + tid; e < ptr[p + 1]; e += THREADS) {
+    const int64_t len = ptr[p + 1] - ptr[p];
+    const int64_t chunk = (len + HIER_SLICES - 1) / HIER_SLICES;
+    const int64_t e_lo = ptr[p] + slice * chunk;
+    const int64_t e_hi = (e_lo + chunk < ptr[p + 1]) ? e_lo + chunk : ptr[p + 1];
+    for (int64_t e = e_lo + tid; e < e_hi; e += THREADS) {
         const int c = cond[e], o = obs[e];
         if (c < c_lo || c >= c_hi) continue;  // a condition another rank simulates (ownership by partition bounds)
         const int64_t lo = t_offsets[c], hi = t_offsets[c + 1];
@@ -97,9 +104,10 @@ hier_sums_kernel(const int64_t* __restrict__ ptr, const int* __restrict__ cond, 
         __syncthreads();
     }
     if (tid == 0) {
-        sums[p * 3 + 0] = r0[0];
-        sums[p * 3 + 1] = r1[0];
-        sums[p * 3 + 2] = r2[0];
+        double* o = sums + ((size_t)p * HIER_SLICES + slice) * 3;
+        o[0] = r0[0];
+        o[1] = r1[0];
+        o[2] = r2[0];
     }
 }
 
@@ -182,7 +190,7 @@ inline bool hier_build_kind(HierKind& k, const int32_t* idx, int n, const int32_
     if (!up((void**)&k.d_ptr, k.ptr.data(), sizeof(int64_t) * k.ptr.size()) ||
         !up((void**)&k.d_cond, k.cond.data(), sizeof(int) * k.cond.size()) ||
         !up((void**)&k.d_obs, k.obs.data(), sizeof(int) * k.obs.size()) ||
-        cudaMalloc((void**)&k.d_sums, sizeof(double) * 3 * (n ? n : 1)) != cudaSuccess ||
+        cudaMalloc((void**)&k.d_sums, sizeof(double) * 3 * HIER_SLICES * (n ? n : 1)) != cudaSuccess ||
         cudaMalloc((void**)&k.d_vals, sizeof(double) * (n ? n : 1)) != cudaSuccess) {
         *err = "cudaMalloc failed for hierarchical tables";
         return false;
@@ -303,8 +311,21 @@ inline bool hier_compute(HierDevice* h, const double* d_mes, double* d_y, double
     auto fetch = [&](HierKind& k, std::vector<double>& host) {
         host.resize((size_t)3 * k.n);
         if (k.n == 0) return true;
-        return check(cudaMemcpyAsync(host.data(), k.d_sums, sizeof(double) * 3 * k.n, cudaMemcpyDeviceToHost, stream), "memcpy") &&
-               check(cudaStreamSynchronize(stream), "sync");
+        std::vector<double> part((size_t)3 * HIER_SLICES * k.n);
+        if (!(check(cudaMemcpyAsync(part.data(), k.d_sums, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, stream), "memcpy") &&
+              check(cudaStreamSynchronize(stream), "sync")))
+            return false;
+        for (int p = 0; p < k.n; ++p) {  // slices in fixed order
+            double a = 0.0, b = 0.0, mx = 0.0;
+            for (int sl = 0; sl < HIER_SLICES; ++sl) {
+                const double* o = &part[((size_t)p * HIER_SLICES + sl) * 3];
+                a += o[0];
+                b += o[1];
+                mx = std::max(mx, o[2]);
+            }
+            host[3 * p] = a; host[3 * p + 1] = b; host[3 * p + 2] = mx;
+        }
+        return true;
     };
     auto push = [&](HierKind& k, const std::vector<double>& lin) {
         if (k.n == 0) return true;
@@ -313,8 +334,8 @@ inline bool hier_compute(HierDevice* h, const double* d_mes, double* d_y, double
     };
     HierKind &S = h->scaling, &O = h->offset, &G = h->sigma;
     std::vector<double> hs, ho, hg;
-    if (S.n) hier_sums_kernel<HIER_SCALING, T><<<S.n, T, 0, stream>>>(S.d_ptr, S.d_cond, S.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, S.d_sums, c_lo, c_hi);
-    if (O.n) hier_sums_kernel<HIER_OFFSET, T><<<O.n, T, 0, stream>>>(O.d_ptr, O.d_cond, O.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, O.d_sums, c_lo, c_hi);
+    if (S.n) hier_sums_kernel<HIER_SCALING, T><<<dim3(S.n, HIER_SLICES), T, 0, stream>>>(S.d_ptr, S.d_cond, S.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, S.d_sums, c_lo, c_hi);
+    if (O.n) hier_sums_kernel<HIER_OFFSET, T><<<dim3(O.n, HIER_SLICES), T, 0, stream>>>(O.d_ptr, O.d_cond, O.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, O.d_sums, c_lo, c_hi);
     if (!check(cudaGetLastError(), "hier_sums_kernel") || !fetch(S, hs) || !fetch(O, ho)) return false;
     reduce_kind(hs, S.n);
     reduce_kind(ho, O.n);
@@ -338,7 +359,7 @@ inline bool hier_compute(HierDevice* h, const double* d_mes, double* d_y, double
     for (int i = 0; i < O.n; ++i) lin[i] = unscale(offs[i], h->pscale_opt[O.idx[i]]);
     if (!push(O, lin)) return false;
     if (O.n) hier_apply_kernel<1, T><<<O.n, T, 0, stream>>>(O.d_ptr, O.d_cond, O.d_obs, h->d_t_offsets, h->ny, O.d_vals, d_y);
-    if (G.n) hier_sums_kernel<HIER_SIGMA, T><<<G.n, T, 0, stream>>>(G.d_ptr, G.d_cond, G.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, G.d_sums, c_lo, c_hi);
+    if (G.n) hier_sums_kernel<HIER_SIGMA, T><<<dim3(G.n, HIER_SLICES), T, 0, stream>>>(G.d_ptr, G.d_cond, G.d_obs, h->d_t_offsets, h->ny, d_mes, d_y, G.d_sums, c_lo, c_hi);
     if (!check(cudaGetLastError(), "hier kernels") || !fetch(G, hg)) return false;
     reduce_kind(hg, G.n);
     for (int i = 0; i < G.n; ++i) {

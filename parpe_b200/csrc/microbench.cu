@@ -31,7 +31,9 @@ extern "C" int pb200_measure_fp64_peak(int device, double* tflops) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     constexpr int CHAINS = 16;
-    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    // (long enough that launch ramp and tail are below 1 %: ~35 ms per repetition; the same loop as
+    // tools/microbench/dmma_probe.cu's "DFMA registers only" line, which reads 36.6 TFLOP/s on this pool)
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 17;
     double* d = nullptr;
     if (cudaMalloc(&d, 8) != cudaSuccess) return PB200_ERR_CUDA;
     cudaEvent_t e0, e1;

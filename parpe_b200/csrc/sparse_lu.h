@@ -69,9 +69,15 @@ struct SparseLU {
     const unsigned short* flev_rows;
     const int* blev_ptr;   // backward levels
     const unsigned short* blev_rows;
+    const unsigned short* iord16;  // iord again, 16 bit (staging loops: address and source select without a global load)
+    // per level: 1 = its rows are long (mean >= 48 entries): a row's chain is split over 16 lanes instead of
+    // being walked by one thread ([n_flev] / [n_blev]; entry n_flev of flev_long: the Schur rows)
+    const unsigned char* flev_long;
+    const unsigned char* blev_long;
+    const unsigned char* tlev_long;  // [n_tlevels] numeric phase: the level's targets have long pair lists (mean >= 64)
     /// bytes of the solve tables (row pointers + 16-bit indices), the part worth keeping in shared memory
     int solve_table_bytes() const {
-        return 4 * ((nx + 1) + (n1 + 1) + (n_flev + 1) + (n_blev + 1)) + 2 * (nnzL + nnzU + 2 * n1);
+        return 4 * ((nx + 1) + (n1 + 1) + (n_flev + 1) + (n_blev + 1)) + 2 * (nnzL + nnzU + 2 * n1 + nx);
     }
 };
 
@@ -82,7 +88,8 @@ struct SparseLUHost {
     std::vector<int> s_dst, s_src, s_diag, s_pptr;
     std::vector<int> Lr_ptr, Lr_col, Ur_ptr, Ur_col;
     std::vector<int> flev_ptr, flev_rows, blev_ptr, blev_rows;
-    std::vector<unsigned short> Lr_col16, Ur_col16, flev_rows16, blev_rows16;  // what the solves read
+    std::vector<unsigned short> Lr_col16, Ur_col16, flev_rows16, blev_rows16, iord16;  // what the solves read
+    std::vector<unsigned char> flev_long, blev_long, tlev_long;
     int64_t n_pairs_sparse = 0, n_pairs_schur = 0;
 
     /// view over the host vectors (host harness)
@@ -100,6 +107,8 @@ struct SparseLUHost {
         s.n_flev = (int)flev_ptr.size() - 1; s.n_blev = (int)blev_ptr.size() - 1;
         s.flev_ptr = flev_ptr.data(); s.flev_rows = flev_rows16.data();
         s.blev_ptr = blev_ptr.data(); s.blev_rows = blev_rows16.data();
+        s.iord16 = iord16.data();
+        s.flev_long = flev_long.data(); s.blev_long = blev_long.data(); s.tlev_long = tlev_long.data();
         return s;
     }
 
@@ -113,7 +122,7 @@ struct SparseLUHost {
     /// of CSR entry e in the ELL value array).  deg_max: largest elimination-graph degree of a sparse
     /// pivot; m_align: the dense block's dimension is rounded up to a multiple of it.
     static SparseLUHost build(int nx, const int* j_ptr, const int* j_col, const int* ell_pos, int deg_max,
-                              int m_align = 2) {
+                              int m_align = 2, int m_target = 0) {
         SparseLUHost H;
         H.nx = nx;
         H.nnzJ = j_ptr[nx];
@@ -147,7 +156,9 @@ struct SparseLUHost {
             // past deg_max the elimination goes on only to bring the dense block down to a multiple of
             // m_align (full warps / tensor-core tiles of the dense path), for at most m_align - 1 pivots of
             // at most twice that degree
-            if (deg[best] > deg_max) {
+            if (m_target > 0) {  // (eliminate down to exactly m_target rows, whatever the degrees)
+                if (n_alive <= m_target) break;
+            } else if (deg[best] > deg_max) {
                 const int over = n_alive % (m_align > 1 ? m_align : 1);
                 if (extra == 0) over_budget = over;
                 if (over == 0 || deg[best] > 2 * deg_max || extra >= over_budget) break;
@@ -380,7 +391,48 @@ struct SparseLUHost {
         H.Ur_col16.assign(H.Ur_col.begin(), H.Ur_col.end());
         H.flev_rows16.assign(H.flev_rows.begin(), H.flev_rows.end());
         H.blev_rows16.assign(H.blev_rows.begin(), H.blev_rows.end());
+        H.iord16.assign(H.iord.begin(), H.iord.end());
+        {
+            const int nfl = (int)H.flev_ptr.size() - 1, nbl = (int)H.blev_ptr.size() - 1;
+            H.flev_long.assign(nfl + 1, 0);
+            H.blev_long.assign(nbl + 1, 0);
+            for (int l = 0; l < nfl; ++l) {
+                int64_t tot = 0;
+                const int nr = H.flev_ptr[l + 1] - H.flev_ptr[l];
+                for (int e = H.flev_ptr[l]; e < H.flev_ptr[l + 1]; ++e) tot += H.Lr_ptr[H.flev_rows[e] + 1] - H.Lr_ptr[H.flev_rows[e]];
+                H.flev_long[l] = (nr > 0 && tot >= 48 * (int64_t)nr) ? 1 : 0;
+            }
+            if (m > 0) H.flev_long[nfl] = (H.Lr_ptr[nx] - H.Lr_ptr[n1] >= 48 * (int64_t)m) ? 1 : 0;
+            const int ntl = (int)H.tlevel_ptr.size() - 1;
+            H.tlev_long.assign(ntl + 1, 0);
+            for (int l = 0; l < ntl; ++l) {
+                const int t0 = H.tlevel_ptr[l], t1 = H.tlevel_ptr[l + 1];
+                const int64_t tot = (int64_t)H.t_pptr[t1] - H.t_pptr[t0];
+                H.tlev_long[l] = (t1 > t0 && tot >= 64 * (int64_t)(t1 - t0)) ? 1 : 0;
+            }
+            for (int l = 0; l < nbl; ++l) {
+                int64_t tot = 0;
+                const int nr = H.blev_ptr[l + 1] - H.blev_ptr[l];
+                for (int e = H.blev_ptr[l]; e < H.blev_ptr[l + 1]; ++e) tot += H.Ur_ptr[H.blev_rows[e] + 1] - H.Ur_ptr[H.blev_rows[e]];
+                H.blev_long[l] = (nr > 0 && tot >= 48 * (int64_t)nr) ? 1 : 0;
+            }
+        }
         return H;
+    }
+
+    /// The split the team kernel uses: sparse pivots up to degree 32; if the dense block that leaves is
+    /// larger than `rows_max` (the dense path's fast variant owns one matrix row per thread), the sparse
+    /// elimination is carried on in minimum-degree order until exactly rows_max rows are left -- as long as
+    /// the numeric phase stays below `max_pairs` multiply-adds.  Small models (nx < 128): degree limit nx / 4.
+    static SparseLUHost build_for_team(int nx, const int* j_ptr, const int* j_col, const int* ell_pos, int rows_max = 512,
+                                       int64_t max_pairs = 6000000) {
+        if (nx < 128) return build(nx, j_ptr, j_col, ell_pos, nx / 4 > 2 ? nx / 4 : 2, 2);
+        SparseLUHost best = build(nx, j_ptr, j_col, ell_pos, 32, 32);
+        if (best.m > rows_max) {
+            SparseLUHost next = build(nx, j_ptr, j_col, ell_pos, nx, 32, rows_max);
+            if (next.n_pairs_sparse + next.n_pairs_schur <= max_pairs) best = std::move(next);
+        }
+        return best;
     }
 };
 

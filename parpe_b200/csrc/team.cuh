@@ -22,6 +22,7 @@ struct HostTeam {
     PB_HD void sync() const {}
     PB_HD void warp_sync() const {}
     PB_HD double warp_sum(double v) const { return v; }
+    PB_HD double sum16(double v) const { return v; }
     PB_HD int warp_max_int(int v) const { return v; }
     PB_HD double sum(double v) const { return v; }
     PB_HD double max(double v) const { return v; }
@@ -51,6 +52,12 @@ struct CtaTeam {
     __device__ __forceinline__ double warp_sum(double v) const {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    /// sum over the 16-lane half of the warp the lane belongs to (fixed shuffle tree)
+    __device__ __forceinline__ double sum16(double v) const {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         return v;
     }
     __device__ __forceinline__ int warp_max_int(int v) const {

@@ -46,6 +46,9 @@ simulate_team_kernel(const KernelArgs a, const NetTables T, const SparseLU SP, d
         unsigned short* const s_uc = s_lc + SP.nnzL;
         unsigned short* const s_fr = s_uc + SP.nnzU;
         unsigned short* const s_br = s_fr + SP.n1;
+        unsigned short* const s_io = s_br + SP.n1;
+        for (int e = threadIdx.x; e < SP.nx; e += TEAM_THREADS_) s_io[e] = SP.iord16[e];
+        bdf.SP.iord16 = s_io;
         for (int e = threadIdx.x; e < n_lp; e += TEAM_THREADS_) s_lp[e] = SP.Lr_ptr[e];
         for (int e = threadIdx.x; e < n_up; e += TEAM_THREADS_) s_up[e] = SP.Ur_ptr[e];
         for (int e = threadIdx.x; e < n_fp; e += TEAM_THREADS_) s_fp[e] = SP.flev_ptr[e];
@@ -190,8 +193,7 @@ inline void* team_create_state(const NetTables& H, int sm_count, std::string* er
 #undef UP
     // symbolic factorisation of the Newton matrix's pattern, once per model (the klu_analyze role)
     {
-        const int deg_max = H.nx >= 128 ? 32 : (H.nx / 4 > 2 ? H.nx / 4 : 2);
-        st->sp_host = SparseLUHost::build(H.nx, H.j_ptr, H.j_col, H.jell_pos, deg_max, H.nx >= 128 ? 32 : 2);
+        st->sp_host = SparseLUHost::build_for_team(H.nx, H.j_ptr, H.j_col, H.jell_pos, TEAM_THREADS);
         const SparseLUHost& S = st->sp_host;
         st->sp = S.view();
 #define UPV(field, vec) if ((e = team_upload(st, S.vec.data(), S.vec.size(), &st->sp.field)) != cudaSuccess) return fail(e)
@@ -201,6 +203,7 @@ inline void* team_create_state(const NetTables& H, int sm_count, std::string* er
         UPV(s_dst, s_dst); UPV(s_src, s_src); UPV(s_diag, s_diag); UPV(s_pptr, s_pptr);
         UPV(Lr_ptr, Lr_ptr); UPV(Lr_col, Lr_col16); UPV(Ur_ptr, Ur_ptr); UPV(Ur_col, Ur_col16);
         UPV(flev_ptr, flev_ptr); UPV(flev_rows, flev_rows16); UPV(blev_ptr, blev_ptr); UPV(blev_rows, blev_rows16);
+        UPV(iord16, iord16); UPV(flev_long, flev_long); UPV(blev_long, blev_long); UPV(tlev_long, tlev_long);
 #undef UPV
         // automatic choice (PB200_OPT_LINSOL = 0): sparse where it removes a real part of the dense work --
         // the dense block is at most 3/4 of the matrix -- dense for small or nearly full patterns
@@ -212,17 +215,18 @@ inline void* team_create_state(const NetTables& H, int sm_count, std::string* er
     {
         const size_t total = (227u * 1024u - 1024u) / sizeof(double);  // (static shared memory + margin)
         const size_t tab = ((size_t)st->sp.solve_table_bytes() + 15) / 16 * 2;
-        const int dense_max = H.nx;  // the dense path may be asked to take the whole matrix (fallback / option)
-        const size_t need = dense_max <= TEAM_THREADS ? (size_t)TEAM_SM_ROWS_END
-                                                      : (size_t)TEAM_SM_PANEL + (size_t)dense_max * 8;
+        // the dense path may be asked to take the whole matrix (fallback / PB200_OPT_LINSOL = 1): rows path (ring)
+        // up to 512 rows, otherwise the generic path with a panel of at least 8 columns; the Schur block of the
+        // sparse solver takes the rows path whenever it has <= 512 rows
+        size_t need = H.nx <= TEAM_THREADS ? (size_t)TEAM_SM_ROWS_END : (size_t)TEAM_SM_PANEL + (size_t)H.nx * 8;
+        if (st->sp.m <= TEAM_THREADS && need < (size_t)TEAM_SM_ROWS_END) need = (size_t)TEAM_SM_ROWS_END;
         st->smem = total * sizeof(double);
-        st->sp_tab_off = (total >= need + tab) ? (int)(total - tab) : -1;
-        const size_t avail = (st->sp_tab_off >= 0 ? (size_t)st->sp_tab_off : total);
-        if (avail < need || (st->sp.m <= TEAM_THREADS && avail < (size_t)TEAM_SM_ROWS_END)) {
+        if (total < need) {
             if (err) *err = "model too large for the team kernel's shared-memory staging";
             team_destroy_state(st);
             return nullptr;
         }
+        st->sp_tab_off = (total >= need + tab) ? (int)(total - tab) : -1;
     }
     st->ws_stride = TeamWork::hbm_doubles(H, st->sp.nV);
     st->grid_cap = sm_count;

@@ -29,7 +29,7 @@ static bool tables_for(const char* model, NetTables* T) {
 
 /// symbolic factorisation of a model's pattern, as team_create_state builds it (deg_max <= 0: its rule)
 static SparseLUHost symbolic_for(const NetTables& T, int deg_max) {
-    if (deg_max <= 0) deg_max = T.nx >= 128 ? 32 : (T.nx / 4 > 2 ? T.nx / 4 : 2);
+    if (deg_max <= 0) return SparseLUHost::build_for_team(T.nx, T.j_ptr, T.j_col, T.jell_pos);
     return SparseLUHost::build(T.nx, T.j_ptr, T.j_col, T.jell_pos, deg_max, T.nx >= 128 ? 32 : 2);
 }
 
