@@ -461,6 +461,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="small-model kernel: lanes per condition (0 = model default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra small-model (boehm) measurements")
+    ap.add_argument("--no-cost-only", action="store_true", help="skip the objective-only (no gradient) measurement")
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD,
                     help="chen (default: BASELINE configs[3], nx = 500) | froehlich (configs[4], nx = 1200) | boehm "
                          "(configs[1], the small-model kernel) | net32 | fujita ...")
@@ -484,7 +485,7 @@ def main():
     world, rank = rig.world, rig.rank
     n_total = per_gpu * world if args.scaling == "weak" else args.conditions
     m = measure(rig, model, n_total, args.steps, args.warmup, lanes=args.lanes, hetero=args.heterogeneous,
-                linsol=args.linsol)
+                linsol=args.linsol, want_cost_only=not args.no_cost_only)
     m["linsol"] = args.linsol
 
     extra = {}

@@ -289,6 +289,42 @@ int pb200_get_condition_results(pb200_handle* h, double* llh, double* sllh,
 int pb200_get_model_outputs(pb200_handle* h, const double* theta, int n_opt,
                             double* y_out, double* sigmay_out);
 
+/* parPE's HDF5 input file ------------------------------------------------ */
+/*
+ * Replaces: the HDF5 reads of MultiConditionDataProviderHDF5
+ * (src/parpeamici/multiConditionDataProvider.cpp:42-60,84-102,194-206,224-250,
+ * 302-321) and AnalyticalParameterHdf5Reader, for the input layout of
+ * doc/hdf5.md:1-172 -- /parameters/{optimizationSimulationMapping,
+ * parameterOverrides,pscaleSimulation,pscaleOptimization}, /fixedParameters/{k,
+ * simulationConditions}, /measurements/{t,y,ysigma}/<i>, /amiciOptions
+ * attributes, /{scaling,offset,sigma}Parameter{Indices,sMapToObservables}.
+ * The file is parsed by a built-in reader of the HDF5 subset such files use
+ * (old-style groups, contiguous / compact / chunked datasets, gzip + shuffle
+ * filters; parpe_b200/csrc/h5min.h); no HDF5 library is needed.  Input files
+ * with a pre-equilibration condition are refused.
+ */
+typedef struct pb200_h5 pb200_h5;
+int pb200_h5_open(const char* path, pb200_h5** out);
+void pb200_h5_close(pb200_h5* f);
+int pb200_h5_exists(pb200_h5* f, const char* path);
+/* rank, dims[<= 8], class (0 integer, 1 floating point, 3 string) and element size of a dataset */
+int pb200_h5_dataset_info(pb200_h5* f, const char* path, int* rank, int64_t* dims, int* type_class, int* type_size);
+/* whole dataset as doubles, row-major; returns the element count (out == NULL: count only) or < 0 */
+int64_t pb200_h5_read_double(pb200_h5* f, const char* path, double* out, int64_t capacity);
+/* numeric attribute of a group / dataset as doubles; returns the element count or < 0 */
+int pb200_h5_attribute_double(pb200_h5* f, const char* object, const char* name, double* out, int capacity);
+/* newline-separated names of a group's children; returns their number or < 0 */
+int pb200_h5_list(pb200_h5* f, const char* group, char* buf, int capacity);
+
+/* the assembled tables of an input file (owned by the returned object; the desc points into it) */
+typedef struct pb200_h5_problem pb200_h5_problem;
+int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_problem** out);
+const pb200_problem_desc* pb200_h5_problem_desc(pb200_h5_problem* p);
+const struct pb200_hier_desc* pb200_h5_problem_hier(pb200_h5_problem* p); /* NULL: no hierarchical tables */
+void pb200_h5_problem_free(pb200_h5_problem* p);
+/* pb200_h5_load_problem + pb200_create (+ pb200_hier_attach when the file has the tables) */
+int pb200_create_from_hdf5(const char* path, const char* model_name, int device, pb200_handle** out);
+
 /* hierarchical optimisation -------------------------------------------- */
 /*
  * Analytic inner problem of parpe::HierarchicalOptimizationWrapper

@@ -23,7 +23,7 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v
 
 
 def _sources():
-    return [os.path.join(CSRC, "parpe_b200.cu"), os.path.join(CSRC, "microbench.cu")] + sorted(glob.glob(os.path.join(CSRC, "models", "inst_*.cu")))
+    return [os.path.join(CSRC, "parpe_b200.cu"), os.path.join(CSRC, "microbench.cu"), os.path.join(CSRC, "h5input.cu")] + sorted(glob.glob(os.path.join(CSRC, "models", "inst_*.cu")))
 
 
 def _deps():

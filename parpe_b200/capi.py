@@ -20,6 +20,9 @@ EXPORTED_SYMBOLS = [
     "pb200_evaluate", "pb200_evaluate_device", "pb200_last_launch", "pb200_get_condition_results",
     "pb200_get_model_outputs", "pb200_measure_fp64_peak", "pb200_set_allreduce", "pb200_hier_attach", "pb200_hier_num_outer", "pb200_hier_evaluate",
     "pb200_set_option", "pb200_nccl_unique_id", "pb200_nccl_init", "pb200_last_transfer_bytes", "pb200_linsol_info",
+    "pb200_h5_open", "pb200_h5_close", "pb200_h5_exists", "pb200_h5_dataset_info", "pb200_h5_read_double",
+    "pb200_h5_attribute_double", "pb200_h5_list", "pb200_h5_load_problem", "pb200_h5_problem_desc",
+    "pb200_h5_problem_hier", "pb200_h5_problem_free", "pb200_create_from_hdf5",
 ]
 # pb200_set_option keys (include/parpe_b200.h)
 OPT_REORDER, OPT_ORDER_REFRESH, OPT_KERNEL_VARIANT, OPT_CTAS_PER_SM, OPT_SYNC_PERIOD, OPT_STAGE_SYNC = 1, 2, 3, 4, 5, 6
@@ -74,6 +77,23 @@ def lib():
     L.pb200_nccl_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
     L.pb200_last_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.pb200_linsol_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
+    L.pb200_h5_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.pb200_h5_close.argtypes = [C.c_void_p]
+    L.pb200_h5_close.restype = None
+    L.pb200_h5_exists.argtypes = [C.c_void_p, C.c_char_p]
+    L.pb200_h5_dataset_info.argtypes = [C.c_void_p, C.c_char_p, ip, C.POINTER(C.c_int64), ip, ip]
+    L.pb200_h5_read_double.argtypes = [C.c_void_p, C.c_char_p, dp, C.c_int64]
+    L.pb200_h5_read_double.restype = C.c_int64
+    L.pb200_h5_attribute_double.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, dp, C.c_int]
+    L.pb200_h5_list.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+    L.pb200_h5_load_problem.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.pb200_h5_problem_desc.argtypes = [C.c_void_p]
+    L.pb200_h5_problem_desc.restype = C.POINTER(ProblemDesc)
+    L.pb200_h5_problem_hier.argtypes = [C.c_void_p]
+    L.pb200_h5_problem_hier.restype = C.POINTER(HierDesc)
+    L.pb200_h5_problem_free.argtypes = [C.c_void_p]
+    L.pb200_h5_problem_free.restype = None
+    L.pb200_create_from_hdf5.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     _lib = L
     return L
 
@@ -121,3 +141,49 @@ def dptr(a):
 
 def iptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
+
+
+class H5File:
+    """parPE input files through the library's built-in HDF5 reader (pb200_h5_*; no HDF5 library needed)."""
+
+    def __init__(self, path):
+        self._h = C.c_void_p()
+        check(lib().pb200_h5_open(str(path).encode(), C.byref(self._h)), "pb200_h5_open")
+
+    def close(self):
+        if self._h:
+            lib().pb200_h5_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def exists(self, path):
+        return bool(lib().pb200_h5_exists(self._h, path.encode()))
+
+    def info(self, path):
+        rank, cls, size = C.c_int(), C.c_int(), C.c_int()
+        dims = (C.c_int64 * 8)()
+        check(lib().pb200_h5_dataset_info(self._h, path.encode(), C.byref(rank), dims, C.byref(cls), C.byref(size)),
+              "pb200_h5_dataset_info")
+        return dict(shape=tuple(int(dims[i]) for i in range(rank.value)), type_class=cls.value, type_size=size.value)
+
+    def read(self, path):
+        n = check(lib().pb200_h5_read_double(self._h, path.encode(), None, 0), "pb200_h5_read_double")
+        out = np.zeros(max(int(n), 1))
+        check(lib().pb200_h5_read_double(self._h, path.encode(), dptr(out), len(out)), "pb200_h5_read_double")
+        return out[:n].reshape(self.info(path)["shape"])
+
+    def attribute(self, obj, name):
+        out = np.zeros(64)
+        n = check(lib().pb200_h5_attribute_double(self._h, obj.encode(), name.encode(), dptr(out), len(out)),
+                  "pb200_h5_attribute_double")
+        return out[:n]
+
+    def list(self, group):
+        buf = C.create_string_buffer(1 << 20)
+        check(lib().pb200_h5_list(self._h, group.encode(), buf, len(buf)), "pb200_h5_list")
+        return [s for s in buf.value.decode().split("\n") if s]

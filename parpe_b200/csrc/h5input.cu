@@ -1,0 +1,289 @@
+// h5input.cu -- the data-provider role: parPE's HDF5 parameter-estimation input file -> the tables of
+// pb200_problem_desc (host code only; no CUDA in this file).
+//
+// What it replaces in the reference: MultiConditionDataProviderHDF5's constructor and getters
+// (src/parpeamici/multiConditionDataProvider.cpp:42-60 dataset paths; :84-102 mapping column of a condition;
+// :194-206 pscaleSimulation row; :224-250 simulationConditions -> column of /fixedParameters/k; :302-321
+// /measurements/{t,y,ysigma}/<i>; parameterOverrides :126-169) and AnalyticalParameterHdf5Reader
+// (hierarchicalOptimizationAnalyticalParameterProvider.cpp: /{scaling,offset,sigma}ParameterIndices and
+// ...MapToObservables), reading the layout of doc/hdf5.md:1-172 once, at create time.  The file is parsed by
+// h5min.h (no HDF5 library in this image).
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/parpe_b200.h"
+#include "h5min.h"
+
+namespace pb200 {
+int fail_message(int code, const std::string& msg);  // parpe_b200.cu: sets pb200_last_error
+}
+
+using pb200::H5Error;
+using pb200::H5File;
+
+struct pb200_h5 {
+    std::unique_ptr<H5File> f;
+};
+
+struct pb200_h5_problem {
+    std::string model_name;
+    std::vector<int64_t> t_offsets;
+    std::vector<double> t, y, sigma, k, overrides;
+    std::vector<int32_t> mapping, pscale_sim, pscale_opt;
+    std::vector<int32_t> scaling_idx, offset_idx, sigma_idx, scaling_map, offset_map, sigma_map;
+    pb200_problem_desc desc{};
+    pb200_hier_desc hier{};
+    bool has_hier = false;
+};
+
+namespace {
+template <class F>
+int guarded(F&& fn) {
+    try {
+        return fn();
+    } catch (std::exception const& e) {
+        return pb200::fail_message(PB200_ERR_ARG, e.what());
+    }
+}
+
+std::vector<int32_t> to_i32(const std::vector<int64_t>& v) { return std::vector<int32_t>(v.begin(), v.end()); }
+}  // namespace
+
+extern "C" {
+
+int pb200_h5_open(const char* path, pb200_h5** out) {
+    if (!path || !out) return pb200::fail_message(PB200_ERR_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&] {
+        auto h = std::make_unique<pb200_h5>();
+        h->f = std::make_unique<H5File>(path);
+        *out = h.release();
+        return 0;
+    });
+}
+void pb200_h5_close(pb200_h5* h) { delete h; }
+
+int pb200_h5_exists(pb200_h5* h, const char* path) {
+    if (!h || !path) return 0;
+    try {
+        return h->f->exists(path) ? 1 : 0;
+    } catch (std::exception const&) {
+        return 0;
+    }
+}
+
+int pb200_h5_dataset_info(pb200_h5* h, const char* path, int* rank, int64_t* dims, int* type_class, int* type_size) {
+    if (!h || !path) return pb200::fail_message(PB200_ERR_ARG, "null argument");
+    return guarded([&] {
+        const H5File::Dataset d = h->f->info(path);
+        if (rank) *rank = d.rank;
+        if (dims)
+            for (int i = 0; i < d.rank && i < 8; ++i) dims[i] = (int64_t)d.dims[i];
+        if (type_class) *type_class = d.type_class;
+        if (type_size) *type_size = d.type_size;
+        return 0;
+    });
+}
+
+int64_t pb200_h5_read_double(pb200_h5* h, const char* path, double* out, int64_t capacity) {
+    if (!h || !path) return pb200::fail_message(PB200_ERR_ARG, "null argument");
+    int64_t n = 0;
+    const int rc = guarded([&] {
+        const std::vector<double> v = h->f->read_double(path);
+        n = (int64_t)v.size();
+        if (out) {
+            if (capacity < n) throw H5Error(std::string(path) + ": output buffer too small");
+            std::memcpy(out, v.data(), sizeof(double) * v.size());
+        }
+        return 0;
+    });
+    return rc < 0 ? rc : n;
+}
+
+int pb200_h5_attribute_double(pb200_h5* h, const char* obj, const char* name, double* out, int capacity) {
+    if (!h || !obj || !name) return pb200::fail_message(PB200_ERR_ARG, "null argument");
+    int n = 0;
+    const int rc = guarded([&] {
+        const std::vector<double> v = h->f->attribute(obj, name);
+        n = (int)v.size();
+        if (out) {
+            if (capacity < n) throw H5Error(std::string(name) + ": output buffer too small");
+            std::memcpy(out, v.data(), sizeof(double) * v.size());
+        }
+        return 0;
+    });
+    return rc < 0 ? rc : n;
+}
+
+int pb200_h5_list(pb200_h5* h, const char* group, char* buf, int capacity) {
+    if (!h || !group) return pb200::fail_message(PB200_ERR_ARG, "null argument");
+    int n = 0;
+    const int rc = guarded([&] {
+        std::string all;
+        for (auto& s : h->f->list(group)) {
+            all += s;
+            all += '\n';
+            ++n;
+        }
+        if (buf) {
+            if ((int)all.size() + 1 > capacity) throw H5Error("list: output buffer too small");
+            std::memcpy(buf, all.c_str(), all.size() + 1);
+        }
+        return 0;
+    });
+    return rc < 0 ? rc : n;
+}
+
+int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_problem** out) {
+    if (!path || !model_name || !out) return pb200::fail_message(PB200_ERR_ARG, "null argument");
+    *out = nullptr;
+    int nx = 0, np = 0, nk = 0, ny = 0;
+    if (pb200_model_info(model_name, &nx, &np, &nk, &ny) != 0) return PB200_ERR_MODEL;
+    return guarded([&] {
+        H5File f(path);
+        auto P = std::make_unique<pb200_h5_problem>();
+        P->model_name = model_name;
+        // ---- /fixedParameters: simulationConditions [C x 2] = (preequilibration column, simulation column) of k [nk x nVec]
+        const auto sc_info = f.info("/fixedParameters/simulationConditions");
+        if (sc_info.rank != 2 || sc_info.dims[1] != 2) throw H5Error("/fixedParameters/simulationConditions must be [n x 2]");
+        const int C = (int)sc_info.dims[0];
+        const auto sc = f.read_int("/fixedParameters/simulationConditions");
+        std::vector<double> K;
+        uint64_t nvec = 0;
+        if (nk > 0) {
+            const auto k_info = f.info("/fixedParameters/k");
+            if (k_info.rank != 2 || (int)k_info.dims[0] != nk) throw H5Error("/fixedParameters/k must be [nk x nConditionVectors] with the model's nk");
+            nvec = k_info.dims[1];
+            K = f.read_double("/fixedParameters/k");
+        }
+        P->k.resize((size_t)C * nk);
+        for (int c = 0; c < C; ++c) {
+            if (sc[2 * c] >= 0)
+                throw H5Error("simulation condition " + std::to_string(c) + " has a pre-equilibration condition: not supported "
+                              "(SURVEY 8(f) rank 2)");
+            const int64_t col = sc[2 * c + 1];
+            if (col < 0 || (nk > 0 && (uint64_t)col >= nvec)) throw H5Error("simulationConditions refers to a missing column of k");
+            for (int i = 0; i < nk; ++i) P->k[(size_t)c * nk + i] = K[(size_t)i * nvec + col];
+        }
+        // ---- /measurements/{t,y,ysigma}/<c>
+        P->t_offsets.assign(1, 0);
+        for (int c = 0; c < C; ++c) {
+            const std::string id = std::to_string(c);
+            const auto tc = f.read_double("/measurements/t/" + id);
+            const auto yc = f.read_double("/measurements/y/" + id);
+            const auto sg = f.read_double("/measurements/ysigma/" + id);
+            if (yc.size() != tc.size() * (size_t)ny || sg.size() != yc.size())
+                throw H5Error("/measurements/{y,ysigma}/" + id + " must be [nt x ny] with the model's ny");
+            P->t.insert(P->t.end(), tc.begin(), tc.end());
+            P->y.insert(P->y.end(), yc.begin(), yc.end());
+            P->sigma.insert(P->sigma.end(), sg.begin(), sg.end());
+            P->t_offsets.push_back((int64_t)P->t.size());
+        }
+        // ---- /parameters
+        P->pscale_opt = to_i32(f.read_int("/parameters/pscaleOptimization"));
+        const int n_opt = (int)P->pscale_opt.size();
+        P->mapping.resize((size_t)C * np);
+        if (f.exists("/parameters/optimizationSimulationMapping")) {
+            const auto mi = f.info("/parameters/optimizationSimulationMapping");
+            if (mi.rank != 2 || (int)mi.dims[0] != np || (int)mi.dims[1] != C)
+                throw H5Error("/parameters/optimizationSimulationMapping must be [np x nConditions]");
+            const auto M = f.read_int("/parameters/optimizationSimulationMapping");
+            for (int c = 0; c < C; ++c)
+                for (int i = 0; i < np; ++i) P->mapping[(size_t)c * np + i] = (int32_t)M[(size_t)i * C + c];
+        } else {  // trivial default mapping (multiConditionDataProvider.cpp:97-101)
+            for (int c = 0; c < C; ++c)
+                for (int i = 0; i < np; ++i) P->mapping[(size_t)c * np + i] = i;
+        }
+        {
+            const auto si = f.info("/parameters/pscaleSimulation");
+            if (si.rank != 2 || (int)si.dims[0] != C || (int)si.dims[1] != np)
+                throw H5Error("/parameters/pscaleSimulation must be [nConditions x np]");
+            P->pscale_sim = to_i32(f.read_int("/parameters/pscaleSimulation"));
+        }
+        if (f.exists("/parameters/parameterOverrides")) {
+            const auto oi = f.info("/parameters/parameterOverrides");
+            if (oi.rank != 2 || (int)oi.dims[0] != np || (int)oi.dims[1] != C)
+                throw H5Error("/parameters/parameterOverrides must be [np x nConditions]");
+            const auto O = f.read_double("/parameters/parameterOverrides");
+            P->overrides.resize((size_t)C * np);
+            for (int c = 0; c < C; ++c)
+                for (int i = 0; i < np; ++i) P->overrides[(size_t)c * np + i] = O[(size_t)i * C + c];
+        }
+        // ---- /amiciOptions attributes (deps/AMICI/src/hdf5.cpp readSolverSettingsFromHDF5)
+        pb200_problem_desc& d = P->desc;
+        d.abi_version = PB200_ABI_VERSION;
+        d.model_name = P->model_name.c_str();
+        d.n_conditions = C;
+        d.n_opt = n_opt;
+        d.np = np; d.nk = nk; d.ny = ny;
+        d.t0 = 0.0;
+        auto opt = [&](const char* name, double dflt) {
+            return f.has_attribute("/amiciOptions", name) ? f.attribute("/amiciOptions", name).at(0) : dflt;
+        };
+        d.atol = opt("atol", 1e-16);
+        d.rtol = opt("rtol", 1e-8);
+        d.maxsteps = (int32_t)opt("maxsteps", 10000);
+        d.stldet = (int32_t)opt("stldet", 1);
+        d.sensi_errcon = 1;
+        d.num_trials = 6;
+        d.relaxation_factor = 100.0;
+        d.t_offsets = P->t_offsets.data();
+        d.t = P->t.data(); d.y = P->y.data(); d.sigma = P->sigma.data(); d.k = P->k.data();
+        d.mapping = P->mapping.data(); d.pscale_sim = P->pscale_sim.data(); d.pscale_opt = P->pscale_opt.data();
+        d.overrides = P->overrides.empty() ? nullptr : P->overrides.data();
+        // ---- hierarchical optimisation tables (optional; empty datasets may be omitted: doc/hdf5.md:118-126)
+        auto read_idx = [&](const char* p, std::vector<int32_t>& v) {
+            if (f.exists(p)) v = to_i32(f.read_int(p));
+        };
+        auto read_map = [&](const char* p, std::vector<int32_t>& v) {
+            if (!f.exists(p)) return;
+            const auto mi = f.info(p);
+            if (mi.count() == 0) return;
+            if (mi.rank != 2 || mi.dims[1] != 3) throw H5Error(std::string(p) + " must be [n x 3]");
+            v = to_i32(f.read_int(p));
+        };
+        read_idx("/scalingParameterIndices", P->scaling_idx);
+        read_idx("/offsetParameterIndices", P->offset_idx);
+        read_idx("/sigmaParameterIndices", P->sigma_idx);
+        read_map("/scalingParametersMapToObservables", P->scaling_map);
+        read_map("/offsetParametersMapToObservables", P->offset_map);
+        read_map("/sigmaParametersMapToObservables", P->sigma_map);
+        P->has_hier = !(P->scaling_idx.empty() && P->offset_idx.empty() && P->sigma_idx.empty());
+        pb200_hier_desc& hd = P->hier;
+        hd.n_scaling = (int32_t)P->scaling_idx.size(); hd.n_offset = (int32_t)P->offset_idx.size(); hd.n_sigma = (int32_t)P->sigma_idx.size();
+        hd.scaling_idx = P->scaling_idx.data(); hd.offset_idx = P->offset_idx.data(); hd.sigma_idx = P->sigma_idx.data();
+        hd.n_scaling_rows = (int32_t)P->scaling_map.size() / 3; hd.n_offset_rows = (int32_t)P->offset_map.size() / 3;
+        hd.n_sigma_rows = (int32_t)P->sigma_map.size() / 3;
+        hd.scaling_map = P->scaling_map.data(); hd.offset_map = P->offset_map.data(); hd.sigma_map = P->sigma_map.data();
+        *out = P.release();
+        return 0;
+    });
+}
+
+const pb200_problem_desc* pb200_h5_problem_desc(pb200_h5_problem* p) { return p ? &p->desc : nullptr; }
+const pb200_hier_desc* pb200_h5_problem_hier(pb200_h5_problem* p) { return (p && p->has_hier) ? &p->hier : nullptr; }
+void pb200_h5_problem_free(pb200_h5_problem* p) { delete p; }
+
+int pb200_create_from_hdf5(const char* path, const char* model_name, int device, pb200_handle** out) {
+    if (!out) return pb200::fail_message(PB200_ERR_ARG, "null argument");
+    *out = nullptr;
+    pb200_h5_problem* P = nullptr;
+    int rc = pb200_h5_load_problem(path, model_name, &P);
+    if (rc != 0) return rc;
+    rc = pb200_create(&P->desc, device, out);
+    if (rc == 0 && P->has_hier) {
+        rc = pb200_hier_attach(*out, &P->hier);
+        if (rc != 0) {
+            pb200_destroy(*out);
+            *out = nullptr;
+        }
+    }
+    pb200_h5_problem_free(P);  // (the tables were copied to the device)
+    return rc;
+}
+
+}  // extern "C"

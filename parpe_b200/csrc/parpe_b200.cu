@@ -44,6 +44,7 @@ static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+int fail_message(int code, const std::string& msg) { return fail(code, msg); }
 #define PB_CUDA(call)                                                                              \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \

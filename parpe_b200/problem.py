@@ -38,6 +38,13 @@ class B200SummedGradientFunction:
             self._hd = tables.hier.to_desc()
             capi.check(L.pb200_hier_attach(self._h, C.byref(self._hd)), "pb200_hier_attach")
 
+    @classmethod
+    def from_hdf5(cls, path, model_name: str, device: int = 0):
+        """The data-provider role: a handle straight from a parPE parameter-estimation input file
+        (doc/hdf5.md; pb200_create_from_hdf5).  ``tables`` is rebuilt from the file for the Python side."""
+        tab = tables_from_hdf5(path, model_name)
+        return cls(tab, device=device)
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             capi.lib().pb200_destroy(self._h)
@@ -184,3 +191,38 @@ class B200SummedGradientFunction:
                                                        capi.dptr(grad), capi.dptr(full), C.byref(sec)),
                         "pb200_hier_evaluate")
         return dict(status=rc, fval=fval.value, grad=grad, full_parameters=full, seconds=sec.value)
+
+
+def tables_from_hdf5(path, model_name: str) -> ProblemTables:
+    """ProblemTables of a parPE input file, assembled by the library (pb200_h5_load_problem): what
+    MultiConditionDataProviderHDF5 serves per condition, read once."""
+    from .tables import HierTables
+    L = capi.lib()
+    P = C.c_void_p()
+    capi.check(L.pb200_h5_load_problem(str(path).encode(), model_name.encode(), C.byref(P)), "pb200_h5_load_problem")
+    try:
+        d = L.pb200_h5_problem_desc(P).contents
+        Cn, np_, nk, ny, n_opt = d.n_conditions, d.np, d.nk, d.ny, d.n_opt
+        arr = lambda ptr, n, dt: np.ctypeslib.as_array(ptr, shape=(max(n, 1),))[:n].astype(dt).copy()
+        t_off = arr(d.t_offsets, Cn + 1, np.int64)
+        nt = int(t_off[-1])
+        tab = ProblemTables(
+            model_name=model_name, np_=np_, nk=nk, ny=ny, n_opt=n_opt, t_offsets=t_off, t=arr(d.t, nt, np.float64),
+            y=arr(d.y, nt * ny, np.float64), sigma=arr(d.sigma, nt * ny, np.float64), k=arr(d.k, Cn * nk, np.float64),
+            mapping=arr(d.mapping, Cn * np_, np.int32), pscale_sim=arr(d.pscale_sim, Cn * np_, np.int32),
+            pscale_opt=arr(d.pscale_opt, n_opt, np.int32),
+            overrides=arr(d.overrides, Cn * np_, np.float64) if d.overrides else None, t0=d.t0, atol=d.atol, rtol=d.rtol,
+            maxsteps=d.maxsteps, stldet=d.stldet, sensi_errcon=d.sensi_errcon, num_trials=d.num_trials,
+            relaxation_factor=d.relaxation_factor)
+        hp = L.pb200_h5_problem_hier(P)
+        if hp:
+            h = hp.contents
+            tab.hier = HierTables(
+                scaling_idx=arr(h.scaling_idx, h.n_scaling, np.int32), offset_idx=arr(h.offset_idx, h.n_offset, np.int32),
+                sigma_idx=arr(h.sigma_idx, h.n_sigma, np.int32),
+                scaling_map=arr(h.scaling_map, 3 * h.n_scaling_rows, np.int32),
+                offset_map=arr(h.offset_map, 3 * h.n_offset_rows, np.int32),
+                sigma_map=arr(h.sigma_map, 3 * h.n_sigma_rows, np.int32))
+        return tab
+    finally:
+        L.pb200_h5_problem_free(P)

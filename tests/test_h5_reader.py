@@ -1,0 +1,139 @@
+"""The built-in HDF5 reader (parpe_b200/csrc/h5min.h behind pb200_h5_*) and the input-file -> tables
+assembly (pb200_h5_load_problem: the MultiConditionDataProviderHDF5 role).
+
+Pinned two ways: (1) on a file written by the REAL HDF5 library -- the reference tree's own
+deps/AMICI/tests/cpp/testOptions.h5 (read in place; values from deps/AMICI/tests/cpp/testfunctions.h /
+the model tests that consume it) -- and (2) on parPE-layout input files written by the committed minimal writer
+tools/h5write_min.py (contiguous, chunked and gzip-compressed datasets), round-tripped against the tables
+they were written from; on a GPU the handle created from the file gives the same objective as the handle
+created from the in-memory tables."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from parpe_b200 import capi, synth
+from parpe_b200.problem import B200SummedGradientFunction, tables_from_hdf5
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+REF_FILE = "/root/reference/deps/AMICI/tests/cpp/testOptions.h5"
+
+
+def test_reads_a_file_written_by_the_hdf5_library():
+    if not os.path.exists(REF_FILE):
+        pytest.skip("/root/reference not present")
+    f = capi.H5File(REF_FILE)
+    top = f.list("/")
+    assert top == ["model_calvetti", "model_dirac", "model_events", "model_jakstat_adjoint", "model_nested_events",
+                   "model_neuron", "model_robertson", "model_steadystate"]
+    cases = f.list("/model_steadystate")
+    assert "sensiforward" in cases and "nosensi" in cases and len(cases) == 14   # (a multi-entry group B-tree)
+    g = "/model_steadystate/sensiforward/options"
+    assert f.list(g) == ["kappa", "sens_ind", "theta", "ts"]
+    # the steady-state example's nominal parameters (log10 of 1, 0.5, 0.4, 2, 0.1) and constants -- the same
+    # numbers examples/parpeamici/steadystate/exampleSteadystateScaledTest.h:40-48 uses
+    np.testing.assert_allclose(f.read(g + "/theta"), np.log10([1.0, 0.5, 0.4, 2.0, 0.1]), atol=1e-8)
+    np.testing.assert_allclose(f.read(g + "/kappa"), [0.1, 0.4, 0.7, 1.0])
+    assert np.array_equal(f.read(g + "/sens_ind"), [0, 1, 2, 3, 4])
+    assert f.info(g + "/theta") == dict(shape=(5,), type_class=1, type_size=8)
+    assert f.info(g + "/sens_ind") == dict(shape=(5,), type_class=0, type_size=4)
+    # solver settings as attributes (deps/AMICI/src/hdf5.cpp readSolverSettingsFromHDF5): AMICI's defaults,
+    # linsol = 9 is LinearSolver::KLU
+    assert f.attribute(g, "atol")[0] == 1e-16 and f.attribute(g, "rtol")[0] == 1e-8
+    assert f.attribute(g, "maxsteps")[0] == 10000 and f.attribute(g, "sensi")[0] == 1 and f.attribute(g, "sensi_meth")[0] == 1
+    assert f.attribute(g, "linsol")[0] == 9 and f.attribute(g, "stldet")[0] == 1 and f.attribute(g, "newton_maxsteps")[0] == 40
+    ts = f.read(g + "/ts")
+    assert ts.shape == (51,) and ts[0] == 0.0 and ts[1] == pytest.approx(100.0 / 49.0) and np.all(np.diff(ts) > 0)
+    assert not f.exists(g + "/no_such_dataset")
+    with pytest.raises(capi.B200LibraryError):
+        f.read(g + "/no_such_dataset")
+
+
+def test_rejects_non_hdf5(tmp_path):
+    p = tmp_path / "x.h5"
+    p.write_bytes(b"not an hdf5 file at all" * 10)
+    with pytest.raises(capi.B200LibraryError, match="HDF5"):
+        capi.H5File(p)
+
+
+CASES = [("steadystate_scaled", 5, dict(scale="mixed", condition_specific=2, sigma_mode="mixed", missing_fraction=0.2, ragged=True)),
+         ("boehm", 4, dict(scale="log10", holes=2)),
+         ("net32", 3, dict(scale="log10"))]
+
+
+@pytest.mark.parametrize("compress", [True, False], ids=["gzip-chunked", "contiguous"])
+@pytest.mark.parametrize("model,C,kw", CASES, ids=[c[0] for c in CASES])
+def test_input_file_round_trip(tmp_path, model, C, kw, compress):
+    """ProblemTables -> parPE input file (tools/h5write_min.py) -> pb200_h5_load_problem: every table identical
+    (bit for bit: NaN markers of missing data / model sigmas included), transposed layouts resolved as the
+    reference's hyperslab reads do."""
+    import h5write_min
+    tab = synth.make_problem(model, C, seed=3, **kw)
+    path = tmp_path / "input.h5"
+    h5write_min.write_parpe_input(str(path), tab, compress=compress)
+    f = capi.H5File(path)
+    assert f.info("/parameters/optimizationSimulationMapping")["shape"] == (tab.np_, C)
+    assert f.info("/fixedParameters/k")["shape"] == (tab.nk, C)
+    assert f.list("/measurements/y") == sorted(str(c) for c in range(C))
+    got = tables_from_hdf5(path, model)
+    assert got.n_conditions == C and got.n_opt == tab.n_opt
+    for name in ("t_offsets", "t", "k", "mapping", "pscale_sim", "pscale_opt"):
+        assert np.array_equal(getattr(got, name), getattr(tab, name)), name
+    for name in ("y", "sigma"):
+        a, b = getattr(got, name), getattr(tab, name)
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)]), name
+    if tab.overrides is None:
+        assert got.overrides is None
+    else:
+        assert np.array_equal(np.isnan(got.overrides), np.isnan(tab.overrides))
+        assert np.array_equal(got.overrides[~np.isnan(got.overrides)], tab.overrides[~np.isnan(tab.overrides)])
+    assert got.atol == tab.atol and got.rtol == tab.rtol and got.maxsteps == tab.maxsteps and got.stldet == tab.stldet
+
+
+def test_hierarchical_tables_and_preequilibration(tmp_path):
+    import h5write_min
+    tab = synth.steadystate_hierarchical(6, seed=1)
+    path = tmp_path / "hier.h5"
+    h5write_min.write_parpe_input(str(path), tab)
+    got = tables_from_hdf5(path, "steadystate_scaled")
+    assert got.hier is not None
+    for name in ("scaling_idx", "offset_idx", "sigma_idx", "scaling_map", "offset_map", "sigma_map"):
+        assert np.array_equal(getattr(got.hier, name), getattr(tab.hier, name)), name
+    # a pre-equilibration condition is refused, not ignored
+    w = h5write_min.H5Writer()
+    w.dataset("/fixedParameters/simulationConditions", np.array([[0, 0]], dtype=np.int32))
+    w.dataset("/fixedParameters/k", np.ones((tab.nk, 1)))
+    p2 = tmp_path / "preeq.h5"
+    w.save(str(p2))
+    with pytest.raises(capi.B200LibraryError, match="pre-equilibration"):
+        tables_from_hdf5(p2, "steadystate_scaled")
+    with pytest.raises(capi.B200LibraryError):
+        tables_from_hdf5(path, "no_such_model")
+
+
+@pytest.mark.gpu
+def test_handle_from_input_file_matches_handle_from_tables(tmp_path, oracle_available):
+    import h5write_min
+    from oracle.binding import OracleProblem
+    from tests.util import assert_grad_close, assert_llh_close
+    tab = synth.make_problem("boehm", 6, seed=3, scale="mixed", holes=1, sigma_mode="mixed")
+    path = tmp_path / "boehm.h5"
+    h5write_min.write_parpe_input(str(path), tab)
+    theta = synth.random_theta(tab, seed=1, width=0.3)
+    a = B200SummedGradientFunction.from_hdf5(path, "boehm").evaluate(theta)
+    b = B200SummedGradientFunction(tab).evaluate(theta)
+    assert a[0] == b[0] == 0 and a[1] == b[1] and np.array_equal(a[2], b[2])
+    ro = OracleProblem(tab).evaluate(theta)
+    assert_llh_close(a[1], ro["fval"])
+    assert_grad_close(a[2], ro["grad"])
+    # hierarchical tables ride along: pb200_create_from_hdf5 attaches them
+    import ctypes as C
+    htab = synth.fujita_hierarchical(12, seed=2)
+    hp = tmp_path / "fujita.h5"
+    h5write_min.write_parpe_input(str(hp), htab)
+    h = C.c_void_p()
+    capi.check(capi.lib().pb200_create_from_hdf5(str(hp).encode(), b"fujita", 0, C.byref(h)), "pb200_create_from_hdf5")
+    assert capi.lib().pb200_hier_num_outer(h) == htab.n_opt - len(htab.hier.inner_idx)
+    capi.lib().pb200_destroy(h)
