@@ -207,6 +207,7 @@ struct BdfTeam {
     bool fuse_newton = true;   // sparse path: right-hand sides + forward substitution, backward substitution + update + norm
     bool b_forwarded_ = false; // w.b already holds the forward-substituted right-hand sides
     bool fwd_ok_ = false;      // the factors in w.luV are the ones the coming solve uses (no setup pending)
+    bool acor_zero_ = false;   // the sensitivity columns of acor are zero but the zeros have not been written
     int fail_, ret_;
     // phase cycle counters (device: clock64 of thread 0's SM; exported in stats[14..15] packed as
     // two 32-bit fields of kilo-cycles each: [14] = inversion panel | inversion update, [15] = solve GEMM | model+rhs)
@@ -411,6 +412,13 @@ struct BdfTeam {
         return bad;
     }
 
+    PB_HD void materialize_acor_zero() {
+        tm.sync();
+        PT_FOR(e, nx, (ns + 1) * nx) w.acor[e] = 0.0;
+        tm.sync();
+        acor_zero_ = false;
+    }
+
     /// rhs_sens(false) fused with the forward substitution of the sparse solver: the right-hand sides of a
     /// batch of columns are formed in the staging area (permuted rows, Z[row][column]), substituted there,
     /// and reach w.b already as  y = L11^-1 b1 | b2' = b2 - L21 y  -- one write of w.b instead of a write, a
@@ -432,6 +440,7 @@ struct BdfTeam {
         const int jw = T.jell_w;
         const int nx = this->nx;
         const double rl1 = this->rl1, gamma = this->gamma;
+        const bool azero = acor_zero_;
         // staging area: corrected sensitivity vectors of the batch S[column][row] | right-hand sides Z[row][column]
         // | factor values
         tm.sync();
@@ -450,7 +459,7 @@ struct BdfTeam {
             PT_FOR(x, 0, nel) {
                 const int cl = x / nx, i = x - cl * nx;
                 const size_t e = (size_t)(cb + cl) * nx + i;
-                const double a = ac[e];
+                const double a = azero ? 0.0 : ac[e];
                 S[(size_t)cl * nx + i] = z0[e] + a;
                 Z[(size_t)iord[i] * CB + cl] = rl1 * z1[e] + a;
             }
@@ -521,6 +530,7 @@ struct BdfTeam {
             // (sparse solver, no setup pending: right-hand sides and forward substitution in one staging pass)
             const bool fwd = fuse_newton && lin_sparse && !raw && fwd_ok_ &&
                              w.stage_doubles - (2 * SP.nV > w.stage_doubles ? 0 : SP.nV) >= 2 * nx;
+            if (acor_zero_ && !fwd) materialize_acor_zero();
             bad = fwd ? rhs_sens_fwd() : rhs_sens(raw);
             nfSe += ns;
             bad = tm.any(bad);
@@ -1467,6 +1477,7 @@ struct BdfTeam {
         const int nbatch = (ncols + bc_max - 1) / bc_max;
         const int bc = (ncols + nbatch - 1) / nbatch;
         const int nU0 = n1 + SP.nnzL;
+        const bool azero = update && acor_zero_ && cmin >= 1;
         double loc = 0.0;
         for (int c0 = cmin; c0 <= cmax; c0 += bc) {
             const int nb = (cmax + 1 - c0 < bc) ? cmax + 1 - c0 : bc;
@@ -1517,7 +1528,7 @@ struct BdfTeam {
                         const int cl = ok ? x / nx : 0, i = ok ? x - cl * nx : 0;
                         g[u] = i + (size_t)(c0 + cl) * nx;
                         zi[u] = (int)iord[i] * bc + cl;
-                        a[u] = ok ? acor[g[u]] : 0.0;
+                        a[u] = (ok && !azero) ? acor[g[u]] : 0.0;
                         ew[u] = ok ? ewt[g[u]] : 0.0;
                         d[u] = ok ? nsc * Z[zi[u]] : 0.0;
                     }
@@ -1543,6 +1554,7 @@ struct BdfTeam {
         }
         tm.sync();
         if (!update) return 0.0;
+        if (azero) acor_zero_ = false;  // acor now holds the first correction
         return sqrt(tm.max(loc) / (double)nx);
     }
 
@@ -1672,6 +1684,7 @@ struct BdfTeam {
         if (lin_sparse) {
             // sparse factors + inverse of the Schur block (forward substitution already done by the fused
             // right-hand side of the sensitivity phase)
+            if (acor_zero_ && cmin >= 1 && !fuse_newton) materialize_acor_zero();
             if (!b_forwarded_) sparse_forward(cmin, cmax);
             b_forwarded_ = false;
             const long long t_d0 = now();
@@ -1684,6 +1697,7 @@ struct BdfTeam {
             cyc_solve += t_e - t_s0;
             if (fuse_newton) return del;
         } else {
+            if (acor_zero_ && cmin >= 1) materialize_acor_zero();
             solve_dense(cmin, cmax, nsc);
             tm.sync();
             cyc_solve += now() - t_s0;
@@ -1887,7 +1901,14 @@ struct BdfTeam {
                             (nst >= nstlp + cv::MSBP) || (fabs(gamrat - 1.0) > cv::DGMAX_LSETUP);
         }
         tm.sync();
-        PT_FOR(e, cmin * nx, (cmax + 1) * nx) w.acor[e] = 0.0;
+        // acor = 0 at the start of the iteration.  Sensitivity phase on the fused sparse path: the zeros are not
+        // written (and not read back by the first right-hand side / update) -- acor_zero_ stands for them until
+        // the first update stores acor = delta
+        acor_zero_ = (phase == PH_SENS) && fuse_newton && lin_sparse && !setup_pending &&
+                     w.stage_doubles - (2 * SP.nV > w.stage_doubles ? 0 : SP.nV) >= 2 * nx;
+        if (!acor_zero_) {
+            PT_FOR(e, cmin * nx, (cmax + 1) * nx) w.acor[e] = 0.0;
+        }
         bool jbad = false;
         bool top = true;
         int m_it = 0;
@@ -1950,6 +1971,7 @@ struct BdfTeam {
                 top = true;
                 m_it = 0;
                 tm.sync();
+                acor_zero_ = false;
                 PT_FOR(e, cmin * nx, (cmax + 1) * nx) w.acor[e] = 0.0;
                 continue;
             }

@@ -47,6 +47,12 @@ struct B200ProblemTables {
     double integrationToleranceRelaxationFactor = 100.0; // PARPE_INTEGRATION_TOLERANCE_RELAXATION_FACTOR
     int lanesPerCondition = 0;
 
+    /// The tables of a parPE parameter-estimation input file (doc/hdf5.md), assembled by the library's built-in
+    /// HDF5 reader (pb200_h5_load_problem) -- what MultiConditionDataProviderHDF5 serves per condition, read once.
+    /// Hierarchical index / map tables, if the file has them, are returned through `hierarchical`.
+    static B200ProblemTables fromHdf5(std::string const& path, std::string const& modelName,
+                                      struct B200HierarchicalTables* hierarchical = nullptr);
+
     pb200_problem_desc desc() const {
         pb200_problem_desc d{};
         d.abi_version = PB200_ABI_VERSION;
@@ -266,6 +272,46 @@ struct B200HierarchicalTables {
         return d;
     }
 };
+
+inline B200ProblemTables B200ProblemTables::fromHdf5(std::string const& path, std::string const& modelName,
+                                                     B200HierarchicalTables* hierarchical) {
+    pb200_h5_problem* P = nullptr;
+    if (pb200_h5_load_problem(path.c_str(), modelName.c_str(), &P) != 0)
+        throw std::runtime_error(std::string("pb200_h5_load_problem: ") + pb200_last_error());
+    const pb200_problem_desc& d = *pb200_h5_problem_desc(P);
+    B200ProblemTables T;
+    T.modelName = modelName;
+    T.numConditions = d.n_conditions;
+    T.numOptimizationParameters = d.n_opt;
+    T.np = d.np; T.nk = d.nk; T.ny = d.ny;
+    const size_t C = static_cast<size_t>(d.n_conditions);
+    T.tOffsets.assign(d.t_offsets, d.t_offsets + C + 1);
+    const size_t nt = static_cast<size_t>(T.tOffsets.back());
+    T.t.assign(d.t, d.t + nt);
+    T.y.assign(d.y, d.y + nt * d.ny);
+    T.sigma.assign(d.sigma, d.sigma + nt * d.ny);
+    T.k.assign(d.k, d.k + C * d.nk);
+    T.mapping.assign(d.mapping, d.mapping + C * d.np);
+    T.pscaleSim.assign(d.pscale_sim, d.pscale_sim + C * d.np);
+    T.pscaleOpt.assign(d.pscale_opt, d.pscale_opt + d.n_opt);
+    if (d.overrides) T.overrides.assign(d.overrides, d.overrides + C * d.np);
+    T.t0 = d.t0; T.atol = d.atol; T.rtol = d.rtol;
+    T.maxSteps = d.maxsteps;
+    T.stabilityLimitDetection = d.stldet != 0;
+    if (hierarchical) {
+        *hierarchical = B200HierarchicalTables();
+        if (const pb200_hier_desc* h = pb200_h5_problem_hier(P)) {
+            hierarchical->scalingIdx.assign(h->scaling_idx, h->scaling_idx + h->n_scaling);
+            hierarchical->offsetIdx.assign(h->offset_idx, h->offset_idx + h->n_offset);
+            hierarchical->sigmaIdx.assign(h->sigma_idx, h->sigma_idx + h->n_sigma);
+            hierarchical->scalingMap.assign(h->scaling_map, h->scaling_map + 3 * h->n_scaling_rows);
+            hierarchical->offsetMap.assign(h->offset_map, h->offset_map + 3 * h->n_offset_rows);
+            hierarchical->sigmaMap.assign(h->sigma_map, h->sigma_map + 3 * h->n_sigma_rows);
+        }
+    }
+    pb200_h5_problem_free(P);
+    return T;
+}
 
 class B200HierarchicalOptimizationWrapper : public GradientFunction {
   public:

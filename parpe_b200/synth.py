@@ -42,9 +42,11 @@ def condition_constants(model: str, C: int, rng: np.random.Generator, heterogene
         k[:, 1] = 1.0 + 0.05 * rng.standard_normal(C)
     elif model == "boehm":
         if heterogeneous:
-            # conditions that really differ (as the 6 doses of the Fujita problem span 300x): the constant
-            # is log-uniform over 2.5 decades, so step counts and Newton behaviour vary across the warp
-            k[:, 0] = 0.693 * 10.0 ** rng.uniform(-1.25, 1.25, C)
+            # conditions that really differ (as the 6 doses of the Fujita problem span 300x): the constant is
+            # log-uniform over 2.5 decades below its nominal value (larger values make the REFERENCE integrator
+            # fail on ~10 % of the conditions: not a throughput workload), so step counts and Newton behaviour
+            # vary across the warp
+            k[:, 0] = 0.693 * 10.0 ** rng.uniform(-2.4, 0.08, C)
         else:
             k[:, 0] = 0.693 * (1.0 + 0.02 * rng.standard_normal(C))
     return k

@@ -1,0 +1,85 @@
+"""AddressSanitizer + UndefinedBehaviorSanitizer over the HOST build of both integrator cores.
+
+compute-sanitizer is closed on the GPU pool (profiles/r02_sanitizer.log keeps its answer), so memcheck /
+racecheck logs of the kernels cannot be produced.  What can be checked without it: the device cores compile for
+the host from the SAME source (one-lane group / one-thread team), so every index computation of the algorithm --
+history arrays, ELL Jacobian, blocked inversion, sparse factor tables and level lists, staging-area layouts of the
+fused passes, column batches -- runs here under ASan/UBSan with heap-allocated buffers of exactly the sizes the
+kernels carve from HBM / shared memory; an out-of-bounds index in that logic aborts the run.  (Races between the
+threads of a block are outside what a one-thread build can see.)"""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HH = os.path.join(ROOT, "tests", "host_harness")
+
+
+def _asan_lib():
+    p = subprocess.run(["gcc", "-print-file-name=libasan.so"], stdout=subprocess.PIPE, text=True).stdout.strip()
+    return p if os.path.isabs(p) and os.path.exists(p) else None
+
+
+TEAM_BODY = """
+    from tests.host_harness import binding as hh
+    hh.LIB_TEAM = %r
+    hh.build_team = lambda force=False: None
+    import numpy as np
+    from parpe_b200 import synth
+    from parpe_b200.models import get_spec
+    spec = get_spec("net32")
+    tab = synth.make_problem("net32", 1, seed=7, timepoints=synth.DEFAULT_TIMEPOINTS["net32"][:5])
+    p = np.asarray(spec.p_nominal) * 1.3
+    args = ("net32", p, tab.k[0], list(range(spec.np)), tab.t, tab.y_of(0), tab.sigma_of(0))
+    for kw in (dict(), dict(sparse=True), dict(sparse=True, deg_max=3, stage_doubles=150),
+               dict(sparse=True, deg_max=100), dict(sparse=True, fuse_history=False, fuse_newton=False),
+               dict(panel_width=4)):
+        r = hh.simulate_team(*args, **kw)
+        assert r["status"] == 0, (kw, r["status"])
+    rng = np.random.default_rng(0)
+    sp = get_spec("chen")
+    Jv = rng.standard_normal(sp.nnz)
+    rows = np.repeat(np.arange(sp.nx), np.diff(sp.j_ptr))
+    Jv[rows == sp.j_col] = -np.abs(Jv[rows == sp.j_col]) - 3.0
+    hh.team_solve("chen", Jv, 0.3, rng.standard_normal((51, sp.nx)), sparse=True)
+    hh.team_solve("chen", Jv, 0.3, rng.standard_normal((51, sp.nx)), sparse=True, stage_doubles=6000)
+    hh.team_solve("net31", rng.standard_normal(get_spec("net31").nnz) * 0.1, 0.3, rng.standard_normal((6, 31)))
+    print("ASAN-OK")
+"""
+
+SMALL_BODY = """
+    from tests.host_harness import binding as hh
+    hh.LIB = %r
+    hh.build = lambda force=False: None
+    import numpy as np
+    from parpe_b200 import synth
+    from parpe_b200.models import get_spec
+    for model in ("steadystate", "boehm", "fujita"):
+        spec = get_spec(model)
+        tab = synth.make_problem(model, 1, seed=3)
+        p = np.asarray(spec.p_nominal, dtype=float)
+        r = hh.simulate(model, p, tab.k[0], list(range(spec.np)), tab.t, tab.y_of(0), tab.sigma_of(0))
+        assert r["status"] == 0, model
+        r = hh.simulate(model, p, tab.k[0], [0, 2], tab.t, tab.y_of(0), tab.sigma_of(0))
+        assert r["status"] == 0, model
+    print("ASAN-OK")
+"""
+
+
+@pytest.mark.parametrize("which", ["team", "small"])
+def test_host_cores_under_asan_ubsan(tmp_path, which):
+    asan = _asan_lib()
+    if asan is None:
+        pytest.skip("libasan not available")
+    src = os.path.join(HH, "host_sim_team.cpp" if which == "team" else "host_sim.cpp")
+    lib = str(tmp_path / ("libhost_%s_asan.so" % which))
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=address,undefined",
+                           "-fno-sanitize-recover=undefined", "-o", lib, src])
+    body = (TEAM_BODY if which == "team" else SMALL_BODY) % lib
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", textwrap.dedent(body)], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and "ASAN-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
