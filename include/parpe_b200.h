@@ -211,6 +211,9 @@ enum {
     PB200_OPT_STAGE_SYNC = 6,     /* CTA barrier between the stages of a step attempt (default 0) */
     PB200_OPT_PARTIAL_SUMS = 7,   /* 1: pb200_evaluate on a partitioned handle without a collective
                                      returns rank-local partial sums instead of failing (tests) */
+    PB200_OPT_FUSE_OFF = 9,       /* large-model path, experiments: bit 0 switches the fused history pass off, bit 1
+                                     the fused Newton iteration of the sparse solver, bit 2 the lazy zeroing of the
+                                     correction (default 0: all on; results agree to rounding) */
     PB200_OPT_LINSOL = 8          /* large-model path: 0 automatic (by fill of the symbolic factorisation),
                                      1 dense inverse (amici LinearSolver::dense), 2 sparse fixed-pattern LU
                                      with a dense Schur block (LinearSolver::KLU's role) */

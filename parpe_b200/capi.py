@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
 ]
 # pb200_set_option keys (include/parpe_b200.h)
 OPT_REORDER, OPT_ORDER_REFRESH, OPT_KERNEL_VARIANT, OPT_CTAS_PER_SM, OPT_SYNC_PERIOD, OPT_STAGE_SYNC = 1, 2, 3, 4, 5, 6
-OPT_PARTIAL_SUMS, OPT_LINSOL = 7, 8
+OPT_PARTIAL_SUMS, OPT_LINSOL, OPT_FUSE_OFF = 7, 8, 9
 LINSOL_AUTO, LINSOL_DENSE, LINSOL_SPARSE = 0, 1, 2
 
 _lib = None

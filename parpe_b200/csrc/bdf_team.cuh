@@ -208,6 +208,7 @@ struct BdfTeam {
     bool b_forwarded_ = false; // w.b already holds the forward-substituted right-hand sides
     bool fwd_ok_ = false;      // the factors in w.luV are the ones the coming solve uses (no setup pending)
     bool acor_zero_ = false;   // the sensitivity columns of acor are zero but the zeros have not been written
+    bool lazy_acor = true;     // (experiments: false = zero acor eagerly at the start of every sensitivity iteration)
     int fail_, ret_;
     // phase cycle counters (device: clock64 of thread 0's SM; exported in stats[14..15] packed as
     // two 32-bit fields of kilo-cycles each: [14] = inversion panel | inversion update, [15] = solve GEMM | model+rhs)
@@ -456,12 +457,21 @@ struct BdfTeam {
             const int nel = ncb * nx;
             tm.sync();
             // flat, coalesced: S = zn[0] + acor (what J multiplies), Z = rl1 zn[1] + acor (the rest of the residual)
-            PT_FOR(x, 0, nel) {
-                const int cl = x / nx, i = x - cl * nx;
-                const size_t e = (size_t)(cb + cl) * nx + i;
-                const double a = azero ? 0.0 : ac[e];
-                S[(size_t)cl * nx + i] = z0[e] + a;
-                Z[(size_t)iord[i] * CB + cl] = rl1 * z1[e] + a;
+            if (azero) {  // (acor = 0, not materialised: first iteration)
+                PT_FOR(x, 0, nel) {
+                    const int cl = x / nx, i = x - cl * nx;
+                    const size_t e = (size_t)(cb + cl) * nx + i;
+                    S[(size_t)cl * nx + i] = z0[e] + 0.0;
+                    Z[(size_t)iord[i] * CB + cl] = rl1 * z1[e] + 0.0;
+                }
+            } else {
+                PT_FOR(x, 0, nel) {
+                    const int cl = x / nx, i = x - cl * nx;
+                    const size_t e = (size_t)(cb + cl) * nx + i;
+                    const double a = ac[e];
+                    S[(size_t)cl * nx + i] = z0[e] + a;
+                    Z[(size_t)iord[i] * CB + cl] = rl1 * z1[e] + a;
+                }
             }
             tm.sync();
             // one matrix row per thread (ELL entries in registers); the only global loads of the loop over the
@@ -1528,7 +1538,7 @@ struct BdfTeam {
                         const int cl = ok ? x / nx : 0, i = ok ? x - cl * nx : 0;
                         g[u] = i + (size_t)(c0 + cl) * nx;
                         zi[u] = (int)iord[i] * bc + cl;
-                        a[u] = (ok && !azero) ? acor[g[u]] : 0.0;
+                        a[u] = (ok && !azero) ? acor[g[u]] : 0.0;  // (azero is uniform: the load is skipped for all)
                         ew[u] = ok ? ewt[g[u]] : 0.0;
                         d[u] = ok ? nsc * Z[zi[u]] : 0.0;
                     }
@@ -1904,7 +1914,7 @@ struct BdfTeam {
         // acor = 0 at the start of the iteration.  Sensitivity phase on the fused sparse path: the zeros are not
         // written (and not read back by the first right-hand side / update) -- acor_zero_ stands for them until
         // the first update stores acor = delta
-        acor_zero_ = (phase == PH_SENS) && fuse_newton && lin_sparse && !setup_pending &&
+        acor_zero_ = (phase == PH_SENS) && lazy_acor && fuse_newton && lin_sparse && !setup_pending &&
                      w.stage_doubles - (2 * SP.nV > w.stage_doubles ? 0 : SP.nV) >= 2 * nx;
         if (!acor_zero_) {
             PT_FOR(e, cmin * nx, (cmax + 1) * nx) w.acor[e] = 0.0;

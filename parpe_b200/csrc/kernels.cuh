@@ -63,6 +63,8 @@ struct KernelArgs {
     int max_groups;                // lane groups of a CTA that pull work (launch geometry: few conditions are
                                    // spread over all SMs instead of filling the first CTAs)
     int linsol;                    // large-model path: 0 automatic, 1 dense inverse, 2 sparse LU + dense Schur block
+    int fuse_off;                  // large-model path, experiments: bit 0 no fused history pass, bit 1 no fused Newton
+                                   // iteration, bit 2 acor zeroed eagerly (default 0: everything on)
     SolverOptions opt;
     int num_trials;
     double relaxation_factor;

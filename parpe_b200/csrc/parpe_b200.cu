@@ -158,7 +158,7 @@ struct pb200_handle {
     DevBuf<double> d_coll;  // staging buffer of the small NCCL reductions of the hierarchical passes
     // tuning options (pb200_set_option; never read from the environment)
     int opt_variant = 2, opt_ctas_per_sm = 0, opt_sync_period = 1, opt_stage_sync = 0, opt_partial_sums = 0;
-    int opt_linsol = 0, opt_order_refresh = 16;
+    int opt_linsol = 0, opt_order_refresh = 16, opt_fuse_off = 0;
     int evals_since_order = 0;
     int64_t last_h2d = 0, last_d2h = 0;
     // large-model path: device tables + workspace (ModelOps::create_state)
@@ -238,6 +238,7 @@ static int enqueue_evaluation(pb200_handle* h, const double* theta, const int* i
     a.stage_sync = h->opt_stage_sync;
     a.ctas_per_sm_cap = h->opt_ctas_per_sm;
     a.linsol = h->opt_linsol;
+    a.fuse_off = h->opt_fuse_off;
     PB_CUDA(cudaEventRecord(h->ev_start, stream));
     if (n > 0) {
         int e = h->ops->launch(a, h->lanes, h->opt_variant, h->sm_count, stream, &h->last_lanes, &h->last_grid,
@@ -483,6 +484,7 @@ int pb200_set_option(pb200_handle* h, int key, int value) {
         if (value < 0 || value > 2) return fail(PB200_ERR_ARG, "linear solver: 0 automatic, 1 dense, 2 sparse");
         h->opt_linsol = value;
         break;
+    case PB200_OPT_FUSE_OFF: h->opt_fuse_off = value; break;
     default: return fail(PB200_ERR_ARG, "unknown option");
     }
     return 0;

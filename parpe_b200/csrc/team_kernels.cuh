@@ -29,6 +29,9 @@ simulate_team_kernel(const KernelArgs a, const NetTables T, const SparseLU SP, d
     bdf.T = T;
     bdf.SP = SP;
     bdf.use_sparse = use_sparse != 0;
+    bdf.fuse_history = !(a.fuse_off & 1);
+    bdf.fuse_newton = !(a.fuse_off & 2);
+    bdf.lazy_acor = !(a.fuse_off & 4);
     bdf.opt = a.opt;
     bdf.w.carve(workspace + (size_t)blockIdx.x * ws_stride, T, SP.enabled ? SP.nV : 0);
     bdf.w.NB = 0;  // panel width of the generic dense path: chosen per inversion from the panel capacity
