@@ -462,6 +462,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra small-model (boehm) measurements")
     ap.add_argument("--no-cost-only", action="store_true", help="skip the objective-only (no gradient) measurement")
+    ap.add_argument("--quick", action="store_true",
+                    help="scaling records of workloads whose single evaluation takes tens of seconds (NOT the driver's "
+                         "line): one host evaluation as warm-up, ONE timed step, one end-to-end evaluation; says so in config")
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD,
                     help="chen (default: BASELINE configs[3], nx = 500) | froehlich (configs[4], nx = 1200) | boehm "
                          "(configs[1], the small-model kernel) | net32 | fujita ...")
@@ -480,6 +483,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args, model, per_gpu)
     args.warmup = max(args.warmup, 3)
+    if args.quick:
+        args.warmup, args.steps, args.no_cost_only, args.no_extra, args.no_cpu_baseline = 0, 1, True, True, True
 
     rig = Rig(args)
     world, rank = rig.world, rig.rank
@@ -519,7 +524,9 @@ def main():
                                 "(PB200_OPT_REORDER); results do not depend on it",
                        "collective": ("one ncclAllReduce of %d doubles per evaluation, issued by libparpe_b200 "
                                       "(pb200_nccl_init) on the evaluation's stream" % (2 + tab.n_opt)) if world > 1 else "none (1 GPU)",
-                       "lanes_per_condition": ll["lanes"], "grid": ll["grid"], "block": ll["block"]},
+                       "lanes_per_condition": ll["lanes"], "grid": ll["grid"], "block": ll["block"],
+                       **({"quick": "one host evaluation as the only warm-up, one timed step, one e2e evaluation "
+                                    "(scaling record of a long-running workload, not a driver line)"} if args.quick else {})},
             "e2e": {"value": m["e2e"], "unit": UNIT, "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
                     "note": "pb200_evaluate with host theta/idx/fval/gradient on every rank; bytes as counted by the "
                             "library (pb200_last_transfer_bytes): parameter table 48 B/parameter, index list 4 B/condition "

@@ -31,6 +31,9 @@ def test_fixtures_exist():
 def test_oracle_reproduces_fixture(oracle_available, path):
     from oracle.binding import OracleProblem
     doc, tab, theta = _load(path)
+    if doc["case"] == "froehlich_full" and not os.environ.get("PB200_SLOW_TESTS"):
+        pytest.skip("one nx = 1200 full-horizon solve takes > 4 min on a host core (set PB200_SLOW_TESTS=1); the fixture "
+                    "comes from this same oracle build (tools/make_golden.py) and chen_full exercises the same path")
     if doc["case"].endswith("_full"):
         # (full-horizon large-model cases take minutes per condition on a host core: the first condition only)
         r = OracleProblem(tab).evaluate(theta, idx=[0])
