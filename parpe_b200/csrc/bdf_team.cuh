@@ -442,6 +442,8 @@ struct BdfTeam {
         const int nx = this->nx;
         const double rl1 = this->rl1, gamma = this->gamma;
         const bool azero = acor_zero_;
+        PB_ASSUME_GLOBAL(z0); PB_ASSUME_GLOBAL(z1); PB_ASSUME_GLOBAL(ac); PB_ASSUME_GLOBAL(jc); PB_ASSUME_GLOBAL(dfdp);
+        PB_ASSUME_GLOBAL(jcol); PB_ASSUME_GLOBAL(plist); PB_ASSUME_GLOBAL(bb);
         // staging area: corrected sensitivity vectors of the batch S[column][row] | right-hand sides Z[row][column]
         // | factor values
         tm.sync();

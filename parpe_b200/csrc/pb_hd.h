@@ -45,8 +45,11 @@
 // the compiler it is shared memory so that it emits LDS/STS (the kernels always place it there).
 #if defined(__CUDA_ARCH__)
 #define PB_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+// ... and that a pointer into the HBM workspace is global memory (LDG/STG instead of generic LD/ST)
+#define PB_ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
 #else
 #define PB_ASSUME_SHARED(p) ((void)0)
+#define PB_ASSUME_GLOBAL(p) ((void)0)
 #endif
 
 // Make a value opaque to the optimiser: stops it from cloning a large code region once per
