@@ -737,6 +737,7 @@ struct BdfTeam {
         // function), so a store through a generic pointer would force a reload of every member after it
         const int nx = this->dn;  // dimension of the dense matrix (the whole Newton matrix or the Schur block)
         double* const A = w.A;
+        PB_ASSUME_GLOBAL(A);
         const int i = threadIdx.x;
         const bool rowok = i < nx;
         double* const sm = smem_base();
@@ -1028,6 +1029,7 @@ struct BdfTeam {
         const double* const b = w.b;
         const int* const perm = w.gidx;
         const int* const omap = lin_sparse ? SP.ord + SP.n1 : nullptr;  // solution row of block row r
+        PB_ASSUME_GLOBAL(A); PB_ASSUME_GLOBAL(b); PB_ASSUME_GLOBAL(scr); PB_ASSUME_GLOBAL(perm);
         auto b_entry = [&](int ch, int e) -> double {
             const int cc = e / KC, kk = e - cc * KC;
             const int k = ch * KC + kk;
@@ -1145,6 +1147,7 @@ struct BdfTeam {
         const double* const b = w.b;
         const int* const perm = w.gidx;
         const int* const omap = lin_sparse ? SP.ord + SP.n1 : nullptr;
+        PB_ASSUME_GLOBAL(A); PB_ASSUME_GLOBAL(b); PB_ASSUME_GLOBAL(scr); PB_ASSUME_GLOBAL(perm);
         auto b_entry = [&](int ch, int e) -> double {
             const int kk = e / TN, cc = e - kk * TN;
             const int k = ch * KC + kk;
