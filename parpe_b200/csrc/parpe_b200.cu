@@ -189,7 +189,9 @@ static int enqueue_evaluation(pb200_handle* h, const double* theta, const int* i
     int lo, hi;
     pb200_partition_bounds(n_idx, h->rank, h->world, &lo, &hi);
     const int n = hi - lo;
-    for (int r = lo; r < hi; ++r)
+    // the WHOLE list is validated on every rank (not only this rank's share): with a collective inside the
+    // evaluation a rank that bailed out alone would leave the others waiting in the all-reduce
+    for (int r = 0; r < n_idx; ++r)
         if (idx[r] < 0 || idx[r] >= h->C) return fail(PB200_ERR_ARG, "data index out of range");
     if (int rc = ensure_capacity(h, n > 0 ? n : 1)) return rc;
     if (h->staged_pending) {  // pinned staging buffers may still be in flight
