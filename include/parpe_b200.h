@@ -288,6 +288,10 @@ int pb200_get_condition_results(pb200_handle* h, double* llh, double* sllh,
  * (multiConditionProblem.cpp:506-563): simulate ALL conditions without
  * sensitivities; y_out / sigmay_out use the layout of desc->y.
  * Returns PB200_EVAL_SUCCESS / PB200_EVAL_FAILURE.
+ * On a partitioned handle only the conditions of this rank's share are
+ * simulated: their outputs are filled, all others are NaN (the status is the
+ * global one when a collective is set).  pb200_hier_evaluate works on these
+ * per-rank outputs and reduces what it needs.
  */
 int pb200_get_model_outputs(pb200_handle* h, const double* theta, int n_opt,
                             double* y_out, double* sigmay_out);
