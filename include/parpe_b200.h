@@ -165,6 +165,32 @@ int pb200_create(const pb200_problem_desc* desc, int device, pb200_handle** out)
 void pb200_destroy(pb200_handle* h);
 
 /*
+ * Pre-equilibration.  Replaces: the pre-equilibration branch of
+ * MultiConditionDataProviderHDF5::updateFixedSimulationParameters
+ * (src/parpeamici/multiConditionDataProvider.cpp:224-250: column 0 of
+ * /fixedParameters/simulationConditions != -1 selects the pre-equilibration condition,
+ * /fixedParameters/reinitializationIndices the states re-initialised afterwards; doc/hdf5.md:36-58)
+ * and what AMICI then does with ExpData::fixedParametersPreequilibration /
+ * reinitialization_state_idxs_sim (deps/AMICI/src/amici.cpp:95-108,
+ * steadystateproblem.cpp:82-106,711-794): the model is simulated with the pre-equilibration
+ * condition's constants from x0 until the weighted RMS norm of xdot (and of the sensitivity
+ * right-hand sides) falls below 1 at 100 x the integration tolerances, the main simulation starts
+ * from that steady state (and its sensitivities), and the listed states whose initial value depends
+ * on the constants are reset to their initial value.  AMICI's defaults are implemented:
+ * steady state by simulation (newton_maxsteps = 0), sensitivities integrated along
+ * (integrateIfNewtonFails), convergence check on the sensitivities on.
+ *   has_preeq       [C]     1 = condition c is pre-equilibrated; NULL switches pre-equilibration off
+ *   k_preeq         [C*nk]  constants of the pre-equilibration condition (rows of conditions
+ *                           without one are ignored)
+ *   reinit_offsets  [C+1], reinit_idx: ragged list of state indices per condition; NULL = none
+ * Output times t = +inf in the problem table (post-equilibration) need no call: the data point is
+ * evaluated at the steady state the simulation is carried on to (rdata.cpp:234-258).
+ * Small-model kernels only; PB200_ERR_ARG for the large-model (network) kernels.
+ */
+int pb200_set_preequilibration(pb200_handle* h, const int32_t* has_preeq, const double* k_preeq,
+                               const int64_t* reinit_offsets, const int32_t* reinit_idx);
+
+/*
  * Shard the data indices of every evaluation over `world` handles (one per GPU /
  * process): this handle then simulates positions [floor(rank*n/world),
  * floor((rank+1)*n/world)) of the index list only.

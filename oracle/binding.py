@@ -37,6 +37,8 @@ def lib():
         L.ora_create.restype = C.c_void_p
         L.ora_create.argtypes = [C.POINTER(ProblemDesc), C.c_int, C.c_int]
         L.ora_destroy.argtypes = [C.c_void_p]
+        L.ora_set_preequilibration.argtypes = [C.c_void_p, C.POINTER(C.c_int32), dp, C.POINTER(C.c_int64),
+                                               C.POINTER(C.c_int32)]
         L.ora_evaluate.argtypes = [C.c_void_p, dp, ip, C.c_int, dp, dp, C.c_int, C.c_int, dp, dp, ip,
                                    C.POINTER(C.c_int64), dp]
         L.ora_get_model_outputs.argtypes = [C.c_void_p, dp, dp, dp, C.c_int]
@@ -86,6 +88,12 @@ class OracleProblem:
             self._hd = tables.hier.to_desc()
             if lib().ora_hier_attach(self._h, C.byref(self._hd)) != 0:
                 raise RuntimeError(lib().ora_last_error().decode())
+        pre = tables.preeq_args()
+        if pre is not None:
+            flag, kp, off, flat = pre
+            lib().ora_set_preequilibration(self._h, flag.ctypes.data_as(C.POINTER(C.c_int32)), _dp(kp),
+                                           off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           flat.ctypes.data_as(C.POINTER(C.c_int32)))
 
     def __del__(self):
         if getattr(self, "_h", None):

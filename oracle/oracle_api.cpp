@@ -107,6 +107,25 @@ ora_problem* ora_create(const pb200_problem_desc* d, int ism, int linsol) {
 
 void ora_destroy(ora_problem* h) { delete h; }
 
+// counterpart of pb200_set_preequilibration (include/parpe_b200.h)
+int ora_set_preequilibration(ora_problem* h, const int32_t* has_preeq, const double* k_preeq,
+                             const int64_t* reinit_offsets, const int32_t* reinit_idx) {
+    Tables& t = h->p->mutableTables();
+    t.has_preeq.clear();
+    t.k_preeq.clear();
+    t.reinit_idx.clear();
+    if (!has_preeq)
+        return 0;
+    const int C = t.n_conditions;
+    t.has_preeq.assign(has_preeq, has_preeq + C);
+    t.k_preeq.assign(k_preeq, k_preeq + (size_t)C * t.nk);
+    t.reinit_idx.resize(C);
+    if (reinit_offsets)
+        for (int c = 0; c < C; ++c)
+            t.reinit_idx[c].assign(reinit_idx + reinit_offsets[c], reinit_idx + reinit_offsets[c + 1]);
+    return 0;
+}
+
 // returns 0/1 (FunctionEvaluationStatus) or -1 on exception
 int ora_evaluate(ora_problem* h, const double* theta, const int* idx, int n_idx, double* fval,
                  double* grad, int nthreads, int collect_stats, double* llh_c, double* sllh_c,
@@ -132,6 +151,8 @@ int ora_evaluate(ora_problem* h, const double* theta, const int* idx, int n_idx,
                 s[PB200_STAT_NETF] = res[r].netf;
                 s[PB200_STAT_NCFN] = res[r].ncfn;
                 s[PB200_STAT_TRIALS] = res[r].trials;
+                s[14] = res[r].preeq_steps;   // steps of the pre-equilibration simulation
+                s[15] = res[r].posteq_steps;  // steps of the post-equilibration simulation
             }
         }
         return rc;

@@ -128,6 +128,12 @@ ConditionResult Problem::runAndLogSimulation(amici::Model& model, int c, bool se
         std::vector<double>(tab_.sigma.begin() + lo * tab_.ny, tab_.sigma.begin() + hi * tab_.ny));
     edata.fixedParameters.assign(tab_.k.begin() + (size_t)c * tab_.nk, tab_.k.begin() + (size_t)(c + 1) * tab_.nk);
     edata.plist = plistFor(mappingFor(c));
+    // updateFixedSimulationParameters, multiConditionDataProvider.cpp:224-250
+    if (!tab_.has_preeq.empty() && tab_.has_preeq[c]) {
+        edata.fixedParametersPreequilibration.assign(tab_.k_preeq.begin() + (size_t)c * tab_.nk,
+                                                     tab_.k_preeq.begin() + (size_t)(c + 1) * tab_.nk);
+        edata.reinitialization_state_idxs_sim = tab_.reinit_idx[c];
+    }
 
     std::unique_ptr<amici::ReturnData> rdata;
     int trial = 1;
@@ -174,6 +180,10 @@ ConditionResult Problem::runAndLogSimulation(amici::Model& model, int c, bool se
             r.numsteps = rdata->numsteps;
             r.order = rdata->order;
         }
+        if (rdata->preeq_numsteps.size() >= 2)
+            r.preeq_steps = rdata->preeq_numsteps[1];
+        if (rdata->posteq_numsteps.size() >= 2)
+            r.posteq_steps = rdata->posteq_numsteps[1];
         return r;
     }
     r.llh = NAN;

@@ -36,6 +36,11 @@ struct Tables {
     std::vector<int> pscale_sim;        // [C*np]
     std::vector<int> pscale_opt;        // [n_opt]
     std::vector<double> overrides;      // [C*np] or empty
+    // pre-equilibration (multiConditionDataProvider.cpp:224-250): per simulation the constants of the
+    // pre-equilibration condition and the states re-initialised afterwards; has_preeq empty = none
+    std::vector<int> has_preeq;                  // [C]
+    std::vector<double> k_preeq;                 // [C*nk]
+    std::vector<std::vector<int>> reinit_idx;    // [C] ragged
     double t0 = 0.0, atol = 1e-16, rtol = 1e-8;
     int maxsteps = 10000;
     int stldet = 1;
@@ -55,6 +60,7 @@ struct ConditionResult {  // AmiciResultPackageSimple, amiciSimulationRunner.h:1
     int trials = 0;
     long nst = -1, nfe = -1, nsetups = -1, nni = -1, netf = -1, ncfn = -1;
     std::vector<int> numsteps, order;  // per output time (full reporting only)
+    long preeq_steps = -1, posteq_steps = -1;  // internal steps of the simulations to steady state (full reporting only)
 };
 
 class Problem {
@@ -76,6 +82,7 @@ class Problem {
     void mapAndSetOptimizationToSimulationVariables(int c, const double* theta, std::vector<double>& p_sim) const;
 
     const Tables& tables() const { return tab_; }
+    Tables& mutableTables() { return tab_; }
     const amici::Model& model() const { return *model_; }
 
   private:

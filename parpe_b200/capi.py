@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "pb200_set_option", "pb200_nccl_unique_id", "pb200_nccl_init", "pb200_last_transfer_bytes", "pb200_linsol_info",
     "pb200_h5_open", "pb200_h5_close", "pb200_h5_exists", "pb200_h5_dataset_info", "pb200_h5_read_double",
     "pb200_h5_attribute_double", "pb200_h5_list", "pb200_h5_load_problem", "pb200_h5_problem_desc",
-    "pb200_h5_problem_hier", "pb200_h5_problem_free", "pb200_create_from_hdf5",
+    "pb200_h5_problem_hier", "pb200_h5_problem_free", "pb200_create_from_hdf5", "pb200_set_preequilibration",
 ]
 # pb200_set_option keys (include/parpe_b200.h)
 OPT_REORDER, OPT_ORDER_REFRESH, OPT_KERNEL_VARIANT, OPT_CTAS_PER_SM, OPT_SYNC_PERIOD, OPT_STAGE_SYNC = 1, 2, 3, 4, 5, 6
@@ -94,6 +94,8 @@ def lib():
     L.pb200_h5_problem_free.argtypes = [C.c_void_p]
     L.pb200_h5_problem_free.restype = None
     L.pb200_create_from_hdf5.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.pb200_set_preequilibration.argtypes = [C.c_void_p, C.POINTER(C.c_int32), dp, C.POINTER(C.c_int64),
+                                             C.POINTER(C.c_int32)]
     _lib = L
     return L
 

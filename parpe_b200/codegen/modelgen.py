@@ -229,6 +229,10 @@ def emit_device_header(d: Derived, path: str) -> None:
     A("    // columns are integrated; for the others sx == 0 identically (bit DYN_MASK >> ip)")
     A("    static constexpr int NPD = %d;" % max(sum(dyn), 0))
     A("    static constexpr unsigned DYN_MASK = 0x%xu;" % sum(1 << i for i, v in enumerate(dyn) if v))
+    x0k = [any(sym in set(s.consts) for sym in sp.sympify(e).free_symbols) for e in s.x0]
+    A("    // states whose initial value depends on the constants k (AMICI's _x0_fixedParameters_idx,")
+    A("    // de_export.py:688-749): the ones a re-initialisation after pre-equilibration may touch (bit i)")
+    A("    static constexpr unsigned X0K_MASK = 0x%xu;" % sum(1 << i for i, v in enumerate(x0k) if v))
     A("    // operation counts of the generated expressions (after CSE)")
     A("    static constexpr int FLOPS_XDOT = %d, FLOPS_J = %d, FLOPS_DXDOTDP = %d, NNZ_DXDOTDP = %d;" %
       (fl["xdot"], fl["J"], fl["dxdotdp"], fl["nnz_dxdotdp"]))
@@ -311,6 +315,7 @@ def emit_amici_model(d: Derived, outdir: str) -> None:
     A("// GENERATED by parpe_b200/codegen/modelgen.py from parpe_b200/models/%s.py -- do not edit." % n)
     A("// TEST INFRASTRUCTURE (oracle): amici::Model_ODE subclass in the MATLAB-generated layout")
     A("// (pythonGenerated=false; cf. deps/AMICI/models/model_steadystate/model_steadystate.h).")
+    A("#include <algorithm>")
     A("#include <memory>")
     A("#include <cmath>")
     A('#include "amici/model_ode.h"')
@@ -353,6 +358,28 @@ def emit_amici_model(d: Derived, outdir: str) -> None:
     A("    }")
     A("    void fsx0(realtype* sx0, const realtype t, const realtype* x0, const realtype* p, const realtype* k, const int ip) override {")
     L.extend(_switch_ip(pr, s.nx, d.sx0, "sx0", "        "))
+    A("    }")
+    # re-initialisation of states whose initial value depends on the constants, in the layout of the
+    # python-generated models (deps/AMICI/python/sdist/amici/de_export.py:688-749)
+    x0k = [i for i, e in enumerate(s.x0) if any(sym in set(s.consts) for sym in sp.sympify(e).free_symbols)]
+    A("    static bool reinit_has(gsl::span<const int> idxs, int i) { return std::find(idxs.begin(), idxs.end(), i) != idxs.end(); }")
+    A("    void fx0_fixedParameters(realtype* x0_fixedParameters, const realtype t, const realtype* p, const realtype* k, gsl::span<const int> reinitialization_state_idxs) override {")
+    for i in x0k:
+        A("        if (reinit_has(reinitialization_state_idxs, %d)) x0_fixedParameters[%d] = %s;" % (i, i, pr.doprint(s.x0[i])))
+    A("    }")
+    A("    void fsx0_fixedParameters(realtype* sx0_fixedParameters, const realtype t, const realtype* x0, const realtype* p, const realtype* k, const int ip, gsl::span<const int> reinitialization_state_idxs) override {")
+    for i in x0k:
+        A("        if (reinit_has(reinitialization_state_idxs, %d)) sx0_fixedParameters[%d] = 0.0;" % (i, i))
+    A("        switch (ip) {")
+    for c in range(s.np):
+        body = ["            if (reinit_has(reinitialization_state_idxs, %d)) sx0_fixedParameters[%d] = %s;" % (i, i, pr.doprint(d.sx0[i, c]))
+                for i in x0k if d.sx0[i, c] != 0]
+        if body:
+            A("        case %d:" % c)
+            L.extend(body)
+            A("            break;")
+    A("        default: break;")
+    A("        }")
     A("    }")
     A("    void fy(double* y, const realtype t, const realtype* x, const realtype* p, const realtype* k, const realtype*, const realtype*) override {")
     L.extend(_cse_block(pr, ["y[%d]" % i for i in range(s.ny)], list(s.observables), "        "))

@@ -649,10 +649,81 @@ PB_ASSUME_SHARED(sh);
 }
 
 
+/// Convergence test of a simulation to steady state (SteadystateProblem::runSteadystateSimulation,
+/// deps/AMICI/src/steadystateproblem.cpp:711-794, with getWrms :553-591, getWrmsNorm :519-551 and
+/// getWrmsFSA :593-626): wrms(xdot(t, x)) < 1 with the weights 1 / (rtol*|x| + atol) and -- when
+/// sensitivities are integrated -- wrms(J*sx_ip + dxdotdp_ip) < 1 with 1 / (rtol*|sx_ip| + atol)
+/// for the parameters of plist in order, stopping at the first one above the threshold.  x / sx are
+/// column 0 / the sensitivity columns of zn[0] (what the solver returns at tn).  The tolerances are
+/// the steady-state ones (AMICI: 100 x the integration tolerances, solver.h:1908-1923).
+/// Scratch: yj, ysh, fout, Jcur, dfdp, scr -- all rewritten by the next step attempt.  Out of line.
 template <class M, class Grp>
+PB_HD_NOINLINE static bool ss_converged_shared(GroupShared<M>* sh, const Grp g, double t, double rtol, double atol,
+                                               int ns, int nsall) {
+    constexpr int NX = M::NX, G = Grp::G;
+    PB_ASSUME_SHARED(sh);
+    g.sync();
+    for (int i = g.lane(); i < NX; i += G) {
+        sh->yj[i] = sh->zn[0][i];
+        sh->ysh[i] = sh->zn[0][i];
+    }
+    g.sync();
+    int conv = 0;
+    if (g.lane() == 0) {
+        eval_xdot_shared<M>(sh, t);
+        double s = 0.0;
+        for (int i = 0; i < NX; ++i) {
+            const double w = pb_rcp(rtol * fabs(sh->ysh[i]) + atol);
+            const double prod = sh->fout[i] * w;
+            s += prod * prod;
+        }
+        const double wrms = sqrt(pb_div(s, (double)NX));
+        conv = (wrms < 1.0) ? 1 : 0;
+    }
+    conv = g.bcast0(conv);
+    if (!conv || ns == 0) return conv != 0;
+    // sensitivities: Model_ODE::fsxdot (model_ode.cpp:486-515) at (t, x)
+    if (g.lane() == 0) {
+        eval_jac_shared<M>(sh->Jcur, t, sh->ysh, sh);
+        eval_dfdp_shared<M>(sh, t, sh->ysh);
+    }
+    g.sync();
+    for (int c = 1 + g.lane(); c <= ns; c += G) {
+        const double* dcol = sh->dfdp + sh->cdcol[c - 1] * NX;
+        const double* sx = sh->zn[0] + c * NX;
+        double s = 0.0;
+        for (int i = 0; i < NX; ++i) {
+            double F = dcol[i];
+            for (int j = 0; j < NX; ++j) F += sh->Jcur[i + j * NX] * sx[j];
+            const double w = pb_rcp(rtol * fabs(sx[i]) + atol);
+            const double prod = F * w;
+            s += prod * prod;
+        }
+        sh->scr[c] = sqrt(pb_div(s, (double)NX));
+    }
+    g.sync();
+    if (g.lane() == 0) {
+        double wrms = 0.0;
+        for (int j = 0; j < nsall; ++j) {
+            const int c = sh->colof[j];
+            wrms = c > 0 ? sh->scr[c] : 0.0;  // a parameter the state does not depend on: sx == 0, sxdot == 0
+            if (wrms > 1.0) break;
+        }
+        conv = (wrms < 1.0) ? 1 : 0;
+    }
+    conv = g.bcast0(conv);
+    g.sync();
+    return conv != 0;
+}
+
+/// SS: with support for steady states -- output times t = inf (post-equilibration) and a
+/// pre-equilibration phase (begin() modes 1 / 2).  The SS = false instantiation is the code without
+/// any of it (an infinite output time is an error there).
+template <class M, class Grp, bool SS = false>
 struct Bdf {
     static constexpr int NX = M::NX, NP = M::NP, NK = M::NK, NY = M::NY;
     static constexpr int G = Grp::G;
+    static_assert(!SS || NX <= 32, "steady-state support uses a 32-bit mask of re-initialised states");
     // 2-D lane mapping of the row-parallel kernels: the G lanes of a group are LR "row lanes"
     // (the power of two >= NX, at most G) times CG "column groups"; lane l works on the rows
     // (l % LR) + r*LR, r < RPL, of the columns c = cmin + (l / LR), + CG, ...
@@ -702,6 +773,14 @@ struct Bdf {
     // stage of the attempt the state machine is in (stage_pre / stage_nls / stage_post)
     enum { ST_PRE = 0, ST_NLS = 1, ST_DONE = 2 };
     int stage_, fail_, ret_;
+    // steady-state support (SS only): what the simulation is doing
+    enum { SS_OFF = 0, SS_PREEQ = 1, SS_POSTEQ = 2 };
+    int ss_mode_;
+    /// true while CVode is driven in CV_ONE_STEP mode without a stop time (Solver::step,
+    /// deps/AMICI/src/solver.cpp:161-175): simulation to steady state
+    PB_HD bool one_step() const { return SS && ss_mode_ != SS_OFF; }
+    /// AMICI always sets a stop time in CV_NORMAL mode; it is absent only in one-step mode
+    PB_HD bool tstop_active() const { return SS ? tstopset : true; }
 
 // columns of this lane in [cmin, cmax] (column-parallel cold paths: initial values, data points)
 #define PB_FOR_COLS(c, cmin, cmax) \
@@ -1440,9 +1519,12 @@ struct Bdf {
     /// zn[1], initial step) or the stop tests of a later call.  Returns 0 to enter the step loop,
     /// TSTOP_RETURN if tn is already at tout, or a negative failure code.
     PB_HD int cvode_begin(double tout) {
-        // Solver::run -> setStopTime(tout); apply_max_num_steps()
-        tstop = tout;
-        tstopset = true;
+        // Solver::run -> setStopTime(tout); apply_max_num_steps().  Solver::step (one-step mode,
+        // simulation to steady state) sets no stop time.
+        if (!one_step()) {
+            tstop = tout;
+            tstopset = true;
+        }
         if (opt.maxsteps <= nst) return SIM_ERROR;
         mxstep_ = opt.maxsteps - nst;
         nstloc_ = 0;
@@ -1451,14 +1533,14 @@ struct Bdf {
             h = 1.0;  // zn[1] = f(t0, y0), znS[1] = fS(t0, y0, yS0), unscaled
             const int r = reload_zn1();
             if (r) return r == cv::RHSFUNC_RECVR ? SIM_FIRST_RHSFUNC_ERR : SIM_FIRST_SRHSFUNC_ERR;
-            if ((tstop - tn) * (tout - tn) <= 0.0) return SIM_ILL_INPUT;
+            if (tstop_active() && (tstop - tn) * (tout - tn) <= 0.0) return SIM_ILL_INPUT;
             const int hr = hin(tout);
             if (hr != 0) return hr;
-            if ((tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
+            if (tstop_active() && (tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
             hscale = h;
             hprime = h;
             PB_FOR_ELEMS(e) S()->zn[1][e] *= h;
-        } else {
+        } else if (tstop_active()) {
             const double troundoff = cv::FUZZ_FACTOR * cv::UROUND * (fabs(tn) + fabs(h));
             if (fabs(tn - tstop) <= troundoff) {
                 tstopset = false;
@@ -1570,8 +1652,24 @@ struct Bdf {
     /// Start one simulation (ForwardProblem::workForwardProblem, forwardproblem.cpp:67-203) at
     /// the given tolerances: x0/sx0 (Model::initialize, model.cpp:249-275), CVodeInit
     /// (cvodes.c:677-830).  S()->p / S()->k / S()->plist must be set.
-    PB_HD void begin(const ConditionIO& io, double rtol, double atol) {
+    ///
+    /// SS only -- pre-equilibration (amici.cpp:95-108; SteadystateProblem::workSteadyStateProblem with
+    /// it = -1, steadystateproblem.cpp:82-106,257-289):
+    ///   mode SS_PREEQ   S()->k holds the constants of the PRE-EQUILIBRATION condition; the simulation
+    ///                   runs from x0 / sx0 to steady state (a solver of its own in the reference:
+    ///                   createSteadystateSimSolver :796-839) and ends with SIM_SUCCESS, the steady state
+    ///                   in zn[0];
+    ///   mode SS_POSTEQ  (after a successful SS_PREEQ run, S()->k now the simulation condition's
+    ///                   constants) start the main simulation from the state and sensitivities in zn[0]
+    ///                   (ForwardProblem::ForwardProblem forwardproblem.cpp:59-63); the states of
+    ///                   `reinit_mask` are re-initialised from x0 / sx0
+    ///                   (Solver::updateAndReinitStatesAndSensitivities -> Model::reinitialize,
+    ///                   model.cpp:277-291, fx0_fixedParameters / fsx0_fixedParameters :1849-1923).
+    PB_HD void begin(const ConditionIO& io, double rtol, double atol, int mode = 0, unsigned reinit_mask = 0u) {
         io_ = io;
+        ss_mode_ = (SS && mode == SS_PREEQ) ? SS_PREEQ : SS_OFF;
+        const bool keep = SS && mode == SS_POSTEQ;  // initial values: the pre-equilibrated state
+        if (SS) reinit_mask &= M::X0K_MASK;         // only states whose x0 depends on the constants are re-initialised
         opt.rtol = rtol;
         opt.atol = atol;
         nsall = io.ns;
@@ -1606,7 +1704,7 @@ struct Bdf {
             PB_UNROLL
             for (int i = 0; i < NX; ++i) {
                 const int e = c * NX + i;
-                S()->zn[0][e] = v[i];
+                if (!keep || ((reinit_mask >> i) & 1u)) S()->zn[0][e] = v[i];
                 for (int j = 1; j < cv::L_MAX; ++j) S()->zn[j][e] = 0.0;
                 S()->acor[e] = 0.0;
                 S()->ewt[e] = 1.0;
@@ -1662,25 +1760,43 @@ struct Bdf {
         if (!in_step_) {
             if (!in_cvode_) {
                 for (;;) {
+                    if (SS && ss_mode_ == SS_PREEQ) break;
                     if (it_ >= io_.nt) { finish(SIM_SUCCESS); return; }
                     tout_ = io_.t[it_];
-                    if (!PB_FINITE(tout_)) { finish(SIM_ERROR); return; }  // t = inf (post-equilibration) is not implemented: an error, never a silently dropped point (pb200_create rejects such tables)
+                    if (!PB_FINITE(tout_)) {
+                        // t = inf: post-equilibration (amici.cpp:109-114; ForwardProblem stops at the first infinite
+                        // output time, forwardproblem.cpp:149-150).  Without steady-state support an error, never a
+                        // silently dropped point.
+                        if (!SS) { finish(SIM_ERROR); return; }
+                        ss_mode_ = SS_POSTEQ;
+                        break;
+                    }
                     bool integrate = (tout_ > opt.t0) && (tn < tout_);
                     if (integrate) {  // is_next_t_too_close, forwardproblem.cpp:23-35
                         const double tdiff = tout_ - tn;
                         if (fabs(tdiff) < 2.0 * cv::UROUND * fmax(fabs(tn), fabs(tout_))) integrate = false;
                     }
                     if (integrate) break;
-                    double* yo = io_.y_out ? io_.y_out + (size_t)it_ * NY : nullptr;
-                    double* so = io_.sigmay_out ? io_.sigmay_out + (size_t)it_ * NY : nullptr;
-#if defined(PB200_HOST_TRACE)
-                    if (io_.trace) { io_.trace[2 * it_] = nst; io_.trace[2 * it_ + 1] = q; }
-#endif
-                    if (!data_point(tout_, io_.my + (size_t)it_ * NY, io_.sd + (size_t)it_ * NY, llh_, yo, so)) {
-                        finish(SIM_ERROR);
+                    if (!output_point()) return;
+                }
+                if (one_step()) {
+                    // one trip of SteadystateProblem::runSteadystateSimulation (steadystateproblem.cpp:711-794):
+                    // convergence test at the solver's current state, then ONE internal step towards
+                    // max(t, 1) * 10.  Steady-state tolerances: 100 x the integration tolerances.
+                    if (ss_converged_shared<M, Grp>(S(), g, tn, 100.0 * opt.rtol, 100.0 * opt.atol, ns, nsall)) {
+                        if (ss_mode_ == SS_POSTEQ) {
+                            // ReturnData::processPostEquilibration (rdata.cpp:234-258): every t = inf point
+                            // is evaluated at the steady state
+                            while (it_ < io_.nt) {
+                                tout_ = io_.t[it_];
+                                if (!output_point()) return;
+                            }
+                        }
+                        finish(SIM_SUCCESS);
                         return;
                     }
-                    it_++;
+                    if (nst >= opt.maxsteps) { finish(SIM_ERROR); return; }
+                    tout_ = fmax(tn, 1.0) * 10.0;
                 }
                 const int r = cvode_begin(tout_);
                 if (r < 0) { finish(r); return; }
@@ -1702,6 +1818,22 @@ struct Bdf {
         stage_ = ST_NLS;
     }
 
+    /// The data point of output time it_ (tout_) at the current state; false = the simulation has ended
+    /// with an error (sigma not positive).
+    PB_HD bool output_point() {
+        double* yo = io_.y_out ? io_.y_out + (size_t)it_ * NY : nullptr;
+        double* so = io_.sigmay_out ? io_.sigmay_out + (size_t)it_ * NY : nullptr;
+#if defined(PB200_HOST_TRACE)
+        if (io_.trace) { io_.trace[2 * it_] = nst; io_.trace[2 * it_ + 1] = q; }
+#endif
+        if (!data_point(tout_, io_.my + (size_t)it_ * NY, io_.sd + (size_t)it_ * NY, llh_, yo, so)) {
+            finish(SIM_ERROR);
+            return false;
+        }
+        it_++;
+        return true;
+    }
+
     /// stage_nls: the Newton corrector of one phase (state, then all sensitivities) + error test
     PB_HD void stage_nls(int phase) {
         if (stage_ != ST_NLS) return;
@@ -1720,6 +1852,10 @@ struct Bdf {
         in_step_ = false;
         if (r < 0) return finish(r);
         nstloc_++;
+        if (one_step()) {  // CV_ONE_STEP: return after every internal step (cvodes.c:3590-3600)
+            in_cvode_ = false;
+            return false;
+        }
         const double troundoff = cv::FUZZ_FACTOR * cv::UROUND * (fabs(tn) + fabs(h));
         if (fabs(tn - tstop) <= troundoff) {
             tn = tstop;
@@ -1744,6 +1880,10 @@ struct Bdf {
 
     PB_HD bool finish(int status) {
         stage_ = ST_DONE;
+        // any failure while simulating to steady state ends as AmiException -> AMICI_ERROR
+        // (SteadystateProblem::findSteadyStateBySimulation / handleSteadyStateFailure,
+        // steadystateproblem.cpp:198-255,397-425; amici.cpp:186-192)
+        if (one_step() && status != SIM_SUCCESS) status = SIM_ERROR;
         sim_status_ = status;
         if (status != SIM_SUCCESS) llh_ = NAN;  // ReturnData::invalidate (rdata.cpp)
         g.sync();

@@ -40,6 +40,12 @@ struct KernelArgs {
     const int* nplist;             // [C]
     const int* inv_j;              // [C*np] optimisation indices a condition maps to, ascending (padding: INT_MAX)
     const int* inv_i;              // [C*np] the model parameter of each entry of inv_j (ascending within equal j)
+    // steady states (pb200_set_preequilibration / t = inf output times): null / 0 without them
+    const double* k_preeq;         // [C*nk] constants of the pre-equilibration condition
+    const int* preeq_flag;         // [C] 1 = the condition is pre-equilibrated
+    const unsigned* reinit_mask;   // [C] states re-initialised after pre-equilibration (bit i = state i)
+    int steady;                    // 1 = some condition has a pre-equilibration or a t = inf output time:
+                                   //     the steady-state instantiation of the kernel is launched
     // --- per evaluation ---
     const double* theta_tab;       // [n_opt*3*2]: for optimisation parameter j and simulation
                                    // scale s: (value in simulation scale, unscaled value)
@@ -86,13 +92,20 @@ constexpr double PB_LN10 = 2.302585092994046;
 /// larger than the SM's instruction caches and is streamed from L2 every attempt
 /// (profiles/README.md); a line fetched for one warp is reused by the others only while they
 /// are close behind.
-template <class M, int G, int THREADS, bool CTA_SYNC>
+///
+/// SS = true is the instantiation with steady-state support: output times
+/// t = inf (post-equilibration) and a pre-equilibration phase per condition
+/// (amici.cpp:95-114: preeq -> forward problem -> posteq); it is launched only for problems that
+/// have either, the SS = false kernel is the code without any of it.
+template <class M, int G, int THREADS, bool CTA_SYNC, bool SS = false>
 __global__ void __launch_bounds__(THREADS, PB_MIN_BLOCKS_FOR(THREADS, G)) simulate_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char pb_smem_raw[];
     LaneGroup<G> grp;
     GroupShared<M>* sh = reinterpret_cast<GroupShared<M>*>(pb_smem_raw) + (threadIdx.x / G);
     PB_ASSUME_SHARED(sh);
-    Bdf<M, LaneGroup<G>> bdf;
+    using BdfT = Bdf<M, LaneGroup<G>, SS>;
+    BdfT bdf;
+    bool preeq_phase = false;  // SS: the pre-equilibration of the current condition is running
     bdf.sh = sh;
     bdf.opt = a.opt;
     const int lane = grp.lane();
@@ -136,7 +149,13 @@ __global__ void __launch_bounds__(THREADS, PB_MIN_BLOCKS_FOR(THREADS, G)) simula
                     sh->p[i] = pu;
                     sh->plist[i] = a.plist[cp + i];
                 }
-                for (int i = lane; i < M::NK; i += G) sh->k[i] = a.k[(size_t)c * M::NK + i];
+                if constexpr (SS) preeq_phase = a.preeq_flag && a.preeq_flag[c] != 0;
+                {
+                    // pre-equilibration runs with the constants of the pre-equilibration condition
+                    // (ConditionContext, deps/AMICI/src/edata.cpp:511-524)
+                    const double* ksrc = (SS && preeq_phase) ? a.k_preeq : a.k;
+                    for (int i = lane; i < M::NK; i += G) sh->k[i] = ksrc[(size_t)c * M::NK + i];
+                }
                 grp.sync();
                 const int64_t t0off = a.t_offsets[c];
                 io.nt = (int)(a.t_offsets[c + 1] - t0off);
@@ -147,7 +166,8 @@ __global__ void __launch_bounds__(THREADS, PB_MIN_BLOCKS_FOR(THREADS, G)) simula
                 io.y_out = a.y_out ? a.y_out + t0off * M::NY : nullptr;
                 io.sigmay_out = a.sigmay_out ? a.sigmay_out + t0off * M::NY : nullptr;
                 trial = 1;
-                bdf.begin(io, a.opt.rtol, a.opt.atol);
+                if constexpr (SS) bdf.begin(io, a.opt.rtol, a.opt.atol, preeq_phase ? BdfT::SS_PREEQ : BdfT::SS_OFF);
+                else bdf.begin(io, a.opt.rtol, a.opt.atol);
                 active = true;
             }
         }
@@ -166,13 +186,43 @@ __global__ void __launch_bounds__(THREADS, PB_MIN_BLOCKS_FOR(THREADS, G)) simula
         else __syncwarp();
         if (active && bdf.stage_post()) {
             const int status = bdf.status();
-            if (status != SIM_SUCCESS && trial < a.num_trials) {
+            bool resumed = false;
+            if constexpr (SS) {
+                if (preeq_phase && status == SIM_SUCCESS) {
+                    // ---- pre-equilibrated: the main simulation starts from the steady state with the
+                    //      simulation condition's constants (ForwardProblem, forwardproblem.cpp:59-63,
+                    //      119-120), at the tolerances of the current trial ----
+                    const int c = a.idx[r];
+                    double relax = 1.0;
+                    for (int e = 1; e < trial; ++e) relax *= a.relaxation_factor;
+                    grp.sync();
+                    for (int i = lane; i < M::NK; i += G) sh->k[i] = a.k[(size_t)c * M::NK + i];
+                    grp.sync();
+                    preeq_phase = false;
+                    bdf.begin(io, a.opt.rtol * relax, a.opt.atol * relax, BdfT::SS_POSTEQ,
+                              a.reinit_mask ? a.reinit_mask[c] : 0u);
+                    resumed = true;
+                }
+            }
+            if (resumed) {
+            } else if (status != SIM_SUCCESS && trial < a.num_trials) {
                 // ---- A8: runAndLogSimulation retry (multiConditionProblem.cpp:369-465): trial t
                 //      runs at tolerances * relaxation^(t-1) relative to the template ----
                 double relax = 1.0;
                 for (int e = 0; e < trial; ++e) relax *= a.relaxation_factor;
                 ++trial;
-                bdf.begin(io, a.opt.rtol * relax, a.opt.atol * relax);
+                if constexpr (SS) {
+                    const int c = a.idx[r];
+                    preeq_phase = a.preeq_flag && a.preeq_flag[c] != 0;
+                    if (preeq_phase) {  // the whole simulation is repeated, pre-equilibration included
+                        grp.sync();
+                        for (int i = lane; i < M::NK; i += G) sh->k[i] = a.k_preeq[(size_t)c * M::NK + i];
+                        grp.sync();
+                    }
+                    bdf.begin(io, a.opt.rtol * relax, a.opt.atol * relax, preeq_phase ? BdfT::SS_PREEQ : BdfT::SS_OFF);
+                } else {
+                    bdf.begin(io, a.opt.rtol * relax, a.opt.atol * relax);
+                }
             } else {
                 // ---- outputs: A7 result package + A6 chain rule to the optimiser scale ----
                 if (lane == 0) {
@@ -296,6 +346,8 @@ struct ModelOps {
     void (*destroy_state)(void* state);
     // large-model path: description of the linear solver chosen at create (null otherwise)
     int (*linsol_info)(void* state, int64_t* out, int n);
+    // 1 = the model's kernels handle pre-equilibration and t = inf output times (KernelArgs::steady)
+    int supports_steady;
 };
 
 void register_model(const ModelOps& ops);
@@ -303,9 +355,9 @@ const ModelOps* find_model(const char* name);
 int model_count();
 const ModelOps* model_at(int i);
 
-template <class M, int G, int THREADS, bool CTA_SYNC>
+template <class M, int G, int THREADS, bool CTA_SYNC, bool SS = false>
 int launch_one(const KernelArgs& a, int sm_count, cudaStream_t stream, int* grid_used, int* block_used) {
-    auto kern = simulate_kernel<M, G, THREADS, CTA_SYNC>;
+    auto kern = simulate_kernel<M, G, THREADS, CTA_SYNC, SS>;
     const int groups_per_block = THREADS / G;
     const size_t smem = sizeof(GroupShared<M>) * groups_per_block;
     // the attribute is per device (context): set before every launch (cheap), not cached per process
@@ -374,6 +426,13 @@ int launch_model(const KernelArgs& a, int lanes, int variant, int sm_count, cuda
     // >= 8): half the warps walk the instruction stream for the same conditions (measured on the
     // Boehm shape: +4.5 %; four per lane: -40 %)
     int G = ((M::NX & (M::NX - 1)) == 0 && M::NX >= 8) ? GH : GN;
+    if (a.steady) {
+        // problems with a pre-equilibration or t = inf output times: the steady-state instantiation, offered
+        // in the default shape only (default lane-group width, one CTA per SM)
+        constexpr int GS = ((M::NX & (M::NX - 1)) == 0 && M::NX >= 8) ? GH : GN;
+        if (lanes_used) *lanes_used = GS;
+        return launch_one<M, GS, pb_big_cta_threads<M, GS>(), true, true>(a, sm_count, stream, grid_used, block_used);
+    }
     if (lanes == GN || lanes == GH || lanes == G2) G = lanes;
     if (lanes_used) *lanes_used = G;
     if (G == GH && GH != GN) return launch_shape<M, GH>(a, variant, sm_count, stream, grid_used, block_used);
@@ -392,6 +451,7 @@ ModelOps make_ops() {
     o.create_state = nullptr;
     o.destroy_state = nullptr;
     o.linsol_info = nullptr;
+    o.supports_steady = 1;
     return o;
 }
 

@@ -163,6 +163,11 @@ struct pb200_handle {
     int64_t last_h2d = 0, last_d2h = 0;
     // large-model path: device tables + workspace (ModelOps::create_state)
     void* model_state = nullptr;
+    // steady states: t = inf output times in the table / pre-equilibration tables (pb200_set_preequilibration)
+    bool has_inf = false, has_preeq = false;
+    DevBuf<double> d_k_preeq;
+    DevBuf<int> d_preeq_flag;
+    DevBuf<unsigned> d_reinit_mask;
 };
 
 static int ensure_capacity(pb200_handle* h, int n) {
@@ -311,14 +316,21 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
     if (pb200_device_count() <= 0) return fail(PB200_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
     PB_CUDA(cudaSetDevice(device));
     const int C = d->n_conditions;
+    bool has_inf = false;
     for (int c = 0; c < C; ++c) {
         if (d->t_offsets[c + 1] < d->t_offsets[c]) return fail(PB200_ERR_ARG, "t_offsets not monotone");
-        // Output times: finite and non-decreasing (amici::ExpData requires sorted time points).  t = inf
-        // (post-equilibration, steadystateproblem.cpp) is not implemented: rejected here rather than
-        // silently dropped from the objective.
+        // Output times: non-decreasing (amici::ExpData requires sorted time points), finite or +inf.
+        // t = +inf asks for post-equilibration (steadystateproblem.cpp): the data point is evaluated at the
+        // steady state the simulation is carried on to.  Models whose kernels do not handle it refuse the
+        // table rather than silently dropping the point from the objective.
         for (int64_t it = d->t_offsets[c]; it < d->t_offsets[c + 1]; ++it) {
-            if (!std::isfinite(d->t[it]))
-                return fail(PB200_ERR_ARG, "non-finite output time (t = inf / post-equilibration is not supported)");
+            if (std::isnan(d->t[it]) || d->t[it] == -std::numeric_limits<double>::infinity())
+                return fail(PB200_ERR_ARG, "output time is NaN or -inf");
+            if (std::isinf(d->t[it])) {
+                if (!ops->supports_steady)
+                    return fail(PB200_ERR_ARG, "non-finite output time (t = inf / post-equilibration is not supported for this model)");
+                has_inf = true;
+            }
             if (it > d->t_offsets[c] && d->t[it] < d->t[it - 1])
                 return fail(PB200_ERR_ARG, "output times of a condition must be non-decreasing");
         }
@@ -346,6 +358,7 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
     h->ny = d->ny;
     h->lanes = d->lanes_per_condition;
     h->reorder = 1;
+    h->has_inf = has_inf;
     h->pscale_opt.assign(d->pscale_opt, d->pscale_opt + d->n_opt);
     h->t_offsets.assign(d->t_offsets, d->t_offsets + C + 1);
     h->nt_total = C > 0 ? d->t_offsets[C] : 0;
@@ -424,6 +437,10 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
     a.nplist = h->d_nplist.p;
     a.inv_j = h->d_inv_j.p;
     a.inv_i = h->d_inv_i.p;
+    a.k_preeq = nullptr;
+    a.preeq_flag = nullptr;
+    a.reinit_mask = nullptr;
+    a.steady = has_inf ? 1 : 0;
     a.opt.t0 = d->t0;
     a.opt.rtol = d->rtol;
     a.opt.atol = d->atol;
@@ -455,6 +472,48 @@ void pb200_destroy(pb200_handle* h) {
     if (h->ev_staged) cudaEventDestroy(h->ev_staged);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+}
+
+int pb200_set_preequilibration(pb200_handle* h, const int32_t* has_preeq, const double* k_preeq,
+                               const int64_t* reinit_offsets, const int32_t* reinit_idx) {
+    if (!h) return fail(PB200_ERR_ARG, "null handle");
+    PB_CUDA(cudaSetDevice(h->device));
+    if (h->stream) PB_CUDA(cudaStreamSynchronize(h->stream));
+    KernelArgs& a = h->args;
+    if (!has_preeq) {  // switch pre-equilibration off
+        h->has_preeq = false;
+        a.k_preeq = nullptr;
+        a.preeq_flag = nullptr;
+        a.reinit_mask = nullptr;
+        a.steady = h->has_inf ? 1 : 0;
+        return 0;
+    }
+    if (!h->ops->supports_steady) return fail(PB200_ERR_ARG, "pre-equilibration is not supported for this model");
+    if (!k_preeq && h->nk > 0) return fail(PB200_ERR_ARG, "k_preeq is null");
+    std::vector<int> flag(h->C);
+    std::vector<unsigned> mask(h->C, 0u);
+    bool any = false;
+    for (int c = 0; c < h->C; ++c) {
+        flag[c] = has_preeq[c] != 0;
+        any = any || flag[c];
+        if (!reinit_offsets) continue;
+        if (reinit_offsets[c + 1] < reinit_offsets[c]) return fail(PB200_ERR_ARG, "reinit_offsets not monotone");
+        for (int64_t e = reinit_offsets[c]; e < reinit_offsets[c + 1]; ++e) {
+            const int i = reinit_idx[e];
+            if (i < 0 || i >= h->ops->nx) return fail(PB200_ERR_ARG, "re-initialisation state index out of range");
+            if (i >= 32) return fail(PB200_ERR_ARG, "re-initialisation of state indices >= 32 is not supported");
+            mask[c] |= 1u << i;
+        }
+    }
+    PB_CUDA(h->d_k_preeq.upload(k_preeq, (size_t)h->C * h->nk));
+    PB_CUDA(h->d_preeq_flag.upload(flag.data(), flag.size()));
+    PB_CUDA(h->d_reinit_mask.upload(mask.data(), mask.size()));
+    h->has_preeq = any;
+    a.k_preeq = h->d_k_preeq.p;
+    a.preeq_flag = h->d_preeq_flag.p;
+    a.reinit_mask = h->d_reinit_mask.p;
+    a.steady = (h->has_inf || any) ? 1 : 0;
+    return 0;
 }
 
 int pb200_set_partition(pb200_handle* h, int rank, int world) {

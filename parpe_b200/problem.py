@@ -37,6 +37,13 @@ class B200SummedGradientFunction:
         if tables.hier is not None:
             self._hd = tables.hier.to_desc()
             capi.check(L.pb200_hier_attach(self._h, C.byref(self._hd)), "pb200_hier_attach")
+        pre = tables.preeq_args()
+        if pre is not None:
+            flag, kp, off, flat = pre
+            capi.check(L.pb200_set_preequilibration(self._h, flag.ctypes.data_as(C.POINTER(C.c_int32)), capi.dptr(kp),
+                                                    off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                    flat.ctypes.data_as(C.POINTER(C.c_int32))),
+                       "pb200_set_preequilibration")
 
     @classmethod
     def from_hdf5(cls, path, model_name: str, device: int = 0):

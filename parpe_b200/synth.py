@@ -57,7 +57,8 @@ def make_problem(model: str, n_conditions: int, *, scale: str = "log10", seed: i
                  simulate: Optional[Callable] = None, noise: float = 0.1,
                  missing_fraction: float = 0.0, ragged: bool = False,
                  condition_specific: int = 0, rtol: float = 1e-8, atol: float = 1e-12,
-                 holes: int = 0, heterogeneous: bool = False, **kw) -> ProblemTables:
+                 holes: int = 0, heterogeneous: bool = False, posteq: int = 0, preeq: bool = False,
+                 **kw) -> ProblemTables:
     """Build tables for ``model`` with ``n_conditions`` conditions.
 
     scale: 'log10' | 'lin' | 'mixed' (optimiser scale of every parameter; the
@@ -72,6 +73,11 @@ def make_problem(model: str, n_conditions: int, *, scale: str = "log10", seed: i
            to an optimisation parameter (mapping = -1): they take their value from
            ``/parameters/parameterOverrides`` (a perturbed nominal value in the simulation scale) and drop
            out of the sensitivity list (multiConditionDataProvider.cpp:84-102,126-169,323-339).
+    posteq: the last `posteq` output times of every condition become t = inf (post-equilibration: the data
+           point is evaluated at the steady state, deps/AMICI/src/steadystateproblem.cpp).
+    preeq: three of four conditions (c % 4 != 1) get a pre-equilibration condition -- the simulation
+           condition's constants perturbed by up to 50 % -- and the re-initialisation list [0, 2][: c % 3]
+           (multiConditionDataProvider.cpp:224-250).
     simulate(tables, theta) -> y_flat: optional callable producing noise-free
            outputs to derive measurements from; without it measurements are
            positive pseudo-data (throughput work is independent of them).
@@ -84,7 +90,13 @@ def make_problem(model: str, n_conditions: int, *, scale: str = "log10", seed: i
     if ragged:
         nts = np.maximum(1, len(tp) - (np.arange(C) % 3))
     t_offsets = np.concatenate([[0], np.cumsum(nts)]).astype(np.int64)
-    t = np.concatenate([tp[:n] for n in nts])
+
+    def _times(n):
+        tt = np.array(tp[:n], dtype=float)
+        if posteq:
+            tt[max(0, n - posteq):] = np.inf
+        return tt
+    t = np.concatenate([_times(n) for n in nts])
     np_, nk, ny = spec.np, spec.nk, spec.ny
 
     n_groups = 2 if condition_specific else 1
@@ -134,6 +146,11 @@ def make_problem(model: str, n_conditions: int, *, scale: str = "log10", seed: i
         y = np.where(rng.random(y.size) < missing_fraction, np.nan, y)
     tab.y = np.ascontiguousarray(y)
     tab.sigma = np.ascontiguousarray(sigma)
+    if preeq:
+        prng = np.random.default_rng(seed + 2000)
+        tab.has_preeq = np.array([1 if c % 4 != 1 else 0 for c in range(C)], dtype=np.int32)
+        tab.k_preeq = tab.k * (1.0 + 0.5 * prng.uniform(-1, 1, size=tab.k.shape))
+        tab.reinit_idx = [[0, 2][: (c % 3)] for c in range(C)]
     return tab
 
 

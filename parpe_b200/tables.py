@@ -126,6 +126,25 @@ class ProblemTables:
     relaxation_factor: float = 100.0
     lanes_per_condition: int = 0
     hier: Optional[HierTables] = None
+    # pre-equilibration (pb200_set_preequilibration): per simulation condition a flag, the constants of
+    # the pre-equilibration condition and the states re-initialised afterwards
+    has_preeq: Optional[np.ndarray] = None   # int32 [C]
+    k_preeq: Optional[np.ndarray] = None     # float64 [C, nk]
+    reinit_idx: Optional[list] = None        # C lists of state indices
+
+    def preeq_args(self):
+        """(has_preeq, k_preeq, reinit_offsets, reinit_idx) arrays for pb200_set_preequilibration, or None."""
+        if self.has_preeq is None:
+            return None
+        Cn = self.n_conditions
+        flag = np.ascontiguousarray(self.has_preeq, dtype=np.int32).reshape(Cn)
+        kp = np.ascontiguousarray(self.k_preeq if self.k_preeq is not None else np.zeros((Cn, self.nk)),
+                                  dtype=np.float64).reshape(Cn, self.nk)
+        lists = self.reinit_idx if self.reinit_idx is not None else [[] for _ in range(Cn)]
+        off = np.zeros(Cn + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(l) for l in lists])
+        flat = np.ascontiguousarray([i for l in lists for i in l] or [0], dtype=np.int32)
+        return flag, kp, off, flat
 
     def __post_init__(self):
         self.t_offsets = np.ascontiguousarray(self.t_offsets, dtype=np.int64)

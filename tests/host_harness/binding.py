@@ -27,8 +27,40 @@ def lib():
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
         L.hs_simulate.argtypes = [C.c_char_p, dp, dp, ip, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double,
                                   C.c_double, C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int64), dp, dp, ip]
+        L.hs_simulate_ss.argtypes = [C.c_char_p, dp, dp, dp, C.c_uint, ip, C.c_int, C.c_int, dp, dp, dp, C.c_double,
+                                     C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int64),
+                                     dp, dp, ip, dp]
         _lib = L
     return _lib
+
+
+def simulate_ss(model, p_unscaled, k, plist, t, my, sd, k_preeq=None, reinit_idx=(), t0=0.0, rtol=1e-8, atol=1e-12,
+                maxsteps=10000, stldet=1, errconS=1, want_outputs=False, nx=None):
+    """The steady-state instantiation of the core: t = inf output times (post-equilibration) and, with
+    ``k_preeq``, pre-equilibration + re-initialisation of the states ``reinit_idx``."""
+    d = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    p_unscaled, k, t, my, sd = d(p_unscaled), d(k), d(t), d(my).reshape(-1), d(sd).reshape(-1)
+    kp = d(k_preeq) if k_preeq is not None else None
+    plist = np.ascontiguousarray(plist, dtype=np.int32)
+    ns = len(plist)
+    llh = C.c_double()
+    sllh = np.zeros(max(ns, 1))
+    stats = np.zeros(20, dtype=np.int64)
+    y = np.zeros(my.size) if want_outputs else None
+    s = np.zeros(my.size) if want_outputs else None
+    trace = np.zeros(2 * len(t), dtype=np.int32)
+    xpre = np.zeros(64 * 64)
+    mask = 0
+    for i in reinit_idx:
+        mask |= 1 << int(i)
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+    st = lib().hs_simulate_ss(model.encode(), P(p_unscaled), P(k), P(kp), mask,
+                              plist.ctypes.data_as(C.POINTER(C.c_int)), ns, len(t), P(t), P(my), P(sd), t0, rtol, atol,
+                              maxsteps, stldet, errconS, C.byref(llh), P(sllh),
+                              stats.ctypes.data_as(C.POINTER(C.c_int64)), P(y), P(s),
+                              trace.ctypes.data_as(C.POINTER(C.c_int)), P(xpre))
+    return dict(numsteps=trace[0::2], order=trace[1::2], status=st, llh=llh.value, sllh=sllh[:ns], stats=stats, y=y,
+                sigmay=s, x_preeq=xpre, nst_preeq=int(stats[16]))
 
 
 def simulate(model, p_unscaled, k, plist, t, my, sd, t0=0.0, rtol=1e-8, atol=1e-12, maxsteps=10000, stldet=1,

@@ -38,6 +38,71 @@ static int run(const double* p_unscaled, const double* k, const int* plist, int 
     return status;
 }
 
+/// The steady-state instantiation (Bdf<M, Grp, true>): t = inf output times and, with k_preeq != nullptr,
+/// a pre-equilibration phase followed by the re-initialisation of the states in reinit_mask -- the
+/// sequence simulate_kernel's steady-state variant runs per condition.
+template <class M>
+static int run_ss(const double* p_unscaled, const double* k, const double* k_preeq, unsigned reinit_mask,
+                  const int* plist, int ns, int nt, const double* t, const double* my, const double* sd, double t0,
+                  double rtol, double atol, int maxsteps, int stldet, int errconS, double* llh, double* sllh,
+                  int64_t* stats, double* y_out, double* sigmay_out, int* trace, double* x_preeq) {
+    static thread_local GroupShared<M> sh;
+    static thread_local Bdf<M, SingleLane, true> bdf;
+    using B = Bdf<M, SingleLane, true>;
+    bdf.sh = &sh;
+    for (int i = 0; i < M::NP; ++i) sh.p[i] = p_unscaled[i];
+    for (int i = 0; i < ns; ++i) sh.plist[i] = plist[i];
+    bdf.opt.t0 = t0;
+    bdf.opt.maxsteps = maxsteps;
+    bdf.opt.stldet = stldet;
+    bdf.opt.errconS = errconS;
+    ConditionIO io{nt, t, my, sd, ns, y_out, sigmay_out, trace};
+    int status;
+    if (k_preeq) {
+        for (int i = 0; i < M::NK; ++i) sh.k[i] = k_preeq[i];
+        bdf.begin(io, rtol, atol, B::SS_PREEQ);
+        while (!bdf.advance()) {}
+        status = bdf.status();
+        stats[16] = bdf.nst;  // steps of the pre-equilibration
+        if (x_preeq)
+            for (int i = 0; i < M::NX * bdf.ncol; ++i) x_preeq[i] = sh.zn[0][i];
+        if (status == SIM_SUCCESS) {
+            for (int i = 0; i < M::NK; ++i) sh.k[i] = k[i];
+            bdf.begin(io, rtol, atol, B::SS_POSTEQ, reinit_mask);
+            while (!bdf.advance()) {}
+            status = bdf.status();
+        }
+    } else {
+        for (int i = 0; i < M::NK; ++i) sh.k[i] = k[i];
+        bdf.begin(io, rtol, atol);
+        while (!bdf.advance()) {}
+        status = bdf.status();
+    }
+    *llh = bdf.llh();
+    for (int j = 0; j < ns; ++j) sllh[j] = sh.sllh[j + 1];
+    const int64_t npre = stats[16];
+    bdf.export_stats(stats, 1);
+    stats[16] = k_preeq ? npre : 0;
+    return status;
+}
+
+extern "C" int hs_simulate_ss(const char* model, const double* p_unscaled, const double* k, const double* k_preeq,
+                              unsigned reinit_mask, const int* plist, int ns, int nt, const double* t,
+                              const double* my, const double* sd, double t0, double rtol, double atol, int maxsteps,
+                              int stldet, int errconS, double* llh, double* sllh, int64_t* stats, double* y_out,
+                              double* sigmay_out, int* trace, double* x_preeq) {
+#define DISPATCH_SS(NAME)                                                                                          \
+    if (!std::strcmp(model, #NAME))                                                                                \
+        return run_ss<models::Model_##NAME>(p_unscaled, k, k_preeq, reinit_mask, plist, ns, nt, t, my, sd, t0, rtol, \
+                                            atol, maxsteps, stldet, errconS, llh, sllh, stats, y_out, sigmay_out,  \
+                                            trace, x_preeq);
+    DISPATCH_SS(steadystate)
+    DISPATCH_SS(steadystate_scaled)
+    DISPATCH_SS(boehm)
+    DISPATCH_SS(fujita)
+    return -12345;
+}
+
 extern "C" int hs_simulate(const char* model, const double* p_unscaled, const double* k, const int* plist, int ns,
                            int nt, const double* t, const double* my, const double* sd, double t0, double rtol,
                            double atol, int maxsteps, int stldet, int errconS, double* llh, double* sllh,

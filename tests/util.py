@@ -23,3 +23,22 @@ def assert_grad_close(a, b, what="gradient"):
     e = np.abs(a - b) / np.maximum(np.abs(b), 1e-4 * scale + 1e-300)
     assert np.all(e <= GRAD_RTOL), "%s: max relative error %.3e > %.1e\n got %r\n ref %r" % (
         what, float(np.max(e)), GRAD_RTOL, a, b)
+
+
+def condition_inputs(tab, theta, c):
+    """What the kernel prologue derives for condition c (A5): unscaled model parameters, the sensitivity
+    parameter list, and the chain-rule factors d p / d (simulation-scale parameter) per plist entry."""
+    from parpe_b200.tables import SCALE_LN, SCALE_LOG10
+    p = np.empty(tab.np_)
+    for i in range(tab.np_):
+        j = tab.mapping[c, i]
+        if j < 0:  # unmapped: the override value, given in the simulation scale
+            v, sc = tab.overrides[c, i], tab.pscale_sim[c, i]
+            p[i] = 10.0 ** v if sc == SCALE_LOG10 else (np.exp(v) if sc == SCALE_LN else v)
+            continue
+        p[i] = 10.0 ** theta[j] if tab.pscale_opt[j] == SCALE_LOG10 else (
+            np.exp(theta[j]) if tab.pscale_opt[j] == SCALE_LN else theta[j])
+    plist = [i for i in range(tab.np_) if tab.mapping[c, i] >= 0]
+    fac = np.array([p[i] * np.log(10) if tab.pscale_sim[c, i] == SCALE_LOG10 else
+                    (p[i] if tab.pscale_sim[c, i] == SCALE_LN else 1.0) for i in plist])
+    return p, plist, fac
