@@ -11,7 +11,7 @@ import pytest
 
 from parpe_b200 import synth
 from parpe_b200.tables import SCALE_LN, SCALE_LOG10
-from tests.util import assert_grad_close, assert_llh_close
+from tests.util import assert_grad_close, assert_llh_close, assert_outputs_close
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.json")))
@@ -58,6 +58,7 @@ def test_host_core_against_fixture(path):
         import functools
         # the full-horizon Chen-shape case runs with the sparse linear solver (as the CUDA path does by default)
         simulate = functools.partial(simulate_team, sparse=True) if doc["case"] == "chen_full" else simulate_team
+    steady = tab.has_preeq is not None or bool(np.any(np.isinf(tab.t)))
     for c in range(1 if doc["case"].endswith("_full") else tab.n_conditions):
         p = np.empty(tab.np_)
         for i in range(tab.np_):
@@ -71,7 +72,13 @@ def test_host_core_against_fixture(path):
             p[i] = lin
         plist = [i for i in range(tab.np_) if tab.mapping[c, i] >= 0]
         lo, hi = tab.t_offsets[c], tab.t_offsets[c + 1]
-        r = simulate(doc["model"], p, tab.k[c], plist, tab.t[lo:hi], tab.y_of(c), tab.sigma_of(c))
+        if steady:  # the steady-state instantiation of the core (pre-/post-equilibration)
+            from tests.host_harness.binding import simulate_ss
+            pre = tab.has_preeq is not None and tab.has_preeq[c]
+            r = simulate_ss(doc["model"], p, tab.k[c], plist, tab.t[lo:hi], tab.y_of(c), tab.sigma_of(c),
+                            k_preeq=tab.k_preeq[c] if pre else None, reinit_idx=tab.reinit_idx[c] if pre else ())
+        else:
+            r = simulate(doc["model"], p, tab.k[c], plist, tab.t[lo:hi], tab.y_of(c), tab.sigma_of(c))
         assert r["status"] == 0
         assert_llh_close(r["llh"], doc["llh"][c])
         fac = np.array([p[i] * np.log(10) if tab.pscale_sim[c, i] == SCALE_LOG10 else
@@ -93,9 +100,11 @@ def test_cuda_path_against_fixture(path):
     assert_llh_close(res["llh"], doc["llh"])
     for c in range(tab.n_conditions):
         assert_grad_close(res["sllh"][c], doc["sllh"][c], "per-condition sllh[%d]" % c)
-    if "nst" in doc:  # step counts stay close to the reference's (a wrong factorisation converges, but slower)
+    if doc.get("nst") is not None:  # step counts stay close to the reference's (a wrong factorisation converges, but slower)
         nst_ref = np.array(doc["nst"])
-        assert np.all(np.abs(res["stats"][:, 0] - nst_ref) <= 0.1 * nst_ref + 5), (res["stats"][:, 0], nst_ref)
+        tol = 0.2 if "preeq_steps" in doc and max(doc["preeq_steps"]) > 0 else 0.1  # (after a pre-equilibration the
+        # main simulation starts near a steady state and its step sequence is more sensitive: DESIGN 6)
+        assert np.all(np.abs(res["stats"][:, 0] - nst_ref) <= tol * nst_ref + 5), (res["stats"][:, 0], nst_ref)
         assert np.all(res["stats"][:, 16] == 0)  # no sparse-factorisation fallback
     if doc["case"].endswith("_full") and doc["model"] == "froehlich":
         return  # (the subset / output passes repeat the same integration: skipped for the nx = 1200 case)
@@ -105,5 +114,5 @@ def test_cuda_path_against_fixture(path):
     rc, y, s = gpu.getModelOutputsAndSigmas(theta)
     assert rc == 0
     yref = np.array([np.nan if v is None else v for v in doc["y"]])
-    np.testing.assert_allclose(y, yref, rtol=1e-6, atol=1e-9)
+    assert_outputs_close(y, yref, tab)
     np.testing.assert_allclose(s, np.array([np.nan if v is None else v for v in doc["sigmay"]]), rtol=1e-12)

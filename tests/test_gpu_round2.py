@@ -135,7 +135,8 @@ def test_unmapped_parameter_without_override_fails_like_the_reference(oracle_ava
 
 # ---------------------------------------------------------------- t = inf
 def test_nonfinite_or_decreasing_output_times_are_rejected():
-    for bad in ([0.1, np.inf], [0.1, np.nan], [1.0, 0.5]):
+    # (t = +inf at the END of a condition's list is post-equilibration: tests/test_gpu_steadystate.py)
+    for bad in ([0.1, -np.inf], [0.1, np.nan], [1.0, 0.5], [np.inf, 1.0]):
         tab = synth.make_problem("boehm", 2, seed=0, timepoints=np.array(bad))
         with pytest.raises(capi.B200LibraryError, match="output time"):
             _gpu(tab)

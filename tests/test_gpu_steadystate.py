@@ -1,0 +1,185 @@
+"""Steady states on the GPU: post-equilibration (output times t = inf) and pre-equilibration
+with re-initialisation of states through the C ABI (pb200_set_preequilibration) against the reference's own
+SteadystateProblem (deps/AMICI/src/steadystateproblem.cpp, oracle/_ref) on the same seeded inputs.  The committed
+fixtures steadystate_posteq / steadystate_scaled_preeq / boehm_preeq_posteq are covered by
+tests/test_golden_fixtures.py::test_cuda_path_against_fixture."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from parpe_b200 import capi, synth
+from tests.util import assert_grad_close, assert_llh_close, assert_outputs_close
+
+pytestmark = pytest.mark.gpu
+SIM_ERROR = -99
+
+
+def _oracle_sim(tab, theta):
+    from oracle.binding import OracleProblem
+    rc, y, _ = OracleProblem(tab).get_model_outputs(theta)
+    assert rc == 0
+    return y
+
+
+def _problem(model, C, preeq, posteq, n_finite=6, seed=3, **kw):
+    tp = np.asarray(synth.DEFAULT_TIMEPOINTS[model], dtype=float)[:n_finite + posteq]
+    return synth.make_problem(model, C, seed=seed, timepoints=tp, preeq=preeq, posteq=posteq,
+                              simulate=_oracle_sim, **kw)
+
+
+def _both(tab):
+    from oracle.binding import OracleProblem
+    from parpe_b200.problem import B200SummedGradientFunction
+    return B200SummedGradientFunction(tab), OracleProblem(tab)
+
+
+CASES = [
+    ("steadystate", 4, False, 2, dict(scale="lin")),
+    ("steadystate", 8, True, 0, dict(scale="log10", sigma_mode="data")),
+    ("steadystate_scaled", 6, True, 2, dict(scale="mixed", sigma_mode="mixed", missing_fraction=0.2, ragged=True)),
+    ("boehm", 5, True, 1, dict(scale="log10")),
+    ("boehm", 4, False, 2, dict(scale="mixed", sigma_mode="mixed")),
+]
+
+
+@pytest.mark.parametrize("model,C,preeq,posteq,kw", CASES,
+                         ids=["%s-%d-%s%s" % (m, c, "preeq" if p else "", "+posteq" if q else "") for m, c, p, q, _ in CASES])
+def test_steady_state_evaluate_matches_oracle(oracle_available, model, C, preeq, posteq, kw):
+    tab = _problem(model, C, preeq, posteq, **kw)
+    gpu, ora = _both(tab)
+    assert gpu.last_launch() is not None
+    for seed, width in ((0, 0.0), (1, 0.3)):
+        theta = synth.random_theta(tab, seed=seed, width=width)
+        ro = ora.evaluate(theta)
+        st, fval, grad, _ = gpu.evaluate(theta)
+        assert st == ro["status"] == 0
+        assert_llh_close(fval, ro["fval"], "nllh")
+        assert_grad_close(grad, ro["grad"], "gradient")
+        res = gpu.condition_results()
+        assert np.array_equal(res["status"], ro["cond_status"])
+        assert_llh_close(res["llh"], ro["llh"], "per-condition llh")
+        for c in range(C):
+            assert_grad_close(res["sllh"][c], ro["sllh"][c], "per-condition sllh[%d]" % c)
+        # cost only: the pre-equilibration then integrates no sensitivities either
+        st, fval0, g0, _ = gpu.evaluate(theta, want_gradient=False)
+        ro0 = ora.evaluate(theta, want_grad=False)
+        assert st == 0 and g0 is None
+        assert_llh_close(fval0, ro0["fval"], "nllh (cost only)")
+    # a minibatch with duplicates and the model outputs (t = inf rows: the observables at the steady state)
+    sub = [C - 1, 0, 0, 1]
+    st, fs, gs, _ = gpu.evaluate(theta, sub)
+    rs = ora.evaluate(theta, idx=sub)
+    assert_llh_close(fs, rs["fval"])
+    assert_grad_close(gs, rs["grad"])
+    rc, y, s = gpu.getModelOutputsAndSigmas(theta)
+    rco, yo, so = ora.get_model_outputs(theta)
+    assert rc == rco == 0
+    assert_outputs_close(y, yo, tab)
+    np.testing.assert_allclose(s, so, rtol=1e-12)
+
+
+def test_fujita_shape_within_the_reference_variants_spread(oracle_available):
+    """See tests/test_host_steadystate.py: where the steady-state stopping rule fires depends on the step sequence;
+    on the Fujita shape the reference's KLU and dense variants differ by ~2e-5 at the t = inf points."""
+    from oracle.binding import LINSOL_DENSE, LINSOL_KLU, OracleProblem
+    from parpe_b200.problem import B200SummedGradientFunction
+    tab = _problem("fujita", 6, True, 2)
+    theta = synth.random_theta(tab, seed=1, width=0.3)
+    a = OracleProblem(tab, linsol=LINSOL_KLU).evaluate(theta)
+    b = OracleProblem(tab, linsol=LINSOL_DENSE).evaluate(theta)
+    spread = abs(a["fval"] - b["fval"]) / abs(a["fval"])
+    gs = np.max(np.abs(a["grad"]))
+    gspread = np.max(np.abs(a["grad"] - b["grad"]) / np.maximum(np.abs(a["grad"]), 1e-4 * gs))
+    st, fval, grad, _ = B200SummedGradientFunction(tab).evaluate(theta)
+    assert st == a["status"] == 0
+    assert abs(fval - a["fval"]) / abs(a["fval"]) <= max(3.0 * spread, 1e-6)
+    assert np.max(np.abs(grad - a["grad"]) / np.maximum(np.abs(a["grad"]), 1e-4 * gs)) <= max(3.0 * gspread, 1e-4)
+
+
+def test_many_conditions_through_the_work_queue(oracle_available):
+    """More conditions than lane groups of a CTA wave would need is not required: 600 conditions, three of four
+    pre-equilibrated, pulled from the in-kernel queue by the steady-state kernel; all results against the oracle."""
+    tab = _problem("steadystate", 600, True, 1, scale="log10")
+    gpu, ora = _both(tab)
+    theta = synth.random_theta(tab, seed=2, width=0.3)
+    ro = ora.evaluate(theta)
+    st, fval, grad, _ = gpu.evaluate(theta)
+    assert st == ro["status"] == 0
+    assert_llh_close(fval, ro["fval"])
+    assert_grad_close(grad, ro["grad"])
+    res = gpu.condition_results()
+    assert_llh_close(res["llh"], ro["llh"])
+    # run-to-run reproducible (fixed-order reduction; per-condition results independent of the schedule)
+    st2, fval2, grad2, _ = gpu.evaluate(theta)
+    assert fval2 == fval and np.array_equal(grad, grad2)
+
+
+def test_equilibration_failure_maps_to_inf(oracle_available):
+    """Too few steps to equilibrate: AMICI_ERROR per condition (steadystateproblem.cpp:397-425), retried with relaxed
+    tolerances, then fval = +inf / functionEvaluationFailure (multiConditionProblem.cpp:669-672)."""
+    tab = _problem("steadystate", 4, True, 1)
+    tab.maxsteps = 150
+    tab.num_trials = 2
+    gpu, ora = _both(tab)
+    theta = synth.random_theta(tab, seed=1, width=0.3)
+    ro = ora.evaluate(theta)
+    st, fval, _, _ = gpu.evaluate(theta)
+    assert st == ro["status"] == 1 and np.isinf(fval) and np.isinf(ro["fval"])
+    res = gpu.condition_results()
+    assert np.array_equal(res["status"], ro["cond_status"])
+    assert np.all(res["status"] == SIM_ERROR)
+    assert np.all(res["stats"][:, 12] == 2)  # both trials used
+
+
+def test_relaxed_tolerance_retry_repeats_the_pre_equilibration(oracle_available):
+    """maxsteps between what the first and the relaxed trial need: trial 1 fails in the equilibration, trial 2
+    (tolerances x 100, pre-equilibration included) succeeds -- same trial count and result as the reference."""
+    tab = _problem("steadystate", 4, True, 0)
+    gpu, ora = _both(tab)
+    theta = synth.random_theta(tab, seed=1, width=0.3)
+    tab2 = _problem("steadystate", 4, True, 0)
+    tab2.maxsteps = 450
+    gpu2, ora2 = _both(tab2)
+    ro = ora2.evaluate(theta, collect_stats=True)
+    st, fval, grad, _ = gpu2.evaluate(theta)
+    res = gpu2.condition_results()
+    assert np.array_equal(res["status"], ro["cond_status"])
+    assert np.array_equal(res["stats"][:, 12], ro["stats"][:, 12]), (res["stats"][:, 12], ro["stats"][:, 12])
+    assert np.any(res["stats"][:, 12] > 1)
+    if ro["status"] == 0:
+        assert st == 0
+        assert abs(fval - ro["fval"]) <= 1e-3 * abs(ro["fval"])  # (relaxed tolerances: 1e-6 / 1e-10)
+
+
+def test_switching_pre_equilibration_off_restores_the_plain_problem():
+    from parpe_b200.problem import B200SummedGradientFunction
+    tab = synth.make_problem("boehm", 6, seed=4, preeq=True)
+    plain = synth.make_problem("boehm", 6, seed=4)
+    theta = synth.random_theta(tab, seed=1, width=0.3)
+    f = B200SummedGradientFunction(tab)
+    st, with_pre, g_pre, _ = f.evaluate(theta)
+    assert st == 0
+    capi.check(capi.lib().pb200_set_preequilibration(f._h, None, None, None, None), "off")
+    st, off, g_off, _ = f.evaluate(theta)
+    st, ref, g_ref, _ = B200SummedGradientFunction(plain).evaluate(theta)
+    assert off == ref and np.array_equal(g_off, g_ref)
+    assert with_pre != ref
+
+
+def test_large_model_kernel_refuses_steady_states():
+    from parpe_b200.problem import B200SummedGradientFunction
+    tab = synth.make_problem("net32", 2, seed=0)
+    f = B200SummedGradientFunction(tab)
+    flag = np.ones(2, dtype=np.int32)
+    rc = capi.lib().pb200_set_preequilibration(f._h, flag.ctypes.data_as(C.POINTER(C.c_int32)), capi.dptr(tab.k),
+                                               None, None)
+    assert rc == -1 and "not supported" in capi.last_error()
+
+
+def test_bad_reinitialisation_index_is_an_error():
+    from parpe_b200.problem import B200SummedGradientFunction
+    tab = synth.make_problem("boehm", 2, seed=0, preeq=True)
+    tab.reinit_idx = [[0], [8]]  # nx = 8
+    with pytest.raises(capi.B200LibraryError, match="index out of range"):
+        B200SummedGradientFunction(tab)

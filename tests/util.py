@@ -42,3 +42,16 @@ def condition_inputs(tab, theta, c):
     fac = np.array([p[i] * np.log(10) if tab.pscale_sim[c, i] == SCALE_LOG10 else
                     (p[i] if tab.pscale_sim[c, i] == SCALE_LN else 1.0) for i in plist])
     return p, plist, fac
+
+
+def assert_outputs_close(y, yref, tab, what="model outputs"):
+    """Model outputs in the layout of the measurement table: rows of finite output times to 1e-6 relative; rows at
+    t = inf (post-equilibration) to 2e-5 -- the reference's stopping rule (wrms(xdot) < 1 at the steady-state
+    tolerances rtol 1e-6 / atol 1e-10) determines the steady state to about that tolerance only, and the step at
+    which it fires depends on the step sequence (the reference's own KLU / dense variants differ likewise)."""
+    y = np.asarray(y, dtype=float).reshape(-1, tab.ny)
+    yref = np.asarray(yref, dtype=float).reshape(-1, tab.ny)
+    inf_rows = np.isinf(tab.t)
+    np.testing.assert_allclose(y[~inf_rows], yref[~inf_rows], rtol=1e-6, atol=1e-9, err_msg=what)
+    if np.any(inf_rows):
+        np.testing.assert_allclose(y[inf_rows], yref[inf_rows], rtol=2e-5, atol=1e-9, err_msg=what + " (t = inf)")

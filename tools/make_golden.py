@@ -37,7 +37,20 @@ CASES = {
     # linear-solver setups per solve), two conditions each -- what bench.py integrates
     "chen_full": ("chen", 2, dict(scale="log10", seed=19)),
     "froehlich_full": ("froehlich", 2, dict(scale="log10", seed=20)),
+    # steady states: output times t = inf (post-equilibration) and pre-equilibration with
+    # re-initialisation of states, deps/AMICI/src/steadystateproblem.cpp
+    "steadystate_posteq": ("steadystate", 4, dict(scale="lin", seed=21, sigma_mode="data", posteq=2,
+                                                  timepoints=[0.001, 0.01, 0.1, 1.0, 10.0, 100.0, 1000.0])),
+    "steadystate_scaled_preeq": ("steadystate_scaled", 6, dict(scale="mixed", seed=22, sigma_mode="mixed",
+                                                               missing_fraction=0.2, ragged=True, preeq=True,
+                                                               condition_specific=2)),
+    "boehm_preeq_posteq": ("boehm", 5, dict(scale="log10", seed=23, preeq=True, posteq=1,
+                                            timepoints=[0.0, 2.5, 5.0, 10.0, 20.0, 40.0, 80.0])),
 }
+
+
+def kw_has_inf(kw):
+    return bool(kw.get("posteq"))
 
 
 def build_case(name):
@@ -63,7 +76,9 @@ def main():
             case=name, model=CASES[name][0], n_conditions=CASES[name][1], kwargs=CASES[name][2],
             theta=theta.tolist(), nllh=r["fval"], grad=r["grad"].tolist(), llh=r["llh"].tolist(),
             sllh=r["sllh"].tolist(), subset=sub, subset_nllh=rs["fval"], subset_grad=rs["grad"].tolist(),
-            nst=r["stats"][:, 0].tolist(),
+            # (with t = inf points the reference reports 0 steps at the last output time: no comparable count)
+            nst=None if kw_has_inf(CASES[name][2]) else r["stats"][:, 0].tolist(),
+            preeq_steps=r["stats"][:, 14].tolist(), posteq_steps=r["stats"][:, 15].tolist(),
             y=np.where(np.isnan(y), None, y).tolist(), sigmay=np.where(np.isnan(s), None, s).tolist())
         with open(os.path.join(outdir, name + ".json"), "w") as fh:
             json.dump(doc, fh, indent=1)
