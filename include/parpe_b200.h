@@ -333,8 +333,11 @@ int pb200_get_model_outputs(pb200_handle* h, const double* theta, int n_opt,
  * attributes, /{scaling,offset,sigma}Parameter{Indices,sMapToObservables}.
  * The file is parsed by a built-in reader of the HDF5 subset such files use
  * (old-style groups, contiguous / compact / chunked datasets, gzip + shuffle
- * filters; parpe_b200/csrc/h5min.h); no HDF5 library is needed.  Input files
- * with a pre-equilibration condition are refused.
+ * filters, variable-length integer sequences in global heap collections;
+ * parpe_b200/csrc/h5min.h); no HDF5 library is needed.  Pre-equilibration
+ * conditions (column 0 of /fixedParameters/simulationConditions) and
+ * /fixedParameters/reinitializationIndices are read (multiConditionDataProvider.cpp:224-250,
+ * 497-524) and applied by pb200_create_from_hdf5 through pb200_set_preequilibration.
  */
 typedef struct pb200_h5 pb200_h5;
 int pb200_h5_open(const char* path, pb200_h5** out);
@@ -344,6 +347,8 @@ int pb200_h5_exists(pb200_h5* f, const char* path);
 int pb200_h5_dataset_info(pb200_h5* f, const char* path, int* rank, int64_t* dims, int* type_class, int* type_size);
 /* whole dataset as doubles, row-major; returns the element count (out == NULL: count only) or < 0 */
 int64_t pb200_h5_read_double(pb200_h5* f, const char* path, double* out, int64_t capacity);
+/* the elements' bytes as stored (e.g. fixed-length strings); returns the byte count (out == NULL: count only) or < 0 */
+int64_t pb200_h5_read_raw(pb200_h5* f, const char* path, char* out, int64_t capacity);
 /* numeric attribute of a group / dataset as doubles; returns the element count or < 0 */
 int pb200_h5_attribute_double(pb200_h5* f, const char* object, const char* name, double* out, int capacity);
 /* newline-separated names of a group's children; returns their number or < 0 */
@@ -354,9 +359,54 @@ typedef struct pb200_h5_problem pb200_h5_problem;
 int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_problem** out);
 const pb200_problem_desc* pb200_h5_problem_desc(pb200_h5_problem* p);
 const struct pb200_hier_desc* pb200_h5_problem_hier(pb200_h5_problem* p); /* NULL: no hierarchical tables */
+/* the arguments of pb200_set_preequilibration as read from the file; returns 1 if any condition is
+ * pre-equilibrated (pointers into the object), else 0 */
+int pb200_h5_problem_preeq(pb200_h5_problem* p, const int32_t** has_preeq, const double** k_preeq,
+                           const int64_t** reinit_offsets, const int32_t** reinit_idx);
 void pb200_h5_problem_free(pb200_h5_problem* p);
-/* pb200_h5_load_problem + pb200_create (+ pb200_hier_attach when the file has the tables) */
+/* pb200_h5_load_problem + pb200_create (+ pb200_hier_attach / pb200_set_preequilibration when the file has the tables) */
 int pb200_create_from_hdf5(const char* path, const char* model_name, int device, pb200_handle** out);
+
+/* per-simulation result logging ----------------------------------------- */
+/*
+ * SURVEY 8(f) rank 4.  Replaces: logSimulation / saveSimulation
+ * (src/parpeamici/multiConditionProblem.cpp:254-325), which appends one record per simulation job to
+ * extendable datasets of the result file's group /multistarts/<n> (doc/hdf5.md:190-226):
+ *   jobId [int 1 x n], simulationLabel [string n] ("o<opt>i<iter>c<condition>"),
+ *   simulationLogLikelihood [1 x n], simulationLogLikelihoodGradient [np x n] (sllh in simulation
+ *   scale, plist-compacted, NaN padded -- or all NaN when no gradient was requested),
+ *   simulationParameters [np x n] (the condition's model parameters in simulation scale),
+ *   simulationWallTimeInSec [1 x n], simulationStatus [int 1 x n] (AMICI status),
+ * plus, beyond the reference's datasets, the tolerance-relaxation retry statistics:
+ *   simulationTrials [int 1 x n], simulationIntegratorStatistics [int64 14 x n] (PB200_STAT_NST ..
+ *   PB200_STAT_QSUM).
+ * The records are collected in host memory and written ONCE by pb200_result_log_write as a classic-format
+ * HDF5 file (parpe_b200/csrc/h5wmin.h; no HDF5 library needed; contiguous datasets of the same names,
+ * types and shapes instead of extendable chunked ones).  Conditions run side by side on the GPU, so
+ * simulationWallTimeInSec is the evaluation's device time shared equally among its simulations.
+ */
+typedef struct pb200_result_log pb200_result_log;
+int pb200_result_log_create(pb200_result_log** out);
+void pb200_result_log_destroy(pb200_result_log* log);
+/* the per-condition results of the handle's last pb200_evaluate, as records of `group`; returns their number */
+int pb200_result_log_append(pb200_result_log* log, pb200_handle* h, const char* group, int optimization_idx,
+                            int iteration_idx);
+/* the same from host arrays (sllh / parameters: [n*np] row-major per record; seconds, sllh, parameters, stats
+ * ([n*PB200_NSTATS]) may be NULL) */
+int pb200_result_log_append_records(pb200_result_log* log, const char* group, int n, int np,
+                                    const int32_t* condition_idx, int optimization_idx, int iteration_idx,
+                                    const double* llh, const double* sllh, const double* parameters,
+                                    const double* seconds, const int32_t* status, const int64_t* stats);
+int pb200_result_log_num_records(pb200_result_log* log, const char* group);
+int pb200_result_log_write(pb200_result_log* log, const char* path);
+/*
+ * Replaces: the result datasets of the standalone simulator (src/parpeamici/standaloneSimulator.cpp:57-270;
+ * doc/hdf5.md:228-252): simulates all conditions at `theta` and writes <group>/llh [C], <group>/parameters
+ * [n_opt], <group>/t/<m> [nt], <group>/yMes/<m> [nt x ny], <group>/ySim/<m> [nt x ny].  Returns the
+ * evaluation status (PB200_EVAL_*) or a negative error.
+ */
+int pb200_write_simulation_results(pb200_handle* h, const double* theta, int n_opt, const char* path,
+                                   const char* group);
 
 /* hierarchical optimisation -------------------------------------------- */
 /*

@@ -63,6 +63,19 @@ class NetworkModel : public amici::Model_ODE {
         pb200::net::x0(T_, tm, k, x0);
     }
     void fsx0(realtype*, const realtype, const realtype*, const realtype*, const realtype*, const int) override {}
+    // re-initialisation after pre-equilibration, in the layout of the python-generated models
+    // (deps/AMICI/python/sdist/amici/de_export.py:688-749): the listed states whose initial value depends on a
+    // constant take that value again, their sensitivities sx0 = 0
+    void fx0_fixedParameters(realtype* x0, const realtype, const realtype*, const realtype* k,
+                             gsl::span<const int> reinitialization_state_idxs) override {
+        for (int i : reinitialization_state_idxs)
+            if (T_.x0_kidx[i] >= 0) x0[i] = T_.x0_base[i] * k[T_.x0_kidx[i]];
+    }
+    void fsx0_fixedParameters(realtype* sx0, const realtype, const realtype*, const realtype*, const realtype*,
+                              const int, gsl::span<const int> reinitialization_state_idxs) override {
+        for (int i : reinitialization_state_idxs)
+            if (T_.x0_kidx[i] >= 0) sx0[i] = 0.0;
+    }
     void fy(double* y, const realtype, const realtype* x, const realtype*, const realtype*, const realtype*,
             const realtype*) override {
         for (int j = 0; j < T_.ny; ++j) y[j] = pb200::net::observable(T_, j, x);

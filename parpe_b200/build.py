@@ -8,6 +8,7 @@ from __future__ import annotations
 import concurrent.futures
 import glob
 import os
+import re
 import subprocess
 import sys
 
@@ -23,13 +24,27 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v
 
 
 def _sources():
-    return [os.path.join(CSRC, "parpe_b200.cu"), os.path.join(CSRC, "microbench.cu"), os.path.join(CSRC, "h5input.cu")] + sorted(glob.glob(os.path.join(CSRC, "models", "inst_*.cu")))
+    return [os.path.join(CSRC, "parpe_b200.cu"), os.path.join(CSRC, "microbench.cu"), os.path.join(CSRC, "h5input.cu"),
+            os.path.join(CSRC, "team_kernel_plain.cu"), os.path.join(CSRC, "team_kernel_steady.cu")] + sorted(glob.glob(os.path.join(CSRC, "models", "inst_*.cu")))
 
 
-def _deps():
-    return (glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) +
-            glob.glob(os.path.join(CSRC, "models", "*.cuh")) +
-            [os.path.join(HERE, "..", "include", "parpe_b200.h")])
+_INCLUDE = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+
+
+def _deps(src, seen=None):
+    """The files `src` includes, transitively (quoted includes, resolved relative to the including file): an
+    object is rebuilt only when one of ITS headers changed -- the large-model kernels take minutes to compile."""
+    seen = set() if seen is None else seen
+    try:
+        text = open(src).read()
+    except OSError:
+        return seen
+    for inc in _INCLUDE.findall(text):
+        path = os.path.normpath(os.path.join(os.path.dirname(src), inc))
+        if path not in seen and os.path.exists(path):
+            seen.add(path)
+            _deps(path, seen)
+    return seen
 
 
 def _compile(src, obj, log):
@@ -45,11 +60,11 @@ def _compile(src, obj, log):
 def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     srcs = _sources()
-    newest_dep = max(os.path.getmtime(p) for p in _deps())
     jobs = []
     for s in srcs:
         o = os.path.join(OBJ, os.path.basename(s)[:-3] + ".o")
-        stale = force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), newest_dep)
+        newest = max([os.path.getmtime(s)] + [os.path.getmtime(p) for p in _deps(s)])
+        stale = force or not os.path.exists(o) or os.path.getmtime(o) < newest
         jobs.append((s, o, stale))
     todo = [(s, o) for s, o, st in jobs if st]
     if todo:

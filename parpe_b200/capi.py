@@ -21,8 +21,11 @@ EXPORTED_SYMBOLS = [
     "pb200_get_model_outputs", "pb200_measure_fp64_peak", "pb200_set_allreduce", "pb200_hier_attach", "pb200_hier_num_outer", "pb200_hier_evaluate",
     "pb200_set_option", "pb200_nccl_unique_id", "pb200_nccl_init", "pb200_last_transfer_bytes", "pb200_linsol_info",
     "pb200_h5_open", "pb200_h5_close", "pb200_h5_exists", "pb200_h5_dataset_info", "pb200_h5_read_double",
-    "pb200_h5_attribute_double", "pb200_h5_list", "pb200_h5_load_problem", "pb200_h5_problem_desc",
+    "pb200_h5_attribute_double", "pb200_h5_list", "pb200_h5_read_raw", "pb200_h5_load_problem", "pb200_h5_problem_desc",
     "pb200_h5_problem_hier", "pb200_h5_problem_free", "pb200_create_from_hdf5", "pb200_set_preequilibration",
+    "pb200_h5_problem_preeq", "pb200_result_log_create", "pb200_result_log_destroy", "pb200_result_log_append",
+    "pb200_result_log_append_records", "pb200_result_log_num_records", "pb200_result_log_write",
+    "pb200_write_simulation_results",
 ]
 # pb200_set_option keys (include/parpe_b200.h)
 OPT_REORDER, OPT_ORDER_REFRESH, OPT_KERNEL_VARIANT, OPT_CTAS_PER_SM, OPT_SYNC_PERIOD, OPT_STAGE_SYNC = 1, 2, 3, 4, 5, 6
@@ -84,6 +87,8 @@ def lib():
     L.pb200_h5_dataset_info.argtypes = [C.c_void_p, C.c_char_p, ip, C.POINTER(C.c_int64), ip, ip]
     L.pb200_h5_read_double.argtypes = [C.c_void_p, C.c_char_p, dp, C.c_int64]
     L.pb200_h5_read_double.restype = C.c_int64
+    L.pb200_h5_read_raw.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int64]
+    L.pb200_h5_read_raw.restype = C.c_int64
     L.pb200_h5_attribute_double.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, dp, C.c_int]
     L.pb200_h5_list.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
     L.pb200_h5_load_problem.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
@@ -91,6 +96,18 @@ def lib():
     L.pb200_h5_problem_desc.restype = C.POINTER(ProblemDesc)
     L.pb200_h5_problem_hier.argtypes = [C.c_void_p]
     L.pb200_h5_problem_hier.restype = C.POINTER(HierDesc)
+    L.pb200_h5_problem_preeq.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(dp),
+                                         C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_int32))]
+    i32p = C.POINTER(C.c_int32)
+    L.pb200_result_log_create.argtypes = [C.POINTER(C.c_void_p)]
+    L.pb200_result_log_destroy.argtypes = [C.c_void_p]
+    L.pb200_result_log_destroy.restype = None
+    L.pb200_result_log_append.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+    L.pb200_result_log_append_records.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, i32p, C.c_int, C.c_int, dp, dp,
+                                                  dp, dp, i32p, C.POINTER(C.c_int64)]
+    L.pb200_result_log_num_records.argtypes = [C.c_void_p, C.c_char_p]
+    L.pb200_result_log_write.argtypes = [C.c_void_p, C.c_char_p]
+    L.pb200_write_simulation_results.argtypes = [C.c_void_p, dp, C.c_int, C.c_char_p, C.c_char_p]
     L.pb200_h5_problem_free.argtypes = [C.c_void_p]
     L.pb200_h5_problem_free.restype = None
     L.pb200_create_from_hdf5.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
@@ -145,6 +162,54 @@ def iptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
 
 
+class ResultLog:
+    """Per-simulation result logging (pb200_result_log_*): what parPE's logSimulation writes per simulation job
+    (multiConditionProblem.cpp:254-325; doc/hdf5.md:190-226), collected in memory and written once."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        check(lib().pb200_result_log_create(C.byref(self._h)), "pb200_result_log_create")
+
+    def append(self, fun, group="/multistarts/0", optimization_idx=0, iteration_idx=0):
+        """the per-condition results of ``fun``'s last evaluate (a B200SummedGradientFunction)"""
+        return check(lib().pb200_result_log_append(self._h, fun._h, group.encode(), optimization_idx, iteration_idx),
+                     "pb200_result_log_append")
+
+    def append_records(self, group, condition_idx, llh, status, sllh=None, parameters=None, seconds=None, stats=None,
+                       optimization_idx=0, iteration_idx=0, np_=0):
+        cidx = np.ascontiguousarray(condition_idx, dtype=np.int32)
+        llh = np.ascontiguousarray(llh, dtype=np.float64)
+        status = np.ascontiguousarray(status, dtype=np.int32)
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        sllh, parameters, seconds = f(sllh), f(parameters), f(seconds)
+        if stats is not None:
+            stats = np.ascontiguousarray(stats, dtype=np.int64)
+        if sllh is not None:
+            np_ = sllh.reshape(len(llh), -1).shape[1]
+        i32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        return check(lib().pb200_result_log_append_records(
+            self._h, group.encode(), len(llh), np_, i32(cidx), optimization_idx, iteration_idx, dptr(llh), dptr(sllh),
+            dptr(parameters), dptr(seconds), i32(status),
+            stats.ctypes.data_as(C.POINTER(C.c_int64)) if stats is not None else None), "pb200_result_log_append_records")
+
+    def num_records(self, group="/multistarts/0"):
+        return lib().pb200_result_log_num_records(self._h, group.encode())
+
+    def write(self, path):
+        check(lib().pb200_result_log_write(self._h, str(path).encode()), "pb200_result_log_write")
+
+    def close(self):
+        if self._h:
+            lib().pb200_result_log_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class H5File:
     """parPE input files through the library's built-in HDF5 reader (pb200_h5_*; no HDF5 library needed)."""
 
@@ -172,6 +237,15 @@ class H5File:
         check(lib().pb200_h5_dataset_info(self._h, path.encode(), C.byref(rank), dims, C.byref(cls), C.byref(size)),
               "pb200_h5_dataset_info")
         return dict(shape=tuple(int(dims[i]) for i in range(rank.value)), type_class=cls.value, type_size=size.value)
+
+    def read_strings(self, path):
+        """fixed-length string dataset -> list of str"""
+        info = self.info(path)
+        n = int(np.prod(info["shape"])) if info["shape"] else 1
+        buf = C.create_string_buffer(n * info["type_size"] + 1)
+        check(lib().pb200_h5_read_raw(self._h, path.encode(), buf, len(buf)), "pb200_h5_read_raw")
+        sz = info["type_size"]
+        return [buf.raw[i * sz:(i + 1) * sz].split(b"\0")[0].decode() for i in range(n)]
 
     def read(self, path):
         n = check(lib().pb200_h5_read_double(self._h, path.encode(), None, 0), "pb200_h5_read_double")

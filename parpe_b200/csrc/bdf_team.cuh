@@ -175,7 +175,9 @@ struct TeamWork {
     }
 };
 
-template <class Team>
+/// SS: with support for steady states -- output times t = inf (post-equilibration) and a pre-equilibration
+/// phase (preequilibrate() + simulate(..., keep_state)); the SS = false instantiation is the code without any of it.
+template <class Team, bool SS = false>
 struct BdfTeam {
     NetTables T;
     SparseLU SP{};   // symbolic factorisation (enabled = 0: dense path only)
@@ -2638,9 +2640,14 @@ struct BdfTeam {
     }
 
     /// Prologue of CVode(tout) in CV_NORMAL mode with tstop = tout, as AMICI drives it
-    PB_HD int cvode_begin(double tout) {
-        tstop = tout;
-        tstopset = true;
+    PB_HD int cvode_begin(double tout, bool onestep = false) {
+        // Solver::run sets tstop = tout; Solver::step (CV_ONE_STEP, simulation to steady state:
+        // deps/AMICI/src/solver.cpp:161-175) sets none
+        const bool one = SS && onestep;
+        if (!one) {
+            tstop = tout;
+            tstopset = true;
+        }
         if (opt.maxsteps <= nst) return SIM_ERROR;
         mxstep_ = opt.maxsteps - nst;
         nstloc_ = 0;
@@ -2649,16 +2656,16 @@ struct BdfTeam {
             h = 1.0;
             const int r = reload_zn1();
             if (r) return r == cv::RHSFUNC_RECVR ? SIM_FIRST_RHSFUNC_ERR : SIM_FIRST_SRHSFUNC_ERR;
-            if ((tstop - tn) * (tout - tn) <= 0.0) return SIM_ILL_INPUT;
+            if (!one && (tstop - tn) * (tout - tn) <= 0.0) return SIM_ILL_INPUT;
             const int hr = hin(tout);
             if (hr != 0) return hr;
-            if ((tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
+            if (!one && (tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * cv::UROUND);
             hscale = h;
             hprime = h;
             tm.sync();
             PT_FOR_ELEMS(e) w.zn(1)[e] *= h;
             tm.sync();
-        } else {
+        } else if (!one) {
             const double troundoff = cv::FUZZ_FACTOR * cv::UROUND * (fabs(tn) + fabs(h));
             if (fabs(tn - tstop) <= troundoff) {
                 tstopset = false;
@@ -2670,6 +2677,103 @@ struct BdfTeam {
             }
         }
         return 0;
+    }
+
+    // ---------------------------------------------------------------- steady states (SS only)
+    /// Convergence test of a simulation to steady state (SteadystateProblem::getWrms / getWrmsFSA,
+    /// deps/AMICI/src/steadystateproblem.cpp:519-626): wrms(xdot(x)) < 1 with weights 1 / (rtol |x| + atol) and,
+    /// with sensitivities, wrms(J sx_c + dxdotdp_c) < 1 with 1 / (rtol |sx_c| + atol) for the columns in
+    /// order, stopping at the first above the threshold; x / sx = zn[0] (the solver's state at tn); the
+    /// tolerances are 100 x the integration tolerances (AMICI's steady-state defaults, solver.h:1908-1923).
+    /// Scratch: yj, ysh, vb, v, fout, Jcur, dfdp -- all rewritten by the next step attempt.
+    PB_HD bool ss_converged() {
+        const double rtol = 100.0 * opt.rtol, atol = 100.0 * opt.atol;
+        const double* __restrict__ z0 = w.zn(0);
+        tm.sync();
+        PT_FOR(i, 0, nx) {
+            w.yj[i] = z0[i];
+            w.ysh[i] = z0[i];
+        }
+        eval_xdot();
+        nfe--;  // (Model::fxdot called by the steady-state problem itself: not one of CVODES' evaluations)
+        tm.sync();
+        double s = 0.0;
+        PT_FOR(i, 0, nx) {
+            const double v = w.fout[i] * (1.0 / (rtol * fabs(z0[i]) + atol));
+            s += v * v;
+        }
+        s = tm.sum(s);
+        if (!(sqrt(s / (double)nx) < 1.0)) return false;
+        if (!sensi) return true;
+        refresh_Jcur();
+        const double* __restrict__ jc = w.Jcur;
+        const int* __restrict__ jcol = T.jell_col;
+        const int jw = T.jell_w;
+        bool above = false, last_ok = true;
+        for (int c = 1 + tm.warp(); c <= ns; c += tm.nwarps()) {  // one warp per column, lanes over the rows
+            const double* __restrict__ sx = z0 + (size_t)c * nx;
+            const double* __restrict__ dcol = w.dfdp + (size_t)w.plist[c - 1] * nx;
+            double sc = 0.0;
+            for (int i = tm.lane(); i < nx; i += Team::WARP) {
+                double F = dcol[i];
+                for (int t = 0; t < jw; ++t) {
+                    const int j = jcol[t * nx + i];
+                    if (j >= 0) F += jc[t * nx + i] * sx[j];
+                }
+                const double v = F * (1.0 / (rtol * fabs(sx[i]) + atol));
+                sc += v * v;
+            }
+            sc = tm.warp_sum(sc);
+            const double wr = sqrt(sc / (double)nx);
+            if (wr > 1.0) above = true;
+            if (c == ns && !(wr < 1.0)) last_ok = false;
+        }
+        return !tm.any(above || !last_ok);
+    }
+
+    /// One internal step: the body of the CVode loop (cvodes.c:3366-3605) in CV_ONE_STEP mode; the step is
+    /// completed alone (the convergence test needs the corrected history).  Returns 0 or a failure status.
+    PB_HD int ss_step() {
+        if (nst > 0 && !ewt_set()) return SIM_ILL_INPUT;
+        if (nstloc_ >= mxstep_) return SIM_TOO_MUCH_WORK;
+        const double nrm = wnorm1(0, errtest_cmax(), w.zn(0));
+        if (cv::UROUND * nrm > 1.0) return SIM_TOO_MUCH_ACC;
+        step_begin();
+        for (;;) {
+            int a = attempt_predict();
+            if (a < 0) return a;
+            attempt_correct(PH_STATE);
+            attempt_correct(PH_SENS);
+            a = attempt_finish();
+            if (a < 0) return a;
+            if (a == 0) break;
+        }
+        nstloc_++;
+        if (pending_complete_) {
+            const long long t_h0 = now();
+            complete_elements();
+            cyc_hist += now() - t_h0;
+        }
+        return 0;
+    }
+
+    /// SteadystateProblem::runSteadystateSimulation (steadystateproblem.cpp:711-794): test, then one step
+    /// towards max(t, 1) * 10, until converged.  Any failure ends as AMICI_ERROR (:198-255, 397-425).
+    /// Out of line: ONE copy of the step machinery beside the main loop's, shared by pre- and post-equilibration.
+    PT_NOINLINE int to_steady_state() {
+        for (;;) {
+            if (ss_converged()) return SIM_SUCCESS;
+            if (nst >= opt.maxsteps) return SIM_ERROR;
+            if (cvode_begin(fmax(tn, 1.0) * 10.0, true) < 0) return SIM_ERROR;
+            if (ss_step() < 0) return SIM_ERROR;
+        }
+    }
+
+    /// Pre-equilibration (amici.cpp:95-108; workSteadyStateProblem with it = -1): w.k holds the constants of
+    /// the PRE-EQUILIBRATION condition; from x0 / sx0 to steady state, which stays in zn[0].
+    PB_HD int preequilibrate(const ConditionIO& io, double rtol, double atol) {
+        begin(io, rtol, atol);
+        return finish(to_steady_state());
     }
 
     // ---------------------------------------------------------------- likelihood
@@ -2715,7 +2819,13 @@ struct BdfTeam {
 
     // ---------------------------------------------------------------- one simulation
     /// w.p / w.k / w.plist must be set (and synchronised) by the caller
-    PB_HD void begin(const ConditionIO& io, double rtol, double atol) {
+    ///
+    /// keep_state (SS only; after preequilibrate(), w.k now the simulation condition's constants): the main
+    /// simulation starts from the state and sensitivities in zn[0] (ForwardProblem, forwardproblem.cpp:59-63);
+    /// the states of the list reinit[0..n_reinit) whose initial value depends on the constants are reset to it,
+    /// their sensitivities to sx0 = 0 (Model::reinitialize, model.cpp:277-291,1849-1923).
+    PB_HD void begin(const ConditionIO& io, double rtol, double atol, bool keep_state = false,
+                     const int* reinit = nullptr, int n_reinit = 0) {
         io_ = io;
         opt.rtol = rtol;
         opt.atol = atol;
@@ -2724,8 +2834,18 @@ struct BdfTeam {
         ncol = ns + 1;
         sensi = ns > 0;
         tm.sync();
-        net::x0(T, tm, w.k, w.zn(0));
-        PT_FOR(e, nx, nx * ncol) w.zn(0)[e] = 0.0;  // sx0 = 0: initial values do not depend on p
+        if (SS && keep_state) {
+            for (int e = tm.tid(); e < n_reinit; e += tm.size()) {
+                const int i = reinit[e];
+                const int ki = T.x0_kidx[i];
+                if (ki < 0) continue;
+                w.zn(0)[i] = T.x0_base[i] * w.k[ki];
+                for (int c = 1; c < ncol; ++c) w.zn(0)[(size_t)c * nx + i] = 0.0;
+            }
+        } else {
+            net::x0(T, tm, w.k, w.zn(0));
+            PT_FOR(e, nx, nx * ncol) w.zn(0)[e] = 0.0;  // sx0 = 0: initial values do not depend on p
+        }
         PT_FOR_ELEMS(e) {
             for (int j = 1; j < cv::L_MAX; ++j) w.zn(j)[e] = 0.0;
             w.acor[e] = 0.0;
@@ -2765,12 +2885,29 @@ struct BdfTeam {
     }
 
     /// ForwardProblem::workForwardProblem: output times in order, CVode(tout) with tstop = tout
-    PB_HD int simulate(const ConditionIO& io, double rtol, double atol) {
-        begin(io, rtol, atol);
+    PB_HD int simulate(const ConditionIO& io, double rtol, double atol, bool keep_state = false,
+                       const int* reinit = nullptr, int n_reinit = 0) {
+        begin(io, rtol, atol, keep_state, reinit, n_reinit);
         const int ny = T.ny;
         for (it_ = 0; it_ < io_.nt; ++it_) {
             tout_ = io_.t[it_];
-            if (!PB_FINITE(tout_)) return finish(SIM_ERROR);  // t = inf (post-equilibration) is not implemented: an error, never a silently dropped point
+            if (!PB_FINITE(tout_)) {
+                // t = inf: post-equilibration (amici.cpp:109-114; ForwardProblem stops at the first infinite output
+                // time, forwardproblem.cpp:149-150).  Without steady-state support an error, never a silently
+                // dropped point.
+                if (!SS) return finish(SIM_ERROR);
+                if (to_steady_state() != SIM_SUCCESS) return finish(SIM_ERROR);
+                // ReturnData::processPostEquilibration (rdata.cpp:234-258): every t = inf point at the steady state
+                for (; it_ < io_.nt; ++it_) {
+                    double* yo = io_.y_out ? io_.y_out + (size_t)it_ * ny : nullptr;
+                    double* so = io_.sigmay_out ? io_.sigmay_out + (size_t)it_ * ny : nullptr;
+#if defined(PB200_HOST_TRACE)
+                    if (io_.trace) { io_.trace[2 * it_] = nst; io_.trace[2 * it_ + 1] = q; }
+#endif
+                    if (!data_point(io_.my + (size_t)it_ * ny, io_.sd + (size_t)it_ * ny, yo, so)) return finish(SIM_ERROR);
+                }
+                return finish(SIM_SUCCESS);
+            }
             bool integrate = (tout_ > opt.t0) && (tn < tout_);
             if (integrate) {  // is_next_t_too_close
                 const double tdiff = tout_ - tn;

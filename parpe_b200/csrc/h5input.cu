@@ -35,6 +35,11 @@ struct pb200_h5_problem {
     std::vector<double> t, y, sigma, k, overrides;
     std::vector<int32_t> mapping, pscale_sim, pscale_opt;
     std::vector<int32_t> scaling_idx, offset_idx, sigma_idx, scaling_map, offset_map, sigma_map;
+    // pre-equilibration (simulationConditions column 0, reinitializationIndices)
+    std::vector<int32_t> has_preeq, reinit_idx;
+    std::vector<double> k_preeq;
+    std::vector<int64_t> reinit_off;
+    bool any_preeq = false;
     pb200_problem_desc desc{};
     pb200_hier_desc hier{};
     bool has_hier = false;
@@ -104,6 +109,21 @@ int64_t pb200_h5_read_double(pb200_h5* h, const char* path, double* out, int64_t
     return rc < 0 ? rc : n;
 }
 
+int64_t pb200_h5_read_raw(pb200_h5* h, const char* path, char* out, int64_t capacity) {
+    if (!h || !path) return pb200::fail_message(PB200_ERR_ARG, "null argument");
+    int64_t n = 0;
+    const int rc = guarded([&] {
+        const std::vector<uint8_t> v = h->f->read_bytes(path);
+        n = (int64_t)v.size();
+        if (out) {
+            if (capacity < n) throw H5Error(std::string(path) + ": output buffer too small");
+            std::memcpy(out, v.data(), v.size());
+        }
+        return 0;
+    });
+    return rc < 0 ? rc : n;
+}
+
 int pb200_h5_attribute_double(pb200_h5* h, const char* obj, const char* name, double* out, int capacity) {
     if (!h || !obj || !name) return pb200::fail_message(PB200_ERR_ARG, "null argument");
     int n = 0;
@@ -161,14 +181,37 @@ int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_pro
             K = f.read_double("/fixedParameters/k");
         }
         P->k.resize((size_t)C * nk);
+        P->has_preeq.assign(C, 0);
+        P->k_preeq.assign((size_t)C * nk, 0.0);
+        P->reinit_off.assign(C + 1, 0);
+        // ragged list of the states re-initialised after pre-equilibration (getReinitializationIndices,
+        // multiConditionDataProvider.cpp:497-524): a 1-D dataset of variable-length int sequences, one per simulation
+        std::vector<std::vector<int64_t>> reinit;
+        if (f.exists("/fixedParameters/reinitializationIndices")) {
+            reinit = f.read_vlen_int("/fixedParameters/reinitializationIndices");
+            if ((int)reinit.size() != C) throw H5Error("/fixedParameters/reinitializationIndices must have one entry per simulation condition");
+        }
         for (int c = 0; c < C; ++c) {
-            if (sc[2 * c] >= 0)
-                throw H5Error("simulation condition " + std::to_string(c) + " has a pre-equilibration condition: not supported "
-                              "(SURVEY 8(f) rank 2)");
             const int64_t col = sc[2 * c + 1];
             if (col < 0 || (nk > 0 && (uint64_t)col >= nvec)) throw H5Error("simulationConditions refers to a missing column of k");
             for (int i = 0; i < nk; ++i) P->k[(size_t)c * nk + i] = K[(size_t)i * nvec + col];
+            // column 0: the pre-equilibration condition, -1 = none (updateFixedSimulationParameters,
+            // multiConditionDataProvider.cpp:224-250)
+            const int64_t pre = sc[2 * c];
+            if (pre >= 0) {
+                if (nk > 0 && (uint64_t)pre >= nvec) throw H5Error("simulationConditions refers to a missing column of k (pre-equilibration)");
+                P->has_preeq[c] = 1;
+                P->any_preeq = true;
+                for (int i = 0; i < nk; ++i) P->k_preeq[(size_t)c * nk + i] = K[(size_t)i * nvec + pre];
+                if (!reinit.empty())
+                    for (int64_t v : reinit[c]) {
+                        if (v < 0 || v >= nx) throw H5Error("reinitializationIndices: state index out of range");
+                        P->reinit_idx.push_back((int32_t)v);
+                    }
+            }
+            P->reinit_off[c + 1] = (int64_t)P->reinit_idx.size();
         }
+        if (P->reinit_idx.empty()) P->reinit_idx.push_back(0);
         // ---- /measurements/{t,y,ysigma}/<c>
         P->t_offsets.assign(1, 0);
         for (int c = 0; c < C; ++c) {
@@ -228,6 +271,15 @@ int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_pro
         d.rtol = opt("rtol", 1e-8);
         d.maxsteps = (int32_t)opt("maxsteps", 10000);
         d.stldet = (int32_t)opt("stldet", 1);
+        // Steady states are found by simulation (AMICI's default newton_maxsteps = 0); a file that asks
+        // for Newton's method first would be simulated differently by the reference: refused, not ignored
+        {
+            bool steady = P->any_preeq;
+            for (double tv : P->t) steady = steady || std::isinf(tv);
+            if (steady && opt("newton_maxsteps", 0.0) > 0.0)
+                throw H5Error("/amiciOptions newton_maxsteps > 0 with pre-/post-equilibration: Newton's method for steady "
+                              "states is not supported (only steady state by simulation, newton_maxsteps = 0)");
+        }
         d.sensi_errcon = 1;
         d.num_trials = 6;
         d.relaxation_factor = 100.0;
@@ -265,6 +317,15 @@ int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_pro
 }
 
 const pb200_problem_desc* pb200_h5_problem_desc(pb200_h5_problem* p) { return p ? &p->desc : nullptr; }
+int pb200_h5_problem_preeq(pb200_h5_problem* p, const int32_t** has_preeq, const double** k_preeq,
+                           const int64_t** reinit_offsets, const int32_t** reinit_idx) {
+    if (!p || !p->any_preeq) return 0;
+    if (has_preeq) *has_preeq = p->has_preeq.data();
+    if (k_preeq) *k_preeq = p->k_preeq.data();
+    if (reinit_offsets) *reinit_offsets = p->reinit_off.data();
+    if (reinit_idx) *reinit_idx = p->reinit_idx.data();
+    return 1;
+}
 const pb200_hier_desc* pb200_h5_problem_hier(pb200_h5_problem* p) { return (p && p->has_hier) ? &p->hier : nullptr; }
 void pb200_h5_problem_free(pb200_h5_problem* p) { delete p; }
 
@@ -275,12 +336,12 @@ int pb200_create_from_hdf5(const char* path, const char* model_name, int device,
     int rc = pb200_h5_load_problem(path, model_name, &P);
     if (rc != 0) return rc;
     rc = pb200_create(&P->desc, device, out);
-    if (rc == 0 && P->has_hier) {
-        rc = pb200_hier_attach(*out, &P->hier);
-        if (rc != 0) {
-            pb200_destroy(*out);
-            *out = nullptr;
-        }
+    if (rc == 0 && P->has_hier) rc = pb200_hier_attach(*out, &P->hier);
+    if (rc == 0 && P->any_preeq)
+        rc = pb200_set_preequilibration(*out, P->has_preeq.data(), P->k_preeq.data(), P->reinit_off.data(), P->reinit_idx.data());
+    if (rc != 0 && *out) {
+        pb200_destroy(*out);
+        *out = nullptr;
     }
     pb200_h5_problem_free(P);  // (the tables were copied to the device)
     return rc;

@@ -43,9 +43,12 @@ class H5File {
     struct Dataset {
         int rank = 0;
         std::vector<uint64_t> dims;
-        int type_class = -1;  // 0 fixed point, 1 floating point, 3 string (fixed length)
+        int type_class = -1;  // 0 fixed point, 1 floating point, 3 string (fixed length), 9 variable-length sequence
         int type_size = 0;
         bool type_signed = true;
+        // variable-length sequences (class 9): the element type (integers only)
+        int base_class = -1, base_size = 0;
+        bool base_signed = true;
         uint64_t count() const {
             uint64_t n = 1;
             for (auto d : dims) n *= d;
@@ -99,6 +102,14 @@ class H5File {
         convert(raw.data(), r.d, out.data(), out.size(), path);
         return out;
     }
+    /// the elements' bytes as stored (fixed-length strings, any fixed-size type)
+    std::vector<uint8_t> read_bytes(const std::string& path) const {
+        uint64_t a;
+        if (!locate(path, a)) throw H5Error("no such dataset: " + path);
+        DsRaw r = dataset_raw(a, path);
+        if (r.d.type_class == 9) throw H5Error(path + ": variable-length data has no raw form");
+        return read_raw(r, path);
+    }
     std::vector<int64_t> read_int(const std::string& path) const {
         uint64_t a;
         if (!locate(path, a)) throw H5Error("no such dataset: " + path);
@@ -107,6 +118,33 @@ class H5File {
         std::vector<uint8_t> raw = read_raw(r, path);
         std::vector<int64_t> out(r.d.count());
         for (size_t i = 0; i < out.size(); ++i) out[i] = get_int(raw.data() + i * r.d.type_size, r.d.type_size, r.d.type_signed);
+        return out;
+    }
+
+    /// ragged integer dataset: a 1-D dataset of variable-length integer sequences (h5py.vlen_dtype(int32), what
+    /// parPE writes for /fixedParameters/reinitializationIndices) -> one vector per element.  Each element is stored
+    /// as (length, global-heap collection address, object index); the sequences live in global heap collections.
+    std::vector<std::vector<int64_t>> read_vlen_int(const std::string& path) const {
+        uint64_t a;
+        if (!locate(path, a)) throw H5Error("no such dataset: " + path);
+        DsRaw r = dataset_raw(a, path);
+        if (r.d.type_class != 9 || r.d.base_class != 0) throw H5Error(path + ": not a dataset of variable-length integer sequences");
+        if (r.d.type_size != (int)(4 + so_ + 4)) throw H5Error(path + ": unexpected size of a variable-length element");
+        std::vector<uint8_t> raw = read_raw(r, path);
+        std::vector<std::vector<int64_t>> out(r.d.count());
+        for (size_t i = 0; i < out.size(); ++i) {
+            const uint8_t* p = raw.data() + i * r.d.type_size;
+            const uint64_t len = rd(p, 4);
+            const uint64_t coll = rd(p + 4, so_);
+            const uint64_t index = rd(p + 4 + so_, 4);
+            if (len == 0) continue;
+            if (coll == UNDEF || coll == 0) throw H5Error(path + ": variable-length element without heap object");
+            size_t nbytes = 0;
+            const uint8_t* data = global_heap_object(coll, index, nbytes, path);
+            if (nbytes < len * (uint64_t)r.d.base_size) throw H5Error(path + ": heap object shorter than the sequence");
+            out[i].resize(len);
+            for (uint64_t e = 0; e < len; ++e) out[i][e] = get_int(data + e * r.d.base_size, r.d.base_size, r.d.base_signed);
+        }
         return out;
     }
 
@@ -238,6 +276,28 @@ class H5File {
         return out;
     }
 
+    /// object `index` of the global heap collection at `addr` (GCOL: version 1; objects = index u16, reference count
+    /// u16, reserved u32, size, data padded to 8 bytes; object 0 is the free space)
+    const uint8_t* global_heap_object(uint64_t addr, uint64_t index, size_t& nbytes, const std::string& what) const {
+        const uint8_t* h = at(addr, 8 + sl_);
+        if (std::memcmp(h, "GCOL", 4) || h[4] != 1) throw H5Error(what + ": bad global heap collection");
+        const uint64_t total = rd(h + 8, sl_);
+        h = at(addr, total);
+        uint64_t off = 8 + sl_;
+        while (off + 8 + sl_ <= total) {
+            const uint64_t idx = rd(h + off, 2);
+            const uint64_t size = rd(h + off + 8, sl_);
+            if (idx == 0) break;  // free space: end of the objects
+            if (off + 8 + sl_ + size > total) throw H5Error(what + ": global heap object overruns its collection");
+            if (idx == index) {
+                nbytes = (size_t)size;
+                return h + off + 8 + sl_;
+            }
+            off += 8 + sl_ + ((size + 7) & ~(uint64_t)7);
+        }
+        throw H5Error(what + ": global heap object not found");
+    }
+
     std::string heap_string(uint64_t heap_addr, uint64_t off) const {
         const uint8_t* h = at(heap_addr, 8 + 2 * sl_ + so_);
         if (std::memcmp(h, "HEAP", 4)) throw H5Error("bad local heap signature");
@@ -345,6 +405,16 @@ class H5File {
             if (d.type_size != 4 && d.type_size != 8) throw H5Error(what + ": float size");
         } else if (d.type_class == 3) {
             // fixed-length string: readable as raw bytes only
+        } else if (d.type_class == 9) {
+            // variable-length: sequences of integers only (strings: bits 0-3 of the class bit field = 1)
+            if ((p[1] & 0x0f) != 0) throw H5Error(what + ": variable-length strings are not supported");
+            if (n < 16) throw H5Error(what + ": short variable-length datatype message");
+            Dataset base;
+            parse_datatype(p + 8, n - 8, base, what + " (element type)");
+            if (base.type_class != 0) throw H5Error(what + ": variable-length sequences of non-integer elements are not supported");
+            d.base_class = base.type_class;
+            d.base_size = base.type_size;
+            d.base_signed = base.type_signed;
         } else {
             throw H5Error(what + ": datatype class " + std::to_string(d.type_class) + " is not supported");
         }

@@ -43,7 +43,9 @@ struct KernelArgs {
     // steady states (pb200_set_preequilibration / t = inf output times): null / 0 without them
     const double* k_preeq;         // [C*nk] constants of the pre-equilibration condition
     const int* preeq_flag;         // [C] 1 = the condition is pre-equilibrated
-    const unsigned* reinit_mask;   // [C] states re-initialised after pre-equilibration (bit i = state i)
+    const unsigned* reinit_mask;   // [C] states re-initialised after pre-equilibration (bit i = state i; nx <= 32)
+    const int64_t* reinit_off;     // [C+1] the same as a ragged list of state indices (large-model kernel)
+    const int* reinit_idx;
     int steady;                    // 1 = some condition has a pre-equilibration or a t = inf output time:
                                    //     the steady-state instantiation of the kernel is launched
     // --- per evaluation ---

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/parpe_b200.h"
+#include "h5wmin.h"
 #include "hier_kernels.cuh"
 #include "kernels.cuh"
 #include "nccl_dyn.h"
@@ -123,6 +124,10 @@ struct pb200_handle {
     int rank = 0, world = 1;
     std::vector<int> pscale_opt;
     std::vector<int64_t> t_offsets;
+    // host copies for the result log (simulation parameters per condition: A5 on the host)
+    std::vector<int> mapping_host, pscale_sim_host;
+    std::vector<double> overrides_host;
+    double last_seconds = 0.0;
     // resident tables
     DevBuf<int64_t> d_t_offsets;
     DevBuf<double> d_t, d_my, d_sd, d_k, d_ov_scaled, d_ov_unscaled;
@@ -168,6 +173,8 @@ struct pb200_handle {
     DevBuf<double> d_k_preeq;
     DevBuf<int> d_preeq_flag;
     DevBuf<unsigned> d_reinit_mask;
+    DevBuf<int64_t> d_reinit_off;
+    DevBuf<int> d_reinit_idx;
 };
 
 static int ensure_capacity(pb200_handle* h, int n) {
@@ -362,6 +369,9 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
     h->pscale_opt.assign(d->pscale_opt, d->pscale_opt + d->n_opt);
     h->t_offsets.assign(d->t_offsets, d->t_offsets + C + 1);
     h->nt_total = C > 0 ? d->t_offsets[C] : 0;
+    h->mapping_host.assign(d->mapping, d->mapping + (size_t)C * d->np);
+    h->pscale_sim_host.assign(d->pscale_sim, d->pscale_sim + (size_t)C * d->np);
+    if (d->overrides) h->overrides_host.assign(d->overrides, d->overrides + (size_t)C * d->np);
 
     // A5 getSensitivityParameterList (multiConditionDataProvider.cpp:323-339), once per condition
     std::vector<int> plist((size_t)C * d->np, 0), nplist(C, 0);
@@ -440,6 +450,8 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
     a.k_preeq = nullptr;
     a.preeq_flag = nullptr;
     a.reinit_mask = nullptr;
+    a.reinit_off = nullptr;
+    a.reinit_idx = nullptr;
     a.steady = has_inf ? 1 : 0;
     a.opt.t0 = d->t0;
     a.opt.rtol = d->rtol;
@@ -485,6 +497,8 @@ int pb200_set_preequilibration(pb200_handle* h, const int32_t* has_preeq, const 
         a.k_preeq = nullptr;
         a.preeq_flag = nullptr;
         a.reinit_mask = nullptr;
+        a.reinit_off = nullptr;
+        a.reinit_idx = nullptr;
         a.steady = h->has_inf ? 1 : 0;
         return 0;
     }
@@ -492,26 +506,35 @@ int pb200_set_preequilibration(pb200_handle* h, const int32_t* has_preeq, const 
     if (!k_preeq && h->nk > 0) return fail(PB200_ERR_ARG, "k_preeq is null");
     std::vector<int> flag(h->C);
     std::vector<unsigned> mask(h->C, 0u);
+    std::vector<int64_t> roff(h->C + 1, 0);
+    std::vector<int> ridx;
     bool any = false;
     for (int c = 0; c < h->C; ++c) {
         flag[c] = has_preeq[c] != 0;
         any = any || flag[c];
+        roff[c + 1] = roff[c];
         if (!reinit_offsets) continue;
         if (reinit_offsets[c + 1] < reinit_offsets[c]) return fail(PB200_ERR_ARG, "reinit_offsets not monotone");
         for (int64_t e = reinit_offsets[c]; e < reinit_offsets[c + 1]; ++e) {
             const int i = reinit_idx[e];
             if (i < 0 || i >= h->ops->nx) return fail(PB200_ERR_ARG, "re-initialisation state index out of range");
-            if (i >= 32) return fail(PB200_ERR_ARG, "re-initialisation of state indices >= 32 is not supported");
-            mask[c] |= 1u << i;
+            if (i < 32) mask[c] |= 1u << i;  // (the small-model kernels -- nx <= 32 -- take the list as a bit mask)
+            ridx.push_back(i);
         }
+        roff[c + 1] = (int64_t)ridx.size();
     }
+    if (ridx.empty()) ridx.push_back(0);
     PB_CUDA(h->d_k_preeq.upload(k_preeq, (size_t)h->C * h->nk));
     PB_CUDA(h->d_preeq_flag.upload(flag.data(), flag.size()));
     PB_CUDA(h->d_reinit_mask.upload(mask.data(), mask.size()));
+    PB_CUDA(h->d_reinit_off.upload(roff.data(), roff.size()));
+    PB_CUDA(h->d_reinit_idx.upload(ridx.data(), ridx.size()));
     h->has_preeq = any;
     a.k_preeq = h->d_k_preeq.p;
     a.preeq_flag = h->d_preeq_flag.p;
     a.reinit_mask = h->d_reinit_mask.p;
+    a.reinit_off = h->d_reinit_off.p;
+    a.reinit_idx = h->d_reinit_idx.p;
     a.steady = (h->has_inf || any) ? 1 : 0;
     return 0;
 }
@@ -618,10 +641,11 @@ int pb200_evaluate(pb200_handle* h, const double* theta, int n_opt, const int* i
     PB_CUDA(cudaMemcpyAsync(h->h_out.p, h->d_out.p, sizeof(double) * (2 + h->n_opt), cudaMemcpyDeviceToHost, h->stream));
     PB_CUDA(cudaStreamSynchronize(h->stream));
     h->last_d2h += (int64_t)sizeof(double) * (2 + h->n_opt);
-    if (seconds) {
+    {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop);
-        *seconds = ms * 1e-3;
+        h->last_seconds = ms * 1e-3;
+        if (seconds) *seconds = h->last_seconds;
     }
     if (h->world > 1 && !h->nccl && h->allreduce)  // host transport; NCCL has reduced d_out on the stream already
         h->allreduce(h->allreduce_user, h->h_out.p, 2 + h->n_opt, PB200_REDUCE_SUM);
@@ -737,6 +761,178 @@ int pb200_get_model_outputs(pb200_handle* h, const double* theta, int n_opt, dou
     if (sigmay_out) PB_CUDA(cudaMemcpyAsync(sigmay_out, h->d_sout.p, sizeof(double) * ny_total, cudaMemcpyDeviceToHost, h->stream));
     PB_CUDA(cudaStreamSynchronize(h->stream));
     return h->h_out.p[1] == 0.0 ? PB200_EVAL_SUCCESS : PB200_EVAL_FAILURE;
+}
+
+// ---- per-simulation result logging ---------------------------------
+// Replaces: logSimulation / saveSimulation (multiConditionProblem.cpp:254-325) and the standalone simulator's
+// result datasets (standaloneSimulator.cpp:57-270; doc/hdf5.md:175-252).  Records are collected in host memory
+// and written once, as a classic-format HDF5 file (h5wmin.h).
+}  // extern "C"
+
+struct pb200_result_log {
+    struct Group {
+        int np = 0;
+        std::vector<int32_t> job_id, status, trials;
+        std::vector<std::string> label;
+        std::vector<double> llh, seconds;
+        std::vector<double> sllh, params;   // [record][np]
+        std::vector<int64_t> stats;         // [record][14]
+    };
+    std::vector<std::pair<std::string, Group>> groups;  // in order of first use
+    int next_job = 0;
+    Group& get(const std::string& name, int np) {
+        for (auto& g : groups)
+            if (g.first == name) return g.second;
+        groups.emplace_back(name, Group());
+        groups.back().second.np = np;
+        return groups.back().second;
+    }
+};
+
+extern "C" {
+
+int pb200_result_log_create(pb200_result_log** out) {
+    if (!out) return fail(PB200_ERR_ARG, "null argument");
+    *out = new pb200_result_log;
+    return 0;
+}
+void pb200_result_log_destroy(pb200_result_log* log) { delete log; }
+
+int pb200_result_log_append_records(pb200_result_log* log, const char* group, int n, int np, const int32_t* condition_idx,
+                                    int optimization_idx, int iteration_idx, const double* llh, const double* sllh,
+                                    const double* parameters, const double* seconds, const int32_t* status,
+                                    const int64_t* stats) {
+    if (!log || !group || n < 0 || np < 0 || (n > 0 && (!condition_idx || !llh || !status)))
+        return fail(PB200_ERR_ARG, "null argument");
+    pb200_result_log::Group& g = log->get(group, np);
+    if (g.np != np) return fail(PB200_ERR_ARG, "result log: records of one group must have the same number of model parameters");
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (int r = 0; r < n; ++r) {
+        g.job_id.push_back(log->next_job++);
+        // simulation label: optimisation index 'o', iteration index 'i', condition index 'c' (doc/hdf5.md:208-210)
+        g.label.push_back("o" + std::to_string(optimization_idx) + "i" + std::to_string(iteration_idx) + "c" +
+                          std::to_string(condition_idx[r]));
+        g.llh.push_back(llh[r]);
+        g.status.push_back(status[r]);
+        g.seconds.push_back(seconds ? seconds[r] : nan);
+        for (int i = 0; i < np; ++i) {
+            g.sllh.push_back(sllh ? sllh[(size_t)r * np + i] : nan);
+            g.params.push_back(parameters ? parameters[(size_t)r * np + i] : nan);
+        }
+        g.trials.push_back(stats ? (int32_t)stats[(size_t)r * PB200_NSTATS + PB200_STAT_TRIALS] : 0);
+        for (int k = 0; k < 14; ++k) g.stats.push_back(stats ? stats[(size_t)r * PB200_NSTATS + k] : 0);
+    }
+    return n;
+}
+
+int pb200_result_log_append(pb200_result_log* log, pb200_handle* h, const char* group, int optimization_idx,
+                            int iteration_idx) {
+    if (!log || !h || !group) return fail(PB200_ERR_ARG, "null argument");
+    const int n = h->last_n, np = h->np;
+    std::vector<double> llh(n), sllh((size_t)n * np), params((size_t)n * np), seconds(n);
+    std::vector<int> status(n);
+    std::vector<int64_t> stats((size_t)n * NSTATS);
+    const int rc = pb200_get_condition_results(h, llh.data(), sllh.data(), status.data(), stats.data());
+    if (rc < 0) return rc;
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    std::vector<int32_t> cidx(n);
+    for (int r = 0; r < n; ++r) {
+        const int c = h->idx_cache[r];
+        cidx[r] = c;
+        // the condition's model parameters in simulation scale (mapAndSetOptimizationToSimulationVariables,
+        // multiConditionDataProvider.cpp:126-169) from the parameter table of the last evaluation
+        int k = 0;
+        for (int i = 0; i < np; ++i) {
+            const int j = h->mapping_host[(size_t)c * np + i];
+            double v = nan;
+            if (j >= 0) v = h->h_theta_tab.p[((size_t)j * 3 + h->pscale_sim_host[(size_t)c * np + i]) * 2 + 0];
+            else if (!h->overrides_host.empty()) v = h->overrides_host[(size_t)c * np + i];
+            params[(size_t)r * np + i] = v;
+            if (j >= 0) ++k;
+        }
+        // sllh is plist-compacted: entries beyond nplist are padding -> NaN, as saveSimulation pads
+        for (int i = (h->last_want_grad ? k : 0); i < np; ++i) sllh[(size_t)r * np + i] = nan;
+        // conditions run side by side on the GPU: the evaluation's device time shared equally
+        seconds[r] = n > 0 ? h->last_seconds / n : 0.0;
+    }
+    return pb200_result_log_append_records(log, group, n, np, cidx.data(), optimization_idx, iteration_idx, llh.data(),
+                                           sllh.data(), params.data(), seconds.data(), status.data(), stats.data());
+}
+
+int pb200_result_log_num_records(pb200_result_log* log, const char* group) {
+    if (!log || !group) return fail(PB200_ERR_ARG, "null argument");
+    for (auto& g : log->groups)
+        if (g.first == group) return (int)g.second.llh.size();
+    return 0;
+}
+
+int pb200_result_log_write(pb200_result_log* log, const char* path) {
+    if (!log || !path) return fail(PB200_ERR_ARG, "null argument");
+    try {
+        H5Writer w;
+        for (auto& kv : log->groups) {
+            const std::string& gp = kv.first;
+            const pb200_result_log::Group& g = kv.second;
+            const uint64_t n = g.llh.size(), np = (uint64_t)g.np;
+            // one COLUMN per simulation, as hdf5CreateOrExtendAndWriteTo*2DArray lays the records out
+            auto transpose = [&](const std::vector<double>& v) {
+                std::vector<double> t(v.size());
+                for (uint64_t r = 0; r < n; ++r)
+                    for (uint64_t i = 0; i < np; ++i) t[i * n + r] = v[r * np + i];
+                return t;
+            };
+            w.doubles(gp + "/simulationLogLikelihood", g.llh, {1, n});
+            w.ints(gp + "/jobId", g.job_id, {1, n});
+            w.doubles(gp + "/simulationLogLikelihoodGradient", transpose(g.sllh), {np, n});
+            w.doubles(gp + "/simulationParameters", transpose(g.params), {np, n});
+            w.doubles(gp + "/simulationWallTimeInSec", g.seconds, {1, n});
+            w.ints(gp + "/simulationStatus", g.status, {1, n});
+            w.strings(gp + "/simulationLabel", g.label);
+            // beyond the reference's datasets: the tolerance-relaxation retry count and CVODES' counters
+            w.ints(gp + "/simulationTrials", g.trials, {1, n});
+            std::vector<int64_t> st(g.stats.size());
+            for (uint64_t r = 0; r < n; ++r)
+                for (uint64_t k = 0; k < 14; ++k) st[k * n + r] = g.stats[r * 14 + k];
+            w.int64s(gp + "/simulationIntegratorStatistics", st, {14, n});
+        }
+        w.save(path);
+    } catch (std::exception const& e) {
+        return fail(PB200_ERR_ARG, e.what());
+    }
+    return 0;
+}
+
+int pb200_write_simulation_results(pb200_handle* h, const double* theta, int n_opt, const char* path, const char* group) {
+    if (!h || !theta || !path || !group) return fail(PB200_ERR_ARG, "null argument");
+    if (n_opt != h->n_opt) return fail(PB200_ERR_ARG, "parameter vector size does not match numParameters");
+    if (h->world > 1) return fail(PB200_ERR_ARG, "simulation result files are written from an unpartitioned handle");
+    const size_t ny_total = (size_t)h->nt_total * h->ny;
+    std::vector<double> y(ny_total > 0 ? ny_total : 1), s(ny_total > 0 ? ny_total : 1), t(h->nt_total > 0 ? h->nt_total : 1),
+        my(ny_total > 0 ? ny_total : 1), llh(h->C > 0 ? h->C : 1);
+    const int rc = pb200_get_model_outputs(h, theta, n_opt, y.data(), s.data());
+    if (rc < 0) return rc;
+    if (pb200_get_condition_results(h, llh.data(), nullptr, nullptr, nullptr) < 0) return PB200_ERR_CUDA;
+    PB_CUDA(cudaMemcpy(t.data(), h->d_t.p, sizeof(double) * h->nt_total, cudaMemcpyDeviceToHost));
+    PB_CUDA(cudaMemcpy(my.data(), h->d_my.p, sizeof(double) * ny_total, cudaMemcpyDeviceToHost));
+    try {
+        H5Writer w;
+        const std::string g = group;
+        llh.resize(h->C);
+        w.doubles(g + "/llh", llh, {(uint64_t)h->C});
+        w.doubles(g + "/parameters", std::vector<double>(theta, theta + n_opt), {(uint64_t)n_opt});
+        for (int c = 0; c < h->C; ++c) {
+            const int64_t lo = h->t_offsets[c], hi = h->t_offsets[c + 1];
+            const uint64_t nt = (uint64_t)(hi - lo), ny = (uint64_t)h->ny;
+            const std::string id = std::to_string(c);
+            w.doubles(g + "/t/" + id, std::vector<double>(t.begin() + lo, t.begin() + hi), {nt});
+            w.doubles(g + "/yMes/" + id, std::vector<double>(my.begin() + lo * h->ny, my.begin() + hi * h->ny), {nt, ny});
+            w.doubles(g + "/ySim/" + id, std::vector<double>(y.begin() + lo * h->ny, y.begin() + hi * h->ny), {nt, ny});
+        }
+        w.save(path);
+    } catch (std::exception const& e) {
+        return fail(PB200_ERR_ARG, e.what());
+    }
+    return rc;
 }
 
 // ---- hierarchical optimisation (A15) -----------------------------------------------

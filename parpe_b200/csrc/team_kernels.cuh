@@ -18,14 +18,16 @@ namespace pb200 {
 
 constexpr int TEAM_THREADS = 512;
 
-template <int TEAM_THREADS_>
+/// SS = true: the instantiation with steady-state support (pre-equilibration, t = inf output times), launched
+/// only for problems that have either (KernelArgs::steady); SS = false is the code without any of it.
+template <int TEAM_THREADS_, bool SS = false>
 __global__ void __launch_bounds__(TEAM_THREADS_, 1)
 simulate_team_kernel(const KernelArgs a, const NetTables T, const SparseLU SP, double* __restrict__ workspace,
                      size_t ws_stride, int smem_doubles, int sp_tab_off, int use_sparse) {
     extern __shared__ __align__(16) double pb_team_smem[];
     __shared__ int s_pos;
     CtaTeam tm;
-    BdfTeam<CtaTeam> bdf(tm);
+    BdfTeam<CtaTeam, SS> bdf(tm);
     bdf.T = T;
     bdf.SP = SP;
     bdf.use_sparse = use_sparse != 0;
@@ -99,7 +101,27 @@ simulate_team_kernel(const KernelArgs a, const NetTables T, const SparseLU SP, d
         int trial = 1, status;
         double relax = 1.0;
         for (;;) {
-            status = bdf.simulate(io, a.opt.rtol * relax, a.opt.atol * relax);
+            // pre-equilibration with the pre-equilibration condition's constants (ConditionContext,
+            // deps/AMICI/src/edata.cpp:511-524), then the main simulation from the steady state with the
+            // simulation condition's; a retry repeats both (multiConditionProblem.cpp:369-465)
+            const bool pre = SS && a.preeq_flag && a.preeq_flag[c] != 0;
+            const int* reinit = nullptr;
+            int nre = 0;
+            status = SIM_SUCCESS;
+            if (pre) {
+                __syncthreads();
+                for (int i = tid; i < T.nk; i += TEAM_THREADS) bdf.w.k[i] = a.k_preeq[(size_t)c * T.nk + i];
+                __syncthreads();
+                status = bdf.preequilibrate(io, a.opt.rtol * relax, a.opt.atol * relax);
+                __syncthreads();
+                for (int i = tid; i < T.nk; i += TEAM_THREADS) bdf.w.k[i] = a.k[(size_t)c * T.nk + i];
+                __syncthreads();
+                if (a.reinit_off) {
+                    reinit = a.reinit_idx + a.reinit_off[c];
+                    nre = (int)(a.reinit_off[c + 1] - a.reinit_off[c]);
+                }
+            }
+            if (status == SIM_SUCCESS) status = bdf.simulate(io, a.opt.rtol * relax, a.opt.atol * relax, pre, reinit, nre);
             if (status == SIM_SUCCESS || trial >= a.num_trials) break;
             relax *= a.relaxation_factor;
             ++trial;
@@ -238,6 +260,21 @@ inline void* team_create_state(const NetTables& H, int sm_count, std::string* er
     return st;
 }
 
+int team_launch_kernel_plain(const KernelArgs& a, const TeamState& st, int grid, int use_sparse, cudaStream_t stream);
+int team_launch_kernel_steady(const KernelArgs& a, const TeamState& st, int grid, int use_sparse, cudaStream_t stream);
+
+/// body of the two functions above (SS = false / true)
+template <bool SS>
+int team_launch_kernel(const KernelArgs& a, const TeamState& st, int grid, int use_sparse, cudaStream_t stream) {
+    auto kern = simulate_team_kernel<TEAM_THREADS, SS>;
+    // (the attribute is per device and per function: set at every launch, to this model's size)
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st.smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, TEAM_THREADS, st.smem, stream>>>(a, st.dev, st.sp, st.workspace, st.ws_stride,
+                                                  (int)(st.smem / sizeof(double)), st.sp_tab_off, use_sparse);
+    return (int)cudaGetLastError();
+}
+
 inline int team_launch(const KernelArgs& a, void* state, cudaStream_t stream, int* lanes_used, int* grid_used,
                        int* block_used) {
     auto* st = static_cast<TeamState*>(state);
@@ -245,18 +282,16 @@ inline int team_launch(const KernelArgs& a, void* state, cudaStream_t stream, in
     int grid = st->grid_cap;  // persistent: one team per SM, work queue inside
     if (grid > a.n) grid = a.n;
     if (grid < 1) grid = 1;
-    // (the attribute is per device and per function: set at every launch, to this model's size)
-    cudaError_t e = cudaFuncSetAttribute(simulate_team_kernel<TEAM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)st->smem);
-    if (e != cudaSuccess) return (int)e;
     const int use_sparse = a.linsol == 2 ? 1 : (a.linsol == 1 ? 0 : (st->sparse_default ? 1 : 0));
-    simulate_team_kernel<TEAM_THREADS><<<grid, TEAM_THREADS, st->smem, stream>>>(a, st->dev, st->sp, st->workspace, st->ws_stride,
-                                                                                (int)(st->smem / sizeof(double)), st->sp_tab_off,
-                                                                                use_sparse);
+    // the kernel is generic over the network tables: it is instantiated ONCE per variant, in its own translation
+    // unit (team_kernel_plain.cu / team_kernel_steady.cu), not once per model
+    const int e = a.steady ? team_launch_kernel_steady(a, *st, grid, use_sparse, stream)
+                           : team_launch_kernel_plain(a, *st, grid, use_sparse, stream);
+    if (e != 0) return e;
     if (lanes_used) *lanes_used = TEAM_THREADS;
     if (grid_used) *grid_used = grid;
     if (block_used) *block_used = TEAM_THREADS;
-    return (int)cudaGetLastError();
+    return 0;
 }
 
 /// description of the linear solver for reports (pb200_linsol_info): see parpe_b200/problem.py for the names
@@ -295,6 +330,7 @@ inline int team_linsol_info(void* state, int64_t* v, int n) {
             o.create_state = &create_##NAME;                                                                  \
             o.destroy_state = &pb200::team_destroy_state;                                                     \
             o.linsol_info = &pb200::team_linsol_info;                                                         \
+            o.supports_steady = 1;                                                                            \
             pb200::register_model(o);                                                                         \
         }                                                                                                     \
     } reg_net_instance_##NAME;                                                                                \

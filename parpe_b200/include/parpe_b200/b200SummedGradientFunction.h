@@ -40,6 +40,10 @@ struct B200ProblemTables {
     std::vector<int32_t> pscaleOpt;           // [n_opt]
     std::vector<double> overrides;            // [C*np] or empty
     std::vector<std::string> parameterIds;    // /parameters/parameterNames
+    // pre-equilibration (simulationConditions column 0, reinitializationIndices); hasPreeq empty = none
+    std::vector<int32_t> hasPreeq;                        // [C]
+    std::vector<double> kPreeq;                           // [C*nk]
+    std::vector<std::vector<int>> reinitializationIndices; // [C] ragged
     double t0 = 0.0, atol = 1e-16, rtol = 1e-8;
     int maxSteps = 10000;
     bool stabilityLimitDetection = true;
@@ -81,6 +85,14 @@ class B200SummedGradientFunction : public SummedGradientFunction<int> {
         pb200_problem_desc d = tables_.desc();
         if (pb200_create(&d, device, &handle_) != 0)
             throw std::runtime_error(std::string("pb200_create: ") + pb200_last_error());
+        if (!tables_.hasPreeq.empty()) {
+            try {
+                setPreequilibration(tables_.hasPreeq, tables_.kPreeq, tables_.reinitializationIndices);
+            } catch (...) {
+                pb200_destroy(handle_);
+                throw;
+            }
+        }
     }
     ~B200SummedGradientFunction() override { pb200_destroy(handle_); }
     B200SummedGradientFunction(const B200SummedGradientFunction&) = delete;
@@ -150,6 +162,24 @@ class B200SummedGradientFunction : public SummedGradientFunction<int> {
     /// LoadBalancerMaster/Worker distribute over MPI ranks in the reference).  evaluate() still returns
     /// the GLOBAL fval / gradient / status on every rank -- as the reference master does after summing
     /// all workers' results -- and therefore needs a collective: initNccl() or setAllreduce().
+    /// Pre-equilibration (include/parpe_b200.h: pb200_set_preequilibration) -- what
+    /// MultiConditionDataProviderHDF5::updateFixedSimulationParameters puts into
+    /// ExpData::fixedParametersPreequilibration / reinitialization_state_idxs_sim
+    /// (src/parpeamici/multiConditionDataProvider.cpp:224-250): per simulation condition a flag, the constants of
+    /// the pre-equilibration condition (row-major [C x nk]) and the list of states re-initialised afterwards.
+    void setPreequilibration(std::vector<int32_t> const& hasPreeq, std::vector<double> const& kPreeq,
+                             std::vector<std::vector<int>> const& reinitializationIndices = {}) {
+        std::vector<int64_t> off(hasPreeq.size() + 1, 0);
+        std::vector<int32_t> idx;
+        for (size_t c = 0; c < hasPreeq.size(); ++c) {
+            if (c < reinitializationIndices.size())
+                idx.insert(idx.end(), reinitializationIndices[c].begin(), reinitializationIndices[c].end());
+            off[c + 1] = static_cast<int64_t>(idx.size());
+        }
+        if (idx.empty()) idx.push_back(0);
+        if (pb200_set_preequilibration(handle_, hasPreeq.data(), kPreeq.data(), off.data(), idx.data()) != 0)
+            throw std::runtime_error(std::string("pb200_set_preequilibration: ") + pb200_last_error());
+    }
     void setPartition(int rank, int world) {
         if (pb200_set_partition(handle_, rank, world) != 0)
             throw std::runtime_error(std::string("pb200_set_partition: ") + pb200_last_error());
@@ -298,6 +328,15 @@ inline B200ProblemTables B200ProblemTables::fromHdf5(std::string const& path, st
     T.t0 = d.t0; T.atol = d.atol; T.rtol = d.rtol;
     T.maxSteps = d.maxsteps;
     T.stabilityLimitDetection = d.stldet != 0;
+    {
+        const int32_t* flag = nullptr; const double* kp = nullptr; const int64_t* off = nullptr; const int32_t* idx = nullptr;
+        if (pb200_h5_problem_preeq(P, &flag, &kp, &off, &idx)) {
+            T.hasPreeq.assign(flag, flag + C);
+            T.kPreeq.assign(kp, kp + C * d.nk);
+            T.reinitializationIndices.resize(C);
+            for (size_t c = 0; c < C; ++c) T.reinitializationIndices[c].assign(idx + off[c], idx + off[c + 1]);
+        }
+    }
     if (hierarchical) {
         *hierarchical = B200HierarchicalTables();
         if (const pb200_hier_desc* h = pb200_h5_problem_hier(P)) {

@@ -230,6 +230,14 @@ def tables_from_hdf5(path, model_name: str) -> ProblemTables:
                 scaling_map=arr(h.scaling_map, 3 * h.n_scaling_rows, np.int32),
                 offset_map=arr(h.offset_map, 3 * h.n_offset_rows, np.int32),
                 sigma_map=arr(h.sigma_map, 3 * h.n_sigma_rows, np.int32))
+        flag, kp = C.POINTER(C.c_int32)(), C.POINTER(C.c_double)()
+        roff, ridx = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)()
+        if L.pb200_h5_problem_preeq(P, C.byref(flag), C.byref(kp), C.byref(roff), C.byref(ridx)):
+            tab.has_preeq = arr(flag, Cn, np.int32)
+            tab.k_preeq = arr(kp, Cn * nk, np.float64).reshape(Cn, nk)
+            off = arr(roff, Cn + 1, np.int64)
+            flat = arr(ridx, max(int(off[-1]), 1), np.int32)
+            tab.reinit_idx = [flat[off[c]:off[c + 1]].tolist() for c in range(Cn)]
         return tab
     finally:
         L.pb200_h5_problem_free(P)

@@ -107,6 +107,7 @@ def lib_team():
         L.hs_team_simulate.argtypes = [C.c_char_p, dp, dp, ip, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double,
                                        C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int64),
                                        dp, dp, ip, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.hs_team_simulate_ss.argtypes = L.hs_team_simulate.argtypes + [dp, ip, C.c_int]
         L.hs_team_solve.argtypes = [C.c_char_p, dp, C.c_double, dp, C.c_int, C.c_int, dp, C.c_int, C.c_int, C.c_int, ip]
         _lib_team = L
     return _lib_team
@@ -114,7 +115,9 @@ def lib_team():
 
 def simulate_team(model, p_unscaled, k, plist, t, my, sd, t0=0.0, rtol=1e-8, atol=1e-12, maxsteps=10000, stldet=1,
                   errconS=1, want_outputs=False, panel_width=0, sparse=False, deg_max=0, stage_doubles=0,
-                  fuse_history=True, fuse_newton=True):
+                  fuse_history=True, fuse_newton=True, steady=False, k_preeq=None, reinit_idx=()):
+    """``steady``: the steady-state instantiation of the core (t = inf output times; with ``k_preeq`` a
+    pre-equilibration followed by the re-initialisation of the states ``reinit_idx``)."""
     d = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     p_unscaled, k, t, my, sd = d(p_unscaled), d(k), d(t), d(my).reshape(-1), d(sd).reshape(-1)
     plist = np.ascontiguousarray(plist, dtype=np.int32)
@@ -126,11 +129,17 @@ def simulate_team(model, p_unscaled, k, plist, t, my, sd, t0=0.0, rtol=1e-8, ato
     s = np.zeros(my.size) if want_outputs else None
     trace = np.zeros(2 * len(t), dtype=np.int32)
     P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
-    st = lib_team().hs_team_simulate(model.encode(), P(p_unscaled), P(k), plist.ctypes.data_as(C.POINTER(C.c_int)), ns,
-                                     len(t), P(t), P(my), P(sd), t0, rtol, atol, maxsteps, stldet, errconS, panel_width,
-                                     C.byref(llh), P(sllh), stats.ctypes.data_as(C.POINTER(C.c_int64)), P(y), P(s),
-                                     trace.ctypes.data_as(C.POINTER(C.c_int)), int(sparse), deg_max, stage_doubles,
-                                     int(fuse_history) + 2 * int(fuse_newton))
+    args = [model.encode(), P(p_unscaled), P(k), plist.ctypes.data_as(C.POINTER(C.c_int)), ns,
+            len(t), P(t), P(my), P(sd), t0, rtol, atol, maxsteps, stldet, errconS, panel_width,
+            C.byref(llh), P(sllh), stats.ctypes.data_as(C.POINTER(C.c_int64)), P(y), P(s),
+            trace.ctypes.data_as(C.POINTER(C.c_int)), int(sparse), deg_max, stage_doubles,
+            int(fuse_history) + 2 * int(fuse_newton)]
+    if steady or k_preeq is not None:
+        kp = d(k_preeq) if k_preeq is not None else None
+        ri = np.ascontiguousarray(list(reinit_idx) or [0], dtype=np.int32)
+        st = lib_team().hs_team_simulate_ss(*args, P(kp), ri.ctypes.data_as(C.POINTER(C.c_int)), len(reinit_idx))
+    else:
+        st = lib_team().hs_team_simulate(*args)
     return dict(numsteps=trace[0::2], order=trace[1::2], status=st, llh=llh.value, sllh=sllh[:ns], stats=stats, y=y, sigmay=s)
 
 

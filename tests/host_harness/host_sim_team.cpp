@@ -35,11 +35,15 @@ static SparseLUHost symbolic_for(const NetTables& T, int deg_max) {
 
 /// sparse != 0: sparse LU + dense Schur block (deg_max: largest degree of a sparse pivot, <= 0 = default);
 /// stage_doubles: capacity of the staging area of the triangular solves (small values force column batches)
-extern "C" int hs_team_simulate(const char* model, const double* p_unscaled, const double* k, const int* plist, int ns,
-                                int nt, const double* t, const double* my, const double* sd, double t0, double rtol,
-                                double atol, int maxsteps, int stldet, int errconS, int panel_width, double* llh,
-                                double* sllh, int64_t* stats, double* y_out, double* sigmay_out, int* trace, int sparse,
-                                int deg_max, int stage_doubles, int fuse_history) {
+/// SS: the steady-state instantiation (t = inf output times; with k_preeq a pre-equilibration phase followed by
+/// the re-initialisation of the listed states) -- the sequence simulate_team_kernel<.., true> runs per condition
+template <bool SS>
+static int team_sim(const char* model, const double* p_unscaled, const double* k, const int* plist, int ns,
+                    int nt, const double* t, const double* my, const double* sd, double t0, double rtol,
+                    double atol, int maxsteps, int stldet, int errconS, int panel_width, double* llh,
+                    double* sllh, int64_t* stats, double* y_out, double* sigmay_out, int* trace, int sparse,
+                    int deg_max, int stage_doubles, int fuse_history, const double* k_preeq, const int* reinit,
+                    int n_reinit) {
     NetTables T;
     if (!tables_for(model, &T)) return -12345;
     SparseLUHost SH;
@@ -51,7 +55,7 @@ extern "C" int hs_team_simulate(const char* model, const double* p_unscaled, con
     if (stage_doubles <= 0) stage_doubles = 24064;
     std::vector<double> stage(stage_doubles > T.nx ? stage_doubles : T.nx);
     HostTeam tm;
-    BdfTeam<HostTeam> bdf(tm);
+    BdfTeam<HostTeam, SS> bdf(tm);
     bdf.T = T;
     if (sparse) bdf.SP = SH.view();
     bdf.use_sparse = sparse != 0;
@@ -74,11 +78,45 @@ extern "C" int hs_team_simulate(const char* model, const double* p_unscaled, con
     bdf.opt.stldet = stldet;
     bdf.opt.errconS = errconS;
     ConditionIO io{nt, t, my, sd, ns, y_out, sigmay_out, trace};
-    const int status = bdf.simulate(io, rtol, atol);
+    int status;
+    int64_t nst_preeq = 0;
+    if (SS && k_preeq) {
+        for (int i = 0; i < T.nk; ++i) bdf.w.k[i] = k_preeq[i];
+        status = bdf.preequilibrate(io, rtol, atol);
+        nst_preeq = bdf.nst;
+        if (status == SIM_SUCCESS) {
+            for (int i = 0; i < T.nk; ++i) bdf.w.k[i] = k[i];
+            status = bdf.simulate(io, rtol, atol, true, reinit, n_reinit);
+        }
+    } else {
+        status = bdf.simulate(io, rtol, atol);
+    }
     *llh = bdf.llh();
     for (int j = 0; j < ns; ++j) sllh[j] = bdf.w.sllh[j + 1];
     bdf.export_stats(stats, 1);
+    if (SS) stats[14] = nst_preeq;  // (the cycle counters are zero on the host)
     return status;
+}
+
+extern "C" int hs_team_simulate(const char* model, const double* p_unscaled, const double* k, const int* plist, int ns,
+                                int nt, const double* t, const double* my, const double* sd, double t0, double rtol,
+                                double atol, int maxsteps, int stldet, int errconS, int panel_width, double* llh,
+                                double* sllh, int64_t* stats, double* y_out, double* sigmay_out, int* trace, int sparse,
+                                int deg_max, int stage_doubles, int fuse_history) {
+    return team_sim<false>(model, p_unscaled, k, plist, ns, nt, t, my, sd, t0, rtol, atol, maxsteps, stldet, errconS,
+                           panel_width, llh, sllh, stats, y_out, sigmay_out, trace, sparse, deg_max, stage_doubles,
+                           fuse_history, nullptr, nullptr, 0);
+}
+
+extern "C" int hs_team_simulate_ss(const char* model, const double* p_unscaled, const double* k, const int* plist,
+                                   int ns, int nt, const double* t, const double* my, const double* sd, double t0,
+                                   double rtol, double atol, int maxsteps, int stldet, int errconS, int panel_width,
+                                   double* llh, double* sllh, int64_t* stats, double* y_out, double* sigmay_out,
+                                   int* trace, int sparse, int deg_max, int stage_doubles, int fuse_history,
+                                   const double* k_preeq, const int* reinit, int n_reinit) {
+    return team_sim<true>(model, p_unscaled, k, plist, ns, nt, t, my, sd, t0, rtol, atol, maxsteps, stldet, errconS,
+                          panel_width, llh, sllh, stats, y_out, sigmay_out, trace, sparse, deg_max, stage_doubles,
+                          fuse_history, k_preeq, reinit, n_reinit);
 }
 
 /// the blocked inversion + solve GEMM alone: x = A^-1 b for a dense column-major A given through

@@ -140,7 +140,7 @@ def test_nonfinite_or_decreasing_output_times_are_rejected():
         tab = synth.make_problem("boehm", 2, seed=0, timepoints=np.array(bad))
         with pytest.raises(capi.B200LibraryError, match="output time"):
             _gpu(tab)
-    tab = synth.make_problem("net32", 2, seed=0, timepoints=np.array([0.1, np.inf]))
+    tab = synth.make_problem("net32", 2, seed=0, timepoints=np.array([np.inf, 0.1]))
     with pytest.raises(capi.B200LibraryError, match="output time"):
         _gpu(tab)
 

@@ -101,14 +101,31 @@ def test_hierarchical_tables_and_preequilibration(tmp_path):
     assert got.hier is not None
     for name in ("scaling_idx", "offset_idx", "sigma_idx", "scaling_map", "offset_map", "sigma_map"):
         assert np.array_equal(getattr(got.hier, name), getattr(tab.hier, name)), name
-    # a pre-equilibration condition is refused, not ignored
-    w = h5write_min.H5Writer()
-    w.dataset("/fixedParameters/simulationConditions", np.array([[0, 0]], dtype=np.int32))
-    w.dataset("/fixedParameters/k", np.ones((tab.nk, 1)))
+    # pre-equilibration: column 0 of simulationConditions selects further columns of k, the ragged
+    # /fixedParameters/reinitializationIndices (variable-length int32 sequences in a global heap collection, as
+    # h5py.vlen_dtype writes them for parPE: python/parpe/hdf5_pe_input.py:430-437) the states to re-initialise.
+    # (No file with such a dataset written by the real HDF5 library exists in the reference tree: this part of
+    # the reader is pinned on the committed writer's rendering of the format specification only.)
+    ptab = synth.make_problem("boehm", 7, seed=2, preeq=True, posteq=1)
     p2 = tmp_path / "preeq.h5"
-    w.save(str(p2))
-    with pytest.raises(capi.B200LibraryError, match="pre-equilibration"):
-        tables_from_hdf5(p2, "steadystate_scaled")
+    h5write_min.write_parpe_input(str(p2), ptab)
+    f = capi.H5File(p2)
+    assert f.info("/fixedParameters/k")["shape"] == (ptab.nk, 7 + int(np.sum(ptab.has_preeq)))
+    assert f.info("/fixedParameters/reinitializationIndices")["type_class"] == 9
+    got = tables_from_hdf5(p2, "boehm")
+    assert np.array_equal(got.has_preeq, ptab.has_preeq)
+    assert np.array_equal(got.k, ptab.k) and np.array_equal(got.t, ptab.t) and np.isinf(got.t).sum() == 7
+    for c in range(7):
+        if ptab.has_preeq[c]:
+            assert np.array_equal(got.k_preeq[c], ptab.k_preeq[c])
+            assert got.reinit_idx[c] == list(ptab.reinit_idx[c])
+        else:
+            assert got.reinit_idx[c] == []
+    # Newton's method for steady states is not built: a file asking for it is refused, not simulated differently
+    p3 = tmp_path / "newton.h5"
+    h5write_min.write_parpe_input(str(p3), ptab, attrs=dict(newton_maxsteps=np.int32(40)))
+    with pytest.raises(capi.B200LibraryError, match="newton_maxsteps"):
+        tables_from_hdf5(p3, "boehm")
     with pytest.raises(capi.B200LibraryError):
         tables_from_hdf5(path, "no_such_model")
 
@@ -126,6 +143,16 @@ def test_handle_from_input_file_matches_handle_from_tables(tmp_path, oracle_avai
     b = B200SummedGradientFunction(tab).evaluate(theta)
     assert a[0] == b[0] == 0 and a[1] == b[1] and np.array_equal(a[2], b[2])
     ro = OracleProblem(tab).evaluate(theta)
+    assert_llh_close(a[1], ro["fval"])
+    assert_grad_close(a[2], ro["grad"])
+    # a file with pre-equilibration conditions and t = inf output times: the handle from the file applies them
+    ptab = synth.make_problem("boehm", 6, seed=5, preeq=True, posteq=1)
+    pp = tmp_path / "boehm_preeq.h5"
+    h5write_min.write_parpe_input(str(pp), ptab)
+    a = B200SummedGradientFunction.from_hdf5(pp, "boehm").evaluate(theta)
+    b = B200SummedGradientFunction(ptab).evaluate(theta)
+    assert a[0] == b[0] == 0 and a[1] == b[1] and np.array_equal(a[2], b[2])
+    ro = OracleProblem(ptab).evaluate(theta)
     assert_llh_close(a[1], ro["fval"])
     assert_grad_close(a[2], ro["grad"])
     # hierarchical tables ride along: pb200_create_from_hdf5 attaches them

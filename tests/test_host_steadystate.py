@@ -143,3 +143,105 @@ def test_without_steady_states_both_instantiations_agree_bit_for_bit():
         assert a["status"] == b["status"] == 0
         assert a["llh"] == b["llh"] and np.array_equal(a["sllh"], b["sllh"])
         assert np.array_equal(a["stats"][:14], b["stats"][:14])
+
+
+# ---------------------------------------------------------------- large-model core (bdf_team.cuh)
+TIGHT = dict(rtol=1e-11, atol=1e-15, maxsteps=100000)
+
+
+def _team_problem(preeq, posteq, tight):
+    from oracle.binding import OracleProblem
+
+    def sim(tab, theta):
+        rc, y, _ = OracleProblem(tab).get_model_outputs(theta)
+        assert rc == 0
+        return y
+    tp = np.asarray(synth.DEFAULT_TIMEPOINTS["net32"], dtype=float)[:3 + posteq]
+    kw = TIGHT if tight else {}
+    tab = synth.make_problem("net32", 3, seed=0, timepoints=tp, preeq=preeq, posteq=posteq, simulate=sim, **kw)
+    return tab, synth.random_theta(tab, seed=1, width=0.2)
+
+
+def _team_host(tab, theta, c, sparse):
+    from tests.host_harness.binding import simulate_team
+    p, plist, fac = condition_inputs(tab, theta, c)
+    lo, hi = tab.t_offsets[c], tab.t_offsets[c + 1]
+    pre = tab.has_preeq is not None and tab.has_preeq[c]
+    r = simulate_team(tab.model_name, p, tab.k[c], plist, tab.t[lo:hi], tab.y_of(c), tab.sigma_of(c), steady=True,
+                      sparse=sparse, rtol=tab.rtol, atol=tab.atol, maxsteps=tab.maxsteps,
+                      k_preeq=tab.k_preeq[c] if pre else None, reinit_idx=tab.reinit_idx[c] if pre else ())
+    r["sllh_sim"] = r["sllh"] * fac
+    return r
+
+
+def _spread(a, b):
+    """largest relative difference of two reference variants: per-condition llh, sllh (floored as assert_grad_close)"""
+    sl = np.max(np.abs(a["llh"] - b["llh"]) / np.abs(a["llh"]))
+    gs = np.max(np.abs(a["sllh"]), axis=1)[:, None]
+    sg = np.max(np.abs(a["sllh"] - b["sllh"]) / np.maximum(np.abs(a["sllh"]), 1e-4 * gs))
+    return sl, sg
+
+
+@pytest.mark.parametrize("sparse", [False, True], ids=["dense", "sparse"])
+@pytest.mark.parametrize("preeq,posteq", [(False, 2), (True, 1)], ids=["posteq", "preeq+posteq"])
+def test_team_core_steady_state_within_the_reference_variants_spread(oracle_available, preeq, posteq, sparse):
+    """The generated network models have rate constants over six decades: their slowest modes equilibrate only after
+    thousands of steps, and the state at which AMICI's stopping rule fires is determined to about the steady-state
+    tolerance times that stiffness ratio -- at the default tolerances the reference's KLU and dense variants differ by
+    1e-2 in llh.  With rtol 1e-11 / atol 1e-15 they agree to ~1e-6 / 2e-4 (llh / sllh); the core has to stay within a
+    small multiple of that spread and take the reference's number of steps in every phase."""
+    from oracle.binding import LINSOL_DENSE, LINSOL_KLU, OracleProblem
+    tab, theta = _team_problem(preeq, posteq, tight=True)
+    a = OracleProblem(tab, linsol=LINSOL_KLU).evaluate(theta, collect_stats=True)
+    b = OracleProblem(tab, linsol=LINSOL_DENSE).evaluate(theta)
+    assert a["status"] == 0 and b["status"] == 0
+    sl, sg = _spread(a, b)
+    assert sl < 1e-5 and sg < 2e-3, (sl, sg)
+    for c in range(tab.n_conditions):
+        r = _team_host(tab, theta, c, sparse)
+        assert r["status"] == 0
+        assert abs(r["llh"] - a["llh"][c]) / abs(a["llh"][c]) <= max(5.0 * sl, 3e-6)
+        ref = a["sllh"][c][:len(r["sllh_sim"])]
+        e = np.abs(r["sllh_sim"] - ref) / np.maximum(np.abs(ref), 1e-4 * np.max(np.abs(ref)))
+        assert np.max(e) <= max(5.0 * sg, 1e-3), (np.max(e), sg)
+        if preeq and tab.has_preeq[c]:
+            assert abs(r["stats"][14] - a["stats"][c, 14]) <= 0.1 * a["stats"][c, 14]
+        if posteq:
+            mine = r["numsteps"][-1] - r["numsteps"][-posteq - 1]
+            assert abs(mine - a["stats"][c, 15]) <= 0.1 * a["stats"][c, 15] + 5
+
+
+def test_team_core_steady_state_at_default_tolerances(oracle_available):
+    """Default tolerances: same statuses, step counts of the equilibrations within 15 % of the reference's, results
+    within a small multiple of the reference variants' own spread (1e-2: see above)."""
+    from oracle.binding import LINSOL_DENSE, LINSOL_KLU, OracleProblem
+    tab, theta = _team_problem(True, 1, tight=False)
+    a = OracleProblem(tab, linsol=LINSOL_KLU).evaluate(theta, collect_stats=True)
+    b = OracleProblem(tab, linsol=LINSOL_DENSE).evaluate(theta)
+    sl, sg = _spread(a, b)
+    for c in range(tab.n_conditions):
+        r = _team_host(tab, theta, c, sparse=True)
+        assert r["status"] == a["cond_status"][c] == 0
+        assert abs(r["llh"] - a["llh"][c]) / abs(a["llh"][c]) <= max(5.0 * sl, 1e-6)
+        if tab.has_preeq[c]:
+            assert abs(r["stats"][14] - a["stats"][c, 14]) <= 0.15 * a["stats"][c, 14]
+        mine = r["numsteps"][-1] - r["numsteps"][-2]
+        assert abs(mine - a["stats"][c, 15]) <= 0.15 * a["stats"][c, 15] + 5
+
+
+def test_team_core_equilibration_failure_and_plain_instantiation(oracle_available):
+    from oracle.binding import OracleProblem
+    from tests.host_harness.binding import simulate_team
+    tab, theta = _team_problem(True, 1, tight=False)
+    tab.maxsteps = 500
+    tab.num_trials = 1
+    ro = OracleProblem(tab).evaluate(theta)
+    assert ro["status"] == 1
+    for c in range(tab.n_conditions):
+        r = _team_host(tab, theta, c, sparse=False)
+        assert r["status"] == ro["cond_status"][c] == SIM_ERROR
+    # the instantiation without steady-state support ends with an error at t = inf
+    p, plist, _ = condition_inputs(tab, theta, 1)
+    lo, hi = tab.t_offsets[1], tab.t_offsets[2]
+    r = simulate_team("net32", p, tab.k[1], plist, tab.t[lo:hi], tab.y_of(1), tab.sigma_of(1))
+    assert r["status"] == SIM_ERROR and np.isnan(r["llh"])

@@ -41,6 +41,15 @@ class Dataset:
         self.attrs = {}
 
 
+class VlenDataset:
+    """1-D dataset of variable-length int32 sequences (h5py.vlen_dtype(np.int32)), e.g. parPE's
+    /fixedParameters/reinitializationIndices (python/parpe/hdf5_pe_input.py:430-437)."""
+
+    def __init__(self, sequences):
+        self.sequences = [np.ascontiguousarray(s, dtype=np.int32) for s in sequences]
+        self.attrs = {}
+
+
 class H5Writer:
     def __init__(self):
         self.root = Node()
@@ -57,6 +66,11 @@ class H5Writer:
         parts = [p for p in path.split("/") if p]
         g = self.group("/".join(parts[:-1]))
         g.children[parts[-1]] = Dataset(data, chunks, compress)
+
+    def vlen_dataset(self, path, sequences):
+        parts = [p for p in path.split("/") if p]
+        g = self.group("/".join(parts[:-1]))
+        g.children[parts[-1]] = VlenDataset(sequences)
 
     def attr(self, path, name, value):
         self.group(path).attrs[name] = np.asarray(value)
@@ -106,6 +120,29 @@ class H5Writer:
         body = b"".join(messages)
         hdr = struct.pack("<BBHII", 1, 0, len(messages), 1, len(body)) + b"\0" * 4
         return self._alloc(hdr + body)
+
+    def _write_vlen_dataset(self, d: VlenDataset) -> int:
+        """Elements (length u32, global heap collection address u64, object index u32); the sequences are the
+        objects 1..n of ONE global heap collection (GCOL version 1), object 0 = the free space at its end."""
+        objs = bytearray()
+        for i, s in enumerate(d.sequences):
+            if len(s):
+                objs += struct.pack("<HHIQ", i + 1, 1, 0, s.nbytes) + _pad8(s.tobytes())
+        total = max(4096, 16 + len(objs) + 16)
+        total += (-total) % 8
+        free = total - 16 - len(objs)
+        coll = b"GCOL" + bytes([1, 0, 0, 0]) + struct.pack("<Q", total) + bytes(objs)
+        coll += struct.pack("<HHIQ", 0, 0, 0, free) + b"\0" * (free - 16)
+        assert len(coll) == total
+        caddr = self._alloc(coll)
+        elems = b"".join(struct.pack("<IQI", len(s), caddr if len(s) else 0, i + 1 if len(s) else 0)
+                         for i, s in enumerate(d.sequences))
+        base = self._datatype(np.dtype(np.int32))
+        dtype = bytes([0x19, 0x00, 0x00, 0x00]) + struct.pack("<I", 16) + base
+        msgs = [self._message(0x0001, self._dataspace((len(d.sequences),))), self._message(0x0003, dtype)]
+        addr = self._alloc(elems) if elems else UNDEF
+        msgs.append(self._message(0x0008, struct.pack("<BBQQ", 3, 1, addr, len(elems))))
+        return self._object_header(msgs)
 
     def _write_dataset(self, d: Dataset) -> int:
         a = d.data
@@ -158,7 +195,10 @@ class H5Writer:
         entries = []
         for name in sorted(g.children):
             ch = g.children[name]
-            addr = self._write_dataset(ch) if isinstance(ch, Dataset) else self._write_group(ch)[0]
+            if isinstance(ch, VlenDataset):
+                addr = self._write_vlen_dataset(ch)
+            else:
+                addr = self._write_dataset(ch) if isinstance(ch, Dataset) else self._write_group(ch)[0]
             entries.append((name, addr))
         # local heap: offset 0 holds the empty string (the B-tree's first key), then the names
         heap = bytearray(b"\0" * 8)
@@ -208,7 +248,9 @@ class H5Writer:
 
 def write_parpe_input(path, tab, hier=None, compress=True, attrs=None):
     """ProblemTables -> parPE parameter-estimation input file (doc/hdf5.md).  Conditions use one column of
-    /fixedParameters/k each; no pre-equilibration (simulationConditions column 0 = -1)."""
+    /fixedParameters/k each; pre-equilibration conditions (tab.has_preeq / k_preeq / reinit_idx) become further
+    columns of k referenced by simulationConditions column 0, with /fixedParameters/reinitializationIndices as parPE
+    writes it (a ragged int32 dataset)."""
     C, np_, nk, ny = tab.n_conditions, tab.np_, tab.nk, tab.ny
     w = H5Writer()
     w.attr("/amiciOptions", "atol", np.float64(tab.atol))
@@ -219,8 +261,20 @@ def write_parpe_input(path, tab, hier=None, compress=True, attrs=None):
     w.attr("/amiciOptions", "sensi_meth", np.int32(1))
     for k_, v_ in (attrs or {}).items():
         w.attr("/amiciOptions", k_, v_)
-    w.dataset("/fixedParameters/k", np.asarray(tab.k, dtype=np.float64).T.copy(), chunks=(max(nk, 1), 1), compress=compress)
-    sc = np.stack([np.full(C, -1), np.arange(C)], axis=1).astype(np.int32)
+    kmat = np.asarray(tab.k, dtype=np.float64)
+    pre_col = np.full(C, -1)
+    if getattr(tab, "has_preeq", None) is not None:
+        extra = []
+        for c in range(C):
+            if tab.has_preeq[c]:
+                pre_col[c] = C + len(extra)
+                extra.append(np.asarray(tab.k_preeq[c], dtype=np.float64))
+        if extra:
+            kmat = np.vstack([kmat] + extra)
+        lists = tab.reinit_idx if tab.reinit_idx is not None else [[] for _ in range(C)]
+        w.vlen_dataset("/fixedParameters/reinitializationIndices", [lists[c] if tab.has_preeq[c] else [] for c in range(C)])
+    w.dataset("/fixedParameters/k", kmat.T.copy(), chunks=(max(nk, 1), 1), compress=compress)
+    sc = np.stack([pre_col, np.arange(C)], axis=1).astype(np.int32)
     w.dataset("/fixedParameters/simulationConditions", sc)
     for c in range(C):
         lo, hi = int(tab.t_offsets[c]), int(tab.t_offsets[c + 1])
