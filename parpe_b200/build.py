@@ -25,7 +25,9 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v
 
 def _sources():
     return [os.path.join(CSRC, "parpe_b200.cu"), os.path.join(CSRC, "microbench.cu"), os.path.join(CSRC, "h5input.cu"),
-            os.path.join(CSRC, "team_kernel_plain.cu"), os.path.join(CSRC, "team_kernel_steady.cu")] + sorted(glob.glob(os.path.join(CSRC, "models", "inst_*.cu")))
+            os.path.join(CSRC, "team_kernel_plain.cu"), os.path.join(CSRC, "team_kernel_steady.cu")] + \
+        sorted(glob.glob(os.path.join(CSRC, "models", "inst_*.cu"))) + \
+        sorted(glob.glob(os.path.join(CSRC, "models", "imported", "inst_*.cu")))  # (codegen/amici_import.py, build time)
 
 
 _INCLUDE = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
@@ -57,8 +59,29 @@ def _compile(src, obj, log):
     return obj
 
 
+# AMICI-generated models of the reference tree that the back-end codegen/amici_import.py re-homes as device code at
+# build time (never committed: the output contains the reference's generated expressions)
+REFERENCE_MODELS = ["/root/reference/deps/AMICI/models/model_steadystate"]
+
+
+def import_reference_models(verbose: bool = False):
+    from .codegen import amici_import
+    for d in REFERENCE_MODELS:
+        if not os.path.isdir(d):
+            continue
+        name = "amici_" + os.path.basename(d)[len("model_"):]
+        out = os.path.join(amici_import.OUTDIR, name + ".cuh")
+        srcs = glob.glob(os.path.join(d, "*.cpp")) + glob.glob(os.path.join(d, "*.h")) + [amici_import.__file__]
+        if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(p) for p in srcs):
+            continue
+        amici_import.import_model(d, name)
+        if verbose:
+            print("imported", d, "->", out)
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
+    import_reference_models(verbose)
     srcs = _sources()
     jobs = []
     for s in srcs:

@@ -14,7 +14,10 @@ def build(force=False):
     src = os.path.join(_HERE, "host_sim.cpp")
     deps = [src, os.path.join(_HERE, "..", "..", "parpe_b200", "csrc", "bdf_core.cuh")]
     mdir = os.path.join(_HERE, "..", "..", "parpe_b200", "csrc", "models")
-    deps += [os.path.join(mdir, f) for f in os.listdir(mdir)]
+    deps += [os.path.join(mdir, f) for f in os.listdir(mdir) if not os.path.isdir(os.path.join(mdir, f))]
+    idir = os.path.join(mdir, "imported")
+    if os.path.isdir(idir):
+        deps += [os.path.join(idir, f) for f in os.listdir(idir)]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", LIB, src])
 

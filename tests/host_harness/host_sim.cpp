@@ -14,6 +14,11 @@
 #include "../../parpe_b200/csrc/models/fujita.cuh"
 #include "../../parpe_b200/csrc/models/steadystate.cuh"
 #include "../../parpe_b200/csrc/models/steadystate_scaled.cuh"
+// the reference's own AMICI-generated model, re-homed by parpe_b200/codegen/amici_import.py at build time (git-ignored)
+#if __has_include("../../parpe_b200/csrc/models/imported/amici_steadystate.cuh")
+#include "../../parpe_b200/csrc/models/imported/amici_steadystate.cuh"
+#define PB200_HAVE_AMICI_STEADYSTATE 1
+#endif
 
 using namespace pb200;
 
@@ -100,6 +105,9 @@ extern "C" int hs_simulate_ss(const char* model, const double* p_unscaled, const
     DISPATCH_SS(steadystate_scaled)
     DISPATCH_SS(boehm)
     DISPATCH_SS(fujita)
+#if defined(PB200_HAVE_AMICI_STEADYSTATE)
+    DISPATCH_SS(amici_steadystate)
+#endif
     return -12345;
 }
 
@@ -115,5 +123,8 @@ extern "C" int hs_simulate(const char* model, const double* p_unscaled, const do
     DISPATCH(steadystate_scaled)
     DISPATCH(boehm)
     DISPATCH(fujita)
+#if defined(PB200_HAVE_AMICI_STEADYSTATE)
+    DISPATCH(amici_steadystate)
+#endif
     return -12345;
 }

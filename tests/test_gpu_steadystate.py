@@ -199,10 +199,16 @@ def test_large_model_kernel_steady_states(oracle_available, model, linsol):
     e = np.abs(res["sllh"] - a["sllh"]) / np.maximum(np.abs(a["sllh"]), 1e-4 * gs)
     assert np.max(e) <= max(5.0 * sg, 1e-3), (np.max(e), sg)
     assert abs(fval - a["fval"]) / abs(a["fval"]) <= max(5.0 * sl, 3e-6)
-    # cost only, and a condition without pre-equilibration alone
+    # cost only: without sensitivities the stopping rule tests xdot alone and fires earlier -- a weaker criterion
+    # with a spread of its own (net32: 4e-4 per condition between the reference's KLU and dense variants; net31: 1e-8)
     st, f0, _, _ = gpu.evaluate(theta, want_gradient=False)
-    a0 = OracleProblem(tab).evaluate(theta, want_grad=False)
-    assert st == 0 and abs(f0 - a0["fval"]) / abs(a0["fval"]) <= max(5.0 * sl, 3e-6)
+    a0 = OracleProblem(tab, linsol=LINSOL_KLU).evaluate(theta, want_grad=False)
+    b0 = OracleProblem(tab, linsol=LINSOL_DENSE).evaluate(theta, want_grad=False)
+    sl0 = np.max(np.abs(a0["llh"] - b0["llh"]) / np.abs(a0["llh"]))
+    res0 = gpu.condition_results()
+    assert st == 0 and np.all(res0["status"] == 0)
+    assert np.max(np.abs(res0["llh"] - a0["llh"]) / np.abs(a0["llh"])) <= max(5.0 * sl0, 3e-6)
+    assert abs(f0 - a0["fval"]) / abs(a0["fval"]) <= max(5.0 * sl0, 3e-6)
 
 
 def test_large_model_kernel_equilibration_failure(oracle_available):
