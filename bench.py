@@ -59,6 +59,13 @@ def host_threads():
 
 
 def workload_name(model, per_gpu, n_gpus, total, hetero=False):
+    name = _workload_name(model, per_gpu, n_gpus, total, hetero)
+    if STEADY:
+        name += "; steady-state variant: 3 of 4 conditions pre-equilibrated, last two output times t = inf"
+    return name
+
+
+def _workload_name(model, per_gpu, n_gpus, total, hetero=False):
     if model in LARGE_MODELS:
         from parpe_b200.models import get_spec
         sp = get_spec(model)
@@ -72,9 +79,13 @@ def workload_name(model, per_gpu, n_gpus, total, hetero=False):
     return "%s, %d conditions total on %d GPU" % (model, total, n_gpus)
 
 
+STEADY = False  # --steady: three of four conditions pre-equilibrated, the last two output times t = inf
+
+
 def make_tables(model, n_conditions, hetero=False):
     from parpe_b200 import synth
-    tab = synth.make_problem(model, n_conditions, scale="log10", seed=0, heterogeneous=hetero)
+    kw = dict(preeq=True, posteq=2) if STEADY else {}
+    tab = synth.make_problem(model, n_conditions, scale="log10", seed=0, heterogeneous=hetero, **kw)
     theta = synth.random_theta(tab, seed=1, width=1.0 if hetero else THETA_WIDTH.get(model, 0.5))
     return tab, theta
 
@@ -482,7 +493,13 @@ def main():
                     help="weak: conditions per GPU; strong: total conditions (0 = default of the workload)")
     ap.add_argument("--linsol", type=int, default=0, help="large models: 0 automatic, 1 dense inverse, 2 sparse LU")
     ap.add_argument("--heterogeneous", action="store_true", help="boehm: conditions that differ by up to 300x, theta +-1")
+    ap.add_argument("--steady", action="store_true",
+                    help="steady-state variant of the workload (DESIGN 3.5): three of four conditions pre-equilibrated, "
+                         "the last two output times t = inf; the integrator statistics (and so the roofline figures) "
+                         "count the main simulation only")
     args = ap.parse_args()
+    global STEADY
+    STEADY = bool(args.steady)
     model = args.workload
     if args.scaling == "weak":
         per_gpu = args.conditions or DEFAULT_CONDITIONS.get(model, 4 * 148 * 32)
