@@ -134,7 +134,14 @@ typedef struct pb200_problem_desc {
     double relaxation_factor;  /* PARPE_INTEGRATION_TOLERANCE_RELAXATION_FACTOR, default 100 */
     /* kernel mapping hint: lanes cooperating on one condition (0 = automatic) */
     int32_t lanes_per_condition;
-    int32_t reserved[7];
+    /* steady states (pre-/post-equilibration): > 0 = Newton's method first, with this many steps at most, the
+     * simulation to steady state if it fails, Newton once more if that fails too -- what the reference does with
+     * Solver::setNewtonMaxSteps(n) AND the model's steadyStateComputationMode = steadyStateSensitivityMode =
+     * integrateIfNewtonFails (deps/AMICI/src/steadystateproblem.cpp:120-166,628-715; newton_solver.cpp:43-125).
+     * 0 = steady state by simulation only: AMICI's defaults (both modes integrationOnly, with which the reference
+     * ignores newton_maxsteps).  Small-model kernels only. */
+    int32_t newton_maxsteps;
+    int32_t reserved[6];
 } pb200_problem_desc;
 
 typedef struct pb200_handle pb200_handle;
@@ -176,9 +183,9 @@ void pb200_destroy(pb200_handle* h);
  * condition's constants from x0 until the weighted RMS norm of xdot (and of the sensitivity
  * right-hand sides) falls below 1 at 100 x the integration tolerances, the main simulation starts
  * from that steady state (and its sensitivities), and the listed states whose initial value depends
- * on the constants are reset to their initial value.  AMICI's defaults are implemented:
- * steady state by simulation (newton_maxsteps = 0), sensitivities integrated along
- * (integrateIfNewtonFails), convergence check on the sensitivities on.
+ * on the constants are reset to their initial value.  AMICI's defaults are implemented -- steady
+ * state by simulation, sensitivities integrated along, convergence check on the sensitivities on --
+ * and, with pb200_problem_desc::newton_maxsteps > 0, Newton's method first (small-model kernels).
  *   has_preeq       [C]     1 = condition c is pre-equilibrated; NULL switches pre-equilibration off
  *   k_preeq         [C*nk]  constants of the pre-equilibration condition (rows of conditions
  *                           without one are ignored)

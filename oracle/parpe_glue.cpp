@@ -57,6 +57,14 @@ Problem::Problem(std::unique_ptr<amici::Model> model, Tables tables)
     : model_(std::move(model)), tab_(std::move(tables)) {
     if (model_->np() != tab_.np || model_->nk() != tab_.nk || model_->ny != tab_.ny)
         throw std::invalid_argument("table dimensions do not match the model");
+    // Newton's method for steady states needs more than Solver::newton_maxsteps > 0: the MODEL's modes must allow
+    // it (AMICI's default for both is integrationOnly, model.h:2063-2072; /amiciOptions attributes
+    // steadyStateComputationMode / steadyStateSensitivityMode, deps/AMICI/src/hdf5.cpp:1433-1448).  The tables'
+    // newton_maxsteps > 0 stands for "both modes integrateIfNewtonFails with this many Newton steps".
+    if (tab_.newton_maxsteps > 0) {
+        model_->setSteadyStateComputationMode(amici::SteadyStateComputationMode::integrateIfNewtonFails);
+        model_->setSteadyStateSensitivityMode(amici::SteadyStateSensitivityMode::integrateIfNewtonFails);
+    }
 }
 
 // multiConditionDataProvider.cpp:84-102 (column `c` of optimizationSimulationMapping)
@@ -101,6 +109,7 @@ std::unique_ptr<amici::Solver> Problem::makeSolver(bool sensi) const {
     solver->setRelativeTolerance(tab_.rtol);
     solver->setMaxSteps(tab_.maxsteps);
     solver->setStabilityLimitFlag(tab_.stldet != 0);
+    solver->setNewtonMaxSteps(tab_.newton_maxsteps);
     solver->setLinearSolver(static_cast<amici::LinearSolver>(tab_.linsol));
     solver->setInternalSensitivityMethod(static_cast<amici::InternalSensitivityMethod>(tab_.ism));
     if (sensi) {

@@ -46,6 +46,7 @@ struct Tables {
     int stldet = 1;
     int num_trials = 6;
     double relaxation_factor = 100.0;
+    int newton_maxsteps = 0;  // amici::Solver::setNewtonMaxSteps (AMICI default 0)
     int ism = 2;     // amici::InternalSensitivityMethod (1 simultaneous, 2 staggered)
     int linsol = 9;  // amici::LinearSolver (1 dense, 9 KLU)
 };

@@ -160,6 +160,7 @@ struct SolverOptions {
     int maxsteps;
     int stldet;
     int errconS;
+    int newton_maxsteps;  // steady states: Newton iterations tried before / after the simulation (AMICI default 0 = none)
 };
 
 // ---- lane groups ---------------------------------------------------------------
@@ -659,13 +660,17 @@ PB_ASSUME_SHARED(sh);
 /// Scratch: yj, ysh, fout, Jcur, dfdp, scr -- all rewritten by the next step attempt.  Out of line.
 template <class M, class Grp>
 PB_HD_NOINLINE static bool ss_converged_shared(GroupShared<M>* sh, const Grp g, double t, double rtol, double atol,
-                                               int ns, int nsall) {
+                                               int ns, int nsall, const double* xsrc) {
     constexpr int NX = M::NX, G = Grp::G;
     PB_ASSUME_SHARED(sh);
+    PB_ASSUME_SHARED(xsrc);
     g.sync();
+    // xsrc: the state the test is made at -- zn[0] (the solver's state), or the last trial point of a failed Newton
+    // attempt before the first step of a post-equilibration (SteadystateProblem::state_.x is what getWrms reads)
     for (int i = g.lane(); i < NX; i += G) {
-        sh->yj[i] = sh->zn[0][i];
-        sh->ysh[i] = sh->zn[0][i];
+        const double v = xsrc[i];
+        sh->yj[i] = v;
+        sh->ysh[i] = v;
     }
     g.sync();
     int conv = 0;
@@ -714,6 +719,147 @@ PB_HD_NOINLINE static bool ss_converged_shared(GroupShared<M>* sh, const Grp g, 
     conv = g.bcast0(conv);
     g.sync();
     return conv != 0;
+}
+
+/// J(t, x) delta = rhs for nrhs right-hand sides by LU with partial pivoting (the pivot order of
+/// SUNDlsMat_denseGETRF), serially by the group's first lane: the linear system of the steady-state Newton solver
+/// (NewtonSolver::prepareLinearSystem / solveLinearSystem, deps/AMICI/src/newton_solver.cpp:86-125; the reference
+/// factorises with KLU by default).  x = sh->ysh; the factors overwrite sh->Jcur, which is zeroed again afterwards
+/// (the Jacobian functions write structural non-zeros only).  rhs: nrhs columns of stride NX, solved in place.
+/// Returns 1 if the matrix is singular or not finite.  Lane 0 only (callers synchronise).
+template <class M>
+PB_HD_NOINLINE static int ss_newton_linsolve_lane0(GroupShared<M>* sh, double t, double* rhs, int nrhs) {
+    constexpr int NX = M::NX;
+    PB_ASSUME_SHARED(sh);
+    PB_ASSUME_SHARED(rhs);
+    double* A = sh->Jcur;
+    for (int e = 0; e < NX * NX; ++e) A[e] = 0.0;
+    eval_jac_shared<M>(A, t, sh->ysh, sh);
+    int piv[NX];
+    int bad = 0;
+    for (int k = 0; k < NX && !bad; ++k) {
+        int l = k;
+        for (int i = k + 1; i < NX; ++i)
+            if (fabs(A[i + k * NX]) > fabs(A[l + k * NX])) l = i;
+        piv[k] = l;
+        const double d = A[l + k * NX];
+        if (d == 0.0 || !PB_FINITE(d)) { bad = 1; break; }
+        if (l != k)
+            for (int j = 0; j < NX; ++j) {
+                const double tmp = A[l + j * NX];
+                A[l + j * NX] = A[k + j * NX];
+                A[k + j * NX] = tmp;
+            }
+        const double mult = pb_rcp(A[k + k * NX]);
+        for (int i = k + 1; i < NX; ++i) A[i + k * NX] *= mult;
+        for (int j = k + 1; j < NX; ++j) {
+            const double akj = A[k + j * NX];
+            if (akj != 0.0)
+                for (int i = k + 1; i < NX; ++i) A[i + j * NX] -= akj * A[i + k * NX];
+        }
+    }
+    if (!bad) {
+        for (int c = 0; c < nrhs; ++c) {
+            double* b = rhs + c * NX;
+            for (int k = 0; k < NX; ++k) {  // row permutation, then forward substitution (unit lower triangle)
+                const int l = piv[k];
+                if (l != k) { const double tmp = b[l]; b[l] = b[k]; b[k] = tmp; }
+            }
+            for (int k = 0; k < NX - 1; ++k)
+                for (int i = k + 1; i < NX; ++i) b[i] -= b[k] * A[i + k * NX];
+            for (int k = NX - 1; k >= 0; --k) {
+                b[k] = pb_div(b[k], A[k + k * NX]);
+                for (int i = 0; i < k; ++i) b[i] -= b[k] * A[i + k * NX];
+            }
+        }
+    }
+    for (int e = 0; e < NX * NX; ++e) A[e] = 0.0;
+    return bad;
+}
+
+/// SteadystateProblem::applyNewtonsMethod (deps/AMICI/src/steadystateproblem.cpp:628-683) with getWrms (:553-591),
+/// getNewtonStep (:889-896) and updateDampingFactor (:697-715; damping on, lower bound 1e-8: AMICI's defaults):
+/// damped Newton iteration x <- x_old + gamma * delta, J(x_old) delta = -xdot(x_old), accepted while the weighted
+/// RMS norm of xdot decreases, converged when it is below 1 at the steady-state tolerances.  x (NX values in
+/// group-shared memory) is iterated in place and holds the LAST TRIAL POINT on return, as the reference's state_.x
+/// does.  Scratch: yj, ysh (x_old), fout, b (delta), Jcur.  Executed by the group's first lane.
+/// Returns the number of Newton steps taken (>= 0) on convergence, -1 otherwise (too many steps, damping factor at
+/// its lower bound, singular Jacobian).
+template <class M, class Grp>
+PB_HD_NOINLINE static int ss_newton_shared(GroupShared<M>* sh, const Grp g, double t, double rtol, double atol,
+                                           int max_steps, bool retry, double* x) {
+    constexpr int NX = M::NX;
+    PB_ASSUME_SHARED(sh);
+    PB_ASSUME_SHARED(x);
+    g.sync();
+    int result = -1;
+    if (g.lane() == 0) {
+        double* xold = sh->ysh;
+        double* delta = sh->b;
+        auto wrms_at = [&](const double* xs) {  // getWrms: xdot at xs, weights 1 / (rtol |xs| + atol)
+            for (int i = 0; i < NX; ++i) sh->yj[i] = xs[i];
+            eval_xdot_shared<M>(sh, t);
+            double s = 0.0;
+            for (int i = 0; i < NX; ++i) {
+                const double prod = sh->fout[i] * pb_rcp(rtol * fabs(xs[i]) + atol);
+                s += prod * prod;
+            }
+            return sqrt(pb_div(s, (double)NX));
+        };
+        for (int i = 0; i < NX; ++i) xold[i] = x[i];
+        double wrms = wrms_at(x);
+        bool converged = retry ? false : (wrms < 1.0);
+        bool update_direction = true, failed = false;
+        double gamma = 1.0;
+        int it = 0;
+        while (!converged && it < max_steps) {
+            if (update_direction) {
+                // xdot at the accepted state (x == xold whenever a new direction is taken)
+                for (int i = 0; i < NX; ++i) sh->yj[i] = xold[i];
+                eval_xdot_shared<M>(sh, t);
+                for (int i = 0; i < NX; ++i) delta[i] = -sh->fout[i];
+                if (ss_newton_linsolve_lane0<M>(sh, t, delta, 1)) { failed = true; break; }
+            }
+            for (int i = 0; i < NX; ++i) x[i] = xold[i] + gamma * delta[i];
+            const double wrms_tmp = wrms_at(x);
+            const bool ok = wrms_tmp < wrms;
+            if (ok) {
+                wrms = wrms_tmp;
+                converged = wrms < 1.0;
+                for (int i = 0; i < NX; ++i) xold[i] = x[i];
+            }
+            gamma = ok ? fmin(1.0, 2.0 * gamma) : gamma / 4.0;
+            if (gamma < 1e-8) { failed = true; break; }
+            update_direction = ok;
+            ++it;
+        }
+        result = (converged && !failed) ? it : -1;
+    }
+    result = g.bcast0(result);
+    g.sync();
+    return result;
+}
+
+/// NewtonSolver::computeNewtonSensis (newton_solver.cpp:52-84): sx_ip = -J(x)^-1 dxdotdp_ip at the steady state x
+/// (column 0 of zn[0]) into the sensitivity columns of zn[0].  Returns 1 if the Jacobian is singular.
+template <class M, class Grp>
+PB_HD_NOINLINE static int ss_newton_sensis_shared(GroupShared<M>* sh, const Grp g, double t, int ns) {
+    constexpr int NX = M::NX;
+    PB_ASSUME_SHARED(sh);
+    g.sync();
+    int bad = 0;
+    if (g.lane() == 0) {
+        for (int i = 0; i < NX; ++i) sh->ysh[i] = sh->zn[0][i];
+        eval_dfdp_shared<M>(sh, t, sh->ysh);
+        for (int c = 1; c <= ns; ++c) {
+            const double* dcol = sh->dfdp + sh->cdcol[c - 1] * NX;
+            for (int i = 0; i < NX; ++i) sh->zn[0][c * NX + i] = -dcol[i];
+        }
+        bad = ss_newton_linsolve_lane0<M>(sh, t, sh->zn[0] + NX, ns);
+    }
+    bad = g.bcast0(bad);
+    g.sync();
+    return bad;
 }
 
 /// SS: with support for steady states -- output times t = inf (post-equilibration) and a
@@ -776,6 +922,8 @@ struct Bdf {
     // steady-state support (SS only): what the simulation is doing
     enum { SS_OFF = 0, SS_PREEQ = 1, SS_POSTEQ = 2 };
     int ss_mode_;
+    int ss_newton_;  // Newton attempts of the current steady-state phase: 0 none yet, 1 first done, 2 retry done,
+                     // 3 retry requested (the simulation has just failed)
     /// true while CVode is driven in CV_ONE_STEP mode without a stop time (Solver::step,
     /// deps/AMICI/src/solver.cpp:161-175): simulation to steady state
     PB_HD bool one_step() const { return SS && ss_mode_ != SS_OFF; }
@@ -1668,6 +1816,7 @@ struct Bdf {
     PB_HD void begin(const ConditionIO& io, double rtol, double atol, int mode = 0, unsigned reinit_mask = 0u) {
         io_ = io;
         ss_mode_ = (SS && mode == SS_PREEQ) ? SS_PREEQ : SS_OFF;
+        ss_newton_ = 0;
         const bool keep = SS && mode == SS_POSTEQ;  // initial values: the pre-equilibrated state
         if (SS) reinit_mask &= M::X0K_MASK;         // only states whose x0 depends on the constants are re-initialised
         opt.rtol = rtol;
@@ -1757,6 +1906,10 @@ struct Bdf {
     /// -- then order/step adjustment, prediction and BDF coefficients.
     PB_HD void stage_pre() {
         if (stage_ != ST_PRE) return;
+        if (SS && ss_newton_ == 3) {  // (requested by finish())
+            if (!steady_retry()) finish(SIM_ERROR);
+            return;
+        }
         if (!in_step_) {
             if (!in_cvode_) {
                 for (;;) {
@@ -1768,6 +1921,7 @@ struct Bdf {
                         // output time, forwardproblem.cpp:149-150).  Without steady-state support an error, never a
                         // silently dropped point.
                         if (!SS) { finish(SIM_ERROR); return; }
+                        if (ss_mode_ != SS_POSTEQ) ss_newton_ = 0;
                         ss_mode_ = SS_POSTEQ;
                         break;
                     }
@@ -1780,19 +1934,30 @@ struct Bdf {
                     if (!output_point()) return;
                 }
                 if (one_step()) {
+                    const double rtol_ss = 100.0 * opt.rtol, atol_ss = 100.0 * opt.atol;  // steady-state tolerances
+                    const double* xchk = S()->zn[0];
+                    if (opt.newton_maxsteps > 0 && ss_newton_ == 0) {
+                        // SteadystateProblem::findSteadyState (steadystateproblem.cpp:120-166): Newton's method first
+                        // (newton_maxsteps > 0; AMICI's default 0 goes straight to the simulation).  Pre-equilibration:
+                        // in place -- a simulation after a failed attempt starts from the last trial point, as the
+                        // reference's does (createSteadystateSimSolver sets the new solver up at state_.x).
+                        // Post-equilibration: on a copy (acor is free between steps), the solver keeps its state.
+                        ss_newton_ = 1;
+                        double* x = S()->zn[0];
+                        if (ss_mode_ == SS_POSTEQ) {
+                            x = S()->acor;
+                            g.sync();
+                            PB_FOR_RANGE(e, 0, NX) x[e] = S()->zn[0][e];
+                        }
+                        const int it = ss_newton_shared<M, Grp>(S(), g, tn, rtol_ss, atol_ss, opt.newton_maxsteps, false, x);
+                        if (it >= 0) { steady_found(it > 0, x); return; }
+                        xchk = x;  // the simulation's first convergence test reads the last Newton trial point
+                    }
                     // one trip of SteadystateProblem::runSteadystateSimulation (steadystateproblem.cpp:711-794):
                     // convergence test at the solver's current state, then ONE internal step towards
                     // max(t, 1) * 10.  Steady-state tolerances: 100 x the integration tolerances.
-                    if (ss_converged_shared<M, Grp>(S(), g, tn, 100.0 * opt.rtol, 100.0 * opt.atol, ns, nsall)) {
-                        if (ss_mode_ == SS_POSTEQ) {
-                            // ReturnData::processPostEquilibration (rdata.cpp:234-258): every t = inf point
-                            // is evaluated at the steady state
-                            while (it_ < io_.nt) {
-                                tout_ = io_.t[it_];
-                                if (!output_point()) return;
-                            }
-                        }
-                        finish(SIM_SUCCESS);
+                    if (ss_converged_shared<M, Grp>(S(), g, tn, rtol_ss, atol_ss, ns, nsall, xchk)) {
+                        steady_success();
                         return;
                     }
                     if (nst >= opt.maxsteps) { finish(SIM_ERROR); return; }
@@ -1816,6 +1981,55 @@ struct Bdf {
         const int r = attempt_predict();
         if (r < 0) { finish(r); return; }
         stage_ = ST_NLS;
+    }
+
+    /// The steady state is reached: every t = inf output time is evaluated there
+    /// (ReturnData::processPostEquilibration, rdata.cpp:234-258); a pre-equilibration just ends.
+    PB_HD void steady_success() {
+        if (ss_mode_ == SS_POSTEQ) {
+            while (it_ < io_.nt) {
+                tout_ = io_.t[it_];
+                if (!output_point()) return;
+            }
+        }
+        finish(SIM_SUCCESS);
+    }
+
+    /// Newton's method found the steady state x: it becomes the state, and -- unless the iteration started in the
+    /// steady state (no step taken: getSensitivityFlag, steadystateproblem.cpp:453-517) -- the sensitivities are
+    /// those of the steady state, sx = -J^-1 dxdotdp (workSteadyStateProblem :91-103; a singular Jacobian there is
+    /// an AmiException -> AMICI_ERROR).
+    PB_HD void steady_found(bool newton_sensis, const double* x) {
+        g.sync();
+        if (x != S()->zn[0]) PB_FOR_RANGE(e, 0, NX) S()->zn[0][e] = x[e];
+        g.sync();
+        if (sensi && newton_sensis) {
+            if (ss_newton_sensis_shared<M, Grp>(S(), g, tn, ns)) {
+                ss_newton_ = 2;
+                finish(SIM_ERROR);
+                return;
+            }
+        }
+        steady_success();
+    }
+
+    /// The simulation to steady state failed: Newton's method once more, from the last state the simulation reached
+    /// and with at least one step (findSteadyStateByNewtonsMethod(model, true), steadystateproblem.cpp:160-162).
+    /// Returns true if that found the steady state.
+    PB_HD bool steady_retry() {
+        ss_newton_ = 2;
+        if (in_step_ && undo_) {  // the failure came in the middle of a step: back to the last completed one (cvRestore)
+            tn = saved_t_;
+            shift_history(-1.0);
+            undo_ = false;
+        }
+        in_step_ = false;
+        g.sync();
+        const int it = ss_newton_shared<M, Grp>(S(), g, tn, 100.0 * opt.rtol, 100.0 * opt.atol, opt.newton_maxsteps, true,
+                                                S()->zn[0]);
+        if (it < 0) return false;
+        steady_found(true, S()->zn[0]);
+        return true;
     }
 
     /// The data point of output time it_ (tout_) at the current state; false = the simulation has ended
@@ -1879,6 +2093,13 @@ struct Bdf {
     }
 
     PB_HD bool finish(int status) {
+        if (SS && one_step() && status != SIM_SUCCESS && opt.newton_maxsteps > 0 && ss_newton_ < 2) {
+            // the simulation to steady state failed: Newton's method once more, at the top of the next stage_pre
+            // (ONE copy of that code instead of one per call site of finish())
+            ss_newton_ = 3;
+            stage_ = ST_PRE;
+            return false;
+        }
         stage_ = ST_DONE;
         // any failure while simulating to steady state ends as AmiException -> AMICI_ERROR
         // (SteadystateProblem::findSteadyStateBySimulation / handleSteadyStateFailure,

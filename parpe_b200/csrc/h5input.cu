@@ -271,14 +271,22 @@ int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_pro
         d.rtol = opt("rtol", 1e-8);
         d.maxsteps = (int32_t)opt("maxsteps", 10000);
         d.stldet = (int32_t)opt("stldet", 1);
-        // Steady states are found by simulation (AMICI's default newton_maxsteps = 0); a file that asks
-        // for Newton's method first would be simulated differently by the reference: refused, not ignored
+        // Steady states: Newton's method is used by the reference only when the MODEL's modes allow it
+        // (/amiciOptions steadyStateComputationMode / steadyStateSensitivityMode: 0 newtonOnly, 1 integrationOnly --
+        // AMICI's default for both --, 2 integrateIfNewtonFails; deps/AMICI/src/hdf5.cpp:1433-1448,
+        // steadystateproblem.cpp:120-166) and newton_maxsteps > 0.  Built: (1, 1 or 2) = by simulation, and (2, 2) =
+        // Newton first, simulation if it fails, Newton once more; other combinations are refused, not approximated.
         {
+            const int comp = (int)opt("steadyStateComputationMode", 1.0), sens = (int)opt("steadyStateSensitivityMode", 1.0);
+            const int nmax = (int)opt("newton_maxsteps", 0.0);
             bool steady = P->any_preeq;
             for (double tv : P->t) steady = steady || std::isinf(tv);
-            if (steady && opt("newton_maxsteps", 0.0) > 0.0)
-                throw H5Error("/amiciOptions newton_maxsteps > 0 with pre-/post-equilibration: Newton's method for steady "
-                              "states is not supported (only steady state by simulation, newton_maxsteps = 0)");
+            d.newton_maxsteps = 0;
+            if (comp == 2 && sens == 2) d.newton_maxsteps = nmax > 0 ? nmax : 0;
+            else if (!(comp == 1 && (sens == 1 || sens == 2)) && steady)
+                throw H5Error("/amiciOptions steadyStateComputationMode = " + std::to_string(comp) +
+                              ", steadyStateSensitivityMode = " + std::to_string(sens) + " with pre-/post-equilibration: "
+                              "only (1, 1|2) = steady state by simulation and (2, 2) = Newton first are supported");
         }
         d.sensi_errcon = 1;
         d.num_trials = 6;

@@ -350,6 +350,8 @@ struct ModelOps {
     int (*linsol_info)(void* state, int64_t* out, int n);
     // 1 = the model's kernels handle pre-equilibration and t = inf output times (KernelArgs::steady)
     int supports_steady;
+    // 1 = ... and Newton's method for steady states (SolverOptions::newton_maxsteps > 0)
+    int supports_newton;
 };
 
 void register_model(const ModelOps& ops);
@@ -454,6 +456,7 @@ ModelOps make_ops() {
     o.destroy_state = nullptr;
     o.linsol_info = nullptr;
     o.supports_steady = 1;
+    o.supports_newton = 1;
     return o;
 }
 

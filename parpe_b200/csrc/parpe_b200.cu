@@ -459,6 +459,10 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
     a.opt.maxsteps = d->maxsteps;
     a.opt.stldet = d->stldet;
     a.opt.errconS = d->sensi_errcon;
+    a.opt.newton_maxsteps = d->newton_maxsteps > 0 ? d->newton_maxsteps : 0;
+    if (has_inf && a.opt.newton_maxsteps > 0 && !ops->supports_newton)
+        return fail(PB200_ERR_ARG, "newton_maxsteps > 0 with t = inf output times: Newton's method for steady states is not "
+                                   "supported for this model (only steady state by simulation, newton_maxsteps = 0)");
     a.num_trials = d->num_trials > 0 ? d->num_trials : 1;
     a.relaxation_factor = d->relaxation_factor;
     if (int rc = ensure_capacity(h, C > 0 ? C : 1)) return rc;
@@ -503,6 +507,9 @@ int pb200_set_preequilibration(pb200_handle* h, const int32_t* has_preeq, const 
         return 0;
     }
     if (!h->ops->supports_steady) return fail(PB200_ERR_ARG, "pre-equilibration is not supported for this model");
+    if (a.opt.newton_maxsteps > 0 && !h->ops->supports_newton)
+        return fail(PB200_ERR_ARG, "newton_maxsteps > 0 with pre-equilibration: Newton's method for steady states is not "
+                                   "supported for this model (only steady state by simulation, newton_maxsteps = 0)");
     if (!k_preeq && h->nk > 0) return fail(PB200_ERR_ARG, "k_preeq is null");
     std::vector<int> flag(h->C);
     std::vector<unsigned> mask(h->C, 0u);

@@ -50,6 +50,7 @@ struct B200ProblemTables {
     int numSimulationTrials = 6;                         // PARPE_NUM_SIMULATION_TRIALS
     double integrationToleranceRelaxationFactor = 100.0; // PARPE_INTEGRATION_TOLERANCE_RELAXATION_FACTOR
     int lanesPerCondition = 0;
+    int newtonMaxSteps = 0;  // amici::Solver::setNewtonMaxSteps (steady states; 0 = by simulation only)
 
     /// The tables of a parPE parameter-estimation input file (doc/hdf5.md), assembled by the library's built-in
     /// HDF5 reader (pb200_h5_load_problem) -- what MultiConditionDataProviderHDF5 serves per condition, read once.
@@ -75,6 +76,7 @@ struct B200ProblemTables {
         d.num_trials = numSimulationTrials;
         d.relaxation_factor = integrationToleranceRelaxationFactor;
         d.lanes_per_condition = lanesPerCondition;
+        d.newton_maxsteps = newtonMaxSteps;
         return d;
     }
 };
@@ -328,6 +330,7 @@ inline B200ProblemTables B200ProblemTables::fromHdf5(std::string const& path, st
     T.t0 = d.t0; T.atol = d.atol; T.rtol = d.rtol;
     T.maxSteps = d.maxsteps;
     T.stabilityLimitDetection = d.stldet != 0;
+    T.newtonMaxSteps = d.newton_maxsteps;
     {
         const int32_t* flag = nullptr; const double* kp = nullptr; const int64_t* off = nullptr; const int32_t* idx = nullptr;
         if (pb200_h5_problem_preeq(P, &flag, &kp, &off, &idx)) {

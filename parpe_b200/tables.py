@@ -45,7 +45,8 @@ class ProblemDesc(C.Structure):
         ("num_trials", C.c_int32),
         ("relaxation_factor", C.c_double),
         ("lanes_per_condition", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("newton_maxsteps", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -125,6 +126,7 @@ class ProblemTables:
     num_trials: int = 6
     relaxation_factor: float = 100.0
     lanes_per_condition: int = 0
+    newton_maxsteps: int = 0   # steady states: Newton iterations before / after the simulation (AMICI default 0)
     hier: Optional[HierTables] = None
     # pre-equilibration (pb200_set_preequilibration): per simulation condition a flag, the constants of
     # the pre-equilibration condition and the states re-initialised afterwards
@@ -185,6 +187,7 @@ class ProblemTables:
         d.maxsteps, d.stldet, d.sensi_errcon = self.maxsteps, self.stldet, self.sensi_errcon
         d.num_trials, d.relaxation_factor = self.num_trials, self.relaxation_factor
         d.lanes_per_condition = self.lanes_per_condition
+        d.newton_maxsteps = self.newton_maxsteps
         return d
 
     # per-condition views in the reference's layout (row-major obs + it*ny)

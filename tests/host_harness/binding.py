@@ -32,13 +32,13 @@ def lib():
                                   C.c_double, C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int64), dp, dp, ip]
         L.hs_simulate_ss.argtypes = [C.c_char_p, dp, dp, dp, C.c_uint, ip, C.c_int, C.c_int, dp, dp, dp, C.c_double,
                                      C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int64),
-                                     dp, dp, ip, dp]
+                                     dp, dp, ip, dp, C.c_int]
         _lib = L
     return _lib
 
 
 def simulate_ss(model, p_unscaled, k, plist, t, my, sd, k_preeq=None, reinit_idx=(), t0=0.0, rtol=1e-8, atol=1e-12,
-                maxsteps=10000, stldet=1, errconS=1, want_outputs=False, nx=None):
+                maxsteps=10000, stldet=1, errconS=1, want_outputs=False, nx=None, newton_maxsteps=0):
     """The steady-state instantiation of the core: t = inf output times (post-equilibration) and, with
     ``k_preeq``, pre-equilibration + re-initialisation of the states ``reinit_idx``."""
     d = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -61,7 +61,7 @@ def simulate_ss(model, p_unscaled, k, plist, t, my, sd, k_preeq=None, reinit_idx
                               plist.ctypes.data_as(C.POINTER(C.c_int)), ns, len(t), P(t), P(my), P(sd), t0, rtol, atol,
                               maxsteps, stldet, errconS, C.byref(llh), P(sllh),
                               stats.ctypes.data_as(C.POINTER(C.c_int64)), P(y), P(s),
-                              trace.ctypes.data_as(C.POINTER(C.c_int)), P(xpre))
+                              trace.ctypes.data_as(C.POINTER(C.c_int)), P(xpre), newton_maxsteps)
     return dict(numsteps=trace[0::2], order=trace[1::2], status=st, llh=llh.value, sllh=sllh[:ns], stats=stats, y=y,
                 sigmay=s, x_preeq=xpre, nst_preeq=int(stats[16]))
 

@@ -36,6 +36,7 @@ static int run(const double* p_unscaled, const double* k, const int* plist, int 
     bdf.opt.maxsteps = maxsteps;
     bdf.opt.stldet = stldet;
     bdf.opt.errconS = errconS;
+    bdf.opt.newton_maxsteps = 0;
     ConditionIO io{nt, t, my, sd, ns, y_out, sigmay_out, trace};
     int status = bdf.simulate(io, rtol, atol, *llh);
     for (int j = 0; j < ns; ++j) sllh[j] = sh.sllh[j + 1];
@@ -50,7 +51,7 @@ template <class M>
 static int run_ss(const double* p_unscaled, const double* k, const double* k_preeq, unsigned reinit_mask,
                   const int* plist, int ns, int nt, const double* t, const double* my, const double* sd, double t0,
                   double rtol, double atol, int maxsteps, int stldet, int errconS, double* llh, double* sllh,
-                  int64_t* stats, double* y_out, double* sigmay_out, int* trace, double* x_preeq) {
+                  int64_t* stats, double* y_out, double* sigmay_out, int* trace, double* x_preeq, int newton_maxsteps) {
     static thread_local GroupShared<M> sh;
     static thread_local Bdf<M, SingleLane, true> bdf;
     using B = Bdf<M, SingleLane, true>;
@@ -61,6 +62,7 @@ static int run_ss(const double* p_unscaled, const double* k, const double* k_pre
     bdf.opt.maxsteps = maxsteps;
     bdf.opt.stldet = stldet;
     bdf.opt.errconS = errconS;
+    bdf.opt.newton_maxsteps = newton_maxsteps;
     ConditionIO io{nt, t, my, sd, ns, y_out, sigmay_out, trace};
     int status;
     if (k_preeq) {
@@ -95,12 +97,12 @@ extern "C" int hs_simulate_ss(const char* model, const double* p_unscaled, const
                               unsigned reinit_mask, const int* plist, int ns, int nt, const double* t,
                               const double* my, const double* sd, double t0, double rtol, double atol, int maxsteps,
                               int stldet, int errconS, double* llh, double* sllh, int64_t* stats, double* y_out,
-                              double* sigmay_out, int* trace, double* x_preeq) {
+                              double* sigmay_out, int* trace, double* x_preeq, int newton_maxsteps) {
 #define DISPATCH_SS(NAME)                                                                                          \
     if (!std::strcmp(model, #NAME))                                                                                \
         return run_ss<models::Model_##NAME>(p_unscaled, k, k_preeq, reinit_mask, plist, ns, nt, t, my, sd, t0, rtol, \
                                             atol, maxsteps, stldet, errconS, llh, sllh, stats, y_out, sigmay_out,  \
-                                            trace, x_preeq);
+                                            trace, x_preeq, newton_maxsteps);
     DISPATCH_SS(steadystate)
     DISPATCH_SS(steadystate_scaled)
     DISPATCH_SS(boehm)

@@ -230,3 +230,43 @@ def test_bad_reinitialisation_index_is_an_error():
     tab.reinit_idx = [[0], [8]]  # nx = 8
     with pytest.raises(capi.B200LibraryError, match="index out of range"):
         B200SummedGradientFunction(tab)
+
+
+@pytest.mark.parametrize("newton_maxsteps,maxsteps", [(40, 10000), (2, 10000), (3, 150)], ids=["newton", "newton-fails-then-simulation", "retry"])
+def test_newtons_method_for_steady_states(oracle_available, newton_maxsteps, maxsteps):
+    """Newton's method first (the model's steady-state modes at integrateIfNewtonFails, newton_maxsteps > 0), the
+    simulation from its last trial point if it fails, Newton once more if the simulation fails:
+    deps/AMICI/src/steadystateproblem.cpp:120-166,628-715; newton_solver.cpp:43-125 (tests/test_host_steadystate.py has
+    the details per path)."""
+    tab = _problem("steadystate", 8, True, 1 if maxsteps < 1000 else 2)
+    tab.newton_maxsteps = newton_maxsteps
+    tab.maxsteps = maxsteps
+    tab.num_trials = 1
+    gpu, ora = _both(tab)
+    theta = synth.random_theta(tab, seed=1, width=0.3)
+    ro = ora.evaluate(theta)
+    st, fval, grad, _ = gpu.evaluate(theta)
+    res = gpu.condition_results()
+    assert np.array_equal(res["status"], ro["cond_status"])
+    ok = ro["cond_status"] == 0
+    assert np.any(ok)
+    assert_llh_close(res["llh"][ok], ro["llh"][ok])
+    for c in np.nonzero(ok)[0]:
+        assert_grad_close(res["sllh"][c], ro["sllh"][c], "per-condition sllh[%d]" % c)
+    assert st == ro["status"]
+    if st == 0:
+        assert_llh_close(fval, ro["fval"])
+        assert_grad_close(grad, ro["grad"])
+    st0, f0, _, _ = gpu.evaluate(theta, want_gradient=False)
+    ro0 = ora.evaluate(theta, want_grad=False)
+    assert st0 == ro0["status"]
+    if st0 == 0:
+        assert_llh_close(f0, ro0["fval"])
+
+
+def test_large_model_kernel_refuses_newton():
+    from parpe_b200.problem import B200SummedGradientFunction
+    tab = synth.make_problem("net32", 2, seed=0, timepoints=np.array([0.1, np.inf]))
+    tab.newton_maxsteps = 10
+    with pytest.raises(capi.B200LibraryError, match="Newton"):
+        B200SummedGradientFunction(tab)

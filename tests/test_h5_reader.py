@@ -121,10 +121,16 @@ def test_hierarchical_tables_and_preequilibration(tmp_path):
             assert got.reinit_idx[c] == list(ptab.reinit_idx[c])
         else:
             assert got.reinit_idx[c] == []
-    # Newton's method for steady states is not built: a file asking for it is refused, not simulated differently
+    # Newton's method for steady states: the reference uses it only if the MODEL's modes allow it (AMICI's default
+    # integrationOnly ignores newton_maxsteps); (2, 2) = integrateIfNewtonFails for both is built, others are refused
     p3 = tmp_path / "newton.h5"
     h5write_min.write_parpe_input(str(p3), ptab, attrs=dict(newton_maxsteps=np.int32(40)))
-    with pytest.raises(capi.B200LibraryError, match="newton_maxsteps"):
+    assert tables_from_hdf5(p3, "boehm").newton_maxsteps == 0
+    h5write_min.write_parpe_input(str(p3), ptab, attrs=dict(newton_maxsteps=np.int32(40), steadyStateComputationMode=np.int32(2),
+                                                           steadyStateSensitivityMode=np.int32(2)))
+    assert tables_from_hdf5(p3, "boehm").newton_maxsteps == 40
+    h5write_min.write_parpe_input(str(p3), ptab, attrs=dict(newton_maxsteps=np.int32(40), steadyStateComputationMode=np.int32(0)))
+    with pytest.raises(capi.B200LibraryError, match="steadyStateComputationMode"):
         tables_from_hdf5(p3, "boehm")
     with pytest.raises(capi.B200LibraryError):
         tables_from_hdf5(path, "no_such_model")

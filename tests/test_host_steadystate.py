@@ -245,3 +245,91 @@ def test_team_core_equilibration_failure_and_plain_instantiation(oracle_availabl
     lo, hi = tab.t_offsets[1], tab.t_offsets[2]
     r = simulate_team("net32", p, tab.k[1], plist, tab.t[lo:hi], tab.y_of(1), tab.sigma_of(1))
     assert r["status"] == SIM_ERROR and np.isnan(r["llh"])
+
+
+EDGE = [
+    ("steadystate", [np.inf], False),                       # nothing but post-equilibration, straight from t0
+    ("steadystate", [np.inf, np.inf], True),                # ... after a pre-equilibration
+    ("steadystate", [0.0, np.inf], False),                  # a data point at t0, then t = inf (no step taken yet)
+    ("steadystate", [0.0, 0.0, 1.0, 1.0, np.inf], True),    # repeated output times
+    ("boehm", [0.0, np.inf], True),
+    ("steadystate", [1e-3], True),                          # one early point after a pre-equilibration
+]
+
+
+@pytest.mark.parametrize("model,tp,preeq", EDGE, ids=["only-inf", "only-inf-preeq", "t0-inf", "repeats", "boehm-t0-inf", "early"])
+def test_steady_state_edge_cases(oracle_available, model, tp, preeq):
+    from oracle.binding import OracleProblem
+    tab = synth.make_problem(model, 3, seed=0, timepoints=np.array(tp, dtype=float), preeq=preeq)
+    theta = synth.random_theta(tab, seed=1, width=0.3)
+    ro = OracleProblem(tab).evaluate(theta)
+    assert ro["status"] == 0
+    for c in range(tab.n_conditions):
+        r = _host(tab, theta, c)
+        assert r["status"] == 0
+        assert_llh_close(r["llh"], ro["llh"][c])
+        assert_grad_close(r["sllh_sim"], ro["sllh"][c][:len(r["sllh_sim"])])
+
+
+# ---------------------------------------------------------------- Newton's method for steady states
+def _newton_problem(model, newton_maxsteps, maxsteps=10000, posteq=2):
+    tab, theta = _problem(model, preeq=True, posteq=posteq)
+    tab.newton_maxsteps = newton_maxsteps
+    tab.maxsteps = maxsteps
+    tab.num_trials = 1
+    return tab, theta
+
+
+def test_newton_finds_the_steady_states(oracle_available):
+    """newton_maxsteps = 40 with the model's modes at integrateIfNewtonFails: pre- and post-equilibration by damped
+    Newton iteration (SteadystateProblem::applyNewtonsMethod), sensitivities sx = -J^-1 dxdotdp
+    (NewtonSolver::computeNewtonSensis) -- no simulation step in either phase, on both sides."""
+    from oracle.binding import OracleProblem
+    tab, theta = _newton_problem("steadystate", 40)
+    ro = OracleProblem(tab).evaluate(theta, collect_stats=True)
+    assert ro["status"] == 0 and np.all(ro["stats"][:, 14] <= 0) and np.all(ro["stats"][:, 15] <= 0)
+    for c in range(tab.n_conditions):
+        r = _host(tab, theta, c, newton_maxsteps=40)
+        assert r["status"] == 0 and r["nst_preeq"] == 0
+        assert r["numsteps"][-1] == r["numsteps"][-3]  # no step after the last finite output time
+        assert_llh_close(r["llh"], ro["llh"][c])
+        assert_grad_close(r["sllh_sim"], ro["sllh"][c][:len(r["sllh_sim"])])
+    # cost only
+    ro0 = OracleProblem(tab).evaluate(theta, want_grad=False)
+    for c in range(tab.n_conditions):
+        assert_llh_close(_host(tab, theta, c, want_grad=False, newton_maxsteps=40)["llh"], ro0["llh"][c])
+
+
+def test_failed_newton_attempt_then_simulation_from_its_last_trial_point(oracle_available):
+    """Two Newton steps are too few: the pre-equilibration then SIMULATES from the last Newton trial point (the
+    reference sets the new solver up at state_.x, steadystateproblem.cpp:796-839) -- fewer steps than from x0 -- and
+    the post-equilibration's first convergence test reads that point too."""
+    from oracle.binding import OracleProblem
+    tab, theta = _newton_problem("steadystate", 2)
+    ro = OracleProblem(tab).evaluate(theta, collect_stats=True)
+    plain, _ = _problem("steadystate", preeq=True, posteq=2)
+    rp = OracleProblem(plain).evaluate(theta, collect_stats=True)
+    assert ro["status"] == 0
+    for c in range(tab.n_conditions):
+        r = _host(tab, theta, c, newton_maxsteps=2)
+        assert r["status"] == 0
+        assert_llh_close(r["llh"], ro["llh"][c])
+        assert_grad_close(r["sllh_sim"], ro["sllh"][c][:len(r["sllh_sim"])])
+        if tab.has_preeq[c]:
+            assert abs(r["nst_preeq"] - ro["stats"][c, 14]) <= 0.1 * ro["stats"][c, 14] + 2
+            assert ro["stats"][c, 14] < rp["stats"][c, 14]  # (the trial point is closer to the steady state than x0)
+
+
+def test_newton_retry_after_a_failed_simulation(oracle_available):
+    """maxsteps too small for the simulation to equilibrate: Newton's method once more from the last state the
+    simulation reached (findSteadyStateByNewtonsMethod(model, true)); same statuses and results as the reference."""
+    from oracle.binding import OracleProblem
+    tab, theta = _newton_problem("steadystate", 3, maxsteps=150, posteq=1)
+    ro = OracleProblem(tab).evaluate(theta, collect_stats=True)
+    assert np.any(ro["cond_status"] == 0) and np.any(ro["cond_status"] != 0)
+    for c in range(tab.n_conditions):
+        r = _host(tab, theta, c, newton_maxsteps=3)
+        assert r["status"] == ro["cond_status"][c]
+        if r["status"] == 0:
+            assert_llh_close(r["llh"], ro["llh"][c])
+            assert_grad_close(r["sllh_sim"], ro["sllh"][c][:len(r["sllh_sim"])])
