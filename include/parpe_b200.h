@@ -356,6 +356,9 @@ int pb200_h5_dataset_info(pb200_h5* f, const char* path, int* rank, int64_t* dim
 int64_t pb200_h5_read_double(pb200_h5* f, const char* path, double* out, int64_t capacity);
 /* the elements' bytes as stored (e.g. fixed-length strings); returns the byte count (out == NULL: count only) or < 0 */
 int64_t pb200_h5_read_raw(pb200_h5* f, const char* path, char* out, int64_t capacity);
+/* dataset of strings (fixed-length, or variable-length as h5py writes str arrays), newline separated; returns
+ * their number or < 0 */
+int pb200_h5_read_strings(pb200_h5* f, const char* path, char* buf, int capacity);
 /* numeric attribute of a group / dataset as doubles; returns the element count or < 0 */
 int pb200_h5_attribute_double(pb200_h5* f, const char* object, const char* name, double* out, int capacity);
 /* newline-separated names of a group's children; returns their number or < 0 */
@@ -366,6 +369,12 @@ typedef struct pb200_h5_problem pb200_h5_problem;
 int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_problem** out);
 const pb200_problem_desc* pb200_h5_problem_desc(pb200_h5_problem* p);
 const struct pb200_hier_desc* pb200_h5_problem_hier(pb200_h5_problem* p); /* NULL: no hierarchical tables */
+/* /parameters/{lowerBound, upperBound, nominalValues, parameterNames} of the file (what
+ * MultiConditionProblem::fillParametersMin / fillParametersMax and
+ * MultiConditionDataProviderHDF5::getProblemParameterIds read, multiConditionDataProvider.cpp:49-58,426-432):
+ * pointers into the object, NULL for a dataset the file does not have; names newline separated.  Returns n_opt. */
+int pb200_h5_problem_parameters(pb200_h5_problem* p, const double** lower, const double** upper,
+                                const double** nominal, const char** names);
 /* the arguments of pb200_set_preequilibration as read from the file; returns 1 if any condition is
  * pre-equilibrated (pointers into the object), else 0 */
 int pb200_h5_problem_preeq(pb200_h5_problem* p, const int32_t** has_preeq, const double** k_preeq,

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "pb200_h5_open", "pb200_h5_close", "pb200_h5_exists", "pb200_h5_dataset_info", "pb200_h5_read_double",
     "pb200_h5_attribute_double", "pb200_h5_list", "pb200_h5_read_raw", "pb200_h5_load_problem", "pb200_h5_problem_desc",
     "pb200_h5_problem_hier", "pb200_h5_problem_free", "pb200_create_from_hdf5", "pb200_set_preequilibration",
-    "pb200_h5_problem_preeq", "pb200_result_log_create", "pb200_result_log_destroy", "pb200_result_log_append",
+    "pb200_h5_problem_preeq", "pb200_h5_problem_parameters", "pb200_h5_read_strings", "pb200_result_log_create", "pb200_result_log_destroy", "pb200_result_log_append",
     "pb200_result_log_append_records", "pb200_result_log_num_records", "pb200_result_log_write",
     "pb200_write_simulation_results",
 ]
@@ -108,6 +108,8 @@ def lib():
     L.pb200_result_log_num_records.argtypes = [C.c_void_p, C.c_char_p]
     L.pb200_result_log_write.argtypes = [C.c_void_p, C.c_char_p]
     L.pb200_write_simulation_results.argtypes = [C.c_void_p, dp, C.c_int, C.c_char_p, C.c_char_p]
+    L.pb200_h5_problem_parameters.argtypes = [C.c_void_p, C.POINTER(dp), C.POINTER(dp), C.POINTER(dp), C.POINTER(C.c_char_p)]
+    L.pb200_h5_read_strings.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
     L.pb200_h5_problem_free.argtypes = [C.c_void_p]
     L.pb200_h5_problem_free.restype = None
     L.pb200_create_from_hdf5.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
@@ -239,13 +241,10 @@ class H5File:
         return dict(shape=tuple(int(dims[i]) for i in range(rank.value)), type_class=cls.value, type_size=size.value)
 
     def read_strings(self, path):
-        """fixed-length string dataset -> list of str"""
-        info = self.info(path)
-        n = int(np.prod(info["shape"])) if info["shape"] else 1
-        buf = C.create_string_buffer(n * info["type_size"] + 1)
-        check(lib().pb200_h5_read_raw(self._h, path.encode(), buf, len(buf)), "pb200_h5_read_raw")
-        sz = info["type_size"]
-        return [buf.raw[i * sz:(i + 1) * sz].split(b"\0")[0].decode() for i in range(n)]
+        """dataset of fixed- or variable-length strings -> list of str"""
+        buf = C.create_string_buffer(1 << 20)
+        n = check(lib().pb200_h5_read_strings(self._h, path.encode(), buf, len(buf)), "pb200_h5_read_strings")
+        return buf.value.decode().split("\n")[:n]
 
     def read(self, path):
         n = check(lib().pb200_h5_read_double(self._h, path.encode(), None, 0), "pb200_h5_read_double")

@@ -36,6 +36,10 @@ struct pb200_h5_problem {
     std::vector<int32_t> mapping, pscale_sim, pscale_opt;
     std::vector<int32_t> scaling_idx, offset_idx, sigma_idx, scaling_map, offset_map, sigma_map;
     // pre-equilibration (simulationConditions column 0, reinitializationIndices)
+    // /parameters/{lowerBound, upperBound, nominalValues, parameterNames} (what MultiConditionProblem's
+    // fillParametersMin / fillParametersMax and getProblemParameterIds read); empty when the file has none
+    std::vector<double> lower, upper, nominal;
+    std::string names;  // newline separated
     std::vector<int32_t> has_preeq, reinit_idx;
     std::vector<double> k_preeq;
     std::vector<int64_t> reinit_off;
@@ -256,6 +260,20 @@ int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_pro
             for (int c = 0; c < C; ++c)
                 for (int i = 0; i < np; ++i) P->overrides[(size_t)c * np + i] = O[(size_t)i * C + c];
         }
+        // ---- bounds, nominal values and names of the optimisation parameters (optional)
+        auto opt_vec = [&](const char* p, std::vector<double>& v) {
+            if (!f.exists(p)) return;
+            v = f.read_double(p);
+            if ((int)v.size() != n_opt) throw H5Error(std::string(p) + " must have one entry per optimisation parameter");
+        };
+        opt_vec("/parameters/lowerBound", P->lower);
+        opt_vec("/parameters/upperBound", P->upper);
+        opt_vec("/parameters/nominalValues", P->nominal);
+        if (f.exists("/parameters/parameterNames")) {
+            const auto nm = f.read_strings("/parameters/parameterNames");
+            if ((int)nm.size() != n_opt) throw H5Error("/parameters/parameterNames must have one entry per optimisation parameter");
+            for (auto& s : nm) { P->names += s; P->names += '\n'; }
+        }
         // ---- /amiciOptions attributes (deps/AMICI/src/hdf5.cpp readSolverSettingsFromHDF5)
         pb200_problem_desc& d = P->desc;
         d.abi_version = PB200_ABI_VERSION;
@@ -325,6 +343,33 @@ int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_pro
 }
 
 const pb200_problem_desc* pb200_h5_problem_desc(pb200_h5_problem* p) { return p ? &p->desc : nullptr; }
+int pb200_h5_problem_parameters(pb200_h5_problem* p, const double** lower, const double** upper, const double** nominal,
+                                const char** names) {
+    if (!p) return pb200::fail_message(PB200_ERR_ARG, "null argument");
+    if (lower) *lower = p->lower.empty() ? nullptr : p->lower.data();
+    if (upper) *upper = p->upper.empty() ? nullptr : p->upper.data();
+    if (nominal) *nominal = p->nominal.empty() ? nullptr : p->nominal.data();
+    if (names) *names = p->names.empty() ? nullptr : p->names.c_str();
+    return p->desc.n_opt;
+}
+int pb200_h5_read_strings(pb200_h5* h, const char* path, char* buf, int capacity) {
+    if (!h || !path) return pb200::fail_message(PB200_ERR_ARG, "null argument");
+    int n = 0;
+    const int rc = guarded([&] {
+        std::string all;
+        for (auto& s : h->f->read_strings(path)) {
+            all += s;
+            all += '\n';
+            ++n;
+        }
+        if (buf) {
+            if ((int)all.size() + 1 > capacity) throw H5Error(std::string(path) + ": output buffer too small");
+            std::memcpy(buf, all.c_str(), all.size() + 1);
+        }
+        return 0;
+    });
+    return rc < 0 ? rc : n;
+}
 int pb200_h5_problem_preeq(pb200_h5_problem* p, const int32_t** has_preeq, const double** k_preeq,
                            const int64_t** reinit_offsets, const int32_t** reinit_idx) {
     if (!p || !p->any_preeq) return 0;

@@ -46,9 +46,10 @@ class H5File {
         int type_class = -1;  // 0 fixed point, 1 floating point, 3 string (fixed length), 9 variable-length sequence
         int type_size = 0;
         bool type_signed = true;
-        // variable-length sequences (class 9): the element type (integers only)
+        // variable-length data (class 9): sequences of integers (the element type below) or strings
         int base_class = -1, base_size = 0;
         bool base_signed = true;
+        bool vlen_string = false;
         uint64_t count() const {
             uint64_t n = 1;
             for (auto d : dims) n *= d;
@@ -128,7 +129,8 @@ class H5File {
         uint64_t a;
         if (!locate(path, a)) throw H5Error("no such dataset: " + path);
         DsRaw r = dataset_raw(a, path);
-        if (r.d.type_class != 9 || r.d.base_class != 0) throw H5Error(path + ": not a dataset of variable-length integer sequences");
+        if (r.d.type_class != 9 || r.d.vlen_string || r.d.base_class != 0)
+            throw H5Error(path + ": not a dataset of variable-length integer sequences");
         if (r.d.type_size != (int)(4 + so_ + 4)) throw H5Error(path + ": unexpected size of a variable-length element");
         std::vector<uint8_t> raw = read_raw(r, path);
         std::vector<std::vector<int64_t>> out(r.d.count());
@@ -144,6 +146,38 @@ class H5File {
             if (nbytes < len * (uint64_t)r.d.base_size) throw H5Error(path + ": heap object shorter than the sequence");
             out[i].resize(len);
             for (uint64_t e = 0; e < len; ++e) out[i][e] = get_int(data + e * r.d.base_size, r.d.base_size, r.d.base_signed);
+        }
+        return out;
+    }
+
+    /// dataset of strings: fixed-length (class 3, null / space padded) or variable-length (h5py's default for str:
+    /// class 9 with the string bit; the characters live in global heap collections)
+    std::vector<std::string> read_strings(const std::string& path) const {
+        uint64_t a;
+        if (!locate(path, a)) throw H5Error("no such dataset: " + path);
+        DsRaw r = dataset_raw(a, path);
+        std::vector<uint8_t> raw = read_raw(r, path);
+        std::vector<std::string> out(r.d.count());
+        if (r.d.type_class == 3) {
+            for (size_t i = 0; i < out.size(); ++i) {
+                const char* p = reinterpret_cast<const char*>(raw.data() + i * r.d.type_size);
+                size_t len = strnlen(p, (size_t)r.d.type_size);
+                while (len > 0 && p[len - 1] == ' ') --len;  // (space-padded strings)
+                out[i].assign(p, len);
+            }
+        } else if (r.d.type_class == 9 && r.d.vlen_string) {
+            if (r.d.type_size != (int)(4 + so_ + 4)) throw H5Error(path + ": unexpected size of a variable-length element");
+            for (size_t i = 0; i < out.size(); ++i) {
+                const uint8_t* p = raw.data() + i * r.d.type_size;
+                const uint64_t len = rd(p, 4), coll = rd(p + 4, so_), index = rd(p + 4 + so_, 4);
+                if (len == 0 || coll == UNDEF || coll == 0) continue;
+                size_t nbytes = 0;
+                const uint8_t* data = global_heap_object(coll, index, nbytes, path);
+                if (nbytes < len) throw H5Error(path + ": heap object shorter than the string");
+                out[i].assign(reinterpret_cast<const char*>(data), strnlen(reinterpret_cast<const char*>(data), (size_t)len));
+            }
+        } else {
+            throw H5Error(path + ": not a dataset of strings");
         }
         return out;
     }
@@ -406,8 +440,12 @@ class H5File {
         } else if (d.type_class == 3) {
             // fixed-length string: readable as raw bytes only
         } else if (d.type_class == 9) {
-            // variable-length: sequences of integers only (strings: bits 0-3 of the class bit field = 1)
-            if ((p[1] & 0x0f) != 0) throw H5Error(what + ": variable-length strings are not supported");
+            // variable-length: strings (bits 0-3 of the class bit field = 1) or sequences of integers
+            if ((p[1] & 0x0f) == 1) {
+                d.vlen_string = true;
+                return;
+            }
+            if ((p[1] & 0x0f) != 0) throw H5Error(what + ": unknown variable-length type");
             if (n < 16) throw H5Error(what + ": short variable-length datatype message");
             Dataset base;
             parse_datatype(p + 8, n - 8, base, what + " (element type)");

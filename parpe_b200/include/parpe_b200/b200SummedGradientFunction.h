@@ -40,6 +40,7 @@ struct B200ProblemTables {
     std::vector<int32_t> pscaleOpt;           // [n_opt]
     std::vector<double> overrides;            // [C*np] or empty
     std::vector<std::string> parameterIds;    // /parameters/parameterNames
+    std::vector<double> lowerBound, upperBound, nominalValues;  // /parameters/{lowerBound,upperBound,nominalValues}
     // pre-equilibration (simulationConditions column 0, reinitializationIndices); hasPreeq empty = none
     std::vector<int32_t> hasPreeq;                        // [C]
     std::vector<double> kPreeq;                           // [C*nk]
@@ -331,6 +332,20 @@ inline B200ProblemTables B200ProblemTables::fromHdf5(std::string const& path, st
     T.maxSteps = d.maxsteps;
     T.stabilityLimitDetection = d.stldet != 0;
     T.newtonMaxSteps = d.newton_maxsteps;
+    {
+        const double* lo = nullptr; const double* up = nullptr; const double* nom = nullptr; const char* names = nullptr;
+        const int n = pb200_h5_problem_parameters(P, &lo, &up, &nom, &names);
+        if (lo) T.lowerBound.assign(lo, lo + n);
+        if (up) T.upperBound.assign(up, up + n);
+        if (nom) T.nominalValues.assign(nom, nom + n);
+        if (names) {
+            std::string cur;
+            for (const char* c = names; *c; ++c) {
+                if (*c == '\n') { T.parameterIds.push_back(cur); cur.clear(); }
+                else cur.push_back(*c);
+            }
+        }
+    }
     {
         const int32_t* flag = nullptr; const double* kp = nullptr; const int64_t* off = nullptr; const int32_t* idx = nullptr;
         if (pb200_h5_problem_preeq(P, &flag, &kp, &off, &idx)) {

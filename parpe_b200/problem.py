@@ -230,6 +230,12 @@ def tables_from_hdf5(path, model_name: str) -> ProblemTables:
                 scaling_map=arr(h.scaling_map, 3 * h.n_scaling_rows, np.int32),
                 offset_map=arr(h.offset_map, 3 * h.n_offset_rows, np.int32),
                 sigma_map=arr(h.sigma_map, 3 * h.n_sigma_rows, np.int32))
+        lo, up, nom, names = C.POINTER(C.c_double)(), C.POINTER(C.c_double)(), C.POINTER(C.c_double)(), C.c_char_p()
+        L.pb200_h5_problem_parameters(P, C.byref(lo), C.byref(up), C.byref(nom), C.byref(names))
+        tab.lower_bound = arr(lo, n_opt, np.float64) if lo else None
+        tab.upper_bound = arr(up, n_opt, np.float64) if up else None
+        tab.nominal_values = arr(nom, n_opt, np.float64) if nom else None
+        tab.parameter_names = names.value.decode().split("\n")[:n_opt] if names.value else None
         flag, kp = C.POINTER(C.c_int32)(), C.POINTER(C.c_double)()
         roff, ridx = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)()
         if L.pb200_h5_problem_preeq(P, C.byref(flag), C.byref(kp), C.byref(roff), C.byref(ridx)):

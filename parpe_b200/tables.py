@@ -133,6 +133,11 @@ class ProblemTables:
     has_preeq: Optional[np.ndarray] = None   # int32 [C]
     k_preeq: Optional[np.ndarray] = None     # float64 [C, nk]
     reinit_idx: Optional[list] = None        # C lists of state indices
+    # /parameters/{lowerBound, upperBound, nominalValues, parameterNames} (the optimisation problem's side of the file)
+    lower_bound: Optional[np.ndarray] = None
+    upper_bound: Optional[np.ndarray] = None
+    nominal_values: Optional[np.ndarray] = None
+    parameter_names: Optional[list] = None
 
     def preeq_args(self):
         """(has_preeq, k_preeq, reinit_offsets, reinit_idx) arrays for pb200_set_preequilibration, or None."""

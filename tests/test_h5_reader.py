@@ -136,6 +136,41 @@ def test_hierarchical_tables_and_preequilibration(tmp_path):
         tables_from_hdf5(path, "no_such_model")
 
 
+def test_parameter_names_bounds_and_nominal_values(tmp_path):
+    """/parameters/{parameterNames, lowerBound, upperBound, nominalValues}: what MultiConditionProblem's
+    fillParametersMin / fillParametersMax and getProblemParameterIds read (multiConditionDataProvider.cpp:49-58,
+    426-432); names as h5py writes a list of str (variable-length strings) and as fixed-length strings."""
+    import h5write_min
+    tab = synth.make_problem("boehm", 3, seed=1, condition_specific=2)
+    tab.lower_bound = np.linspace(-5, -3, tab.n_opt)
+    tab.upper_bound = np.linspace(3, 5, tab.n_opt)
+    tab.nominal_values = np.linspace(-1, 1, tab.n_opt)
+    tab.parameter_names = ["p%d_%s" % (j, "x" * (j % 4)) for j in range(tab.n_opt)]
+    path = tmp_path / "names.h5"
+    h5write_min.write_parpe_input(str(path), tab)
+    got = tables_from_hdf5(path, "boehm")
+    assert got.parameter_names == tab.parameter_names
+    assert np.array_equal(got.lower_bound, tab.lower_bound) and np.array_equal(got.upper_bound, tab.upper_bound)
+    assert np.array_equal(got.nominal_values, tab.nominal_values)
+    f = capi.H5File(path)
+    assert f.read_strings("/parameters/parameterNames") == tab.parameter_names
+    assert f.info("/parameters/parameterNames")["type_class"] == 9
+    # a file without them: None, not an error
+    plain = synth.make_problem("boehm", 2, seed=1)
+    p2 = tmp_path / "plain.h5"
+    h5write_min.write_parpe_input(str(p2), plain)
+    g2 = tables_from_hdf5(p2, "boehm")
+    assert g2.parameter_names is None and g2.nominal_values is None and g2.lower_bound is not None
+    # fixed-length strings (the result log's labels) through the same call
+    log = capi.ResultLog()
+    log.append_records("/multistarts/0", [3, 11], [1.0, 2.0], [0, 0], optimization_idx=2, iteration_idx=5)
+    p3 = tmp_path / "log.h5"
+    log.write(p3)
+    assert capi.H5File(p3).read_strings("/multistarts/0/simulationLabel") == ["o2i5c3", "o2i5c11"]
+    with pytest.raises(capi.B200LibraryError, match="strings"):
+        capi.H5File(p3).read_strings("/multistarts/0/jobId")
+
+
 @pytest.mark.gpu
 def test_handle_from_input_file_matches_handle_from_tables(tmp_path, oracle_available):
     import h5write_min

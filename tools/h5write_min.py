@@ -43,10 +43,15 @@ class Dataset:
 
 class VlenDataset:
     """1-D dataset of variable-length int32 sequences (h5py.vlen_dtype(np.int32)), e.g. parPE's
-    /fixedParameters/reinitializationIndices (python/parpe/hdf5_pe_input.py:430-437)."""
+    /fixedParameters/reinitializationIndices (python/parpe/hdf5_pe_input.py:430-437) -- or, with ``strings``, of
+    variable-length strings (what h5py writes for a list of str, e.g. /parameters/parameterNames)."""
 
-    def __init__(self, sequences):
-        self.sequences = [np.ascontiguousarray(s, dtype=np.int32) for s in sequences]
+    def __init__(self, sequences, strings=False):
+        self.strings = strings
+        if strings:
+            self.sequences = [np.frombuffer(s.encode(), dtype=np.uint8) for s in sequences]
+        else:
+            self.sequences = [np.ascontiguousarray(s, dtype=np.int32) for s in sequences]
         self.attrs = {}
 
 
@@ -67,10 +72,10 @@ class H5Writer:
         g = self.group("/".join(parts[:-1]))
         g.children[parts[-1]] = Dataset(data, chunks, compress)
 
-    def vlen_dataset(self, path, sequences):
+    def vlen_dataset(self, path, sequences, strings=False):
         parts = [p for p in path.split("/") if p]
         g = self.group("/".join(parts[:-1]))
-        g.children[parts[-1]] = VlenDataset(sequences)
+        g.children[parts[-1]] = VlenDataset(sequences, strings)
 
     def attr(self, path, name, value):
         self.group(path).attrs[name] = np.asarray(value)
@@ -137,8 +142,13 @@ class H5Writer:
         caddr = self._alloc(coll)
         elems = b"".join(struct.pack("<IQI", len(s), caddr if len(s) else 0, i + 1 if len(s) else 0)
                          for i, s in enumerate(d.sequences))
-        base = self._datatype(np.dtype(np.int32))
-        dtype = bytes([0x19, 0x00, 0x00, 0x00]) + struct.pack("<I", 16) + base
+        if d.strings:
+            # class 9, type "string" (bit field: type 1, padding null-terminated, ASCII); base type: 1-byte string
+            base = bytes([0x13, 0x00, 0x00, 0x00]) + struct.pack("<I", 1)
+            dtype = bytes([0x19, 0x01, 0x00, 0x00]) + struct.pack("<I", 16) + base
+        else:
+            base = self._datatype(np.dtype(np.int32))
+            dtype = bytes([0x19, 0x00, 0x00, 0x00]) + struct.pack("<I", 16) + base
         msgs = [self._message(0x0001, self._dataspace((len(d.sequences),))), self._message(0x0003, dtype)]
         addr = self._alloc(elems) if elems else UNDEF
         msgs.append(self._message(0x0008, struct.pack("<BBQQ", 3, 1, addr, len(elems))))
@@ -289,8 +299,14 @@ def write_parpe_input(path, tab, hier=None, compress=True, attrs=None):
               chunks=(np_, 1), compress=compress)
     w.dataset("/parameters/pscaleSimulation", np.asarray(tab.pscale_sim, dtype=np.int32))
     w.dataset("/parameters/pscaleOptimization", np.asarray(tab.pscale_opt, dtype=np.int32))
-    w.dataset("/parameters/lowerBound", np.full(tab.n_opt, -5.0))
-    w.dataset("/parameters/upperBound", np.full(tab.n_opt, 5.0))
+    w.dataset("/parameters/lowerBound", np.asarray(tab.lower_bound, dtype=np.float64)
+              if getattr(tab, "lower_bound", None) is not None else np.full(tab.n_opt, -5.0))
+    w.dataset("/parameters/upperBound", np.asarray(tab.upper_bound, dtype=np.float64)
+              if getattr(tab, "upper_bound", None) is not None else np.full(tab.n_opt, 5.0))
+    if getattr(tab, "nominal_values", None) is not None:
+        w.dataset("/parameters/nominalValues", np.asarray(tab.nominal_values, dtype=np.float64))
+    if getattr(tab, "parameter_names", None) is not None:
+        w.vlen_dataset("/parameters/parameterNames", list(tab.parameter_names), strings=True)
     if tab.overrides is not None:
         w.dataset("/parameters/parameterOverrides", np.asarray(tab.overrides, dtype=np.float64).T.copy(), chunks=(np_, 1),
                   compress=compress)
