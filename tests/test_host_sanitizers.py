@@ -4,7 +4,8 @@ compute-sanitizer is closed on the GPU pool (profiles/r02_sanitizer.log keeps it
 racecheck logs of the kernels cannot be produced.  What can be checked without it: the device cores compile for
 the host from the SAME source (one-lane group / one-thread team), so every index computation of the algorithm --
 history arrays, ELL Jacobian, blocked inversion, sparse factor tables and level lists, staging-area layouts of the
-fused passes, column batches -- runs here under ASan/UBSan with heap-allocated buffers of exactly the sizes the
+fused passes, column batches, the steady-state paths (pre-/post-equilibration, Newton's method and its linear
+solves in the group's scratch arrays) -- runs here under ASan/UBSan with heap-allocated buffers of exactly the sizes the
 kernels carve from HBM / shared memory; an out-of-bounds index in that logic aborts the run.  (Races between the
 threads of a block are outside what a one-thread build can see.)"""
 import os
@@ -47,6 +48,15 @@ TEAM_BODY = """
     hh.team_solve("chen", Jv, 0.3, rng.standard_normal((51, sp.nx)), sparse=True)
     hh.team_solve("chen", Jv, 0.3, rng.standard_normal((51, sp.nx)), sparse=True, stage_doubles=6000)
     hh.team_solve("net31", rng.standard_normal(get_spec("net31").nnz) * 0.1, 0.3, rng.standard_normal((6, 31)))
+    # steady-state instantiation: pre-equilibration + re-initialisation + a t = inf output time, both linear solvers
+    tp = np.array([0.1, 0.3, np.inf])
+    tab = synth.make_problem("net32", 3, seed=7, timepoints=tp, preeq=True)
+    for c in (0, 1, 2):
+        pre = bool(tab.has_preeq[c])
+        for kw in (dict(), dict(sparse=True)):
+            r = hh.simulate_team("net32", p, tab.k[c], list(range(spec.np)), tp, tab.y_of(c), tab.sigma_of(c), steady=True,
+                                 k_preeq=tab.k_preeq[c] if pre else None, reinit_idx=tab.reinit_idx[c] if pre else (), **kw)
+            assert r["status"] == 0, (c, kw, r["status"])
     print("ASAN-OK")
 """
 
@@ -65,6 +75,16 @@ SMALL_BODY = """
         assert r["status"] == 0, model
         r = hh.simulate(model, p, tab.k[0], [0, 2], tab.t, tab.y_of(0), tab.sigma_of(0))
         assert r["status"] == 0, model
+        # steady-state instantiation: pre-equilibration + re-initialisation + t = inf output times, by simulation and
+        # with Newton's method (first attempt, failed attempt + simulation, retry after a failed simulation)
+        tp = np.concatenate([np.asarray(tab.t[:4], dtype=float), [np.inf, np.inf]])
+        ts = synth.make_problem(model, 3, seed=3, timepoints=tp, preeq=True)
+        for c in (0, 1, 2):
+            pre = bool(ts.has_preeq[c])
+            for kw in (dict(), dict(newton_maxsteps=40), dict(newton_maxsteps=2), dict(newton_maxsteps=3, maxsteps=150)):
+                r = hh.simulate_ss(model, p, ts.k[c], list(range(spec.np)), tp, ts.y_of(c), ts.sigma_of(c),
+                                   k_preeq=ts.k_preeq[c] if pre else None, reinit_idx=ts.reinit_idx[c] if pre else (), **kw)
+                assert r["status"] in (0, -99, -1), (model, c, kw, r["status"])
     print("ASAN-OK")
 """
 
