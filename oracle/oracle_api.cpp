@@ -27,6 +27,11 @@
 #include "model_steadystate.h"
 #endif
 
+#ifdef PB200_ORACLE_WITH_PYGEN
+// models written by AMICI's python code generator at build time (parpe_b200/codegen/amici_pygen.py)
+std::unique_ptr<amici::Model> pb200_pygen_model(const std::string& name);
+#endif
+
 using namespace pb200_oracle;
 
 namespace {
@@ -43,6 +48,9 @@ std::unique_ptr<amici::Model> makeModel(const std::string& name) {
 #ifdef PB200_ORACLE_WITH_VENDORED
     if (name == "steadystate_vendored")
         return std::make_unique<amici::model_model_steadystate::Model_model_steadystate>();
+#endif
+#ifdef PB200_ORACLE_WITH_PYGEN
+    if (name.rfind("pygen_", 0) == 0) return pb200_pygen_model(name);
 #endif
     return nullptr;
 }

@@ -62,6 +62,7 @@ def _compile(src, obj, log):
 # AMICI-generated models of the reference tree that the back-end codegen/amici_import.py re-homes as device code at
 # build time (never committed: the output contains the reference's generated expressions)
 REFERENCE_MODELS = ["/root/reference/deps/AMICI/models/model_steadystate"]
+PYGEN_MODELS = [("steadystate", False), ("boehm", True)]
 
 
 def import_reference_models(verbose: bool = False):
@@ -77,6 +78,24 @@ def import_reference_models(verbose: bool = False):
         amici_import.import_model(d, name)
         if verbose:
             print("imported", d, "->", out)
+    # models written by AMICI's own python code generator (run in place from the reference tree) from the repo's
+    # symbolic descriptions: the python-generated layout, without and with repeating elements (w)
+    from .codegen import amici_pygen
+    if amici_pygen.available():
+        for model, with_w in PYGEN_MODELS:
+            name = "pygen_" + model + ("_w" if with_w else "")
+            src = os.path.join(amici_pygen.SRC_ROOT, name)
+            deps = [amici_pygen.__file__, os.path.join(HERE, "models", model + ".py")]
+            if not os.path.exists(os.path.join(src, name + ".h")) or \
+                    os.path.getmtime(os.path.join(src, name + ".h")) < max(os.path.getmtime(p) for p in deps):
+                amici_pygen.generate(model, with_w)
+                if verbose:
+                    print("generated", src)
+            out = os.path.join(amici_import.OUTDIR, name + ".cuh")
+            if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(os.path.join(src, name + ".h")),
+                                                                      os.path.getmtime(amici_import.__file__)):
+                amici_import.import_model(src, name)
+        amici_pygen.write_registry()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

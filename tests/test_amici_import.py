@@ -97,3 +97,78 @@ def test_cuda_path_with_the_imported_model(oracle_available):
     st1, f1, g1, _ = B200SummedGradientFunction(tab1).evaluate(theta)
     st2, f2, g2, _ = B200SummedGradientFunction(tab2).evaluate(theta)
     assert st1 == st2 == 0 and abs(f2 - f1) <= 1e-7 * abs(f1)
+
+
+# ---------------------------------------------------------------- the python-generated layout
+PYGEN = [("pygen_steadystate", "steadystate"), ("pygen_boehm_w", "boehm")]
+
+
+def _pygen_available(name):
+    return os.path.exists(os.path.join(os.path.dirname(IMPORTED), name + ".cuh"))
+
+
+def _pygen_problem(name, spec_model, **kw):
+    tab = synth.make_problem(spec_model, 4, seed=2, **kw)
+    theta = synth.random_theta(tab, seed=1, width=0.3)
+    tab.model_name = name  # same dimensions and parameter order: the generator was fed the repo's description
+    return tab, theta
+
+
+def test_amicis_python_generator_runs_here_and_its_output_is_imported(tmp_path):
+    """AMICI's own python code generator (amici.de_export.DEExporter, run in place from the reference tree with
+    libsbml / toposort / the SWIG extension stubbed) writes a model directory in the python-generated layout; the
+    back-end re-homes it: macros, sparse blocks, the chain rule through the repeating elements."""
+    from parpe_b200.codegen import amici_import, amici_pygen
+    if not amici_pygen.available():
+        pytest.skip("/root/reference not present")
+    src = amici_pygen.generate("steadystate", True, root=str(tmp_path / "src"))
+    assert os.path.exists(os.path.join(src, "dxdotdw.cpp")) and os.path.exists(os.path.join(src, "x0_fixedParameters.cpp"))
+    dims = amici_import.parse_dimensions(open(os.path.join(src, "pygen_steadystate_w.h")).read())
+    assert dims["nx_solver"] == 3 and dims["np"] == 5 and dims["nw"] > 0 and dims["ndxdotdw"] == dims["nw"]
+    text = open(amici_import.import_model(src, outdir=str(tmp_path / "out"))).read()
+    assert "struct Model_pygen_steadystate_w" in text and "NX = 3, NP = 5, NK = 4, NY = 3, NNZ = 9" in text
+    assert "X0K_MASK = 0x7u" in text and "DYN_MASK = 0x1fu" in text
+    assert "dxdotdw[" in text and "*dwdx[" in text and "*dwdp[" in text and "#define" in text and "#undef" in text
+
+
+@pytest.mark.parametrize("name,spec_model", PYGEN)
+@pytest.mark.parametrize("steady", [False, True], ids=["plain", "preeq+posteq"])
+def test_host_core_with_a_python_generated_model_matches_the_reference_running_it(oracle_available, name, spec_model,
+                                                                                  steady):
+    """The generated model through the device core (host build) against the SAME generated model compiled as an
+    amici::Model_ODE and run by the reference (pythonGenerated = true: Model_ODE assembles J and dxdotdp from the
+    sparse blocks; x0_fixedParameters re-initialises after pre-equilibration)."""
+    if not _pygen_available(name):
+        pytest.skip("no generated model in this build")
+    from oracle import binding as ob
+    from tests.host_harness.binding import simulate_ss
+    if not ob.lib().ora_has_model(name.encode()):
+        pytest.skip("oracle built without the generated models")
+    tab, theta = _pygen_problem(name, spec_model, preeq=steady, posteq=1 if steady else 0,
+                                scale="mixed", sigma_mode="mixed")
+    ro = ob.OracleProblem(tab).evaluate(theta)
+    assert ro["status"] == 0
+    for c in range(tab.n_conditions):
+        p, plist, fac = condition_inputs(tab, theta, c)
+        lo, hi = tab.t_offsets[c], tab.t_offsets[c + 1]
+        pre = steady and tab.has_preeq[c]
+        r = simulate_ss(name, p, tab.k[c], plist, tab.t[lo:hi], tab.y_of(c), tab.sigma_of(c),
+                        k_preeq=tab.k_preeq[c] if pre else None, reinit_idx=tab.reinit_idx[c] if pre else ())
+        assert r["status"] == 0
+        assert_llh_close(r["llh"], ro["llh"][c])
+        assert_grad_close(r["sllh"] * fac, ro["sllh"][c][:len(plist)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,spec_model", PYGEN)
+def test_cuda_path_with_a_python_generated_model(oracle_available, name, spec_model):
+    from oracle import binding as ob
+    from parpe_b200.problem import B200SummedGradientFunction
+    if name not in capi.models() or not ob.lib().ora_has_model(name.encode()):
+        pytest.skip("no generated model in this build")
+    tab, theta = _pygen_problem(name, spec_model, preeq=True, posteq=1, scale="mixed", sigma_mode="mixed")
+    ro = ob.OracleProblem(tab).evaluate(theta)
+    st, fval, grad, _ = B200SummedGradientFunction(tab).evaluate(theta)
+    assert st == ro["status"] == 0
+    assert_llh_close(fval, ro["fval"])
+    assert_grad_close(grad, ro["grad"])
