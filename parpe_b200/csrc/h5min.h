@@ -50,9 +50,10 @@ class H5File {
         int base_class = -1, base_size = 0;
         bool base_signed = true;
         bool vlen_string = false;
-        uint64_t count() const {
+        uint64_t count() const {  // (saturates instead of wrapping: a damaged dataspace must not look small)
             uint64_t n = 1;
-            for (auto d : dims) n *= d;
+            for (auto d : dims)
+                if (__builtin_mul_overflow(n, d, &n)) return ~(uint64_t)0;
             return n;
         }
     };
@@ -232,9 +233,20 @@ class H5File {
     static const uint64_t UNDEF = ~(uint64_t)0;
 
     const uint8_t* at(uint64_t addr, size_t need) const {
+        const uint64_t size = buf_.size();
+        if (addr == UNDEF || base_ > size || addr > size - base_) throw H5Error("address out of file");
         const uint64_t a = base_ + addr;
-        if (addr == UNDEF || a + need > buf_.size()) throw H5Error("address out of file");
+        if (need > size - a) throw H5Error("address out of file");
         return buf_.data() + a;
+    }
+    /// a damaged file must not walk B-trees forever (cycles): nodes visited per read
+    mutable uint64_t visits_ = 0;
+    void visit() const {
+        if (++visits_ > 2000000) throw H5Error("B-tree too large or cyclic");
+    }
+    /// p .. p + k must lie inside the message [m, m + n)
+    static void need(const uint8_t* p, size_t k, const uint8_t* m, size_t n, const std::string& what) {
+        if (p < m || (size_t)(p - m) > n || k > n - (size_t)(p - m)) throw H5Error(what + ": message too short");
     }
     static uint64_t rd(const uint8_t* p, int n) {
         uint64_t v = 0;
@@ -251,6 +263,7 @@ class H5File {
             if (off + 8 > buf_.size()) throw H5Error("not an HDF5 file (no signature)");
             if (!std::memcmp(buf_.data() + off, sig, 8)) break;
         }
+        if (off + 128 > buf_.size()) throw H5Error("truncated file (superblock)");  // (the largest superblock has 96 bytes)
         const uint8_t* p = buf_.data() + off + 8;
         const int ver = p[0];
         if (ver == 0 || ver == 1) {
@@ -347,6 +360,7 @@ class H5File {
 
     void btree_group(uint64_t node, uint64_t heap, std::map<std::string, uint64_t>& out, int depth = 0) const {
         if (depth > 32) throw H5Error("group B-tree too deep");
+        visit();
         const uint8_t* h = at(node, 8 + 2 * so_);
         if (std::memcmp(h, "TREE", 4) || h[4] != 0) throw H5Error("bad group B-tree node");
         const int level = h[5];
@@ -424,6 +438,8 @@ class H5File {
             q = p + 4;
         } else throw H5Error(what + ": unsupported dataspace version");
         d.dims.clear();
+        if (d.rank > 32) throw H5Error(what + ": dataspace rank");
+        need(q, (size_t)d.rank * sl_, p, n, what);
         for (int i = 0; i < d.rank; ++i) d.dims.push_back(rdl(q));
     }
     void parse_datatype(const uint8_t* p, size_t n, Dataset& d, const std::string& what) const {
@@ -466,25 +482,34 @@ class H5File {
             else if (m.type == 0x0003) { parse_datatype(m.p, m.n, r.d, what); have_type = true; }
             else if (m.type == 0x0008) {
                 const uint8_t* p = m.p;
+                need(p, 2, m.p, m.n, what);
                 if (p[0] != 3) throw H5Error(what + ": data layout message version " + std::to_string(p[0]) + " is not supported");
                 r.layout = p[1];
                 p += 2;
                 if (r.layout == 0) {
+                    need(p, 2, m.p, m.n, what);
                     r.size = rd(p, 2);
                     r.compact = p + 2;
+                    need(r.compact, (size_t)r.size, m.p, m.n, what);
                 } else if (r.layout == 1) {
+                    need(p, (size_t)so_ + sl_, m.p, m.n, what);
                     r.addr = rdo(p);
                     r.size = rdl(p);
                 } else if (r.layout == 2) {
+                    need(p, 1 + (size_t)so_, m.p, m.n, what);
                     const int dim = *p++;
                     r.btree = rdo(p);
+                    if (dim < 1 || dim > 33) throw H5Error(what + ": chunk rank");
+                    need(p, 4 * (size_t)(dim - 1), m.p, m.n, what);
                     for (int i = 0; i < dim - 1; ++i, p += 4) r.chunk.push_back((uint32_t)rd(p, 4));
                 } else throw H5Error(what + ": unknown layout class");
             } else if (m.type == 0x000B) {
                 const uint8_t* p = m.p;
+                need(p, 2, m.p, m.n, what);
                 const int ver = p[0], nf = p[1];
                 p += (ver == 1) ? 8 : 2;
                 for (int i = 0; i < nf; ++i) {
+                    need(p, 8, m.p, m.n, what);
                     const int id = (int)rd(p, 2);
                     p += 2;
                     int name_len = 0;
@@ -517,6 +542,7 @@ class H5File {
 
     void chunk_tree(uint64_t node, const DsRaw& r, std::vector<uint8_t>& out, const std::string& what, int depth = 0) const {
         if (depth > 32) throw H5Error(what + ": chunk B-tree too deep");
+        visit();
         const uint8_t* h = at(node, 8 + 2 * so_);
         if (std::memcmp(h, "TREE", 4) || h[4] != 1) throw H5Error(what + ": bad chunk B-tree node");
         const int level = h[5];
@@ -525,8 +551,16 @@ class H5File {
         const size_t keysz = 8 + 8 * (size_t)(rank + 1);
         const uint8_t* p = at(node + 8 + 2 * so_, (used + 1) * keysz + used * (size_t)so_);
         const size_t es = (size_t)r.d.type_size;
-        size_t chunk_elems = 1;
-        for (int i = 0; i < rank; ++i) chunk_elems *= r.chunk[i];
+        uint64_t chunk_elems64 = 1, chunk_bytes64 = 0;
+        for (int i = 0; i < rank; ++i)
+            if (r.chunk[i] == 0 || __builtin_mul_overflow(chunk_elems64, (uint64_t)r.chunk[i], &chunk_elems64))
+                throw H5Error(what + ": chunk dimensions");
+        // (a chunk is at most as large as the -- already bounded -- dataset, rounded up to whole chunks per dimension:
+        // bounded here by the output size times 2^rank, and absolutely)
+        if (__builtin_mul_overflow(chunk_elems64, (uint64_t)es, &chunk_bytes64) || chunk_bytes64 > ((uint64_t)1 << 31) ||
+            chunk_bytes64 > (uint64_t)buf_.size() * 1100u + (16u << 20))
+            throw H5Error(what + ": chunk larger than its file can hold");
+        const size_t chunk_elems = (size_t)chunk_elems64;
         for (unsigned i = 0; i < used; ++i) {
             const uint32_t csize = (uint32_t)rd(p, 4);
             const uint32_t fmask = (uint32_t)rd(p + 4, 4);
@@ -588,7 +622,15 @@ class H5File {
     }
 
     std::vector<uint8_t> read_raw(const DsRaw& r, const std::string& what) const {
-        const size_t bytes = (size_t)r.d.count() * r.d.type_size;
+        // size of the dataset in memory, bounded by what the file can hold (a damaged dataspace or datatype must end
+        // in an error, not in a huge allocation): contiguous / compact data are in the file as they are, chunks may be
+        // deflated (ratio bounded generously)
+        uint64_t bytes64 = 0;
+        if (r.d.type_size <= 0 || __builtin_mul_overflow(r.d.count(), (uint64_t)r.d.type_size, &bytes64))
+            throw H5Error(what + ": dataset size overflows");
+        const uint64_t limit = r.layout == 2 ? (uint64_t)buf_.size() * 1100u + (16u << 20) : (uint64_t)buf_.size();
+        if (bytes64 > limit) throw H5Error(what + ": dataset larger than its file can hold");
+        const size_t bytes = (size_t)bytes64;
         std::vector<uint8_t> out(bytes, 0);
         if (bytes == 0) return out;
         if (r.layout == 0) {
@@ -625,21 +667,28 @@ class H5File {
     }
 
     void parse_attr(const uint8_t* p, size_t n, std::string& name, Attr& a) const {
+        need(p, 9, p, n, "attribute");
         const int ver = p[0];
         if (ver < 1 || ver > 3) throw H5Error("unsupported attribute message version");
         const size_t name_sz = (size_t)rd(p + 2, 2), dt_sz = (size_t)rd(p + 4, 2), ds_sz = (size_t)rd(p + 6, 2);
         const uint8_t* q = p + 8;
         if (ver == 3) ++q;  // name character set
         auto pad = [&](size_t v) { return ver == 1 ? ((v + 7) & ~(size_t)7) : v; };
+        need(q, pad(name_sz), p, n, "attribute");
         name.assign(reinterpret_cast<const char*>(q), strnlen(reinterpret_cast<const char*>(q), name_sz));
         q += pad(name_sz);
+        need(q, pad(dt_sz), p, n, "attribute " + name);
         parse_datatype(q, dt_sz, a.d, "attribute " + name);
         q += pad(dt_sz);
-        if (q[0] == 1 && q[1] == 0 && ds_sz >= 8) { a.d.rank = 0; a.d.dims.clear(); }  // scalar (v1)
+        need(q, pad(ds_sz), p, n, "attribute " + name);
+        if (ds_sz >= 8 && q[0] == 1 && q[1] == 0) { a.d.rank = 0; a.d.dims.clear(); }  // scalar (v1)
         else parse_dataspace(q, ds_sz, a.d, "attribute " + name);
         q += pad(ds_sz);
         a.data = q;
-        if (q + a.d.count() * a.d.type_size > p + n) throw H5Error("attribute " + name + ": data overruns the message");
+        uint64_t nbytes = 0;
+        if (a.d.type_size <= 0 || __builtin_mul_overflow(a.d.count(), (uint64_t)a.d.type_size, &nbytes))
+            throw H5Error("attribute " + name + ": size overflows");
+        need(q, (size_t)nbytes, p, n, "attribute " + name + ": data");
     }
     bool find_attr(uint64_t addr, const std::string& name, Attr& a) const {
         for (auto& m : messages(addr))

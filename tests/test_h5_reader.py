@@ -205,3 +205,47 @@ def test_handle_from_input_file_matches_handle_from_tables(tmp_path, oracle_avai
     capi.check(capi.lib().pb200_create_from_hdf5(str(hp).encode(), b"fujita", 0, C.byref(h)), "pb200_create_from_hdf5")
     assert capi.lib().pb200_hier_num_outer(h) == htab.n_opt - len(htab.hier.inner_idx)
     capi.lib().pb200_destroy(h)
+
+
+def test_damaged_files_end_in_errors_not_in_out_of_bounds_reads(tmp_path):
+    """The reader parses files it did not write: truncated and bit-flipped copies of a parPE input file (chunked +
+    gzip datasets, variable-length sequences and strings, attributes) and of a result file go through every accessor
+    of h5min.h in an ASan/UBSan build; each must end in an H5Error or in data, never in a memory error."""
+    import subprocess
+    import h5write_min
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], stdout=subprocess.PIPE, text=True).stdout.strip()
+    if not (os.path.isabs(asan) and os.path.exists(asan)):
+        pytest.skip("libasan not available")
+    exe = str(tmp_path / "h5_robust")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                           "-o", exe, os.path.join(ROOT, "tests", "host_harness", "h5_robust.cpp"), "-ldl"])
+    tab = synth.make_problem("boehm", 5, seed=2, preeq=True, posteq=1, holes=1)
+    tab.parameter_names = ["p%d" % j for j in range(tab.n_opt)]
+    good = tmp_path / "good.h5"
+    h5write_min.write_parpe_input(str(good), tab)
+    log = capi.ResultLog()
+    log.append_records("/multistarts/0", [1, 2, 3], [1.0, 2.0, 3.0], [0, 0, -4], sllh=np.ones((3, 4)))
+    good2 = tmp_path / "good2.h5"
+    log.write(good2)
+    files = [str(good), str(good2)]
+    rng = np.random.default_rng(int(os.environ.get("PB200_FUZZ_SEED", "0")))
+    for src in (good, good2):
+        raw = bytearray(src.read_bytes())
+        for i in range(150):
+            b = bytearray(raw)
+            kind = i % 3
+            if kind == 0:   # truncation
+                b = b[:int(rng.integers(8, len(b)))]
+            elif kind == 1:  # a few flipped bytes anywhere
+                for pos in rng.integers(0, len(b), 4):
+                    b[pos] ^= int(rng.integers(1, 256))
+            else:           # an 8-byte field overwritten by a large number (addresses, sizes, counts)
+                pos = int(rng.integers(0, len(b) - 8))
+                b[pos:pos + 8] = int(rng.integers(0, 2 ** 62)).to_bytes(8, "little")
+            p = tmp_path / ("m_%s_%d.h5" % (src.stem, i))
+            p.write_bytes(bytes(b))
+            files.append(str(p))
+    r = subprocess.run([exe] + files, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600,
+                       env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1:allocator_may_return_null=1"))
+    assert r.returncode == 0 and "ROBUST-OK" in r.stdout, r.stdout[-500:] + r.stderr[-3000:]
+    assert "opened=" in r.stdout and int(r.stdout.split("datasets=")[1]) > 100
