@@ -219,6 +219,10 @@ def test_damaged_files_end_in_errors_not_in_out_of_bounds_reads(tmp_path):
     exe = str(tmp_path / "h5_robust")
     subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
                            "-o", exe, os.path.join(ROOT, "tests", "host_harness", "h5_robust.cpp"), "-ldl"])
+    # the writer (h5wmin.h) under the same sanitizers: every kind of object it emits, read back
+    w = subprocess.run([exe, "--write", str(tmp_path / "written.h5")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1"))
+    assert w.returncode == 0 and "WRITE-OK" in w.stdout, w.stdout + w.stderr[-2000:]
     tab = synth.make_problem("boehm", 5, seed=2, preeq=True, posteq=1, holes=1)
     tab.parameter_names = ["p%d" % j for j in range(tab.n_opt)]
     good = tmp_path / "good.h5"
