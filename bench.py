@@ -528,6 +528,20 @@ def main():
             mb = measure(rig, "boehm", nb, 5, 3, hetero=het, want_cost_only=False, sample_clocks=False)
             if rank == 0:
                 extra[key] = mb
+        # ... and its steady-state variant (three of four conditions pre-equilibrated, the last two output
+        # times t = inf -- the steady-state instantiation of the kernel; `--workload boehm --steady` as a line of its own)
+        was = STEADY
+        STEADY = True
+        try:
+            mb = measure(rig, "boehm", nb, 5, 3, hetero=False, want_cost_only=False, sample_clocks=False)
+            if rank == 0:
+                extra["boehm_steady"] = mb
+        except Exception as e:  # (an extra key must not cost the driver its line)
+            if world > 1:
+                raise
+            extra["boehm_steady_error"] = repr(e)
+        finally:
+            STEADY = was
     if rank == 0:
         peak_tf = rig.capi.measure_fp64_peak(rig.local_rank)
         peaks = {}
@@ -564,10 +578,16 @@ def main():
             "nllh": float(m["out_host"][0]), "failed_conditions": float(m["out_host"][1]), "wall_s": m["wall"],
         }
         for key, mb in extra.items():
+            if key.endswith("_error"):
+                line[key] = mb
+                continue
             rb = roofline_of(rig, "boehm", mb, peaks, peak_tf)
             line[key] = {"value": mb["value"], "unit": UNIT, "e2e": mb["e2e"], "steps": 5,
                          "workload": workload_name("boehm", DEFAULT_CONDITIONS["boehm"], world, mb["n_total"],
-                                                   key.endswith("heterogeneous")),
+                                                   key.endswith("heterogeneous")) +
+                                     ("; steady-state variant: 3 of 4 conditions pre-equilibrated, last two output times "
+                                      "t = inf (the integrator statistics count the main simulation only)"
+                                      if key.endswith("steady") else ""),
                          "roofline_frac_fp64": rb["fp64"]["frac"], "kernel_ms": rb["kernel_ms"],
                          "mean_nst": rb["mean_stats_per_solve"]["nst"], "failed_conditions": float(mb["out_host"][1])}
         if world == 1 and not args.no_cpu_baseline:
