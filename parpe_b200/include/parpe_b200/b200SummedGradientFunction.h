@@ -209,6 +209,15 @@ class B200SummedGradientFunction : public SummedGradientFunction<int> {
             throw std::runtime_error(std::string("pb200_nccl_init: ") + pb200_last_error());
     }
 
+    /// The standalone simulator's result datasets (src/parpeamici/standaloneSimulator.cpp:57-270; doc/hdf5.md:228-252):
+    /// llh, parameters, t/<m>, yMes/<m>, ySim/<m> under `group` of a new HDF5 file (pb200_write_simulation_results).
+    FunctionEvaluationStatus writeSimulationResults(gsl::span<const double> parameters, std::string const& path,
+                                                    std::string const& group = "/multistarts/0") const {
+        const int rc = pb200_write_simulation_results(handle_, parameters.data(), static_cast<int>(parameters.size()),
+                                                      path.c_str(), group.c_str());
+        if (rc < 0) throw std::runtime_error(std::string("pb200_write_simulation_results: ") + pb200_last_error());
+        return rc == PB200_EVAL_SUCCESS ? functionEvaluationSuccess : functionEvaluationFailure;
+    }
     pb200_handle* handle() const { return handle_; }
     const B200ProblemTables& tables() const { return tables_; }
 
@@ -223,6 +232,34 @@ class B200SummedGradientFunction : public SummedGradientFunction<int> {
 /// (nllh, #errors, gradient) combined by ONE ncclAllReduce inside the library.  evaluate() drives all
 /// devices (a host thread per extra device for the duration of the call) and returns the global
 /// result; Ipopt / Ceres / the minibatch optimizer use it like any parpe::SummedGradientFunction<int>.
+/// Per-simulation result logging: what parPE's logSimulation / saveSimulation writes per simulation job
+/// (src/parpeamici/multiConditionProblem.cpp:254-325; doc/hdf5.md:190-226), collected in memory after each
+/// evaluate() and written once (pb200_result_log_*).
+class B200ResultLog {
+  public:
+    B200ResultLog() {
+        if (pb200_result_log_create(&log_) != 0)
+            throw std::runtime_error(std::string("pb200_result_log_create: ") + pb200_last_error());
+    }
+    ~B200ResultLog() { pb200_result_log_destroy(log_); }
+    B200ResultLog(const B200ResultLog&) = delete;
+    B200ResultLog& operator=(const B200ResultLog&) = delete;
+    /// the per-condition results of `fun`'s last evaluate as records of `group`; returns their number
+    int append(B200SummedGradientFunction const& fun, std::string const& group, int optimizationIdx, int iterationIdx) {
+        const int n = pb200_result_log_append(log_, fun.handle(), group.c_str(), optimizationIdx, iterationIdx);
+        if (n < 0) throw std::runtime_error(std::string("pb200_result_log_append: ") + pb200_last_error());
+        return n;
+    }
+    int numRecords(std::string const& group) const { return pb200_result_log_num_records(log_, group.c_str()); }
+    void write(std::string const& path) const {
+        if (pb200_result_log_write(log_, path.c_str()) != 0)
+            throw std::runtime_error(std::string("pb200_result_log_write: ") + pb200_last_error());
+    }
+
+  private:
+    pb200_result_log* log_ = nullptr;
+};
+
 class B200MultiGpuSummedGradientFunction : public SummedGradientFunction<int> {
   public:
     B200MultiGpuSummedGradientFunction(B200ProblemTables const& tables, std::vector<int> const& devices) {
