@@ -141,7 +141,19 @@ typedef struct pb200_problem_desc {
      * 0 = steady state by simulation only: AMICI's defaults (both modes integrationOnly, with which the reference
      * ignores newton_maxsteps).  Small-model kernels only. */
     int32_t newton_maxsteps;
-    int32_t reserved[6];
+    /* /amiciOptions linsol (amici::LinearSolver, deps/AMICI/include/amici/defines.h; read by hdf5.cpp
+     * readSolverSettingsFromHDF5) as far as this path distinguishes linear solvers: 0 = automatic, 1 = dense
+     * (LinearSolver::dense / LAPACKDense: the dense inverse), 2 = sparse (LinearSolver::KLU / SuperLUMT: the
+     * fixed-pattern sparse LU with a dense Schur block).  The initial value of PB200_OPT_LINSOL; only the
+     * large-model kernels have a choice (the small-model kernels always invert densely). */
+    int32_t linsol;
+    /* 1 = steadyStateComputationMode newtonOnly (steadystateproblem.cpp:143-146: turnOffSimulation): Newton's
+     * method with newton_maxsteps steps at most and NO simulation to steady state if it fails -- the simulation
+     * then ends with AMICI_ERROR; sensitivities of the steady state by the linear solve (steadyStateSensitivityMode
+     * newtonOnly or integrateIfNewtonFails).  Needs newton_maxsteps > 0 (with 0 the reference runs neither method and
+     * fails every simulation: refused at pb200_create).  Small-model kernels only. */
+    int32_t newton_only;
+    int32_t reserved[4];
 } pb200_problem_desc;
 
 typedef struct pb200_handle pb200_handle;
@@ -192,7 +204,8 @@ void pb200_destroy(pb200_handle* h);
  *   reinit_offsets  [C+1], reinit_idx: ragged list of state indices per condition; NULL = none
  * Output times t = +inf in the problem table (post-equilibration) need no call: the data point is
  * evaluated at the steady state the simulation is carried on to (rdata.cpp:234-258).
- * Small-model kernels only; PB200_ERR_ARG for the large-model (network) kernels.
+ * Both kernel families (PB200_ERR_ARG for a model whose kernels were built without the steady-state
+ * instantiation); Newton's method for the small-model kernels only.
  */
 int pb200_set_preequilibration(pb200_handle* h, const int32_t* has_preeq, const double* k_preeq,
                                const int64_t* reinit_offsets, const int32_t* reinit_idx);

@@ -102,6 +102,7 @@ ora_problem* ora_create(const pb200_problem_desc* d, int ism, int linsol) {
         t.num_trials = d->num_trials;
         t.relaxation_factor = d->relaxation_factor;
         t.newton_maxsteps = d->newton_maxsteps;
+        t.newton_only = d->newton_only;
         t.ism = ism;
         t.linsol = linsol;
         model->setT0(d->t0);

@@ -62,7 +62,8 @@ Problem::Problem(std::unique_ptr<amici::Model> model, Tables tables)
     // steadyStateComputationMode / steadyStateSensitivityMode, deps/AMICI/src/hdf5.cpp:1433-1448).  The tables'
     // newton_maxsteps > 0 stands for "both modes integrateIfNewtonFails with this many Newton steps".
     if (tab_.newton_maxsteps > 0) {
-        model_->setSteadyStateComputationMode(amici::SteadyStateComputationMode::integrateIfNewtonFails);
+        model_->setSteadyStateComputationMode(tab_.newton_only ? amici::SteadyStateComputationMode::newtonOnly
+                                                               : amici::SteadyStateComputationMode::integrateIfNewtonFails);
         model_->setSteadyStateSensitivityMode(amici::SteadyStateSensitivityMode::integrateIfNewtonFails);
     }
 }

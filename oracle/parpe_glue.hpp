@@ -47,6 +47,7 @@ struct Tables {
     int num_trials = 6;
     double relaxation_factor = 100.0;
     int newton_maxsteps = 0;  // amici::Solver::setNewtonMaxSteps (AMICI default 0)
+    int newton_only = 0;      // 1 = steadyStateComputationMode newtonOnly (with newton_maxsteps > 0)
     int ism = 2;     // amici::InternalSensitivityMethod (1 simultaneous, 2 staggered)
     int linsol = 9;  // amici::LinearSolver (1 dense, 9 KLU)
 };

@@ -160,7 +160,12 @@ struct SolverOptions {
     int maxsteps;
     int stldet;
     int errconS;
-    int newton_maxsteps;  // steady states: Newton iterations tried before / after the simulation (AMICI default 0 = none)
+    // steady states: > 0 Newton iterations tried before / after the simulation (AMICI default 0 = none);
+    // < 0: Newton's method ONLY, with -newton_maxsteps iterations at most and no simulation if it fails
+    // (steadyStateComputationMode newtonOnly, steadystateproblem.cpp:143-146)
+    int newton_maxsteps;
+    PB_HD int newton_steps() const { return newton_maxsteps < 0 ? -newton_maxsteps : newton_maxsteps; }
+    PB_HD bool newton_only() const { return newton_maxsteps < 0; }
 };
 
 // ---- lane groups ---------------------------------------------------------------
@@ -1936,7 +1941,7 @@ struct Bdf {
                 if (one_step()) {
                     const double rtol_ss = 100.0 * opt.rtol, atol_ss = 100.0 * opt.atol;  // steady-state tolerances
                     const double* xchk = S()->zn[0];
-                    if (opt.newton_maxsteps > 0 && ss_newton_ == 0) {
+                    if (opt.newton_maxsteps != 0 && ss_newton_ == 0) {
                         // SteadystateProblem::findSteadyState (steadystateproblem.cpp:120-166): Newton's method first
                         // (newton_maxsteps > 0; AMICI's default 0 goes straight to the simulation).  Pre-equilibration:
                         // in place -- a simulation after a failed attempt starts from the last trial point, as the
@@ -1949,8 +1954,13 @@ struct Bdf {
                             g.sync();
                             PB_FOR_RANGE(e, 0, NX) x[e] = S()->zn[0][e];
                         }
-                        const int it = ss_newton_shared<M, Grp>(S(), g, tn, rtol_ss, atol_ss, opt.newton_maxsteps, false, x);
+                        const int it = ss_newton_shared<M, Grp>(S(), g, tn, rtol_ss, atol_ss, opt.newton_steps(), false, x);
                         if (it >= 0) { steady_found(it > 0, x); return; }
+                        if (opt.newton_only()) {  // turnOffSimulation: nothing else is tried (handleSteadyStateFailure)
+                            ss_newton_ = 2;
+                            finish(SIM_ERROR);
+                            return;
+                        }
                         xchk = x;  // the simulation's first convergence test reads the last Newton trial point
                     }
                     // one trip of SteadystateProblem::runSteadystateSimulation (steadystateproblem.cpp:711-794):

@@ -289,22 +289,81 @@ int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_pro
         d.rtol = opt("rtol", 1e-8);
         d.maxsteps = (int32_t)opt("maxsteps", 10000);
         d.stldet = (int32_t)opt("stldet", 1);
+        // Options that select an ALGORITHM (deps/AMICI/src/hdf5.cpp readSolverSettingsFromHDF5; enums in
+        // deps/AMICI/include/amici/defines.h).  What this path implements is accepted, what would change the results
+        // beyond the path's tolerance is refused with a message, never silently replaced:
+        //   lmm   2 = BDF (1 = Adams refused)             iter  2 = Newton (1 = functional refused)
+        //   ism   1 simultaneous / 2 staggered / 3 staggered1: accepted -- the sensitivity corrector is the staggered
+        //         one; the reference's own variants agree to ~1e-9, far inside the path's tolerance
+        //   sensi_meth / sensi_meth_preeq  1 forward, 2 adjoint (parPE's generator writes adjoint,
+        //         python/parpe/hdf5_pe_input.py:869-871): accepted -- the gradient is the same quantity and is always
+        //         computed by forward sensitivities here; sensi (order) is decided per evaluation by gradient.empty()
+        //   linsol  1 dense / 3 LAPACKDense -> dense; 9 KLU / 10 SuperLUMT -> sparse where the symbolic analysis allows
+        //         (automatic); band / diagonal / iterative solvers (2, 4..8) refused
+        //   ss_tol_factor, ss_tol_sensi_factor (100), ss_atol / ss_rtol / ss_atol_sensi / ss_rtol_sensi (unset),
+        //   check_sensi_steadystate_conv (1), newton_step_steadystate_conv (0), newton_damping_factor_mode (1 = on),
+        //   max_nonlin_iters (3), max_conv_fails (10), max_step_size (0), rtol_fsa / atol_fsa (unset): only AMICI's
+        //         defaults are built; a file that sets another value is refused when it matters (the steady-state
+        //         ones only with pre-/post-equilibration in the file)
+        //   interpType, nmaxevent, ordering, maxtime, maxstepsB, atolB / rtolB, quad_*: no role on this path
+        auto opt_int = [&](const char* name, int dflt) { return (int)std::llround(opt(name, (double)dflt)); };
+        auto refuse = [&](const char* name, const std::string& why) {
+            throw H5Error(std::string("/amiciOptions ") + name + " = " + std::to_string(opt(name, 0.0)) + ": " + why);
+        };
+        if (opt_int("lmm", 2) != 2) refuse("lmm", "only BDF (2) is implemented");
+        if (opt_int("iter", 2) != 2) refuse("iter", "only Newton iteration (2) is implemented");
+        { const int ism = opt_int("ism", 2); if (ism < 1 || ism > 3) refuse("ism", "not an InternalSensitivityMethod"); }
+        for (const char* nm : {"sensi_meth", "sensi_meth_preeq"}) {
+            const int v = opt_int(nm, 1);
+            if (v < 0 || v > 2) refuse(nm, "not a SensitivityMethod");
+        }
+        switch (opt_int("linsol", 9)) {
+        case 1: case 3: d.linsol = 1; break;   // LinearSolver::dense, LAPACKDense
+        case 9: case 10: d.linsol = 0; break;  // KLU, SuperLUMT: sparse where the pattern's fill allows (automatic)
+        default: refuse("linsol", "only the direct dense (1, 3) and sparse (9, 10) linear solvers have a counterpart");
+        }
+        if (opt_int("max_nonlin_iters", 3) != 3) refuse("max_nonlin_iters", "only CVODES' default 3 is implemented");
+        if (opt_int("max_conv_fails", 10) != 10) refuse("max_conv_fails", "only CVODES' default 10 is implemented");
+        if (opt("max_step_size", 0.0) != 0.0) refuse("max_step_size", "a maximum step size is not implemented");
+        for (const char* nm : {"rtol_fsa", "atol_fsa"})
+            if (f.has_attribute("/amiciOptions", nm) && opt(nm, 0.0) != (nm[0] == 'r' ? d.rtol : d.atol))
+                refuse(nm, "sensitivity tolerances other than rtol / atol are not implemented");
         // Steady states: Newton's method is used by the reference only when the MODEL's modes allow it
         // (/amiciOptions steadyStateComputationMode / steadyStateSensitivityMode: 0 newtonOnly, 1 integrationOnly --
         // AMICI's default for both --, 2 integrateIfNewtonFails; deps/AMICI/src/hdf5.cpp:1433-1448,
-        // steadystateproblem.cpp:120-166) and newton_maxsteps > 0.  Built: (1, 1 or 2) = by simulation, and (2, 2) =
-        // Newton first, simulation if it fails, Newton once more; other combinations are refused, not approximated.
+        // steadystateproblem.cpp:120-166) and newton_maxsteps > 0.  Built: (1, 1 or 2) = by simulation, (2, 2) =
+        // Newton first, simulation if it fails, Newton once more, and (0, 0 or 2) = Newton's method only (sensitivities
+        // by the linear solve at the steady state); other combinations are refused, not approximated.
         {
-            const int comp = (int)opt("steadyStateComputationMode", 1.0), sens = (int)opt("steadyStateSensitivityMode", 1.0);
-            const int nmax = (int)opt("newton_maxsteps", 0.0);
+            const int comp = opt_int("steadyStateComputationMode", 1), sens = opt_int("steadyStateSensitivityMode", 1);
+            const int nmax = opt_int("newton_maxsteps", 0);
             bool steady = P->any_preeq;
             for (double tv : P->t) steady = steady || std::isinf(tv);
             d.newton_maxsteps = 0;
+            d.newton_only = 0;
             if (comp == 2 && sens == 2) d.newton_maxsteps = nmax > 0 ? nmax : 0;
+            else if (comp == 0 && (sens == 0 || sens == 2) && nmax > 0) { d.newton_maxsteps = nmax; d.newton_only = 1; }
             else if (!(comp == 1 && (sens == 1 || sens == 2)) && steady)
                 throw H5Error("/amiciOptions steadyStateComputationMode = " + std::to_string(comp) +
                               ", steadyStateSensitivityMode = " + std::to_string(sens) + " with pre-/post-equilibration: "
-                              "only (1, 1|2) = steady state by simulation and (2, 2) = Newton first are supported");
+                              "only (1, 1|2) = steady state by simulation, (2, 2) = Newton first and (0, 0|2) with "
+                              "newton_maxsteps > 0 = Newton only are supported");
+            if (steady) {
+                if (opt("ss_tol_factor", 100.0) != 100.0) refuse("ss_tol_factor", "only AMICI's default 100 is implemented");
+                if (opt("ss_tol_sensi_factor", 100.0) != 100.0) refuse("ss_tol_sensi_factor", "only AMICI's default 100 is implemented");
+                for (const char* nm : {"ss_atol", "ss_rtol", "ss_atol_sensi", "ss_rtol_sensi"}) {
+                    // (unset = factor x the integration tolerance; a file may spell that default out)
+                    const double dflt = 100.0 * (std::strstr(nm, "atol") ? d.atol : d.rtol);
+                    if (f.has_attribute("/amiciOptions", nm) && opt(nm, dflt) != dflt)
+                        refuse(nm, "steady-state tolerances other than 100 x atol / rtol are not implemented");
+                }
+                if (opt_int("check_sensi_steadystate_conv", 1) != 1)
+                    refuse("check_sensi_steadystate_conv", "only the default (sensitivities are part of the convergence check) is implemented");
+                if (opt_int("newton_step_steadystate_conv", 0) != 0)
+                    refuse("newton_step_steadystate_conv", "the Newton-step convergence check is not implemented");
+                if (d.newton_maxsteps > 0 && opt_int("newton_damping_factor_mode", 1) != 1)
+                    refuse("newton_damping_factor_mode", "only the default damped Newton iteration is implemented");
+            }
         }
         d.sensi_errcon = 1;
         d.num_trials = 6;

@@ -460,7 +460,16 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
     a.opt.stldet = d->stldet;
     a.opt.errconS = d->sensi_errcon;
     a.opt.newton_maxsteps = d->newton_maxsteps > 0 ? d->newton_maxsteps : 0;
-    if (has_inf && a.opt.newton_maxsteps > 0 && !ops->supports_newton)
+    if (d->newton_only != 0) {
+        // steadyStateComputationMode newtonOnly: with newton_maxsteps = 0 the reference runs neither Newton's method
+        // nor the simulation (steadystateproblem.cpp:133-146) and every simulation fails -- a configuration error
+        if (d->newton_only != 1) return fail(PB200_ERR_ARG, "newton_only must be 0 or 1");
+        if (a.opt.newton_maxsteps <= 0) return fail(PB200_ERR_ARG, "newton_only needs newton_maxsteps > 0");
+        a.opt.newton_maxsteps = -a.opt.newton_maxsteps;  // (SolverOptions: negative = Newton's method only)
+    }
+    if (d->linsol < 0 || d->linsol > 2) return fail(PB200_ERR_ARG, "linsol: 0 automatic, 1 dense, 2 sparse");
+    h->opt_linsol = d->linsol;  // (PB200_OPT_LINSOL can still change it)
+    if (has_inf && a.opt.newton_maxsteps != 0 && !ops->supports_newton)
         return fail(PB200_ERR_ARG, "newton_maxsteps > 0 with t = inf output times: Newton's method for steady states is not "
                                    "supported for this model (only steady state by simulation, newton_maxsteps = 0)");
     a.num_trials = d->num_trials > 0 ? d->num_trials : 1;
@@ -507,7 +516,7 @@ int pb200_set_preequilibration(pb200_handle* h, const int32_t* has_preeq, const 
         return 0;
     }
     if (!h->ops->supports_steady) return fail(PB200_ERR_ARG, "pre-equilibration is not supported for this model");
-    if (a.opt.newton_maxsteps > 0 && !h->ops->supports_newton)
+    if (a.opt.newton_maxsteps != 0 && !h->ops->supports_newton)
         return fail(PB200_ERR_ARG, "newton_maxsteps > 0 with pre-equilibration: Newton's method for steady states is not "
                                    "supported for this model (only steady state by simulation, newton_maxsteps = 0)");
     if (!k_preeq && h->nk > 0) return fail(PB200_ERR_ARG, "k_preeq is null");

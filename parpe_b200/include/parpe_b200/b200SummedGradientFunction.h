@@ -52,6 +52,8 @@ struct B200ProblemTables {
     double integrationToleranceRelaxationFactor = 100.0; // PARPE_INTEGRATION_TOLERANCE_RELAXATION_FACTOR
     int lanesPerCondition = 0;
     int newtonMaxSteps = 0;  // amici::Solver::setNewtonMaxSteps (steady states; 0 = by simulation only)
+    bool newtonOnly = false; // steadyStateComputationMode newtonOnly: no simulation if Newton's method fails
+    int linearSolver = 0;    // large models: 0 automatic, 1 dense (LinearSolver::dense), 2 sparse (LinearSolver::KLU)
 
     /// The tables of a parPE parameter-estimation input file (doc/hdf5.md), assembled by the library's built-in
     /// HDF5 reader (pb200_h5_load_problem) -- what MultiConditionDataProviderHDF5 serves per condition, read once.
@@ -78,6 +80,8 @@ struct B200ProblemTables {
         d.relaxation_factor = integrationToleranceRelaxationFactor;
         d.lanes_per_condition = lanesPerCondition;
         d.newton_maxsteps = newtonMaxSteps;
+        d.newton_only = newtonOnly ? 1 : 0;
+        d.linsol = linearSolver;
         return d;
     }
 };
@@ -369,6 +373,8 @@ inline B200ProblemTables B200ProblemTables::fromHdf5(std::string const& path, st
     T.maxSteps = d.maxsteps;
     T.stabilityLimitDetection = d.stldet != 0;
     T.newtonMaxSteps = d.newton_maxsteps;
+    T.newtonOnly = d.newton_only != 0;
+    T.linearSolver = d.linsol;
     {
         const double* lo = nullptr; const double* up = nullptr; const double* nom = nullptr; const char* names = nullptr;
         const int n = pb200_h5_problem_parameters(P, &lo, &up, &nom, &names);

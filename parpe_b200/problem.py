@@ -220,7 +220,8 @@ def tables_from_hdf5(path, model_name: str) -> ProblemTables:
             pscale_opt=arr(d.pscale_opt, n_opt, np.int32),
             overrides=arr(d.overrides, Cn * np_, np.float64) if d.overrides else None, t0=d.t0, atol=d.atol, rtol=d.rtol,
             maxsteps=d.maxsteps, stldet=d.stldet, sensi_errcon=d.sensi_errcon, num_trials=d.num_trials,
-            relaxation_factor=d.relaxation_factor, newton_maxsteps=d.newton_maxsteps)
+            relaxation_factor=d.relaxation_factor, newton_maxsteps=d.newton_maxsteps, newton_only=d.newton_only,
+            linsol=d.linsol)
         hp = L.pb200_h5_problem_hier(P)
         if hp:
             h = hp.contents

@@ -46,7 +46,9 @@ class ProblemDesc(C.Structure):
         ("relaxation_factor", C.c_double),
         ("lanes_per_condition", C.c_int32),
         ("newton_maxsteps", C.c_int32),
-        ("reserved", C.c_int32 * 6),
+        ("linsol", C.c_int32),
+        ("newton_only", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -127,6 +129,8 @@ class ProblemTables:
     relaxation_factor: float = 100.0
     lanes_per_condition: int = 0
     newton_maxsteps: int = 0   # steady states: Newton iterations before / after the simulation (AMICI default 0)
+    newton_only: int = 0       # 1 = steadyStateComputationMode newtonOnly: no simulation if Newton's method fails
+    linsol: int = 0            # large models: 0 automatic, 1 dense, 2 sparse (initial value of PB200_OPT_LINSOL)
     hier: Optional[HierTables] = None
     # pre-equilibration (pb200_set_preequilibration): per simulation condition a flag, the constants of
     # the pre-equilibration condition and the states re-initialised afterwards
@@ -193,6 +197,7 @@ class ProblemTables:
         d.num_trials, d.relaxation_factor = self.num_trials, self.relaxation_factor
         d.lanes_per_condition = self.lanes_per_condition
         d.newton_maxsteps = self.newton_maxsteps
+        d.newton_only, d.linsol = self.newton_only, self.linsol
         return d
 
     # per-condition views in the reference's layout (row-major obs + it*ny)

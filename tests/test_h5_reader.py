@@ -132,8 +132,62 @@ def test_hierarchical_tables_and_preequilibration(tmp_path):
     h5write_min.write_parpe_input(str(p3), ptab, attrs=dict(newton_maxsteps=np.int32(40), steadyStateComputationMode=np.int32(0)))
     with pytest.raises(capi.B200LibraryError, match="steadyStateComputationMode"):
         tables_from_hdf5(p3, "boehm")
+    # newtonOnly computation mode (0, 0|2) with newton_maxsteps > 0: Newton's method without the simulation fallback
+    for sens in (0, 2):
+        h5write_min.write_parpe_input(str(p3), ptab, attrs=dict(newton_maxsteps=np.int32(40), steadyStateComputationMode=np.int32(0),
+                                                               steadyStateSensitivityMode=np.int32(sens)))
+        got = tables_from_hdf5(p3, "boehm")
+        assert got.newton_maxsteps == 40 and got.newton_only == 1
     with pytest.raises(capi.B200LibraryError):
         tables_from_hdf5(path, "no_such_model")
+
+
+def test_algorithm_selecting_options_are_honoured_or_refused(tmp_path):
+    """/amiciOptions attributes that select an algorithm (deps/AMICI/src/hdf5.cpp readSolverSettingsFromHDF5): what the
+    path implements is accepted -- parPE's own generator writes sensi_meth = adjoint and linsol = KLU
+    (python/parpe/hdf5_pe_input.py:859-879) --, the linear solver is mapped, anything that would change the results
+    beyond the path's tolerance is refused with the attribute's name in the message."""
+    import h5write_min
+    i32, f64 = np.int32, np.float64
+    tab = synth.make_problem("net32", 2, seed=3, scale="log10")
+    path = tmp_path / "opts.h5"
+
+    def load(t=tab, model="net32", **attrs):
+        h5write_min.write_parpe_input(str(path), t, attrs=attrs)
+        return tables_from_hdf5(path, model)
+
+    # what parPE's generator writes
+    got = load(linsol=i32(9), sensi=i32(1), sensi_meth=i32(2), sensi_meth_preeq=i32(2), steadyStateSensitivityMode=i32(1),
+               nmaxevent=i32(10), maxstepsB=i32(5000))
+    assert got.linsol == 0 and got.newton_maxsteps == 0 and got.newton_only == 0
+    # linear solvers: dense variants -> dense inverse, sparse direct -> automatic, the rest refused
+    assert load(linsol=i32(1)).linsol == 1 and load(linsol=i32(3)).linsol == 1 and load(linsol=i32(10)).linsol == 0
+    for v in (2, 4, 5, 6, 7, 8, 0, 11):
+        with pytest.raises(capi.B200LibraryError, match="linsol"):
+            load(linsol=i32(v))
+    # the sensitivity corrector variants and AMICI's defaults spelled out are accepted
+    for ism in (1, 2, 3):
+        load(ism=i32(ism))
+    load(lmm=i32(2), iter=i32(2), max_nonlin_iters=i32(3), max_conv_fails=i32(10), max_step_size=f64(0.0),
+         rtol_fsa=f64(tab.rtol), atol_fsa=f64(tab.atol), interpType=i32(1), ordering=i32(1))
+    for name, v in (("lmm", i32(1)), ("iter", i32(1)), ("ism", i32(4)), ("sensi_meth", i32(3)), ("max_nonlin_iters", i32(5)),
+                    ("max_conv_fails", i32(20)), ("max_step_size", f64(0.5)), ("rtol_fsa", f64(1e-4)), ("atol_fsa", f64(1e-6))):
+        with pytest.raises(capi.B200LibraryError, match=name):
+            load(**{name: v})
+    # steady-state options matter only for files with pre-/post-equilibration
+    assert load(ss_tol_factor=f64(10.0), newton_step_steadystate_conv=i32(1)).n_conditions == 2
+    ptab = synth.make_problem("boehm", 3, seed=2, preeq=True, posteq=1)
+    load(ptab, "boehm", ss_tol_factor=f64(100.0), ss_atol=f64(100.0 * ptab.atol), ss_rtol=f64(100.0 * ptab.rtol),
+         check_sensi_steadystate_conv=i32(1), newton_step_steadystate_conv=i32(0))
+    for name, v in (("ss_tol_factor", f64(10.0)), ("ss_tol_sensi_factor", f64(1.0)), ("ss_atol", f64(1e-9)), ("ss_rtol_sensi", f64(1e-3)),
+                    ("check_sensi_steadystate_conv", i32(0)), ("newton_step_steadystate_conv", i32(1))):
+        with pytest.raises(capi.B200LibraryError, match=name):
+            load(ptab, "boehm", **{name: v})
+    # the damping mode matters only when Newton's method is used
+    load(ptab, "boehm", newton_damping_factor_mode=i32(0))
+    with pytest.raises(capi.B200LibraryError, match="newton_damping_factor_mode"):
+        load(ptab, "boehm", newton_damping_factor_mode=i32(0), newton_maxsteps=i32(20), steadyStateComputationMode=i32(2),
+             steadyStateSensitivityMode=i32(2))
 
 
 def test_parameter_names_bounds_and_nominal_values(tmp_path):

@@ -76,12 +76,13 @@ SMALL_BODY = """
         r = hh.simulate(model, p, tab.k[0], [0, 2], tab.t, tab.y_of(0), tab.sigma_of(0))
         assert r["status"] == 0, model
         # steady-state instantiation: pre-equilibration + re-initialisation + t = inf output times, by simulation and
-        # with Newton's method (first attempt, failed attempt + simulation, retry after a failed simulation)
+        # with Newton's method (first attempt, failed attempt + simulation, retry after a failed simulation, Newton only)
         tp = np.concatenate([np.asarray(tab.t[:4], dtype=float), [np.inf, np.inf]])
         ts = synth.make_problem(model, 3, seed=3, timepoints=tp, preeq=True)
         for c in (0, 1, 2):
             pre = bool(ts.has_preeq[c])
-            for kw in (dict(), dict(newton_maxsteps=40), dict(newton_maxsteps=2), dict(newton_maxsteps=3, maxsteps=150)):
+            for kw in (dict(), dict(newton_maxsteps=40), dict(newton_maxsteps=2), dict(newton_maxsteps=3, maxsteps=150),
+                       dict(newton_maxsteps=-40), dict(newton_maxsteps=-2)):  # (negative = Newton's method only)
                 r = hh.simulate_ss(model, p, ts.k[c], list(range(spec.np)), tp, ts.y_of(c), ts.sigma_of(c),
                                    k_preeq=ts.k_preeq[c] if pre else None, reinit_idx=ts.reinit_idx[c] if pre else (), **kw)
                 assert r["status"] in (0, -99, -1), (model, c, kw, r["status"])

@@ -333,3 +333,34 @@ def test_newton_retry_after_a_failed_simulation(oracle_available):
         if r["status"] == 0:
             assert_llh_close(r["llh"], ro["llh"][c])
             assert_grad_close(r["sllh_sim"], ro["sllh"][c][:len(r["sllh_sim"])])
+
+
+def test_newton_only_mode(oracle_available):
+    """steadyStateComputationMode newtonOnly (turnOffSimulation, steadystateproblem.cpp:143-146): with enough Newton
+    steps the results of `Newton first`; with too few there is NO simulation to fall back on -- the simulation ends
+    with AMICI_ERROR on both sides, condition by condition (the conditions that start in their steady state or need
+    no pre-equilibration and converge within the budget still succeed)."""
+    from oracle.binding import OracleProblem
+    tab, theta = _newton_problem("steadystate", 40)
+    tab.newton_only = 1
+    ro = OracleProblem(tab).evaluate(theta, collect_stats=True)
+    assert ro["status"] == 0 and np.all(ro["stats"][:, 14] <= 0) and np.all(ro["stats"][:, 15] <= 0)
+    for c in range(tab.n_conditions):
+        r = _host(tab, theta, c, newton_maxsteps=-40)  # (SolverOptions: negative = Newton's method only)
+        assert r["status"] == 0 and r["nst_preeq"] == 0
+        assert_llh_close(r["llh"], ro["llh"][c])
+        assert_grad_close(r["sllh_sim"], ro["sllh"][c][:len(r["sllh_sim"])])
+    for nmax in (1, 2, 4):
+        tab, theta = _newton_problem("steadystate", nmax)
+        tab.newton_only = 1
+        ro = OracleProblem(tab).evaluate(theta, collect_stats=True)
+        for c in range(tab.n_conditions):
+            r = _host(tab, theta, c, newton_maxsteps=-nmax)
+            assert r["status"] == ro["cond_status"][c], (nmax, c)
+            if r["status"] == 0:
+                assert_llh_close(r["llh"], ro["llh"][c])
+                assert_grad_close(r["sllh_sim"], ro["sllh"][c][:len(r["sllh_sim"])])
+            else:
+                assert r["status"] == SIM_ERROR and np.isnan(r["llh"])
+        if nmax <= 2:
+            assert np.any(ro["cond_status"] != 0)  # (the case is exercised: too few steps do fail somewhere)
