@@ -153,7 +153,14 @@ typedef struct pb200_problem_desc {
      * newtonOnly or integrateIfNewtonFails).  Needs newton_maxsteps > 0 (with 0 the reference runs neither method and
      * fails every simulation: refused at pb200_create).  Small-model kernels only. */
     int32_t newton_only;
-    int32_t reserved[4];
+    /* 1 = steadyStateSensitivityMode newtonOnly together with a SIMULATION to steady state (computation mode
+     * integrationOnly, or integrateIfNewtonFails with newton_maxsteps > 0 for `Newton first`): the simulation runs
+     * without the sensitivity columns (Solver::switchForwardSensisOff, steadystateproblem.cpp:728-736) and the
+     * sensitivities of the steady state come from the linear solve sx = -J^-1 dxdotdp (newton_solver.cpp:52-84;
+     * a singular Jacobian is AMICI_ERROR).  0 = sensitivities integrated along (integrationOnly /
+     * integrateIfNewtonFails).  Small-model kernels only. */
+    int32_t steady_sens_newton;
+    int32_t reserved[3];
 } pb200_problem_desc;
 
 typedef struct pb200_handle pb200_handle;
@@ -197,7 +204,8 @@ void pb200_destroy(pb200_handle* h);
  * from that steady state (and its sensitivities), and the listed states whose initial value depends
  * on the constants are reset to their initial value.  AMICI's defaults are implemented -- steady
  * state by simulation, sensitivities integrated along, convergence check on the sensitivities on --
- * and, with pb200_problem_desc::newton_maxsteps > 0, Newton's method first (small-model kernels).
+ * and, with pb200_problem_desc::newton_maxsteps > 0, Newton's method first; newton_only and
+ * steady_sens_newton select the model's other steady-state modes (small-model kernels).
  *   has_preeq       [C]     1 = condition c is pre-equilibrated; NULL switches pre-equilibration off
  *   k_preeq         [C*nk]  constants of the pre-equilibration condition (rows of conditions
  *                           without one are ignored)

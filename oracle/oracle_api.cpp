@@ -103,6 +103,7 @@ ora_problem* ora_create(const pb200_problem_desc* d, int ism, int linsol) {
         t.relaxation_factor = d->relaxation_factor;
         t.newton_maxsteps = d->newton_maxsteps;
         t.newton_only = d->newton_only;
+        t.steady_sens_newton = d->steady_sens_newton;
         t.ism = ism;
         t.linsol = linsol;
         model->setT0(d->t0);

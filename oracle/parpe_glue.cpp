@@ -66,6 +66,10 @@ Problem::Problem(std::unique_ptr<amici::Model> model, Tables tables)
                                                                : amici::SteadyStateComputationMode::integrateIfNewtonFails);
         model_->setSteadyStateSensitivityMode(amici::SteadyStateSensitivityMode::integrateIfNewtonFails);
     }
+    // steady_sens_newton: sensitivity mode newtonOnly; with newton_maxsteps = 0 the computation mode stays at AMICI's
+    // default integrationOnly (steady state by simulation without sensitivities, then the linear solve)
+    if (tab_.steady_sens_newton)
+        model_->setSteadyStateSensitivityMode(amici::SteadyStateSensitivityMode::newtonOnly);
 }
 
 // multiConditionDataProvider.cpp:84-102 (column `c` of optimizationSimulationMapping)

@@ -48,6 +48,7 @@ struct Tables {
     double relaxation_factor = 100.0;
     int newton_maxsteps = 0;  // amici::Solver::setNewtonMaxSteps (AMICI default 0)
     int newton_only = 0;      // 1 = steadyStateComputationMode newtonOnly (with newton_maxsteps > 0)
+    int steady_sens_newton = 0;  // 1 = steadyStateSensitivityMode newtonOnly
     int ism = 2;     // amici::InternalSensitivityMethod (1 simultaneous, 2 staggered)
     int linsol = 9;  // amici::LinearSolver (1 dense, 9 KLU)
 };

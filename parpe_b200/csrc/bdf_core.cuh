@@ -159,7 +159,12 @@ struct SolverOptions {
     double rtol, atol;
     int maxsteps;
     int stldet;
+    // bit 0: sensitivities take part in the error test (AMICI forces 1, solver.cpp:646).  Bit 1 (steady-state
+    // instantiation only, set by pb200_create together with bit 0): steadyStateSensitivityMode newtonOnly -- a
+    // simulation to steady state runs WITHOUT the sensitivities, which are solved for at the steady state
+    // (steadystateproblem.cpp:728-736, 91-103)
     int errconS;
+    PB_HD bool ss_sens_by_solve() const { return (errconS & 2) != 0; }
     // steady states: > 0 Newton iterations tried before / after the simulation (AMICI default 0 = none);
     // < 0: Newton's method ONLY, with -newton_maxsteps iterations at most and no simulation if it fails
     // (steadyStateComputationMode newtonOnly, steadystateproblem.cpp:143-146)
@@ -929,6 +934,27 @@ struct Bdf {
     int ss_mode_;
     int ss_newton_;  // Newton attempts of the current steady-state phase: 0 none yet, 1 first done, 2 retry done,
                      // 3 retry requested (the simulation has just failed)
+    // steadyStateSensitivityMode newtonOnly: the sensitivity columns are switched off for the current steady-state
+    // phase (Solver::switchForwardSensisOff -> CVodeSensToggleOff); ns_full_ = their number
+    bool sens_off_;
+    int ns_full_;
+    PB_HD void sens_toggle_off() {
+        if (!SS || !opt.ss_sens_by_solve() || !sensi) return;
+        ns_full_ = ns;
+        ns = 0;
+        ncol = 1;
+        sensi = false;
+        sens_off_ = true;
+    }
+    /// true if the columns had been off (and are integrated / evaluated again from here on)
+    PB_HD bool sens_back_on() {
+        if (!SS || !sens_off_) return false;
+        ns = ns_full_;
+        ncol = ns + 1;
+        sensi = true;
+        sens_off_ = false;
+        return true;
+    }
     /// true while CVode is driven in CV_ONE_STEP mode without a stop time (Solver::step,
     /// deps/AMICI/src/solver.cpp:161-175): simulation to steady state
     PB_HD bool one_step() const { return SS && ss_mode_ != SS_OFF; }
@@ -1865,6 +1891,13 @@ struct Bdf {
                 S()->b[e] = 0.0;
             }
         }
+        if (SS) {
+            // (pre-equilibration in sensitivity mode newtonOnly: the simulation's solver is created without
+            // sensitivities, createSteadystateSimSolver steadystateproblem.cpp:796-839; sx0 is set above because a
+            // Newton attempt that starts in the steady state leaves the sensitivities at their initial values)
+            sens_off_ = false;
+            if (ss_mode_ == SS_PREEQ) sens_toggle_off();
+        }
         PB_UNROLL
         for (int j = 0; j < cv::L_MAX; ++j) l[j] = 0.0;
         tq1 = tq2 = tq3 = tq4 = tq5 = 0.0;
@@ -1926,7 +1959,10 @@ struct Bdf {
                         // output time, forwardproblem.cpp:149-150).  Without steady-state support an error, never a
                         // silently dropped point.
                         if (!SS) { finish(SIM_ERROR); return; }
-                        if (ss_mode_ != SS_POSTEQ) ss_newton_ = 0;
+                        if (ss_mode_ != SS_POSTEQ) {
+                            ss_newton_ = 0;
+                            sens_toggle_off();  // (the solver carries on without them, :728-736)
+                        }
                         ss_mode_ = SS_POSTEQ;
                         break;
                     }
@@ -1996,6 +2032,15 @@ struct Bdf {
     /// The steady state is reached: every t = inf output time is evaluated there
     /// (ReturnData::processPostEquilibration, rdata.cpp:234-258); a pre-equilibration just ends.
     PB_HD void steady_success() {
+        if (sens_back_on()) {
+            // the simulation ran without the sensitivities: sx = -J^-1 dxdotdp at the steady state
+            // (getSensitivityFlag(newtonSensi), workSteadyStateProblem :91-103)
+            if (ss_newton_sensis_shared<M, Grp>(S(), g, tn, ns)) {
+                ss_newton_ = 2;
+                finish(SIM_ERROR);
+                return;
+            }
+        }
         if (ss_mode_ == SS_POSTEQ) {
             while (it_ < io_.nt) {
                 tout_ = io_.t[it_];
@@ -2013,6 +2058,7 @@ struct Bdf {
         g.sync();
         if (x != S()->zn[0]) PB_FOR_RANGE(e, 0, NX) S()->zn[0][e] = x[e];
         g.sync();
+        sens_back_on();
         if (sensi && newton_sensis) {
             if (ss_newton_sensis_shared<M, Grp>(S(), g, tn, ns)) {
                 ss_newton_ = 2;

@@ -8,6 +8,7 @@
 // (hierarchicalOptimizationAnalyticalParameterProvider.cpp: /{scaling,offset,sigma}ParameterIndices and
 // ...MapToObservables), reading the layout of doc/hdf5.md:1-172 once, at create time.  The file is parsed by
 // h5min.h (no HDF5 library in this image).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -328,26 +329,41 @@ int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_pro
         for (const char* nm : {"rtol_fsa", "atol_fsa"})
             if (f.has_attribute("/amiciOptions", nm) && opt(nm, 0.0) != (nm[0] == 'r' ? d.rtol : d.atol))
                 refuse(nm, "sensitivity tolerances other than rtol / atol are not implemented");
-        // Steady states: Newton's method is used by the reference only when the MODEL's modes allow it
-        // (/amiciOptions steadyStateComputationMode / steadyStateSensitivityMode: 0 newtonOnly, 1 integrationOnly --
-        // AMICI's default for both --, 2 integrateIfNewtonFails; deps/AMICI/src/hdf5.cpp:1433-1448,
-        // steadystateproblem.cpp:120-166) and newton_maxsteps > 0.  Built: (1, 1 or 2) = by simulation, (2, 2) =
-        // Newton first, simulation if it fails, Newton once more, and (0, 0 or 2) = Newton's method only (sensitivities
-        // by the linear solve at the steady state); other combinations are refused, not approximated.
+        // Steady states (/amiciOptions steadyStateComputationMode / steadyStateSensitivityMode: 0 newtonOnly,
+        // 1 integrationOnly -- AMICI's default for both --, 2 integrateIfNewtonFails; newton_maxsteps;
+        // deps/AMICI/src/hdf5.cpp:1433-1448).  SteadystateProblem::findSteadyState (steadystateproblem.cpp:120-166)
+        // with forward sensitivities: Newton's method is OFF with computation mode 1, newton_maxsteps = 0 or --
+        // for evaluations with gradient -- sensitivity mode 1; the simulation is OFF with computation mode 0.
+        //   (1, 1|2), (2, 1|2) with newton_maxsteps = 0   steady state by simulation, sensitivities integrated along
+        //   (1, 0),   (2, 0)   with newton_maxsteps = 0   ... simulated without them, solved for at the steady state
+        //   (2, 2) / (2, 0) with newton_maxsteps > 0      Newton first, simulation if it fails, Newton once more
+        //   (0, 0|2) with newton_maxsteps > 0             Newton's method only
+        // Refused (only when the file has pre-/post-equilibration; never approximated): (2, 1) with newton_maxsteps > 0
+        // (evaluations with gradient would simulate, those without would try Newton first), (0, 1) (the reference
+        // throws, steadystateproblem.cpp:73-84) and computation mode 0 without Newton steps (nothing would run).
         {
             const int comp = opt_int("steadyStateComputationMode", 1), sens = opt_int("steadyStateSensitivityMode", 1);
-            const int nmax = opt_int("newton_maxsteps", 0);
+            const int nmax = std::max(0, opt_int("newton_maxsteps", 0));
             bool steady = P->any_preeq;
             for (double tv : P->t) steady = steady || std::isinf(tv);
             d.newton_maxsteps = 0;
             d.newton_only = 0;
-            if (comp == 2 && sens == 2) d.newton_maxsteps = nmax > 0 ? nmax : 0;
-            else if (comp == 0 && (sens == 0 || sens == 2) && nmax > 0) { d.newton_maxsteps = nmax; d.newton_only = 1; }
-            else if (!(comp == 1 && (sens == 1 || sens == 2)) && steady)
+            d.steady_sens_newton = 0;
+            bool ok = comp >= 0 && comp <= 2 && sens >= 0 && sens <= 2;
+            if (ok && comp == 0) {
+                ok = nmax > 0 && sens != 1;
+                if (ok) { d.newton_maxsteps = nmax; d.newton_only = 1; }
+            } else if (ok) {
+                const int n = comp == 2 ? nmax : 0;  // (computation mode 1 ignores newton_maxsteps)
+                ok = !(n > 0 && sens == 1);
+                if (ok) { d.newton_maxsteps = n; d.steady_sens_newton = sens == 0 ? 1 : 0; }
+            }
+            if (!steady) d.newton_maxsteps = d.newton_only = d.steady_sens_newton = 0;  // (no role without steady states)
+            else if (!ok)
                 throw H5Error("/amiciOptions steadyStateComputationMode = " + std::to_string(comp) +
-                              ", steadyStateSensitivityMode = " + std::to_string(sens) + " with pre-/post-equilibration: "
-                              "only (1, 1|2) = steady state by simulation, (2, 2) = Newton first and (0, 0|2) with "
-                              "newton_maxsteps > 0 = Newton only are supported");
+                              ", steadyStateSensitivityMode = " + std::to_string(sens) + ", newton_maxsteps = " +
+                              std::to_string(nmax) + " with pre-/post-equilibration: this combination is not supported "
+                              "(see the table in csrc/h5input.cu)");
             if (steady) {
                 if (opt("ss_tol_factor", 100.0) != 100.0) refuse("ss_tol_factor", "only AMICI's default 100 is implemented");
                 if (opt("ss_tol_sensi_factor", 100.0) != 100.0) refuse("ss_tol_sensi_factor", "only AMICI's default 100 is implemented");

@@ -164,6 +164,7 @@ struct pb200_handle {
     // tuning options (pb200_set_option; never read from the environment)
     int opt_variant = 2, opt_ctas_per_sm = 0, opt_sync_period = 1, opt_stage_sync = 0, opt_partial_sums = 0;
     int opt_linsol = 0, opt_order_refresh = 16, opt_fuse_off = 0;
+    bool steady_sens_newton = false;  // pb200_problem_desc::steady_sens_newton
     int evals_since_order = 0;
     int64_t last_h2d = 0, last_d2h = 0;
     // large-model path: device tables + workspace (ModelOps::create_state)
@@ -468,6 +469,17 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
         a.opt.newton_maxsteps = -a.opt.newton_maxsteps;  // (SolverOptions: negative = Newton's method only)
     }
     if (d->linsol < 0 || d->linsol > 2) return fail(PB200_ERR_ARG, "linsol: 0 automatic, 1 dense, 2 sparse");
+    if (d->steady_sens_newton != 0) {
+        if (d->steady_sens_newton != 1) return fail(PB200_ERR_ARG, "steady_sens_newton must be 0 or 1");
+        if (!a.opt.errconS) return fail(PB200_ERR_ARG, "steady_sens_newton needs sensi_errcon = 1 (AMICI forces it)");
+        // (the mode matters only where a steady state is computed: refused for a model without Newton's linear
+        // solve once the problem has t = inf output times -- here -- or gets a pre-equilibration -- there)
+        h->steady_sens_newton = true;
+        if (ops->supports_newton) a.opt.errconS = 3;  // (SolverOptions::errconS bit 1)
+        else if (has_inf)
+            return fail(PB200_ERR_ARG, "steady_sens_newton with t = inf output times: the linear solve for the sensitivities "
+                                       "of a steady state is not supported for this model");
+    }
     h->opt_linsol = d->linsol;  // (PB200_OPT_LINSOL can still change it)
     if (has_inf && a.opt.newton_maxsteps != 0 && !ops->supports_newton)
         return fail(PB200_ERR_ARG, "newton_maxsteps > 0 with t = inf output times: Newton's method for steady states is not "
@@ -516,6 +528,9 @@ int pb200_set_preequilibration(pb200_handle* h, const int32_t* has_preeq, const 
         return 0;
     }
     if (!h->ops->supports_steady) return fail(PB200_ERR_ARG, "pre-equilibration is not supported for this model");
+    if (h->steady_sens_newton && !h->ops->supports_newton)
+        return fail(PB200_ERR_ARG, "steady_sens_newton with pre-equilibration: the linear solve for the sensitivities of a "
+                                   "steady state is not supported for this model");
     if (a.opt.newton_maxsteps != 0 && !h->ops->supports_newton)
         return fail(PB200_ERR_ARG, "newton_maxsteps > 0 with pre-equilibration: Newton's method for steady states is not "
                                    "supported for this model (only steady state by simulation, newton_maxsteps = 0)");

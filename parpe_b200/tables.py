@@ -48,7 +48,8 @@ class ProblemDesc(C.Structure):
         ("newton_maxsteps", C.c_int32),
         ("linsol", C.c_int32),
         ("newton_only", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("steady_sens_newton", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -130,6 +131,7 @@ class ProblemTables:
     lanes_per_condition: int = 0
     newton_maxsteps: int = 0   # steady states: Newton iterations before / after the simulation (AMICI default 0)
     newton_only: int = 0       # 1 = steadyStateComputationMode newtonOnly: no simulation if Newton's method fails
+    steady_sens_newton: int = 0  # 1 = steadyStateSensitivityMode newtonOnly with a simulation to steady state
     linsol: int = 0            # large models: 0 automatic, 1 dense, 2 sparse (initial value of PB200_OPT_LINSOL)
     hier: Optional[HierTables] = None
     # pre-equilibration (pb200_set_preequilibration): per simulation condition a flag, the constants of
@@ -197,7 +199,7 @@ class ProblemTables:
         d.num_trials, d.relaxation_factor = self.num_trials, self.relaxation_factor
         d.lanes_per_condition = self.lanes_per_condition
         d.newton_maxsteps = self.newton_maxsteps
-        d.newton_only, d.linsol = self.newton_only, self.linsol
+        d.newton_only, d.linsol, d.steady_sens_newton = self.newton_only, self.linsol, self.steady_sens_newton
         return d
 
     # per-condition views in the reference's layout (row-major obs + it*ny)

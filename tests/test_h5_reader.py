@@ -138,6 +138,27 @@ def test_hierarchical_tables_and_preequilibration(tmp_path):
                                                                steadyStateSensitivityMode=np.int32(sens)))
         got = tables_from_hdf5(p3, "boehm")
         assert got.newton_maxsteps == 40 and got.newton_only == 1
+    # the whole table of (computation mode, sensitivity mode, newton_maxsteps) -> what runs (csrc/h5input.cu;
+    # SteadystateProblem::findSteadyState, deps/AMICI/src/steadystateproblem.cpp:120-166)
+    table = {  # (comp, sens, nmax): (newton_maxsteps, newton_only, steady_sens_newton) or None = refused
+        (1, 1, 0): (0, 0, 0), (1, 2, 30): (0, 0, 0), (1, 0, 30): (0, 0, 1), (2, 0, 0): (0, 0, 1), (2, 1, 0): (0, 0, 0),
+        (2, 2, 30): (30, 0, 0), (2, 0, 30): (30, 0, 1), (2, 1, 30): None, (0, 0, 30): (30, 1, 0), (0, 2, 30): (30, 1, 0),
+        (0, 1, 30): None, (0, 0, 0): None, (3, 1, 0): None, (1, 3, 0): None}
+    for (comp, sens, nmax), want in table.items():
+        h5write_min.write_parpe_input(str(p3), ptab, attrs=dict(newton_maxsteps=np.int32(nmax), steadyStateComputationMode=np.int32(comp),
+                                                               steadyStateSensitivityMode=np.int32(sens)))
+        if want is None:
+            with pytest.raises(capi.B200LibraryError, match="steadyStateComputationMode"):
+                tables_from_hdf5(p3, "boehm")
+        else:
+            got = tables_from_hdf5(p3, "boehm")
+            assert (got.newton_maxsteps, got.newton_only, got.steady_sens_newton) == want, (comp, sens, nmax)
+    # ... which has no role in a file without steady states
+    plain = synth.make_problem("boehm", 3, seed=2)
+    h5write_min.write_parpe_input(str(p3), plain, attrs=dict(newton_maxsteps=np.int32(30), steadyStateComputationMode=np.int32(0),
+                                                             steadyStateSensitivityMode=np.int32(1)))
+    got = tables_from_hdf5(p3, "boehm")
+    assert (got.newton_maxsteps, got.newton_only, got.steady_sens_newton) == (0, 0, 0)
     with pytest.raises(capi.B200LibraryError):
         tables_from_hdf5(path, "no_such_model")
 

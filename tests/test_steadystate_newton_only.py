@@ -1,7 +1,9 @@
-"""steadyStateComputationMode newtonOnly on the GPU (pb200_problem_desc::newton_only; SteadystateProblem::
-findSteadyState with turnOffSimulation, deps/AMICI/src/steadystateproblem.cpp:120-166) through the C ABI against the
-reference, and the descriptor's checks.  The per-path CPU parity of the same integrator source is
-tests/test_host_steadystate.py::test_newton_only_mode.
+"""The steady-state modes `newtonOnly` on the GPU through the C ABI against the reference, and the descriptor's
+checks: steadyStateComputationMode newtonOnly (pb200_problem_desc::newton_only; SteadystateProblem::findSteadyState
+with turnOffSimulation, deps/AMICI/src/steadystateproblem.cpp:120-166) and steadyStateSensitivityMode newtonOnly
+(pb200_problem_desc::steady_sens_newton; the simulation to steady state runs without the sensitivity columns,
+:728-736, which are solved for at the steady state, :91-103).  The per-path CPU parity of the same integrator source
+is tests/test_host_steadystate.py::test_newton_only_mode / test_sensitivity_mode_newton_only.
 
 NOTE: written after the round's GPU budget was spent -- the CPU parity of the integrator core (same source, host
 build) is green, the GPU cases of this file have not run on a B200 yet.  (This file sorts after the other test
@@ -70,3 +72,46 @@ def test_newton_only_descriptor_checks_need_no_device():
     assert d.newton_only == 1 and d.newton_maxsteps == 0 and d.linsol == 0
     tab.linsol = 2
     assert tab.to_desc().linsol == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("newton_maxsteps", [0, 2], ids=["simulation", "newton-fails-then-simulation"])
+def test_sensitivities_of_steady_states_by_the_linear_solve(oracle_available, newton_maxsteps):
+    """steady_sens_newton: pre- and post-equilibration simulated without the sensitivity columns (fewer steps than
+    with them in the error test -- the reference's counts), sx = -J^-1 dxdotdp at each steady state."""
+    from tests.test_gpu_steadystate import _both, _problem as base
+    tab = base("steadystate_scaled", 6, True, 2, scale="mixed", sigma_mode="mixed")
+    tab.steady_sens_newton = 1
+    tab.newton_maxsteps = newton_maxsteps
+    gpu, ora = _both(tab)
+    theta = synth.random_theta(tab, seed=1, width=0.3)
+    ro = ora.evaluate(theta, collect_stats=True)
+    st, fval, grad, _ = gpu.evaluate(theta)
+    res = gpu.condition_results()
+    assert ro["status"] == 0 and st == 0 and np.all(res["status"] == 0)
+    assert_llh_close(fval, ro["fval"])
+    assert_grad_close(grad, ro["grad"])
+    for c in range(tab.n_conditions):
+        assert_grad_close(res["sllh"][c], ro["sllh"][c], "per-condition sllh[%d]" % c)
+    # the plain mode integrates the sensitivities along and needs more steps for the same problem
+    tab.steady_sens_newton = 0
+    tab.newton_maxsteps = 0
+    plain, _ = _both(tab)
+    st2, f2, g2, _ = plain.evaluate(theta)
+    assert st2 == 0
+    assert_llh_close(f2, fval)
+    nst, nst_plain = gpu.condition_results()["stats"][:, 0], plain.condition_results()["stats"][:, 0]
+    assert np.sum(nst) < np.sum(nst_plain)
+
+
+@pytest.mark.gpu
+def test_large_model_kernel_refuses_the_linear_solve_for_steady_state_sensitivities():
+    from parpe_b200.problem import B200SummedGradientFunction
+    tab = synth.make_problem("net32", 2, seed=0, timepoints=np.array([0.1, np.inf]))
+    tab.steady_sens_newton = 1
+    with pytest.raises(capi.B200LibraryError, match="steady_sens_newton"):
+        B200SummedGradientFunction(tab)
+    # without steady states in the problem the flag has no role
+    tab = synth.make_problem("net32", 2, seed=0)
+    tab.steady_sens_newton = 1
+    assert B200SummedGradientFunction(tab).evaluate(synth.random_theta(tab, seed=1, width=0.3))[0] == 0
