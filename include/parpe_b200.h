@@ -160,7 +160,13 @@ typedef struct pb200_problem_desc {
      * a singular Jacobian is AMICI_ERROR).  0 = sensitivities integrated along (integrationOnly /
      * integrateIfNewtonFails).  Small-model kernels only. */
     int32_t steady_sens_newton;
-    int32_t reserved[3];
+    /* /amiciOptions ism (amici::InternalSensitivityMethod, CVodeSensInit1's ism): 0 or 2 = staggered -- the
+     * path's corrector (north star: forward, staggered); 1 = simultaneous (CV_SIMULTANEOUS: state and
+     * sensitivities in one Newton iteration and one error test, cvodes_nls_sim.c) -- small-model kernels only,
+     * run by their full-feature (steady-state) instantiation; PB200_ERR_ARG for the large-model kernels.  AMICI's
+     * own default is simultaneous; the variants agree to ~1e-9 relative. */
+    int32_t ism;
+    int32_t reserved[2];
 } pb200_problem_desc;
 
 typedef struct pb200_handle pb200_handle;

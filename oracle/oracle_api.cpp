@@ -104,7 +104,7 @@ ora_problem* ora_create(const pb200_problem_desc* d, int ism, int linsol) {
         t.newton_maxsteps = d->newton_maxsteps;
         t.newton_only = d->newton_only;
         t.steady_sens_newton = d->steady_sens_newton;
-        t.ism = ism;
+        t.ism = d->ism == 1 ? 1 : ism;  // (the descriptor's request for the simultaneous corrector wins)
         t.linsol = linsol;
         model->setT0(d->t0);
         auto* h = new ora_problem;

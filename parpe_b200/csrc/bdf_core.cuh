@@ -163,8 +163,11 @@ struct SolverOptions {
     // instantiation only, set by pb200_create together with bit 0): steadyStateSensitivityMode newtonOnly -- a
     // simulation to steady state runs WITHOUT the sensitivities, which are solved for at the steady state
     // (steadystateproblem.cpp:728-736, 91-103)
+    // Bit 2 (steady-state instantiation only, with bit 0): the SIMULTANEOUS corrector (CV_SIMULTANEOUS, AMICI's
+    // InternalSensitivityMethod::simultaneous) instead of the staggered one.
     int errconS;
     PB_HD bool ss_sens_by_solve() const { return (errconS & 2) != 0; }
+    PB_HD bool simultaneous() const { return (errconS & 4) != 0; }
     // steady states: > 0 Newton iterations tried before / after the simulation (AMICI default 0 = none);
     // < 0: Newton's method ONLY, with -newton_maxsteps iterations at most and no simulation if it fails
     // (steadyStateComputationMode newtonOnly, steadystateproblem.cpp:143-146)
@@ -1336,6 +1339,79 @@ struct Bdf {
         }
     }
 
+    /// The simultaneous corrector (steady-state instantiation only): cvNls with do_sensi_sim (cvodes.c:6894-7007),
+    /// SUNNonlinSolSolve_Newton on the wrapped vector (state, sensitivities) with cvNlsResidualSensSim /
+    /// cvNlsLSolveSensSim / cvNlsConvTestSensSim (cvodes_nls_sim.c:374-560): every iteration evaluates f at the
+    /// current state iterate and the sensitivity right-hand sides at the current (state, sensitivity) iterates --
+    /// AMICI's fsxdot re-evaluates J and dxdotdp there (model_ode.cpp:486-515) --, solves all columns with the same
+    /// matrix, and tests the MAXIMUM of the columns' WRMS norms (cvSensUpdateNorm); one convergence rate, one
+    /// iteration counter (nni), acnrm = the joint norm when the sensitivities take part in the error test.
+    PB_HD int nls_simultaneous(int nflag) {
+        const int cmax = ns;
+        convfail = ((nflag == cv::FIRST_CALL) || (nflag == cv::PREV_ERR_FAIL)) ? cv::NO_FAILURES : cv::FAIL_OTHER;
+        bool setup_pending = (nflag == cv::PREV_CONV_FAIL) || (nflag == cv::PREV_ERR_FAIL) || (nst == 0) ||
+                             (nst >= nstlp + cv::MSBP) || (fabs(gamrat - 1.0) > cv::DGMAX_LSETUP);
+        PB_FOR_RANGE(e, 0, (cmax + 1) * NX) S()->acor[e] = 0.0;
+        bool jbad = false;
+        bool top = true;
+        int m_it = 0;
+        for (;;) {
+            int ret = rhs(PH_STATE, tn, false);  // (S()->yj = the state iterate)
+            if (ret == 0) {
+                g.sync();
+                PB_FOR_ROWS0(r, i) S()->ysh[i] = S()->yj[i];
+                refresh_Jcur(tn);
+                ret = rhs(PH_SENS, tn, false);
+            }
+            if (ret != 0 && top) return ret;
+            if (ret == 0 && setup_pending) {
+                if (jbad) convfail = cv::FAIL_BAD_J;
+                const int lr = lsetup();  // Jacobian at S()->yj
+                setup_pending = false;
+                jcurNLS = jcur;
+                gamrat = 1.0;
+                gammap = gamma;
+                crate = 1.0;
+                crateS = 1.0;
+                nstlp = nst;
+                if (lr != 0) return cv::CONV_RECVR;
+            }
+            top = false;
+            if (ret == 0) {
+                nni++;
+                const double del = newton_update(0, cmax);
+                if (m_it > 0) crate = fmax(cv::CRDOWN * crate, pb_div(del, delp));
+                const double dcon = pb_div(del * fmin(1.0, crate), tq4);
+                if (dcon <= 1.0) {
+                    const int ecmax = errtest_cmax();
+                    acnrm = (m_it == 0 && ecmax == cmax) ? del : wnorm1(0, ecmax, S()->acor);
+                    jcurNLS = false;
+                    jcur = false;
+                    publish_state();
+                    return 0;
+                }
+                if ((m_it >= 1) && (del > cv::RDIV * delp)) {
+                    ret = cv::CONV_RECVR;
+                } else {
+                    delp = del;
+                    m_it++;
+                    if (m_it >= cv::NLS_MAXCOR) ret = cv::CONV_RECVR;
+                    else continue;
+                }
+            }
+            if ((ret > 0) && !jcurNLS) {  // retry once with a fresh Jacobian if it was stale
+                setup_pending = true;
+                jbad = true;
+                top = true;
+                m_it = 0;
+                g.sync();
+                PB_FOR_RANGE(e, 0, (cmax + 1) * NX) S()->acor[e] = 0.0;
+                continue;
+            }
+            return ret;
+        }
+    }
+
     // ---------------------------------------------------------------- step control
     /// cvCompleteStep (cvodes.c:7634-7736)
     PB_HD void complete_step() {
@@ -1540,6 +1616,19 @@ struct Bdf {
     /// The corrector of one phase of the attempt (state, then -- staggered -- all sensitivities)
     /// with its error test (cvodes.c:5905-6008).
     PB_HD void attempt_correct(int phase) {
+        if (SS && sensi && opt.simultaneous()) {
+            // CV_SIMULTANEOUS: one Newton iteration on state and sensitivities together, ONE error test on the
+            // joint norm (cvStep cvodes.c:5869-5905 without the staggered block :5938-6010)
+            if (phase == PH_SENS) return;
+            ret_ = nls_simultaneous(nflag_);
+            if (ret_ != 0) {
+                fail_ = 1;
+            } else {
+                dsm_ = acnrm * tq2;
+                if (dsm_ > 1.0) fail_ = 2;
+            }
+            return;
+        }
         if (phase == PH_SENS) {
             if (fail_ || !sensi) return;
             ncf_ = nef_ = 0;

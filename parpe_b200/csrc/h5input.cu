@@ -294,8 +294,9 @@ int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_pro
         // deps/AMICI/include/amici/defines.h).  What this path implements is accepted, what would change the results
         // beyond the path's tolerance is refused with a message, never silently replaced:
         //   lmm   2 = BDF (1 = Adams refused)             iter  2 = Newton (1 = functional refused)
-        //   ism   1 simultaneous / 2 staggered / 3 staggered1: accepted -- the sensitivity corrector is the staggered
-        //         one; the reference's own variants agree to ~1e-9, far inside the path's tolerance
+        //   ism   1 simultaneous: honoured (small-model kernels; pb200_create refuses it for the large-model kernels,
+        //         which have the staggered corrector only); 2 staggered; 3 staggered1: runs the staggered corrector --
+        //         the reference's own variants agree to ~1e-9, far inside the path's tolerance
         //   sensi_meth / sensi_meth_preeq  1 forward, 2 adjoint (parPE's generator writes adjoint,
         //         python/parpe/hdf5_pe_input.py:869-871): accepted -- the gradient is the same quantity and is always
         //         computed by forward sensitivities here; sensi (order) is decided per evaluation by gradient.empty()
@@ -313,7 +314,11 @@ int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_pro
         };
         if (opt_int("lmm", 2) != 2) refuse("lmm", "only BDF (2) is implemented");
         if (opt_int("iter", 2) != 2) refuse("iter", "only Newton iteration (2) is implemented");
-        { const int ism = opt_int("ism", 2); if (ism < 1 || ism > 3) refuse("ism", "not an InternalSensitivityMethod"); }
+        {   // (absent = staggered, the north-star configuration -- AMICI's own default would be simultaneous)
+            const int ism = opt_int("ism", 2);
+            if (ism < 1 || ism > 3) refuse("ism", "not an InternalSensitivityMethod");
+            d.ism = ism == 1 ? 1 : 0;  // 3 (staggered1: one sensitivity at a time) runs the staggered corrector
+        }
         for (const char* nm : {"sensi_meth", "sensi_meth_preeq"}) {
             const int v = opt_int(nm, 1);
             if (v < 0 || v > 2) refuse(nm, "not a SensitivityMethod");

@@ -165,6 +165,7 @@ struct pb200_handle {
     int opt_variant = 2, opt_ctas_per_sm = 0, opt_sync_period = 1, opt_stage_sync = 0, opt_partial_sums = 0;
     int opt_linsol = 0, opt_order_refresh = 16, opt_fuse_off = 0;
     bool steady_sens_newton = false;  // pb200_problem_desc::steady_sens_newton
+    bool simultaneous = false;        // pb200_problem_desc::ism == 1: needs the full-feature kernel instantiation
     int evals_since_order = 0;
     int64_t last_h2d = 0, last_d2h = 0;
     // large-model path: device tables + workspace (ModelOps::create_state)
@@ -481,6 +482,20 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
                                        "of a steady state is not supported for this model");
     }
     h->opt_linsol = d->linsol;  // (PB200_OPT_LINSOL can still change it)
+    if (d->ism != 0) {
+        // InternalSensitivityMethod: 0 / 2 staggered (the path's corrector), 1 simultaneous -- small-model kernels
+        // only, run by the full-feature (steady-state) instantiation; 3 staggered1 is not built
+        if (d->ism != 1 && d->ism != 2) return fail(PB200_ERR_ARG, "ism: 0 or 2 staggered, 1 simultaneous");
+        if (d->ism == 1) {
+            if (!ops->supports_newton || !ops->supports_steady)
+                return fail(PB200_ERR_ARG, "ism = 1: the simultaneous corrector is built for the small-model kernels only "
+                                           "(the large-model kernels use the staggered one, ism = 2)");
+            if (!a.opt.errconS) return fail(PB200_ERR_ARG, "ism = 1 needs sensi_errcon = 1 (AMICI forces it)");
+            a.opt.errconS |= 4;  // (SolverOptions::errconS bit 2)
+            h->simultaneous = true;
+            a.steady = 1;
+        }
+    }
     if (has_inf && a.opt.newton_maxsteps != 0 && !ops->supports_newton)
         return fail(PB200_ERR_ARG, "newton_maxsteps > 0 with t = inf output times: Newton's method for steady states is not "
                                    "supported for this model (only steady state by simulation, newton_maxsteps = 0)");
@@ -524,7 +539,7 @@ int pb200_set_preequilibration(pb200_handle* h, const int32_t* has_preeq, const 
         a.reinit_mask = nullptr;
         a.reinit_off = nullptr;
         a.reinit_idx = nullptr;
-        a.steady = h->has_inf ? 1 : 0;
+        a.steady = (h->has_inf || h->simultaneous) ? 1 : 0;
         return 0;
     }
     if (!h->ops->supports_steady) return fail(PB200_ERR_ARG, "pre-equilibration is not supported for this model");
@@ -566,7 +581,7 @@ int pb200_set_preequilibration(pb200_handle* h, const int32_t* has_preeq, const 
     a.reinit_mask = h->d_reinit_mask.p;
     a.reinit_off = h->d_reinit_off.p;
     a.reinit_idx = h->d_reinit_idx.p;
-    a.steady = (h->has_inf || any) ? 1 : 0;
+    a.steady = (h->has_inf || any || h->simultaneous) ? 1 : 0;
     return 0;
 }
 

@@ -54,6 +54,7 @@ struct B200ProblemTables {
     int newtonMaxSteps = 0;  // amici::Solver::setNewtonMaxSteps (steady states; 0 = by simulation only)
     bool newtonOnly = false; // steadyStateComputationMode newtonOnly: no simulation if Newton's method fails
     bool steadySensNewton = false; // steadyStateSensitivityMode newtonOnly with a simulation to steady state
+    int internalSensitivityMethod = 0; // 0 / 2 staggered, 1 simultaneous (small-model kernels only)
     int linearSolver = 0;    // large models: 0 automatic, 1 dense (LinearSolver::dense), 2 sparse (LinearSolver::KLU)
 
     /// The tables of a parPE parameter-estimation input file (doc/hdf5.md), assembled by the library's built-in
@@ -84,6 +85,7 @@ struct B200ProblemTables {
         d.newton_only = newtonOnly ? 1 : 0;
         d.linsol = linearSolver;
         d.steady_sens_newton = steadySensNewton ? 1 : 0;
+        d.ism = internalSensitivityMethod;
         return d;
     }
 };
@@ -378,6 +380,7 @@ inline B200ProblemTables B200ProblemTables::fromHdf5(std::string const& path, st
     T.newtonOnly = d.newton_only != 0;
     T.linearSolver = d.linsol;
     T.steadySensNewton = d.steady_sens_newton != 0;
+    T.internalSensitivityMethod = d.ism;
     {
         const double* lo = nullptr; const double* up = nullptr; const double* nom = nullptr; const char* names = nullptr;
         const int n = pb200_h5_problem_parameters(P, &lo, &up, &nom, &names);

@@ -221,7 +221,7 @@ def tables_from_hdf5(path, model_name: str) -> ProblemTables:
             overrides=arr(d.overrides, Cn * np_, np.float64) if d.overrides else None, t0=d.t0, atol=d.atol, rtol=d.rtol,
             maxsteps=d.maxsteps, stldet=d.stldet, sensi_errcon=d.sensi_errcon, num_trials=d.num_trials,
             relaxation_factor=d.relaxation_factor, newton_maxsteps=d.newton_maxsteps, newton_only=d.newton_only,
-            linsol=d.linsol, steady_sens_newton=d.steady_sens_newton)
+            linsol=d.linsol, steady_sens_newton=d.steady_sens_newton, ism=d.ism)
         hp = L.pb200_h5_problem_hier(P)
         if hp:
             h = hp.contents

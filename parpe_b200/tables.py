@@ -49,7 +49,8 @@ class ProblemDesc(C.Structure):
         ("linsol", C.c_int32),
         ("newton_only", C.c_int32),
         ("steady_sens_newton", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("ism", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -132,6 +133,7 @@ class ProblemTables:
     newton_maxsteps: int = 0   # steady states: Newton iterations before / after the simulation (AMICI default 0)
     newton_only: int = 0       # 1 = steadyStateComputationMode newtonOnly: no simulation if Newton's method fails
     steady_sens_newton: int = 0  # 1 = steadyStateSensitivityMode newtonOnly with a simulation to steady state
+    ism: int = 0               # 0 / 2 staggered corrector, 1 simultaneous (small-model kernels only)
     linsol: int = 0            # large models: 0 automatic, 1 dense, 2 sparse (initial value of PB200_OPT_LINSOL)
     hier: Optional[HierTables] = None
     # pre-equilibration (pb200_set_preequilibration): per simulation condition a flag, the constants of
@@ -200,6 +202,7 @@ class ProblemTables:
         d.lanes_per_condition = self.lanes_per_condition
         d.newton_maxsteps = self.newton_maxsteps
         d.newton_only, d.linsol, d.steady_sens_newton = self.newton_only, self.linsol, self.steady_sens_newton
+        d.ism = self.ism
         return d
 
     # per-condition views in the reference's layout (row-major obs + it*ny)

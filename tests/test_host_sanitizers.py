@@ -82,7 +82,9 @@ SMALL_BODY = """
         for c in (0, 1, 2):
             pre = bool(ts.has_preeq[c])
             for kw in (dict(), dict(newton_maxsteps=40), dict(newton_maxsteps=2), dict(newton_maxsteps=3, maxsteps=150),
-                       dict(newton_maxsteps=-40), dict(newton_maxsteps=-2)):  # (negative = Newton's method only)
+                       dict(newton_maxsteps=-40), dict(newton_maxsteps=-2),  # (negative = Newton's method only)
+                       dict(errconS=3), dict(errconS=3, newton_maxsteps=2), dict(errconS=5), dict(errconS=7)):  # (bit 1: steady-state
+                # sensitivities by the linear solve; bit 2: simultaneous corrector)
                 r = hh.simulate_ss(model, p, ts.k[c], list(range(spec.np)), tp, ts.y_of(c), ts.sigma_of(c),
                                    k_preeq=ts.k_preeq[c] if pre else None, reinit_idx=ts.reinit_idx[c] if pre else (), **kw)
                 assert r["status"] in (0, -99, -1), (model, c, kw, r["status"])

@@ -418,3 +418,23 @@ def test_sensitivity_mode_newton_only_with_a_singular_jacobian(oracle_available)
         r = _host(tab, theta, c, errconS=3)
         assert r["status"] == SIM_ERROR and np.isnan(r["llh"])
         assert _host(tab, theta, c, want_grad=False, errconS=3)["status"] == 0  # (cost only: no solve)
+
+
+@pytest.mark.parametrize("sens_newton", [0, 1], ids=["sensitivities-integrated", "sensitivities-by-solve"])
+def test_simultaneous_corrector_through_the_steady_state_phases(oracle_available, sens_newton):
+    """ism = simultaneous (pb200_problem_desc::ism = 1) in a problem with pre- and post-equilibration: the
+    simulations to steady state take the reference's number of steps with that corrector too."""
+    from oracle.binding import OracleProblem
+    tab, theta = _problem("steadystate", preeq=True, posteq=2)
+    tab.ism = 1
+    tab.steady_sens_newton = sens_newton
+    ro = OracleProblem(tab).evaluate(theta, collect_stats=True)
+    assert ro["status"] == 0
+    for c in range(tab.n_conditions):
+        r = _host(tab, theta, c, errconS=5 | (2 if sens_newton else 0))
+        assert r["status"] == 0
+        assert_llh_close(r["llh"], ro["llh"][c])
+        assert_grad_close(r["sllh_sim"], ro["sllh"][c][:len(r["sllh_sim"])])
+        if tab.has_preeq[c]:
+            assert abs(r["nst_preeq"] - ro["stats"][c, 14]) <= 0.1 * ro["stats"][c, 14] + 2
+        assert abs((r["numsteps"][-1] - r["numsteps"][-3]) - ro["stats"][c, 15]) <= 0.1 * ro["stats"][c, 15] + 2

@@ -115,3 +115,42 @@ def test_large_model_kernel_refuses_the_linear_solve_for_steady_state_sensitivit
     tab = synth.make_problem("net32", 2, seed=0)
     tab.steady_sens_newton = 1
     assert B200SummedGradientFunction(tab).evaluate(synth.random_theta(tab, seed=1, width=0.3))[0] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,C,kw", [("boehm", 40, dict(scale="log10")),
+                                        ("steadystate_scaled", 12, dict(scale="mixed", sigma_mode="mixed", missing_fraction=0.2, ragged=True))],
+                         ids=["boehm", "steadystate_scaled"])
+def test_simultaneous_corrector_matches_reference(oracle_available, model, C, kw):
+    """pb200_problem_desc::ism = 1: the simultaneous corrector (CV_SIMULTANEOUS) of the full-feature kernel
+    instantiation against the reference run with InternalSensitivityMethod::simultaneous; CPU parity of the same
+    source: tests/test_host_core.py::test_simultaneous_corrector_matches_cvodes."""
+    from tests.test_gpu_steadystate import _both
+    tab = synth.make_problem(model, C, seed=3, **kw)
+    tab.ism = 1
+    gpu, ora = _both(tab)  # (the oracle honours the descriptor's ism)
+    theta = synth.random_theta(tab, seed=1, width=0.3)
+    ro = ora.evaluate(theta, collect_stats=True)
+    st, fval, grad, _ = gpu.evaluate(theta)
+    res = gpu.condition_results()
+    assert ro["status"] == 0 and st == 0 and np.all(res["status"] == 0)
+    assert_llh_close(fval, ro["fval"])
+    assert_grad_close(grad, ro["grad"])
+    for c in range(tab.n_conditions):
+        assert_grad_close(res["sllh"][c], ro["sllh"][c], "per-condition sllh[%d]" % c)
+    # CVODES' counters of the simultaneous corrector: no separate sensitivity iterations / error-test failures
+    assert np.all(res["stats"][:, 5] == 0) and np.all(res["stats"][:, 8] == 0)
+    nst, nst_ref = res["stats"][:, 0], ro["stats"][:, 0]
+    assert abs(np.sum(nst) - np.sum(nst_ref)) <= 0.05 * np.sum(nst_ref)  # (per condition rounding decides: a few per cent either way)
+    st0, f0, _, _ = gpu.evaluate(theta, want_gradient=False)
+    assert st0 == 0
+    assert_llh_close(f0, ora.evaluate(theta, want_grad=False)["fval"])
+
+
+@pytest.mark.gpu
+def test_large_model_kernel_refuses_the_simultaneous_corrector():
+    from parpe_b200.problem import B200SummedGradientFunction
+    tab = synth.make_problem("net32", 2, seed=0)
+    tab.ism = 1
+    with pytest.raises(capi.B200LibraryError, match="ism"):
+        B200SummedGradientFunction(tab)
