@@ -25,6 +25,8 @@
 // the reference's own pre-generated model (deps/AMICI/models/model_steadystate),
 // compiled in place by the Makefile: cross-checks our generator
 #include "model_steadystate.h"
+// ... and its model with a spline input (deps/AMICI/models/model_jakstat_adjoint)
+#include "model_jakstat_adjoint.h"
 #endif
 
 #ifdef PB200_ORACLE_WITH_PYGEN
@@ -48,6 +50,8 @@ std::unique_ptr<amici::Model> makeModel(const std::string& name) {
 #ifdef PB200_ORACLE_WITH_VENDORED
     if (name == "steadystate_vendored")
         return std::make_unique<amici::model_model_steadystate::Model_model_steadystate>();
+    if (name == "jakstat_vendored")
+        return std::make_unique<amici::model_model_jakstat_adjoint::Model_model_jakstat_adjoint>();
 #endif
 #ifdef PB200_ORACLE_WITH_PYGEN
     if (name.rfind("pygen_", 0) == 0) return pb200_pygen_model(name);

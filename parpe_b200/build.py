@@ -61,7 +61,8 @@ def _compile(src, obj, log):
 
 # AMICI-generated models of the reference tree that the back-end codegen/amici_import.py re-homes as device code at
 # build time (never committed: the output contains the reference's generated expressions)
-REFERENCE_MODELS = ["/root/reference/deps/AMICI/models/model_steadystate"]
+REFERENCE_MODELS = ["/root/reference/deps/AMICI/models/model_steadystate",
+                    "/root/reference/deps/AMICI/models/model_jakstat_adjoint"]  # (a spline input: amici::spline_pos)
 PYGEN_MODELS = [("steadystate", False), ("boehm", True)]
 
 

@@ -19,6 +19,10 @@
 #include "../../parpe_b200/csrc/models/imported/amici_steadystate.cuh"
 #define PB200_HAVE_AMICI_STEADYSTATE 1
 #endif
+#if __has_include("../../parpe_b200/csrc/models/imported/amici_jakstat_adjoint.cuh")
+#include "../../parpe_b200/csrc/models/imported/amici_jakstat_adjoint.cuh"
+#define PB200_HAVE_AMICI_JAKSTAT 1
+#endif
 // models written by AMICI's python code generator at build time (parpe_b200/codegen/amici_pygen.py), re-homed likewise
 #if __has_include("../../parpe_b200/csrc/models/imported/pygen_steadystate.cuh")
 #include "../../parpe_b200/csrc/models/imported/pygen_steadystate.cuh"
@@ -119,6 +123,9 @@ extern "C" int hs_simulate_ss(const char* model, const double* p_unscaled, const
 #if defined(PB200_HAVE_AMICI_STEADYSTATE)
     DISPATCH_SS(amici_steadystate)
 #endif
+#if defined(PB200_HAVE_AMICI_JAKSTAT)
+    DISPATCH_SS(amici_jakstat_adjoint)
+#endif
 #if defined(PB200_HAVE_PYGEN_STEADYSTATE)
     DISPATCH_SS(pygen_steadystate)
 #endif
@@ -142,6 +149,9 @@ extern "C" int hs_simulate(const char* model, const double* p_unscaled, const do
     DISPATCH(fujita)
 #if defined(PB200_HAVE_AMICI_STEADYSTATE)
     DISPATCH(amici_steadystate)
+#endif
+#if defined(PB200_HAVE_AMICI_JAKSTAT)
+    DISPATCH(amici_jakstat_adjoint)
 #endif
 #if defined(PB200_HAVE_PYGEN_STEADYSTATE)
     DISPATCH(pygen_steadystate)

@@ -35,7 +35,7 @@ def test_importer_reads_the_vendored_model(tmp_path):
     assert "w[1] = x[0]*x[0];" in text and "J[8] = -k[3]-dwdx[1];" in text
     assert amici_import.parse_dimensions(open(os.path.join(REF_MODEL, "model_steadystate.h")).read())["nw"] == 2
     # models outside the supported scope are refused, not mistranslated
-    for bad, why in (("model_dirac", "events"), ("model_jakstat_adjoint", "spline|events|not supported|no device counterpart"),
+    for bad, why in (("model_dirac", "events"), ("model_events", "events"),
                      ("model_robertson", "not supported|not found|no device counterpart")):
         d = os.path.join(os.path.dirname(REF_MODEL), bad)
         if os.path.isdir(d):
@@ -172,3 +172,114 @@ def test_cuda_path_with_a_python_generated_model(oracle_available, name, spec_mo
     assert st == ro["status"] == 0
     assert_llh_close(fval, ro["fval"])
     assert_grad_close(grad, ro["grad"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a model with a time-dependent input through the classic layout's spline functions: deps/AMICI/models/
+# model_jakstat_adjoint (w[0] = amici::spline_pos(t, 5, 0.0, p[5], 5.0, p[6], ..., 0.0, 0.0); SURVEY H8 and the
+# survey's offline stand-in for the Boehm configuration)
+JAK_MODEL = "/root/reference/deps/AMICI/models/model_jakstat_adjoint"
+JAK_IMPORTED = os.path.join(os.path.dirname(IMPORTED), "amici_jakstat_adjoint.cuh")
+JAK_FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "imported", "jakstat_sensiforward.json")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_importer_maps_the_spline_functions(tmp_path):
+    if not os.path.isdir(JAK_MODEL):
+        pytest.skip("/root/reference not present")
+    from parpe_b200.codegen import amici_import
+    text = open(amici_import.import_model(JAK_MODEL, outdir=str(tmp_path))).read()
+    assert "NX = 9, NP = 17, NK = 2, NY = 3, NNZ = 18" in text and '#include "../../amici_functions.cuh"' in text
+    assert "w[0] = pb200::amifn::spline_pos(t,5,0.0,p[5],5.0,p[6],1.0E1,p[7],2.0E1,p[8],6.0E1,p[9],0.0,0.0);" in text
+    assert "pb200::amifn::Dspline_pos(4,t,5," in text and "amici::" not in text
+    # parameters the states depend on: rate constants, the initial value and the five spline nodes
+    assert "DYN_MASK = 0x3ffu" in text
+
+
+def test_spline_functions_match_the_reference(tmp_path):
+    """csrc/amici_functions.cuh (variadic templates, the Forsythe-Malcolm-Moler interpolant written from the book)
+    against the reference's own amici::spline / spline_pos / Dspline / Dspline_pos (C varargs,
+    deps/AMICI/src/symbolic_functions.cpp:109-269, spline.cpp:16-257) compiled in place: 2 to 5 nodes, both end
+    conditions, every node derivative, inside and outside the node range."""
+    import subprocess
+    lib = os.path.join(ROOT, "oracle", "_ref", "libamici_ref.a")
+    if not os.path.isdir("/root/reference") or not os.path.exists(lib):
+        pytest.skip("needs /root/reference and the reference build (oracle/_ref)")
+    src = tmp_path / "check.cpp"
+    src.write_text(r"""
+#include <cmath>
+#include <cstdio>
+#include "amici/symbolic_functions.h"
+#include "amici_functions.cuh"
+#define BOTH(expr) { using namespace amici; const double a = expr; { using namespace pb200::amifn; const double b = expr; \
+                     worst = fmax(worst, fabs(a - b) / fmax(fabs(a), 1e-12)); ++n; } }
+int main() {
+    double worst = 0.0; long n = 0;
+    const double p[5] = {0.31, 1.7, 0.9, 0.05, 0.4};
+    for (int ss = 0; ss <= 1; ++ss)
+        for (double t = -3.0; t <= 90.0; t += 0.37) {
+            const double e = ss, s = 0.3;
+            BOTH(spline_pos(t, 5, 0.0, p[0], 5.0, p[1], 1.0E1, p[2], 2.0E1, p[3], 6.0E1, p[4], e, s))
+            BOTH(spline(t, 5, 0.0, p[0], 5.0, p[1], 1.0E1, p[2], 2.0E1, p[3], 6.0E1, p[4], e, s))
+            BOTH(spline(t, 4, 0.0, p[0], 5.0, p[1], 1.0E1, p[2], 2.0E1, p[3], e, s))
+            BOTH(spline(t, 3, 0.0, p[0], 5.0, p[1], 1.0E1, p[2], e, s))
+            BOTH(spline(t, 2, 0.0, p[0], 5.0, p[1], e, s))
+            for (int id = 4; id <= 12; id += 2) {
+                BOTH(Dspline_pos(id, t, 5, 0.0, p[0], 5.0, p[1], 1.0E1, p[2], 2.0E1, p[3], 6.0E1, p[4], e, s))
+                BOTH(Dspline(id, t, 5, 0.0, p[0], 5.0, p[1], 1.0E1, p[2], 2.0E1, p[3], 6.0E1, p[4], e, s))
+            }
+        }
+    printf("%ld comparisons, worst relative difference %.3e\n", n, worst);
+    return worst < 1e-12 ? 0 : 1;
+}
+""")
+    A = "/root/reference/deps/AMICI"
+    exe = str(tmp_path / "check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + A + "/include", "-I" + os.path.join(ROOT, "oracle", "_ref", "include"),
+                           "-I" + A + "/ThirdParty/gsl", "-I" + A + "/ThirdParty/sundials/include",
+                           "-I" + A + "/ThirdParty/sundials/include/sundials/amici_matlab",
+                           "-I" + os.path.join(ROOT, "parpe_b200", "csrc"), str(src), lib, "-o", exe, "-fopenmp", "-ldl", "-lm"])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0, out.stdout
+
+
+def _jakstat(corrector):
+    import json
+    from tests.util import jakstat_tables
+    doc = json.load(open(JAK_FIXTURE))
+    tab = jakstat_tables(doc)
+    tab.ism = 1 if corrector == "simultaneous" else 0
+    return doc, tab, np.array(doc["theta"])
+
+
+@pytest.mark.parametrize("corrector", ["staggered", "simultaneous"])
+def test_host_core_with_the_imported_spline_model_against_the_reference_fixture(corrector):
+    """No oracle needed: the imported model_jakstat_adjoint in the host build of the device core against the committed
+    outputs of the reference running its own vendored model on its own test inputs (tools/make_golden_jakstat.py)."""
+    if not os.path.exists(JAK_IMPORTED):
+        pytest.skip("no imported model in this build")
+    from tests.host_harness.binding import simulate_ss
+    doc, tab, theta = _jakstat(corrector)
+    ref = doc["reference"][corrector]
+    for c in range(tab.n_conditions):
+        p, plist, fac = condition_inputs(tab, theta, c)
+        lo, hi = tab.t_offsets[c], tab.t_offsets[c + 1]
+        r = simulate_ss("amici_jakstat_adjoint", p, tab.k[c], plist, tab.t[lo:hi], tab.y_of(c), tab.sigma_of(c),
+                        errconS=5 if corrector == "simultaneous" else 1)
+        assert r["status"] == 0
+        assert_llh_close(r["llh"], ref["llh"][c])
+        assert_grad_close(r["sllh"] * fac, np.array(ref["sllh"][c])[:len(plist)])
+        assert abs(r["numsteps"][-1] - ref["nst"][c]) <= 0.1 * ref["nst"][c] + 2
+
+
+def test_reference_reproduces_the_spline_model_fixture(oracle_available):
+    from oracle.binding import OracleProblem
+    doc, tab, theta = _jakstat("staggered")
+    try:
+        ora = OracleProblem(tab, 2, 9, model_name="jakstat_vendored")
+    except RuntimeError:
+        pytest.skip("oracle built without the vendored model")
+    r = ora.evaluate(theta)
+    ref = doc["reference"]["staggered"]
+    assert r["fval"] == pytest.approx(ref["nllh"], rel=1e-10)
+    np.testing.assert_allclose(r["grad"], ref["grad"], rtol=1e-7, atol=1e-9 * np.max(np.abs(ref["grad"])))

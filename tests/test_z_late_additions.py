@@ -1,13 +1,16 @@
-"""The steady-state modes `newtonOnly` on the GPU through the C ABI against the reference, and the descriptor's
+"""GPU cases of what was added after the round's GPU budget was spent (the CPU parity of the same integrator /
+model source is green; NONE of the `gpu`-marked cases of this file has run on a B200 yet -- the file sorts last so
+that the driver's `-x` run reaches them after everything that was verified).
+
+The steady-state modes `newtonOnly` on the GPU through the C ABI against the reference, and the descriptor's
 checks: steadyStateComputationMode newtonOnly (pb200_problem_desc::newton_only; SteadystateProblem::findSteadyState
 with turnOffSimulation, deps/AMICI/src/steadystateproblem.cpp:120-166) and steadyStateSensitivityMode newtonOnly
 (pb200_problem_desc::steady_sens_newton; the simulation to steady state runs without the sensitivity columns,
 :728-736, which are solved for at the steady state, :91-103).  The per-path CPU parity of the same integrator source
 is tests/test_host_steadystate.py::test_newton_only_mode / test_sensitivity_mode_newton_only.
 
-NOTE: written after the round's GPU budget was spent -- the CPU parity of the integrator core (same source, host
-build) is green, the GPU cases of this file have not run on a B200 yet.  (This file sorts after the other test
-files on purpose.)"""
+Further down: the simultaneous corrector (pb200_problem_desc::ism = 1) and the imported model with a spline input
+(deps/AMICI/models/model_jakstat_adjoint through csrc/amici_functions.cuh) against its committed reference fixture."""
 import numpy as np
 import pytest
 
@@ -154,3 +157,33 @@ def test_large_model_kernel_refuses_the_simultaneous_corrector():
     tab.ism = 1
     with pytest.raises(capi.B200LibraryError, match="ism"):
         B200SummedGradientFunction(tab)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("corrector", ["staggered", "simultaneous"])
+def test_imported_model_with_a_spline_input_against_the_reference_fixture(corrector):
+    """deps/AMICI/models/model_jakstat_adjoint (w[0] = amici::spline_pos(t, 5, ...): a time-dependent input through the
+    classic layout's spline functions, csrc/amici_functions.cuh) as device code, on the reference's own test inputs,
+    against the outputs of the reference running its own vendored model (tests/golden/imported/
+    jakstat_sensiforward.json, tools/make_golden_jakstat.py); CPU parity of the same generated model source:
+    tests/test_amici_import.py."""
+    import json
+    import os
+    from parpe_b200.problem import B200SummedGradientFunction
+    from tests.util import jakstat_tables
+    if "amici_jakstat_adjoint" not in capi.models():
+        pytest.skip("the library was built without /root/reference: no imported model")
+    doc = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "imported", "jakstat_sensiforward.json")))
+    tab = jakstat_tables(doc)
+    tab.ism = 1 if corrector == "simultaneous" else 0
+    ref = doc["reference"][corrector]
+    gpu = B200SummedGradientFunction(tab)
+    st, fval, grad, _ = gpu.evaluate(np.array(doc["theta"]))
+    res = gpu.condition_results()
+    assert st == 0 and np.all(res["status"] == 0)
+    assert_llh_close(fval, ref["nllh"])
+    assert_grad_close(grad, np.array(ref["grad"]))
+    assert_llh_close(res["llh"], np.array(ref["llh"]))
+    for c in range(tab.n_conditions):
+        assert_grad_close(res["sllh"][c], np.array(ref["sllh"][c]), "per-condition sllh[%d]" % c)
+    assert abs(np.sum(res["stats"][:, 0]) - np.sum(ref["nst"])) <= 0.1 * np.sum(ref["nst"])

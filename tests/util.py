@@ -55,3 +55,28 @@ def assert_outputs_close(y, yref, tab, what="model outputs"):
     np.testing.assert_allclose(y[~inf_rows], yref[~inf_rows], rtol=1e-6, atol=1e-9, err_msg=what)
     if np.any(inf_rows):
         np.testing.assert_allclose(y[inf_rows], yref[inf_rows], rtol=2e-5, atol=1e-9, err_msg=what + " (t = inf)")
+
+
+def jakstat_tables(doc):
+    """ProblemTables of the fixture tests/golden/imported/jakstat_sensiforward.json (tools/make_golden_jakstat.py): the
+    reference's own test inputs of deps/AMICI/models/model_jakstat_adjoint (np = 17 parameters, all log10; nk = 2
+    compartment volumes; ny = 3 observables at 16 output times) as a multi-condition problem."""
+    from parpe_b200.tables import ProblemTables
+    nan = lambda rows: np.array([[np.nan if v is None else v for v in row] for row in rows], dtype=float)
+    ts, Y, S = np.array(doc["ts"], dtype=float), nan(doc["Y"]), nan(doc["Sigma_Y"])
+    C, nt = len(doc["conditions"]), len(ts)
+    y, sd, k = [], [], []
+    for cond in doc["conditions"]:
+        yc, sc = Y.copy(), S.copy()
+        if "data_sigma" in cond:
+            sc[:] = cond["data_sigma"]
+        if "drop_observable" in cond:
+            yc[:, cond["drop_observable"]] = np.nan
+        y.append(yc.ravel())
+        sd.append(sc.ravel())
+        k.append(np.array(doc["kappa"]) * np.array(cond["kappa_factor"]))
+    return ProblemTables(
+        model_name=doc["model"], np_=17, nk=2, ny=3, n_opt=17, t_offsets=np.arange(C + 1, dtype=np.int64) * nt,
+        t=np.tile(ts, C), y=np.concatenate(y), sigma=np.concatenate(sd), k=np.concatenate(k),
+        mapping=np.tile(np.arange(17, dtype=np.int32), C), pscale_sim=np.full(17 * C, 2, dtype=np.int32),
+        pscale_opt=np.full(17, 2, dtype=np.int32), overrides=None, atol=1e-12, rtol=1e-8)
