@@ -21,71 +21,71 @@
 namespace pb200 {
 namespace amifn {
 
-/// Piecewise cubic s(t) = y[i] + w (b[i] + w (c[i] + w d[i])), w = t - x[i], on [x[i], x[i+1]); the first / last
-/// piece is continued outside the nodes (as the reference's seval does).
+/// Piecewise cubic s(t) = fk[i] + w (c1[i] + w (c2[i] + w c3[i])), w = t - tk[i], on [tk[i], tk[i+1]) -- knots tk, values fk,
+/// coefficients c1..c3; the first / last piece is continued outside the knots (as the reference's seval does).
 template <int N>
 struct Cubic {
     static_assert(N >= 2, "a spline needs two nodes");
-    double x[N], y[N], b[N], c[N], d[N];
+    double tk[N], fk[N], c1[N], c2[N], c3[N];
 
-    /// Coefficients from the nodes: tridiagonal system for the scaled second derivatives sigma_i (diagonal in b,
-    /// off-diagonal in d, right-hand side in c), eliminated in place.
+    /// Coefficients from the nodes: tridiagonal system for the scaled second derivatives sigma_i (diagonal in c1,
+    /// off-diagonal in c3, right-hand side in c2), eliminated in place.
     PB_HD void fit(bool slope_at_first, double slope_first) {
         if (N == 2) {
-            const double s = (y[1] - y[0]) / (x[1] - x[0]);
-            for (int i = 0; i < N; ++i) { b[i] = s; c[i] = 0.0; d[i] = 0.0; }
+            const double s = (fk[1] - fk[0]) / (tk[1] - tk[0]);
+            for (int i = 0; i < N; ++i) { c1[i] = s; c2[i] = 0.0; c3[i] = 0.0; }
             return;
         }
         constexpr int L = N - 1;  // last node
-        d[0] = x[1] - x[0];
-        c[1] = (y[1] - y[0]) / d[0];
+        c3[0] = tk[1] - tk[0];
+        c2[1] = (fk[1] - fk[0]) / c3[0];
         for (int i = 1; i < L; ++i) {
-            d[i] = x[i + 1] - x[i];
-            b[i] = 2.0 * (d[i - 1] + d[i]);
-            c[i + 1] = (y[i + 1] - y[i]) / d[i];
-            c[i] = c[i + 1] - c[i];
+            c3[i] = tk[i + 1] - tk[i];
+            c1[i] = 2.0 * (c3[i - 1] + c3[i]);
+            c2[i + 1] = (fk[i + 1] - fk[i]) / c3[i];
+            c2[i] = c2[i + 1] - c2[i];
         }
         // end conditions: third derivative from divided differences over the outer four nodes
-        b[0] = -d[0];
-        b[L] = -d[L - 1];
-        c[0] = 0.0;
-        c[L] = 0.0;
+        c1[0] = -c3[0];
+        c1[L] = -c3[L - 1];
+        c2[0] = 0.0;
+        c2[L] = 0.0;
         if (N > 3) {
-            c[0] = c[2] / (x[3] - x[1]) - c[1] / (x[2] - x[0]);
-            c[L] = c[L - 1] / (x[L] - x[L - 2]) - c[L - 2] / (x[L - 1] - x[L - 3]);
-            c[0] = c[0] * d[0] * d[0] / (x[3] - x[0]);
-            c[L] = -c[L] * d[L - 1] * d[L - 1] / (x[L] - x[L - 3]);
+            c2[0] = c2[2] / (tk[3] - tk[1]) - c2[1] / (tk[2] - tk[0]);
+            c2[L] = c2[L - 1] / (tk[L] - tk[L - 2]) - c2[L - 2] / (tk[L - 1] - tk[L - 3]);
+            c2[0] = c2[0] * c3[0] * c3[0] / (tk[3] - tk[0]);
+            c2[L] = -c2[L] * c3[L - 1] * c3[L - 1] / (tk[L] - tk[L - 3]);
         }
         if (slope_at_first) {  // ... or the prescribed slope at the first node
-            b[0] = 2.0 * (x[1] - x[0]);
-            c[0] = (y[1] - y[0]) / (x[1] - x[0]) - slope_first;
+            c1[0] = 2.0 * (tk[1] - tk[0]);
+            c2[0] = (fk[1] - fk[0]) / (tk[1] - tk[0]) - slope_first;
         }
         for (int i = 1; i < N; ++i) {  // elimination
-            const double f = d[i - 1] / b[i - 1];
-            b[i] -= f * d[i - 1];
-            c[i] -= f * c[i - 1];
+            const double f = c3[i - 1] / c1[i - 1];
+            c1[i] -= f * c3[i - 1];
+            c2[i] -= f * c2[i - 1];
         }
-        c[L] = c[L] / b[L];  // back substitution: c = sigma
-        for (int i = L - 1; i >= 0; --i) c[i] = (c[i] - d[i] * c[i + 1]) / b[i];
+        c2[L] = c2[L] / c1[L];  // back substitution: c = sigma
+        for (int i = L - 1; i >= 0; --i) c2[i] = (c2[i] - c3[i] * c2[i + 1]) / c1[i];
         // polynomial coefficients of the pieces
-        b[L] = (y[L] - y[L - 1]) / d[L - 1] + d[L - 1] * (c[L - 1] + 2.0 * c[L]);
+        c1[L] = (fk[L] - fk[L - 1]) / c3[L - 1] + c3[L - 1] * (c2[L - 1] + 2.0 * c2[L]);
         for (int i = 0; i < L; ++i) {
-            b[i] = (y[i + 1] - y[i]) / d[i] - d[i] * (c[i + 1] + 2.0 * c[i]);
-            d[i] = (c[i + 1] - c[i]) / d[i];
-            c[i] = 3.0 * c[i];
+            c1[i] = (fk[i + 1] - fk[i]) / c3[i] - c3[i] * (c2[i + 1] + 2.0 * c2[i]);
+            c3[i] = (c2[i + 1] - c2[i]) / c3[i];
+            c2[i] = 3.0 * c2[i];
         }
-        c[L] = 3.0 * c[L];
-        d[L] = d[L - 1];
+        c2[L] = 3.0 * c2[L];
+        c3[L] = c3[L - 1];
     }
 
     PB_HD double operator()(double t) const {
         int i = 0;
-        if (t >= x[N - 1]) i = N - 1;
+        if (t >= tk[N - 1]) i = N - 1;
         else
             for (int j = 1; j < N - 1; ++j)
-                if (t >= x[j]) i = j;
-        const double w = t - x[i];
-        return y[i] + w * (b[i] + w * (c[i] + w * d[i]));
+                if (t >= tk[j]) i = j;
+        const double w = t - tk[i];
+        return fk[i] + w * (c1[i] + w * (c2[i] + w * c3[i]));
     }
 };
 
@@ -108,14 +108,14 @@ PB_HD double eval(int id, double t, A... args) {
     const bool clamp = static_cast<int>(v[M - 2]) == 1;
     const double slope = v[M - 1];
     Cubic<N> s;
-    for (int i = 0; i < N; ++i) s.x[i] = v[2 * i];
+    for (int i = 0; i < N; ++i) s.tk[i] = v[2 * i];
     if (KIND == VALUE) {
-        for (int i = 0; i < N; ++i) s.y[i] = v[2 * i + 1];
+        for (int i = 0; i < N; ++i) s.fk[i] = v[2 * i + 1];
         s.fit(clamp, slope);
         return s(t);
     }
     if (KIND == VALUE_POS || KIND == DVALUE_POS) {
-        for (int i = 0; i < N; ++i) s.y[i] = log(v[2 * i + 1]);
+        for (int i = 0; i < N; ++i) s.fk[i] = log(v[2 * i + 1]);
         s.fit(clamp, slope);
     }
     if (KIND == VALUE_POS) return exp(s(t));
@@ -124,7 +124,7 @@ PB_HD double eval(int id, double t, A... args) {
     // unit vector e_j -- with the same end-condition arguments, as the reference passes them
     const int j = id / 2 - 2;
     const double pos = (KIND == DVALUE_POS) ? exp(s(t)) : 1.0;
-    for (int i = 0; i < N; ++i) s.y[i] = (i == j) ? 1.0 : 0.0;
+    for (int i = 0; i < N; ++i) s.fk[i] = (i == j) ? 1.0 : 0.0;
     s.fit(clamp, slope);
     const double ds = s(t);
     // positive spline: d exp(S(log u)) / d u_j = exp(S) * dS/d(log u_j) / u_j
