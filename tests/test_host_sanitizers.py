@@ -88,6 +88,20 @@ SMALL_BODY = """
                 r = hh.simulate_ss(model, p, ts.k[c], list(range(spec.np)), tp, ts.y_of(c), ts.sigma_of(c),
                                    k_preeq=ts.k_preeq[c] if pre else None, reinit_idx=ts.reinit_idx[c] if pre else (), **kw)
                 assert r["status"] in (0, -99, -1), (model, c, kw, r["status"])
+    # the imported model with a spline input (csrc/amici_functions.cuh: coefficient arrays on the stack), if built
+    import json, os
+    from tests.util import jakstat_tables, condition_inputs
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(hh.__file__))))
+    fx = os.path.join(root, "tests", "golden", "imported", "jakstat_sensiforward.json")
+    if os.path.exists(os.path.join(root, "parpe_b200", "csrc", "models", "imported", "amici_jakstat_adjoint.cuh")):
+        doc = json.load(open(fx))
+        tj = jakstat_tables(doc)
+        for c in range(tj.n_conditions):
+            pj, plist, _ = condition_inputs(tj, np.array(doc["theta"]), c)
+            lo, hi = tj.t_offsets[c], tj.t_offsets[c + 1]
+            for ec in (1, 5):
+                r = hh.simulate_ss("amici_jakstat_adjoint", pj, tj.k[c], plist, tj.t[lo:hi], tj.y_of(c), tj.sigma_of(c), errconS=ec)
+                assert r["status"] == 0, (c, ec, r["status"])
     print("ASAN-OK")
 """
 
