@@ -162,9 +162,9 @@ typedef struct pb200_problem_desc {
     int32_t steady_sens_newton;
     /* /amiciOptions ism (amici::InternalSensitivityMethod, CVodeSensInit1's ism): 0 or 2 = staggered -- the
      * path's corrector (north star: forward, staggered); 1 = simultaneous (CV_SIMULTANEOUS: state and
-     * sensitivities in one Newton iteration and one error test, cvodes_nls_sim.c) -- small-model kernels only,
-     * run by their full-feature (steady-state) instantiation; PB200_ERR_ARG for the large-model kernels.  AMICI's
-     * own default is simultaneous; the variants agree to ~1e-9 relative. */
+     * sensitivities in one Newton iteration and one error test, cvodes_nls_sim.c) -- run by the full-feature
+     * (steady-state) instantiation of the model's kernels, small- and large-model alike.  AMICI's own default is
+     * simultaneous; the variants agree to ~1e-9 relative. */
     int32_t ism;
     int32_t reserved[2];
 } pb200_problem_desc;

@@ -1909,8 +1909,56 @@ struct BdfTeam {
     // ---------------------------------------------------------------- nonlinear solve
     /// cvNls / cvStgrNls + SUNNonlinSolSolve_Newton + the convergence tests for the columns of
     /// `phase`; on success the corrected vector is zn[0] + acor.
+    /// The residual of one Newton iteration: the columns of `phase` -- or, simultaneous corrector, the state column and
+    /// then the sensitivity columns at the current state iterate with J and dxdotdp re-evaluated there (AMICI's
+    /// fsxdot, model_ode.cpp:486-515; cvNlsResidualSensSim).  One call site of rhs() for both correctors.
+    PB_HD int residual(int phase) {
+        if constexpr (SS) {
+            const bool sim = simultaneous_now(phase);
+            int ret = 0;
+            int ph_last = sim ? (int)PH_SENS : phase;
+            PB_OPAQUE_INT(ph_last);
+            for (int ph = phase; ph <= ph_last && ret == 0; ++ph) {
+                if (sim && ph == PH_SENS) {
+                    tm.sync();
+                    PT_FOR(i, 0, nx) w.ysh[i] = w.yj[i];
+                    refresh_Jcur();
+                }
+                ret = rhs(ph, false);
+            }
+            return ret;
+        } else {
+            return rhs(phase, false);
+        }
+    }
+    /// true in the state phase of a step with the simultaneous corrector (steady-state instantiation only; the plain
+    /// instantiation must not even declare a variable for it: its machine code is the measured one)
+    PB_HD bool simultaneous_now(int phase) const {
+        if constexpr (SS) return (phase == PH_STATE) && sensi && opt.simultaneous();
+        else return false;
+    }
+    /// last column of the Newton iteration of `phase`
+    PB_HD int nls_cmax(int phase) const {
+        if constexpr (SS) return simultaneous_now(phase) ? ns : phase_cmax(phase);
+        else return phase_cmax(phase);
+    }
+    /// norm of the accumulated correction for the error test, at convergence of iteration m_it
+    PB_HD double nls_acnrm(int phase, int m_it, double del, int cmin, int cmax) {
+        if constexpr (SS) {  // (simultaneous: the norm spans the columns that take part in the error test)
+            const int ncmax = simultaneous_now(phase) ? errtest_cmax() : cmax;
+            return (m_it == 0 && ncmax == cmax) ? del : wnorm1(cmin, ncmax, w.acor);
+        } else {
+            return (m_it == 0) ? del : wnorm1(cmin, cmax, w.acor);
+        }
+    }
+
+    /// When simultaneous_now(phase) (steady-state instantiation only; SolverOptions::simultaneous()) the SIMULTANEOUS
+    /// corrector: cvNls with do_sensi_sim (cvodes.c:6894-7007) over the wrapped vector of cvodes_nls_sim.c:374-560 --
+    /// see Bdf::nls_simultaneous (bdf_core.cuh) for the scheme.  It runs through the SAME call sites as the staggered
+    /// phases (the right-hand sides of both phases in turn, one setup, one update over the columns 0 .. ns, the joint
+    /// norm), so the kernel does not carry a second copy of the solver; the fused sparse paths stay off.
     PB_HD int nls(int phase, int nflag) {
-        const int cmin = phase_cmin(phase), cmax = phase_cmax(phase);
+        const int cmin = phase_cmin(phase), cmax = nls_cmax(phase);
         bool setup_pending = false;
         if (phase == PH_STATE) {
             convfail = ((nflag == cv::FIRST_CALL) || (nflag == cv::PREV_ERR_FAIL)) ? cv::NO_FAILURES : cv::FAIL_OTHER;
@@ -1931,7 +1979,7 @@ struct BdfTeam {
         int m_it = 0;
         for (;;) {
             fwd_ok_ = (phase == PH_SENS) && !setup_pending;
-            int ret = rhs(phase, false);
+            int ret = residual(phase);
             fwd_ok_ = false;
             if (ret != 0 && top) return ret;
             if (ret == 0 && setup_pending) {
@@ -1962,7 +2010,7 @@ struct BdfTeam {
                 else crateS = cr;
                 const double dcon = del * fmin(1.0, cr) / tq4;
                 if (dcon <= 1.0) {
-                    const double an = (m_it == 0) ? del : wnorm1(cmin, cmax, w.acor);
+                    const double an = nls_acnrm(phase, m_it, del, cmin, cmax);
                     if (phase == PH_STATE) {
                         acnrm = an;
                         jcurNLS = false;
@@ -1971,6 +2019,9 @@ struct BdfTeam {
                         jcurNLSS = false;
                     }
                     jcur = false;
+                    if constexpr (SS) {
+                        if (simultaneous_now(phase)) publish_state();
+                    }
                     return 0;
                 }
                 if ((m_it >= 1) && (del > cv::RDIV * delp)) {
@@ -2495,8 +2546,13 @@ struct BdfTeam {
         else cyc_sens += now() - t_c0;
     }
     PB_HD void attempt_correct_(int phase) {
+        // (steady-state instantiation: the simultaneous corrector does all columns in the state phase -- one Newton
+        // iteration and ONE error test -- and nothing in the sensitivity phase)
         if (phase == PH_SENS) {
             if (fail_ || !sensi) return;
+            if constexpr (SS) {
+                if (opt.simultaneous()) return;
+            }
             ncf_ = nef_ = 0;
             publish_state();
             PT_FOR(i, 0, nx) w.yj[i] = w.ysh[i];

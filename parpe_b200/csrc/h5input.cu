@@ -294,8 +294,8 @@ int pb200_h5_load_problem(const char* path, const char* model_name, pb200_h5_pro
         // deps/AMICI/include/amici/defines.h).  What this path implements is accepted, what would change the results
         // beyond the path's tolerance is refused with a message, never silently replaced:
         //   lmm   2 = BDF (1 = Adams refused)             iter  2 = Newton (1 = functional refused)
-        //   ism   1 simultaneous: honoured (small-model kernels; pb200_create refuses it for the large-model kernels,
-        //         which have the staggered corrector only); 2 staggered; 3 staggered1: runs the staggered corrector --
+        //   ism   1 simultaneous: honoured (the full-feature instantiation of the model's kernels); 2 staggered;
+        //         3 staggered1: runs the staggered corrector --
         //         the reference's own variants agree to ~1e-9, far inside the path's tolerance
         //   sensi_meth / sensi_meth_preeq  1 forward, 2 adjoint (parPE's generator writes adjoint,
         //         python/parpe/hdf5_pe_input.py:869-871): accepted -- the gradient is the same quantity and is always

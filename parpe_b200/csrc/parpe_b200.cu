@@ -483,13 +483,13 @@ int pb200_create(const pb200_problem_desc* d, int device, pb200_handle** out) {
     }
     h->opt_linsol = d->linsol;  // (PB200_OPT_LINSOL can still change it)
     if (d->ism != 0) {
-        // InternalSensitivityMethod: 0 / 2 staggered (the path's corrector), 1 simultaneous -- small-model kernels
-        // only, run by the full-feature (steady-state) instantiation; 3 staggered1 is not built
+        // InternalSensitivityMethod: 0 / 2 staggered (the path's corrector), 1 simultaneous -- run by the
+        // full-feature (steady-state) instantiation of either kernel family; 3 staggered1 is not built
         if (d->ism != 1 && d->ism != 2) return fail(PB200_ERR_ARG, "ism: 0 or 2 staggered, 1 simultaneous");
         if (d->ism == 1) {
-            if (!ops->supports_newton || !ops->supports_steady)
-                return fail(PB200_ERR_ARG, "ism = 1: the simultaneous corrector is built for the small-model kernels only "
-                                           "(the large-model kernels use the staggered one, ism = 2)");
+            if (!ops->supports_steady)
+                return fail(PB200_ERR_ARG, "ism = 1: the simultaneous corrector lives in the model's full-feature kernel "
+                                           "instantiation, which this model was built without");
             if (!a.opt.errconS) return fail(PB200_ERR_ARG, "ism = 1 needs sensi_errcon = 1 (AMICI forces it)");
             a.opt.errconS |= 4;  // (SolverOptions::errconS bit 2)
             h->simultaneous = true;

@@ -54,7 +54,7 @@ struct B200ProblemTables {
     int newtonMaxSteps = 0;  // amici::Solver::setNewtonMaxSteps (steady states; 0 = by simulation only)
     bool newtonOnly = false; // steadyStateComputationMode newtonOnly: no simulation if Newton's method fails
     bool steadySensNewton = false; // steadyStateSensitivityMode newtonOnly with a simulation to steady state
-    int internalSensitivityMethod = 0; // 0 / 2 staggered, 1 simultaneous (small-model kernels only)
+    int internalSensitivityMethod = 0; // 0 / 2 staggered, 1 simultaneous
     int linearSolver = 0;    // large models: 0 automatic, 1 dense (LinearSolver::dense), 2 sparse (LinearSolver::KLU)
 
     /// The tables of a parPE parameter-estimation input file (doc/hdf5.md), assembled by the library's built-in

@@ -133,7 +133,7 @@ class ProblemTables:
     newton_maxsteps: int = 0   # steady states: Newton iterations before / after the simulation (AMICI default 0)
     newton_only: int = 0       # 1 = steadyStateComputationMode newtonOnly: no simulation if Newton's method fails
     steady_sens_newton: int = 0  # 1 = steadyStateSensitivityMode newtonOnly with a simulation to steady state
-    ism: int = 0               # 0 / 2 staggered corrector, 1 simultaneous (small-model kernels only)
+    ism: int = 0               # 0 / 2 staggered corrector, 1 simultaneous
     linsol: int = 0            # large models: 0 automatic, 1 dense, 2 sparse (initial value of PB200_OPT_LINSOL)
     hier: Optional[HierTables] = None
     # pre-equilibration (pb200_set_preequilibration): per simulation condition a flag, the constants of

@@ -187,7 +187,7 @@ def test_algorithm_selecting_options_are_honoured_or_refused(tmp_path):
         with pytest.raises(capi.B200LibraryError, match="linsol"):
             load(linsol=i32(v))
     # the sensitivity corrector variants and AMICI's defaults spelled out are accepted
-    # ... the simultaneous one is honoured (pb200_problem_desc::ism; pb200_create refuses it for a large model),
+    # ... the simultaneous one is honoured (pb200_problem_desc::ism: the full-feature instantiation of the kernels),
     # staggered1 runs the staggered corrector, an absent attribute means staggered (the north-star configuration)
     assert [load(ism=i32(ism)).ism for ism in (1, 2, 3)] == [1, 0, 0] and load().ism == 0
     load(lmm=i32(2), iter=i32(2), max_nonlin_iters=i32(3), max_conv_fails=i32(10), max_step_size=f64(0.0),

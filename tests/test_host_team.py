@@ -322,3 +322,31 @@ def test_fused_newton_iteration_of_the_sparse_path(stage):
         assert a["status"] == b["status"] == 0
         assert np.array_equal(a["stats"][:14], b["stats"][:14])
         assert a["llh"] == b["llh"] and np.array_equal(a["sllh"], b["sllh"])
+
+
+@pytest.mark.parametrize("model", ["net32", "net31"])
+@pytest.mark.parametrize("sparse", [False, True], ids=["dense", "sparse"])
+def test_simultaneous_corrector_team(oracle_available, model, sparse):
+    """pb200_problem_desc::ism = 1 for the large-model core (BdfTeam::nls_simultaneous, steady-state instantiation,
+    one-thread team): state and sensitivities in one Newton iteration with the joint norm and one error test
+    (cvodes_nls_sim.c) -- against the reference run with InternalSensitivityMethod::simultaneous, both linear
+    solvers; CVODES' counters of that corrector (no nniS / netfS), step counts within a few per cent."""
+    from oracle.binding import OracleProblem
+    from tests.host_harness.binding import simulate_team
+    from tests.util import assert_grad_close, assert_llh_close, condition_inputs
+    tab = synth.make_problem(model, 3, seed=0, scale="log10")
+    theta = synth.random_theta(tab, seed=1, width=0.3)
+    tab.ism = 1
+    ro = OracleProblem(tab, 2, 9).evaluate(theta, collect_stats=True)  # (the descriptor's ism wins)
+    stag = OracleProblem(synth.make_problem(model, 3, seed=0, scale="log10"), 2, 9).evaluate(theta, collect_stats=True)
+    assert ro["status"] == 0 and np.any(ro["stats"][:, 0] != stag["stats"][:, 0])
+    for c in range(tab.n_conditions):
+        p, plist, fac = condition_inputs(tab, theta, c)
+        lo, hi = tab.t_offsets[c], tab.t_offsets[c + 1]
+        r = simulate_team(model, p, tab.k[c], plist, tab.t[lo:hi], tab.y_of(c), tab.sigma_of(c), errconS=5, steady=True,
+                          sparse=sparse)
+        assert r["status"] == 0
+        assert_llh_close(r["llh"], ro["llh"][c])
+        assert_grad_close(r["sllh"] * fac, ro["sllh"][c][:len(plist)])
+        assert abs(r["numsteps"][-1] - ro["stats"][c, 0]) <= 0.1 * ro["stats"][c, 0] + 2
+        assert r["stats"][5] == 0 and r["stats"][8] == 0 and r["stats"][4] > 0

@@ -151,12 +151,27 @@ def test_simultaneous_corrector_matches_reference(oracle_available, model, C, kw
 
 
 @pytest.mark.gpu
-def test_large_model_kernel_refuses_the_simultaneous_corrector():
-    from parpe_b200.problem import B200SummedGradientFunction
-    tab = synth.make_problem("net32", 2, seed=0)
+@pytest.mark.parametrize("linsol", [1, 2], ids=["dense", "sparse"])
+def test_simultaneous_corrector_of_the_large_model_kernel(oracle_available, linsol):
+    """ism = 1 on a table-driven network model (one thread block per condition): BdfTeam::nls_simultaneous of the
+    steady-state instantiation, both linear solvers, against the reference run with the simultaneous corrector; CPU
+    parity of the same source with a one-thread team: tests/test_host_team.py::test_simultaneous_corrector_team."""
+    from tests.test_gpu_steadystate import _both
+    tab = synth.make_problem("net32", 6, seed=3, scale="log10")
     tab.ism = 1
-    with pytest.raises(capi.B200LibraryError, match="ism"):
-        B200SummedGradientFunction(tab)
+    tab.linsol = linsol
+    gpu, ora = _both(tab)
+    theta = synth.random_theta(tab, seed=1, width=0.3)
+    ro = ora.evaluate(theta, collect_stats=True)
+    st, fval, grad, _ = gpu.evaluate(theta)
+    res = gpu.condition_results()
+    assert ro["status"] == 0 and st == 0 and np.all(res["status"] == 0)
+    assert_llh_close(fval, ro["fval"])
+    assert_grad_close(grad, ro["grad"])
+    for c in range(tab.n_conditions):
+        assert_grad_close(res["sllh"][c], ro["sllh"][c], "per-condition sllh[%d]" % c)
+    assert np.all(res["stats"][:, 5] == 0) and np.all(res["stats"][:, 8] == 0)  # no nniS / netfS
+    assert abs(np.sum(res["stats"][:, 0]) - np.sum(ro["stats"][:, 0])) <= 0.05 * np.sum(ro["stats"][:, 0])
 
 
 @pytest.mark.gpu
