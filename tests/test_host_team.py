@@ -350,3 +350,21 @@ def test_simultaneous_corrector_team(oracle_available, model, sparse):
         assert_grad_close(r["sllh"] * fac, ro["sllh"][c][:len(plist)])
         assert abs(r["numsteps"][-1] - ro["stats"][c, 0]) <= 0.1 * ro["stats"][c, 0] + 2
         assert r["stats"][5] == 0 and r["stats"][8] == 0 and r["stats"][4] > 0
+
+
+def test_simultaneous_corrector_team_chen_shape(oracle_available):
+    """The same on the Chen shape (nx = 500, 50 sensitivity columns, sparse LU + dense Schur block) over the first two
+    output times: the reference's step count exactly."""
+    from oracle.binding import OracleProblem
+    from tests.host_harness.binding import simulate_team
+    from tests.util import assert_grad_close, assert_llh_close, condition_inputs
+    tab = synth.make_problem("chen", 1, seed=16, scale="log10", timepoints=[0.1, 0.3])
+    theta = synth.random_theta(tab, seed=5, width=0.3)
+    tab.ism = 1
+    ro = OracleProblem(tab, 2, 9).evaluate(theta, collect_stats=True)
+    p, plist, fac = condition_inputs(tab, theta, 0)
+    r = simulate_team("chen", p, tab.k[0], plist, tab.t, tab.y_of(0), tab.sigma_of(0), errconS=5, steady=True, sparse=True)
+    assert r["status"] == 0 and ro["status"] == 0
+    assert_llh_close(r["llh"], ro["llh"][0])
+    assert_grad_close(r["sllh"] * fac, ro["sllh"][0][:len(plist)])
+    assert abs(r["numsteps"][-1] - ro["stats"][0, 0]) <= 2
