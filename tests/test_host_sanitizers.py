@@ -37,7 +37,10 @@ TEAM_BODY = """
     args = ("net32", p, tab.k[0], list(range(spec.np)), tab.t, tab.y_of(0), tab.sigma_of(0))
     for kw in (dict(), dict(sparse=True), dict(sparse=True, deg_max=3, stage_doubles=150),
                dict(sparse=True, deg_max=100), dict(sparse=True, fuse_history=False, fuse_newton=False),
-               dict(panel_width=4)):
+               dict(panel_width=4),
+               # the simultaneous corrector of the steady-state instantiation (SolverOptions::errconS bit 2)
+               dict(errconS=5, steady=True), dict(errconS=5, steady=True, sparse=True),
+               dict(errconS=5, steady=True, sparse=True, deg_max=3, stage_doubles=150)):
         r = hh.simulate_team(*args, **kw)
         assert r["status"] == 0, (kw, r["status"])
     rng = np.random.default_rng(0)
